@@ -1,0 +1,219 @@
+/*
+ * voxactb.h -- C ABI of libvoxactb.so: the B200 (sm_100a) voxel-policy hot path.
+ *
+ * Drop-in boundary for the VoxAct-B / PerAct hot path:
+ *   - vxb_voxelize_f32      replaces VoxelGrid.coords_to_bounding_voxel_grid
+ *                           (reference peract/voxel/voxel_grid.py:148-198)
+ *   - vxb_qnet_forward_f32  replaces PerceiverVoxelLangEncoder.forward
+ *                           (reference peract/agents/peract_bc/perceiver_lang_io.py:345-485)
+ *   - vxb_qnet_prepare      one-off weight re-layout for the above (conv weights to
+ *                           tap-major, upsample-conv folding, bf16 hi/lo split)
+ *   - vxb_select_action_f32 replaces QFunction._argmax_3d / choose_highest_action and the
+ *                           act() tail (reference qattention_peract_bc_agent.py:57-80,709-724)
+ *
+ * Conventions: plain C types only; every pointer is a DEVICE pointer unless it says "host";
+ * the caller owns every buffer (outputs and workspaces, sized by the *_bytes queries);
+ * all work is enqueued asynchronously on the caller's stream (a cudaStream_t passed as void*);
+ * return value 0 = OK, negative = vxb_status; vxb_last_error() gives a thread-local message.
+ * There is no CPU fallback anywhere in this library.
+ */
+#ifndef VOXACTB_H_
+#define VOXACTB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VXB_VERSION 100
+
+typedef enum vxb_status {
+  VXB_OK = 0,
+  VXB_E_BADARG = -1,
+  VXB_E_UNSUPPORTED_SHAPE = -2,
+  VXB_E_WORKSPACE_TOO_SMALL = -3,
+  VXB_E_CUDA = -4,
+  VXB_E_NO_DEVICE = -5
+} vxb_status;
+
+int vxb_version(void);
+const char* vxb_last_error(void);
+/* 0 if a CUDA device of compute capability 10.x is current, else VXB_E_NO_DEVICE. */
+int vxb_check_device(void);
+
+/* ------------------------------------------------------------------ voxelizer (K1) */
+/* layout of the voxel grid output */
+#define VXB_LAYOUT_CHANNELS_LAST 0 /* [B,V,V,V,3+F+3+1]  (what voxel_grid.py:196-198 returns) */
+
+size_t vxb_voxelize_workspace_bytes(int B, int N, int V, int F);
+
+/*
+ * coords  [B,N,3] fp32 world-frame points, feats [B,N,F] fp32 (may be NULL when F==0),
+ * bounds  [Bb,6]  fp32 (min xyz, max xyz), Bb is 1 (shared) or B (per-sample VLM crop),
+ * out     [B,V,V,V,3+F+3+1] fp32,
+ * out_idx NULL or [B,N,3] int32: the clamped (V+2)-grid voxel index of every point
+ *         (voxel_grid.py:159-163), for the bit-exact parity test.
+ */
+int vxb_voxelize_f32(const float* coords, const float* feats, const float* bounds, int Bb,
+                     int B, int N, int F, int V, float* out, int layout, int32_t* out_idx,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ Q-network */
+typedef struct vxb_qnet_desc {
+  int32_t struct_bytes;     /* sizeof(vxb_qnet_desc), for ABI checking */
+  int32_t voxel_size;       /* V */
+  int32_t patch_size;       /* voxel_patch_size k (odd) */
+  int32_t patch_stride;     /* voxel_patch_stride s; V % s == 0 and conv output == V/s required */
+  int32_t initial_dim;      /* 10 */
+  int32_t im_channels;      /* 64 */
+  int32_t low_dim_size;     /* proprio width per arm (4 or 7) */
+  int32_t two_robots;       /* 0: PerceiverVoxelLangEncoder, 1: ...2RobotsEncoder (C = 3*im) */
+  int32_t lang_seq_len;     /* 77 */
+  int32_t lang_emb_dim;     /* 512 */
+  int32_t num_latents;      /* L */
+  int32_t latent_dim;       /* D */
+  int32_t depth;            /* self-attention layers */
+  int32_t iterations;       /* cross-attention iterations */
+  int32_t cross_heads, cross_dim_head, latent_heads, latent_dim_head;
+  int32_t final_dim;        /* 64 */
+  int32_t num_rotation_classes, num_grip_classes, num_collision_classes;
+  int32_t arm_pred_loss;    /* 1: dense2/arm_ff head present and evaluated */
+  int32_t no_language;      /* 1: language tokens zeroed (perceiver_lang_io.py:376-378) */
+  float   act_slope;        /* 0.02 for 'lrelu', 0 for 'relu' */
+  int32_t math_mode;        /* VXB_MATH_* */
+} vxb_qnet_desc;
+
+#define VXB_MATH_FP32_SIMT 0  /* fp32 FFMA everywhere (reference arithmetic, slow path for parity) */
+#define VXB_MATH_BF16X3    1  /* tcgen05 split-bf16 (hi*hi + hi*lo + lo*hi), fp32 accumulate in TMEM */
+
+/* Parameter slots: device pointers to contiguous fp32 tensors with the reference's shapes
+ * (perceiver_lang_io.py:137-334; state-dict names in the comments). */
+enum vxb_param_slot {
+  VXB_P_POS_ENCODING = 0,        /* pos_encoding [1,77+S^3,C] */
+  VXB_P_LATENTS,                 /* latents [L,D] */
+  VXB_P_INPRE_W, VXB_P_INPRE_B,  /* input_preprocess.conv3d [64,10,1,1,1],[64] */
+  VXB_P_PATCH_W, VXB_P_PATCH_B,  /* patchify.conv3d [64,64,k,k,k],[64] */
+  VXB_P_LANG_W, VXB_P_LANG_B,    /* lang_preprocess [C,512],[C] */
+  VXB_P_PROPRIO_W, VXB_P_PROPRIO_B,   /* proprio_preprocess.linear [64,low],[64] (right arm for 2 robots) */
+  VXB_P_PROPRIO2_W, VXB_P_PROPRIO2_B, /* 2 robots: proprio_preprocess_left_arm.linear, else NULL */
+  VXB_P_CROSS_NORM_W, VXB_P_CROSS_NORM_B,       /* cross_attend_blocks.0.norm */
+  VXB_P_CROSS_NORMCTX_W, VXB_P_CROSS_NORMCTX_B, /* cross_attend_blocks.0.norm_context */
+  VXB_P_CROSS_Q_W,               /* cross_attend_blocks.0.fn.to_q [ch*dh, D] */
+  VXB_P_CROSS_KV_W,              /* cross_attend_blocks.0.fn.to_kv [2*ch*dh, C] */
+  VXB_P_CROSS_OUT_W, VXB_P_CROSS_OUT_B,         /* cross_attend_blocks.0.fn.to_out */
+  VXB_P_CROSS_FF_NORM_W, VXB_P_CROSS_FF_NORM_B, /* cross_attend_blocks.1.norm */
+  VXB_P_CROSS_FF0_W, VXB_P_CROSS_FF0_B,         /* cross_attend_blocks.1.fn.net.0 [8D,D] */
+  VXB_P_CROSS_FF2_W, VXB_P_CROSS_FF2_B,         /* cross_attend_blocks.1.fn.net.2 [D,4D] */
+  VXB_P_DEC_NORM_W, VXB_P_DEC_NORM_B,           /* decoder_cross_attn.norm (C) */
+  VXB_P_DEC_NORMCTX_W, VXB_P_DEC_NORMCTX_B,     /* decoder_cross_attn.norm_context (D) */
+  VXB_P_DEC_Q_W, VXB_P_DEC_KV_W, VXB_P_DEC_OUT_W, VXB_P_DEC_OUT_B, /* decoder_cross_attn.fn.* */
+  VXB_P_UP0_W, VXB_P_UP0_B,      /* up0.conv_up.0.conv3d [64,C,k,k,k] */
+  VXB_P_UP1_W, VXB_P_UP1_B,      /* up0.conv_up.2.conv3d [64,64,k,k,k] */
+  VXB_P_FINAL_W, VXB_P_FINAL_B,  /* final.conv3d [64,128,3,3,3] */
+  VXB_P_TRANS_W, VXB_P_TRANS_B,  /* trans_decoder.conv3d [1,64,3,3,3] */
+  VXB_P_TRANS2_W, VXB_P_TRANS2_B,/* 2 robots: trans_decoder_left_arm.conv3d, else NULL */
+  VXB_P_DENSE0_W, VXB_P_DENSE0_B,/* dense0.linear [256,flat] */
+  VXB_P_DENSE1_W, VXB_P_DENSE1_B,/* dense1.linear [64,256] */
+  VXB_P_RGC_W, VXB_P_RGC_B,      /* rot_grip_collision_ff.linear [3R+G+Cc,64] */
+  VXB_P_DENSE2_W, VXB_P_DENSE2_B,/* arm head: dense2.linear [64,flat]; 2 robots: dense0_left_arm */
+  VXB_P_ARM_W, VXB_P_ARM_B,      /* arm head: arm_ff.linear [2,64];    2 robots: rot_grip_collision_ff_left_arm */
+  VXB_P_DENSE1L_W, VXB_P_DENSE1L_B, /* 2 robots: dense1_left_arm.linear, else NULL */
+  VXB_P_FIXED_COUNT,
+  /* followed by depth x VXB_P_LAYER_STRIDE per-layer slots */
+  VXB_PL_ATTN_NORM_W = 0, VXB_PL_ATTN_NORM_B,   /* layers.i.0.norm */
+  VXB_PL_Q_W, VXB_PL_KV_W, VXB_PL_OUT_W, VXB_PL_OUT_B, /* layers.i.0.fn.{to_q,to_kv,to_out} */
+  VXB_PL_FF_NORM_W, VXB_PL_FF_NORM_B,           /* layers.i.1.norm */
+  VXB_PL_FF0_W, VXB_PL_FF0_B, VXB_PL_FF2_W, VXB_PL_FF2_B, /* layers.i.1.fn.net.{0,2} */
+  VXB_P_LAYER_STRIDE
+};
+
+/* number of entries the params array must hold for this descriptor */
+int vxb_qnet_num_params(const vxb_qnet_desc* d);
+
+/* bytes of the "prepared weights" arena and of the per-call workspace for batch B */
+size_t vxb_qnet_prepared_bytes(const vxb_qnet_desc* d);
+size_t vxb_qnet_workspace_bytes(const vxb_qnet_desc* d, int B);
+
+/* Re-layout / fold / split the weights into `prepared` (device, 256-byte aligned). Must be re-run
+ * whenever a parameter changes. params: HOST array of device pointers (vxb_param_slot order). */
+int vxb_qnet_prepare(const vxb_qnet_desc* d, const void* const* params, void* prepared,
+                     size_t prepared_bytes, void* stream);
+
+/*
+ * grid        [B,V,V,V,initial_dim] fp32 channels-last (the voxelizer's native output; the
+ *             reference's [B,10,V,V,V] argument is the permuted view of this memory),
+ * proprio     [B,low_dim_size]; proprio2 = left arm for two_robots else NULL,
+ * lang_tokens [B,77,512],
+ * q_trans     [B,1,V,V,V]; q_trans2 = left arm grid for two_robots else NULL,
+ * rot_grip    [B,3R+G], collision [B,Cc] (NULL allowed when num_rotation_classes==0),
+ * rot_grip2/collision2: left-arm heads for two_robots else NULL,
+ * arm_out     [B,2] when arm_pred_loss else NULL.
+ */
+int vxb_qnet_forward_f32(const vxb_qnet_desc* d, const void* const* params, const void* prepared,
+                         const float* grid, const float* proprio, const float* proprio2,
+                         const float* lang_tokens, int B,
+                         float* q_trans, float* q_trans2, float* rot_grip, float* collision,
+                         float* rot_grip2, float* collision2, float* arm_out,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* number of this library's kernels enqueued by the most recent vxb_qnet_forward_f32 on the calling
+ * thread, and by one vxb_voxelize_f32 call (bench.py's gpu_launches) */
+int vxb_last_launch_count(void);
+int vxb_voxelize_launches(void);
+
+/* ------------------------------------------------------------------ action selection */
+/*
+ * softmax-free argmax of the translation grid (softmax is monotone: agent:709-718), per-axis-group
+ * argmax of rot/grip, collision argmax, and the metric attention coordinate
+ * bounds_min + res*idx + res/2 (agent:724).  q_trans [B,V^3]; rot_grip [B,3R+2]; collision [B,2];
+ * bounds [Bb,6].  Outputs: coords [B,3] int32, rot_grip_idx [B,4] int32, coll_idx [B] int32,
+ * attention_xyz [B,3] fp32.
+ */
+size_t vxb_select_action_workspace_bytes(int B, int V);
+int vxb_select_action_f32(const float* q_trans, const float* rot_grip, const float* collision,
+                          const float* bounds, int Bb, int B, int V, int R,
+                          int32_t* coords, int32_t* rot_grip_idx, int32_t* coll_idx,
+                          float* attention_xyz, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ building blocks (exported for the per-op parity tests) */
+/* C[M,N] = act(alpha * A[M,K] * W[N,K]^T + bias[N]) (+ residual[(m % res_rows),N]); row-major fp32. */
+int vxb_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
+                   const float* residual, int res_rows, float* C, int ldc,
+                   int M, int N, int K, float alpha, float act_slope /* <0: no activation */,
+                   int math_mode, void* stream);
+/* rows of length n: y = (x-mean)/sqrt(var+1e-5)*w+b */
+int vxb_layernorm_f32(const float* x, const float* w, const float* b, float* y, int rows, int n,
+                      void* stream);
+/* spatial soft-argmax (T=0.01) + max over P = Dd*Hh*Ww positions of channels-last x [B,P,C]:
+ * ss [B,3C] ordered (c, [x,y,z]) with the reference's meshgrid axis convention
+ * (network_utils.py:782-808), mx [B,C]. ws: vxb_spatial_softmax_workspace_bytes. */
+size_t vxb_spatial_softmax_workspace_bytes(int B, int P, int C);
+int vxb_spatial_softmax_f32(const float* x, int B, int Dd, int Hh, int Ww, int C, float* ss,
+                            int ss_stride, float* mx, int mx_stride, void* ws, size_t ws_bytes,
+                            void* stream);
+/* channels-last conv3d, replicate padding k/2, stride s, weight in PyTorch layout [Co,Ci,k,k,k];
+ * x [B,Di,Di,Di,Ci] -> y [B,Do,Do,Do,Co]; ws >= vxb_conv3d_workspace_bytes. */
+size_t vxb_conv3d_workspace_bytes(int Ci, int Co, int k);
+int vxb_conv3d_f32(const float* x, const float* w, const float* bias, float* y, int B, int Di,
+                   int Ci, int Co, int k, int s, float act_slope, int math_mode, void* ws,
+                   size_t ws_bytes, void* stream);
+/* fused conv(k,pad k/2,replicate) o trilinear-upsample(x s, align_corners=False): the second half of
+ * Conv3DUpsampleBlock (network_utils.py:245-251) evaluated as s^3 polyphase 3x3x3 convolutions on
+ * the low-resolution tensor.  x [B,S,S,S,Ci] -> y [B,S*s,S*s,S*s,Co]. */
+size_t vxb_upconv3d_workspace_bytes(int Ci, int Co, int k, int s);
+int vxb_upconv3d_f32(const float* x, const float* w, const float* bias, float* y, int B, int S,
+                     int Ci, int Co, int k, int s, float act_slope, int math_mode, void* ws,
+                     size_t ws_bytes, void* stream);
+/* softmax(scale * Q K^T) V per (batch, head); q [B,Nq,H*dh] (ldq), k/v rows [B,Nk,*] (ldkv). */
+size_t vxb_attention_workspace_bytes(int B, int H, int Nq, int Nk);
+int vxb_attention_f32(const float* q, int ldq, long long q_batch_stride, const float* k,
+                      const float* v, int ldkv, long long kv_batch_stride, float* out, int ldo,
+                      long long o_batch_stride, int B, int H, int Nq, int Nk, int dh, float scale,
+                      int math_mode, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXACTB_H_ */

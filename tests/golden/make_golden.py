@@ -1,0 +1,120 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own modules (authoring container only).
+
+    python tests/golden/make_golden.py
+
+Imports VoxelGrid / PerceiverVoxelLangEncoder from /root/reference (unmodified), feeds them the
+seeded synthetic inputs of voxactb_b200.synth and stores the outputs.  Inputs are regenerated from
+the seeds at test time (a checksum of every input is stored to detect RNG drift); small inputs are
+stored verbatim.  The GPU box has no /root/reference: these files are what travels.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import refimport  # noqa: E402
+from voxactb_b200 import synth  # noqa: E402
+
+QNET_CASES = {
+    # name: dict(V, k, s, L, depth, B, cameras, H, W, low_dim, arm, crop, seed)
+    'qnet_v20': dict(V=20, k=5, s=5, L=64, depth=2, B=2, cameras=2, H=32, W=32, low_dim=4, arm=False, crop=False, seed=11),
+    'qnet_v20_arm_crop': dict(V=20, k=5, s=5, L=96, depth=1, B=3, cameras=2, H=32, W=32, low_dim=7, arm=True, crop=True, seed=12),
+    'qnet_v32_config1': dict(V=32, k=5, s=4, L=2048, depth=6, B=1, cameras=1, H=128, W=128, low_dim=4, arm=False, crop=False, seed=1235),
+    'qnet_v100_b1': dict(V=100, k=5, s=5, L=2048, depth=6, B=1, cameras=4, H=128, W=128, low_dim=4, arm=False, crop=False, seed=1236),
+}
+VOXEL_CASES = {
+    'voxel_v20': dict(V=20, B=2, cameras=2, H=32, W=32, crop=False, seed=21),
+    'voxel_v32_crop': dict(V=32, B=3, cameras=1, H=48, W=40, crop=True, seed=22),
+    'voxel_v100': dict(V=100, B=1, cameras=4, H=128, W=128, crop=False, seed=23),
+}
+
+
+def checksum(t):
+    return float(t.double().abs().sum())
+
+
+def ref_indices(vg, coords, bounds):
+    """voxel_grid.py:152-163 evaluated with the reference module's own buffers."""
+    bb_mins = bounds[..., 0:3]
+    bb_maxs = bounds[..., 3:6]
+    res = (bb_maxs - bb_mins) / (vg._dims_orig.float() + 1e-12)
+    denom = res + 1e-12
+    shifted = bb_mins - res
+    fl = torch.floor((coords - shifted.unsqueeze(1)) / denom.unsqueeze(1)).int()
+    return torch.max(torch.min(fl, vg._dims_m_one), vg._dims_m_one_zeros)
+
+
+def encoder_kwargs(c):
+    return dict(depth=c['depth'], iterations=1, voxel_size=c['V'], initial_dim=10, low_dim_size=c['low_dim'],
+                layer=0, num_rotation_classes=72, num_grip_classes=2, num_collision_classes=2, input_axis=3,
+                num_latents=c['L'], latent_dim=512, cross_heads=1, latent_heads=8, cross_dim_head=64,
+                latent_dim_head=64, weight_tie_layers=False, activation='lrelu', pos_encoding_with_lang=True,
+                input_dropout=0.1, attn_dropout=0.1, decoder_dropout=0.0, lang_fusion_type='seq',
+                voxel_patch_size=c['k'], voxel_patch_stride=c['s'], no_skip_connection=False,
+                no_perceiver=False, no_language=False, final_dim=64, arm_pred_loss=c['arm'])
+
+
+def main():
+    RefVG, RefEnc = refimport.load()
+    torch.set_num_threads(os.cpu_count())
+    for name, c in VOXEL_CASES.items():
+        obs = synth.make_observation(c['seed'], c['B'], c['cameras'], c['H'], c['W'], per_sample_crop=c['crop'])
+        coords, feats = synth.flatten_cameras(obs)
+        vg = RefVG(synth.SCENE_BOUNDS, c['V'], 'cpu', c['B'], 3, coords.shape[1])
+        grid = vg.coords_to_bounding_voxel_grid(coords, feats, obs['bounds'])
+        idx = ref_indices(vg, coords, obs['bounds'])
+        out = dict(cfg=np.array([c['V'], c['B'], c['cameras'], c['H'], c['W'], int(c['crop']), c['seed']]),
+                   in_checksum=np.array([checksum(coords), checksum(feats), checksum(obs['bounds'])]),
+                   idx_checksum=np.array([int(idx.long().sum()), int((idx.long() * torch.arange(1, 4)).sum())]),
+                   occupied=np.array([int((grid[..., -1] > 0).sum())]),
+                   grid_sum=np.array([float(grid.double().sum()), float(grid.double().abs().sum())]))
+        if c['V'] <= 32:
+            out['grid'] = grid.numpy()
+            out['idx'] = idx.numpy().astype(np.int16)
+        else:
+            nz = torch.nonzero(grid[..., -1].reshape(-1) > 0).reshape(-1)
+            sel = nz[:: max(1, nz.numel() // 4096)]
+            out['sample_pos'] = sel.numpy().astype(np.int64)
+            out['sample_val'] = grid.reshape(-1, grid.shape[-1])[sel].numpy()
+            out['idx_head'] = idx[:, :4096].numpy().astype(np.int16)
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+        print(name, 'occupied', out['occupied'])
+    for name, c in QNET_CASES.items():
+        obs = synth.make_observation(c['seed'], c['B'], c['cameras'], c['H'], c['W'], low_dim=c['low_dim'],
+                                     per_sample_crop=c['crop'])
+        coords, feats = synth.flatten_cameras(obs)
+        vg = RefVG(synth.SCENE_BOUNDS, c['V'], 'cpu', c['B'], 3, coords.shape[1])
+        grid = vg.coords_to_bounding_voxel_grid(coords, feats, obs['bounds']).permute(0, 4, 1, 2, 3)
+        net = RefEnc(**encoder_kwargs(c)).eval()
+        sd = synth.random_state_dict(net, c['seed'] + 1000)
+        missing = net.load_state_dict(sd, strict=False)
+        assert not missing.unexpected_keys, missing
+        with torch.no_grad():
+            outs = net(grid, obs['proprio'], obs['lang_goal_emb'], obs['lang_token_embs'], None, obs['bounds'], None)
+        trans = outs[0]
+        out = dict(in_checksum=np.array([checksum(coords), checksum(feats), checksum(obs['proprio']),
+                                         checksum(obs['lang_token_embs']), checksum(obs['bounds'])]),
+                   sd_checksum=np.array([sum(checksum(v) for v in sd.values())]),
+                   keys=np.array(sorted(net.state_dict().keys())),
+                   rot_grip=outs[1].numpy(), collision=outs[2].numpy(),
+                   trans_argmax=trans.reshape(c['B'], -1).argmax(-1).numpy(),
+                   trans_stats=np.array([float(trans.double().sum()), float(trans.double().abs().sum()),
+                                         float(trans.max()), float(trans.min())]))
+        if c['arm']:
+            out['arm'] = outs[3].numpy()
+        if c['V'] <= 32:
+            out['trans'] = trans.numpy()
+        else:
+            out['trans_strided'] = trans.reshape(c['B'], -1)[:, ::97].numpy()
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+        print(name, 'trans range', out['trans_stats'][2:], 'rot_grip absmax', float(np.abs(out['rot_grip']).max()))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,97 @@
+"""The CPU oracle against (a) the reference's own modules, imported live when /root/reference is
+mounted, and (b) the committed golden fixtures generated from them (always)."""
+import numpy as np
+import pytest
+import torch
+
+import refimport
+import util
+from oracle import qnet_oracle, voxel_oracle
+from voxactb_b200 import synth
+
+import make_golden
+
+needs_ref = pytest.mark.skipif(not refimport.available(), reason='/root/reference not mounted')
+
+
+@pytest.mark.parametrize('name', ['voxel_v20', 'voxel_v32_crop', 'voxel_v100'])
+def test_voxel_oracle_matches_golden(name):
+    c = make_golden.VOXEL_CASES[name]
+    g = util.golden(name)
+    obs = synth.make_observation(c['seed'], c['B'], c['cameras'], c['H'], c['W'], per_sample_crop=c['crop'])
+    coords, feats = synth.flatten_cameras(obs)
+    assert np.allclose([util.checksum(coords), util.checksum(feats), util.checksum(obs['bounds'])],
+                       g['in_checksum'], rtol=1e-12), 'synthetic input drifted from the golden run'
+    idx = voxel_oracle.voxel_indices(coords.numpy(), obs['bounds'].numpy(), c['V'])
+    grid = voxel_oracle.voxelize(coords.numpy(), feats.numpy(), obs['bounds'].numpy(), c['V'])
+    assert int(idx.astype(np.int64).sum()) == int(g['idx_checksum'][0])
+    assert int((grid[..., -1] > 0).sum()) == int(g['occupied'][0])
+    if 'grid' in g.files:
+        assert np.array_equal(idx, g['idx'].astype(np.int32))       # bit-exact indices
+        assert np.array_equal(grid, g['grid'])                       # same sequential fp32 sums
+    else:
+        assert np.array_equal(idx[:, :4096], g['idx_head'].astype(np.int32))
+        flat = grid.reshape(-1, grid.shape[-1])
+        assert np.array_equal(flat[g['sample_pos']], g['sample_val'])
+
+
+@pytest.mark.parametrize('name', ['qnet_v20', 'qnet_v20_arm_crop', 'qnet_v32_config1'])
+def test_qnet_oracle_matches_golden(name):
+    c = make_golden.QNET_CASES[name]
+    g = util.golden(name)
+    obs, enc, sd = util.make_case(c)
+    coords, feats = synth.flatten_cameras(obs)
+    assert np.allclose([util.checksum(coords), util.checksum(feats), util.checksum(obs['proprio']),
+                        util.checksum(obs['lang_token_embs']), util.checksum(obs['bounds'])],
+                       g['in_checksum'], rtol=1e-12)
+    assert np.allclose(sum(util.checksum(v) for v in sd.values()), g['sd_checksum'], rtol=1e-12)
+    out = qnet_oracle.qfunction_forward(sd, util.oracle_cfg(c), voxel_oracle.voxelize, obs['rgb'], obs['pcd'],
+                                        obs['proprio'], obs['lang_token_embs'], obs['bounds'], c['V'])
+    assert util.rel_err(out['trans'], g['trans']) < 1e-5
+    assert util.rel_err(out['rot_grip'], g['rot_grip']) < 1e-5
+    assert util.rel_err(out['collision'], g['collision']) < 1e-5
+    if c['arm']:
+        assert util.rel_err(out['arm'], g['arm']) < 1e-5
+    assert np.array_equal(out['trans'].reshape(c['B'], -1).argmax(-1).numpy(), g['trans_argmax'])
+
+
+def test_state_dict_keys_match_reference():
+    """Checkpoint compatibility: our module exposes exactly the reference's state_dict keys."""
+    for name in ('qnet_v20', 'qnet_v20_arm_crop'):
+        c = make_golden.QNET_CASES[name]
+        _, enc, _ = util.make_case(c)
+        assert sorted(enc.state_dict().keys()) == list(util.golden(name)['keys'])
+
+
+@needs_ref
+def test_voxel_oracle_vs_live_reference():
+    RefVG, _ = refimport.load()
+    for seed, V, crop in ((5, 16, False), (6, 24, True)):
+        obs = synth.make_observation(seed, 2, 2, 24, 24, per_sample_crop=crop)
+        coords, feats = synth.flatten_cameras(obs)
+        ref = RefVG(synth.SCENE_BOUNDS, V, 'cpu', 2, 3, coords.shape[1]).coords_to_bounding_voxel_grid(
+            coords, feats, obs['bounds'])
+        mine = voxel_oracle.voxelize(coords.numpy(), feats.numpy(), obs['bounds'].numpy(), V)
+        assert np.array_equal(ref.numpy(), mine)
+
+
+@needs_ref
+def test_qnet_oracle_and_signature_vs_live_reference():
+    import inspect
+    from voxactb_b200 import PerceiverVoxelLangEncoder, VoxelGrid
+    RefVG, RefEnc = refimport.load()
+    assert inspect.signature(RefEnc.__init__) == inspect.signature(PerceiverVoxelLangEncoder.__init__)
+    assert list(inspect.signature(RefEnc.forward).parameters) == \
+        list(inspect.signature(PerceiverVoxelLangEncoder.forward).parameters)
+    assert list(inspect.signature(RefVG.__init__).parameters) == list(inspect.signature(VoxelGrid.__init__).parameters)
+    c = dict(V=16, k=5, s=4, L=48, depth=1, B=2, cameras=1, H=16, W=16, low_dim=7, arm=True, crop=False, seed=77)
+    obs, enc, sd = util.make_case(c)
+    net = RefEnc(**make_golden.encoder_kwargs(c)).eval()
+    net.load_state_dict(sd, strict=False)
+    coords, feats = synth.flatten_cameras(obs)
+    grid = torch.from_numpy(voxel_oracle.voxelize(coords.numpy(), feats.numpy(), obs['bounds'].numpy(), 16)).permute(0, 4, 1, 2, 3)
+    with torch.no_grad():
+        ref = net(grid, obs['proprio'], None, obs['lang_token_embs'], None, obs['bounds'], None)
+    out = qnet_oracle.qnet_forward(sd, util.oracle_cfg(c), grid, obs['proprio'], obs['lang_token_embs'])
+    for a, b in zip(ref, (out['trans'], out['rot_grip'], out['collision'], out['arm'])):
+        assert util.rel_err(b, a) < 1e-6

@@ -1,0 +1,102 @@
+"""Full hot path on the GPU (QFunction -> VoxelGrid -> PerceiverVoxelLangEncoder through the C ABI)
+against the CPU oracle and the reference goldens.  Gate: Q-values within 1e-3 relative (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+import util
+from oracle import qnet_oracle, voxel_oracle
+from voxactb_b200 import QFunction, VoxelGrid, _lib, synth
+
+import make_golden
+
+pytestmark = pytest.mark.gpu
+
+MODES = [_lib.MATH_FP32_SIMT]
+
+
+def run_qfunction(c, obs, enc, mode):
+    enc.math_mode = mode
+    dev = torch.device('cuda')
+    vg = VoxelGrid(synth.SCENE_BOUNDS, c['V'], dev, c['B'], 3, c['cameras'] * c['H'] * c['W'])
+    q = QFunction(enc, vg, 0.15, 5, dev, False, c['arm']).to(dev).eval()
+    rgb = [t.cuda() for t in obs['rgb']]
+    pcd = [t.cuda() for t in obs['pcd']]
+    rgb_pcd = [[r, p] for r, p in zip(rgb, pcd)]
+    out = q(rgb_pcd, obs['proprio'].cuda(), pcd, obs['lang_goal_emb'].cuda(), obs['lang_token_embs'].cuda(),
+            obs['bounds'].cuda(), None, None)
+    torch.cuda.synchronize()
+    return q, out
+
+
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('name', ['qnet_v20', 'qnet_v20_arm_crop', 'qnet_v32_config1'])
+def test_forward_matches_oracle_and_golden(cuda_lib, mode, name):
+    c = make_golden.QNET_CASES[name]
+    g = util.golden(name)
+    obs, enc, sd = util.make_case(c)
+    q, out = run_qfunction(c, obs, enc, mode)
+    trans, rot_grip, coll, grid = out
+    assert trans.shape == (c['B'], 1, c['V'], c['V'], c['V']) and grid.shape == (c['B'], 10, c['V'], c['V'], c['V'])
+    ref = qnet_oracle.qfunction_forward(sd, util.oracle_cfg(c), voxel_oracle.voxelize, obs['rgb'], obs['pcd'],
+                                        obs['proprio'], obs['lang_token_embs'], obs['bounds'], c['V'])
+    for ours, key in ((trans, 'trans'), (rot_grip, 'rot_grip'), (coll, 'collision')):
+        assert util.rel_err(ours, ref[key]) < util.Q_REL_TOL, key
+        assert util.rel_err(ours, g[key]) < util.Q_REL_TOL, key + ' (golden)'
+    # action selection (choose_highest_action / _argmax_3d) against the oracle helpers
+    coords, rg, ic = q.choose_highest_action(trans, rot_grip, coll)
+    rc, rrg, ric = qnet_oracle.choose_highest_action(trans.cpu(), rot_grip.cpu(), coll.cpu())
+    assert torch.equal(coords.cpu(), rc) and torch.equal(rg.cpu(), rrg) and torch.equal(ic.cpu(), ric)
+    _, _, _, xyz = q.select_action(trans, rot_grip, coll, obs['bounds'].cuda())
+    ref_xyz = qnet_oracle.attention_coordinate(rc, obs['bounds'].expand(c['B'], 6), c['V'])
+    torch.testing.assert_close(xyz.cpu(), ref_xyz, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize('mode', MODES)
+def test_forward_v100_against_golden(cuda_lib, mode):
+    """BASELINE.json geometry (100^3, 4 cameras, 2048 latents, depth 6), B=1, vs the reference golden."""
+    name = 'qnet_v100_b1'
+    c = make_golden.QNET_CASES[name]
+    g = util.golden(name)
+    obs, enc, sd = util.make_case(c)
+    _, (trans, rot_grip, coll, grid) = run_qfunction(c, obs, enc, mode)
+    assert util.rel_err(rot_grip, g['rot_grip']) < util.Q_REL_TOL
+    assert util.rel_err(coll, g['collision']) < util.Q_REL_TOL
+    t = trans.reshape(1, -1).cpu()
+    scale = float(np.abs(g['trans_stats'][2:]).max())
+    assert float((t[:, ::97] - torch.from_numpy(g['trans_strided'])).abs().max()) / scale < util.Q_REL_TOL
+    assert abs(float(t.double().sum()) - g['trans_stats'][0]) / g['trans_stats'][1] < 1e-4
+    assert int(t.argmax()) == int(g['trans_argmax'][0])
+
+
+@pytest.mark.parametrize('mode', MODES)
+def test_forward_batch_invariance_full_size(cuda_lib, mode):
+    """B=4 at 100^3: every sample's result equals the same sample run alone (batch sharding is exact)."""
+    c = dict(make_golden.QNET_CASES['qnet_v100_b1'], B=4, seed=4321)
+    obs, enc, sd = util.make_case(c)
+    _, (trans, rot_grip, coll, _) = run_qfunction(c, obs, enc, mode)
+    one = dict(obs)
+    for k in ('proprio', 'lang_goal_emb', 'lang_token_embs'):
+        one[k] = obs[k][2:3].contiguous()
+    one['rgb'] = [t[2:3].contiguous() for t in obs['rgb']]
+    one['pcd'] = [t[2:3].contiguous() for t in obs['pcd']]
+    c1 = dict(c, B=1)
+    _, (t1, r1, c1o, _) = run_qfunction(c1, one, enc, mode)
+    assert util.rel_err(trans[2:3], t1) < 1e-4
+    assert util.rel_err(rot_grip[2:3], r1) < 1e-4
+    assert util.rel_err(coll[2:3], c1o) < 1e-4
+
+
+def test_checkpoint_roundtrip_and_deepcopy(cuda_lib, tmp_path):
+    import copy
+    c = make_golden.QNET_CASES['qnet_v20']
+    obs, enc, sd = util.make_case(c)
+    enc2 = copy.deepcopy(enc)
+    q, out = run_qfunction(c, obs, enc, _lib.MATH_FP32_SIMT)
+    path = tmp_path / 'QAttentionAgent_layer0.pt'
+    torch.save(q.state_dict(), path)
+    loaded = torch.load(path)
+    assert all(k.startswith('_qnet.') for k in loaded)
+    q2, out2 = run_qfunction(c, obs, enc2, _lib.MATH_FP32_SIMT)
+    q2.load_state_dict(loaded)
+    assert torch.equal(out[0], out2[0])

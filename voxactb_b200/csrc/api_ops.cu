@@ -1,0 +1,229 @@
+// C-ABI wrappers of the individual building blocks (per-op parity tests) and action selection.
+#include "common.cuh"
+#include "ops.cuh"
+#include "simt_gemm.cuh"
+#include "dispatch.cuh"
+
+using namespace vxb;
+
+namespace vxb {
+
+// ---------------------------------------------------------------- action selection
+// argmax over V^3 per sample: (value, index) pairs, ties -> lowest index (torch.argmax on CPU
+// returns the first maximal element).  Pass 1: per-chunk, pass 2: merge + heads.
+__global__ void __launch_bounds__(256)
+argmax_partial_kernel(const float* __restrict__ q, size_t n, int chunks, float* __restrict__ pv,
+                      int* __restrict__ pi) {
+  const int b = blockIdx.y, ck = blockIdx.x;
+  const size_t per = (n + chunks - 1) / chunks;
+  const size_t beg = ck * per, end = min(n, beg + per);
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (size_t i = beg + threadIdx.x; i < end; i += 256) {
+    const float v = q[(size_t)b * n + i];
+    if (v > best || (v == best && (int)i < bi)) { best = v; bi = (int)i; }
+  }
+  __shared__ float sv[256];
+  __shared__ int si[256];
+  sv[threadIdx.x] = best; si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const float v2 = sv[threadIdx.x + o];
+      const int i2 = si[threadIdx.x + o];
+      if (v2 > sv[threadIdx.x] || (v2 == sv[threadIdx.x] && i2 < si[threadIdx.x])) {
+        sv[threadIdx.x] = v2; si[threadIdx.x] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { pv[b * chunks + ck] = sv[0]; pi[b * chunks + ck] = si[0]; }
+}
+
+__device__ __forceinline__ int small_argmax(const float* v, int n) {
+  int bi = 0;
+  float best = v[0];
+  for (int i = 1; i < n; ++i)
+    if (v[i] > best) { best = v[i]; bi = i; }
+  return bi;
+}
+
+__global__ void select_action_final_kernel(const float* __restrict__ pv, const int* __restrict__ pi,
+                                           int chunks, const float* __restrict__ rot_grip,
+                                           const float* __restrict__ collision,
+                                           const float* __restrict__ bounds, int Bb, int B, int V,
+                                           int R, int32_t* __restrict__ coords,
+                                           int32_t* __restrict__ rg_idx, int32_t* __restrict__ coll_idx,
+                                           float* __restrict__ att_xyz) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int k = 0; k < chunks; ++k) {
+    const float v = pv[b * chunks + k];
+    const int i = pi[b * chunks + k];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+  // _argmax_3d (qattention_peract_bc_agent.py:57-63): ((idx // h) // d, (idx // h) % w, idx % w)
+  const int c0 = (bi / V) / V, c1 = (bi / V) % V, c2 = bi % V;
+  coords[b * 3 + 0] = c0; coords[b * 3 + 1] = c1; coords[b * 3 + 2] = c2;
+  if (rot_grip && rg_idx) {
+    const float* rg = rot_grip + (size_t)b * (3 * R + 2);
+    rg_idx[b * 4 + 0] = small_argmax(rg, R);
+    rg_idx[b * 4 + 1] = small_argmax(rg + R, R);
+    rg_idx[b * 4 + 2] = small_argmax(rg + 2 * R, R);
+    rg_idx[b * 4 + 3] = small_argmax(rg + 3 * R, 2);
+  }
+  if (collision && coll_idx) coll_idx[b] = small_argmax(collision + (size_t)b * 2, 2);
+  if (att_xyz && bounds) {
+    const float* bd = bounds + (Bb == 1 ? 0 : b) * 6;
+    const int cc[3] = {c0, c1, c2};
+    for (int a = 0; a < 3; ++a) {
+      // res = (bounds[:,3:] - bounds[:,:3]) / voxel_size ; coord = bounds[:, :3] + res*idx + res/2  (agent:701,724)
+      const float res = __fdiv_rn(__fsub_rn(bd[3 + a], bd[a]), (float)V);
+      att_xyz[b * 3 + a] = __fadd_rn(__fadd_rn(bd[a], __fmul_rn(res, (float)cc[a])), __fdiv_rn(res, 2.f));
+    }
+  }
+}
+
+}  // namespace vxb
+
+static const int kArgmaxChunks = 64;
+
+extern "C" size_t vxb_select_action_workspace_bytes(int B, int V) {
+  (void)V;
+  return align_up((size_t)B * kArgmaxChunks * 4, 256) * 2;
+}
+
+extern "C" int vxb_select_action_f32(const float* q_trans, const float* rot_grip,
+                                     const float* collision, const float* bounds, int Bb, int B,
+                                     int V, int R, int32_t* coords, int32_t* rot_grip_idx,
+                                     int32_t* coll_idx, float* attention_xyz, void* ws,
+                                     size_t ws_bytes, void* stream) {
+  VXB_CHECK_ARG(q_trans && coords && ws, "select_action: null pointer");
+  VXB_CHECK_ARG(B > 0 && V > 0, "select_action: bad sizes");
+  VXB_CHECK_ARG(!bounds || Bb == 1 || Bb == B, "select_action: bounds batch must be 1 or B");
+  if (ws_bytes < vxb_select_action_workspace_bytes(B, V)) {
+    set_error("select_action: workspace too small");
+    return VXB_E_WORKSPACE_TOO_SMALL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* pv = (float*)ws;
+  int* pi = (int*)((char*)ws + align_up((size_t)B * kArgmaxChunks * 4, 256));
+  const size_t n = (size_t)V * V * V;
+  argmax_partial_kernel<<<dim3(kArgmaxChunks, B), 256, 0, st>>>(q_trans, n, kArgmaxChunks, pv, pi);
+  VXB_LAUNCH_CHECK();
+  select_action_final_kernel<<<cdiv(B, 64), 64, 0, st>>>(pv, pi, kArgmaxChunks, rot_grip, collision, bounds,
+                                                         Bb, B, V, R, coords, rot_grip_idx, coll_idx,
+                                                         attention_xyz);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// ---------------------------------------------------------------- building blocks
+extern "C" int vxb_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
+                              const float* residual, int res_rows, float* C, int ldc, int M, int N,
+                              int K, float alpha, float act_slope, int math_mode, void* stream) {
+  VXB_CHECK_ARG(A && W && C && M > 0 && N > 0 && K >= 0, "linear: bad arguments");
+  return linear(A, lda, W, ldw, bias, residual, res_rows, ldc, C, ldc, M, N, K, alpha, act_slope,
+                math_mode, (cudaStream_t)stream);
+}
+
+extern "C" int vxb_layernorm_f32(const float* x, const float* w, const float* b, float* y, int rows,
+                                 int n, void* stream) {
+  VXB_CHECK_ARG(x && w && b && y && rows > 0 && n > 0 && n % 4 == 0, "layernorm: bad arguments");
+  layernorm_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, w, b, y, rows, n, rows, 0);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+static int ss_chunks_api(size_t P) { return (int)std::min<size_t>(1024, std::max<size_t>(1, (P + 1023) / 1024)); }
+
+extern "C" size_t vxb_spatial_softmax_workspace_bytes(int B, int P, int C) {
+  (void)C;
+  return (size_t)B * ss_chunks_api((size_t)P) * 6 * 256 * sizeof(float);
+}
+
+extern "C" int vxb_spatial_softmax_f32(const float* x, int B, int Dd, int Hh, int Ww, int C, float* ss,
+                                       int ss_stride, float* mx, int mx_stride, void* ws,
+                                       size_t ws_bytes, void* stream) {
+  VXB_CHECK_ARG(x && ss && ws && B > 0 && C > 0 && C <= 256, "spatial_softmax: bad arguments");
+  const size_t P = (size_t)Dd * Hh * Ww;
+  if (ws_bytes < vxb_spatial_softmax_workspace_bytes(B, (int)P, C)) {
+    set_error("spatial_softmax: workspace too small");
+    return VXB_E_WORKSPACE_TOO_SMALL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = ss_chunks_api(P);
+  const int chunk = (int)((P + chunks - 1) / chunks);
+  spatial_softmax_partial_kernel<<<dim3(chunks, B), 256, 0, st>>>(x, (int)P, C, Dd, Hh, Ww, chunk, (float*)ws);
+  VXB_LAUNCH_CHECK();
+  spatial_softmax_merge_kernel<<<B, 256, 0, st>>>((float*)ws, chunks, C, ss, ss_stride, mx, mx_stride);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+extern "C" size_t vxb_conv3d_workspace_bytes(int Ci, int Co, int k) {
+  return align_up((size_t)Ci * Co * k * k * k * sizeof(float), 256);
+}
+
+extern "C" int vxb_conv3d_f32(const float* x, const float* w, const float* bias, float* y, int B,
+                              int Di, int Ci, int Co, int k, int s, float act_slope, int math_mode,
+                              void* ws, size_t ws_bytes, void* stream) {
+  VXB_CHECK_ARG(x && w && y && ws && B > 0 && Di > 0 && (k & 1) && s > 0, "conv3d: bad arguments");
+  if (ws_bytes < vxb_conv3d_workspace_bytes(Ci, Co, k)) {
+    set_error("conv3d: workspace too small");
+    return VXB_E_WORKSPACE_TOO_SMALL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int k3 = k * k * k;
+  conv_weight_to_tapmajor_kernel<<<cdiv((size_t)Co * Ci * k3, 256), 256, 0, st>>>(w, (float*)ws, Co, Ci, k3);
+  VXB_LAUNCH_CHECK();
+  const int Do = (Di + 2 * (k / 2) - k) / s + 1;
+  return conv3d(x, nullptr, Ci, 0, (const float*)ws, bias, y, B, Di, Do, Co, k, s, act_slope, math_mode, st);
+}
+
+extern "C" size_t vxb_upconv3d_workspace_bytes(int Ci, int Co, int k, int s) {
+  (void)k;
+  return align_up((size_t)s * s * s * Co * 27 * Ci * sizeof(float), 256);
+}
+
+extern "C" int vxb_upconv3d_f32(const float* x, const float* w, const float* bias, float* y, int B,
+                                int S, int Ci, int Co, int k, int s, float act_slope, int math_mode,
+                                void* ws, size_t ws_bytes, void* stream) {
+  VXB_CHECK_ARG(x && w && y && ws && B > 0 && S > 0 && (k & 1) && s > 0, "upconv3d: bad arguments");
+  if (2 * (k / 2) > s + 1) {
+    set_error("upconv3d: folding needs k/2 <= (s+1)/2 (k=%d, s=%d)", k, s);
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  if (ws_bytes < vxb_upconv3d_workspace_bytes(Ci, Co, k, s)) {
+    set_error("upconv3d: workspace too small");
+    return VXB_E_WORKSPACE_TOO_SMALL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)s * s * s * Co * 27 * Ci;
+  fold_upconv_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, (float*)ws, Co, Ci, k, s);
+  VXB_LAUNCH_CHECK();
+  return upconv3d_folded(x, (const float*)ws, bias, y, B, S, Ci, Co, s, act_slope, math_mode, st);
+}
+
+extern "C" size_t vxb_attention_workspace_bytes(int B, int H, int Nq, int Nk) {
+  const size_t Nkp = ((size_t)Nk + 3) / 4 * 4;
+  return align_up((size_t)B * H * Nq * Nkp * sizeof(float), 256);
+}
+
+extern "C" int vxb_attention_f32(const float* q, int ldq, long long q_batch_stride, const float* k,
+                                 const float* v, int ldkv, long long kv_batch_stride, float* out,
+                                 int ldo, long long o_batch_stride, int B, int H, int Nq, int Nk,
+                                 int dh, float scale, int math_mode, void* ws, size_t ws_bytes,
+                                 void* stream) {
+  VXB_CHECK_ARG(q && k && v && out && ws && B > 0 && H > 0 && Nq > 0 && Nk > 0 && dh > 0,
+                "attention: bad arguments");
+  if (ws_bytes < vxb_attention_workspace_bytes(B, H, Nq, Nk)) {
+    set_error("attention: workspace too small");
+    return VXB_E_WORKSPACE_TOO_SMALL;
+  }
+  return attention_materialized(q, ldq, q_batch_stride, k, v, ldkv, kv_batch_stride, out, ldo,
+                                o_batch_stride, B, H, Nq, Nk, dh, scale, (float*)ws, math_mode,
+                                (cudaStream_t)stream);
+}

@@ -1,0 +1,486 @@
+// Host-side orchestration of the PerceiverActor Q-network forward behind the C ABI.
+// Mirrors PerceiverVoxelLangEncoder.forward (reference peract/agents/peract_bc/perceiver_lang_io.py:345-485)
+// step by step; every activation is channels-last.
+#include "common.cuh"
+#include "ops.cuh"
+#include "simt_gemm.cuh"
+#include "dispatch.cuh"
+
+namespace vxb {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct Dims {
+  int V, k, s, S, T, nl, n, im, C, L, D, depth, low, R, G, Cc, flat, fin;
+  int ch, cdh, lh, ldh;
+  size_t V3;
+};
+
+static int make_dims(const vxb_qnet_desc* d, Dims& m) {
+  VXB_CHECK_ARG(d != nullptr, "qnet: null descriptor");
+  VXB_CHECK_ARG(d->struct_bytes == (int)sizeof(vxb_qnet_desc),
+                "qnet: descriptor size mismatch (%d vs %zu) -- header/library version skew",
+                d->struct_bytes, sizeof(vxb_qnet_desc));
+  m.V = d->voxel_size; m.k = d->patch_size; m.s = d->patch_stride;
+  VXB_CHECK_ARG(m.V > 0 && m.k > 0 && m.s > 0, "qnet: bad voxel/patch sizes");
+  const int pad = m.k / 2;
+  const int conv_out = (m.V + 2 * pad - m.k) / m.s + 1;
+  m.S = m.V / m.s;
+  if ((m.k & 1) == 0 || conv_out != m.S || m.S * m.s != m.V) {
+    // the reference fails here too: the patchified grid would not match pos_encoding
+    // (perceiver_lang_io.py:206-209 vs :422)
+    set_error("qnet: voxel_size=%d patch=%d stride=%d gives %d^3 patches but the positional encoding "
+              "has (V//stride)^3=%d^3", m.V, m.k, m.s, conv_out, m.S);
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  if (2 * pad > m.s + 1) {
+    set_error("qnet: upsample-conv folding needs patch_size/2 <= (stride+1)/2 (k=%d, s=%d)", m.k, m.s);
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  m.T = m.S * m.S * m.S;
+  m.nl = d->lang_seq_len;
+  m.n = m.nl + m.T;
+  m.im = d->im_channels;
+  m.C = d->two_robots ? 3 * m.im : 2 * m.im;
+  m.L = d->num_latents; m.D = d->latent_dim; m.depth = d->depth; m.low = d->low_dim_size;
+  m.R = d->num_rotation_classes; m.G = d->num_grip_classes; m.Cc = d->num_collision_classes;
+  m.fin = d->final_dim;
+  m.ch = d->cross_heads; m.cdh = d->cross_dim_head; m.lh = d->latent_heads; m.ldh = d->latent_dim_head;
+  m.flat = m.im * 4 + m.C * 4 + m.im * 4;
+  m.V3 = (size_t)m.V * m.V * m.V;
+  if (m.im != 64 || m.fin != 64 || d->initial_dim != 10) {
+    set_error("qnet: only im_channels=64, final_dim=64, initial_dim=10 are compiled");
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  if (m.D % 4 || m.C % 16 || (m.ch * m.cdh) % 4 || (m.lh * m.ldh) % 4 || m.low <= 0 || m.R <= 0) {
+    set_error("qnet: unsupported latent/head dimensions");
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  if (d->two_robots) {
+    set_error("qnet: PerceiverVoxelLang2RobotsEncoder is not built yet");
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  if (d->math_mode != VXB_MATH_FP32_SIMT && d->math_mode != VXB_MATH_BF16X3) {
+    set_error("qnet: unknown math_mode %d", d->math_mode);
+    return VXB_E_BADARG;
+  }
+  return VXB_OK;
+}
+
+// ---- prepared-weights arena
+struct Prepared {
+  float* patch_wt;   // [64][k^3][64]
+  float* up0_wt;     // [64][k^3][C]
+  float* up1_fold;   // [s^3][64][27][64]
+  float* final_wt;   // [64][27][128]
+  float* trans_wt;   // [27][64]
+  float* q_cross;    // [L][ch*cdh]  = to_q(LN(latents)), batch independent
+  float* lat_norm;   // [L][D] scratch for the above
+};
+static void carve_prepared(const Dims& m, Arena& a, Prepared& p) {
+  const int k3 = m.k * m.k * m.k;
+  p.patch_wt = a.get<float>((size_t)64 * k3 * 64);
+  p.up0_wt = a.get<float>((size_t)64 * k3 * m.C);
+  p.up1_fold = a.get<float>((size_t)m.s * m.s * m.s * 64 * 27 * 64);
+  p.final_wt = a.get<float>((size_t)64 * 27 * 128);
+  p.trans_wt = a.get<float>((size_t)27 * 64);
+  p.q_cross = a.get<float>((size_t)m.L * m.ch * m.cdh);
+  p.lat_norm = a.get<float>((size_t)m.L * m.D);
+}
+
+// ---- per-call workspace
+struct Work {
+  float *d0, *u0, *u;            // [B,V^3,64]
+  float *patch;                  // [B,T,64]
+  float *pfeat;                  // [B,64]
+  float *lang_lin;               // [B,nl,C]
+  float *ins;                    // [B,n,C]
+  float *ctx_n;                  // [B,n,C]   LayerNorm'd tokens (cross attn context / decoder queries)
+  float *kv_c;                   // [B,n,2*ch*cdh]
+  float *x;                      // [B,L,D]
+  float *xn;                     // [B,L,D]
+  float *qb;                     // [B,L,max(lh*ldh, ...)] / decoder q [B,n,ch*cdh]
+  float *kvb;                    // [B,L,2*lh*ldh]
+  float *att;                    // attention output [B, max(L*lh*ldh, n*ch*cdh)]
+  float *ffh;                    // [B,L,8D]
+  float *ffg;                    // [B,L,4D]
+  float *dec;                    // [B,T,C]
+  float *low;                    // [B,T,64]
+  float *feats;                  // [B,flat]
+  float *h0, *h1, *h2, *rgc;     // head activations
+  float *sim;                    // attention scores
+  float *ss_part;                // spatial softmax partials
+};
+static int ss_chunks(size_t P) { return (int)std::min<size_t>(1024, std::max<size_t>(1, (P + 1023) / 1024)); }
+
+static size_t sim_floats(const Dims& m, int B) {
+  auto pad4 = [](size_t v) { return (v + 3) / 4 * 4; };
+  size_t a = (size_t)B * m.ch * m.L * pad4(m.n);
+  size_t b = (size_t)B * m.lh * m.L * pad4(m.L);
+  size_t c = (size_t)B * m.ch * m.T * pad4(m.L);
+  return std::max(a, std::max(b, c));
+}
+
+static void carve_work(const Dims& m, int B, Arena& a, Work& w) {
+  w.d0 = a.get<float>((size_t)B * m.V3 * 64);
+  w.u0 = a.get<float>((size_t)B * m.V3 * 64);
+  w.u = a.get<float>((size_t)B * m.V3 * 64);
+  w.patch = a.get<float>((size_t)B * m.T * 64);
+  w.pfeat = a.get<float>((size_t)B * 64);
+  w.lang_lin = a.get<float>((size_t)B * m.nl * m.C);
+  w.ins = a.get<float>((size_t)B * m.n * m.C);
+  w.ctx_n = a.get<float>((size_t)B * m.n * m.C);
+  w.kv_c = a.get<float>((size_t)B * m.n * 2 * m.ch * m.cdh);
+  w.x = a.get<float>((size_t)B * m.L * m.D);
+  w.xn = a.get<float>((size_t)B * m.L * m.D);
+  w.qb = a.get<float>((size_t)B * std::max((size_t)m.L * m.lh * m.ldh, (size_t)m.n * m.ch * m.cdh));
+  w.kvb = a.get<float>((size_t)B * m.L * 2 * std::max(m.lh * m.ldh, m.ch * m.cdh));
+  w.att = a.get<float>((size_t)B * std::max((size_t)m.L * std::max(m.lh * m.ldh, m.ch * m.cdh),
+                                            (size_t)m.n * m.ch * m.cdh));
+  w.ffh = a.get<float>((size_t)B * m.L * 8 * m.D);
+  w.ffg = a.get<float>((size_t)B * m.L * 4 * m.D);
+  w.dec = a.get<float>((size_t)B * m.T * m.C);
+  w.low = a.get<float>((size_t)B * m.T * 64);
+  w.feats = a.get<float>((size_t)B * m.flat);
+  w.h0 = a.get<float>((size_t)B * 256);
+  w.h1 = a.get<float>((size_t)B * 64);
+  w.h2 = a.get<float>((size_t)B * 64);
+  w.rgc = a.get<float>((size_t)B * (3 * m.R + m.G + m.Cc));
+  w.sim = a.get<float>(sim_floats(m, B));
+  w.ss_part = a.get<float>((size_t)B * ss_chunks(m.V3) * 6 * 256);
+}
+
+// ---- small launch helpers -------------------------------------------------------------------
+static thread_local int g_launches = 0;  // kernels enqueued by the current API call
+static thread_local int g_last_launches = 0;
+#define COUNT_LAUNCH() (++g_launches)
+
+static int layernorm_batched(const float* x, size_t x_batch_stride, const float* w, const float* b,
+                             float* y, int batches, int rows_per_batch, int n, cudaStream_t st) {
+  COUNT_LAUNCH();
+  const size_t rows = (size_t)batches * rows_per_batch;
+  layernorm_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, w, b, y, (int)rows, n, rows_per_batch, x_batch_stride);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+static int layernorm(const float* x, const float* w, const float* b, float* y, size_t rows, int n,
+                     cudaStream_t st) {
+  return layernorm_batched(x, 0, w, b, y, 1, (int)rows, n, st);
+}
+
+static int spatial_softmax(const float* x, int B, int Dd, int Hh, int Ww, int C, float* ss,
+                           int ss_stride, float* mx, int mx_stride, float* partial,
+                           cudaStream_t st) {
+  const size_t P = (size_t)Dd * Hh * Ww;
+  VXB_CHECK_ARG(C <= 256 && C > 0, "spatial_softmax: C=%d > 256", C);
+  const int chunks = ss_chunks(P);
+  const int chunk = (int)((P + chunks - 1) / chunks);
+  COUNT_LAUNCH();
+  spatial_softmax_partial_kernel<<<dim3(chunks, B), 256, 0, st>>>(x, (int)P, C, Dd, Hh, Ww, chunk, partial);
+  VXB_LAUNCH_CHECK();
+  COUNT_LAUNCH();
+  spatial_softmax_merge_kernel<<<B, 256, 0, st>>>(partial, chunks, C, ss, ss_stride, mx, mx_stride);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+static int attention(const float* q, int ldq, long long qbs, const float* k, const float* v,
+                     int ldkv, long long kvbs, float* out, int ldo, long long obs, int B, int H,
+                     int Nq, int Nk, int dh, float scale, float* sim, int math_mode,
+                     cudaStream_t st) {
+  g_launches += 3;
+  return attention_materialized(q, ldq, qbs, k, v, ldkv, kvbs, out, ldo, obs, B, H, Nq, Nk, dh, scale,
+                                sim, math_mode, st);
+}
+
+// x = x + FF(LN(x)), FeedForward = Linear(D,8D) -> GEGLU -> Linear(4D,D)  (perceiver_lang_io.py:74-90)
+static int feed_forward(const Dims& m, int B, Work& w, const float* nw, const float* nb,
+                        const float* w0, const float* b0, const float* w2, const float* b2,
+                        int math_mode, cudaStream_t st) {
+  const size_t rows = (size_t)B * m.L;
+  VXB_TRY(layernorm(w.x, nw, nb, w.xn, rows, m.D, st));
+  COUNT_LAUNCH();
+  VXB_TRY(linear(w.xn, m.D, w0, m.D, b0, nullptr, 1, 0, w.ffh, 8 * m.D, (int)rows, 8 * m.D, m.D, 1.f,
+                 -1.f, math_mode, st));
+  COUNT_LAUNCH();
+  geglu_kernel<<<148 * 8, 256, 0, st>>>(w.ffh, w.ffg, rows, 4 * m.D);
+  VXB_LAUNCH_CHECK();
+  COUNT_LAUNCH();
+  VXB_TRY(linear(w.ffg, 4 * m.D, w2, 4 * m.D, b2, w.x, (int)rows, m.D, w.x, m.D, (int)rows, m.D,
+                 4 * m.D, 1.f, -1.f, math_mode, st));
+  return VXB_OK;
+}
+
+static int conv_weight_prepare(const float* w, float* o, int Co, int Ci, int k3, cudaStream_t st) {
+  conv_weight_to_tapmajor_kernel<<<cdiv((size_t)Co * Ci * k3, 256), 256, 0, st>>>(w, o, Co, Ci, k3);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+}  // namespace vxb
+
+using namespace vxb;
+
+extern "C" int vxb_version(void) { return VXB_VERSION; }
+extern "C" const char* vxb_last_error(void) { return vxb::g_err; }
+
+extern "C" int vxb_check_device(void) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("no CUDA device");
+    return VXB_E_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+    set_error("device %d is not compute capability 10.x (sm_100a required)", dev);
+    return VXB_E_NO_DEVICE;
+  }
+  return VXB_OK;
+}
+
+extern "C" int vxb_qnet_num_params(const vxb_qnet_desc* d) {
+  if (!d) return 0;
+  return VXB_P_FIXED_COUNT + d->depth * VXB_P_LAYER_STRIDE;
+}
+
+extern "C" size_t vxb_qnet_prepared_bytes(const vxb_qnet_desc* d) {
+  Dims m;
+  if (make_dims(d, m) != VXB_OK) return 0;
+  Arena a(nullptr, 0);
+  Prepared p;
+  carve_prepared(m, a, p);
+  return a.off;
+}
+
+extern "C" size_t vxb_qnet_workspace_bytes(const vxb_qnet_desc* d, int B) {
+  Dims m;
+  if (make_dims(d, m) != VXB_OK || B <= 0) return 0;
+  Arena a(nullptr, 0);
+  Work w;
+  carve_work(m, B, a, w);
+  return a.off;
+}
+
+extern "C" int vxb_qnet_prepare(const vxb_qnet_desc* d, const void* const* params, void* prepared,
+                                size_t prepared_bytes, void* stream) {
+  Dims m;
+  VXB_TRY(make_dims(d, m));
+  VXB_CHECK_ARG(params && prepared, "qnet_prepare: null pointer");
+  Arena a(prepared, prepared_bytes);
+  Prepared p;
+  carve_prepared(m, a, p);
+  if (!a.ok) {
+    set_error("qnet_prepare: prepared arena too small (%zu < %zu)", prepared_bytes, a.off);
+    return VXB_E_WORKSPACE_TOO_SMALL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  auto P = [&](int slot) { return (const float*)params[slot]; };
+  const int k3 = m.k * m.k * m.k;
+  VXB_TRY(conv_weight_prepare(P(VXB_P_PATCH_W), p.patch_wt, 64, 64, k3, st));
+  VXB_TRY(conv_weight_prepare(P(VXB_P_UP0_W), p.up0_wt, 64, m.C, k3, st));
+  VXB_TRY(conv_weight_prepare(P(VXB_P_FINAL_W), p.final_wt, 64, 128, 27, st));
+  VXB_TRY(conv_weight_prepare(P(VXB_P_TRANS_W), p.trans_wt, 1, 64, 27, st));
+  {
+    const size_t total = (size_t)m.s * m.s * m.s * 64 * 27 * 64;
+    fold_upconv_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(P(VXB_P_UP1_W), p.up1_fold, 64, 64, m.k, m.s);
+    VXB_LAUNCH_CHECK();
+  }
+  // q of the encoder cross-attention depends only on parameters: to_q(LN(latents))
+  VXB_TRY(layernorm(P(VXB_P_LATENTS), P(VXB_P_CROSS_NORM_W), P(VXB_P_CROSS_NORM_B), p.lat_norm, m.L, m.D, st));
+  VXB_TRY(linear(p.lat_norm, m.D, P(VXB_P_CROSS_Q_W), m.D, nullptr, nullptr, 1, 0, p.q_cross,
+                 m.ch * m.cdh, m.L, m.ch * m.cdh, m.D, 1.f, -1.f, VXB_MATH_FP32_SIMT, st));
+  return VXB_OK;
+}
+
+static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* const* params,
+                             const Prepared& pw, Work& w, const float* grid, const float* proprio,
+                             const float* lang_tokens, int B, float* q_trans, float* rot_grip,
+                             float* collision, float* arm_out, cudaStream_t st) {
+  auto P = [&](int slot) { return (const float*)params[slot]; };
+  auto PL = [&](int layer, int slot) {
+    return (const float*)params[VXB_P_FIXED_COUNT + layer * VXB_P_LAYER_STRIDE + slot];
+  };
+  const int mm = d->math_mode;
+  const float slope = d->act_slope;
+  const size_t MV = (size_t)B * m.V3;
+
+  // (1) d0 = act(conv1x1(grid))                                   perceiver_lang_io.py:357
+  COUNT_LAUNCH();
+  pointwise_conv_kernel<10><<<cdiv(MV, 64), 256, (64 * 10 + 64) * sizeof(float), st>>>(
+      grid, P(VXB_P_INPRE_W), P(VXB_P_INPRE_B), w.d0, MV, 64, slope);
+  VXB_LAUNCH_CHECK();
+  // (2) feats[0:256] = [ss0(d0), maxpool(d0)]                      :360
+  VXB_TRY(spatial_softmax(w.d0, B, m.V, m.V, m.V, 64, w.feats, m.flat, w.feats + 192, m.flat, w.ss_part, st));
+  // (3) patchify conv k, stride s, replicate pad                   :363
+  COUNT_LAUNCH();
+  VXB_TRY(conv3d(w.d0, nullptr, 64, 0, pw.patch_wt, P(VXB_P_PATCH_B), w.patch, B, m.V, m.S, 64, m.k,
+                 m.s, slope, mm, st));
+  // (4) proprio -> 64, language tokens -> C, token assembly + pos  :370-422
+  COUNT_LAUNCH();
+  VXB_TRY(linear(proprio, m.low, P(VXB_P_PROPRIO_W), m.low, P(VXB_P_PROPRIO_B), nullptr, 1, 0, w.pfeat,
+                 64, B, 64, m.low, 1.f, slope, VXB_MATH_FP32_SIMT, st));
+  if (d->no_language) {
+    // lang_preprocess(0) = bias
+    VXB_CUDA(cudaMemsetAsync(w.lang_lin, 0, (size_t)B * m.nl * m.C * sizeof(float), st));
+    COUNT_LAUNCH();
+    VXB_TRY(linear(w.lang_lin, m.C, P(VXB_P_LANG_W), d->lang_emb_dim, P(VXB_P_LANG_B), nullptr, 1, 0,
+                   w.lang_lin, m.C, B * m.nl, m.C, 0, 1.f, -1.f, VXB_MATH_FP32_SIMT, st));
+  } else {
+    COUNT_LAUNCH();
+    VXB_TRY(linear(lang_tokens, d->lang_emb_dim, P(VXB_P_LANG_W), d->lang_emb_dim, P(VXB_P_LANG_B),
+                   nullptr, 1, 0, w.lang_lin, m.C, B * m.nl, m.C, d->lang_emb_dim, 1.f, -1.f, mm, st));
+  }
+  COUNT_LAUNCH();
+  assemble_tokens_kernel<<<148 * 8, 256, 0, st>>>(w.lang_lin, w.patch, w.pfeat, nullptr,
+                                                  P(VXB_P_POS_ENCODING), w.ins, B, m.nl, m.T, m.C, 64);
+  VXB_LAUNCH_CHECK();
+
+  // (5) latents: x = repeat(latents) is never materialised; the first residual reads latents[m % L]   :425
+  const int cq = m.ch * m.cdh;   // cross-attention inner dim
+  const int lq = m.lh * m.ldh;   // latent-attention inner dim
+  for (int it = 0; it < d->iterations; ++it) {
+    // (6) encoder cross attention: x = Attn(LN(x), ctx=LN_ctx(ins)) + x      :431
+    VXB_TRY(layernorm(w.ins, P(VXB_P_CROSS_NORMCTX_W), P(VXB_P_CROSS_NORMCTX_B), w.ctx_n, (size_t)B * m.n, m.C, st));
+    COUNT_LAUNCH();
+    VXB_TRY(linear(w.ctx_n, m.C, P(VXB_P_CROSS_KV_W), m.C, nullptr, nullptr, 1, 0, w.kv_c, 2 * cq,
+                   B * m.n, 2 * cq, m.C, 1.f, -1.f, mm, st));
+    const float* qx;
+    long long qbs;
+    if (it == 0) {
+      qx = pw.q_cross;  // LN(latents) W_q^T is batch independent on the first iteration
+      qbs = 0;
+    } else {
+      VXB_TRY(layernorm(w.x, P(VXB_P_CROSS_NORM_W), P(VXB_P_CROSS_NORM_B), w.xn, (size_t)B * m.L, m.D, st));
+      COUNT_LAUNCH();
+      VXB_TRY(linear(w.xn, m.D, P(VXB_P_CROSS_Q_W), m.D, nullptr, nullptr, 1, 0, w.qb, cq, B * m.L, cq,
+                     m.D, 1.f, -1.f, mm, st));
+      qx = w.qb;
+      qbs = (long long)m.L * cq;
+    }
+    VXB_TRY(attention(qx, cq, qbs, w.kv_c, w.kv_c + cq, 2 * cq, (long long)m.n * 2 * cq, w.att, cq,
+                      (long long)m.L * cq, B, m.ch, m.L, m.n, m.cdh, 1.f / sqrtf((float)m.cdh), w.sim,
+                      mm, st));
+    COUNT_LAUNCH();
+    VXB_TRY(linear(w.att, cq, P(VXB_P_CROSS_OUT_W), cq, P(VXB_P_CROSS_OUT_B),
+                   it == 0 ? P(VXB_P_LATENTS) : w.x, it == 0 ? m.L : B * m.L, m.D, w.x, m.D, B * m.L,
+                   m.D, cq, 1.f, -1.f, mm, st));
+    VXB_TRY(feed_forward(m, B, w, P(VXB_P_CROSS_FF_NORM_W), P(VXB_P_CROSS_FF_NORM_B), P(VXB_P_CROSS_FF0_W),
+                         P(VXB_P_CROSS_FF0_B), P(VXB_P_CROSS_FF2_W), P(VXB_P_CROSS_FF2_B), mm, st));
+    // (7) latent self-attention stack                                         :435-437
+    for (int l = 0; l < m.depth; ++l) {
+      VXB_TRY(layernorm(w.x, PL(l, VXB_PL_ATTN_NORM_W), PL(l, VXB_PL_ATTN_NORM_B), w.xn, (size_t)B * m.L, m.D, st));
+      COUNT_LAUNCH();
+      VXB_TRY(linear(w.xn, m.D, PL(l, VXB_PL_Q_W), m.D, nullptr, nullptr, 1, 0, w.qb, lq, B * m.L, lq,
+                     m.D, 1.f, -1.f, mm, st));
+      COUNT_LAUNCH();
+      VXB_TRY(linear(w.xn, m.D, PL(l, VXB_PL_KV_W), m.D, nullptr, nullptr, 1, 0, w.kvb, 2 * lq, B * m.L,
+                     2 * lq, m.D, 1.f, -1.f, mm, st));
+      VXB_TRY(attention(w.qb, lq, (long long)m.L * lq, w.kvb, w.kvb + lq, 2 * lq, (long long)m.L * 2 * lq,
+                        w.att, lq, (long long)m.L * lq, B, m.lh, m.L, m.L, m.ldh,
+                        1.f / sqrtf((float)m.ldh), w.sim, mm, st));
+      COUNT_LAUNCH();
+      VXB_TRY(linear(w.att, lq, PL(l, VXB_PL_OUT_W), lq, PL(l, VXB_PL_OUT_B), w.x, B * m.L, m.D, w.x, m.D,
+                     B * m.L, m.D, lq, 1.f, -1.f, mm, st));
+      VXB_TRY(feed_forward(m, B, w, PL(l, VXB_PL_FF_NORM_W), PL(l, VXB_PL_FF_NORM_B), PL(l, VXB_PL_FF0_W),
+                           PL(l, VXB_PL_FF0_B), PL(l, VXB_PL_FF2_W), PL(l, VXB_PL_FF2_B), mm, st));
+    }
+  }
+  // (8) decoder cross attention: queries = LN(ins) voxel rows only (the nl language rows are
+  //     dropped right after, :444), context = LN_ctx(x); no residual              :440-448
+  VXB_TRY(layernorm_batched(w.ins + (size_t)m.nl * m.C, (size_t)m.n * m.C, P(VXB_P_DEC_NORM_W),
+                            P(VXB_P_DEC_NORM_B), w.ctx_n, B, m.T, m.C, st));
+  COUNT_LAUNCH();
+  VXB_TRY(linear(w.ctx_n, m.C, P(VXB_P_DEC_Q_W), m.C, nullptr, nullptr, 1, 0, w.qb, cq, B * m.T, cq, m.C,
+                 1.f, -1.f, mm, st));
+  VXB_TRY(layernorm(w.x, P(VXB_P_DEC_NORMCTX_W), P(VXB_P_DEC_NORMCTX_B), w.xn, (size_t)B * m.L, m.D, st));
+  COUNT_LAUNCH();
+  VXB_TRY(linear(w.xn, m.D, P(VXB_P_DEC_KV_W), m.D, nullptr, nullptr, 1, 0, w.kvb, 2 * cq, B * m.L, 2 * cq,
+                 m.D, 1.f, -1.f, mm, st));
+  VXB_TRY(attention(w.qb, cq, (long long)m.T * cq, w.kvb, w.kvb + cq, 2 * cq, (long long)m.L * 2 * cq, w.att,
+                    cq, (long long)m.T * cq, B, m.ch, m.T, m.L, m.cdh, 1.f / sqrtf((float)m.cdh), w.sim, mm, st));
+  COUNT_LAUNCH();
+  VXB_TRY(linear(w.att, cq, P(VXB_P_DEC_OUT_W), cq, P(VXB_P_DEC_OUT_B), nullptr, 1, 0, w.dec, m.C, B * m.T,
+                 m.C, cq, 1.f, -1.f, mm, st));
+  // (9) feats[256 : 256+4C] = [ss1(dec), maxpool(dec)]                           :451
+  VXB_TRY(spatial_softmax(w.dec, B, m.S, m.S, m.S, m.C, w.feats + 256, m.flat, w.feats + 256 + 3 * m.C,
+                          m.flat, w.ss_part, st));
+  // (10) up0: conv k (C->64) at S^3, then [upsample x s o conv k] folded     :454
+  COUNT_LAUNCH();
+  VXB_TRY(conv3d(w.dec, nullptr, m.C, 0, pw.up0_wt, P(VXB_P_UP0_B), w.low, B, m.S, m.S, 64, m.k, 1, slope, mm, st));
+  COUNT_LAUNCH();
+  VXB_TRY(upconv3d_folded(w.low, pw.up1_fold, P(VXB_P_UP1_B), w.u0, B, m.S, 64, 64, m.s, slope, mm, st));
+  // (11) final: conv3 on cat[d0, u0] (128 -> 64)                               :462
+  COUNT_LAUNCH();
+  VXB_TRY(conv3d(w.d0, w.u0, 64, 64, pw.final_wt, P(VXB_P_FINAL_B), w.u, B, m.V, m.V, 64, 3, 1, slope, mm, st));
+  // (12) trans decoder: conv3 64 -> 1, no activation                            :465
+  COUNT_LAUNCH();
+  conv3_to1_kernel<64><<<cdiv(MV, 32), 256, 0, st>>>(w.u, pw.trans_wt, P(VXB_P_TRANS_B), q_trans, B, m.V);
+  VXB_LAUNCH_CHECK();
+  // (13) feats[256+4C :] = [ss_final(u), maxpool(u)], MLP heads                 :470-483
+  const int off = 256 + 4 * m.C;
+  VXB_TRY(spatial_softmax(w.u, B, m.V, m.V, m.V, 64, w.feats + off, m.flat, w.feats + off + 192, m.flat,
+                          w.ss_part, st));
+  COUNT_LAUNCH();
+  VXB_TRY(linear(w.feats, m.flat, P(VXB_P_DENSE0_W), m.flat, P(VXB_P_DENSE0_B), nullptr, 1, 0, w.h0, 256, B,
+                 256, m.flat, 1.f, slope, VXB_MATH_FP32_SIMT, st));
+  COUNT_LAUNCH();
+  VXB_TRY(linear(w.h0, 256, P(VXB_P_DENSE1_W), 256, P(VXB_P_DENSE1_B), nullptr, 1, 0, w.h1, 64, B, 64, 256,
+                 1.f, slope, VXB_MATH_FP32_SIMT, st));
+  const int nout = 3 * m.R + m.G + m.Cc;
+  COUNT_LAUNCH();
+  VXB_TRY(linear(w.h1, 64, P(VXB_P_RGC_W), 64, P(VXB_P_RGC_B), nullptr, 1, 0, w.rgc, nout, B, nout, 64, 1.f,
+                 -1.f, VXB_MATH_FP32_SIMT, st));
+  VXB_CUDA(cudaMemcpy2DAsync(rot_grip, (size_t)(nout - m.Cc) * 4, w.rgc, (size_t)nout * 4,
+                             (size_t)(nout - m.Cc) * 4, B, cudaMemcpyDeviceToDevice, st));
+  VXB_CUDA(cudaMemcpy2DAsync(collision, (size_t)m.Cc * 4, w.rgc + (nout - m.Cc), (size_t)nout * 4,
+                             (size_t)m.Cc * 4, B, cudaMemcpyDeviceToDevice, st));
+  if (d->arm_pred_loss && arm_out) {
+    COUNT_LAUNCH();
+    VXB_TRY(linear(w.feats, m.flat, P(VXB_P_DENSE2_W), m.flat, P(VXB_P_DENSE2_B), nullptr, 1, 0, w.h2, 64, B,
+                   64, m.flat, 1.f, slope, VXB_MATH_FP32_SIMT, st));
+    COUNT_LAUNCH();
+    VXB_TRY(linear(w.h2, 64, P(VXB_P_ARM_W), 64, P(VXB_P_ARM_B), nullptr, 1, 0, arm_out, 2, B, 2, 64, 1.f,
+                   -1.f, VXB_MATH_FP32_SIMT, st));
+  }
+  return VXB_OK;
+}
+
+extern "C" int vxb_qnet_forward_f32(const vxb_qnet_desc* d, const void* const* params,
+                                    const void* prepared, const float* grid, const float* proprio,
+                                    const float* proprio2, const float* lang_tokens, int B,
+                                    float* q_trans, float* q_trans2, float* rot_grip,
+                                    float* collision, float* rot_grip2, float* collision2,
+                                    float* arm_out, void* ws, size_t ws_bytes, void* stream) {
+  Dims m;
+  VXB_TRY(make_dims(d, m));
+  VXB_CHECK_ARG(B > 0, "qnet_forward: B must be positive");
+  VXB_CHECK_ARG(params && prepared && grid && proprio && q_trans && rot_grip && collision && ws,
+                "qnet_forward: null pointer argument");
+  VXB_CHECK_ARG(d->no_language || lang_tokens, "qnet_forward: lang_tokens is null");
+  VXB_CHECK_ARG(!d->arm_pred_loss || arm_out, "qnet_forward: arm_pred_loss set but arm_out is null");
+  (void)proprio2; (void)q_trans2; (void)rot_grip2; (void)collision2;
+  Arena pa((void*)prepared, (size_t)-1);
+  Prepared pw;
+  carve_prepared(m, pa, pw);
+  Arena wa(ws, ws_bytes);
+  Work w;
+  carve_work(m, B, wa, w);
+  if (!wa.ok) {
+    set_error("qnet_forward: workspace too small (%zu < %zu)", ws_bytes, wa.off);
+    return VXB_E_WORKSPACE_TOO_SMALL;
+  }
+  g_launches = 0;
+  int rc = qnet_forward_impl(d, m, params, pw, w, grid, proprio, lang_tokens, B, q_trans, rot_grip,
+                             collision, arm_out, (cudaStream_t)stream);
+  g_last_launches = g_launches;
+  return rc;
+}
+
+extern "C" int vxb_last_launch_count(void) { return g_last_launches; }

@@ -1,0 +1,252 @@
+// K1: point cloud -> dense voxel grid (scatter-mean), B200 native.
+//
+// Replaces VoxelGrid.coords_to_bounding_voxel_grid (reference peract/voxel/voxel_grid.py:148-198,
+// with _scatter_nd :127-146 and _scatter_mean :106-125).
+//
+// Design (HBM-bound; algorithmic bytes/sample = N*(12+4F) read + V^3*(7+F)*4 write):
+//   1. scatter: one thread per point computes the reference's clamped (V+2)-grid index with the
+//      reference's exact fp32 operation order (sub, div, floor; no FMA contraction, no
+//      reciprocal), drops points that fall in the cropped border, and accumulates
+//      [count, xyz, features] into a per-sample open-addressing hash table that stays L2-resident
+//      (2N slots x 32 B = 4 MB/sample at N=65536) -- so the dense (V+2)^3 x 7 accumulation buffer
+//      of the reference (2 x 29.7 MB zero-fill + read-back per sample) never exists.  Points of
+//      one warp that hit the same voxel are first combined with match_any + shuffles (per-warp
+//      binning) so hot surface voxels cost one atomic set per warp, not 32.
+//   2. fill: one pass writes the dense [B,V,V,V,7+F] output with 128-bit coalesced stores staged
+//      through shared memory; an occupancy bitmap (1 bit/voxel) tells the 94+% empty voxels apart
+//      without touching the table.
+#include "common.cuh"
+
+namespace vxb {
+
+struct VoxEntry {  // 32 bytes for F<=3; generic F uses stride_f floats
+  int key;         // flat cropped voxel id + 1, 0 = empty
+  float cnt;
+  float sum[6];
+};
+
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352dU;
+  x ^= x >> 15;
+  x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
+}
+
+// Reference index arithmetic, voxel_grid.py:152-163 (fp32, this exact operation order).
+struct AxisMap {
+  float shifted;  // bb_min - res
+  float denom;    // res + 1e-12
+};
+__device__ __forceinline__ void make_axis_maps(const float* __restrict__ bnd, int V, AxisMap m[3]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float mn = bnd[a], mx = bnd[3 + a];
+    float range = __fsub_rn(mx, mn);
+    // dims_orig.float() + 1e-12 is evaluated in fp32 by torch -> exactly V
+    float res = __fdiv_rn(range, __fadd_rn((float)V, 1e-12f));
+    m[a].shifted = __fsub_rn(mn, res);
+    m[a].denom = __fadd_rn(res, 1e-12f);
+  }
+}
+__device__ __forceinline__ int axis_index(float p, const AxisMap& m, int V) {
+  float q = __fdiv_rn(__fsub_rn(p, m.shifted), m.denom);
+  float f = floorf(q);
+  f = fminf(fmaxf(f, 0.f), (float)(V + 1));  // == min(.,V+1), max(.,0) on the int (voxel_grid.py:162-163)
+  return (int)f;
+}
+
+template <int F>
+__global__ void __launch_bounds__(256)
+vox_scatter_kernel(const float* __restrict__ coords, const float* __restrict__ feats,
+                   const float* __restrict__ bounds, int Bb, int N, int V,
+                   float* __restrict__ table, int slots, int entry_floats,
+                   uint32_t* __restrict__ bitmap, int bitmap_words,
+                   int32_t* __restrict__ out_idx) {
+  const int b = blockIdx.y;
+  __shared__ AxisMap maps[3];
+  if (threadIdx.x == 0) make_axis_maps(bounds + (Bb == 1 ? 0 : b) * 6, V, maps);
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = n < N;
+  float val[3 + F];
+  int key = 0;
+  if (in_range) {
+    const float* c = coords + ((size_t)b * N + n) * 3;
+    val[0] = c[0]; val[1] = c[1]; val[2] = c[2];
+#pragma unroll
+    for (int f = 0; f < F; ++f) val[3 + f] = feats[((size_t)b * N + n) * F + f];
+    int ix = axis_index(val[0], maps[0], V);
+    int iy = axis_index(val[1], maps[1], V);
+    int iz = axis_index(val[2], maps[2], V);
+    if (out_idx) {
+      int32_t* o = out_idx + ((size_t)b * N + n) * 3;
+      o[0] = ix; o[1] = iy; o[2] = iz;
+    }
+    // border cells (index 0 or V+1) are cropped by vox[:, 1:-1, 1:-1, 1:-1] (voxel_grid.py:184)
+    if (ix >= 1 && ix <= V && iy >= 1 && iy <= V && iz >= 1 && iz <= V)
+      key = ((ix - 1) * V + (iy - 1)) * V + (iz - 1) + 1;
+  }
+  // ---- per-warp binning: combine lanes that target the same voxel
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned peers = __match_any_sync(0xffffffffu, key);
+  const unsigned leader = __ffs(peers) - 1;
+  float cnt = 1.f;
+  // warp-uniform loop over the lanes that are not the first of their voxel group; the group
+  // leader adds their contribution (deterministic lane order), everybody else just feeds shuffles.
+  unsigned followers = __ballot_sync(0xffffffffu, key != 0 && lane != leader);
+  while (followers) {
+    const int src = __ffs(followers) - 1;
+    followers &= followers - 1;
+    const bool take = (lane == leader) && ((peers >> src) & 1u);
+#pragma unroll
+    for (int j = 0; j < 3 + F; ++j) {
+      float v = __shfl_sync(0xffffffffu, val[j], src);
+      if (take) val[j] += v;
+    }
+    if (take) cnt += 1.f;
+  }
+  if (key == 0 || lane != leader) return;
+
+  float* tab = table + (size_t)b * slots * entry_floats;
+  uint32_t h = hash_u32((uint32_t)key) & (uint32_t)(slots - 1);
+  while (true) {
+    int* kp = reinterpret_cast<int*>(tab + (size_t)h * entry_floats);
+    int prev = atomicCAS(kp, 0, key);
+    if (prev == 0 || prev == key) break;
+    h = (h + 1) & (uint32_t)(slots - 1);
+  }
+  float* e = tab + (size_t)h * entry_floats;
+  atomicAdd(e + 1, cnt);
+#pragma unroll
+  for (int j = 0; j < 3 + F; ++j) atomicAdd(e + 2 + j, val[j]);
+  const int vid = key - 1;
+  atomicOr(bitmap + (size_t)b * bitmap_words + (vid >> 5), 1u << (vid & 31));
+}
+
+// Dense writer. One warp emits 32 consecutive voxels = 32*(7+F) floats with float4 stores.
+template <int F>
+__global__ void __launch_bounds__(256)
+vox_fill_kernel(const float* __restrict__ table, int slots, int entry_floats,
+                const uint32_t* __restrict__ bitmap, int bitmap_words, int V,
+                float* __restrict__ out) {
+  constexpr int CH = 7 + F;
+  const int b = blockIdx.y;
+  const int V3 = V * V * V;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ __align__(16) float stage[8][32 * CH];
+  const int v0 = (blockIdx.x * 8 + warp) * 32;  // first voxel of this warp
+  if (v0 >= V3) return;
+  const uint32_t word = bitmap[(size_t)b * bitmap_words + (v0 >> 5)];
+  const int v = v0 + lane;
+  float vals[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) vals[j] = 0.f;
+  if (v < V3) {
+    const int ix = v / (V * V), iy = (v / V) % V, iz = v % V;
+    const float Vf = (float)V;
+    // index_grid[:, :-2, :-2, :-2] / voxel_d  (voxel_grid.py:197)
+    vals[3 + F + 0] = __fdiv_rn((float)ix, Vf);
+    vals[3 + F + 1] = __fdiv_rn((float)iy, Vf);
+    vals[3 + F + 2] = __fdiv_rn((float)iz, Vf);
+    if ((word >> lane) & 1u) {
+      const float* tab = table + (size_t)b * slots * entry_floats;
+      const int key = v + 1;
+      uint32_t h = hash_u32((uint32_t)key) & (uint32_t)(slots - 1);
+      while (true) {
+        const float* e = tab + (size_t)h * entry_floats;
+        int kk = *reinterpret_cast<const int*>(e);
+        if (kk == key) {
+          float cnt = fmaxf(e[1], 1.f);  // out_count.clamp_(1)  (voxel_grid.py:119)
+#pragma unroll
+          for (int j = 0; j < 3 + F; ++j) vals[j] = __fdiv_rn(e[2 + j], cnt);
+          vals[CH - 1] = 1.f;            // occupied = (count > 0)  (voxel_grid.py:192)
+          break;
+        }
+        if (kk == 0) break;  // cannot happen for a set bit; guards against an endless probe
+        h = (h + 1) & (uint32_t)(slots - 1);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < CH; ++j) stage[warp][lane * CH + j] = vals[j];
+  __syncwarp();
+  const int nvalid = min(32, V3 - v0);
+  float* dst = out + ((size_t)b * V3 + v0) * CH;
+  if (nvalid == 32 && ((((size_t)b * V3 + v0) * CH) % 4 == 0)) {
+    const float4* s4 = reinterpret_cast<const float4*>(stage[warp]);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = lane; i < 32 * CH / 4; i += 32) d4[i] = s4[i];
+  } else {
+    for (int i = lane; i < nvalid * CH; i += 32) dst[i] = stage[warp][i];
+  }
+}
+
+static int table_slots(int N) {
+  int s = 1024;
+  while (s < 2 * N) s <<= 1;
+  return s;
+}
+static int entry_floats_for(int F) { return (int)align_up(2 + 3 + F, 8); }
+
+}  // namespace vxb
+
+using namespace vxb;
+
+extern "C" size_t vxb_voxelize_workspace_bytes(int B, int N, int V, int F) {
+  if (B <= 0 || N <= 0 || V <= 0 || F < 0) return 0;
+  size_t tab = (size_t)B * table_slots(N) * entry_floats_for(F) * sizeof(float);
+  size_t words = align_up(((size_t)V * V * V + 31) / 32, 64);
+  return align_up(tab, 256) + align_up((size_t)B * words * 4, 256);
+}
+
+extern "C" int vxb_voxelize_launches(void) { return 3; }
+
+template <int F>
+static int voxelize_impl(const float* coords, const float* feats, const float* bounds, int Bb,
+                         int B, int N, int V, float* out, int32_t* out_idx, void* ws,
+                         cudaStream_t st) {
+  const int slots = table_slots(N);
+  const int ef = entry_floats_for(F);
+  const size_t tab_bytes = align_up((size_t)B * slots * ef * sizeof(float), 256);
+  const int words = (int)align_up(((size_t)V * V * V + 31) / 32, 64);
+  float* table = (float*)ws;
+  uint32_t* bitmap = (uint32_t*)((char*)ws + tab_bytes);
+  VXB_CUDA(cudaMemsetAsync(ws, 0, tab_bytes + (size_t)B * words * 4, st));
+  dim3 g1(cdiv(N, 256), B);
+  vox_scatter_kernel<F><<<g1, 256, 0, st>>>(coords, feats, bounds, Bb, N, V, table, slots, ef,
+                                            bitmap, words, out_idx);
+  VXB_LAUNCH_CHECK();
+  dim3 g2(cdiv((long long)V * V * V, 256), B);
+  vox_fill_kernel<F><<<g2, 256, 0, st>>>(table, slots, ef, bitmap, words, V, out);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+extern "C" int vxb_voxelize_f32(const float* coords, const float* feats, const float* bounds,
+                                int Bb, int B, int N, int F, int V, float* out, int layout,
+                                int32_t* out_idx, void* ws, size_t ws_bytes, void* stream) {
+  VXB_CHECK_ARG(coords && bounds && out && ws, "voxelize: null pointer argument");
+  VXB_CHECK_ARG(B > 0 && N > 0 && V > 0, "voxelize: B, N, V must be positive");
+  VXB_CHECK_ARG(Bb == 1 || Bb == B, "voxelize: bounds batch must be 1 or B (got %d, B=%d)", Bb, B);
+  VXB_CHECK_ARG(layout == VXB_LAYOUT_CHANNELS_LAST, "voxelize: unknown layout %d", layout);
+  VXB_CHECK_ARG(F == 0 || feats, "voxelize: feats is null but F=%d", F);
+  if ((long long)V * V * V >= (1ll << 30)) {
+    set_error("voxelize: V=%d too large", V);
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  if (ws_bytes < vxb_voxelize_workspace_bytes(B, N, V, F)) {
+    set_error("voxelize: workspace too small (%zu < %zu)", ws_bytes,
+              vxb_voxelize_workspace_bytes(B, N, V, F));
+    return VXB_E_WORKSPACE_TOO_SMALL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (F) {
+    case 0: return voxelize_impl<0>(coords, feats, bounds, Bb, B, N, V, out, out_idx, ws, st);
+    case 3: return voxelize_impl<3>(coords, feats, bounds, Bb, B, N, V, out, out_idx, ws, st);
+    default:
+      set_error("voxelize: feature_size %d not compiled (0 or 3)", F);
+      return VXB_E_UNSUPPORTED_SHAPE;
+  }
+}

@@ -1,0 +1,383 @@
+"""B200-native ``PerceiverVoxelLangEncoder`` -- host-side mirror of the reference interface.
+
+Same constructor keywords/defaults, ``forward`` signature, return tuple and ``state_dict`` key
+names/shapes as reference peract/agents/peract_bc/perceiver_lang_io.py:136-485, so a checkpoint
+written by either implementation loads into the other (agent ``save_weights``/``load_weights``,
+qattention_peract_bc_agent.py:826-880).  The module owns the parameters only; all arithmetic runs
+in libvoxactb.so (hand-written sm_100a CUDA) through ``vxb_qnet_prepare`` / ``vxb_qnet_forward_f32``.
+There is no PyTorch or CPU fallback: a CPU tensor or a missing library raises.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+
+LRELU_SLOPE = 0.02  # reference helpers/network_utils.py:12
+
+_FIXED_SLOTS = [
+    'pos_encoding', 'latents',
+    'input_preprocess.conv3d.weight', 'input_preprocess.conv3d.bias',
+    'patchify.conv3d.weight', 'patchify.conv3d.bias',
+    'lang_preprocess.weight', 'lang_preprocess.bias',
+    'proprio_preprocess.linear.weight', 'proprio_preprocess.linear.bias',
+    None, None,  # 2-robot left-arm proprio
+    'cross_attend_blocks.0.norm.weight', 'cross_attend_blocks.0.norm.bias',
+    'cross_attend_blocks.0.norm_context.weight', 'cross_attend_blocks.0.norm_context.bias',
+    'cross_attend_blocks.0.fn.to_q.weight', 'cross_attend_blocks.0.fn.to_kv.weight',
+    'cross_attend_blocks.0.fn.to_out.weight', 'cross_attend_blocks.0.fn.to_out.bias',
+    'cross_attend_blocks.1.norm.weight', 'cross_attend_blocks.1.norm.bias',
+    'cross_attend_blocks.1.fn.net.0.weight', 'cross_attend_blocks.1.fn.net.0.bias',
+    'cross_attend_blocks.1.fn.net.2.weight', 'cross_attend_blocks.1.fn.net.2.bias',
+    'decoder_cross_attn.norm.weight', 'decoder_cross_attn.norm.bias',
+    'decoder_cross_attn.norm_context.weight', 'decoder_cross_attn.norm_context.bias',
+    'decoder_cross_attn.fn.to_q.weight', 'decoder_cross_attn.fn.to_kv.weight',
+    'decoder_cross_attn.fn.to_out.weight', 'decoder_cross_attn.fn.to_out.bias',
+    'up0.conv_up.0.conv3d.weight', 'up0.conv_up.0.conv3d.bias',
+    'up0.conv_up.2.conv3d.weight', 'up0.conv_up.2.conv3d.bias',
+    'final.conv3d.weight', 'final.conv3d.bias',
+    'trans_decoder.conv3d.weight', 'trans_decoder.conv3d.bias',
+    None, None,  # 2-robot left-arm trans decoder
+    'dense0.linear.weight', 'dense0.linear.bias',
+    'dense1.linear.weight', 'dense1.linear.bias',
+    'rot_grip_collision_ff.linear.weight', 'rot_grip_collision_ff.linear.bias',
+    'dense2.linear.weight', 'dense2.linear.bias',
+    'arm_ff.linear.weight', 'arm_ff.linear.bias',
+    None, None,
+]
+_LAYER_SLOTS = ['0.norm.weight', '0.norm.bias', '0.fn.to_q.weight', '0.fn.to_kv.weight',
+                '0.fn.to_out.weight', '0.fn.to_out.bias', '1.norm.weight', '1.norm.bias',
+                '1.fn.net.0.weight', '1.fn.net.0.bias', '1.fn.net.2.weight', '1.fn.net.2.bias']
+
+
+class _Node(nn.Module):
+    """Parameter container: gives parameters the reference's dotted state-dict names."""
+
+    def child(self, name):
+        if name not in self._modules:
+            self.add_module(name, _Node())
+        return self._modules[name]
+
+
+def _register(root, dotted, tensor, buffer=False):
+    parts = dotted.split('.')
+    node = root
+    for p in parts[:-1]:
+        node = node.child(p) if isinstance(node, _Node) else _child_of(node, p)
+    if buffer:
+        node.register_buffer(parts[-1], tensor)
+    else:
+        node.register_parameter(parts[-1], nn.Parameter(tensor))
+
+
+def _child_of(module, name):
+    if name not in module._modules:
+        module.add_module(name, _Node())
+    return module._modules[name]
+
+
+def _uniform(shape, bound):
+    return torch.empty(shape).uniform_(-bound, bound)
+
+
+def _init_weight(shape, fan_in, fan_out, activation):
+    """Initialisers the reference blocks use (network_utils.py:140-156, 263-276): Kaiming-uniform
+    for relu/lrelu, Xavier-uniform for linear outputs."""
+    if activation == 'lrelu':
+        gain = math.sqrt(2.0 / (1 + LRELU_SLOPE ** 2))
+        return _uniform(shape, gain * math.sqrt(3.0 / fan_in))
+    if activation == 'relu':
+        return _uniform(shape, math.sqrt(2.0) * math.sqrt(3.0 / fan_in))
+    if activation is None:
+        return _uniform(shape, math.sqrt(6.0 / (fan_in + fan_out)))
+    raise ValueError('%s not recognized.' % activation)
+
+
+def _spatial_positions(n):
+    """SpatialSoftmax3D buffers pos_x/pos_y/pos_z (network_utils.py:782-795); kept so the
+    state_dict has the reference's keys -- the kernels regenerate them on the fly."""
+    lin = np.linspace(-1., 1., n)
+    px, py, pz = np.meshgrid(lin, lin, lin)
+    return [torch.from_numpy(a.reshape(-1)).float() for a in (px, py, pz)]
+
+
+class PerceiverVoxelLangEncoder(nn.Module):
+    """Drop-in for reference perceiver_lang_io.py:136 (same keywords and defaults)."""
+
+    math_mode = _lib.MATH_FP32_SIMT
+
+    def __init__(self, depth, iterations, voxel_size, initial_dim, low_dim_size, layer=0,
+                 num_rotation_classes=72, num_grip_classes=2, num_collision_classes=2, input_axis=3,
+                 num_latents=512, im_channels=64, latent_dim=512, cross_heads=1, latent_heads=8,
+                 cross_dim_head=64, latent_dim_head=64, activation='relu', weight_tie_layers=False,
+                 pos_encoding_with_lang=True, input_dropout=0.1, attn_dropout=0.1,
+                 decoder_dropout=0.0, lang_fusion_type='seq', voxel_patch_size=9,
+                 voxel_patch_stride=8, no_skip_connection=False, no_perceiver=False,
+                 no_language=False, final_dim=64, arm_pred_loss=False):
+        super().__init__()
+        self.depth = depth
+        self.layer = layer
+        self.init_dim = int(initial_dim)
+        self.iterations = iterations
+        self.input_axis = input_axis
+        self.voxel_size = voxel_size
+        self.low_dim_size = low_dim_size
+        self.im_channels = im_channels
+        self.pos_encoding_with_lang = pos_encoding_with_lang
+        self.lang_fusion_type = lang_fusion_type
+        self.voxel_patch_size = voxel_patch_size
+        self.voxel_patch_stride = voxel_patch_stride
+        self.num_rotation_classes = num_rotation_classes
+        self.num_grip_classes = num_grip_classes
+        self.num_collision_classes = num_collision_classes
+        self.final_dim = final_dim
+        self.input_dropout = input_dropout
+        self.attn_dropout = attn_dropout
+        self.decoder_dropout = decoder_dropout
+        self.no_skip_connection = no_skip_connection
+        self.no_perceiver = no_perceiver
+        self.no_language = no_language
+        self.arm_pred_loss = arm_pred_loss
+        self.activation = activation
+        self.num_latents = num_latents
+        self.latent_dim = latent_dim
+        self.cross_heads, self.cross_dim_head = cross_heads, cross_dim_head
+        self.latent_heads, self.latent_dim_head = latent_heads, latent_dim_head
+
+        unsupported = []
+        if lang_fusion_type != 'seq':
+            unsupported.append("lang_fusion_type=%r" % lang_fusion_type)
+        if not pos_encoding_with_lang:
+            unsupported.append('pos_encoding_with_lang=False')
+        if no_skip_connection or no_perceiver:
+            unsupported.append('no_skip_connection/no_perceiver ablations')
+        if weight_tie_layers:
+            unsupported.append('weight_tie_layers=True')
+        if activation not in ('lrelu', 'relu'):
+            unsupported.append('activation=%r' % activation)
+        if num_rotation_classes <= 0:
+            unsupported.append('num_rotation_classes=0 (non-final C2FARM layers)')
+        if low_dim_size <= 0:
+            unsupported.append('low_dim_size=0')
+        if input_axis != 3:
+            unsupported.append('input_axis=%r' % input_axis)
+        if unsupported:
+            raise NotImplementedError(
+                'voxactb_b200.PerceiverVoxelLangEncoder builds the configuration launch_utils.create_agent '
+                'uses (seq language fusion, positional encoding with language, skip connection); '
+                'not built: ' + ', '.join(unsupported))
+
+        spatial = voxel_size // voxel_patch_stride
+        self.input_dim_before_seq = C = im_channels * 2
+        k, D, L = voxel_patch_size, latent_dim, num_latents
+        act = activation
+        reg = lambda name, t: _register(self, name, t)
+        reg('pos_encoding', torch.randn(1, 77 + spatial ** 3, C))
+        reg('input_preprocess.conv3d.weight', _init_weight((im_channels, self.init_dim, 1, 1, 1), self.init_dim, im_channels, act))
+        reg('input_preprocess.conv3d.bias', torch.zeros(im_channels))
+        reg('patchify.conv3d.weight', _init_weight((im_channels, im_channels, k, k, k), im_channels * k ** 3, im_channels * k ** 3, act))
+        reg('patchify.conv3d.bias', torch.zeros(im_channels))
+        b = 1.0 / math.sqrt(512)
+        reg('lang_preprocess.weight', _uniform((C, 512), b))
+        reg('lang_preprocess.bias', _uniform((C,), b))
+        reg('proprio_preprocess.linear.weight', _init_weight((im_channels, low_dim_size), low_dim_size, im_channels, act))
+        reg('proprio_preprocess.linear.bias', torch.zeros(im_channels))
+        for name, n in (('ss0', voxel_size),):
+            for ax, t in zip('xyz', _spatial_positions(n)):
+                _register(self, '%s.pos_%s' % (name, ax), t, buffer=True)
+        reg('latents', torch.randn(L, D))
+
+        def attention(prefix, qdim, cdim, heads, dh):
+            inner = heads * dh
+            reg(prefix + '.fn.to_q.weight', _uniform((inner, qdim), 1 / math.sqrt(qdim)))
+            reg(prefix + '.fn.to_kv.weight', _uniform((2 * inner, cdim), 1 / math.sqrt(cdim)))
+            reg(prefix + '.fn.to_out.weight', _uniform((qdim, inner), 1 / math.sqrt(inner)))
+            reg(prefix + '.fn.to_out.bias', _uniform((qdim,), 1 / math.sqrt(inner)))
+            reg(prefix + '.norm.weight', torch.ones(qdim))
+            reg(prefix + '.norm.bias', torch.zeros(qdim))
+
+        def feedforward(prefix, dim):
+            reg(prefix + '.fn.net.0.weight', _uniform((dim * 8, dim), 1 / math.sqrt(dim)))
+            reg(prefix + '.fn.net.0.bias', _uniform((dim * 8,), 1 / math.sqrt(dim)))
+            reg(prefix + '.fn.net.2.weight', _uniform((dim, dim * 4), 1 / math.sqrt(dim * 4)))
+            reg(prefix + '.fn.net.2.bias', _uniform((dim,), 1 / math.sqrt(dim * 4)))
+            reg(prefix + '.norm.weight', torch.ones(dim))
+            reg(prefix + '.norm.bias', torch.zeros(dim))
+
+        attention('cross_attend_blocks.0', D, C, cross_heads, cross_dim_head)
+        reg('cross_attend_blocks.0.norm_context.weight', torch.ones(C))
+        reg('cross_attend_blocks.0.norm_context.bias', torch.zeros(C))
+        feedforward('cross_attend_blocks.1', D)
+        for i in range(depth):
+            attention('layers.%d.0' % i, D, D, latent_heads, latent_dim_head)
+            feedforward('layers.%d.1' % i, D)
+        attention('decoder_cross_attn', C, D, cross_heads, cross_dim_head)
+        reg('decoder_cross_attn.norm_context.weight', torch.ones(D))
+        reg('decoder_cross_attn.norm_context.bias', torch.zeros(D))
+        reg('up0.conv_up.0.conv3d.weight', _init_weight((final_dim, C, k, k, k), C * k ** 3, final_dim * k ** 3, act))
+        reg('up0.conv_up.0.conv3d.bias', torch.zeros(final_dim))
+        reg('up0.conv_up.2.conv3d.weight', _init_weight((final_dim, final_dim, k, k, k), final_dim * k ** 3, final_dim * k ** 3, act))
+        reg('up0.conv_up.2.conv3d.bias', torch.zeros(final_dim))
+        for ax, t in zip('xyz', _spatial_positions(spatial)):
+            _register(self, 'ss1.pos_%s' % ax, t, buffer=True)
+        reg('final.conv3d.weight', _init_weight((im_channels, im_channels * 2, 3, 3, 3), im_channels * 2 * 27, im_channels * 27, act))
+        reg('final.conv3d.bias', torch.zeros(im_channels))
+        reg('trans_decoder.conv3d.weight', _init_weight((1, final_dim, 3, 3, 3), final_dim * 27, 27, None))
+        reg('trans_decoder.conv3d.bias', torch.zeros(1))
+        for ax, t in zip('xyz', _spatial_positions(voxel_size)):
+            _register(self, 'ss_final.pos_%s' % ax, t, buffer=True)
+        flat = im_channels * 4 + C * 4 + im_channels * 4
+        nout = num_rotation_classes * 3 + num_grip_classes + num_collision_classes
+        reg('dense0.linear.weight', _init_weight((256, flat), flat, 256, act))
+        reg('dense0.linear.bias', torch.zeros(256))
+        reg('dense1.linear.weight', _init_weight((final_dim, 256), 256, final_dim, act))
+        reg('dense1.linear.bias', torch.zeros(final_dim))
+        reg('rot_grip_collision_ff.linear.weight', _init_weight((nout, final_dim), final_dim, nout, None))
+        reg('rot_grip_collision_ff.linear.bias', torch.zeros(nout))
+        if arm_pred_loss:
+            reg('dense2.linear.weight', _init_weight((final_dim, flat), flat, final_dim, act))
+            reg('dense2.linear.bias', torch.zeros(final_dim))
+            reg('arm_ff.linear.weight', _init_weight((2, final_dim), final_dim, 2, None))
+            reg('arm_ff.linear.bias', torch.zeros(2))
+
+        # runtime state (never pickled / deep-copied with live CUDA handles: rebuilt lazily)
+        self._prepared = None
+        self._prepared_key = None
+        self._workspace = None
+        self.last_launch_count = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state['_prepared'] = None
+        state['_prepared_key'] = None
+        state['_workspace'] = None
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            setattr(new, k, copy.deepcopy(v, memo))
+        return new
+
+    def _apply(self, fn, *a, **kw):
+        self._prepared = None
+        self._prepared_key = None
+        self._workspace = None
+        return super()._apply(fn, *a, **kw)
+
+    def _desc(self):
+        d = _lib.QnetDesc()
+        d.struct_bytes = ctypes.sizeof(_lib.QnetDesc)
+        d.voxel_size = self.voxel_size
+        d.patch_size = self.voxel_patch_size
+        d.patch_stride = self.voxel_patch_stride
+        d.initial_dim = self.init_dim
+        d.im_channels = self.im_channels
+        d.low_dim_size = self.low_dim_size
+        d.two_robots = 0
+        d.lang_seq_len = 77
+        d.lang_emb_dim = 512
+        d.num_latents = self.num_latents
+        d.latent_dim = self.latent_dim
+        d.depth = self.depth
+        d.iterations = self.iterations
+        d.cross_heads, d.cross_dim_head = self.cross_heads, self.cross_dim_head
+        d.latent_heads, d.latent_dim_head = self.latent_heads, self.latent_dim_head
+        d.final_dim = self.final_dim
+        d.num_rotation_classes = self.num_rotation_classes
+        d.num_grip_classes = self.num_grip_classes
+        d.num_collision_classes = self.num_collision_classes
+        d.arm_pred_loss = int(bool(self.arm_pred_loss))
+        d.no_language = int(bool(self.no_language))
+        d.act_slope = LRELU_SLOPE if self.activation == 'lrelu' else 0.0
+        d.math_mode = int(self.math_mode)
+        return d
+
+    def _param_table(self):
+        named = dict(self.named_parameters())
+        slots = [named.get(n) if n else None for n in _FIXED_SLOTS]
+        for i in range(self.depth):
+            slots += [named['layers.%d.%s' % (i, s)] for s in _LAYER_SLOTS]
+        arr = (ctypes.c_void_p * len(slots))()
+        keep = []
+        for i, p in enumerate(slots):
+            if p is None:
+                arr[i] = None
+                continue
+            t = _lib.f32(p.detach())
+            keep.append(t)
+            arr[i] = t.data_ptr()
+        return arr, keep, slots
+
+    def _ensure_prepared(self, desc, arr, slots, device):
+        key = (device, int(self.math_mode),
+               tuple((p.data_ptr(), p._version) for p in slots if p is not None))
+        if self._prepared is not None and self._prepared_key == key:
+            return
+        L = _lib.lib()
+        nbytes = L.vxb_qnet_prepared_bytes(ctypes.byref(desc))
+        if nbytes == 0:
+            _lib.check(-2, 'vxb_qnet_prepared_bytes')
+        if self._prepared is None or self._prepared.numel() < nbytes or self._prepared.device != device:
+            self._prepared = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _lib.check(L.vxb_qnet_prepare(ctypes.byref(desc), arr, _lib.ptr(self._prepared), nbytes,
+                                      _lib.stream()), 'vxb_qnet_prepare')
+        self._prepared_key = key
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, ins, proprio, lang_goal_emb, lang_token_embs, prev_layer_voxel_grid, bounds,
+                prev_layer_bounds, mask=None):
+        """ins [B,10,V,V,V] (normally the permuted channels-last voxel grid QFunction.forward passes,
+        qattention_peract_bc_agent.py:100); returns (trans [B,1,V,V,V], rot_and_grip [B,3R+G],
+        collision [B,Cc][, arm [B,2]]) like perceiver_lang_io.py:465-485."""
+        if mask is not None:
+            raise NotImplementedError('attention mask is never passed by the agent (always None)')
+        if self.training and (self.input_dropout > 0 or self.attn_dropout > 0 or self.decoder_dropout > 0):
+            raise NotImplementedError(
+                'training-mode dropout / backward are not built yet: call .eval() (inference path)')
+        if not ins.is_cuda:
+            raise RuntimeError('voxactb_b200.PerceiverVoxelLangEncoder runs on CUDA only (no CPU fallback)')
+        B, C10, V = ins.shape[0], ins.shape[1], ins.shape[2]
+        if C10 != self.init_dim or V != self.voxel_size:
+            raise ValueError('expected ins [B,%d,%d,%d,%d], got %s' % (self.init_dim, self.voxel_size, self.voxel_size, self.voxel_size, tuple(ins.shape)))
+        with torch.no_grad():
+            grid = _lib.f32(ins.permute(0, 2, 3, 4, 1))      # no copy when ins is the permuted view
+            proprio = _lib.f32(proprio)
+            lang = _lib.f32(lang_token_embs)
+            if proprio.shape != (B, self.low_dim_size):
+                raise ValueError('proprio must be [%d,%d], got %s' % (B, self.low_dim_size, tuple(proprio.shape)))
+            if lang.shape != (B, 77, 512):
+                raise ValueError('lang_token_embs must be [%d,77,512], got %s' % (B, tuple(lang.shape)))
+            L = _lib.lib()
+            desc = self._desc()
+            arr, keep, slots = self._param_table()
+            dev = ins.device
+            self._ensure_prepared(desc, arr, slots, dev)
+            ws_bytes = L.vxb_qnet_workspace_bytes(ctypes.byref(desc), B)
+            if ws_bytes == 0:
+                _lib.check(-2, 'vxb_qnet_workspace_bytes')
+            if self._workspace is None or self._workspace.numel() < ws_bytes or self._workspace.device != dev:
+                self._workspace = None
+                self._workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            nrg = self.num_rotation_classes * 3 + self.num_grip_classes
+            trans = torch.empty(B, 1, V, V, V, dtype=torch.float32, device=dev)
+            rot_grip = torch.empty(B, nrg, dtype=torch.float32, device=dev)
+            coll = torch.empty(B, self.num_collision_classes, dtype=torch.float32, device=dev)
+            arm = torch.empty(B, 2, dtype=torch.float32, device=dev) if self.arm_pred_loss else None
+            rc = L.vxb_qnet_forward_f32(ctypes.byref(desc), arr, _lib.ptr(self._prepared), _lib.ptr(grid),
+                                        _lib.ptr(proprio), None, _lib.ptr(lang), B, _lib.ptr(trans), None,
+                                        _lib.ptr(rot_grip), _lib.ptr(coll), None, None, _lib.ptr(arm),
+                                        _lib.ptr(self._workspace), ws_bytes, _lib.stream())
+            _lib.check(rc, 'vxb_qnet_forward_f32')
+            self.last_launch_count = L.vxb_last_launch_count()
+            del keep
+        if self.arm_pred_loss:
+            return trans, rot_grip, coll, arm
+        return trans, rot_grip, coll
