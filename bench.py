@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- policy forward passes/sec at 100^3 voxels (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 16] [--impl ours|reference]
+
+A step = one pass of the hot path over one batch of synthetic observations per GPU:
+voxelize (4 cameras x 128x128 RGB-D points -> 100^3 grid) + PerceiverActor Q-network forward.
+N > 1: launched under torchrun, one process per GPU, the batch shards across ranks with no
+data-path collective (weak scaling: --batch samples per GPU).
+
+`value`  : whole-job passes/s with the observations already resident in HBM.
+`e2e`    : the same through the public API (QFunction.forward + fused action selection) from
+           pinned HOST buffers, host->device copies of the observations and device->host read of the
+           selected actions inside the timed region.
+`roofline`: the dominant kernel (final 3x3x3 conv 128->64 at 100^3) timed live with CUDA events on
+           the launching stream (library stage profiler), algorithmic FLOPs / time vs the measured
+           tensor peak in MEASURED_PEAKS.json.
+`cpu_baseline`: the CPU oracle port (oracle/) of the reference's PyTorch path on the host cores, on
+           a bounded sample (batch 1) of the same workload.
+--impl reference: times that CPU implementation alone (the reference itself is Python and is not
+           present on the GPU box; oracle/ is its restatement, pinned by tests/test_oracle.py).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_PASS = 1672729956352          # BASELINE.md section 4 (single-arm, V=100, k=s=5, L=2048, depth 6)
+FINAL_CONV_FLOPS = 2 * 100 ** 3 * 64 * 128 * 27      # 442.4 GF / sample (direct convolution)
+UPCONV_FLOPS = 2 * 100 ** 3 * 64 * 64 * 125          # 1024 GF / sample (direct convolution, as BASELINE.md counts it)
+VOXELIZE_BYTES = 65536 * 24 + 100 ** 3 * 10 * 4      # 41 572 864 B / sample
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=16, help='samples per GPU')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--math', default=os.environ.get('VXB_MATH', 'auto'), choices=['auto', 'fp32', 'bf16x3'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p['hbm_gbs'], tensor=p['bf16_tflops_sustained'], tensor_burst=p['bf16_tflops'],
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm=6650.0, tensor=1400.0, tensor_burst=1590.0, source='fallback (B200_PROFILING.md)')
+
+
+WORKLOAD = 'batch={b}/GPU, 100^3 voxels, 4 cameras 128x128 RGB-D, CLIP lang tokens [77,512], single-arm PerAct forward (voxelize + Q-net, 2048 latents, depth 6)'
+
+
+def cpu_pass_rate(steps, warmup, threads=None):
+    """The reference's CPU PyTorch path (oracle port) on one sample: passes/s on the host cores."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+    from oracle import qnet_oracle, voxel_oracle
+    import make_golden
+    import util
+    torch.set_num_threads(threads or os.cpu_count())
+    c = dict(make_golden.QNET_CASES['qnet_v100_b1'])
+    obs, enc, sd = util.make_case(c)
+    cfg = util.oracle_cfg(c)
+
+    def one():
+        with torch.no_grad():
+            return qnet_oracle.qfunction_forward(sd, cfg, voxel_oracle.voxelize, obs['rgb'], obs['pcd'],
+                                                 obs['proprio'], obs['lang_token_embs'], obs['bounds'], c['V'])
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return steps / dt, torch.get_num_threads(), dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    rate, cores, spp = cpu_pass_rate(steps, max(1, min(args.warmup, 2)))
+    line = {
+        'impl': 'reference', 'metric': 'policy fwd passes/sec at 100^3 voxels', 'value': rate, 'unit': 'passes/s',
+        'n_gpus': args.gpus, 'steps': steps, 'warmup': max(1, min(args.warmup, 2)), 'ms_per_step': spp * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD.format(b=args.batch),
+                   'note': 'reference CPU PyTorch path (oracle port) on the host cores; each step = 1 sample of the batch'},
+        'cpu_baseline': {'value': rate, 'unit': 'passes/s', 'cores': cores, 'kind': 'port',
+                         'sample': 'batch 1 of the workload per step (voxelize + Q-net forward), torch CPU fp32'},
+        'e2e': {'value': rate, 'unit': 'passes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + q, '--format=csv,noheader,nounits',
+                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(', ') for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.strip().lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from voxactb_b200 import QFunction, VoxelGrid, PerceiverVoxelLangEncoder, _lib, synth
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    L = _lib.lib()
+    _lib.check(L.vxb_check_device(), 'vxb_check_device')
+    math_mode = {'fp32': _lib.MATH_FP32_SIMT, 'bf16x3': _lib.MATH_BF16X3,
+                 'auto': PerceiverVoxelLangEncoder.math_mode}[args.math]
+    B, V = args.batch, 100
+    torch.manual_seed(1234 + rank)
+    enc = PerceiverVoxelLangEncoder(
+        depth=6, iterations=1, voxel_size=V, initial_dim=10, low_dim_size=4, layer=0, num_rotation_classes=72,
+        num_grip_classes=2, num_collision_classes=2, input_axis=3, num_latents=2048, latent_dim=512, cross_heads=1,
+        latent_heads=8, cross_dim_head=64, latent_dim_head=64, activation='lrelu', weight_tie_layers=False,
+        pos_encoding_with_lang=True, input_dropout=0.1, attn_dropout=0.1, decoder_dropout=0.0,
+        lang_fusion_type='seq', voxel_patch_size=5, voxel_patch_stride=5, final_dim=64).eval()
+    enc.load_state_dict(synth.random_state_dict(enc, 2234), strict=False)
+    enc.math_mode = math_mode
+    vg = VoxelGrid(synth.SCENE_BOUNDS, V, dev, B, 3, 4 * 128 * 128)
+    q = QFunction(enc, vg, 0.15, 5, dev, False, False).to(dev).eval()
+
+    obs = synth.make_observation(1234 + rank, B, 4, 128, 128, low_dim=4)
+    host = {k: [t.pin_memory() for t in obs[k]] for k in ('rgb', 'pcd')}
+    for k in ('proprio', 'lang_goal_emb', 'lang_token_embs', 'bounds'):
+        host[k] = obs[k].pin_memory()
+    h2d_bytes = sum(t.numel() * 4 for k in ('rgb', 'pcd') for t in host[k]) + sum(
+        host[k].numel() * 4 for k in ('proprio', 'lang_token_embs', 'bounds'))
+
+    def upload():
+        d = {k: [t.to(dev, non_blocking=True) for t in host[k]] for k in ('rgb', 'pcd')}
+        for k in ('proprio', 'lang_token_embs', 'bounds'):
+            d[k] = host[k].to(dev, non_blocking=True)
+        return d
+
+    resident = upload()
+    resident['lang_goal_emb'] = host['lang_goal_emb'].to(dev)
+    torch.cuda.synchronize()
+
+    def step_device(d):
+        rgb_pcd = [[r, p] for r, p in zip(d['rgb'], d['pcd'])]
+        return q(rgb_pcd, d['proprio'], d['pcd'], resident['lang_goal_emb'], d['lang_token_embs'], d['bounds'], None, None)
+
+    out_host = {'coords': torch.empty(B, 3, dtype=torch.int32).pin_memory(),
+                'rg': torch.empty(B, 4, dtype=torch.int32).pin_memory(),
+                'coll': torch.empty(B, dtype=torch.int32).pin_memory(),
+                'xyz': torch.empty(B, 3, dtype=torch.float32).pin_memory()}
+    d2h_bytes = sum(t.numel() * 4 for t in out_host.values())
+
+    def step_e2e():
+        d = upload()
+        trans, rot_grip, coll, _ = step_device(d)
+        coords, rg, ic, xyz = q.select_action(trans, rot_grip, coll, d['bounds'])
+        out_host['coords'].copy_(coords, non_blocking=True)
+        out_host['rg'].copy_(rg, non_blocking=True)
+        out_host['coll'].copy_(ic, non_blocking=True)
+        out_host['xyz'].copy_(xyz, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller needs the action before the next step
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if profile:
+            L.vxb_profile_enable(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        stages = None
+        if profile:
+            buf = (ctypes.c_double * L.vxb_profile_stage_count())()
+            n = L.vxb_profile_read(buf)
+            L.vxb_profile_enable(0)
+            stages = {L.vxb_profile_stage_name(i).decode(): buf[i] / max(n, 1) for i in range(len(buf))}
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, stages
+
+    # voxelize-only timing (HBM-bound kernel of the path), same stream, CUDA events
+    coords_flat, feats_flat = synth.flatten_cameras(obs)
+    cf, ff, bb = coords_flat.to(dev), feats_flat.to(dev), resident['bounds']
+    clocks = ClockSampler(local)
+    ms_dev, stages = timed(lambda: step_device(resident), args.steps, args.warmup, profile=True)
+    clk = clocks.stop()
+    launches_per_step = L.vxb_voxelize_launches() + enc.last_launch_count
+    ms_vox, _ = timed(lambda: vg.coords_to_bounding_voxel_grid(cf, ff, bb), max(args.steps, 10), 3)
+    ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    per_step = ms_dev / args.steps
+    value = world * B / (per_step * 1e-3)
+    e2e_value = world * B / (ms_e2e / args.steps * 1e-3)
+    final_ms = stages['final_conv']
+    achieved_tf = FINAL_CONV_FLOPS * B / (final_ms * 1e-3) / 1e12
+    vox_ms = ms_vox / max(args.steps, 10)
+    line = {
+        'metric': 'policy fwd passes/sec at 100^3 voxels', 'value': value, 'unit': 'passes/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if math_mode == _lib.MATH_FP32_SIMT else 'bf16x3(split-bf16, fp32 accumulate)',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD.format(b=B), 'global_batch': world * B, 'parallelism': 'batch-sharded x%d, no collective' % world,
+                   'math_mode': 'fp32_simt' if math_mode == _lib.MATH_FP32_SIMT else 'bf16x3_tcgen05',
+                   'l2': 'no explicit flush: each step streams >10 GB of activations, far above the 126 MB L2'},
+        'e2e': {'value': e2e_value, 'unit': 'passes/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
+                'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': (launches_per_step) * args.steps,
+        'clocks': clk,
+        'roofline': {'kernel': 'final_conv (3x3x3, 128->64 @100^3, implicit GEMM)', 'bound': 'tensor',
+                     'achieved': achieved_tf, 'peak': pk['tensor'], 'unit': 'TFLOP/s', 'frac': achieved_tf / pk['tensor'],
+                     'traffic': None, 'peak_source': pk['source'] + ' bf16 sustained', 'ms_per_launch': final_ms,
+                     'whole_forward_tflops': FLOPS_PER_PASS * B / (per_step * 1e-3) / 1e12,
+                     'voxelize': {'bound': 'hbm', 'achieved': VOXELIZE_BYTES * B / (vox_ms * 1e-3) / 1e9, 'peak': pk['hbm'],
+                                  'unit': 'GB/s', 'frac': VOXELIZE_BYTES * B / (vox_ms * 1e-3) / 1e9 / pk['hbm'],
+                                  'ms_per_call': vox_ms}},
+        'stages_ms': stages,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        rate, cores, spp = cpu_pass_rate(3, 1)
+        line['cpu_baseline'] = {'value': rate, 'unit': 'passes/s', 'cores': cores, 'kind': 'port',
+                                'sample': '3 timed single-sample passes (batch 1 of the workload) after 1 warm-up, torch CPU fp32 oracle port'}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

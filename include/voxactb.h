@@ -163,6 +163,14 @@ int vxb_qnet_forward_f32(const vxb_qnet_desc* d, const void* const* params, cons
 int vxb_last_launch_count(void);
 int vxb_voxelize_launches(void);
 
+/* stage timing of vxb_qnet_forward_f32 with CUDA events on the caller's stream (bench.py's live
+ * roofline numbers).  vxb_profile_read ADDS the per-stage milliseconds of every forward since the
+ * last read into ms[0..vxb_profile_stage_count()) and returns how many forwards it consumed. */
+int vxb_profile_stage_count(void);
+const char* vxb_profile_stage_name(int i);
+int vxb_profile_enable(int on);
+int vxb_profile_read(double* ms /* host */);
+
 /* ------------------------------------------------------------------ action selection */
 /*
  * softmax-free argmax of the translation grid (softmax is monotone: agent:709-718), per-axis-group

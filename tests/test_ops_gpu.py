@@ -35,7 +35,8 @@ def test_linear(cuda_lib, mode, M, N, K):
     # broadcast residual rows (latents) + alpha + no activation
     Rb = torch.randn(3, N, generator=g)
     ref2 = 0.5 * F.linear(A, W) + Rb[torch.arange(M) % 3]
-    _lib.check(cuda_lib.vxb_linear_f32(_lib.ptr(Ac), K, _lib.ptr(Wc), K, None, _lib.ptr(Rb.cuda()), 3,
+    Rbc = Rb.cuda()
+    _lib.check(cuda_lib.vxb_linear_f32(_lib.ptr(Ac), K, _lib.ptr(Wc), K, None, _lib.ptr(Rbc), 3,
                                        _lib.ptr(C), N, M, N, K, 0.5, -1.0, mode, _lib.stream()), 'linear')
     assert util.rel_err(C, ref2) < TOL[mode]
 
@@ -46,7 +47,8 @@ def test_layernorm(cuda_lib):
         x = torch.randn(rows, n, generator=g) * 3 + 1
         w, b = torch.randn(n, generator=g), torch.randn(n, generator=g)
         y = torch.empty(rows, n, device='cuda')
-        _lib.check(cuda_lib.vxb_layernorm_f32(_lib.ptr(x.cuda()), _lib.ptr(w.cuda()), _lib.ptr(b.cuda()),
+        xc, wc, bc = x.cuda(), w.cuda(), b.cuda()   # keep the device copies alive across the call
+        _lib.check(cuda_lib.vxb_layernorm_f32(_lib.ptr(xc), _lib.ptr(wc), _lib.ptr(bc),
                                               _lib.ptr(y), rows, n, _lib.stream()), 'layernorm')
         assert util.rel_err(y, F.layer_norm(x, (n,), w, b)) < 1e-5
 
@@ -78,8 +80,9 @@ def test_conv3d(cuda_lib, mode, Di, Ci, Co, k, s):
     ref = qnet_oracle.conv3d_block(x, w, b, s, 'lrelu').permute(0, 2, 3, 4, 1)
     y = torch.empty(ref.shape, device='cuda')
     wk = ws(cuda_lib.vxb_conv3d_workspace_bytes(Ci, Co, k))
-    _lib.check(cuda_lib.vxb_conv3d_f32(_lib.ptr(x.permute(0, 2, 3, 4, 1).contiguous().cuda()), _lib.ptr(w.cuda()),
-                                       _lib.ptr(b.cuda()), _lib.ptr(y), 2, Di, Ci, Co, k, s, 0.02, mode,
+    xc, wc, bc = x.permute(0, 2, 3, 4, 1).contiguous().cuda(), w.cuda(), b.cuda()
+    _lib.check(cuda_lib.vxb_conv3d_f32(_lib.ptr(xc), _lib.ptr(wc),
+                                       _lib.ptr(bc), _lib.ptr(y), 2, Di, Ci, Co, k, s, 0.02, mode,
                                        _lib.ptr(wk), wk.numel(), _lib.stream()), 'conv3d')
     assert util.rel_err(y, ref) < TOL[mode]
 
@@ -98,8 +101,9 @@ def test_upconv3d_equals_upsample_then_conv(cuda_lib, mode, S, k, s):
     ref = qnet_oracle.conv3d_block(up, w, b, 1, 'lrelu').permute(0, 2, 3, 4, 1)
     y = torch.empty(ref.shape, device='cuda')
     wk = ws(cuda_lib.vxb_upconv3d_workspace_bytes(Ci, Co, k, s))
-    _lib.check(cuda_lib.vxb_upconv3d_f32(_lib.ptr(x.permute(0, 2, 3, 4, 1).contiguous().cuda()), _lib.ptr(w.cuda()),
-                                         _lib.ptr(b.cuda()), _lib.ptr(y), 2, S, Ci, Co, k, s, 0.02, mode,
+    xc, wc, bc = x.permute(0, 2, 3, 4, 1).contiguous().cuda(), w.cuda(), b.cuda()
+    _lib.check(cuda_lib.vxb_upconv3d_f32(_lib.ptr(xc), _lib.ptr(wc),
+                                         _lib.ptr(bc), _lib.ptr(y), 2, S, Ci, Co, k, s, 0.02, mode,
                                          _lib.ptr(wk), wk.numel(), _lib.stream()), 'upconv3d')
     assert util.rel_err(y, ref) < max(TOL[mode], 3e-5)
 

@@ -99,4 +99,5 @@ def test_checkpoint_roundtrip_and_deepcopy(cuda_lib, tmp_path):
     assert all(k.startswith('_qnet.') for k in loaded)
     q2, out2 = run_qfunction(c, obs, enc2, _lib.MATH_FP32_SIMT)
     q2.load_state_dict(loaded)
-    assert torch.equal(out[0], out2[0])
+    # identical weights -> identical Q-values up to the voxelizer's atomic summation order
+    assert util.rel_err(out2[0], out[0]) < 1e-5 and util.rel_err(out2[1], out[1]) < 1e-5

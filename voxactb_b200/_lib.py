@@ -48,6 +48,10 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_size_t, c_void_p]),
     'vxb_last_launch_count': (c_int, []),
     'vxb_voxelize_launches': (c_int, []),
+    'vxb_profile_stage_count': (c_int, []),
+    'vxb_profile_stage_name': (ctypes.c_char_p, [c_int]),
+    'vxb_profile_enable': (c_int, [c_int]),
+    'vxb_profile_read': (c_int, [ctypes.POINTER(ctypes.c_double)]),
     'vxb_select_action_workspace_bytes': (c_size_t, [c_int, c_int]),
     'vxb_select_action_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -5,6 +5,7 @@
 #include "ops.cuh"
 #include "simt_gemm.cuh"
 #include "dispatch.cuh"
+#include <vector>
 
 namespace vxb {
 
@@ -155,6 +156,28 @@ static void carve_work(const Dims& m, int B, Arena& a, Work& w) {
   w.sim = a.get<float>(sim_floats(m, B));
   w.ss_part = a.get<float>((size_t)B * ss_chunks(m.V3) * 6 * 256);
 }
+
+// ---- stage profiler: CUDA events on the caller's stream at the stage boundaries of the forward
+// (bench.py's live roofline measurement; off by default, costs nothing when off)
+struct StageProfiler {
+  bool enabled = false;
+  std::vector<std::vector<cudaEvent_t>> calls;  // one event list per forward call
+  std::vector<cudaEvent_t>* cur = nullptr;
+  void begin_call() {
+    if (!enabled) return;
+    calls.emplace_back();
+    cur = &calls.back();
+  }
+  void mark(cudaStream_t st) {
+    if (!enabled || !cur) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    cur->push_back(e);
+  }
+};
+static StageProfiler g_prof;
+#define STAGE_MARK() g_prof.mark(st)
 
 // ---- small launch helpers -------------------------------------------------------------------
 static thread_local int g_launches = 0;  // kernels enqueued by the current API call
@@ -311,17 +334,21 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   const float slope = d->act_slope;
   const size_t MV = (size_t)B * m.V3;
 
+  STAGE_MARK();  // 0: input_preprocess
   // (1) d0 = act(conv1x1(grid))                                   perceiver_lang_io.py:357
   COUNT_LAUNCH();
   pointwise_conv_kernel<10><<<cdiv(MV, 64), 256, (64 * 10 + 64) * sizeof(float), st>>>(
       grid, P(VXB_P_INPRE_W), P(VXB_P_INPRE_B), w.d0, MV, 64, slope);
   VXB_LAUNCH_CHECK();
+  STAGE_MARK();  // 1: ss0 + maxpool
   // (2) feats[0:256] = [ss0(d0), maxpool(d0)]                      :360
   VXB_TRY(spatial_softmax(w.d0, B, m.V, m.V, m.V, 64, w.feats, m.flat, w.feats + 192, m.flat, w.ss_part, st));
+  STAGE_MARK();  // 2: patchify
   // (3) patchify conv k, stride s, replicate pad                   :363
   COUNT_LAUNCH();
   VXB_TRY(conv3d(w.d0, nullptr, 64, 0, pw.patch_wt, P(VXB_P_PATCH_B), w.patch, B, m.V, m.S, 64, m.k,
                  m.s, slope, mm, st));
+  STAGE_MARK();  // 3: token assembly
   // (4) proprio -> 64, language tokens -> C, token assembly + pos  :370-422
   COUNT_LAUNCH();
   VXB_TRY(linear(proprio, m.low, P(VXB_P_PROPRIO_W), m.low, P(VXB_P_PROPRIO_B), nullptr, 1, 0, w.pfeat,
@@ -342,6 +369,7 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
                                                   P(VXB_P_POS_ENCODING), w.ins, B, m.nl, m.T, m.C, 64);
   VXB_LAUNCH_CHECK();
 
+  STAGE_MARK();  // 4: transformer (cross + latent self-attention + FF)
   // (5) latents: x = repeat(latents) is never materialised; the first residual reads latents[m % L]   :425
   const int cq = m.ch * m.cdh;   // cross-attention inner dim
   const int lq = m.lh * m.ldh;   // latent-attention inner dim
@@ -392,6 +420,7 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
                            PL(l, VXB_PL_FF0_B), PL(l, VXB_PL_FF2_W), PL(l, VXB_PL_FF2_B), mm, st));
     }
   }
+  STAGE_MARK();  // 5: decoder cross attention + ss1
   // (8) decoder cross attention: queries = LN(ins) voxel rows only (the nl language rows are
   //     dropped right after, :444), context = LN_ctx(x); no residual              :440-448
   VXB_TRY(layernorm_batched(w.ins + (size_t)m.nl * m.C, (size_t)m.n * m.C, P(VXB_P_DEC_NORM_W),
@@ -411,18 +440,23 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   // (9) feats[256 : 256+4C] = [ss1(dec), maxpool(dec)]                           :451
   VXB_TRY(spatial_softmax(w.dec, B, m.S, m.S, m.S, m.C, w.feats + 256, m.flat, w.feats + 256 + 3 * m.C,
                           m.flat, w.ss_part, st));
+  STAGE_MARK();  // 6: up0 conv at S^3
   // (10) up0: conv k (C->64) at S^3, then [upsample x s o conv k] folded     :454
   COUNT_LAUNCH();
   VXB_TRY(conv3d(w.dec, nullptr, m.C, 0, pw.up0_wt, P(VXB_P_UP0_B), w.low, B, m.S, m.S, 64, m.k, 1, slope, mm, st));
+  STAGE_MARK();  // 7: folded upsample-conv
   COUNT_LAUNCH();
   VXB_TRY(upconv3d_folded(w.low, pw.up1_fold, P(VXB_P_UP1_B), w.u0, B, m.S, 64, 64, m.s, slope, mm, st));
+  STAGE_MARK();  // 8: final conv
   // (11) final: conv3 on cat[d0, u0] (128 -> 64)                               :462
   COUNT_LAUNCH();
   VXB_TRY(conv3d(w.d0, w.u0, 64, 64, pw.final_wt, P(VXB_P_FINAL_B), w.u, B, m.V, m.V, 64, 3, 1, slope, mm, st));
+  STAGE_MARK();  // 9: trans decoder
   // (12) trans decoder: conv3 64 -> 1, no activation                            :465
   COUNT_LAUNCH();
   conv3_to1_kernel<64><<<cdiv(MV, 32), 256, 0, st>>>(w.u, pw.trans_wt, P(VXB_P_TRANS_B), q_trans, B, m.V);
   VXB_LAUNCH_CHECK();
+  STAGE_MARK();  // 10: ss_final + heads
   // (13) feats[256+4C :] = [ss_final(u), maxpool(u)], MLP heads                 :470-483
   const int off = 256 + 4 * m.C;
   VXB_TRY(spatial_softmax(w.u, B, m.V, m.V, m.V, 64, w.feats + off, m.flat, w.feats + off + 192, m.flat,
@@ -449,6 +483,7 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
     VXB_TRY(linear(w.h2, 64, P(VXB_P_ARM_W), 64, P(VXB_P_ARM_B), nullptr, 1, 0, arm_out, 2, B, 2, 64, 1.f,
                    -1.f, VXB_MATH_FP32_SIMT, st));
   }
+  STAGE_MARK();  // end
   return VXB_OK;
 }
 
@@ -477,6 +512,7 @@ extern "C" int vxb_qnet_forward_f32(const vxb_qnet_desc* d, const void* const* p
     return VXB_E_WORKSPACE_TOO_SMALL;
   }
   g_launches = 0;
+  g_prof.begin_call();
   int rc = qnet_forward_impl(d, m, params, pw, w, grid, proprio, lang_tokens, B, q_trans, rot_grip,
                              collision, arm_out, (cudaStream_t)stream);
   g_last_launches = g_launches;
@@ -484,3 +520,35 @@ extern "C" int vxb_qnet_forward_f32(const vxb_qnet_desc* d, const void* const* p
 }
 
 extern "C" int vxb_last_launch_count(void) { return g_last_launches; }
+
+// ---- profiling API (bench.py): stage times of the forward measured with CUDA events on the stream
+extern "C" int vxb_profile_stage_count(void) { return 11; }
+extern "C" const char* vxb_profile_stage_name(int i) {
+  static const char* names[] = {"input_preprocess", "ss0_maxpool", "patchify", "token_assembly",
+                                "transformer", "decoder_attn_ss1", "up0_conv_lowres", "upconv_folded",
+                                "final_conv", "trans_decoder", "ss_final_heads"};
+  return (i >= 0 && i < 11) ? names[i] : "";
+}
+extern "C" int vxb_profile_enable(int on) {
+  g_prof.enabled = on != 0;
+  return VXB_OK;
+}
+// Synchronises on the recorded events, ADDS each stage's milliseconds into ms[0..10], returns the
+// number of forward calls consumed (events are destroyed).
+extern "C" int vxb_profile_read(double* ms) {
+  int ncalls = 0;
+  for (auto& ev : g_prof.calls) {
+    if (ev.size() == 12) {
+      cudaEventSynchronize(ev.back());
+      for (int i = 0; i < 11; ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ev[i], ev[i + 1]) == cudaSuccess && ms) ms[i] += t;
+      }
+      ++ncalls;
+    }
+    for (auto e : ev) cudaEventDestroy(e);
+  }
+  g_prof.calls.clear();
+  g_prof.cur = nullptr;
+  return ncalls;
+}
