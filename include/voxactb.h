@@ -186,11 +186,17 @@ int vxb_select_action_f32(const float* q_trans, const float* rot_grip, const flo
                           float* attention_xyz, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------ building blocks (exported for the per-op parity tests) */
-/* C[M,N] = act(alpha * A[M,K] * W[N,K]^T + bias[N]) (+ residual[(m % res_rows),N]); row-major fp32. */
+/* number of tcgen05 (split-bf16) GEMM kernels launched so far by this process: lets tests prove that
+ * VXB_MATH_BF16X3 really ran on the tensor cores and did not fall back to the FFMA path */
+long long vxb_umma_launch_count(void);
+
+/* C[M,N] = act(alpha * A[M,K] * W[N,K]^T + bias[N]) (+ residual[(m % res_rows),N]); row-major fp32.
+ * ws (vxb_linear_workspace_bytes) holds the bf16 hi/lo operand planes of the tcgen05 path. */
+size_t vxb_linear_workspace_bytes(int M, int N, int K);
 int vxb_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
                    const float* residual, int res_rows, float* C, int ldc,
                    int M, int N, int K, float alpha, float act_slope /* <0: no activation */,
-                   int math_mode, void* stream);
+                   int math_mode, void* ws, size_t ws_bytes, void* stream);
 /* rows of length n: y = (x-mean)/sqrt(var+1e-5)*w+b */
 int vxb_layernorm_f32(const float* x, const float* w, const float* b, float* y, int rows, int n,
                       void* stream);
@@ -203,14 +209,14 @@ int vxb_spatial_softmax_f32(const float* x, int B, int Dd, int Hh, int Ww, int C
                             void* stream);
 /* channels-last conv3d, replicate padding k/2, stride s, weight in PyTorch layout [Co,Ci,k,k,k];
  * x [B,Di,Di,Di,Ci] -> y [B,Do,Do,Do,Co]; ws >= vxb_conv3d_workspace_bytes. */
-size_t vxb_conv3d_workspace_bytes(int Ci, int Co, int k);
+size_t vxb_conv3d_workspace_bytes(int B, int Di, int Ci, int Co, int k);
 int vxb_conv3d_f32(const float* x, const float* w, const float* bias, float* y, int B, int Di,
                    int Ci, int Co, int k, int s, float act_slope, int math_mode, void* ws,
                    size_t ws_bytes, void* stream);
 /* fused conv(k,pad k/2,replicate) o trilinear-upsample(x s, align_corners=False): the second half of
  * Conv3DUpsampleBlock (network_utils.py:245-251) evaluated as s^3 polyphase 3x3x3 convolutions on
  * the low-resolution tensor.  x [B,S,S,S,Ci] -> y [B,S*s,S*s,S*s,Co]. */
-size_t vxb_upconv3d_workspace_bytes(int Ci, int Co, int k, int s);
+size_t vxb_upconv3d_workspace_bytes(int B, int S, int Ci, int Co, int k, int s);
 int vxb_upconv3d_f32(const float* x, const float* w, const float* bias, float* y, int B, int S,
                      int Ci, int Co, int k, int s, float act_slope, int math_mode, void* ws,
                      size_t ws_bytes, void* stream);

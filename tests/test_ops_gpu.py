@@ -11,7 +11,7 @@ from voxactb_b200 import _lib
 
 pytestmark = pytest.mark.gpu
 
-MODES = [_lib.MATH_FP32_SIMT]
+MODES = [_lib.MATH_FP32_SIMT, _lib.MATH_BF16X3]
 TOL = {_lib.MATH_FP32_SIMT: 2e-5, _lib.MATH_BF16X3: 1e-4}
 
 
@@ -19,9 +19,24 @@ def ws(nbytes):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device='cuda')
 
 
+class tensor_core_check:
+    """In BF16X3 mode the op must have launched at least one tcgen05 GEMM (no silent FFMA fallback)."""
+
+    def __init__(self, lib, mode, expect=True):
+        self.lib, self.mode, self.expect = lib, mode, expect
+
+    def __enter__(self):
+        self.before = self.lib.vxb_umma_launch_count()
+
+    def __exit__(self, *exc):
+        if exc[0] is None and self.mode == _lib.MATH_BF16X3 and self.expect:
+            assert self.lib.vxb_umma_launch_count() > self.before, 'BF16X3 mode did not use tcgen05'
+
+
 @pytest.mark.parametrize('mode', MODES)
 @pytest.mark.parametrize('M,N,K', [(300, 128, 512), (77, 128, 512), (2048, 4096, 512), (16, 220, 64),
-                                   (5, 64, 7), (1000, 64, 64), (129, 65, 33)])
+                                   (5, 64, 7), (1000, 64, 64), (129, 65, 33), (4096, 512, 2048),
+                                   (1000, 1024, 520), (8077, 128, 128)])
 def test_linear(cuda_lib, mode, M, N, K):
     g = torch.Generator().manual_seed(M + N + K)
     A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g)
@@ -29,15 +44,19 @@ def test_linear(cuda_lib, mode, M, N, K):
     ref = F.leaky_relu(F.linear(A, W, b) * 1.0, 0.02) + R
     Ac, Wc, bc, Rc = A.cuda(), W.cuda(), b.cuda(), R.cuda()
     C = torch.empty(M, N, device='cuda')
-    _lib.check(cuda_lib.vxb_linear_f32(_lib.ptr(Ac), K, _lib.ptr(Wc), K, _lib.ptr(bc), _lib.ptr(Rc), M,
-                                       _lib.ptr(C), N, M, N, K, 1.0, 0.02, mode, _lib.stream()), 'linear')
+    wk = ws(cuda_lib.vxb_linear_workspace_bytes(M, N, K))
+    with tensor_core_check(cuda_lib, mode, expect=M >= 128 and N >= 32 and K >= 32):
+        _lib.check(cuda_lib.vxb_linear_f32(_lib.ptr(Ac), K, _lib.ptr(Wc), K, _lib.ptr(bc), _lib.ptr(Rc), M,
+                                           _lib.ptr(C), N, M, N, K, 1.0, 0.02, mode, _lib.ptr(wk), wk.numel(),
+                                           _lib.stream()), 'linear')
     assert util.rel_err(C, ref) < TOL[mode]
     # broadcast residual rows (latents) + alpha + no activation
     Rb = torch.randn(3, N, generator=g)
     ref2 = 0.5 * F.linear(A, W) + Rb[torch.arange(M) % 3]
     Rbc = Rb.cuda()
     _lib.check(cuda_lib.vxb_linear_f32(_lib.ptr(Ac), K, _lib.ptr(Wc), K, None, _lib.ptr(Rbc), 3,
-                                       _lib.ptr(C), N, M, N, K, 0.5, -1.0, mode, _lib.stream()), 'linear')
+                                       _lib.ptr(C), N, M, N, K, 0.5, -1.0, mode, _lib.ptr(wk), wk.numel(),
+                                       _lib.stream()), 'linear')
     assert util.rel_err(C, ref2) < TOL[mode]
 
 
@@ -79,11 +98,12 @@ def test_conv3d(cuda_lib, mode, Di, Ci, Co, k, s):
     b = torch.randn(Co, generator=g)
     ref = qnet_oracle.conv3d_block(x, w, b, s, 'lrelu').permute(0, 2, 3, 4, 1)
     y = torch.empty(ref.shape, device='cuda')
-    wk = ws(cuda_lib.vxb_conv3d_workspace_bytes(Ci, Co, k))
+    wk = ws(cuda_lib.vxb_conv3d_workspace_bytes(2, Di, Ci, Co, k))
     xc, wc, bc = x.permute(0, 2, 3, 4, 1).contiguous().cuda(), w.cuda(), b.cuda()
-    _lib.check(cuda_lib.vxb_conv3d_f32(_lib.ptr(xc), _lib.ptr(wc),
-                                       _lib.ptr(bc), _lib.ptr(y), 2, Di, Ci, Co, k, s, 0.02, mode,
-                                       _lib.ptr(wk), wk.numel(), _lib.stream()), 'conv3d')
+    with tensor_core_check(cuda_lib, mode, expect=s == 1 and Ci % 64 == 0 and Co == 64):
+        _lib.check(cuda_lib.vxb_conv3d_f32(_lib.ptr(xc), _lib.ptr(wc),
+                                           _lib.ptr(bc), _lib.ptr(y), 2, Di, Ci, Co, k, s, 0.02, mode,
+                                           _lib.ptr(wk), wk.numel(), _lib.stream()), 'conv3d')
     assert util.rel_err(y, ref) < TOL[mode]
 
 
@@ -100,11 +120,12 @@ def test_upconv3d_equals_upsample_then_conv(cuda_lib, mode, S, k, s):
     up = F.interpolate(x, scale_factor=s, mode='trilinear', align_corners=False)
     ref = qnet_oracle.conv3d_block(up, w, b, 1, 'lrelu').permute(0, 2, 3, 4, 1)
     y = torch.empty(ref.shape, device='cuda')
-    wk = ws(cuda_lib.vxb_upconv3d_workspace_bytes(Ci, Co, k, s))
+    wk = ws(cuda_lib.vxb_upconv3d_workspace_bytes(2, S, Ci, Co, k, s))
     xc, wc, bc = x.permute(0, 2, 3, 4, 1).contiguous().cuda(), w.cuda(), b.cuda()
-    _lib.check(cuda_lib.vxb_upconv3d_f32(_lib.ptr(xc), _lib.ptr(wc),
-                                         _lib.ptr(bc), _lib.ptr(y), 2, S, Ci, Co, k, s, 0.02, mode,
-                                         _lib.ptr(wk), wk.numel(), _lib.stream()), 'upconv3d')
+    with tensor_core_check(cuda_lib, mode):
+        _lib.check(cuda_lib.vxb_upconv3d_f32(_lib.ptr(xc), _lib.ptr(wc),
+                                             _lib.ptr(bc), _lib.ptr(y), 2, S, Ci, Co, k, s, 0.02, mode,
+                                             _lib.ptr(wk), wk.numel(), _lib.stream()), 'upconv3d')
     assert util.rel_err(y, ref) < max(TOL[mode], 3e-5)
 
 

@@ -56,16 +56,19 @@ SIGNATURES = {
     'vxb_select_action_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_size_t, c_void_p]),
+    'vxb_umma_launch_count': (c_ll, []),
+    'vxb_linear_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'vxb_linear_f32': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
-                               c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
+                               c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p, c_size_t,
+                               c_void_p]),
     'vxb_layernorm_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'vxb_spatial_softmax_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'vxb_spatial_softmax_f32': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                         c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
-    'vxb_conv3d_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'vxb_conv3d_workspace_bytes': (c_size_t, [c_int] * 5),
     'vxb_conv3d_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),
-    'vxb_upconv3d_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'vxb_upconv3d_workspace_bytes': (c_size_t, [c_int] * 6),
     'vxb_upconv3d_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                  c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),
     'vxb_attention_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),

@@ -121,12 +121,20 @@ extern "C" int vxb_select_action_f32(const float* q_trans, const float* rot_grip
 }
 
 // ---------------------------------------------------------------- building blocks
+extern "C" long long vxb_umma_launch_count(void) { return umma::launches(); }
+
+extern "C" size_t vxb_linear_workspace_bytes(int M, int N, int K) {
+  return umma::linear_scratch_bytes(M, N, K, true) + 256;
+}
+
 extern "C" int vxb_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
                               const float* residual, int res_rows, float* C, int ldc, int M, int N,
-                              int K, float alpha, float act_slope, int math_mode, void* stream) {
+                              int K, float alpha, float act_slope, int math_mode, void* ws,
+                              size_t ws_bytes, void* stream) {
   VXB_CHECK_ARG(A && W && C && M > 0 && N > 0 && K >= 0, "linear: bad arguments");
+  Arena scratch(ws, ws_bytes);
   return linear(A, lda, W, ldw, bias, residual, res_rows, ldc, C, ldc, M, N, K, alpha, act_slope,
-                math_mode, (cudaStream_t)stream);
+                math_mode, (cudaStream_t)stream, ws ? &scratch : nullptr, nullptr);
 }
 
 extern "C" int vxb_layernorm_f32(const float* x, const float* w, const float* b, float* y, int rows,
@@ -163,15 +171,18 @@ extern "C" int vxb_spatial_softmax_f32(const float* x, int B, int Dd, int Hh, in
   return VXB_OK;
 }
 
-extern "C" size_t vxb_conv3d_workspace_bytes(int Ci, int Co, int k) {
-  return align_up((size_t)Ci * Co * k * k * k * sizeof(float), 256);
+static size_t conv_w_bytes(int Ci, int Co, int k) { return align_up((size_t)Ci * Co * k * k * k * sizeof(float), 256); }
+
+extern "C" size_t vxb_conv3d_workspace_bytes(int B, int Di, int Ci, int Co, int k) {
+  // tap-major fp32 weight + (bf16x3 path) its planes and the padded input planes
+  return 2 * conv_w_bytes(Ci, Co, k) + umma::conv3d_scratch_bytes(B, Di, Ci, 0, k) + 1024;
 }
 
 extern "C" int vxb_conv3d_f32(const float* x, const float* w, const float* bias, float* y, int B,
                               int Di, int Ci, int Co, int k, int s, float act_slope, int math_mode,
                               void* ws, size_t ws_bytes, void* stream) {
   VXB_CHECK_ARG(x && w && y && ws && B > 0 && Di > 0 && (k & 1) && s > 0, "conv3d: bad arguments");
-  if (ws_bytes < vxb_conv3d_workspace_bytes(Ci, Co, k)) {
+  if (ws_bytes < vxb_conv3d_workspace_bytes(B, Di, Ci, Co, k)) {
     set_error("conv3d: workspace too small");
     return VXB_E_WORKSPACE_TOO_SMALL;
   }
@@ -180,12 +191,16 @@ extern "C" int vxb_conv3d_f32(const float* x, const float* w, const float* bias,
   conv_weight_to_tapmajor_kernel<<<cdiv((size_t)Co * Ci * k3, 256), 256, 0, st>>>(w, (float*)ws, Co, Ci, k3);
   VXB_LAUNCH_CHECK();
   const int Do = (Di + 2 * (k / 2) - k) / s + 1;
-  return conv3d(x, nullptr, Ci, 0, (const float*)ws, bias, y, B, Di, Do, Co, k, s, act_slope, math_mode, st);
+  Arena scratch((char*)ws + conv_w_bytes(Ci, Co, k), ws_bytes - conv_w_bytes(Ci, Co, k));
+  return conv3d(x, nullptr, Ci, 0, (const float*)ws, bias, y, B, Di, Do, Co, k, s, act_slope, math_mode, st,
+                &scratch, nullptr);
 }
 
-extern "C" size_t vxb_upconv3d_workspace_bytes(int Ci, int Co, int k, int s) {
+static size_t fold_w_bytes(int Ci, int Co, int s) { return align_up((size_t)s * s * s * Co * 27 * Ci * sizeof(float), 256); }
+
+extern "C" size_t vxb_upconv3d_workspace_bytes(int B, int S, int Ci, int Co, int k, int s) {
   (void)k;
-  return align_up((size_t)s * s * s * Co * 27 * Ci * sizeof(float), 256);
+  return 2 * fold_w_bytes(Ci, Co, s) + umma::upconv_scratch_bytes(B, S, Ci) + 1024;
 }
 
 extern "C" int vxb_upconv3d_f32(const float* x, const float* w, const float* bias, float* y, int B,
@@ -196,7 +211,7 @@ extern "C" int vxb_upconv3d_f32(const float* x, const float* w, const float* bia
     set_error("upconv3d: folding needs k/2 <= (s+1)/2 (k=%d, s=%d)", k, s);
     return VXB_E_UNSUPPORTED_SHAPE;
   }
-  if (ws_bytes < vxb_upconv3d_workspace_bytes(Ci, Co, k, s)) {
+  if (ws_bytes < vxb_upconv3d_workspace_bytes(B, S, Ci, Co, k, s)) {
     set_error("upconv3d: workspace too small");
     return VXB_E_WORKSPACE_TOO_SMALL;
   }
@@ -204,7 +219,8 @@ extern "C" int vxb_upconv3d_f32(const float* x, const float* w, const float* bia
   const size_t total = (size_t)s * s * s * Co * 27 * Ci;
   fold_upconv_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(w, (float*)ws, Co, Ci, k, s);
   VXB_LAUNCH_CHECK();
-  return upconv3d_folded(x, (const float*)ws, bias, y, B, S, Ci, Co, s, act_slope, math_mode, st);
+  Arena scratch((char*)ws + fold_w_bytes(Ci, Co, s), ws_bytes - fold_w_bytes(Ci, Co, s));
+  return upconv3d_folded(x, (const float*)ws, bias, y, B, S, Ci, Co, s, act_slope, math_mode, st, &scratch, nullptr);
 }
 
 extern "C" size_t vxb_attention_workspace_bytes(int B, int H, int Nq, int Nk) {

@@ -3,14 +3,20 @@
 #include "common.cuh"
 #include "simt_gemm.cuh"
 #include "ops.cuh"
+#include "umma_host.cuh"
 
 namespace vxb {
 
 // C[M,N] = act(alpha * A[M,K] W[N,K]^T + bias) + residual[(m % res_rows)]
 inline int linear(const float* A, int lda, const float* W, int ldw, const float* bias,
                   const float* residual, int res_rows, int ldr, float* C, int ldc, int M, int N,
-                  int K, float alpha, float act_slope, int math_mode, cudaStream_t st) {
-  (void)math_mode;
+                  int K, float alpha, float act_slope, int math_mode, cudaStream_t st,
+                  Arena* scratch = nullptr, const umma::Planes* Wpre = nullptr) {
+  if (math_mode == VXB_MATH_BF16X3 && scratch && M >= 128 && N >= 32 && K >= 32) {
+    Arena local(scratch->base, scratch->cap);   // every op bumps from the start of the scratch arena
+    return umma::linear_f32(A, lda, W, ldw, Wpre, bias, residual, res_rows, ldr, C, ldc, M, N, K, alpha,
+                            act_slope, local, st);
+  }
   GemmParams p;
   gemm_params_init(p);
   p.M = M; p.N = N; p.K = K;
@@ -27,8 +33,27 @@ inline int linear(const float* A, int lda, const float* W, int ldw, const float*
 // wt tap-major [Co][k^3][C0+C1]; out [B,Do^3,Co]
 inline int conv3d(const float* src0, const float* src1, int C0, int C1, const float* wt,
                   const float* bias, float* out, int B, int Di, int Do, int Co, int k, int stride,
-                  float act_slope, int math_mode, cudaStream_t st) {
-  (void)math_mode;
+                  float act_slope, int math_mode, cudaStream_t st, Arena* scratch = nullptr,
+                  const umma::Planes* Wpre = nullptr) {
+  if (math_mode == VXB_MATH_BF16X3 && scratch && stride == 1 && Di == Do && C0 % 64 == 0 && C1 % 64 == 0 &&
+      Co == 64) {
+    Arena local(scratch->base, scratch->cap);
+    umma::Planes wp;
+    const long long Kt = (long long)k * k * k * (C0 + C1);
+    if (Wpre) {
+      wp = *Wpre;
+    } else {
+      wp.hi = local.get<__nv_bfloat16>((size_t)Co * Kt);
+      wp.lo = local.get<__nv_bfloat16>((size_t)Co * Kt);
+      wp.ld = Kt;
+      if (!local.ok) {
+        set_error("conv3d: scratch too small");
+        return VXB_E_WORKSPACE_TOO_SMALL;
+      }
+      VXB_TRY(umma::split_rows(wt, Kt, Co, (int)Kt, wp, st));
+    }
+    return umma::conv3d_f32(src0, src1, C0, C1, wp, bias, out, B, Di, Co, k, act_slope, local, st);
+  }
   const int Cin = C0 + C1;
   if (Cin % GBK != 0 || C0 % GBK != 0) {
     set_error("conv3d: channel counts must be multiples of %d (C0=%d, C1=%d)", GBK, C0, C1);
@@ -49,8 +74,25 @@ inline int conv3d(const float* src0, const float* src1, int C0, int C1, const fl
 // phase r written at fine voxel s*q + r.  wfold [s^3][Co][27][Ci]
 inline int upconv3d_folded(const float* low, const float* wfold, const float* bias, float* out,
                            int B, int S, int Ci, int Co, int s, float act_slope, int math_mode,
-                           cudaStream_t st) {
-  (void)math_mode;
+                           cudaStream_t st, Arena* scratch = nullptr, const umma::Planes* Wpre = nullptr) {
+  if (math_mode == VXB_MATH_BF16X3 && scratch && Ci % 64 == 0 && Co == 64) {
+    Arena local(scratch->base, scratch->cap);
+    umma::Planes wp;
+    const long long Kt = 27ll * Ci, Nt = (long long)s * s * s * Co;
+    if (Wpre) {
+      wp = *Wpre;
+    } else {
+      wp.hi = local.get<__nv_bfloat16>((size_t)Nt * Kt);
+      wp.lo = local.get<__nv_bfloat16>((size_t)Nt * Kt);
+      wp.ld = Kt;
+      if (!local.ok) {
+        set_error("upconv3d: scratch too small");
+        return VXB_E_WORKSPACE_TOO_SMALL;
+      }
+      VXB_TRY(umma::split_rows(wfold, Kt, Nt, (int)Kt, wp, st));
+    }
+    return umma::upconv_f32(low, wp, bias, out, B, S, Ci, Co, s, act_slope, local, st);
+  }
   GemmParams p;
   gemm_params_init(p);
   p.M = B * S * S * S; p.N = Co; p.K = 27 * Ci;

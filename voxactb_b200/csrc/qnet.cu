@@ -83,8 +83,19 @@ struct Prepared {
   float* trans_wt;   // [27][64]
   float* q_cross;    // [L][ch*cdh]  = to_q(LN(latents)), batch independent
   float* lat_norm;   // [L][D] scratch for the above
+  // bf16 hi/lo planes of every weight that feeds a tcgen05 GEMM, keyed by the fp32 weight pointer
+  std::vector<std::pair<const float*, umma::Planes>> planes;
 };
-static void carve_prepared(const Dims& m, Arena& a, Prepared& p) {
+struct WeightSpec { const float* w; long long rows, cols; };
+static void add_planes(Arena& a, Prepared& p, const float* w, long long rows, long long cols) {
+  umma::Planes pl;
+  pl.ld = umma::pad8(cols);
+  pl.hi = a.get<__nv_bfloat16>((size_t)rows * pl.ld);
+  pl.lo = a.get<__nv_bfloat16>((size_t)rows * pl.ld);
+  p.planes.push_back({w, pl});
+}
+static void weight_specs(const Dims& m, const void* const* params, const Prepared& p, std::vector<WeightSpec>& v);
+static void carve_prepared(const Dims& m, Arena& a, Prepared& p, const void* const* params = nullptr) {
   const int k3 = m.k * m.k * m.k;
   p.patch_wt = a.get<float>((size_t)64 * k3 * 64);
   p.up0_wt = a.get<float>((size_t)64 * k3 * m.C);
@@ -93,6 +104,38 @@ static void carve_prepared(const Dims& m, Arena& a, Prepared& p) {
   p.trans_wt = a.get<float>((size_t)27 * 64);
   p.q_cross = a.get<float>((size_t)m.L * m.ch * m.cdh);
   p.lat_norm = a.get<float>((size_t)m.L * m.D);
+  std::vector<WeightSpec> specs;
+  weight_specs(m, params, p, specs);
+  p.planes.clear();
+  for (auto& sp : specs) add_planes(a, p, sp.w, sp.rows, sp.cols);
+}
+// every weight matrix [rows, cols] (K-major) consumed by a tensor-core GEMM.  With params == nullptr
+// only the sizes matter (arena sizing); keys are then null.
+static void weight_specs(const Dims& m, const void* const* params, const Prepared& p, std::vector<WeightSpec>& v) {
+  auto P = [&](int slot) { return params ? (const float*)params[slot] : nullptr; };
+  auto PL = [&](int layer, int slot) {
+    return params ? (const float*)params[VXB_P_FIXED_COUNT + layer * VXB_P_LAYER_STRIDE + slot] : nullptr;
+  };
+  const long long k3 = (long long)m.k * m.k * m.k, cq = m.ch * m.cdh, lq = m.lh * m.ldh;
+  v.push_back({p.up0_wt, 64, k3 * m.C});
+  v.push_back({p.up1_fold, (long long)m.s * m.s * m.s * 64, 27 * 64});
+  v.push_back({p.final_wt, 64, 27 * 128});
+  v.push_back({P(VXB_P_LANG_W), m.C, 512});
+  v.push_back({P(VXB_P_CROSS_Q_W), cq, m.D});
+  v.push_back({P(VXB_P_CROSS_KV_W), 2 * cq, m.C});
+  v.push_back({P(VXB_P_CROSS_OUT_W), m.D, cq});
+  v.push_back({P(VXB_P_CROSS_FF0_W), 8ll * m.D, m.D});
+  v.push_back({P(VXB_P_CROSS_FF2_W), m.D, 4ll * m.D});
+  v.push_back({P(VXB_P_DEC_Q_W), cq, m.C});
+  v.push_back({P(VXB_P_DEC_KV_W), 2 * cq, m.D});
+  v.push_back({P(VXB_P_DEC_OUT_W), m.C, cq});
+  for (int l = 0; l < m.depth; ++l) {
+    v.push_back({PL(l, VXB_PL_Q_W), lq, m.D});
+    v.push_back({PL(l, VXB_PL_KV_W), 2 * lq, m.D});
+    v.push_back({PL(l, VXB_PL_OUT_W), m.D, lq});
+    v.push_back({PL(l, VXB_PL_FF0_W), 8ll * m.D, m.D});
+    v.push_back({PL(l, VXB_PL_FF2_W), m.D, 4ll * m.D});
+  }
 }
 
 // ---- per-call workspace
@@ -117,6 +160,8 @@ struct Work {
   float *h0, *h1, *h2, *rgc;     // head activations
   float *sim;                    // attention scores
   float *ss_part;                // spatial softmax partials
+  char *scratch;                 // operand planes of the tcgen05 path
+  size_t scratch_bytes;
 };
 static int ss_chunks(size_t P) { return (int)std::min<size_t>(1024, std::max<size_t>(1, (P + 1023) / 1024)); }
 
@@ -155,6 +200,15 @@ static void carve_work(const Dims& m, int B, Arena& a, Work& w) {
   w.rgc = a.get<float>((size_t)B * (3 * m.R + m.G + m.Cc));
   w.sim = a.get<float>(sim_floats(m, B));
   w.ss_part = a.get<float>((size_t)B * ss_chunks(m.V3) * 6 * 256);
+  // scratch for operand planes: the largest of the GEMM / conv shapes of the forward
+  size_t sb = 0;
+  sb = std::max(sb, umma::linear_scratch_bytes((long long)B * m.L, 8 * m.D, 4 * m.D, false));
+  sb = std::max(sb, umma::linear_scratch_bytes((long long)B * m.n, 8 * m.D, std::max(m.C, 512), false));
+  sb = std::max(sb, umma::conv3d_scratch_bytes(B, m.V, 64, 64, 3));
+  sb = std::max(sb, umma::conv3d_scratch_bytes(B, m.S, m.C, 0, m.k));
+  sb = std::max(sb, umma::upconv_scratch_bytes(B, m.S, 64));
+  w.scratch_bytes = sb + 4096;
+  w.scratch = a.get<char>(w.scratch_bytes);
 }
 
 // ---- stage profiler: CUDA events on the caller's stream at the stage boundaries of the forward
@@ -222,21 +276,41 @@ static int attention(const float* q, int ldq, long long qbs, const float* k, con
                                 sim, math_mode, st);
 }
 
+// ---- per-call context: math mode, stream, scratch arena for operand planes, pre-split weights
+struct Ctx {
+  int mm;
+  cudaStream_t st;
+  Arena scratch;
+  std::vector<std::pair<const float*, umma::Planes>> wp;
+  Ctx(int mode, cudaStream_t s, void* scr, size_t scr_bytes) : mm(mode), st(s), scratch(scr, scr_bytes) {}
+  const umma::Planes* find(const float* w) const {
+    for (auto& e : wp)
+      if (e.first == w) return &e.second;
+    return nullptr;
+  }
+};
+static int lin(Ctx& cx, const float* A, int lda, const float* W, int ldw, const float* bias, const float* residual,
+               int res_rows, int ldr, float* C, int ldc, int M, int N, int K, float alpha, float act_slope,
+               int mode) {
+  COUNT_LAUNCH();
+  return linear(A, lda, W, ldw, bias, residual, res_rows, ldr, C, ldc, M, N, K, alpha, act_slope, mode, cx.st,
+                cx.scratch.base ? &cx.scratch : nullptr, cx.find(W));
+}
+
 // x = x + FF(LN(x)), FeedForward = Linear(D,8D) -> GEGLU -> Linear(4D,D)  (perceiver_lang_io.py:74-90)
-static int feed_forward(const Dims& m, int B, Work& w, const float* nw, const float* nb,
-                        const float* w0, const float* b0, const float* w2, const float* b2,
-                        int math_mode, cudaStream_t st) {
+static int feed_forward(Ctx& cx, const Dims& m, int B, Work& w, const float* nw, const float* nb,
+                        const float* w0, const float* b0, const float* w2, const float* b2) {
+  const int math_mode = cx.mm;
+  cudaStream_t st = cx.st;
   const size_t rows = (size_t)B * m.L;
   VXB_TRY(layernorm(w.x, nw, nb, w.xn, rows, m.D, st));
-  COUNT_LAUNCH();
-  VXB_TRY(linear(w.xn, m.D, w0, m.D, b0, nullptr, 1, 0, w.ffh, 8 * m.D, (int)rows, 8 * m.D, m.D, 1.f,
-                 -1.f, math_mode, st));
+    VXB_TRY(lin(cx, w.xn, m.D, w0, m.D, b0, nullptr, 1, 0, w.ffh, 8 * m.D, (int)rows, 8 * m.D, m.D, 1.f,
+                 -1.f, math_mode));
   COUNT_LAUNCH();
   geglu_kernel<<<148 * 8, 256, 0, st>>>(w.ffh, w.ffg, rows, 4 * m.D);
   VXB_LAUNCH_CHECK();
-  COUNT_LAUNCH();
-  VXB_TRY(linear(w.ffg, 4 * m.D, w2, 4 * m.D, b2, w.x, (int)rows, m.D, w.x, m.D, (int)rows, m.D,
-                 4 * m.D, 1.f, -1.f, math_mode, st));
+    VXB_TRY(lin(cx, w.ffg, 4 * m.D, w2, 4 * m.D, b2, w.x, (int)rows, m.D, w.x, m.D, (int)rows, m.D,
+                 4 * m.D, 1.f, -1.f, math_mode));
   return VXB_OK;
 }
 
@@ -298,7 +372,7 @@ extern "C" int vxb_qnet_prepare(const vxb_qnet_desc* d, const void* const* param
   VXB_CHECK_ARG(params && prepared, "qnet_prepare: null pointer");
   Arena a(prepared, prepared_bytes);
   Prepared p;
-  carve_prepared(m, a, p);
+  carve_prepared(m, a, p, params);
   if (!a.ok) {
     set_error("qnet_prepare: prepared arena too small (%zu < %zu)", prepared_bytes, a.off);
     return VXB_E_WORKSPACE_TOO_SMALL;
@@ -319,6 +393,13 @@ extern "C" int vxb_qnet_prepare(const vxb_qnet_desc* d, const void* const* param
   VXB_TRY(layernorm(P(VXB_P_LATENTS), P(VXB_P_CROSS_NORM_W), P(VXB_P_CROSS_NORM_B), p.lat_norm, m.L, m.D, st));
   VXB_TRY(linear(p.lat_norm, m.D, P(VXB_P_CROSS_Q_W), m.D, nullptr, nullptr, 1, 0, p.q_cross,
                  m.ch * m.cdh, m.L, m.ch * m.cdh, m.D, 1.f, -1.f, VXB_MATH_FP32_SIMT, st));
+  // bf16 hi/lo planes of the GEMM weights (after the re-layouts above: same stream)
+  {
+    std::vector<WeightSpec> specs;
+    weight_specs(m, params, p, specs);
+    for (size_t i = 0; i < specs.size(); ++i)
+      VXB_TRY(umma::split_rows(specs[i].w, specs[i].cols, specs[i].rows, (int)specs[i].cols, p.planes[i].second, st));
+  }
   return VXB_OK;
 }
 
@@ -326,6 +407,8 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
                              const Prepared& pw, Work& w, const float* grid, const float* proprio,
                              const float* lang_tokens, int B, float* q_trans, float* rot_grip,
                              float* collision, float* arm_out, cudaStream_t st) {
+  Ctx cx(d->math_mode, st, d->math_mode == VXB_MATH_BF16X3 ? w.scratch : nullptr, w.scratch_bytes);
+  cx.wp = pw.planes;
   auto P = [&](int slot) { return (const float*)params[slot]; };
   auto PL = [&](int layer, int slot) {
     return (const float*)params[VXB_P_FIXED_COUNT + layer * VXB_P_LAYER_STRIDE + slot];
@@ -347,22 +430,19 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   // (3) patchify conv k, stride s, replicate pad                   :363
   COUNT_LAUNCH();
   VXB_TRY(conv3d(w.d0, nullptr, 64, 0, pw.patch_wt, P(VXB_P_PATCH_B), w.patch, B, m.V, m.S, 64, m.k,
-                 m.s, slope, mm, st));
+                 m.s, slope, mm, st, nullptr, nullptr));
   STAGE_MARK();  // 3: token assembly
   // (4) proprio -> 64, language tokens -> C, token assembly + pos  :370-422
-  COUNT_LAUNCH();
-  VXB_TRY(linear(proprio, m.low, P(VXB_P_PROPRIO_W), m.low, P(VXB_P_PROPRIO_B), nullptr, 1, 0, w.pfeat,
-                 64, B, 64, m.low, 1.f, slope, VXB_MATH_FP32_SIMT, st));
+    VXB_TRY(lin(cx, proprio, m.low, P(VXB_P_PROPRIO_W), m.low, P(VXB_P_PROPRIO_B), nullptr, 1, 0, w.pfeat,
+                 64, B, 64, m.low, 1.f, slope, VXB_MATH_FP32_SIMT));
   if (d->no_language) {
     // lang_preprocess(0) = bias
     VXB_CUDA(cudaMemsetAsync(w.lang_lin, 0, (size_t)B * m.nl * m.C * sizeof(float), st));
-    COUNT_LAUNCH();
-    VXB_TRY(linear(w.lang_lin, m.C, P(VXB_P_LANG_W), d->lang_emb_dim, P(VXB_P_LANG_B), nullptr, 1, 0,
-                   w.lang_lin, m.C, B * m.nl, m.C, 0, 1.f, -1.f, VXB_MATH_FP32_SIMT, st));
+        VXB_TRY(lin(cx, w.lang_lin, m.C, P(VXB_P_LANG_W), d->lang_emb_dim, P(VXB_P_LANG_B), nullptr, 1, 0,
+                   w.lang_lin, m.C, B * m.nl, m.C, 0, 1.f, -1.f, VXB_MATH_FP32_SIMT));
   } else {
-    COUNT_LAUNCH();
-    VXB_TRY(linear(lang_tokens, d->lang_emb_dim, P(VXB_P_LANG_W), d->lang_emb_dim, P(VXB_P_LANG_B),
-                   nullptr, 1, 0, w.lang_lin, m.C, B * m.nl, m.C, d->lang_emb_dim, 1.f, -1.f, mm, st));
+        VXB_TRY(lin(cx, lang_tokens, d->lang_emb_dim, P(VXB_P_LANG_W), d->lang_emb_dim, P(VXB_P_LANG_B),
+                   nullptr, 1, 0, w.lang_lin, m.C, B * m.nl, m.C, d->lang_emb_dim, 1.f, -1.f, mm));
   }
   COUNT_LAUNCH();
   assemble_tokens_kernel<<<148 * 8, 256, 0, st>>>(w.lang_lin, w.patch, w.pfeat, nullptr,
@@ -376,9 +456,8 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   for (int it = 0; it < d->iterations; ++it) {
     // (6) encoder cross attention: x = Attn(LN(x), ctx=LN_ctx(ins)) + x      :431
     VXB_TRY(layernorm(w.ins, P(VXB_P_CROSS_NORMCTX_W), P(VXB_P_CROSS_NORMCTX_B), w.ctx_n, (size_t)B * m.n, m.C, st));
-    COUNT_LAUNCH();
-    VXB_TRY(linear(w.ctx_n, m.C, P(VXB_P_CROSS_KV_W), m.C, nullptr, nullptr, 1, 0, w.kv_c, 2 * cq,
-                   B * m.n, 2 * cq, m.C, 1.f, -1.f, mm, st));
+        VXB_TRY(lin(cx, w.ctx_n, m.C, P(VXB_P_CROSS_KV_W), m.C, nullptr, nullptr, 1, 0, w.kv_c, 2 * cq,
+                   B * m.n, 2 * cq, m.C, 1.f, -1.f, mm));
     const float* qx;
     long long qbs;
     if (it == 0) {
@@ -386,38 +465,33 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
       qbs = 0;
     } else {
       VXB_TRY(layernorm(w.x, P(VXB_P_CROSS_NORM_W), P(VXB_P_CROSS_NORM_B), w.xn, (size_t)B * m.L, m.D, st));
-      COUNT_LAUNCH();
-      VXB_TRY(linear(w.xn, m.D, P(VXB_P_CROSS_Q_W), m.D, nullptr, nullptr, 1, 0, w.qb, cq, B * m.L, cq,
-                     m.D, 1.f, -1.f, mm, st));
+            VXB_TRY(lin(cx, w.xn, m.D, P(VXB_P_CROSS_Q_W), m.D, nullptr, nullptr, 1, 0, w.qb, cq, B * m.L, cq,
+                     m.D, 1.f, -1.f, mm));
       qx = w.qb;
       qbs = (long long)m.L * cq;
     }
     VXB_TRY(attention(qx, cq, qbs, w.kv_c, w.kv_c + cq, 2 * cq, (long long)m.n * 2 * cq, w.att, cq,
                       (long long)m.L * cq, B, m.ch, m.L, m.n, m.cdh, 1.f / sqrtf((float)m.cdh), w.sim,
                       mm, st));
-    COUNT_LAUNCH();
-    VXB_TRY(linear(w.att, cq, P(VXB_P_CROSS_OUT_W), cq, P(VXB_P_CROSS_OUT_B),
+        VXB_TRY(lin(cx, w.att, cq, P(VXB_P_CROSS_OUT_W), cq, P(VXB_P_CROSS_OUT_B),
                    it == 0 ? P(VXB_P_LATENTS) : w.x, it == 0 ? m.L : B * m.L, m.D, w.x, m.D, B * m.L,
-                   m.D, cq, 1.f, -1.f, mm, st));
-    VXB_TRY(feed_forward(m, B, w, P(VXB_P_CROSS_FF_NORM_W), P(VXB_P_CROSS_FF_NORM_B), P(VXB_P_CROSS_FF0_W),
-                         P(VXB_P_CROSS_FF0_B), P(VXB_P_CROSS_FF2_W), P(VXB_P_CROSS_FF2_B), mm, st));
+                   m.D, cq, 1.f, -1.f, mm));
+    VXB_TRY(feed_forward(cx, m, B, w, P(VXB_P_CROSS_FF_NORM_W), P(VXB_P_CROSS_FF_NORM_B), P(VXB_P_CROSS_FF0_W),
+                         P(VXB_P_CROSS_FF0_B), P(VXB_P_CROSS_FF2_W), P(VXB_P_CROSS_FF2_B)));
     // (7) latent self-attention stack                                         :435-437
     for (int l = 0; l < m.depth; ++l) {
       VXB_TRY(layernorm(w.x, PL(l, VXB_PL_ATTN_NORM_W), PL(l, VXB_PL_ATTN_NORM_B), w.xn, (size_t)B * m.L, m.D, st));
-      COUNT_LAUNCH();
-      VXB_TRY(linear(w.xn, m.D, PL(l, VXB_PL_Q_W), m.D, nullptr, nullptr, 1, 0, w.qb, lq, B * m.L, lq,
-                     m.D, 1.f, -1.f, mm, st));
-      COUNT_LAUNCH();
-      VXB_TRY(linear(w.xn, m.D, PL(l, VXB_PL_KV_W), m.D, nullptr, nullptr, 1, 0, w.kvb, 2 * lq, B * m.L,
-                     2 * lq, m.D, 1.f, -1.f, mm, st));
+            VXB_TRY(lin(cx, w.xn, m.D, PL(l, VXB_PL_Q_W), m.D, nullptr, nullptr, 1, 0, w.qb, lq, B * m.L, lq,
+                     m.D, 1.f, -1.f, mm));
+            VXB_TRY(lin(cx, w.xn, m.D, PL(l, VXB_PL_KV_W), m.D, nullptr, nullptr, 1, 0, w.kvb, 2 * lq, B * m.L,
+                     2 * lq, m.D, 1.f, -1.f, mm));
       VXB_TRY(attention(w.qb, lq, (long long)m.L * lq, w.kvb, w.kvb + lq, 2 * lq, (long long)m.L * 2 * lq,
                         w.att, lq, (long long)m.L * lq, B, m.lh, m.L, m.L, m.ldh,
                         1.f / sqrtf((float)m.ldh), w.sim, mm, st));
-      COUNT_LAUNCH();
-      VXB_TRY(linear(w.att, lq, PL(l, VXB_PL_OUT_W), lq, PL(l, VXB_PL_OUT_B), w.x, B * m.L, m.D, w.x, m.D,
-                     B * m.L, m.D, lq, 1.f, -1.f, mm, st));
-      VXB_TRY(feed_forward(m, B, w, PL(l, VXB_PL_FF_NORM_W), PL(l, VXB_PL_FF_NORM_B), PL(l, VXB_PL_FF0_W),
-                           PL(l, VXB_PL_FF0_B), PL(l, VXB_PL_FF2_W), PL(l, VXB_PL_FF2_B), mm, st));
+            VXB_TRY(lin(cx, w.att, lq, PL(l, VXB_PL_OUT_W), lq, PL(l, VXB_PL_OUT_B), w.x, B * m.L, m.D, w.x, m.D,
+                     B * m.L, m.D, lq, 1.f, -1.f, mm));
+      VXB_TRY(feed_forward(cx, m, B, w, PL(l, VXB_PL_FF_NORM_W), PL(l, VXB_PL_FF_NORM_B), PL(l, VXB_PL_FF0_W),
+                           PL(l, VXB_PL_FF0_B), PL(l, VXB_PL_FF2_W), PL(l, VXB_PL_FF2_B)));
     }
   }
   STAGE_MARK();  // 5: decoder cross attention + ss1
@@ -425,32 +499,32 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   //     dropped right after, :444), context = LN_ctx(x); no residual              :440-448
   VXB_TRY(layernorm_batched(w.ins + (size_t)m.nl * m.C, (size_t)m.n * m.C, P(VXB_P_DEC_NORM_W),
                             P(VXB_P_DEC_NORM_B), w.ctx_n, B, m.T, m.C, st));
-  COUNT_LAUNCH();
-  VXB_TRY(linear(w.ctx_n, m.C, P(VXB_P_DEC_Q_W), m.C, nullptr, nullptr, 1, 0, w.qb, cq, B * m.T, cq, m.C,
-                 1.f, -1.f, mm, st));
+    VXB_TRY(lin(cx, w.ctx_n, m.C, P(VXB_P_DEC_Q_W), m.C, nullptr, nullptr, 1, 0, w.qb, cq, B * m.T, cq, m.C,
+                 1.f, -1.f, mm));
   VXB_TRY(layernorm(w.x, P(VXB_P_DEC_NORMCTX_W), P(VXB_P_DEC_NORMCTX_B), w.xn, (size_t)B * m.L, m.D, st));
-  COUNT_LAUNCH();
-  VXB_TRY(linear(w.xn, m.D, P(VXB_P_DEC_KV_W), m.D, nullptr, nullptr, 1, 0, w.kvb, 2 * cq, B * m.L, 2 * cq,
-                 m.D, 1.f, -1.f, mm, st));
+    VXB_TRY(lin(cx, w.xn, m.D, P(VXB_P_DEC_KV_W), m.D, nullptr, nullptr, 1, 0, w.kvb, 2 * cq, B * m.L, 2 * cq,
+                 m.D, 1.f, -1.f, mm));
   VXB_TRY(attention(w.qb, cq, (long long)m.T * cq, w.kvb, w.kvb + cq, 2 * cq, (long long)m.L * 2 * cq, w.att,
                     cq, (long long)m.T * cq, B, m.ch, m.T, m.L, m.cdh, 1.f / sqrtf((float)m.cdh), w.sim, mm, st));
-  COUNT_LAUNCH();
-  VXB_TRY(linear(w.att, cq, P(VXB_P_DEC_OUT_W), cq, P(VXB_P_DEC_OUT_B), nullptr, 1, 0, w.dec, m.C, B * m.T,
-                 m.C, cq, 1.f, -1.f, mm, st));
+    VXB_TRY(lin(cx, w.att, cq, P(VXB_P_DEC_OUT_W), cq, P(VXB_P_DEC_OUT_B), nullptr, 1, 0, w.dec, m.C, B * m.T,
+                 m.C, cq, 1.f, -1.f, mm));
   // (9) feats[256 : 256+4C] = [ss1(dec), maxpool(dec)]                           :451
   VXB_TRY(spatial_softmax(w.dec, B, m.S, m.S, m.S, m.C, w.feats + 256, m.flat, w.feats + 256 + 3 * m.C,
                           m.flat, w.ss_part, st));
   STAGE_MARK();  // 6: up0 conv at S^3
   // (10) up0: conv k (C->64) at S^3, then [upsample x s o conv k] folded     :454
   COUNT_LAUNCH();
-  VXB_TRY(conv3d(w.dec, nullptr, m.C, 0, pw.up0_wt, P(VXB_P_UP0_B), w.low, B, m.S, m.S, 64, m.k, 1, slope, mm, st));
+  VXB_TRY(conv3d(w.dec, nullptr, m.C, 0, pw.up0_wt, P(VXB_P_UP0_B), w.low, B, m.S, m.S, 64, m.k, 1, slope, mm, st,
+                 cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.up0_wt)));
   STAGE_MARK();  // 7: folded upsample-conv
   COUNT_LAUNCH();
-  VXB_TRY(upconv3d_folded(w.low, pw.up1_fold, P(VXB_P_UP1_B), w.u0, B, m.S, 64, 64, m.s, slope, mm, st));
+  VXB_TRY(upconv3d_folded(w.low, pw.up1_fold, P(VXB_P_UP1_B), w.u0, B, m.S, 64, 64, m.s, slope, mm, st,
+                          cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.up1_fold)));
   STAGE_MARK();  // 8: final conv
   // (11) final: conv3 on cat[d0, u0] (128 -> 64)                               :462
   COUNT_LAUNCH();
-  VXB_TRY(conv3d(w.d0, w.u0, 64, 64, pw.final_wt, P(VXB_P_FINAL_B), w.u, B, m.V, m.V, 64, 3, 1, slope, mm, st));
+  VXB_TRY(conv3d(w.d0, w.u0, 64, 64, pw.final_wt, P(VXB_P_FINAL_B), w.u, B, m.V, m.V, 64, 3, 1, slope, mm, st,
+                 cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.final_wt)));
   STAGE_MARK();  // 9: trans decoder
   // (12) trans decoder: conv3 64 -> 1, no activation                            :465
   COUNT_LAUNCH();
@@ -461,27 +535,22 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   const int off = 256 + 4 * m.C;
   VXB_TRY(spatial_softmax(w.u, B, m.V, m.V, m.V, 64, w.feats + off, m.flat, w.feats + off + 192, m.flat,
                           w.ss_part, st));
-  COUNT_LAUNCH();
-  VXB_TRY(linear(w.feats, m.flat, P(VXB_P_DENSE0_W), m.flat, P(VXB_P_DENSE0_B), nullptr, 1, 0, w.h0, 256, B,
-                 256, m.flat, 1.f, slope, VXB_MATH_FP32_SIMT, st));
-  COUNT_LAUNCH();
-  VXB_TRY(linear(w.h0, 256, P(VXB_P_DENSE1_W), 256, P(VXB_P_DENSE1_B), nullptr, 1, 0, w.h1, 64, B, 64, 256,
-                 1.f, slope, VXB_MATH_FP32_SIMT, st));
+    VXB_TRY(lin(cx, w.feats, m.flat, P(VXB_P_DENSE0_W), m.flat, P(VXB_P_DENSE0_B), nullptr, 1, 0, w.h0, 256, B,
+                 256, m.flat, 1.f, slope, VXB_MATH_FP32_SIMT));
+    VXB_TRY(lin(cx, w.h0, 256, P(VXB_P_DENSE1_W), 256, P(VXB_P_DENSE1_B), nullptr, 1, 0, w.h1, 64, B, 64, 256,
+                 1.f, slope, VXB_MATH_FP32_SIMT));
   const int nout = 3 * m.R + m.G + m.Cc;
-  COUNT_LAUNCH();
-  VXB_TRY(linear(w.h1, 64, P(VXB_P_RGC_W), 64, P(VXB_P_RGC_B), nullptr, 1, 0, w.rgc, nout, B, nout, 64, 1.f,
-                 -1.f, VXB_MATH_FP32_SIMT, st));
+    VXB_TRY(lin(cx, w.h1, 64, P(VXB_P_RGC_W), 64, P(VXB_P_RGC_B), nullptr, 1, 0, w.rgc, nout, B, nout, 64, 1.f,
+                 -1.f, VXB_MATH_FP32_SIMT));
   VXB_CUDA(cudaMemcpy2DAsync(rot_grip, (size_t)(nout - m.Cc) * 4, w.rgc, (size_t)nout * 4,
                              (size_t)(nout - m.Cc) * 4, B, cudaMemcpyDeviceToDevice, st));
   VXB_CUDA(cudaMemcpy2DAsync(collision, (size_t)m.Cc * 4, w.rgc + (nout - m.Cc), (size_t)nout * 4,
                              (size_t)m.Cc * 4, B, cudaMemcpyDeviceToDevice, st));
   if (d->arm_pred_loss && arm_out) {
-    COUNT_LAUNCH();
-    VXB_TRY(linear(w.feats, m.flat, P(VXB_P_DENSE2_W), m.flat, P(VXB_P_DENSE2_B), nullptr, 1, 0, w.h2, 64, B,
-                   64, m.flat, 1.f, slope, VXB_MATH_FP32_SIMT, st));
-    COUNT_LAUNCH();
-    VXB_TRY(linear(w.h2, 64, P(VXB_P_ARM_W), 64, P(VXB_P_ARM_B), nullptr, 1, 0, arm_out, 2, B, 2, 64, 1.f,
-                   -1.f, VXB_MATH_FP32_SIMT, st));
+        VXB_TRY(lin(cx, w.feats, m.flat, P(VXB_P_DENSE2_W), m.flat, P(VXB_P_DENSE2_B), nullptr, 1, 0, w.h2, 64, B,
+                   64, m.flat, 1.f, slope, VXB_MATH_FP32_SIMT));
+        VXB_TRY(lin(cx, w.h2, 64, P(VXB_P_ARM_W), 64, P(VXB_P_ARM_B), nullptr, 1, 0, arm_out, 2, B, 2, 64, 1.f,
+                   -1.f, VXB_MATH_FP32_SIMT));
   }
   STAGE_MARK();  // end
   return VXB_OK;
@@ -503,7 +572,7 @@ extern "C" int vxb_qnet_forward_f32(const vxb_qnet_desc* d, const void* const* p
   (void)proprio2; (void)q_trans2; (void)rot_grip2; (void)collision2;
   Arena pa((void*)prepared, (size_t)-1);
   Prepared pw;
-  carve_prepared(m, pa, pw);
+  carve_prepared(m, pa, pw, params);
   Arena wa(ws, ws_bytes);
   Work w;
   carve_work(m, B, wa, w);

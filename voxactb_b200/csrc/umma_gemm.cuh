@@ -1,0 +1,357 @@
+// tcgen05 split-bf16 ("bf16x3") GEMM / implicit-GEMM convolution engine for sm_100a.
+//
+//   D[M,N] (fp32, TMEM) = A_hi*B_hi + A_hi*B_lo + A_lo*B_hi        (A = A_hi + A_lo, B = B_hi + B_lo)
+//
+// Every fp32 operand is stored as two bf16 planes (hi = rn(x), lo = rn(x - hi)): 16 mantissa bits,
+// the same 4 bytes per element as fp32, three kind::f16 MMAs per logical product -- fp32-class
+// accuracy (~2^-16 relative) at 1/3 of the bf16 tensor peak, which is what the 1e-3 Q-value gate
+// needs (single-pass TF32/bf16 miss it).
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: per k-block loads A_hi/A_lo [128 x 64] and B_hi/B_lo [NT x 64] tiles
+//               (SWIZZLE_128B, K-major) into a STAGES-deep smem ring, signalled by mbarriers
+//   warp 1      MMA issuer: one elected lane issues 12 tcgen05.mma (128 x NT x 16) per k-block into one
+//               of two TMEM accumulator stages; tcgen05.commit releases smem slots / publishes the tile
+//   warps 2-5   epilogue: tcgen05.ld the accumulator (lane = row), bias/activation/residual, store
+//               fp32 and/or bf16 hi/lo planes; overlaps with the next tile's main loop
+//
+// The A operand is addressed per k-block as (column a_col[kb], row m0 + a_row[kb]) in one of two
+// source tensors: with a_row = the flat offset of a convolution tap in a zero/replicate PADDED
+// channels-last tensor this is an implicit-GEMM convolution (rows = flat padded voxel index, taps are
+// plain row shifts); with a_row = 0 and a_col = 64*kb it is an ordinary GEMM.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "umma_host.cuh"
+
+namespace vxb {
+namespace umma {
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Spin on the barrier phase.  A wait that lasts ~4 s of SM clock means a lost TMA / MMA completion:
+// trap (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (!done && (spins & 0xFFFu) == 0xFFFu) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000ll) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets columns [col, col+32) of TMEM lane (lane_base + t)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 bytes,
+// 8-row groups SBO bytes apart, version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);            // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                             // leading byte offset: 1 (16 B), as CUTLASS sets it for swizzled K-major
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;   // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                             // version = 1
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = NT
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int NT, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;   // 16 KB per plane
+  static constexpr int B_BYTES = NT * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /* alignment slack */;
+};
+
+template <int NT, int STAGES>
+__global__ void __launch_bounds__(THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_constant__ CUtensorMap mapA0l,
+                 const __grid_constant__ CUtensorMap mapA1h, const __grid_constant__ CUtensorMap mapA1l,
+                 const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
+                 const Params p) {
+  using L = SmemLayout<NT, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* full_bar = bars;                   // [STAGES] TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;         // [STAGES] MMA -> TMA
+  uint64_t* acc_full = bars + 2 * STAGES;      // [2] MMA -> epilogue
+  uint64_t* acc_empty = bars + 2 * STAGES + 2; // [2] epilogue -> MMA
+  uint32_t* tmem_base_smem = (uint32_t*)(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = (2 * NT <= 32) ? 32 : (2 * NT <= 64) ? 64 : (2 * NT <= 128) ? 128 : (2 * NT <= 256) ? 256 : 512;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0h); tma_prefetch_desc(&mapA0l);
+    tma_prefetch_desc(&mapA1h); tma_prefetch_desc(&mapA1l);
+    tma_prefetch_desc(&mapWh); tma_prefetch_desc(&mapWl);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.batches;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const KPlan pl = p.plan;
+      const int tiles_per_z = p.m_tiles * p.n_tiles;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int z = tile / tiles_per_z, tz = tile % tiles_per_z;
+        const int zb = z / p.Hz, zh = z % p.Hz;
+        const int mt = tz / p.n_tiles, nt = tz % p.n_tiles;
+        const int m0 = mt * BM + zb * p.a_row_zb;
+        const int n0 = nt * NT + zb * p.w_row_zb + zh * p.w_row_zh;
+        for (int kb = 0; kb < pl.num_kb; ++kb) {
+          int a_row = 0, a_col = kb * BK, a_src = 0;
+          if (pl.taps) {
+            const int tap = kb / pl.cpb, cb = kb - tap * pl.cpb;
+            const int c = pl.taps >> 1;
+            const int dx = tap % pl.taps, dy = (tap / pl.taps) % pl.taps, dz = tap / (pl.taps * pl.taps);
+            a_row = ((dz - c) * pl.Vp + (dy - c)) * pl.Vp + (dx - c);
+            a_src = cb >= pl.cb_src0;
+            a_col = (a_src ? cb - pl.cb_src0 : cb) * BK;
+          }
+          a_col += zh * p.a_col_zh;
+          const int w_col = kb * BK + zh * p.w_col_zh;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* s = smem + stage * L::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          const CUtensorMap* ah = a_src ? &mapA1h : &mapA0h;
+          const CUtensorMap* al = a_src ? &mapA1l : &mapA0l;
+          tma_load_2d(ah, &full_bar[stage], s, a_col, m0 + a_row);
+          tma_load_2d(al, &full_bar[stage], s + L::A_BYTES, a_col, m0 + a_row);
+          tma_load_2d(&mapWh, &full_bar[stage], s + 2 * L::A_BYTES, w_col, n0);
+          tma_load_2d(&mapWl, &full_bar[stage], s + 2 * L::A_BYTES + L::B_BYTES, w_col, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(NT);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NT);
+        for (int kb = 0; kb < p.plan.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa_hi = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sa_lo = sa_hi + L::A_BYTES;
+          const uint32_t sb_hi = sa_hi + 2 * L::A_BYTES;
+          const uint32_t sb_lo = sb_hi + L::B_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t a_hi = make_desc(sa_hi + k * 32, 1024);
+            const uint64_t a_lo = make_desc(sa_lo + k * 32, 1024);
+            const uint64_t b_hi = make_desc(sb_hi + k * 32, 1024);
+            const uint64_t b_lo = make_desc(sb_lo + k * 32, 1024);
+            tc_mma_bf16(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0);
+            tc_mma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
+            tc_mma_bf16(d_tmem, a_lo, b_hi, idesc, 1);
+          }
+          tc_commit(&empty_bar[stage]);             // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&acc_full[acc]);                  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5)
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const Epilogue& e = p.ep;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int tiles_per_z = p.m_tiles * p.n_tiles;
+      const int z = tile / tiles_per_z, tz = tile % tiles_per_z;
+      const int zb = z / p.Hz, zh = z % p.Hz;
+      const int mt = tz / p.n_tiles, nt = tz % p.n_tiles;
+      const int m = mt * BM + q * 32 + lane;        // this thread's row (within the batch entry)
+      const int n0 = nt * NT;
+      float* const out_f32 = e.out_f32 ? e.out_f32 + zb * p.c_zb + zh * p.c_zh : nullptr;
+      __nv_bfloat16* const out_hi = e.out_hi ? e.out_hi + zb * p.p_zb + zh * p.p_zh : nullptr;
+      __nv_bfloat16* const out_lo = e.out_lo ? e.out_lo + zb * p.p_zb + zh * p.p_zh : nullptr;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      // ---- row mapping
+      bool row_ok = m < e.M;
+      long long orow = m;
+      int qd = 0, qh = 0, qw = 0, qb = 0;
+      if (e.row_mode != ROWS_PLAIN) {
+        const int Vp = e.Vp, V = Vp - 2 * e.pad;
+        const int vp3 = Vp * Vp * Vp;
+        qb = m / vp3;
+        const int r = m - qb * vp3;
+        qd = r / (Vp * Vp) - e.pad; qh = (r / Vp) % Vp - e.pad; qw = r % Vp - e.pad;
+        row_ok = row_ok && qd >= 0 && qd < V && qh >= 0 && qh < V && qw >= 0 && qw < V;
+        if (e.row_mode == ROWS_CONV_FLAT && !e.out_padded) orow = (((long long)qb * V + qd) * V + qh) * V + qw;
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + c0), v);
+        const int n = n0 + c0;
+        if (row_ok && n < e.N) {
+          if (e.row_mode == ROWS_PHASE) {
+            // 64-column block = one polyphase: fine voxel = s*q + r in the padded fine grid
+            const int ph = n / 64;
+            const int s = e.phase_s;
+            const int rd = ph / (s * s), rh = (ph / s) % s, rw = ph % s;
+            const int oV = e.out_Vp;
+            orow = (((long long)qb * oV + qd * s + rd + e.out_pad) * oV + qh * s + rh + e.out_pad) * oV + qw * s + rw + e.out_pad;
+          }
+          const int ncol = (e.row_mode == ROWS_PHASE) ? (n % 64) : n;   // column inside the output row
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float t = __uint_as_float(v[j]) * e.alpha;
+            const int nn = n + j;
+            if (nn < e.N) {
+              if (e.bias) t += e.bias[(e.row_mode == ROWS_PHASE) ? (ncol + j) : nn];
+              if (e.act_slope >= 0.f) t = t > 0.f ? t : t * e.act_slope;
+              if (e.residual) t += e.residual[(long long)(m % e.res_rows) * e.ldr + nn];
+            }
+            f[j] = t;
+          }
+          const bool full = n + 31 < e.N;
+          if (out_f32) {
+            float* dst = out_f32 + orow * e.ldc + ncol;
+            if (full && ((e.ldc & 3) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              for (int j = 0; j < 32; ++j) if (n + j < e.N) dst[j] = f[j];
+            }
+          }
+          if (out_hi) {
+            if (e.transpose_planes) {
+              for (int j = 0; j < 32; ++j) {
+                if (n + j < e.N) {
+                  const __nv_bfloat16 hi = __float2bfloat16_rn(f[j]);
+                  const __nv_bfloat16 lo = __float2bfloat16_rn(f[j] - __bfloat162float(hi));
+                  out_hi[(long long)(ncol + j) * e.ldp + orow] = hi;
+                  out_lo[(long long)(ncol + j) * e.ldp + orow] = lo;
+                }
+              }
+            } else {
+              __nv_bfloat16* dh = out_hi + orow * e.ldp + ncol;
+              __nv_bfloat16* dl = out_lo + orow * e.ldp + ncol;
+              if (full && ((e.ldp & 7) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  __align__(16) __nv_bfloat16 h8[8], l8[8];
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) {
+                    h8[t] = __float2bfloat16_rn(f[j + t]);
+                    l8[t] = __float2bfloat16_rn(f[j + t] - __bfloat162float(h8[t]));
+                  }
+                  *reinterpret_cast<uint4*>(dh + j) = *reinterpret_cast<const uint4*>(h8);
+                  *reinterpret_cast<uint4*>(dl + j) = *reinterpret_cast<const uint4*>(l8);
+                }
+              } else {
+                for (int j = 0; j < 32; ++j) {
+                  if (n + j < e.N) {
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(f[j]);
+                    dh[j] = hi;
+                    dl[j] = __float2bfloat16_rn(f[j] - __bfloat162float(hi));
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace umma
+}  // namespace vxb

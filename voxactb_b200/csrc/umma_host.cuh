@@ -1,0 +1,106 @@
+// Host-visible types of the tcgen05 split-bf16 engine (kernel in umma_gemm.cuh, host code in umma_ops.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace vxb {
+namespace umma {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // bf16 elements per k-block row = 128 bytes = one SWIZZLE_128B span
+constexpr int THREADS = 192;
+
+// Per-k-block operand addressing, derived in the producer from a few integers (no table):
+//   plain GEMM (taps == 0): A block kb = columns [64 kb, 64 kb + 64) of source 0, rows unshifted
+//   convolution (taps = k per axis): kb -> (tap, channel block); the tap is a row shift of
+//   ((dz-c)*Vp + (dy-c))*Vp + (dx-c) in the flat padded grid; channel blocks [0, cb_src0) come from
+//   source 0, the rest from source 1 (fused channel concat); W block kb = columns [64 kb, 64 kb + 64)
+struct KPlan {
+  int num_kb;
+  int taps;        // 0 = plain GEMM, else kernel size per axis (odd)
+  int Vp;          // padded grid extent (conv)
+  int cpb;         // channel blocks (of 64) per tap
+  int cb_src0;     // channel blocks taken from source 0
+};
+
+enum { ROWS_PLAIN = 0, ROWS_CONV_FLAT = 1, ROWS_PHASE = 2 };
+
+struct Epilogue {
+  int M, N;                   // logical extents (rows beyond M / cols beyond N are not stored)
+  int row_mode;
+  // ROWS_CONV_FLAT / ROWS_PHASE: rows are flat indices into a padded [B, Vp, Vp, Vp] grid with `pad`
+  // halo voxels per side; only interior rows are stored.
+  int Vp, pad;
+  int out_padded;             // CONV_FLAT: 1 = output rows keep the padded geometry (row = m), 0 = compact [B,V^3]
+  int phase_s;                // ROWS_PHASE: column block j (64 cols) = phase p = n/64 -> fine voxel s*q + r
+  int out_Vp, out_pad;        // ROWS_PHASE: geometry of the fine output grid (padded)
+  const float* bias;          // [N] (ROWS_PHASE: [64], shared by all phases)
+  float alpha;
+  float act_slope;            // < 0: none
+  const float* residual;      // fp32 [(row % res_rows), ldr] added after the activation, or null
+  int res_rows, ldr;
+  float* out_f32;             // fp32 output or null
+  long long ldc;
+  __nv_bfloat16* out_hi;      // bf16 plane outputs or null
+  __nv_bfloat16* out_lo;
+  long long ldp;
+  int transpose_planes;       // planes written transposed: element (row, col) -> out[(col) * ldp + row] (V^T for attention)
+};
+
+struct Params {
+  int m_tiles, n_tiles;
+  KPlan plan;
+  // batching: tile z = zb * Hz + zh; operand bases shift per z (attention heads / batches)
+  int batches, Hz;
+  int a_row_zb, a_col_zh;        // A: rows per zb, columns per zh
+  int w_row_zb, w_row_zh, w_col_zh;
+  long long c_zb, c_zh;          // fp32 output element offsets per zb / zh
+  long long p_zb, p_zh;          // plane output element offsets per zb / zh
+  Epilogue ep;
+};
+
+
+// bf16 hi/lo planes of an fp32 matrix: x ~= hi + lo, row-major with ld elements between rows
+struct Planes {
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;
+  long long ld;
+};
+struct Operand {
+  Planes p;
+  long long rows, cols;   // logical extent seen by TMA (out-of-bounds reads are zero)
+};
+
+inline size_t plane_elems(long long rows, long long ld) { return (size_t)rows * (size_t)ld; }
+inline long long pad8(long long v) { return (v + 7) / 8 * 8; }
+
+int split_rows(const float* x, long long ldx, long long rows, int cols, Planes out, cudaStream_t st);
+int pad_split(const float* x, int B, int V, int pad, int C, Planes out, cudaStream_t st);
+int halo_fill(Planes p, int B, int V, int pad, int C, cudaStream_t st);
+// D = A W^T on tcgen05; A1 is the optional second A source (fused channel concat in convolutions)
+int gemm(const Operand& A0, const Operand* A1, const Operand& W, int n_tile, Params p, cudaStream_t st);
+long long launches();   // tcgen05 GEMM launches so far in this process
+
+// fp32-in / fp32-out wrappers (operands split into `scratch`)
+size_t linear_scratch_bytes(long long M, long long N, long long K, bool split_w);
+int linear_f32(const float* A, int lda, const float* W, int ldw, const Planes* Wpre, const float* bias,
+               const float* residual, int res_rows, int ldr, float* C, int ldc, int M, int N, int K, float alpha,
+               float act_slope, Arena& scratch, cudaStream_t st);
+size_t conv3d_scratch_bytes(int B, int V, int C0, int C1, int k);
+int conv3d_f32(const float* x0, const float* x1, int C0, int C1, const Planes& Wp, const float* bias, float* out,
+               int B, int V, int Co, int k, float act_slope, Arena& scratch, cudaStream_t st);
+size_t upconv_scratch_bytes(int B, int S, int Ci);
+int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out, int B, int S, int Ci, int Co, int s,
+               float act_slope, Arena& scratch, cudaStream_t st);
+
+inline void params_init(Params& p) {
+  memset(&p, 0, sizeof(p));
+  p.batches = 1;
+  p.Hz = 1;
+  p.ep.alpha = 1.f;
+  p.ep.act_slope = -1.f;
+  p.ep.res_rows = 1;
+}
+
+}  // namespace umma
+}  // namespace vxb
