@@ -107,6 +107,22 @@ def test_conv3d(cuda_lib, mode, Di, Ci, Co, k, s):
     assert util.rel_err(y, ref) < TOL[mode]
 
 
+@pytest.mark.parametrize('V', [20, 32, 50, 37])
+def test_trans_decoder_stencil(cuda_lib, V):
+    """Conv3d(64 -> 1, k3, replicate pad, no activation) = trans_decoder (perceiver_lang_io.py:308-311)."""
+    g = torch.Generator().manual_seed(V)
+    x = torch.randn(2, 64, V, V, V, generator=g)
+    w = torch.randn(1, 64, 3, 3, 3, generator=g) / (64 * 27) ** 0.5
+    b = torch.randn(1, generator=g)
+    ref = qnet_oracle.conv3d_block(x, w, b, 1, None).permute(0, 2, 3, 4, 1)
+    y = torch.empty(ref.shape, device='cuda')
+    wk = ws(cuda_lib.vxb_conv3d_workspace_bytes(2, V, 64, 1, 3))
+    xc, wc, bc = x.permute(0, 2, 3, 4, 1).contiguous().cuda(), w.cuda(), b.cuda()
+    _lib.check(cuda_lib.vxb_conv3d_f32(_lib.ptr(xc), _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(y), 2, V, 64, 1, 3, 1,
+                                       -1.0, _lib.MATH_FP32_SIMT, _lib.ptr(wk), wk.numel(), _lib.stream()), 'conv3d')
+    assert util.rel_err(y, ref) < 1e-5
+
+
 @pytest.mark.parametrize('mode', MODES)
 @pytest.mark.parametrize('S,k,s', [(4, 5, 5), (5, 5, 4), (3, 9, 8), (6, 3, 2)])
 def test_upconv3d_equals_upsample_then_conv(cuda_lib, mode, S, k, s):

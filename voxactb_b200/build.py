@@ -31,17 +31,35 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def _compile_one(args):
+    src, obj, verbose = args
+    cmd = [_nvcc()] + NVCC_FLAGS[:-1] + ['-c', src, '-o', obj]
+    if verbose:
+        print(' '.join(cmd), file=sys.stderr)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    return res.returncode, res.stdout + res.stderr
+
+
 def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into voxactb_b200/libvoxactb.so."""
+    """Compile every CUDA source for sm_100a into voxactb_b200/libvoxactb.so (objects in parallel)."""
     if not force and not _stale():
         return LIB
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + NVCC_FLAGS + ['-o', LIB] + srcs
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, 'build')
+    os.makedirs(objdir, exist_ok=True)
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    jobs = [(os.path.join(CSRC, s), os.path.join(objdir, s[:-3] + '.o'), verbose) for s in srcs]
+    with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+        results = list(ex.map(_compile_one, jobs))
+    for rc, out in results:
+        if rc != 0:
+            raise RuntimeError('nvcc failed:\n' + out)
+    cmd = [_nvcc(), '-shared', '-o', LIB] + [j[1] for j in jobs]
     if verbose:
         print(' '.join(cmd), file=sys.stderr)
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
+        raise RuntimeError('nvcc link failed:\n' + res.stdout + res.stderr)
     return LIB
 
 

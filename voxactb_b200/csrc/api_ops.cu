@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "ops.cuh"
 #include "simt_gemm.cuh"
+#include "stream_ops.cuh"
 #include "dispatch.cuh"
 
 using namespace vxb;
@@ -145,30 +146,20 @@ extern "C" int vxb_layernorm_f32(const float* x, const float* w, const float* b,
   return VXB_OK;
 }
 
-static int ss_chunks_api(size_t P) { return (int)std::min<size_t>(1024, std::max<size_t>(1, (P + 1023) / 1024)); }
-
 extern "C" size_t vxb_spatial_softmax_workspace_bytes(int B, int P, int C) {
-  (void)C;
-  return (size_t)B * ss_chunks_api((size_t)P) * 6 * 256 * sizeof(float);
+  return ss_partial_floats((size_t)P, B, C) * sizeof(float);
 }
 
 extern "C" int vxb_spatial_softmax_f32(const float* x, int B, int Dd, int Hh, int Ww, int C, float* ss,
                                        int ss_stride, float* mx, int mx_stride, void* ws,
                                        size_t ws_bytes, void* stream) {
-  VXB_CHECK_ARG(x && ss && ws && B > 0 && C > 0 && C <= 256, "spatial_softmax: bad arguments");
+  VXB_CHECK_ARG(x && ss && ws && B > 0 && C > 0, "spatial_softmax: bad arguments");
   const size_t P = (size_t)Dd * Hh * Ww;
   if (ws_bytes < vxb_spatial_softmax_workspace_bytes(B, (int)P, C)) {
     set_error("spatial_softmax: workspace too small");
     return VXB_E_WORKSPACE_TOO_SMALL;
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  const int chunks = ss_chunks_api(P);
-  const int chunk = (int)((P + chunks - 1) / chunks);
-  spatial_softmax_partial_kernel<<<dim3(chunks, B), 256, 0, st>>>(x, (int)P, C, Dd, Hh, Ww, chunk, (float*)ws);
-  VXB_LAUNCH_CHECK();
-  spatial_softmax_merge_kernel<<<B, 256, 0, st>>>((float*)ws, chunks, C, ss, ss_stride, mx, mx_stride);
-  VXB_LAUNCH_CHECK();
-  return VXB_OK;
+  return spatial_softmax_run(x, B, Dd, Hh, Ww, C, ss, ss_stride, mx, mx_stride, (float*)ws, (cudaStream_t)stream);
 }
 
 static size_t conv_w_bytes(int Ci, int Co, int k) { return align_up((size_t)Ci * Co * k * k * k * sizeof(float), 256); }
@@ -191,6 +182,8 @@ extern "C" int vxb_conv3d_f32(const float* x, const float* w, const float* bias,
   conv_weight_to_tapmajor_kernel<<<cdiv((size_t)Co * Ci * k3, 256), 256, 0, st>>>(w, (float*)ws, Co, Ci, k3);
   VXB_LAUNCH_CHECK();
   const int Do = (Di + 2 * (k / 2) - k) / s + 1;
+  if (Co == 1 && Ci == 64 && k == 3 && s == 1 && act_slope < 0.f)   // trans_decoder shape: streaming stencil
+    return trans_stencil_run<64>(x, (const float*)ws, bias, y, B, Di, st);
   Arena scratch((char*)ws + conv_w_bytes(Ci, Co, k), ws_bytes - conv_w_bytes(Ci, Co, k));
   return conv3d(x, nullptr, Ci, 0, (const float*)ws, bias, y, B, Di, Do, Co, k, s, act_slope, math_mode, st,
                 &scratch, nullptr);
@@ -225,7 +218,8 @@ extern "C" int vxb_upconv3d_f32(const float* x, const float* w, const float* bia
 
 extern "C" size_t vxb_attention_workspace_bytes(int B, int H, int Nq, int Nk) {
   const size_t Nkp = ((size_t)Nk + 3) / 4 * 4;
-  return align_up((size_t)B * H * Nq * Nkp * sizeof(float), 256);
+  return std::max(align_up((size_t)B * H * Nq * Nkp * sizeof(float), 256),
+                  umma::attention_f32_scratch_bytes(B, H, Nq, Nk, 64) + 256);
 }
 
 extern "C" int vxb_attention_f32(const float* q, int ldq, long long q_batch_stride, const float* k,
@@ -238,6 +232,11 @@ extern "C" int vxb_attention_f32(const float* q, int ldq, long long q_batch_stri
   if (ws_bytes < vxb_attention_workspace_bytes(B, H, Nq, Nk)) {
     set_error("attention: workspace too small");
     return VXB_E_WORKSPACE_TOO_SMALL;
+  }
+  if (math_mode == VXB_MATH_BF16X3 && dh == 64) {
+    Arena scratch(ws, ws_bytes);
+    return umma::attention_f32(q, ldq, q_batch_stride, k, v, ldkv, kv_batch_stride, out, ldo, o_batch_stride, B, H,
+                               Nq, Nk, dh, scale, scratch, (cudaStream_t)stream);
   }
   return attention_materialized(q, ldq, q_batch_stride, k, v, ldkv, kv_batch_stride, out, ldo,
                                 o_batch_stride, B, H, Nq, Nk, dh, scale, (float*)ws, math_mode,

@@ -96,173 +96,6 @@ softmax_rows_kernel(float* __restrict__ x, int n, int ld) {
   for (int i = threadIdx.x; i < ld; i += 256) xr[i] = (i < n) ? xr[i] * inv : 0.f;
 }
 
-// ---------------------------------------------------------------- 1x1x1 conv (K = initial_dim) + activation
-// input_preprocess, perceiver_lang_io.py:217-220,357.  x [M, Cin] -> y [M, Cout]; 4 threads per voxel.
-template <int CIN>
-static __global__ void __launch_bounds__(256)
-pointwise_conv_kernel(const float* __restrict__ x, const float* __restrict__ w /*[Cout,CIN]*/,
-                      const float* __restrict__ bias, float* __restrict__ y, size_t M, int Cout,
-                      float slope) {
-  extern __shared__ float sw[];  // [Cout][CIN] + [Cout]
-  for (int i = threadIdx.x; i < Cout * CIN; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[Cout * CIN + i] = bias[i];
-  __syncthreads();
-  const int per = Cout / 4;  // channels per thread (multiple of 4)
-  const size_t m = (size_t)blockIdx.x * 64 + (threadIdx.x >> 2);
-  const int part = threadIdx.x & 3;
-  if (m >= M) return;
-  float in[CIN];
-#pragma unroll
-  for (int i = 0; i < CIN; ++i) in[i] = x[m * CIN + i];
-  float* yo = y + m * Cout + part * per;
-  for (int c = 0; c < per; c += 4) {
-    float o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = part * per + c + j;
-      float a = sw[Cout * CIN + co];
-#pragma unroll
-      for (int i = 0; i < CIN; ++i) a = fmaf(in[i], sw[co * CIN + i], a);
-      o[j] = slope >= 0.f ? lrelu(a, slope) : a;
-    }
-    *reinterpret_cast<float4*>(yo + c) = make_float4(o[0], o[1], o[2], o[3]);
-  }
-}
-
-// ---------------------------------------------------------------- 3x3x3 conv to ONE channel (trans_decoder)
-// perceiver_lang_io.py:308-311,465.  x [B,V,V,V,C] channels-last, w re-laid [27][C]; y [B,V^3].
-// One warp per output voxel group of 4: each lane owns C/32 channels... simple version: 8 lanes per voxel.
-template <int C>
-static __global__ void __launch_bounds__(256)
-conv3_to1_kernel(const float* __restrict__ x, const float* __restrict__ wt /*[27][C]*/,
-                 const float* __restrict__ bias, float* __restrict__ y, int B, int V) {
-  __shared__ __align__(16) float sw[27 * C];
-  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) sw[i] = wt[i];
-  __syncthreads();
-  constexpr int LPV = 8;              // lanes per voxel
-  constexpr int CPL = C / LPV;        // channels per lane (8 for C=64)
-  const size_t V3 = (size_t)V * V * V;
-  const size_t vox = (size_t)blockIdx.x * (256 / LPV) + (threadIdx.x / LPV);
-  const int part = threadIdx.x % LPV;
-  const bool valid = vox < (size_t)B * V3;
-  float acc = 0.f;
-  if (valid) {
-    const int b = (int)(vox / V3);
-    const int r = (int)(vox % V3);
-    const int d = r / (V * V), h = (r / V) % V, w = r % V;
-#pragma unroll 1
-    for (int dz = -1; dz <= 1; ++dz) {
-      const int id = min(max(d + dz, 0), V - 1);
-#pragma unroll 1
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int ih = min(max(h + dy, 0), V - 1);
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-          const int iw = min(max(w + dx, 0), V - 1);
-          const float* xp = x + ((((size_t)b * V + id) * V + ih) * V + iw) * C + part * CPL;
-          const float* wp = sw + ((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)) * C + part * CPL;
-#pragma unroll
-          for (int c = 0; c < CPL; c += 4) {
-            const float4 xv = *reinterpret_cast<const float4*>(xp + c);
-            const float4 wv = *reinterpret_cast<const float4*>(wp + c);
-            acc = fmaf(xv.x, wv.x, acc);
-            acc = fmaf(xv.y, wv.y, acc);
-            acc = fmaf(xv.z, wv.z, acc);
-            acc = fmaf(xv.w, wv.w, acc);
-          }
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int o = LPV / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (valid && part == 0) y[vox] = acc + bias[0];
-}
-
-// ---------------------------------------------------------------- spatial soft-argmax + max
-// SpatialSoftmax3D (network_utils.py:773-809, temperature 0.01) and AdaptiveMaxPool3d(1), over
-// channels-last x [B,P,C].  Pass 1: each block reduces a chunk of positions for all channels with
-// an online softmax (running max, rescaled sums); pass 2 merges the chunks.
-// partial layout: [B][chunks][6][C] = (max of x/T, sum, sx, sy, sz, max of x)
-__device__ __forceinline__ float lin_coord(int i, int n) {
-  // np.linspace(-1, 1, n)[i] evaluated in double then rounded to fp32 (network_utils.py:783-792)
-  if (n == 1) return -1.f;
-  if (i == n - 1) return 1.f;
-  return (float)(-1.0 + (double)i * (2.0 / (double)(n - 1)));
-}
-
-static __global__ void __launch_bounds__(256)
-spatial_softmax_partial_kernel(const float* __restrict__ x, int P, int C, int Dd, int Hh, int Ww,
-                               int chunk, float* __restrict__ partial) {
-  const int b = blockIdx.y, ck = blockIdx.x, chunks = gridDim.x;
-  const int lanes_p = 256 / C;  // position lanes per block (C = 64 -> 4, 128 -> 2, 192 -> 1)
-  const int c = threadIdx.x % C, pl = threadIdx.x / C;
-  const int p_begin = ck * chunk, p_end = min(P, p_begin + chunk);
-  float m = -INFINITY, s = 0.f, sx = 0.f, sy = 0.f, sz = 0.f, rawm = -INFINITY;
-  if (pl < lanes_p) {
-    for (int p = p_begin + pl; p < p_end; p += lanes_p) {
-      const float raw = x[((size_t)b * P + p) * C + c];
-      rawm = fmaxf(rawm, raw);
-      const float v = __fdiv_rn(raw, 0.01f);  // feature / temperature
-      const int d = p / (Hh * Ww), h = (p / Ww) % Hh, w = p % Ww;
-      // meshgrid(indexing='xy') quirk: pos_x varies along tensor axis H, pos_y along D, pos_z along W
-      const float px = lin_coord(h, Hh), py = lin_coord(d, Dd), pz = lin_coord(w, Ww);
-      if (v > m) {
-        const float sc = expf(m - v);  // exp(-inf) = 0 on the first element
-        s *= sc; sx *= sc; sy *= sc; sz *= sc;
-        m = v;
-      }
-      const float e = expf(v - m);
-      s += e;
-      sx = fmaf(e, px, sx);
-      sy = fmaf(e, py, sy);
-      sz = fmaf(e, pz, sz);
-    }
-  }
-  __shared__ float sm[6][256];
-  sm[0][threadIdx.x] = m; sm[1][threadIdx.x] = s; sm[2][threadIdx.x] = sx;
-  sm[3][threadIdx.x] = sy; sm[4][threadIdx.x] = sz; sm[5][threadIdx.x] = rawm;
-  __syncthreads();
-  if (threadIdx.x < C) {
-    float M = -INFINITY;
-    for (int l = 0; l < lanes_p; ++l) M = fmaxf(M, sm[0][l * C + c]);
-    float S = 0.f, SX = 0.f, SY = 0.f, SZ = 0.f, RM = -INFINITY;
-    for (int l = 0; l < lanes_p; ++l) {
-      RM = fmaxf(RM, sm[5][l * C + c]);
-      const float ml = sm[0][l * C + c];
-      const float sc = (ml == -INFINITY) ? 0.f : expf(ml - M);
-      S += sm[1][l * C + c] * sc;
-      SX += sm[2][l * C + c] * sc;
-      SY += sm[3][l * C + c] * sc;
-      SZ += sm[4][l * C + c] * sc;
-    }
-    float* o = partial + (((size_t)b * chunks + ck) * 6) * C + c;
-    o[0] = M; o[C] = S; o[2 * C] = SX; o[3 * C] = SY; o[4 * C] = SZ; o[5 * C] = RM;
-  }
-}
-
-static __global__ void __launch_bounds__(256)
-spatial_softmax_merge_kernel(const float* __restrict__ partial, int chunks, int C,
-                             float* __restrict__ ss, int ss_stride, float* __restrict__ mx,
-                             int mx_stride) {
-  const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float* p = partial + ((size_t)b * chunks * 6) * C + c;
-    float M = -INFINITY, RM = -INFINITY;
-    for (int k = 0; k < chunks; ++k) M = fmaxf(M, p[(size_t)k * 6 * C]);
-    float S = 0.f, SX = 0.f, SY = 0.f, SZ = 0.f;
-    for (int k = 0; k < chunks; ++k) {
-      const float* q = p + (size_t)k * 6 * C;
-      RM = fmaxf(RM, q[5 * C]);
-      const float sc = (q[0] == -INFINITY) ? 0.f : expf(q[0] - M);
-      S += q[C] * sc; SX += q[2 * C] * sc; SY += q[3 * C] * sc; SZ += q[4 * C] * sc;
-    }
-    float* o = ss + (size_t)b * ss_stride + c * 3;
-    o[0] = SX / S; o[1] = SY / S; o[2] = SZ / S;
-    if (mx) mx[(size_t)b * mx_stride + c] = RM;  // AdaptiveMaxPool3d(1)
-  }
-}
-
 // ---------------------------------------------------------------- token assembly
 // ins_seq[b, j, :]   (j < nl)  = lang_lin[b, j, :] + pos[j, :]
 // ins_seq[b, nl+t, :]          = concat(patch[b, t, :im], p[b, :], (p2[b, :])) + pos[nl+t, :]

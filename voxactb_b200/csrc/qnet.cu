@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "ops.cuh"
 #include "simt_gemm.cuh"
+#include "stream_ops.cuh"
 #include "dispatch.cuh"
 #include <vector>
 
@@ -120,6 +121,7 @@ static void weight_specs(const Dims& m, const void* const* params, const Prepare
   v.push_back({p.up0_wt, 64, k3 * m.C});
   v.push_back({p.up1_fold, (long long)m.s * m.s * m.s * 64, 27 * 64});
   v.push_back({p.final_wt, 64, 27 * 128});
+  v.push_back({p.q_cross, m.L, cq});
   v.push_back({P(VXB_P_LANG_W), m.C, 512});
   v.push_back({P(VXB_P_CROSS_Q_W), cq, m.D});
   v.push_back({P(VXB_P_CROSS_KV_W), 2 * cq, m.C});
@@ -162,8 +164,10 @@ struct Work {
   float *ss_part;                // spatial softmax partials
   char *scratch;                 // operand planes of the tcgen05 path
   size_t scratch_bytes;
+  // plane-domain transformer buffers (bf16 hi/lo; element counts per plane below)
+  __nv_bfloat16 *px[2], *pq[2], *pk[2], *pvt[2], *pp[2], *po[2], *pg[2];
+  float *rowmax, *rowsum;
 };
-static int ss_chunks(size_t P) { return (int)std::min<size_t>(1024, std::max<size_t>(1, (P + 1023) / 1024)); }
 
 static size_t sim_floats(const Dims& m, int B) {
   auto pad4 = [](size_t v) { return (v + 3) / 4 * 4; };
@@ -199,7 +203,7 @@ static void carve_work(const Dims& m, int B, Arena& a, Work& w) {
   w.h2 = a.get<float>((size_t)B * 64);
   w.rgc = a.get<float>((size_t)B * (3 * m.R + m.G + m.Cc));
   w.sim = a.get<float>(sim_floats(m, B));
-  w.ss_part = a.get<float>((size_t)B * ss_chunks(m.V3) * 6 * 256);
+  w.ss_part = a.get<float>(std::max(ss_partial_floats(m.V3, B, 64), ss_partial_floats((size_t)m.T, B, m.C)));
   // scratch for operand planes: the largest of the GEMM / conv shapes of the forward
   size_t sb = 0;
   sb = std::max(sb, umma::linear_scratch_bytes((long long)B * m.L, 8 * m.D, 4 * m.D, false));
@@ -209,6 +213,27 @@ static void carve_work(const Dims& m, int B, Arena& a, Work& w) {
   sb = std::max(sb, umma::upconv_scratch_bytes(B, m.S, 64));
   w.scratch_bytes = sb + 4096;
   w.scratch = a.get<char>(w.scratch_bytes);
+  {
+    using umma::pad8;
+    const size_t cq = (size_t)m.ch * m.cdh, lq = (size_t)m.lh * m.ldh, Bz = (size_t)B;
+    const size_t n_px = std::max(Bz * m.n * m.C, Bz * m.L * m.D);
+    const size_t n_pq = std::max(std::max(Bz * m.L * lq, Bz * m.T * cq), Bz * m.L * cq);
+    const size_t n_pk = std::max(Bz * m.n * cq, Bz * m.L * std::max(lq, cq));
+    const size_t n_pvt = std::max(Bz * cq * pad8(m.n), Bz * std::max(lq, cq) * pad8(m.L));
+    const size_t n_pp = std::max(std::max(Bz * m.ch * m.L * pad8(m.n), Bz * m.lh * m.L * pad8(m.L)),
+                                 Bz * m.ch * m.T * pad8(m.L));
+    const size_t n_po = std::max(Bz * m.L * std::max(lq, cq), Bz * m.T * cq);
+    const size_t n_pg = Bz * m.L * 4 * m.D;
+    const size_t n_rs = std::max(Bz * std::max(m.ch, m.lh) * m.L, Bz * m.ch * m.T);
+    for (int i = 0; i < 2; ++i) {
+      w.px[i] = a.get<__nv_bfloat16>(n_px); w.pq[i] = a.get<__nv_bfloat16>(n_pq);
+      w.pk[i] = a.get<__nv_bfloat16>(n_pk); w.pvt[i] = a.get<__nv_bfloat16>(n_pvt);
+      w.pp[i] = a.get<__nv_bfloat16>(n_pp); w.po[i] = a.get<__nv_bfloat16>(n_po);
+      w.pg[i] = a.get<__nv_bfloat16>(n_pg);
+    }
+    w.rowmax = a.get<float>(n_rs);
+    w.rowsum = a.get<float>(n_rs);
+  }
 }
 
 // ---- stage profiler: CUDA events on the caller's stream at the stage boundaries of the forward
@@ -254,17 +279,8 @@ static int layernorm(const float* x, const float* w, const float* b, float* y, s
 static int spatial_softmax(const float* x, int B, int Dd, int Hh, int Ww, int C, float* ss,
                            int ss_stride, float* mx, int mx_stride, float* partial,
                            cudaStream_t st) {
-  const size_t P = (size_t)Dd * Hh * Ww;
-  VXB_CHECK_ARG(C <= 256 && C > 0, "spatial_softmax: C=%d > 256", C);
-  const int chunks = ss_chunks(P);
-  const int chunk = (int)((P + chunks - 1) / chunks);
-  COUNT_LAUNCH();
-  spatial_softmax_partial_kernel<<<dim3(chunks, B), 256, 0, st>>>(x, (int)P, C, Dd, Hh, Ww, chunk, partial);
-  VXB_LAUNCH_CHECK();
-  COUNT_LAUNCH();
-  spatial_softmax_merge_kernel<<<B, 256, 0, st>>>(partial, chunks, C, ss, ss_stride, mx, mx_stride);
-  VXB_LAUNCH_CHECK();
-  return VXB_OK;
+  g_launches += 2;
+  return spatial_softmax_run(x, B, Dd, Hh, Ww, C, ss, ss_stride, mx, mx_stride, partial, st);
 }
 
 static int attention(const float* q, int ldq, long long qbs, const float* k, const float* v,
@@ -312,6 +328,159 @@ static int feed_forward(Ctx& cx, const Dims& m, int B, Work& w, const float* nw,
     VXB_TRY(lin(cx, w.ffg, 4 * m.D, w2, 4 * m.D, b2, w.x, (int)rows, m.D, w.x, m.D, (int)rows, m.D,
                  4 * m.D, 1.f, -1.f, math_mode));
   return VXB_OK;
+}
+
+// ---- plane-domain (tcgen05) transformer: every GEMM consumes and produces bf16 hi/lo planes, attention is
+// three GEMMs (row max, exp + row sum, P V / sum) -- no fp32 score matrix, no separate split passes.
+static umma::Planes planes_of(__nv_bfloat16* const b[2], long long ld) { return umma::Planes{b[0], b[1], ld}; }
+static umma::Planes sub_rows(const umma::Planes& p, long long row0) {
+  return umma::Planes{p.hi + row0 * p.ld, p.lo + row0 * p.ld, p.ld};
+}
+static int need(const umma::Planes* p, const char* what) {
+  if (!p) {
+    set_error("qnet: weight planes for %s were not prepared", what);
+    return VXB_E_BADARG;
+  }
+  return VXB_OK;
+}
+#define WPLANES(var, ptr)                     \
+  const umma::Planes* var = cx.find(ptr);     \
+  VXB_TRY(need(var, #ptr))
+
+// x = x + FF(LN(x))
+static int feed_forward_planes(Ctx& cx, const Dims& m, int B, Work& w, const float* nw, const float* nb,
+                               const float* w0, const float* b0, const float* w2, const float* b2) {
+  const long long rows = (long long)B * m.L;
+  WPLANES(W0, w0);
+  WPLANES(W2, w2);
+  const umma::Planes xn = planes_of(w.px, m.D), pg = planes_of(w.pg, 4 * m.D);
+  g_launches += 4;
+  VXB_TRY(umma::layernorm_planes(w.x, 0, (int)rows, nw, nb, xn, rows, m.D, cx.st));
+  umma::LinOut o1;
+  o1.bias = b0; o1.out_f32 = w.ffh; o1.ldc = 8 * m.D;
+  VXB_TRY(umma::linear_planes(xn, rows, m.D, *W0, 8 * m.D, o1, cx.st));
+  VXB_TRY(umma::geglu_planes(w.ffh, pg, rows, 4 * m.D, cx.st));
+  umma::LinOut o2;
+  o2.bias = b2; o2.residual = w.x; o2.res_rows = (int)rows; o2.ldr = m.D; o2.out_f32 = w.x; o2.ldc = m.D;
+  return umma::linear_planes(pg, rows, 4 * m.D, *W2, m.D, o2, cx.st);
+}
+
+// K planes and V^T planes of a context already LayerNorm'ed into `ctx` [B*Nk, Kdim]
+static int project_kv(Ctx& cx, Work& w, const umma::Planes& ctx, int B, int Nk, int Kdim, const float* wkv, int inner,
+                      umma::Planes& pk, umma::Planes& pvt) {
+  WPLANES(Wkv, wkv);
+  pk = planes_of(w.pk, inner);
+  pvt = planes_of(w.pvt, umma::pad8(Nk));
+  g_launches += 2;
+  umma::LinOut ok;
+  ok.out_planes = &pk;
+  VXB_TRY(umma::linear_planes(ctx, (long long)B * Nk, Kdim, *Wkv, inner, ok, cx.st));
+  umma::LinOut ov;
+  ov.out_planes = &pvt; ov.transposed = 1; ov.batches = B;
+  return umma::linear_planes(ctx, (long long)B * Nk, Kdim, sub_rows(*Wkv, inner), inner, ov, cx.st);
+}
+
+static int transformer_planes(Ctx& cx, const vxb_qnet_desc* d, const Dims& m, const void* const* params,
+                              const Prepared& pw, Work& w, int B) {
+  auto P = [&](int slot) { return (const float*)params[slot]; };
+  auto PL = [&](int layer, int slot) {
+    return (const float*)params[VXB_P_FIXED_COUNT + layer * VXB_P_LAYER_STRIDE + slot];
+  };
+  cudaStream_t st = cx.st;
+  const int cq = m.ch * m.cdh, lq = m.lh * m.ldh;
+  const long long rowsL = (long long)B * m.L;
+  for (int it = 0; it < d->iterations; ++it) {
+    // encoder cross attention: x = Attn(LN(x), ctx = LN_ctx(ins)) + x                 perceiver_lang_io.py:431
+    umma::Planes ctx = planes_of(w.px, m.C), pk, pvt;
+    ++g_launches;
+    VXB_TRY(umma::layernorm_planes(w.ins, 0, B * m.n, P(VXB_P_CROSS_NORMCTX_W), P(VXB_P_CROSS_NORMCTX_B), ctx,
+                                   (long long)B * m.n, m.C, st));
+    VXB_TRY(project_kv(cx, w, ctx, B, m.n, m.C, P(VXB_P_CROSS_KV_W), cq, pk, pvt));
+    umma::Planes q;
+    int q_batched = 0;
+    if (it == 0) {
+      WPLANES(Qc, pw.q_cross);   // to_q(LN(latents)) is batch independent on the first iteration
+      q = *Qc;
+    } else {
+      WPLANES(Wq, P(VXB_P_CROSS_Q_W));
+      const umma::Planes xn = planes_of(w.px, m.D);
+      q = planes_of(w.pq, cq);
+      q_batched = 1;
+      g_launches += 2;
+      VXB_TRY(umma::layernorm_planes(w.x, 0, (int)rowsL, P(VXB_P_CROSS_NORM_W), P(VXB_P_CROSS_NORM_B), xn, rowsL, m.D, st));
+      umma::LinOut oq;
+      oq.out_planes = &q;
+      VXB_TRY(umma::linear_planes(xn, rowsL, m.D, *Wq, cq, oq, st));
+    }
+    umma::Planes po = planes_of(w.po, cq);
+    g_launches += 4;
+    VXB_TRY(umma::attention_planes(q, q_batched, pk, pvt, B, m.ch, m.L, m.n, m.cdh, 1.f / sqrtf((float)m.cdh), w.rowmax,
+                                   w.rowsum, planes_of(w.pp, umma::pad8(m.n)), po, st));
+    {
+      WPLANES(Wo, P(VXB_P_CROSS_OUT_W));
+      umma::LinOut oo;
+      oo.bias = P(VXB_P_CROSS_OUT_B);
+      oo.residual = it == 0 ? P(VXB_P_LATENTS) : w.x; oo.res_rows = it == 0 ? m.L : (int)rowsL; oo.ldr = m.D;
+      oo.out_f32 = w.x; oo.ldc = m.D;
+      ++g_launches;
+      VXB_TRY(umma::linear_planes(po, rowsL, cq, *Wo, m.D, oo, st));
+    }
+    VXB_TRY(feed_forward_planes(cx, m, B, w, P(VXB_P_CROSS_FF_NORM_W), P(VXB_P_CROSS_FF_NORM_B), P(VXB_P_CROSS_FF0_W),
+                                P(VXB_P_CROSS_FF0_B), P(VXB_P_CROSS_FF2_W), P(VXB_P_CROSS_FF2_B)));
+    // latent self-attention stack                                                       :435-437
+    for (int l = 0; l < m.depth; ++l) {
+      const umma::Planes xn = planes_of(w.px, m.D);
+      umma::Planes ql = planes_of(w.pq, lq);
+      WPLANES(Wq, PL(l, VXB_PL_Q_W));
+      g_launches += 2;
+      VXB_TRY(umma::layernorm_planes(w.x, 0, (int)rowsL, PL(l, VXB_PL_ATTN_NORM_W), PL(l, VXB_PL_ATTN_NORM_B), xn, rowsL,
+                                     m.D, st));
+      umma::LinOut oq;
+      oq.out_planes = &ql;
+      VXB_TRY(umma::linear_planes(xn, rowsL, m.D, *Wq, lq, oq, st));
+      VXB_TRY(project_kv(cx, w, xn, B, m.L, m.D, PL(l, VXB_PL_KV_W), lq, pk, pvt));
+      umma::Planes pol = planes_of(w.po, lq);
+      g_launches += 4;
+      VXB_TRY(umma::attention_planes(ql, 1, pk, pvt, B, m.lh, m.L, m.L, m.ldh, 1.f / sqrtf((float)m.ldh), w.rowmax,
+                                     w.rowsum, planes_of(w.pp, umma::pad8(m.L)), pol, st));
+      WPLANES(Wo, PL(l, VXB_PL_OUT_W));
+      umma::LinOut oo;
+      oo.bias = PL(l, VXB_PL_OUT_B); oo.residual = w.x; oo.res_rows = (int)rowsL; oo.ldr = m.D;
+      oo.out_f32 = w.x; oo.ldc = m.D;
+      ++g_launches;
+      VXB_TRY(umma::linear_planes(pol, rowsL, lq, *Wo, m.D, oo, st));
+      VXB_TRY(feed_forward_planes(cx, m, B, w, PL(l, VXB_PL_FF_NORM_W), PL(l, VXB_PL_FF_NORM_B), PL(l, VXB_PL_FF0_W),
+                                  PL(l, VXB_PL_FF0_B), PL(l, VXB_PL_FF2_W), PL(l, VXB_PL_FF2_B)));
+    }
+  }
+  return VXB_OK;
+}
+
+// decoder cross attention: queries = LN(ins) voxel rows, context = LN_ctx(x); no residual      :440-448
+static int decoder_planes(Ctx& cx, const Dims& m, const void* const* params, Work& w, int B) {
+  auto P = [&](int slot) { return (const float*)params[slot]; };
+  cudaStream_t st = cx.st;
+  const int cq = m.ch * m.cdh;
+  const long long rowsT = (long long)B * m.T, rowsL = (long long)B * m.L;
+  WPLANES(Wq, P(VXB_P_DEC_Q_W));
+  WPLANES(Wo, P(VXB_P_DEC_OUT_W));
+  umma::Planes qn = planes_of(w.px, m.C), q = planes_of(w.pq, cq);
+  g_launches += 3;
+  VXB_TRY(umma::layernorm_planes(w.ins + (size_t)m.nl * m.C, (size_t)m.n * m.C, m.T, P(VXB_P_DEC_NORM_W),
+                                 P(VXB_P_DEC_NORM_B), qn, rowsT, m.C, st));
+  umma::LinOut oq;
+  oq.out_planes = &q;
+  VXB_TRY(umma::linear_planes(qn, rowsT, m.C, *Wq, cq, oq, st));
+  umma::Planes xn = planes_of(w.px, m.D), pk, pvt;
+  VXB_TRY(umma::layernorm_planes(w.x, 0, (int)rowsL, P(VXB_P_DEC_NORMCTX_W), P(VXB_P_DEC_NORMCTX_B), xn, rowsL, m.D, st));
+  VXB_TRY(project_kv(cx, w, xn, B, m.L, m.D, P(VXB_P_DEC_KV_W), cq, pk, pvt));
+  umma::Planes po = planes_of(w.po, cq);
+  g_launches += 5;
+  VXB_TRY(umma::attention_planes(q, 1, pk, pvt, B, m.ch, m.T, m.L, m.cdh, 1.f / sqrtf((float)m.cdh), w.rowmax, w.rowsum,
+                                 planes_of(w.pp, umma::pad8(m.L)), po, st));
+  umma::LinOut oo;
+  oo.bias = P(VXB_P_DEC_OUT_B); oo.out_f32 = w.dec; oo.ldc = m.C;
+  return umma::linear_planes(po, rowsT, cq, *Wo, m.C, oo, st);
 }
 
 static int conv_weight_prepare(const float* w, float* o, int Co, int Ci, int k3, cudaStream_t st) {
@@ -418,14 +587,11 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   const size_t MV = (size_t)B * m.V3;
 
   STAGE_MARK();  // 0: input_preprocess
-  // (1) d0 = act(conv1x1(grid))                                   perceiver_lang_io.py:357
-  COUNT_LAUNCH();
-  pointwise_conv_kernel<10><<<cdiv(MV, 64), 256, (64 * 10 + 64) * sizeof(float), st>>>(
-      grid, P(VXB_P_INPRE_W), P(VXB_P_INPRE_B), w.d0, MV, 64, slope);
-  VXB_LAUNCH_CHECK();
-  STAGE_MARK();  // 1: ss0 + maxpool
-  // (2) feats[0:256] = [ss0(d0), maxpool(d0)]                      :360
-  VXB_TRY(spatial_softmax(w.d0, B, m.V, m.V, m.V, 64, w.feats, m.flat, w.feats + 192, m.flat, w.ss_part, st));
+  // (1) d0 = act(conv1x1(grid)), fused with (2) feats[0:256] = [ss0(d0), maxpool(d0)]   perceiver_lang_io.py:357-360
+  g_launches += 2;
+  VXB_TRY(input_preprocess_ss_run<10>(grid, P(VXB_P_INPRE_W), P(VXB_P_INPRE_B), slope, w.d0, B, m.V, m.V, m.V, 64,
+                                      w.feats, m.flat, w.feats + 192, m.flat, w.ss_part, st));
+  STAGE_MARK();  // 1: (fused into stage 0)
   STAGE_MARK();  // 2: patchify
   // (3) patchify conv k, stride s, replicate pad                   :363
   COUNT_LAUNCH();
@@ -451,6 +617,12 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
 
   STAGE_MARK();  // 4: transformer (cross + latent self-attention + FF)
   // (5) latents: x = repeat(latents) is never materialised; the first residual reads latents[m % L]   :425
+  const bool planes_path = mm == VXB_MATH_BF16X3 && m.cdh == 64 && m.ldh == 64 && m.C % 8 == 0 && m.D % 8 == 0;
+  if (planes_path) {
+    VXB_TRY(transformer_planes(cx, d, m, params, pw, w, B));
+    STAGE_MARK();  // 5: decoder cross attention + ss1
+    VXB_TRY(decoder_planes(cx, m, params, w, B));
+  } else {
   const int cq = m.ch * m.cdh;   // cross-attention inner dim
   const int lq = m.lh * m.ldh;   // latent-attention inner dim
   for (int it = 0; it < d->iterations; ++it) {
@@ -508,6 +680,7 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
                     cq, (long long)m.T * cq, B, m.ch, m.T, m.L, m.cdh, 1.f / sqrtf((float)m.cdh), w.sim, mm, st));
     VXB_TRY(lin(cx, w.att, cq, P(VXB_P_DEC_OUT_W), cq, P(VXB_P_DEC_OUT_B), nullptr, 1, 0, w.dec, m.C, B * m.T,
                  m.C, cq, 1.f, -1.f, mm));
+  }
   // (9) feats[256 : 256+4C] = [ss1(dec), maxpool(dec)]                           :451
   VXB_TRY(spatial_softmax(w.dec, B, m.S, m.S, m.S, m.C, w.feats + 256, m.flat, w.feats + 256 + 3 * m.C,
                           m.flat, w.ss_part, st));
@@ -528,8 +701,7 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   STAGE_MARK();  // 9: trans decoder
   // (12) trans decoder: conv3 64 -> 1, no activation                            :465
   COUNT_LAUNCH();
-  conv3_to1_kernel<64><<<cdiv(MV, 32), 256, 0, st>>>(w.u, pw.trans_wt, P(VXB_P_TRANS_B), q_trans, B, m.V);
-  VXB_LAUNCH_CHECK();
+  VXB_TRY(trans_stencil_run<64>(w.u, pw.trans_wt, P(VXB_P_TRANS_B), q_trans, B, m.V, st));
   STAGE_MARK();  // 10: ss_final + heads
   // (13) feats[256+4C :] = [ss_final(u), maxpool(u)], MLP heads                 :470-483
   const int off = 256 + 4 * m.C;

@@ -170,7 +170,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
         const int z = tile / tiles_per_z, tz = tile % tiles_per_z;
         const int zb = z / p.Hz, zh = z % p.Hz;
         const int mt = tz / p.n_tiles, nt = tz % p.n_tiles;
-        const int m0 = mt * BM + zb * p.a_row_zb;
+        const int m0 = mt * BM + zb * p.a_row_zb + zh * p.a_row_zh;
         const int n0 = nt * NT + zb * p.w_row_zb + zh * p.w_row_zh;
         for (int kb = 0; kb < pl.num_kb; ++kb) {
           int a_row = 0, a_col = kb * BK, a_src = 0;
@@ -186,13 +186,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
           const int w_col = kb * BK + zh * p.w_col_zh;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = smem + stage * L::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           const CUtensorMap* ah = a_src ? &mapA1h : &mapA0h;
           const CUtensorMap* al = a_src ? &mapA1l : &mapA0l;
-          tma_load_2d(ah, &full_bar[stage], s, a_col, m0 + a_row);
-          tma_load_2d(al, &full_bar[stage], s + L::A_BYTES, a_col, m0 + a_row);
-          tma_load_2d(&mapWh, &full_bar[stage], s + 2 * L::A_BYTES, w_col, n0);
-          tma_load_2d(&mapWl, &full_bar[stage], s + 2 * L::A_BYTES + L::B_BYTES, w_col, n0);
+          if (p.terms == 1) {
+            mbar_expect_tx(&full_bar[stage], L::A_BYTES + L::B_BYTES);
+            tma_load_2d(ah, &full_bar[stage], s, a_col, m0 + a_row);
+            tma_load_2d(&mapWh, &full_bar[stage], s + 2 * L::A_BYTES, w_col, n0);
+          } else {
+            mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            tma_load_2d(ah, &full_bar[stage], s, a_col, m0 + a_row);
+            tma_load_2d(al, &full_bar[stage], s + L::A_BYTES, a_col, m0 + a_row);
+            tma_load_2d(&mapWh, &full_bar[stage], s + 2 * L::A_BYTES, w_col, n0);
+            tma_load_2d(&mapWl, &full_bar[stage], s + 2 * L::A_BYTES + L::B_BYTES, w_col, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -223,8 +229,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
             const uint64_t b_hi = make_desc(sb_hi + k * 32, 1024);
             const uint64_t b_lo = make_desc(sb_lo + k * 32, 1024);
             tc_mma_bf16(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0);
-            tc_mma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
-            tc_mma_bf16(d_tmem, a_lo, b_hi, idesc, 1);
+            if (p.terms == 3) {
+              tc_mma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
+              tc_mma_bf16(d_tmem, a_lo, b_hi, idesc, 1);
+            }
           }
           tc_commit(&empty_bar[stage]);             // smem slot reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -264,12 +272,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
         row_ok = row_ok && qd >= 0 && qd < V && qh >= 0 && qh < V && qw >= 0 && qw < V;
         if (e.row_mode == ROWS_CONV_FLAT && !e.out_padded) orow = (((long long)qb * V + qd) * V + qh) * V + qw;
       }
+      const long long rs_off = zb * p.rs_zb + zh * p.rs_zh;
+      float row_acc = (e.mode == EPI_ROWMAX) ? -INFINITY : 0.f;
+      float row_sub = 0.f, row_inv = 1.f;
+      if (row_ok && e.mode == EPI_EXP) row_sub = e.row_sub[rs_off + m];
+      if (row_ok && e.mode == EPI_STORE && e.row_div) row_inv = 1.f / e.row_div[rs_off + m];
 #pragma unroll 1
       for (int c0 = 0; c0 < NT; c0 += 32) {
         uint32_t v[32];
         tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + c0), v);
         const int n = n0 + c0;
         if (row_ok && n < e.N) {
+          if (e.mode == EPI_ROWMAX) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < e.N) row_acc = fmaxf(row_acc, __uint_as_float(v[j]) * e.alpha);
+            continue;
+          }
           if (e.row_mode == ROWS_PHASE) {
             // 64-column block = one polyphase: fine voxel = s*q + r in the padded fine grid
             const int ph = n / 64;
@@ -280,16 +299,29 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
           }
           const int ncol = (e.row_mode == ROWS_PHASE) ? (n % 64) : n;   // column inside the output row
           float f[32];
+          if (e.mode == EPI_EXP) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float t = __uint_as_float(v[j]) * e.alpha;
-            const int nn = n + j;
-            if (nn < e.N) {
-              if (e.bias) t += e.bias[(e.row_mode == ROWS_PHASE) ? (ncol + j) : nn];
-              if (e.act_slope >= 0.f) t = t > 0.f ? t : t * e.act_slope;
-              if (e.residual) t += e.residual[(long long)(m % e.res_rows) * e.ldr + nn];
+            for (int j = 0; j < 32; ++j) {
+              float t = 0.f;
+              if (n + j < e.N) {
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(__uint_as_float(v[j]), e.alpha, -row_sub)));
+                row_acc += t;
+              }
+              f[j] = t;
             }
-            f[j] = t;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float t = __uint_as_float(v[j]) * e.alpha;
+              const int nn = n + j;
+              if (nn < e.N) {
+                if (e.bias) t += e.bias[(e.row_mode == ROWS_PHASE) ? (ncol + j) : nn];
+                if (e.act_slope >= 0.f) t = t > 0.f ? t : t * e.act_slope;
+                if (e.residual) t += e.residual[(long long)(m % e.res_rows) * e.ldr + nn];
+                t *= row_inv;
+              }
+              f[j] = t;
+            }
           }
           const bool full = n + 31 < e.N;
           if (out_f32) {
@@ -314,17 +346,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
             } else {
               __nv_bfloat16* dh = out_hi + orow * e.ldp + ncol;
               __nv_bfloat16* dl = out_lo + orow * e.ldp + ncol;
-              if (full && ((e.ldp & 7) == 0)) {
+              // columns up to the 8-aligned end of the row may be written (zeros beyond N): planes are padded to ld
+              if ((full || e.mode == EPI_EXP) && ((e.ldp & 7) == 0)) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
-                  __align__(16) __nv_bfloat16 h8[8], l8[8];
+                  if (n + j < e.ldp) {
+                    __align__(16) __nv_bfloat16 h8[8], l8[8];
 #pragma unroll
-                  for (int t = 0; t < 8; ++t) {
-                    h8[t] = __float2bfloat16_rn(f[j + t]);
-                    l8[t] = __float2bfloat16_rn(f[j + t] - __bfloat162float(h8[t]));
+                    for (int t = 0; t < 8; ++t) {
+                      h8[t] = __float2bfloat16_rn(f[j + t]);
+                      l8[t] = __float2bfloat16_rn(f[j + t] - __bfloat162float(h8[t]));
+                    }
+                    *reinterpret_cast<uint4*>(dh + j) = *reinterpret_cast<const uint4*>(h8);
+                    *reinterpret_cast<uint4*>(dl + j) = *reinterpret_cast<const uint4*>(l8);
                   }
-                  *reinterpret_cast<uint4*>(dh + j) = *reinterpret_cast<const uint4*>(h8);
-                  *reinterpret_cast<uint4*>(dl + j) = *reinterpret_cast<const uint4*>(l8);
                 }
               } else {
                 for (int j = 0; j < 32; ++j) {
@@ -339,6 +374,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
           }
         }
       }
+      if (row_ok && e.mode == EPI_ROWMAX) {
+        float* a = e.row_stat + rs_off + m;
+        if (row_acc >= 0.f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(row_acc));
+        else atomicMin(reinterpret_cast<unsigned int*>(a), __float_as_uint(row_acc));
+      }
+      if (row_ok && e.mode == EPI_EXP) atomicAdd(e.row_stat + rs_off + m, row_acc);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);

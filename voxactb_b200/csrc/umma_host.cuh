@@ -24,6 +24,11 @@ struct KPlan {
 };
 
 enum { ROWS_PLAIN = 0, ROWS_CONV_FLAT = 1, ROWS_PHASE = 2 };
+// epilogue value modes (attention runs as three GEMMs without ever storing fp32 scores):
+//   EPI_STORE   out = act(alpha*acc + bias) + residual, optionally divided by row_div[row]
+//   EPI_ROWMAX  row_stat[row] = max(row_stat[row], max_n alpha*acc)            (atomic, nothing stored)
+//   EPI_EXP     p = 2^(alpha*acc - row_sub[row]); row_stat[row] += sum_n p (atomic); p stored as planes
+enum { EPI_STORE = 0, EPI_ROWMAX = 1, EPI_EXP = 2 };
 
 struct Epilogue {
   int M, N;                   // logical extents (rows beyond M / cols beyond N are not stored)
@@ -45,6 +50,10 @@ struct Epilogue {
   __nv_bfloat16* out_lo;
   long long ldp;
   int transpose_planes;       // planes written transposed: element (row, col) -> out[(col) * ldp + row] (V^T for attention)
+  int mode;                   // EPI_*
+  float* row_stat;            // EPI_ROWMAX / EPI_EXP: per-row statistic, indexed rs offset(z) + row
+  const float* row_sub;       // EPI_EXP: per-row value subtracted before exp2
+  const float* row_div;       // EPI_STORE: per-row divisor (softmax normalisation folded into P V)
 };
 
 struct Params {
@@ -53,6 +62,9 @@ struct Params {
   // batching: tile z = zb * Hz + zh; operand bases shift per z (attention heads / batches)
   int batches, Hz;
   int a_row_zb, a_col_zh;        // A: rows per zb, columns per zh
+  int a_row_zh;                  // A: rows per zh
+  int terms;                     // 3 = hi*hi + hi*lo + lo*hi (default), 1 = hi*hi only (lo planes are not loaded)
+  long long rs_zb, rs_zh;        // row statistic element offsets per zb / zh
   int w_row_zb, w_row_zh, w_col_zh;
   long long c_zb, c_zh;          // fp32 output element offsets per zb / zh
   long long p_zb, p_zh;          // plane output element offsets per zb / zh
@@ -93,6 +105,38 @@ size_t upconv_scratch_bytes(int B, int S, int Ci);
 int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out, int B, int S, int Ci, int Co, int s,
                float act_slope, Arena& scratch, cudaStream_t st);
 
+// ---- plane-domain building blocks of the transformer (no fp32 round trips between GEMMs)
+// y = LayerNorm(x) written as planes [rows, n]; input rows may be a strided slice per batch
+int layernorm_planes(const float* x, size_t x_batch_stride, int rows_per_batch, const float* w, const float* b,
+                     Planes out, long long rows, int n, cudaStream_t st);
+// out = h[:, :n] * gelu_erf(h[:, n:]) written as planes [rows, n]
+int geglu_planes(const float* h, Planes out, long long rows, int n, cudaStream_t st);
+struct LinOut {
+  const float* bias = nullptr;
+  float alpha = 1.f, act_slope = -1.f;
+  const float* residual = nullptr;
+  int res_rows = 1, ldr = 0;
+  float* out_f32 = nullptr;
+  long long ldc = 0;
+  const Planes* out_planes = nullptr;   // planes [M, ld] or, with transposed, [batches][N][ld] (ld >= rows per batch)
+  int transposed = 0;
+  int batches = 1;                      // transposed only: M = batches * rows_per_batch
+};
+// C[M,N] = A[M,K] W[N,K]^T with plane operands
+int linear_planes(const Planes& A, long long M, int K, const Planes& W, int N, const LinOut& o, cudaStream_t st);
+// softmax(scale q k^T) v per (batch, head) as three tcgen05 GEMMs (row max, exp + row sum -> P planes, P V / sum).
+// Q [(B or 1)*Nq, H*dh] (q_batched = 0: one Q shared by all batches), K [B*Nk, H*dh], Vt [B*H*dh, pad8(Nk)],
+// P scratch planes [B*H*Nq, pad8(Nk)], O planes [B*Nq, H*dh]; rowmax / rowsum: B*H*Nq floats each.
+int attention_planes(const Planes& Q, int q_batched, const Planes& K, const Planes& Vt, int B, int H, int Nq, int Nk,
+                     int dh, float scale, float* rowmax, float* rowsum, const Planes& P, const Planes& O,
+                     cudaStream_t st);
+
+// unit-test entry: fp32 q/k/v in, fp32 out, through the plane-domain attention (scratch sized by the _bytes query)
+size_t attention_f32_scratch_bytes(int B, int H, int Nq, int Nk, int dh);
+int attention_f32(const float* q, int ldq, long long qbs, const float* k, const float* v, int ldkv, long long kvbs,
+                  float* out, int ldo, long long obs, int B, int H, int Nq, int Nk, int dh, float scale, Arena& scratch,
+                  cudaStream_t st);
+
 inline void params_init(Params& p) {
   memset(&p, 0, sizeof(p));
   p.batches = 1;
@@ -100,6 +144,7 @@ inline void params_init(Params& p) {
   p.ep.alpha = 1.f;
   p.ep.act_slope = -1.f;
   p.ep.res_rows = 1;
+  p.terms = 3;
 }
 
 }  // namespace umma

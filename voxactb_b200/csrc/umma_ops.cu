@@ -174,6 +174,100 @@ int halo_fill(Planes p, int B, int V, int pad, int C, cudaStream_t st) {
   return VXB_OK;
 }
 
+// LayerNorm (eps 1e-5, biased variance; reference PreNorm, perceiver_lang_io.py:56-71) -> planes; warp per row
+static __global__ void __launch_bounds__(256)
+layernorm_planes_kernel(const float* __restrict__ x, size_t x_batch_stride, int rows_per_batch,
+                        const float* __restrict__ w, const float* __restrict__ b,
+                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldp, long long rows, int n) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)(row / rows_per_batch) * x_batch_stride + (size_t)(row % rows_per_batch) * n;
+  float s = 0.f;
+  for (int i = lane * 8; i < n; i += 256) {
+    const float4 a = *reinterpret_cast<const float4*>(xr + i), c = *reinterpret_cast<const float4*>(xr + i + 4);
+    s += (a.x + a.y + a.z + a.w) + (c.x + c.y + c.z + c.w);
+  }
+  s = warp_sum(s);
+  const float mean = s / (float)n;
+  float q = 0.f;
+  for (int i = lane * 8; i < n; i += 256) {
+    const float4 a = *reinterpret_cast<const float4*>(xr + i), c = *reinterpret_cast<const float4*>(xr + i + 4);
+    const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
+    const float d4 = c.x - mean, d5 = c.y - mean, d6 = c.z - mean, d7 = c.w - mean;
+    q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3 + d4 * d4 + d5 * d5 + d6 * d6 + d7 * d7;
+  }
+  q = warp_sum(q);
+  const float rstd = rsqrtf(q / (float)n + 1e-5f);
+  for (int i = lane * 8; i < n; i += 256) {
+    float f[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) f[t] = (xr[i + t] - mean) * rstd * w[i + t] + b[i + t];
+    uint4 hh, ll;
+    split8(f, hh, ll);
+    *reinterpret_cast<uint4*>(hi + row * ldp + i) = hh;
+    *reinterpret_cast<uint4*>(lo + row * ldp + i) = ll;
+  }
+}
+
+int layernorm_planes(const float* x, size_t x_batch_stride, int rows_per_batch, const float* w, const float* b,
+                     Planes out, long long rows, int n, cudaStream_t st) {
+  if (n % 8 || out.ld < n) {
+    set_error("layernorm_planes: n must be a multiple of 8 (n=%d)", n);
+    return VXB_E_BADARG;
+  }
+  layernorm_planes_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, x_batch_stride, rows_per_batch, w, b, out.hi, out.lo, out.ld,
+                                                        rows, n);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// GEGLU (perceiver_lang_io.py:74-77, exact erf gelu) -> planes
+static __global__ void __launch_bounds__(256)
+geglu_planes_kernel(const float* __restrict__ h, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                    long long ldp, long long rows, int n) {
+  const long long total8 = rows * (long long)(n / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (n / 8);
+    const int c = (int)(i % (n / 8)) * 8;
+    const float* a = h + r * 2 * n + c;
+    const float* g = a + n;
+    float f[8];
+#pragma unroll
+    for (int t = 0; t < 8; t += 4) {
+      const float4 av = *reinterpret_cast<const float4*>(a + t);
+      const float4 gv = *reinterpret_cast<const float4*>(g + t);
+      f[t + 0] = av.x * (0.5f * gv.x * (1.f + erff(gv.x * 0.70710678118654752f)));
+      f[t + 1] = av.y * (0.5f * gv.y * (1.f + erff(gv.y * 0.70710678118654752f)));
+      f[t + 2] = av.z * (0.5f * gv.z * (1.f + erff(gv.z * 0.70710678118654752f)));
+      f[t + 3] = av.w * (0.5f * gv.w * (1.f + erff(gv.w * 0.70710678118654752f)));
+    }
+    uint4 hh, ll;
+    split8(f, hh, ll);
+    *reinterpret_cast<uint4*>(hi + r * ldp + c) = hh;
+    *reinterpret_cast<uint4*>(lo + r * ldp + c) = ll;
+  }
+}
+
+int geglu_planes(const float* h, Planes out, long long rows, int n, cudaStream_t st) {
+  if (n % 8 || out.ld < n) {
+    set_error("geglu_planes: n must be a multiple of 8 (n=%d)", n);
+    return VXB_E_BADARG;
+  }
+  const long long total8 = rows * (n / 8);
+  geglu_planes_kernel<<<(int)std::min<long long>((total8 + 255) / 256, 148 * 16), 256, 0, st>>>(h, out.hi, out.lo, out.ld,
+                                                                                                 rows, n);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+static __global__ void rowstat_init_kernel(float* __restrict__ mx, float* __restrict__ sum, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    mx[i] = -INFINITY;
+    sum[i] = 0.f;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ launch
 template <int NT, int STAGES>
 static int launch_t(const CUtensorMap* maps, const Params& p, cudaStream_t st) {
@@ -354,6 +448,163 @@ int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out
   Operand A0{a0, rows, Ci};
   Operand w{Wp, N, 27ll * Ci};
   return gemm(A0, nullptr, w, nt, p, st);
+}
+
+
+
+int linear_planes(const Planes& A, long long M, int K, const Planes& W, int N, const LinOut& o, cudaStream_t st) {
+  Params p;
+  params_init(p);
+  const int nt = pick_ntile(N);
+  p.n_tiles = cdiv(N, nt);
+  p.plan.num_kb = cdiv(K, BK);
+  p.ep.N = N; p.ep.row_mode = ROWS_PLAIN;
+  p.ep.bias = o.bias; p.ep.alpha = o.alpha; p.ep.act_slope = o.act_slope;
+  p.ep.residual = o.residual; p.ep.res_rows = o.res_rows > 0 ? o.res_rows : 1; p.ep.ldr = o.ldr;
+  p.ep.out_f32 = o.out_f32; p.ep.ldc = o.ldc;
+  if (o.out_planes) {
+    p.ep.out_hi = o.out_planes->hi; p.ep.out_lo = o.out_planes->lo; p.ep.ldp = o.out_planes->ld;
+    p.ep.transpose_planes = o.transposed;
+  }
+  if (o.transposed && o.batches > 1) {
+    if (M % o.batches) {
+      set_error("linear_planes: M=%lld not divisible by batches=%d", M, o.batches);
+      return VXB_E_BADARG;
+    }
+    const long long rpb = M / o.batches;
+    p.batches = o.batches;
+    p.a_row_zb = (int)rpb;
+    p.m_tiles = cdiv(rpb, BM);
+    p.ep.M = (int)rpb;
+    p.p_zb = (long long)N * o.out_planes->ld;
+  } else {
+    p.m_tiles = cdiv(M, BM);
+    p.ep.M = (int)M;
+  }
+  Operand a{A, M, K}, w{W, N, K};
+  return gemm(a, nullptr, w, nt, p, st);
+}
+
+int attention_planes(const Planes& Q, int q_batched, const Planes& K, const Planes& Vt, int B, int H, int Nq, int Nk,
+                     int dh, float scale, float* rowmax, float* rowsum, const Planes& P, const Planes& O,
+                     cudaStream_t st) {
+  if (dh != 64) {
+    set_error("attention_planes: dim_head must be 64 (got %d)", dh);
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  const long long nstat = (long long)B * H * Nq;
+  rowstat_init_kernel<<<(int)std::min<long long>((nstat + 255) / 256, 148 * 8), 256, 0, st>>>(rowmax, rowsum, nstat);
+  VXB_LAUNCH_CHECK();
+  const Operand q{Q, (long long)(q_batched ? B : 1) * Nq, (long long)H * dh};
+  const Operand k{K, (long long)B * Nk, (long long)H * dh};
+  Params p;
+  params_init(p);
+  p.m_tiles = cdiv(Nq, BM);
+  p.n_tiles = cdiv(Nk, 256);
+  p.plan.num_kb = 1;
+  p.batches = B * H; p.Hz = H;
+  p.a_row_zb = q_batched ? Nq : 0; p.a_col_zh = dh;
+  p.w_row_zb = Nk; p.w_col_zh = dh;
+  p.rs_zb = (long long)H * Nq; p.rs_zh = Nq;
+  p.ep.M = Nq; p.ep.N = Nk; p.ep.row_mode = ROWS_PLAIN;
+  p.ep.alpha = scale * 1.4426950408889634f;   // scores in the log2 domain
+  // (1) row max of the scores from the hi planes alone: a stabiliser, it cancels in p / sum(p)
+  Params p1 = p;
+  p1.terms = 1;
+  p1.ep.mode = EPI_ROWMAX; p1.ep.row_stat = rowmax;
+  VXB_TRY(gemm(q, nullptr, k, 256, p1, st));
+  // (2) P = 2^(s - max) as planes, row sums
+  Params p2 = p;
+  p2.ep.mode = EPI_EXP; p2.ep.row_sub = rowmax; p2.ep.row_stat = rowsum;
+  p2.ep.out_hi = P.hi; p2.ep.out_lo = P.lo; p2.ep.ldp = P.ld;
+  p2.p_zb = (long long)H * Nq * P.ld; p2.p_zh = (long long)Nq * P.ld;
+  VXB_TRY(gemm(q, nullptr, k, 256, p2, st));
+  // (3) O = (P V) / rowsum
+  Params p3;
+  params_init(p3);
+  p3.m_tiles = cdiv(Nq, BM);
+  p3.n_tiles = 1;
+  p3.plan.num_kb = cdiv(Nk, BK);
+  p3.batches = B * H; p3.Hz = H;
+  p3.a_row_zb = H * Nq; p3.a_row_zh = Nq;
+  p3.w_row_zb = H * dh; p3.w_row_zh = dh;
+  p3.rs_zb = (long long)H * Nq; p3.rs_zh = Nq;
+  p3.ep.M = Nq; p3.ep.N = dh; p3.ep.row_mode = ROWS_PLAIN;
+  p3.ep.row_div = rowsum;
+  p3.ep.out_hi = O.hi; p3.ep.out_lo = O.lo; p3.ep.ldp = O.ld;
+  p3.p_zb = (long long)Nq * O.ld; p3.p_zh = dh;
+  const Operand pa{P, (long long)B * H * Nq, (long long)Nk};
+  const Operand vt{Vt, (long long)B * H * dh, (long long)Nk};
+  return gemm(pa, nullptr, vt, 64, p3, st);
+}
+
+
+// ---- fp32 wrapper of attention_planes for the per-op parity test (not used by the Q-network forward)
+static __global__ void split_gather_kernel(const float* __restrict__ x, int ld, long long bs, int B, int rows, int cols,
+                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldp,
+                                           int transposed) {
+  // element (b, r, c) of x -> plane[(b*rows + r), c], or transposed plane[(b*cols + c), r]
+  const long long total = (long long)B * rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols);
+    const int r = (int)((i / cols) % rows);
+    const int b = (int)(i / ((long long)cols * rows));
+    const float f = x[b * bs + (long long)r * ld + c];
+    const __nv_bfloat16 h = __float2bfloat16_rn(f);
+    const __nv_bfloat16 l = __float2bfloat16_rn(f - __bfloat162float(h));
+    const long long o = transposed ? ((long long)b * cols + c) * ldp + r : ((long long)b * rows + r) * ldp + c;
+    hi[o] = h; lo[o] = l;
+  }
+}
+static __global__ void merge_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                           long long ldp, int B, int rows, int cols, float* __restrict__ out, int ldo,
+                                           long long obs) {
+  const long long total = (long long)B * rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols);
+    const int r = (int)((i / cols) % rows);
+    const int b = (int)(i / ((long long)cols * rows));
+    const long long o = ((long long)b * rows + r) * ldp + c;
+    out[b * obs + (long long)r * ldo + c] = __bfloat162float(hi[o]) + __bfloat162float(lo[o]);
+  }
+}
+
+struct AttnScratch { Planes q, k, vt, p, o; float *rmax, *rsum; };
+static void carve_attn(Arena& a, int B, int H, int Nq, int Nk, int dh, AttnScratch& s) {
+  s.q = alloc_planes(a, (long long)B * Nq, (long long)H * dh);
+  s.k = alloc_planes(a, (long long)B * Nk, (long long)H * dh);
+  s.vt = alloc_planes(a, (long long)B * H * dh, pad8(Nk));
+  s.p = alloc_planes(a, (long long)B * H * Nq, pad8(Nk));
+  s.o = alloc_planes(a, (long long)B * Nq, (long long)H * dh);
+  s.rmax = a.get<float>((size_t)B * H * Nq);
+  s.rsum = a.get<float>((size_t)B * H * Nq);
+}
+size_t attention_f32_scratch_bytes(int B, int H, int Nq, int Nk, int dh) {
+  Arena a(nullptr, 0);
+  AttnScratch s;
+  carve_attn(a, B, H, Nq, Nk, dh, s);
+  return a.off;
+}
+int attention_f32(const float* q, int ldq, long long qbs, const float* k, const float* v, int ldkv, long long kvbs,
+                  float* out, int ldo, long long obs, int B, int H, int Nq, int Nk, int dh, float scale, Arena& scratch,
+                  cudaStream_t st) {
+  AttnScratch s;
+  carve_attn(scratch, B, H, Nq, Nk, dh, s);
+  if (!scratch.ok) {
+    set_error("umma attention: scratch too small");
+    return VXB_E_WORKSPACE_TOO_SMALL;
+  }
+  const int inner = H * dh;
+  split_gather_kernel<<<148 * 4, 256, 0, st>>>(q, ldq, qbs, B, Nq, inner, s.q.hi, s.q.lo, s.q.ld, 0);
+  split_gather_kernel<<<148 * 4, 256, 0, st>>>(k, ldkv, kvbs, B, Nk, inner, s.k.hi, s.k.lo, s.k.ld, 0);
+  VXB_CUDA(cudaMemsetAsync(s.vt.hi, 0, plane_elems((long long)B * inner, s.vt.ld) * 2, st));
+  VXB_CUDA(cudaMemsetAsync(s.vt.lo, 0, plane_elems((long long)B * inner, s.vt.ld) * 2, st));
+  split_gather_kernel<<<148 * 4, 256, 0, st>>>(v, ldkv, kvbs, B, Nk, inner, s.vt.hi, s.vt.lo, s.vt.ld, 1);
+  VXB_LAUNCH_CHECK();
+  VXB_TRY(attention_planes(s.q, 1, s.k, s.vt, B, H, Nq, Nk, dh, scale, s.rmax, s.rsum, s.p, s.o, st));
+  merge_planes_kernel<<<148 * 4, 256, 0, st>>>(s.o.hi, s.o.lo, s.o.ld, B, Nq, inner, out, ldo, obs);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
 }
 
 }  // namespace umma
