@@ -111,13 +111,24 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// epilogue staging per warp: a 32 x 32 fp32 transpose tile (row pitch 36 floats: conflict-free 128-bit
+// accesses in both domains) + per-row output metadata
+constexpr int EPI_STAGE_LD = 36;
+struct RowInfo {
+  long long orow[32];   // output row of each accumulator row of the warp, -1 = not stored
+  long long roff[32];   // residual row offset (elements)
+  float rinv[32];       // per-row scale (1 / row_div)
+};
+constexpr int EPI_BYTES_PER_WARP = 32 * EPI_STAGE_LD * 4 + (int)sizeof(RowInfo);
+
 template <int NT, int STAGES>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB per plane
   static constexpr int B_BYTES = NT * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int BAR_BYTES = 1024;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /* alignment slack */;
+  static constexpr int EPI_BYTES = 4 * EPI_BYTES_PER_WARP;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /* alignment slack */;   // dynamic part
 };
 
 template <int NT, int STAGES>
@@ -135,6 +146,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
   uint64_t* acc_full = bars + 2 * STAGES;      // [2] MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * STAGES + 2; // [2] epilogue -> MMA
   uint32_t* tmem_base_smem = (uint32_t*)(bars + 2 * STAGES + 4);
+  __shared__ __align__(16) uint8_t epi_smem[L::EPI_BYTES];   // static: keeps the accesses in the shared window (LDS/STS)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -243,8 +255,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
     }
   } else {
     // ===================================================== epilogue (warps 2..5)
+    // Row domain: lane t owns accumulator row q*32 + t (tcgen05.ld 32x32b).  Values are transposed through a
+    // per-warp shared-memory tile so that the stores (and the residual loads) are column-contiguous:
+    // in the column domain lane l handles rows 4i + l/8 (i = 0..7) and columns 4(l%8)..+3 of a 32-column chunk.
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const Epilogue& e = p.ep;
+    float* stage = reinterpret_cast<float*>(epi_smem + q * EPI_BYTES_PER_WARP);
+    RowInfo* ri = reinterpret_cast<RowInfo*>(stage + 32 * EPI_STAGE_LD);
+    const int tr = lane >> 3, tc = (lane & 7) * 4;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -257,8 +275,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
       float* const out_f32 = e.out_f32 ? e.out_f32 + zb * p.c_zb + zh * p.c_zh : nullptr;
       __nv_bfloat16* const out_hi = e.out_hi ? e.out_hi + zb * p.p_zb + zh * p.p_zh : nullptr;
       __nv_bfloat16* const out_lo = e.out_lo ? e.out_lo + zb * p.p_zb + zh * p.p_zh : nullptr;
-      mbar_wait(&acc_full[acc], acc_phase);
-      tc_fence_after();
       // ---- row mapping
       bool row_ok = m < e.M;
       long long orow = m;
@@ -277,102 +293,157 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
       float row_sub = 0.f, row_inv = 1.f;
       if (row_ok && e.mode == EPI_EXP) row_sub = e.row_sub[rs_off + m];
       if (row_ok && e.mode == EPI_STORE && e.row_div) row_inv = 1.f / e.row_div[rs_off + m];
+      ri->orow[lane] = row_ok ? orow : -1;
+      ri->roff[lane] = e.residual ? (long long)(m % e.res_rows) * e.ldr : 0;
+      ri->rinv[lane] = row_inv;
+      __syncwarp();
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < NT; c0 += 32) {
+        const int n = n0 + c0;
+        if (n >= e.N) break;                         // warp-uniform
         uint32_t v[32];
         tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + c0), v);
-        const int n = n0 + c0;
-        if (row_ok && n < e.N) {
-          if (e.mode == EPI_ROWMAX) {
+        if (e.mode == EPI_ROWMAX) {
+          if (n + 31 < e.N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) row_acc = fmaxf(row_acc, __uint_as_float(v[j]) * e.alpha);
+          } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (n + j < e.N) row_acc = fmaxf(row_acc, __uint_as_float(v[j]) * e.alpha);
-            continue;
           }
-          if (e.row_mode == ROWS_PHASE) {
-            // 64-column block = one polyphase: fine voxel = s*q + r in the padded fine grid
-            const int ph = n / 64;
-            const int s = e.phase_s;
-            const int rd = ph / (s * s), rh = (ph / s) % s, rw = ph % s;
-            const int oV = e.out_Vp;
-            orow = (((long long)qb * oV + qd * s + rd + e.out_pad) * oV + qh * s + rh + e.out_pad) * oV + qw * s + rw + e.out_pad;
-          }
-          const int ncol = (e.row_mode == ROWS_PHASE) ? (n % 64) : n;   // column inside the output row
-          float f[32];
-          if (e.mode == EPI_EXP) {
+          continue;
+        }
+        float f[32];
+        if (e.mode == EPI_EXP) {
 #pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float t;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(__uint_as_float(v[j]), e.alpha, -row_sub)));
+            t = (n + j < e.N) ? t : 0.f;
+            row_acc += t;
+            f[j] = t;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * e.alpha;
+        }
+        if (e.transpose_planes) {
+          // element (row, col) -> plane[col * ldp + row]: lanes are consecutive rows, already contiguous
+          if (row_ok) {
+#pragma unroll 4
             for (int j = 0; j < 32; ++j) {
-              float t = 0.f;
               if (n + j < e.N) {
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(__uint_as_float(v[j]), e.alpha, -row_sub)));
-                row_acc += t;
-              }
-              f[j] = t;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float t = __uint_as_float(v[j]) * e.alpha;
-              const int nn = n + j;
-              if (nn < e.N) {
-                if (e.bias) t += e.bias[(e.row_mode == ROWS_PHASE) ? (ncol + j) : nn];
+                float t = f[j];
+                if (e.bias) t += __ldg(e.bias + n + j);
                 if (e.act_slope >= 0.f) t = t > 0.f ? t : t * e.act_slope;
-                if (e.residual) t += e.residual[(long long)(m % e.res_rows) * e.ldr + nn];
-                t *= row_inv;
+                const __nv_bfloat16 hi = __float2bfloat16_rn(t);
+                out_hi[(long long)(n + j) * e.ldp + orow] = hi;
+                out_lo[(long long)(n + j) * e.ldp + orow] = __float2bfloat16_rn(t - __bfloat162float(hi));
               }
-              f[j] = t;
             }
           }
-          const bool full = n + 31 < e.N;
-          if (out_f32) {
-            float* dst = out_f32 + orow * e.ldc + ncol;
-            if (full && ((e.ldc & 3) == 0)) {
+          continue;
+        }
+        int ncol0 = n;                                // column of the chunk inside the output row
+        if (e.row_mode == ROWS_PHASE) {
+          // 64-column block = one polyphase: fine voxel = s*q + r in the (padded) fine grid
+          const int ph = n / 64;
+          const int s = e.phase_s;
+          const int rd = ph / (s * s), rh = (ph / s) % s, rw = ph % s;
+          const int oV = e.out_Vp;
+          orow = (((long long)qb * oV + qd * s + rd + e.out_pad) * oV + qh * s + rh + e.out_pad) * oV + qw * s + rw + e.out_pad;
+          ri->orow[lane] = row_ok ? orow : -1;
+          ncol0 = n % 64;
+        }
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-              for (int j = 0; j < 32; ++j) if (n + j < e.N) dst[j] = f[j];
-            }
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stage + lane * EPI_STAGE_LD + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        __syncwarp();
+        // ---- column domain: all shared-memory reads first (independent), then math, then predicated stores
+        const int nn = n + tc;                        // absolute GEMM column of this lane's first element
+        const int nv = e.N - nn;                      // valid columns from nn (>= 4: all four)
+        if (nv > 0) {
+          const int ncol = ncol0 + tc;
+          float bv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (e.bias) {
+            const float* bp = e.bias + ((e.row_mode == ROWS_PHASE) ? ncol : nn);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) if (t < nv) bv[t] = __ldg(bp + t);
           }
-          if (out_hi) {
-            if (e.transpose_planes) {
-              for (int j = 0; j < 32; ++j) {
-                if (n + j < e.N) {
-                  const __nv_bfloat16 hi = __float2bfloat16_rn(f[j]);
-                  const __nv_bfloat16 lo = __float2bfloat16_rn(f[j] - __bfloat162float(hi));
-                  out_hi[(long long)(ncol + j) * e.ldp + orow] = hi;
-                  out_lo[(long long)(ncol + j) * e.ldp + orow] = lo;
+          long long orow_r[8];
+          float rinv_r[8];
+          float4 x4[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + tr;
+            orow_r[i] = ri->orow[r];
+            rinv_r[i] = ri->rinv[r];
+            x4[i] = *reinterpret_cast<const float4*>(stage + r * EPI_STAGE_LD + tc);
+          }
+          float4 rv[8];
+          if (e.residual) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (orow_r[i] >= 0) {
+                const float* rp = e.residual + ri->roff[i * 4 + tr] + nn;
+                if (nv >= 4 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+                  rv[i] = *reinterpret_cast<const float4*>(rp);
+                } else {
+                  rv[i].x = rp[0];
+                  if (nv > 1) rv[i].y = rp[1];
+                  if (nv > 2) rv[i].z = rp[2];
+                  if (nv > 3) rv[i].w = rp[3];
                 }
               }
-            } else {
-              __nv_bfloat16* dh = out_hi + orow * e.ldp + ncol;
-              __nv_bfloat16* dl = out_lo + orow * e.ldp + ncol;
-              // columns up to the 8-aligned end of the row may be written (zeros beyond N): planes are padded to ld
-              if ((full || e.mode == EPI_EXP) && ((e.ldp & 7) == 0)) {
+            }
+          }
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  if (n + j < e.ldp) {
-                    __align__(16) __nv_bfloat16 h8[8], l8[8];
+          for (int i = 0; i < 8; ++i) {
+            float x[4] = {x4[i].x + bv[0], x4[i].y + bv[1], x4[i].z + bv[2], x4[i].w + bv[3]};
+            if (e.act_slope >= 0.f) {
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                      h8[t] = __float2bfloat16_rn(f[j + t]);
-                      l8[t] = __float2bfloat16_rn(f[j + t] - __bfloat162float(h8[t]));
-                    }
-                    *reinterpret_cast<uint4*>(dh + j) = *reinterpret_cast<const uint4*>(h8);
-                    *reinterpret_cast<uint4*>(dl + j) = *reinterpret_cast<const uint4*>(l8);
-                  }
-                }
+              for (int t = 0; t < 4; ++t) x[t] = x[t] > 0.f ? x[t] : x[t] * e.act_slope;
+            }
+            if (e.residual) { x[0] += rv[i].x; x[1] += rv[i].y; x[2] += rv[i].z; x[3] += rv[i].w; }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) x[t] *= rinv_r[i];
+            const bool ok = orow_r[i] >= 0;
+            if (out_f32 && ok) {
+              float* dst = out_f32 + orow_r[i] * e.ldc + ncol;
+              if (nv >= 4 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
               } else {
-                for (int j = 0; j < 32; ++j) {
-                  if (n + j < e.N) {
-                    const __nv_bfloat16 hi = __float2bfloat16_rn(f[j]);
-                    dh[j] = hi;
-                    dl[j] = __float2bfloat16_rn(f[j] - __bfloat162float(hi));
-                  }
-                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) if (t < nv) dst[t] = x[t];
+              }
+            }
+            if (out_hi && ok) {
+              __nv_bfloat16* dh = out_hi + orow_r[i] * e.ldp + ncol;
+              __nv_bfloat16* dl = out_lo + orow_r[i] * e.ldp + ncol;
+              const __nv_bfloat162 h01 = __floats2bfloat162_rn(x[0], x[1]), h23 = __floats2bfloat162_rn(x[2], x[3]);
+              const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+              const __nv_bfloat162 l01 = __floats2bfloat162_rn(x[0] - f01.x, x[1] - f01.y);
+              const __nv_bfloat162 l23 = __floats2bfloat162_rn(x[2] - f23.x, x[3] - f23.y);
+              // EXP mode: values beyond N are exact zeros and the row is padded to ld (a multiple of 8)
+              if ((nv >= 4 || e.mode == EPI_EXP) && ((reinterpret_cast<uintptr_t>(dh) & 7) == 0)) {
+                uint2 hv, lv;
+                hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                *reinterpret_cast<uint2*>(dh) = hv;
+                *reinterpret_cast<uint2*>(dl) = lv;
+              } else {
+                const __nv_bfloat16 hh[4] = {h01.x, h01.y, h23.x, h23.y}, ll[4] = {l01.x, l01.y, l23.x, l23.y};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) if (t < nv) { dh[t] = hh[t]; dl[t] = ll[t]; }
               }
             }
           }
         }
+        __syncwarp();
       }
       if (row_ok && e.mode == EPI_ROWMAX) {
         float* a = e.row_stat + rs_off + m;
