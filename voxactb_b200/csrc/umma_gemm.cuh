@@ -131,7 +131,9 @@ struct SmemLayout {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /* alignment slack */;   // dynamic part
 };
 
-template <int NT, int STAGES>
+enum { EPIK_GENERIC = 0, EPIK_PLAIN = 1, EPIK_ROWMAX = 2, EPIK_EXP = 3 };
+
+template <int NT, int STAGES, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_constant__ CUtensorMap mapA0l,
                  const __grid_constant__ CUtensorMap mapA1h, const __grid_constant__ CUtensorMap mapA1l,
@@ -258,13 +260,192 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
     // Row domain: lane t owns accumulator row q*32 + t (tcgen05.ld 32x32b).  Values are transposed through a
     // per-warp shared-memory tile so that the stores (and the residual loads) are column-contiguous:
     // in the column domain lane l handles rows 4i + l/8 (i = 0..7) and columns 4(l%8)..+3 of a 32-column chunk.
+    // EPI selects a compile-time specialisation (the generic body costs ~60 instructions per element):
+    //   EPIK_PLAIN   ROWS_PLAIN store (bias / LeakyReLU / residual / row scale; fp32 and/or plane outputs)
+    //   EPIK_ROWMAX  attention pass 1, EPIK_EXP attention pass 2, EPIK_GENERIC convolution row modes + V^T planes
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const Epilogue& e = p.ep;
     float* stage = reinterpret_cast<float*>(epi_smem + q * EPI_BYTES_PER_WARP);
-    RowInfo* ri = reinterpret_cast<RowInfo*>(stage + 32 * EPI_STAGE_LD);
     const int tr = lane >> 3, tc = (lane & 7) * 4;
     int acc = 0;
     uint32_t acc_phase = 0;
+    if constexpr (EPI != EPIK_GENERIC) {
+      const float slope = e.act_slope >= 0.f ? e.act_slope : 1.f;   // max(x, x*slope) == LeakyReLU for slope in [0,1]
+      const bool f32_vec = e.out_f32 && ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0) &&
+                           ((p.c_zb & 3) == 0) && ((p.c_zh & 3) == 0);
+      const bool res_vec = e.residual && ((e.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.residual) & 15) == 0);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tiles_per_z = p.m_tiles * p.n_tiles;
+        const int z = tile / tiles_per_z, tz = tile % tiles_per_z;
+        const int zb = z / p.Hz, zh = z % p.Hz;
+        const int mt = tz / p.n_tiles, nt = tz % p.n_tiles;
+        const int mw = mt * BM + q * 32;              // first row of this warp
+        const int m = mw + lane;                      // row-domain row of this lane
+        const int n0 = nt * NT;
+        const long long rs_off = zb * p.rs_zb + zh * p.rs_zh;
+        const bool row_ok = m < e.M;
+        float row_acc = (EPI == EPIK_ROWMAX) ? -INFINITY : 0.f;
+        float row_sub = 0.f;
+        if constexpr (EPI == EPIK_EXP) { if (row_ok) row_sub = e.row_sub[rs_off + m]; }
+        float rinv_r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rinv_r[i] = 1.f;
+        if constexpr (EPI == EPIK_PLAIN) {
+          if (e.row_div) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = mw + i * 4 + tr;
+              if (r < e.M) rinv_r[i] = 1.f / e.row_div[rs_off + r];
+            }
+          }
+        }
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+          const int n = n0 + c0;
+          if (n >= e.N) break;                         // warp-uniform
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + c0), v);
+          const bool full = n + 31 < e.N;
+          if constexpr (EPI == EPIK_ROWMAX) {
+            float mx = -INFINITY;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (n + j < e.N) mx = fmaxf(mx, __uint_as_float(v[j]));
+            }
+            row_acc = fmaxf(row_acc, mx * e.alpha);    // alpha > 0
+          } else {
+            if constexpr (EPI == EPIK_EXP) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float t[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t[u]) : "f"(fmaf(__uint_as_float(v[j + u]), e.alpha, -row_sub)));
+                  if (!full) t[u] = (n + j + u < e.N) ? t[u] : 0.f;
+                  row_acc += t[u];
+                }
+                *reinterpret_cast<float4*>(stage + lane * EPI_STAGE_LD + j) = make_float4(t[0], t[1], t[2], t[3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(stage + lane * EPI_STAGE_LD + j) =
+                    make_float4(__uint_as_float(v[j]) * e.alpha, __uint_as_float(v[j + 1]) * e.alpha,
+                                __uint_as_float(v[j + 2]) * e.alpha, __uint_as_float(v[j + 3]) * e.alpha);
+            }
+            __syncwarp();
+            // ---- column domain
+            const int nn = n + tc;
+            const int nv = e.N - nn;
+            if (nv > 0) {
+              float4 x4[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x4[i] = *reinterpret_cast<const float4*>(stage + (i * 4 + tr) * EPI_STAGE_LD + tc);
+              if constexpr (EPI == EPIK_PLAIN) {
+                float bv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (e.bias) {
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) if (t < nv) bv[t] = __ldg(e.bias + nn + t);
+                }
+                float4 rv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e.residual) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const int r = mw + i * 4 + tr;
+                    if (r < e.M) {
+                      const float* rp = e.residual + (long long)(r % e.res_rows) * e.ldr + nn;
+                      if (res_vec && nv >= 4) {
+                        rv[i] = *reinterpret_cast<const float4*>(rp);
+                      } else {
+                        rv[i].x = rp[0];
+                        if (nv > 1) rv[i].y = rp[1];
+                        if (nv > 2) rv[i].z = rp[2];
+                        if (nv > 3) rv[i].w = rp[3];
+                      }
+                    }
+                  }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float4& x = x4[i];
+                  x.x += bv[0]; x.y += bv[1]; x.z += bv[2]; x.w += bv[3];
+                  x.x = fmaxf(x.x, x.x * slope); x.y = fmaxf(x.y, x.y * slope);
+                  x.z = fmaxf(x.z, x.z * slope); x.w = fmaxf(x.w, x.w * slope);
+                  x.x = (x.x + rv[i].x) * rinv_r[i]; x.y = (x.y + rv[i].y) * rinv_r[i];
+                  x.z = (x.z + rv[i].z) * rinv_r[i]; x.w = (x.w + rv[i].w) * rinv_r[i];
+                }
+                if (e.out_f32) {
+                  float* dst0 = e.out_f32 + zb * p.c_zb + zh * p.c_zh + (long long)(mw + tr) * e.ldc + nn;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    if (mw + i * 4 + tr < e.M) {
+                      float* dst = dst0 + (long long)(i * 4) * e.ldc;
+                      if (f32_vec && nv >= 4) {
+                        *reinterpret_cast<float4*>(dst) = x4[i];
+                      } else {
+                        dst[0] = x4[i].x;
+                        if (nv > 1) dst[1] = x4[i].y;
+                        if (nv > 2) dst[2] = x4[i].z;
+                        if (nv > 3) dst[3] = x4[i].w;
+                      }
+                    }
+                  }
+                }
+              }
+              if (e.out_hi) {
+                const long long poff = zb * p.p_zb + zh * p.p_zh + (long long)(mw + tr) * e.ldp + nn;
+                // EXP: values beyond N are exact zeros and rows are padded to ld (a multiple of 8): always 4-wide
+                const bool wide = (EPI == EPIK_EXP) || nv >= 4;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  if (mw + i * 4 + tr < e.M) {
+                    const float4 x = x4[i];
+                    const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
+                    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+                    const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - f01.x, x.y - f01.y);
+                    const __nv_bfloat162 l23 = __floats2bfloat162_rn(x.z - f23.x, x.w - f23.y);
+                    __nv_bfloat16* dh = e.out_hi + poff + (long long)(i * 4) * e.ldp;
+                    __nv_bfloat16* dl = e.out_lo + poff + (long long)(i * 4) * e.ldp;
+                    if (wide) {
+                      uint2 hv, lv;
+                      hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                      lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                      *reinterpret_cast<uint2*>(dh) = hv;
+                      *reinterpret_cast<uint2*>(dl) = lv;
+                    } else {
+                      dh[0] = h01.x; dl[0] = l01.x;
+                      if (nv > 1) { dh[1] = h01.y; dl[1] = l01.y; }
+                      if (nv > 2) { dh[2] = h23.x; dl[2] = l23.x; }
+                    }
+                  }
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+        if constexpr (EPI == EPIK_ROWMAX) {
+          if (row_ok) {
+            float* a = e.row_stat + rs_off + m;
+            if (row_acc >= 0.f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(row_acc));
+            else atomicMin(reinterpret_cast<unsigned int*>(a), __float_as_uint(row_acc));
+          }
+        }
+        if constexpr (EPI == EPIK_EXP) { if (row_ok) atomicAdd(e.row_stat + rs_off + m, row_acc); }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else {
+    RowInfo* ri = reinterpret_cast<RowInfo*>(stage + 32 * EPI_STAGE_LD);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int tiles_per_z = p.m_tiles * p.n_tiles;
       const int z = tile / tiles_per_z, tz = tile % tiles_per_z;
@@ -455,6 +636,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
     }
   }
   tc_fence_before();

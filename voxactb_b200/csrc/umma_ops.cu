@@ -269,12 +269,12 @@ static __global__ void rowstat_init_kernel(float* __restrict__ mx, float* __rest
 }
 
 // ------------------------------------------------------------------------------------------ launch
-template <int NT, int STAGES>
-static int launch_t(const CUtensorMap* maps, const Params& p, cudaStream_t st) {
+template <int NT, int STAGES, int EPI>
+static int launch_e(const CUtensorMap* maps, const Params& p, cudaStream_t st) {
   using L = SmemLayout<NT, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    VXB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    VXB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<NT, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
   static int num_sms = 0;
@@ -285,9 +285,21 @@ static int launch_t(const CUtensorMap* maps, const Params& p, cudaStream_t st) {
   }
   const long long tiles = (long long)p.m_tiles * p.n_tiles * p.batches;
   const int grid = (int)std::min<long long>(tiles, num_sms);
-  umma_gemm_kernel<NT, STAGES><<<grid, THREADS, L::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  umma_gemm_kernel<NT, STAGES, EPI><<<grid, THREADS, L::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
+}
+
+// epilogue specialisation from the runtime description
+template <int NT, int STAGES>
+static int launch_t(const CUtensorMap* maps, const Params& p, cudaStream_t st) {
+  const Epilogue& e = p.ep;
+  if (e.row_mode == ROWS_PLAIN && !e.transpose_planes) {
+    if (e.mode == EPI_ROWMAX) return launch_e<NT, STAGES, EPIK_ROWMAX>(maps, p, st);
+    if (e.mode == EPI_EXP) return launch_e<NT, STAGES, EPIK_EXP>(maps, p, st);
+    return launch_e<NT, STAGES, EPIK_PLAIN>(maps, p, st);
+  }
+  return launch_e<NT, STAGES, EPIK_GENERIC>(maps, p, st);
 }
 
 static long long g_umma_launches = 0;
