@@ -90,7 +90,8 @@ def test_spatial_softmax_and_max(cuda_lib, S, C):
 
 @pytest.mark.parametrize('mode', MODES)
 @pytest.mark.parametrize('Di,Ci,Co,k,s', [(20, 64, 64, 5, 5), (16, 64, 64, 5, 4), (8, 128, 64, 5, 1),
-                                          (12, 64, 64, 3, 1), (10, 16, 32, 3, 1)])
+                                          (12, 64, 64, 3, 1), (10, 16, 32, 3, 1), (20, 64, 64, 3, 1),
+                                          (37, 64, 64, 3, 1)])
 def test_conv3d(cuda_lib, mode, Di, Ci, Co, k, s):
     g = torch.Generator().manual_seed(Di + k)
     x = torch.randn(2, Ci, Di, Di, Di, generator=g)

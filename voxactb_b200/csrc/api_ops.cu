@@ -185,6 +185,22 @@ extern "C" int vxb_conv3d_f32(const float* x, const float* w, const float* bias,
   if (Co == 1 && Ci == 64 && k == 3 && s == 1 && act_slope < 0.f)   // trans_decoder shape: streaming stencil
     return trans_stencil_run<64>(x, (const float*)ws, bias, y, B, Di, st);
   Arena scratch((char*)ws + conv_w_bytes(Ci, Co, k), ws_bytes - conv_w_bytes(Ci, Co, k));
+  if (math_mode == VXB_MATH_BF16X3 && k == 3 && s == 1 && Co == 64 && Ci == 64 && bias) {
+    // input-stationary tcgen05 convolution (conv_umma.cuh): padded hi/lo planes + re-laid weights
+    __nv_bfloat16* wc = scratch.get<__nv_bfloat16>(umma::conv3_weight_elems(Ci));
+    umma::Planes xp;
+    const long long prow = (long long)B * (Di + 2) * (Di + 2) * (Di + 2);
+    xp.hi = scratch.get<__nv_bfloat16>((size_t)prow * 64);
+    xp.lo = scratch.get<__nv_bfloat16>((size_t)prow * 64);
+    xp.ld = 64;
+    if (!scratch.ok) {
+      set_error("conv3d: workspace too small");
+      return VXB_E_WORKSPACE_TOO_SMALL;
+    }
+    VXB_TRY(umma::conv3_prepare_weights((const float*)ws, Ci, wc, st));
+    VXB_TRY(umma::pad_split(x, B, Di, 1, Ci, xp, st));
+    return umma::conv3_planes(xp, nullptr, Ci, 0, wc, bias, act_slope, y, B, Di, st);
+  }
   return conv3d(x, nullptr, Ci, 0, (const float*)ws, bias, y, B, Di, Do, Co, k, s, act_slope, math_mode, st,
                 &scratch, nullptr);
 }

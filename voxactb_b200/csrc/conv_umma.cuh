@@ -1,0 +1,348 @@
+// Input-stationary 3x3x3 convolution on tcgen05 (split-bf16, fp32 accumulate in TMEM) for sm_100a.
+//
+//   out[b,z,y,x,:] = act(bias + sum_{src,dz,dy,dx} W[:, tap, src ch] . in_src[b, z+dz, y+dy, x+dx, :])     (Co = 64)
+//
+// Inputs are bf16 hi/lo planes of the replicate-PADDED channels-last grids [B, Vp, Vp, Vp, 64] (Vp = V + 2), so
+// a tap is a constant shift of the flat padded row index.  The GEMM engine in umma_gemm.cuh re-fetches a
+// 128-row operand tile from L2 for every tap (27x) and is L2-bandwidth bound; this kernel instead
+//   * stages ONE slab per (z plane, 32-channel block): the 128 output rows of a (y,x)-plane tile plus a
+//     Vp+1 row halo on each side (hi and lo planes, SWIZZLE_64B rows of 64 bytes), fetched once by TMA;
+//   * expresses the 9 in-plane taps as ROW-SHIFTED shared-memory matrix descriptors into that slab;
+//   * marches along z with the slab stationary: input plane zi feeds the three output planes zi-1, zi, zi+1,
+//     each with its own TMEM accumulator (4 slots x 128 columns), so every activation byte is staged once;
+//   * streams the weights [W_hi ; W_lo] (N = 128 rows) through a deep ring, multicast across a thread-block
+//     cluster so the L2 -> SM weight traffic is divided by the cluster size;
+//   * issues per 16-wide k step   D[:, 0:128] += A_hi [W_hi ; W_lo]^T   and   D[:, 0:64] += A_lo W_hi^T
+//     (the three split-bf16 terms in two MMAs); the epilogue adds the two column halves.
+//
+// Warp roles (224 threads): 0 = slab TMA producer, 1 = weight TMA producer, 2 = MMA issuer (+ TMEM alloc),
+// 3-6 = epilogue (TMEM -> registers -> smem transpose -> coalesced fp32 stores).
+#pragma once
+#include "umma_gemm.cuh"
+
+namespace vxb {
+namespace umma {
+
+constexpr int CV_KC = 32;             // channels per slab (64-byte rows, SWIZZLE_64B)
+constexpr int CV_THREADS = 224;
+constexpr int CV_WSTAGES = 4;         // weight ring depth; a stage holds the 3 dx taps of one (dz, dy): 24 KB
+constexpr int CV_SLABS = 2;           // slab double buffering
+constexpr int CV_TAPBYTES = 128 * CV_KC * 2;      // [W_hi ; W_lo] of one tap
+constexpr int CV_WBYTES = 3 * CV_TAPBYTES;
+
+struct ConvParams {
+  int B, V, Vp;
+  int ncb;              // 32-channel blocks over all sources
+  int cb_src0;          // blocks taken from source 0
+  int tiles;            // (y,x)-plane tiles of 128 flat rows
+  int zchunks, lz;      // z chunks per column, planes per chunk
+  int items;            // B * tiles * zchunks (padded to a multiple of the cluster size by the launcher)
+  int items_real;
+  int slab_rows;        // 128 + 2 (Vp + 1)
+  int box_rows;         // rows per slab TMA box (two boxes per plane)
+  int base_off_mode;    // descriptor base-offset policy for row-shifted operands (see make_desc64)
+  const float* bias;
+  float act_slope;
+  float* out;           // [B, V, V, V, 64] fp32
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// K-major SWIZZLE_64B descriptor: rows of 64 bytes, 8-row groups 512 bytes apart.  `saddr` may be shifted by
+// whole rows (64 B) from the 512-byte aligned slab base.  Measured on B200 (tests/test_ops_gpu.py::test_conv3d):
+// the hardware applies the swizzle XOR to the absolute shared-memory address, so a row-shifted start address
+// needs base offset 0 (mode 0, the default); mode 1 (base offset = address phase) gives wrong results.
+__device__ __forceinline__ uint64_t make_desc64(uint32_t saddr, int base_off_mode) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  if (base_off_mode == 1) d |= (uint64_t)((saddr >> 7) & 7) << 49;
+  d |= (uint64_t)4 << 61;                             // SWIZZLE_64B
+  return d;
+}
+
+// low / high words of the SWIZZLE_64B K-major descriptor; the low word advances by (bytes >> 4)
+__device__ __forceinline__ uint32_t desc64_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+constexpr uint32_t kDesc64Hi = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
+__device__ __forceinline__ void tc_mma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDesc64Hi) : "memory");
+}
+
+template <int CL>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_constant__ CUtensorMap mapA0l,
+                  const __grid_constant__ CUtensorMap mapA1h, const __grid_constant__ CUtensorMap mapA1l,
+                  const __grid_constant__ CUtensorMap mapW, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(16) uint8_t epi_smem[4 * EPI_BYTES_PER_WARP];
+  __shared__ __align__(8) uint64_t bars[2 * CV_SLABS + 2 * CV_WSTAGES + 8];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int plane_bytes = 2 * p.box_rows * 64;                 // one plane (hi or lo) of a slab
+  const int slab_bytes = 2 * plane_bytes;
+  uint8_t* slab_base = smem;
+  uint8_t* w_base = smem + CV_SLABS * slab_bytes;
+  uint64_t* slab_full = bars;
+  uint64_t* slab_empty = bars + CV_SLABS;
+  uint64_t* w_full = bars + 2 * CV_SLABS;
+  uint64_t* w_empty = w_full + CV_WSTAGES;
+  uint64_t* acc_full = w_empty + CV_WSTAGES;
+  uint64_t* acc_empty = acc_full + 4;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (CL > 1) ? cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0h); tma_prefetch_desc(&mapA0l);
+    tma_prefetch_desc(&mapA1h); tma_prefetch_desc(&mapA1l);
+    tma_prefetch_desc(&mapW);
+    for (int i = 0; i < CV_SLABS; ++i) { mbar_init(&slab_full[i], 1); mbar_init(&slab_empty[i], 1); }
+    for (int i = 0; i < CV_WSTAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], CL); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int groups = p.items / CL;
+  const int Vp = p.Vp, Vp2 = Vp * Vp;
+
+  // item -> (b, tile, zchunk): z chunk slowest so that the CTAs of a cluster always share the chunk length
+  auto decode = [&](int item, int& b, int& t, int& z0, int& lz) {
+    const int per_chunk = p.items / p.zchunks;
+    const int zc = item / per_chunk;
+    int rem = item - zc * per_chunk;
+    const int col = min(rem, p.B * p.tiles - 1);               // padded items repeat the last column (not stored)
+    b = col / p.tiles;
+    t = col - b * p.tiles;
+    z0 = zc * p.lz;
+    lz = min(p.lz, p.V - z0);
+  };
+
+  if (warp == 0) {
+    // ===================================================== slab producer
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t sph = 0;
+      for (int g = cluster_id; g < groups; g += num_clusters) {
+        int b, t, z0, lz;
+        decode(g * CL + rank, b, t, z0, lz);
+        for (int zi = z0 - 1; zi <= z0 + lz; ++zi) {
+          const int row0 = (b * Vp + (zi + 1)) * Vp2 + t * 128 - (Vp + 1);
+          for (int cb = 0; cb < p.ncb; ++cb) {
+            const bool s1 = cb >= p.cb_src0;
+            const int col = (s1 ? cb - p.cb_src0 : cb) * CV_KC;
+            const CUtensorMap* mh = s1 ? &mapA1h : &mapA0h;
+            const CUtensorMap* ml = s1 ? &mapA1l : &mapA0l;
+            mbar_wait(&slab_empty[sb], sph ^ 1);
+            uint8_t* s = slab_base + sb * slab_bytes;
+            mbar_expect_tx(&slab_full[sb], slab_bytes);
+            tma_load_2d(mh, &slab_full[sb], s, col, row0);
+            tma_load_2d(mh, &slab_full[sb], s + p.box_rows * 64, col, row0 + p.box_rows);
+            tma_load_2d(ml, &slab_full[sb], s + plane_bytes, col, row0);
+            tma_load_2d(ml, &slab_full[sb], s + plane_bytes + p.box_rows * 64, col, row0 + p.box_rows);
+            if (++sb == CV_SLABS) { sb = 0; sph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== weight producer (each CTA loads 128/CL rows, multicast)
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wph = 0;
+      constexpr int WROWS = 128 / CL;
+      const uint16_t mask = (uint16_t)((1u << CL) - 1);
+      for (int g = cluster_id; g < groups; g += num_clusters) {
+        int b, t, z0, lz;
+        decode(g * CL + rank, b, t, z0, lz);
+        for (int zi = z0 - 1; zi <= z0 + lz; ++zi) {
+          for (int cb = 0; cb < p.ncb; ++cb) {
+            for (int dzc = 0; dzc < 3; ++dzc) {
+              const int zo = zi - (dzc - 1);
+              if (zo < z0 || zo >= z0 + lz) continue;
+              for (int dyc = 0; dyc < 3; ++dyc) {
+                const int wrow = (cb * 27 + dzc * 9 + dyc * 3) * 128 + (int)rank * WROWS;
+                mbar_wait(&w_empty[ws], wph ^ 1);
+                uint8_t* s = w_base + ws * CV_WBYTES + rank * WROWS * 64;
+                mbar_expect_tx(&w_full[ws], CV_WBYTES);
+#pragma unroll
+                for (int dxc = 0; dxc < 3; ++dxc) {
+                  if (CL > 1) tma_load_2d_mc(&mapW, &w_full[ws], s + dxc * CV_TAPBYTES, 0, wrow + dxc * 128, mask);
+                  else tma_load_2d(&mapW, &w_full[ws], s + dxc * CV_TAPBYTES, 0, wrow + dxc * 128);
+                }
+                if (++ws == CV_WSTAGES) { ws = 0; wph ^= 1; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc128 = make_idesc(128), idesc64 = make_idesc(64);
+      const uint16_t mask = (uint16_t)((1u << CL) - 1);
+      int sb = 0, ws = 0;
+      uint32_t sph = 0, wph = 0;
+      uint32_t acc_ph = 0;                         // bit s: parity of the last completed acc_empty phase of slot s
+      for (int g = cluster_id; g < groups; g += num_clusters) {
+        int b, t, z0, lz;
+        decode(g * CL + rank, b, t, z0, lz);
+        for (int zi = z0 - 1; zi <= z0 + lz; ++zi) {
+          for (int cb = 0; cb < p.ncb; ++cb) {
+            mbar_wait(&slab_full[sb], sph);
+            tc_fence_after();
+            const uint32_t a_hi_lo = desc64_lo(smem_u32(slab_base + sb * slab_bytes));
+            const uint32_t a_lo_lo = desc64_lo(smem_u32(slab_base + sb * slab_bytes + plane_bytes));
+            for (int dzc = 0; dzc < 3; ++dzc) {
+              const int zo = zi - (dzc - 1);
+              if (zo < z0 || zo >= z0 + lz) continue;
+              const int slot = (zo - z0) & 3;
+              // the first contribution to an output plane comes from input plane zo-1 (dzc = 0), channel block 0:
+              // the accumulator slot must have been drained by the epilogue
+              if (dzc == 0 && cb == 0) {
+                mbar_wait(&acc_empty[slot], ((acc_ph >> slot) & 1u) ^ 1u);
+                acc_ph ^= 1u << slot;
+                tc_fence_after();
+              }
+              const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 128);
+              uint32_t accum = (dzc == 0 && cb == 0) ? 0u : 1u;
+#pragma unroll
+              for (int dyc = 0; dyc < 3; ++dyc) {
+                mbar_wait(&w_full[ws], wph);
+                tc_fence_after();
+                const uint32_t wlo = desc64_lo(smem_u32(w_base + ws * CV_WBYTES));
+                // row shift of tap (dy, dx): (Vp + 1) + dy * Vp + dx rows of 64 bytes = 4 descriptor units per row
+                const uint32_t arow = (uint32_t)(dyc * Vp) * 4u;
+#pragma unroll
+                for (int dxc = 0; dxc < 3; ++dxc) {
+#pragma unroll
+                  for (int ks = 0; ks < CV_KC / 16; ++ks) {
+                    const uint32_t aoff = arow + (uint32_t)(dxc * 4 + ks * 2);
+                    const uint32_t boff = (uint32_t)(dxc * (CV_TAPBYTES >> 4) + ks * 2);
+                    tc_mma_bf16_w(d_tmem, a_hi_lo + aoff, wlo + boff, idesc128, accum);   // hi*hi -> cols [0,64), hi*lo -> [64,128)
+                    tc_mma_bf16_w(d_tmem, a_lo_lo + aoff, wlo + boff, idesc64, 1u);       // lo*hi -> cols [0,64)
+                    accum = 1u;
+                  }
+                }
+                if (CL > 1) tc_commit_mc(&w_empty[ws], mask); else tc_commit(&w_empty[ws]);
+                if (++ws == CV_WSTAGES) { ws = 0; wph ^= 1; }
+              }
+            }
+            tc_commit(&slab_empty[sb]);
+            if (++sb == CV_SLABS) { sb = 0; sph ^= 1; }
+          }
+          // input plane zi done: output plane zi-1 has all of its three input planes
+          const int zdone = zi - 1;
+          if (zdone >= z0 && zdone < z0 + lz) tc_commit(&acc_full[(zdone - z0) & 3]);
+        }
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 3..6)
+    const int q = warp & 3;
+    float* stage = reinterpret_cast<float*>(epi_smem + q * EPI_BYTES_PER_WARP);
+    RowInfo* ri = reinterpret_cast<RowInfo*>(stage + 32 * EPI_STAGE_LD);
+    const int tr = lane >> 3, tc = (lane & 7) * 4;
+    const float slope = p.act_slope >= 0.f ? p.act_slope : 1.f;
+    uint32_t full_ph = 0;                          // bit s: parity to wait for on acc_full[s]
+    const int V = p.V;
+    for (int g = cluster_id; g < groups; g += num_clusters) {
+      int b, t, z0, lz;
+      const int item = g * CL + rank;
+      decode(item, b, t, z0, lz);
+      const int per_chunk = p.items / p.zchunks;
+      const bool real = (item % per_chunk) < p.B * p.tiles;
+      // row -> output voxel (fixed over z): flat plane row rr = t*128 + row -> (yp, xp)
+      {
+        const int rr = t * 128 + q * 32 + lane;
+        const int yp = rr / Vp, xp = rr - yp * Vp;
+        const bool ok = real && rr < Vp2 && yp >= 1 && yp <= V && xp >= 1 && xp <= V;
+        ri->orow[lane] = ok ? ((long long)b * V * V * V + (long long)(yp - 1) * V + (xp - 1)) : -1;
+        __syncwarp();
+      }
+      for (int zo = z0; zo < z0 + lz; ++zo) {
+        const int slot = (zo - z0) & 3;
+        mbar_wait(&acc_full[slot], (full_ph >> slot) & 1u);
+        full_ph ^= 1u << slot;
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v0[32], v1[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128 + c0), v0);
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128 + 64 + c0), v1);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(stage + lane * EPI_STAGE_LD + j) =
+                make_float4(__uint_as_float(v0[j]) + __uint_as_float(v1[j]), __uint_as_float(v0[j + 1]) + __uint_as_float(v1[j + 1]),
+                            __uint_as_float(v0[j + 2]) + __uint_as_float(v1[j + 2]), __uint_as_float(v0[j + 3]) + __uint_as_float(v1[j + 3]));
+          __syncwarp();
+          const float4 bv = *reinterpret_cast<const float4*>(p.bias + c0 + tc);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + tr;
+            const long long orow = ri->orow[r];
+            float4 x = *reinterpret_cast<const float4*>(stage + r * EPI_STAGE_LD + tc);
+            x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+            x.x = fmaxf(x.x, x.x * slope); x.y = fmaxf(x.y, x.y * slope);
+            x.z = fmaxf(x.z, x.z * slope); x.w = fmaxf(x.w, x.w * slope);
+            if (orow >= 0)
+              *reinterpret_cast<float4*>(p.out + (orow + (long long)zo * V * V) * 64 + c0 + tc) = x;
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[slot]);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+}  // namespace umma
+}  // namespace vxb

@@ -82,6 +82,7 @@ struct Prepared {
   float* up1_fold;   // [s^3][64][27][64]
   float* final_wt;   // [64][27][128]
   float* trans_wt;   // [27][64]
+  __nv_bfloat16* final_wc;  // [4][27][{hi,lo}][64][32] weights of the input-stationary conv kernel
   float* q_cross;    // [L][ch*cdh]  = to_q(LN(latents)), batch independent
   float* lat_norm;   // [L][D] scratch for the above
   // bf16 hi/lo planes of every weight that feeds a tcgen05 GEMM, keyed by the fp32 weight pointer
@@ -103,6 +104,7 @@ static void carve_prepared(const Dims& m, Arena& a, Prepared& p, const void* con
   p.up1_fold = a.get<float>((size_t)m.s * m.s * m.s * 64 * 27 * 64);
   p.final_wt = a.get<float>((size_t)64 * 27 * 128);
   p.trans_wt = a.get<float>((size_t)27 * 64);
+  p.final_wc = a.get<__nv_bfloat16>(umma::conv3_weight_elems(128));
   p.q_cross = a.get<float>((size_t)m.L * m.ch * m.cdh);
   p.lat_norm = a.get<float>((size_t)m.L * m.D);
   std::vector<WeightSpec> specs;
@@ -553,6 +555,7 @@ extern "C" int vxb_qnet_prepare(const vxb_qnet_desc* d, const void* const* param
   VXB_TRY(conv_weight_prepare(P(VXB_P_UP0_W), p.up0_wt, 64, m.C, k3, st));
   VXB_TRY(conv_weight_prepare(P(VXB_P_FINAL_W), p.final_wt, 64, 128, 27, st));
   VXB_TRY(conv_weight_prepare(P(VXB_P_TRANS_W), p.trans_wt, 1, 64, 27, st));
+  VXB_TRY(umma::conv3_prepare_weights(p.final_wt, 128, p.final_wc, st));
   {
     const size_t total = (size_t)m.s * m.s * m.s * 64 * 27 * 64;
     fold_upconv_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(P(VXB_P_UP1_W), p.up1_fold, 64, 64, m.k, m.s);
@@ -696,8 +699,24 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   STAGE_MARK();  // 8: final conv
   // (11) final: conv3 on cat[d0, u0] (128 -> 64)                               :462
   COUNT_LAUNCH();
-  VXB_TRY(conv3d(w.d0, w.u0, 64, 64, pw.final_wt, P(VXB_P_FINAL_B), w.u, B, m.V, m.V, 64, 3, 1, slope, mm, st,
-                 cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.final_wt)));
+  if (mm == VXB_MATH_BF16X3) {
+    // input-stationary tcgen05 convolution on the padded hi/lo planes of d0 and u0 (no concat, no re-fetch per tap)
+    Arena local(cx.scratch.base, cx.scratch.cap);
+    const size_t prow = (size_t)B * (m.V + 2) * (m.V + 2) * (m.V + 2);
+    umma::Planes d0p{local.get<__nv_bfloat16>(prow * 64), local.get<__nv_bfloat16>(prow * 64), 64};
+    umma::Planes u0p{local.get<__nv_bfloat16>(prow * 64), local.get<__nv_bfloat16>(prow * 64), 64};
+    if (!local.ok) {
+      set_error("qnet: scratch too small for the final convolution planes");
+      return VXB_E_WORKSPACE_TOO_SMALL;
+    }
+    g_launches += 2;
+    VXB_TRY(umma::pad_split(w.d0, B, m.V, 1, 64, d0p, st));
+    VXB_TRY(umma::pad_split(w.u0, B, m.V, 1, 64, u0p, st));
+    VXB_TRY(umma::conv3_planes(d0p, &u0p, 64, 64, pw.final_wc, P(VXB_P_FINAL_B), slope, w.u, B, m.V, st));
+  } else {
+    VXB_TRY(conv3d(w.d0, w.u0, 64, 64, pw.final_wt, P(VXB_P_FINAL_B), w.u, B, m.V, m.V, 64, 3, 1, slope, mm, st,
+                   cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.final_wt)));
+  }
   STAGE_MARK();  // 9: trans decoder
   // (12) trans decoder: conv3 64 -> 1, no activation                            :465
   COUNT_LAUNCH();

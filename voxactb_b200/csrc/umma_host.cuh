@@ -131,6 +131,14 @@ int attention_planes(const Planes& Q, int q_batched, const Planes& K, const Plan
                      int dh, float scale, float* rowmax, float* rowsum, const Planes& P, const Planes& O,
                      cudaStream_t st);
 
+// ---- input-stationary 3x3x3 convolution (conv_umma.cuh), Co = 64, channels a multiple of 32
+// weights: tap-major fp32 [64][27][C0+C1] -> bf16 [ncb][27][{hi,lo}][64][32]
+size_t conv3_weight_elems(int Cin);
+int conv3_prepare_weights(const float* w_tapmajor, int Cin, __nv_bfloat16* wc, cudaStream_t st);
+// x0 / x1: hi-lo planes of the replicate-padded grids [B, V+2, V+2, V+2, 64]; out fp32 [B, V^3, 64]
+int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_bfloat16* wc, const float* bias,
+                 float act_slope, float* out, int B, int V, cudaStream_t st);
+
 // unit-test entry: fp32 q/k/v in, fp32 out, through the plane-domain attention (scratch sized by the _bytes query)
 size_t attention_f32_scratch_bytes(int B, int H, int Nq, int Nk, int dh);
 int attention_f32(const float* q, int ldq, long long qbs, const float* k, const float* v, int ldkv, long long kvbs,

@@ -1,6 +1,8 @@
 // Host side of the tcgen05 split-bf16 engine: TMA tensor maps, operand splitting / padding kernels
 // and the launch wrappers used by dispatch.cuh.
 #include "umma_gemm.cuh"
+#include "conv_umma.cuh"
+#include <cstdlib>
 #include "umma_host.cuh"
 #include <cudaTypedefs.h>
 #include <mutex>
@@ -29,7 +31,7 @@ static EncodeTiledFn get_encode() {
 // 2D bf16 row-major [rows, cols] with `ld` elements between rows; box = 64 columns x box_rows rows,
 // SWIZZLE_128B (64 bf16 = 128 B inner extent), out-of-bounds elements read as zero.
 static int make_map(CUtensorMap* map, const __nv_bfloat16* base, long long rows, long long cols, long long ld,
-                    int box_rows) {
+                    int box_rows, int box_cols = 64) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -41,10 +43,11 @@ static int make_map(CUtensorMap* map, const __nv_bfloat16* base, long long rows,
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d", (int)r, rows, cols, ld, box_rows);
@@ -617,6 +620,123 @@ int attention_f32(const float* q, int ldq, long long qbs, const float* k, const 
   merge_planes_kernel<<<148 * 4, 256, 0, st>>>(s.o.hi, s.o.lo, s.o.ld, B, Nq, inner, out, ldo, obs);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------ conv3 (conv_umma.cuh)
+size_t conv3_weight_elems(int Cin) { return (size_t)(Cin / CV_KC) * 27 * 2 * 64 * CV_KC; }
+
+static __global__ void conv3_weight_kernel(const float* __restrict__ w /*[64][27][Cin]*/, int Cin,
+                                           __nv_bfloat16* __restrict__ wc /*[ncb][27][2][64][32]*/) {
+  const long long total = (long long)(Cin / CV_KC) * 27 * 64 * CV_KC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kc = (int)(i % CV_KC);
+    const int co = (int)((i / CV_KC) % 64);
+    const int tap = (int)((i / (CV_KC * 64)) % 27);
+    const int cb = (int)(i / ((long long)CV_KC * 64 * 27));
+    const float f = w[((long long)co * 27 + tap) * Cin + cb * CV_KC + kc];
+    const __nv_bfloat16 h = __float2bfloat16_rn(f);
+    const long long o = (((long long)(cb * 27 + tap) * 2) * 64 + co) * CV_KC + kc;
+    wc[o] = h;
+    wc[o + 64 * CV_KC] = __float2bfloat16_rn(f - __bfloat162float(h));
+  }
+}
+
+int conv3_prepare_weights(const float* w_tapmajor, int Cin, __nv_bfloat16* wc, cudaStream_t st) {
+  if (Cin % CV_KC) {
+    set_error("conv3: input channels must be a multiple of %d", CV_KC);
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  conv3_weight_kernel<<<148 * 4, 256, 0, st>>>(w_tapmajor, Cin, wc);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+template <int CL>
+static int conv3_launch(const CUtensorMap* maps, const ConvParams& p, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VXB_CUDA(cudaFuncSetAttribute(conv3_umma_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    VXB_CUDA(cudaGetDevice(&dev));
+    VXB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(CV_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int max_clusters = num_sms / CL;
+  if (CL > 1) {
+    cfg.gridDim = dim3(num_sms / CL * CL);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv3_umma_kernel<CL>, &cfg) == cudaSuccess && n > 0) max_clusters = std::min(max_clusters, n);
+    else cudaGetLastError();
+  }
+  const int groups = p.items / CL;
+  cfg.gridDim = dim3(std::min(groups, max_clusters) * CL);
+  VXB_CUDA(cudaLaunchKernelEx(&cfg, conv3_umma_kernel<CL>, maps[0], maps[1], maps[2], maps[3], maps[4], p));
+  return VXB_OK;
+}
+
+int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_bfloat16* wc, const float* bias,
+                 float act_slope, float* out, int B, int V, cudaStream_t st) {
+  const int Vp = V + 2;
+  const long long rows = (long long)B * Vp * Vp * Vp;
+  if (C0 % CV_KC || C1 % CV_KC || x0.ld != 64 || (x1 && x1->ld != 64) || C0 > 64 || C1 > 64 || rows >= (1ll << 31) || Vp > 180) {
+    set_error("conv3_planes: unsupported geometry (C0=%d C1=%d V=%d)", C0, C1, V);
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  static int cl = 0, desc_mode = -1;
+  if (!cl) {
+    const char* e = getenv("VXB_CONV_CLUSTER");
+    cl = e ? atoi(e) : 2;
+    if (cl != 1 && cl != 2 && cl != 4) cl = 2;
+    const char* d = getenv("VXB_CONV_DESC_MODE");
+    desc_mode = d ? atoi(d) : 0;   // measured on B200: the swizzle is a function of the absolute smem address, base offset 0
+  }
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.V = V; p.Vp = Vp;
+  p.ncb = (C0 + C1) / CV_KC; p.cb_src0 = C0 / CV_KC;
+  p.tiles = cdiv((long long)Vp * Vp, 128);
+  // z chunks: enough items for ~3 rounds per cluster, chunks of at least 8 planes
+  int zch = 1;
+  while ((long long)B * p.tiles * zch < 148 * 3 && V / (zch * 2) >= 8) zch *= 2;
+  if (V >= 64 && zch < 4) zch = 4;
+  p.lz = cdiv(V, zch);
+  p.zchunks = cdiv(V, p.lz);
+  const int cols = B * p.tiles;
+  const int cols_pad = cdiv(cols, cl) * cl;
+  p.items = cols_pad * p.zchunks;
+  p.items_real = cols * p.zchunks;
+  p.slab_rows = 128 + 2 * (Vp + 1);
+  p.box_rows = (cdiv(p.slab_rows, 2) + 7) / 8 * 8;
+  p.base_off_mode = desc_mode;
+  p.bias = bias; p.act_slope = act_slope; p.out = out;
+  CUtensorMap maps[5];
+  VXB_TRY(make_map(&maps[0], x0.hi, rows, 64, 64, p.box_rows, CV_KC));
+  VXB_TRY(make_map(&maps[1], x0.lo, rows, 64, 64, p.box_rows, CV_KC));
+  const Planes& xb = x1 ? *x1 : x0;
+  VXB_TRY(make_map(&maps[2], xb.hi, rows, 64, 64, p.box_rows, CV_KC));
+  VXB_TRY(make_map(&maps[3], xb.lo, rows, 64, 64, p.box_rows, CV_KC));
+  VXB_TRY(make_map(&maps[4], wc, (long long)p.ncb * 27 * 128, CV_KC, CV_KC, 128 / cl, CV_KC));
+  const size_t smem = (size_t)CV_SLABS * 4 * p.box_rows * 64 + (size_t)CV_WSTAGES * CV_WBYTES + 1024;
+  ++g_umma_launches;
+  switch (cl) {
+    case 1: return conv3_launch<1>(maps, p, smem, st);
+    case 4: return conv3_launch<4>(maps, p, smem, st);
+    default: return conv3_launch<2>(maps, p, smem, st);
+  }
 }
 
 }  // namespace umma
