@@ -216,7 +216,12 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
     }
   } else if (warp == 2) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) loops so that descriptors live in uniform registers; one elected
+    // lane issues the tcgen05 instructions.
+    {
+      uint32_t leader;
+      asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.b32 %0, 1, 0, P;\n}\n" : "=r"(leader));
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       constexpr uint32_t idesc128 = make_idesc(128), idesc64 = make_idesc(64);
       const uint16_t mask = (uint16_t)((1u << CL) - 1);
       int sb = 0, ws = 0;
@@ -242,36 +247,41 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
                 acc_ph ^= 1u << slot;
                 tc_fence_after();
               }
-              const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 128);
+              const uint32_t d_tmem = tmem_u + (uint32_t)(slot * 128);
               uint32_t accum = (dzc == 0 && cb == 0) ? 0u : 1u;
 #pragma unroll
               for (int dyc = 0; dyc < 3; ++dyc) {
                 mbar_wait(&w_full[ws], wph);
                 tc_fence_after();
                 const uint32_t wlo = desc64_lo(smem_u32(w_base + ws * CV_WBYTES));
-                // row shift of tap (dy, dx): (Vp + 1) + dy * Vp + dx rows of 64 bytes = 4 descriptor units per row
+                // row shift of tap (dy, dx): dyc * Vp + dxc rows of 64 bytes = 4 descriptor units per row
                 const uint32_t arow = (uint32_t)(dyc * Vp) * 4u;
+                if (leader) {
 #pragma unroll
-                for (int dxc = 0; dxc < 3; ++dxc) {
+                  for (int dxc = 0; dxc < 3; ++dxc) {
 #pragma unroll
-                  for (int ks = 0; ks < CV_KC / 16; ++ks) {
-                    const uint32_t aoff = arow + (uint32_t)(dxc * 4 + ks * 2);
-                    const uint32_t boff = (uint32_t)(dxc * (CV_TAPBYTES >> 4) + ks * 2);
-                    tc_mma_bf16_w(d_tmem, a_hi_lo + aoff, wlo + boff, idesc128, accum);   // hi*hi -> cols [0,64), hi*lo -> [64,128)
-                    tc_mma_bf16_w(d_tmem, a_lo_lo + aoff, wlo + boff, idesc64, 1u);       // lo*hi -> cols [0,64)
-                    accum = 1u;
+                    for (int ks = 0; ks < CV_KC / 16; ++ks) {
+                      const uint32_t aoff = arow + (uint32_t)(dxc * 4 + ks * 2);
+                      const uint32_t boff = (uint32_t)(dxc * (CV_TAPBYTES >> 4) + ks * 2);
+                      tc_mma_bf16_w(d_tmem, a_hi_lo + aoff, wlo + boff, idesc128, (dxc | ks) ? 1u : accum);  // hi*hi | hi*lo
+                      tc_mma_bf16_w(d_tmem, a_lo_lo + aoff, wlo + boff, idesc64, 1u);                       // lo*hi
+                    }
                   }
+                  if (CL > 1) tc_commit_mc(&w_empty[ws], mask); else tc_commit(&w_empty[ws]);
                 }
-                if (CL > 1) tc_commit_mc(&w_empty[ws], mask); else tc_commit(&w_empty[ws]);
+                __syncwarp();
+                accum = 1u;
                 if (++ws == CV_WSTAGES) { ws = 0; wph ^= 1; }
               }
             }
-            tc_commit(&slab_empty[sb]);
+            if (leader) tc_commit(&slab_empty[sb]);
+            __syncwarp();
             if (++sb == CV_SLABS) { sb = 0; sph ^= 1; }
           }
           // input plane zi done: output plane zi-1 has all of its three input planes
           const int zdone = zi - 1;
-          if (zdone >= z0 && zdone < z0 + lz) tc_commit(&acc_full[(zdone - z0) & 3]);
+          if (zdone >= z0 && zdone < z0 + lz && leader) tc_commit(&acc_full[(zdone - z0) & 3]);
+          __syncwarp();
         }
       }
     }
