@@ -74,7 +74,8 @@ inline int conv3d(const float* src0, const float* src1, int C0, int C1, const fl
 // phase r written at fine voxel s*q + r.  wfold [s^3][Co][27][Ci]
 inline int upconv3d_folded(const float* low, const float* wfold, const float* bias, float* out,
                            int B, int S, int Ci, int Co, int s, float act_slope, int math_mode,
-                           cudaStream_t st, Arena* scratch = nullptr, const umma::Planes* Wpre = nullptr) {
+                           cudaStream_t st, Arena* scratch = nullptr, const umma::Planes* Wpre = nullptr,
+                           const umma::Planes* out_planes = nullptr) {
   if (math_mode == VXB_MATH_BF16X3 && scratch && Ci % 64 == 0 && Co == 64) {
     Arena local(scratch->base, scratch->cap);
     umma::Planes wp;
@@ -91,7 +92,7 @@ inline int upconv3d_folded(const float* low, const float* wfold, const float* bi
       }
       VXB_TRY(umma::split_rows(wfold, Kt, Nt, (int)Kt, wp, st));
     }
-    return umma::upconv_f32(low, wp, bias, out, B, S, Ci, Co, s, act_slope, local, st);
+    return umma::upconv_f32(low, wp, bias, out, B, S, Ci, Co, s, act_slope, local, st, out_planes);
   }
   GemmParams p;
   gemm_params_init(p);

@@ -168,6 +168,7 @@ struct Work {
   size_t scratch_bytes;
   // plane-domain transformer buffers (bf16 hi/lo; element counts per plane below)
   __nv_bfloat16 *px[2], *pq[2], *pk[2], *pvt[2], *pp[2], *po[2], *pg[2];
+  __nv_bfloat16 *d0p[2], *u0p[2];   // hi/lo planes of the replicate-padded d0 / u0 grids [B,(V+2)^3,64]
   float *rowmax, *rowsum;
 };
 
@@ -235,6 +236,8 @@ static void carve_work(const Dims& m, int B, Arena& a, Work& w) {
     }
     w.rowmax = a.get<float>(n_rs);
     w.rowsum = a.get<float>(n_rs);
+    const size_t n_pad = Bz * (m.V + 2) * (m.V + 2) * (m.V + 2) * 64;
+    for (int i = 0; i < 2; ++i) { w.d0p[i] = a.get<__nv_bfloat16>(n_pad); w.u0p[i] = a.get<__nv_bfloat16>(n_pad); }
   }
 }
 
@@ -592,8 +595,14 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   STAGE_MARK();  // 0: input_preprocess
   // (1) d0 = act(conv1x1(grid)), fused with (2) feats[0:256] = [ss0(d0), maxpool(d0)]   perceiver_lang_io.py:357-360
   g_launches += 2;
+  const bool fused_planes = d->math_mode == VXB_MATH_BF16X3;   // producers write the final conv's operand planes directly
   VXB_TRY(input_preprocess_ss_run<10>(grid, P(VXB_P_INPRE_W), P(VXB_P_INPRE_B), slope, w.d0, B, m.V, m.V, m.V, 64,
-                                      w.feats, m.flat, w.feats + 192, m.flat, w.ss_part, st));
+                                      w.feats, m.flat, w.feats + 192, m.flat, w.ss_part, st,
+                                      fused_planes ? w.d0p[0] : nullptr, fused_planes ? w.d0p[1] : nullptr));
+  if (fused_planes) {
+    ++g_launches;
+    VXB_TRY(umma::halo_fill(umma::Planes{w.d0p[0], w.d0p[1], 64}, B, m.V, 1, 64, st));
+  }
   STAGE_MARK();  // 1: (fused into stage 0)
   STAGE_MARK();  // 2: patchify
   // (3) patchify conv k, stride s, replicate pad                   :363
@@ -694,24 +703,18 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
                  cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.up0_wt)));
   STAGE_MARK();  // 7: folded upsample-conv
   COUNT_LAUNCH();
-  VXB_TRY(upconv3d_folded(w.low, pw.up1_fold, P(VXB_P_UP1_B), w.u0, B, m.S, 64, 64, m.s, slope, mm, st,
-                          cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.up1_fold)));
+  {
+    const umma::Planes u0p{w.u0p[0], w.u0p[1], 64};
+    if (fused_planes) ++g_launches;
+    VXB_TRY(upconv3d_folded(w.low, pw.up1_fold, P(VXB_P_UP1_B), w.u0, B, m.S, 64, 64, m.s, slope, mm, st,
+                            cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.up1_fold), fused_planes ? &u0p : nullptr));
+  }
   STAGE_MARK();  // 8: final conv
   // (11) final: conv3 on cat[d0, u0] (128 -> 64)                               :462
   COUNT_LAUNCH();
   if (mm == VXB_MATH_BF16X3) {
     // input-stationary tcgen05 convolution on the padded hi/lo planes of d0 and u0 (no concat, no re-fetch per tap)
-    Arena local(cx.scratch.base, cx.scratch.cap);
-    const size_t prow = (size_t)B * (m.V + 2) * (m.V + 2) * (m.V + 2);
-    umma::Planes d0p{local.get<__nv_bfloat16>(prow * 64), local.get<__nv_bfloat16>(prow * 64), 64};
-    umma::Planes u0p{local.get<__nv_bfloat16>(prow * 64), local.get<__nv_bfloat16>(prow * 64), 64};
-    if (!local.ok) {
-      set_error("qnet: scratch too small for the final convolution planes");
-      return VXB_E_WORKSPACE_TOO_SMALL;
-    }
-    g_launches += 2;
-    VXB_TRY(umma::pad_split(w.d0, B, m.V, 1, 64, d0p, st));
-    VXB_TRY(umma::pad_split(w.u0, B, m.V, 1, 64, u0p, st));
+    const umma::Planes d0p{w.d0p[0], w.d0p[1], 64}, u0p{w.u0p[0], w.u0p[1], 64};
     VXB_TRY(umma::conv3_planes(d0p, &u0p, 64, 64, pw.final_wc, P(VXB_P_FINAL_B), slope, w.u, B, m.V, st));
   } else {
     VXB_TRY(conv3d(w.d0, w.u0, 64, 64, pw.final_wt, P(VXB_P_FINAL_B), w.u, B, m.V, m.V, 64, 3, 1, slope, mm, st,

@@ -1,6 +1,7 @@
 // HBM-bound streaming kernels of the Q-network: spatial soft-argmax + global max pooling in one pass,
 // and the 3x3x3 conv to ONE channel (trans_decoder).  Every kernel reads its 256 MB/sample input once.
 #pragma once
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace vxb {
@@ -161,7 +162,8 @@ template <int CIN>
 static __global__ void __launch_bounds__(SS_THREADS)
 input_preprocess_ss_kernel(const float* __restrict__ x /*[B,P,CIN]*/, const float* __restrict__ w /*[C,CIN]*/,
                            const float* __restrict__ bias, float slope, float* __restrict__ y /*[B,P,C]*/,
-                           int P, int C, int Dd, int Hh, int Ww, int chunk, float* __restrict__ partial) {
+                           int P, int C, int Dd, int Hh, int Ww, int chunk, float* __restrict__ partial,
+                           __nv_bfloat16* __restrict__ phi, __nv_bfloat16* __restrict__ plo /*padded planes or null*/) {
   extern __shared__ float ss_smem[];
   const int b = blockIdx.y, ck = blockIdx.x, chunks = gridDim.x;
   const int G = C >> 2;
@@ -204,6 +206,19 @@ input_preprocess_ss_kernel(const float* __restrict__ x /*[B,P,CIN]*/, const floa
         o[j] = slope >= 0.f ? lrelu(a, slope) : a;
       }
       yb[(size_t)p * G] = make_float4(o[0], o[1], o[2], o[3]);
+      if (phi) {
+        // hi/lo planes of the replicate-padded grid [B, D+2, H+2, W+2, C] (interior; the halo is filled afterwards)
+        const size_t prow = (((size_t)b * (Dd + 2) + d + 1) * (Hh + 2) + h + 1) * (Ww + 2) + wv + 1;
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(o[0], o[1]), h23 = __floats2bfloat162_rn(o[2], o[3]);
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(o[0] - f01.x, o[1] - f01.y);
+        const __nv_bfloat162 l23 = __floats2bfloat162_rn(o[2] - f23.x, o[3] - f23.y);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+        lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(phi + prow * C + g * 4) = hv;
+        *reinterpret_cast<uint2*>(plo + prow * C + g * 4) = lv;
+      }
       const float px = lutH[h], py = lutD[d], pz = lutW[wv];
 #pragma unroll
       for (int j = 0; j < 4; ++j) ss_update(st[j], o[j], px, py, pz);
@@ -264,7 +279,8 @@ inline int spatial_softmax_run(const float* x, int B, int Dd, int Hh, int Ww, in
 template <int CIN>
 inline int input_preprocess_ss_run(const float* x, const float* w, const float* bias, float slope, float* y, int B,
                                    int Dd, int Hh, int Ww, int C, float* ss, int ss_stride, float* mx, int mx_stride,
-                                   float* partial, cudaStream_t st) {
+                                   float* partial, cudaStream_t st, __nv_bfloat16* phi = nullptr,
+                                   __nv_bfloat16* plo = nullptr) {
   VXB_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 1024, "input_preprocess: C=%d must be a multiple of 4, <= 1024", C);
   const size_t P = (size_t)Dd * Hh * Ww;
   const int chunks = ss_num_chunks(P, B);
@@ -272,7 +288,7 @@ inline int input_preprocess_ss_run(const float* x, const float* w, const float* 
   const int G = C / 4, PL = SS_THREADS / G;
   const size_t smem = ((size_t)(Dd + Hh + Ww) + (size_t)PL * G * 24) * sizeof(float);
   input_preprocess_ss_kernel<CIN><<<dim3(chunks, B), SS_THREADS, smem, st>>>(x, w, bias, slope, y, (int)P, C, Dd, Hh, Ww,
-                                                                            chunk, partial);
+                                                                            chunk, partial, phi, plo);
   VXB_LAUNCH_CHECK();
   ss_merge_kernel<<<dim3(cdiv(C, 32), B), 256, 0, st>>>(partial, chunks, C, ss, ss_stride, mx, mx_stride);
   VXB_LAUNCH_CHECK();

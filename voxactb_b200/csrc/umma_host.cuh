@@ -103,7 +103,7 @@ int conv3d_f32(const float* x0, const float* x1, int C0, int C1, const Planes& W
                int B, int V, int Co, int k, float act_slope, Arena& scratch, cudaStream_t st);
 size_t upconv_scratch_bytes(int B, int S, int Ci);
 int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out, int B, int S, int Ci, int Co, int s,
-               float act_slope, Arena& scratch, cudaStream_t st);
+               float act_slope, Arena& scratch, cudaStream_t st, const Planes* out_planes = nullptr);
 
 // ---- plane-domain building blocks of the transformer (no fp32 round trips between GEMMs)
 // y = LayerNorm(x) written as planes [rows, n]; input rows may be a strided slice per batch

@@ -433,9 +433,10 @@ size_t upconv_scratch_bytes(int B, int S, int Ci) {
   return a.off;
 }
 
-// folded upsample-conv: low [B,S^3,Ci] fp32 -> out [B,(S*s)^3,64] fp32; Wp planes of [s^3*64][27*Ci]
+// folded upsample-conv: low [B,S^3,Ci] fp32 -> out [B,(S*s)^3,64] fp32 and/or out_planes = hi/lo planes of the
+// replicate-padded fine grid [B,(S*s+2)^3,64] (interior written here, halo by halo_fill); Wp planes of [s^3*64][27*Ci]
 int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out, int B, int S, int Ci, int Co, int s,
-               float act_slope, Arena& scratch, cudaStream_t st) {
+               float act_slope, Arena& scratch, cudaStream_t st, const Planes* out_planes) {
   if (Ci % 64 || Co != 64) {
     set_error("umma upconv: needs Ci %% 64 == 0 and Co == 64");
     return VXB_E_UNSUPPORTED_SHAPE;
@@ -457,12 +458,21 @@ int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out
   p.plan.taps = 3; p.plan.Vp = (int)Sp; p.plan.cpb = Ci / 64; p.plan.cb_src0 = Ci / 64;
   p.plan.num_kb = 27 * p.plan.cpb;
   p.ep.M = (int)rows; p.ep.N = N; p.ep.row_mode = ROWS_PHASE; p.ep.Vp = (int)Sp; p.ep.pad = 1;
-  p.ep.phase_s = s; p.ep.out_Vp = S * s; p.ep.out_pad = 0;
+  p.ep.phase_s = s;
   p.ep.bias = bias; p.ep.act_slope = act_slope;
-  p.ep.out_f32 = out; p.ep.ldc = 64;
+  if (out_planes) {
+    // fine voxel (d,h,w) -> row of the padded grid: the epilogue adds out_pad to every coordinate
+    p.ep.out_Vp = S * s + 2; p.ep.out_pad = 1;
+    p.ep.out_hi = out_planes->hi; p.ep.out_lo = out_planes->lo; p.ep.ldp = 64;
+  } else {
+    p.ep.out_Vp = S * s; p.ep.out_pad = 0;
+    p.ep.out_f32 = out; p.ep.ldc = 64;
+  }
   Operand A0{a0, rows, Ci};
   Operand w{Wp, N, 27ll * Ci};
-  return gemm(A0, nullptr, w, nt, p, st);
+  VXB_TRY(gemm(A0, nullptr, w, nt, p, st));
+  if (out_planes) VXB_TRY(halo_fill(*out_planes, B, S * s, 1, 64, st));
+  return VXB_OK;
 }
 
 
