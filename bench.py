@@ -154,6 +154,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ['NCCL_DEBUG'] = os.environ.get('VXB_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
     L = _lib.lib()
     _lib.check(L.vxb_check_device(), 'vxb_check_device')

@@ -185,6 +185,16 @@ extern "C" int vxb_conv3d_f32(const float* x, const float* w, const float* bias,
   if (Co == 1 && Ci == 64 && k == 3 && s == 1 && act_slope < 0.f)   // trans_decoder shape: streaming stencil
     return trans_stencil_run<64>(x, (const float*)ws, bias, y, B, Di, st);
   Arena scratch((char*)ws + conv_w_bytes(Ci, Co, k), ws_bytes - conv_w_bytes(Ci, Co, k));
+  if (math_mode == VXB_MATH_BF16X3 && s > 1 && Co == 64 && Ci == 64 && bias) {
+    // strided (patchify) convolution: gather-loader tcgen05 kernel (patchify_umma.cuh)
+    __nv_bfloat16* wc = scratch.get<__nv_bfloat16>(umma::patchify_weight_elems(k));
+    if (!scratch.ok) {
+      set_error("conv3d: workspace too small");
+      return VXB_E_WORKSPACE_TOO_SMALL;
+    }
+    VXB_TRY(umma::patchify_prepare_weights((const float*)ws, k, wc, st));
+    return umma::patchify_f32(x, wc, bias, act_slope, y, B, Di, k, s, st);
+  }
   if (math_mode == VXB_MATH_BF16X3 && k == 3 && s == 1 && Co == 64 && Ci == 64 && bias) {
     // input-stationary tcgen05 convolution (conv_umma.cuh): padded hi/lo planes + re-laid weights
     __nv_bfloat16* wc = scratch.get<__nv_bfloat16>(umma::conv3_weight_elems(Ci));

@@ -83,6 +83,7 @@ struct Prepared {
   float* final_wt;   // [64][27][128]
   float* trans_wt;   // [27][64]
   __nv_bfloat16* final_wc;  // [4][27][{hi,lo}][64][32] weights of the input-stationary conv kernel
+  __nv_bfloat16* patch_wc;  // [k^3][{hi,lo}][64][64] weights of the patchify kernel
   float* q_cross;    // [L][ch*cdh]  = to_q(LN(latents)), batch independent
   float* lat_norm;   // [L][D] scratch for the above
   // bf16 hi/lo planes of every weight that feeds a tcgen05 GEMM, keyed by the fp32 weight pointer
@@ -105,6 +106,7 @@ static void carve_prepared(const Dims& m, Arena& a, Prepared& p, const void* con
   p.final_wt = a.get<float>((size_t)64 * 27 * 128);
   p.trans_wt = a.get<float>((size_t)27 * 64);
   p.final_wc = a.get<__nv_bfloat16>(umma::conv3_weight_elems(128));
+  p.patch_wc = a.get<__nv_bfloat16>(umma::patchify_weight_elems(m.k));
   p.q_cross = a.get<float>((size_t)m.L * m.ch * m.cdh);
   p.lat_norm = a.get<float>((size_t)m.L * m.D);
   std::vector<WeightSpec> specs;
@@ -559,6 +561,7 @@ extern "C" int vxb_qnet_prepare(const vxb_qnet_desc* d, const void* const* param
   VXB_TRY(conv_weight_prepare(P(VXB_P_FINAL_W), p.final_wt, 64, 128, 27, st));
   VXB_TRY(conv_weight_prepare(P(VXB_P_TRANS_W), p.trans_wt, 1, 64, 27, st));
   VXB_TRY(umma::conv3_prepare_weights(p.final_wt, 128, p.final_wc, st));
+  VXB_TRY(umma::patchify_prepare_weights(p.patch_wt, m.k, p.patch_wc, st));
   {
     const size_t total = (size_t)m.s * m.s * m.s * 64 * 27 * 64;
     fold_upconv_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(P(VXB_P_UP1_W), p.up1_fold, 64, 64, m.k, m.s);
@@ -607,8 +610,12 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   STAGE_MARK();  // 2: patchify
   // (3) patchify conv k, stride s, replicate pad                   :363
   COUNT_LAUNCH();
-  VXB_TRY(conv3d(w.d0, nullptr, 64, 0, pw.patch_wt, P(VXB_P_PATCH_B), w.patch, B, m.V, m.S, 64, m.k,
-                 m.s, slope, mm, st, nullptr, nullptr));
+  if (mm == VXB_MATH_BF16X3) {
+    VXB_TRY(umma::patchify_f32(w.d0, pw.patch_wc, P(VXB_P_PATCH_B), slope, w.patch, B, m.V, m.k, m.s, st));
+  } else {
+    VXB_TRY(conv3d(w.d0, nullptr, 64, 0, pw.patch_wt, P(VXB_P_PATCH_B), w.patch, B, m.V, m.S, 64, m.k,
+                   m.s, slope, mm, st, nullptr, nullptr));
+  }
   STAGE_MARK();  // 3: token assembly
   // (4) proprio -> 64, language tokens -> C, token assembly + pos  :370-422
     VXB_TRY(lin(cx, proprio, m.low, P(VXB_P_PROPRIO_W), m.low, P(VXB_P_PROPRIO_B), nullptr, 1, 0, w.pfeat,

@@ -2,6 +2,7 @@
 // and the launch wrappers used by dispatch.cuh.
 #include "umma_gemm.cuh"
 #include "conv_umma.cuh"
+#include "patchify_umma.cuh"
 #include <cstdlib>
 #include "umma_host.cuh"
 #include <cudaTypedefs.h>
@@ -747,6 +748,65 @@ int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_
     case 4: return conv3_launch<4>(maps, p, smem, st);
     default: return conv3_launch<2>(maps, p, smem, st);
   }
+}
+
+
+// ------------------------------------------------------------------------------------------ patchify (patchify_umma.cuh)
+size_t patchify_weight_elems(int k) { return (size_t)k * k * k * 2 * 64 * 64; }
+
+static __global__ void patchify_weight_kernel(const float* __restrict__ w /*[64][k3][64]*/, int k3,
+                                              __nv_bfloat16* __restrict__ wc /*[k3][2][64][64]*/) {
+  const long long total = (long long)k3 * 64 * 64;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % 64);
+    const int co = (int)((i / 64) % 64);
+    const int tap = (int)(i / 4096);
+    const float f = w[((long long)co * k3 + tap) * 64 + ci];
+    const __nv_bfloat16 h = __float2bfloat16_rn(f);
+    const long long o = ((long long)tap * 2 * 64 + co) * 64 + ci;
+    wc[o] = h;
+    wc[o + 64 * 64] = __float2bfloat16_rn(f - __bfloat162float(h));
+  }
+}
+
+int patchify_prepare_weights(const float* w_tapmajor, int k, __nv_bfloat16* wc, cudaStream_t st) {
+  patchify_weight_kernel<<<148 * 2, 256, 0, st>>>(w_tapmajor, k * k * k, wc);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+int patchify_f32(const float* x, const __nv_bfloat16* wc, const float* bias, float act_slope, float* out, int B, int V,
+                 int k, int s, cudaStream_t st) {
+  const int pad = k / 2;
+  const int S = (V + 2 * pad - k) / s + 1;
+  if (S <= 0 || ((uintptr_t)x & 15) || ((uintptr_t)out & 15) || ((uintptr_t)bias & 15)) {
+    set_error("patchify: bad geometry or unaligned pointers");
+    return VXB_E_BADARG;
+  }
+  PatchifyParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.bias = bias; p.out = out;
+  p.B = B; p.V = V; p.S = S; p.k = k; p.s = s; p.pad = pad;
+  p.tokens = B * S * S * S;
+  p.tiles = cdiv(p.tokens, 128);
+  p.act_slope = act_slope;
+  CUtensorMap map;
+  VXB_TRY(make_map(&map, wc, (long long)k * k * k * 128, 64, 64, 128));
+  static bool attr_set = false;
+  if (!attr_set) {
+    VXB_CUDA(cudaFuncSetAttribute(patchify_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    VXB_CUDA(cudaGetDevice(&dev));
+    VXB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  ++g_umma_launches;
+  patchify_umma_kernel<<<std::min(p.tiles, num_sms), PF_THREADS, PF_SMEM, st>>>(map, p);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
 }
 
 }  // namespace umma
