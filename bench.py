@@ -12,9 +12,10 @@ data-path collective (weak scaling: --batch samples per GPU).
 `e2e`    : the same through the public API (QFunction.forward + fused action selection) from
            pinned HOST buffers, host->device copies of the observations and device->host read of the
            selected actions inside the timed region.
-`roofline`: the dominant kernel (final 3x3x3 conv 128->64 at 100^3) timed live with CUDA events on
-           the launching stream (library stage profiler), algorithmic FLOPs / time vs the measured
-           tensor peak in MEASURED_PEAKS.json.
+`roofline`: the dominant kernel (conv3_umma_kernel: final 3x3x3 conv 128->64 at 100^3) timed live with CUDA
+           events on the launching stream (library stage profiler), algorithmic FLOPs / time vs the measured
+           tensor peak in MEASURED_PEAKS.json; `traffic` = DRAM bytes per launch from the committed
+           ncu --set full capture (profiles/ncu_r01_conv3_umma_b16_summary.json, same batch).
 `cpu_baseline`: the CPU oracle port (oracle/) of the reference's PyTorch path on the host cores, on
            a bounded sample (batch 1) of the same workload.
 --impl reference: times that CPU implementation alone (the reference itself is Python and is not
@@ -48,6 +49,21 @@ def parse():
     ap.add_argument('--math', default=os.environ.get('VXB_MATH', 'auto'), choices=['auto', 'fp32', 'bf16x3'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
+
+
+def ncu_traffic(batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
+    (taken at batch 16); None for any other batch."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_r01_conv3_umma_b16_summary.json')
+    if batch != 16 or not os.path.exists(path):
+        return None
+    d = json.load(open(path))
+    unit = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
+    tot = 0.0
+    for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+        v, u = d[k].split()
+        tot += float(v) * unit[u]
+    return tot
 
 
 def peaks():
@@ -274,9 +290,15 @@ def run_ours(args):
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': (launches_per_step) * args.steps,
         'clocks': clk,
-        'roofline': {'kernel': 'final_conv (3x3x3, 128->64 @100^3, implicit GEMM)', 'bound': 'tensor',
+        'roofline': {'kernel': 'conv3_umma_kernel: final conv 3x3x3, 128->64 @100^3 (input-stationary tcgen05, split-bf16 x3)'
+                               if math_mode != _lib.MATH_FP32_SIMT else 'final conv 3x3x3, 128->64 @100^3 (fp32 FFMA implicit GEMM)',
+                     'bound': 'tensor',
                      'achieved': achieved_tf, 'peak': pk['tensor'], 'unit': 'TFLOP/s', 'frac': achieved_tf / pk['tensor'],
-                     'traffic': None, 'peak_source': pk['source'] + ' bf16 sustained', 'ms_per_launch': final_ms,
+                     'traffic': ncu_traffic(B) if math_mode != _lib.MATH_FP32_SIMT else None,
+                     'algorithmic_flops_per_launch': FINAL_CONV_FLOPS * B,
+                     'note': 'achieved = direct-convolution FLOPs (442.4 GF/sample) / CUDA-event time; the kernel executes 3 bf16 MMAs per '
+                             'logical product (fp32-class accuracy), so its own ceiling is 1/3 of this bf16 peak',
+                     'peak_source': pk['source'] + ' bf16 sustained', 'ms_per_launch': final_ms,
                      'whole_forward_tflops': FLOPS_PER_PASS * B / (per_step * 1e-3) / 1e12,
                      'voxelize': {'bound': 'hbm', 'achieved': VOXELIZE_BYTES * B / (vox_ms * 1e-3) / 1e9, 'peak': pk['hbm'],
                                   'unit': 'GB/s', 'frac': VOXELIZE_BYTES * B / (vox_ms * 1e-3) / 1e9 / pk['hbm'],

@@ -81,6 +81,19 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same MMA with the descriptors given as (low word, shared high word): the low word advances by bytes >> 4
+__device__ __forceinline__ void tc_mma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi) : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets columns [col, col+32) of TMEM lane (lane_base + t)
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -219,39 +232,47 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) loops so that descriptors stay in uniform registers; one elected
+    // lane issues the tcgen05 instructions (a single divergent lane makes ptxas emit a broadcast loop per MMA).
+    {
+      uint32_t leader;
+      asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.b32 %0, 1, 0, P;\n}\n" : "=r"(leader));
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       constexpr uint32_t idesc = make_idesc(NT);
+      constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024, version 1, SWIZZLE_128B
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const int num_kb = p.plan.num_kb;
+      const bool three = p.terms == 3;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NT);
-        for (int kb = 0; kb < p.plan.num_kb; ++kb) {
+        const uint32_t d_tmem = tmem_u + (uint32_t)(acc * NT);
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa_hi = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t sa_lo = sa_hi + L::A_BYTES;
-          const uint32_t sb_hi = sa_hi + 2 * L::A_BYTES;
-          const uint32_t sb_lo = sb_hi + L::B_BYTES;
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t a_hi = ((sa >> 4) & 0x3FFFu) | (1u << 16);
+          const uint32_t a_lo = a_hi + (L::A_BYTES >> 4);
+          const uint32_t b_hi = a_hi + ((2 * L::A_BYTES) >> 4);
+          const uint32_t b_lo = b_hi + (L::B_BYTES >> 4);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t a_hi = make_desc(sa_hi + k * 32, 1024);
-            const uint64_t a_lo = make_desc(sa_lo + k * 32, 1024);
-            const uint64_t b_hi = make_desc(sb_hi + k * 32, 1024);
-            const uint64_t b_lo = make_desc(sb_lo + k * 32, 1024);
-            tc_mma_bf16(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0);
-            if (p.terms == 3) {
-              tc_mma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
-              tc_mma_bf16(d_tmem, a_lo, b_hi, idesc, 1);
+            for (int k = 0; k < BK / 16; ++k) {
+              tc_mma_bf16_lo(d_tmem, a_hi + 2 * k, b_hi + 2 * k, kDescHi, idesc, (kb | k) != 0);
+              if (three) {
+                tc_mma_bf16_lo(d_tmem, a_hi + 2 * k, b_lo + 2 * k, kDescHi, idesc, 1);
+                tc_mma_bf16_lo(d_tmem, a_lo + 2 * k, b_hi + 2 * k, kDescHi, idesc, 1);
+              }
             }
+            tc_commit(&empty_bar[stage]);             // smem slot reusable once these MMAs retire
+            if (kb == num_kb - 1) tc_commit(&acc_full[acc]);   // accumulator complete -> epilogue
           }
-          tc_commit(&empty_bar[stage]);             // smem slot reusable once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&acc_full[acc]);                  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
