@@ -134,6 +134,13 @@ struct RowInfo {
 };
 constexpr int EPI_BYTES_PER_WARP = 32 * EPI_STAGE_LD * 4 + (int)sizeof(RowInfo);
 
+// specialised epilogues: 8 warps (two per TMEM lane quarter, alternating 32-column chunks), 32 x 32 fp32 staging
+// per warp with an XOR swizzle on the 16-byte column index (conflict-free 128-bit accesses in both domains)
+constexpr int EPW_FAST = 8;
+constexpr int EPI_FAST_BYTES_PER_WARP = 32 * 32 * 4;
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == 0 ? 4 : EPW_FAST; }
+__host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 32 * epi_warps(epi); }
+
 template <int NT, int STAGES>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB per plane
@@ -147,7 +154,7 @@ struct SmemLayout {
 enum { EPIK_GENERIC = 0, EPIK_PLAIN = 1, EPIK_ROWMAX = 2, EPIK_EXP = 3 };
 
 template <int NT, int STAGES, int EPI>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(EPI), 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_constant__ CUtensorMap mapA0l,
                  const __grid_constant__ CUtensorMap mapA1h, const __grid_constant__ CUtensorMap mapA1l,
                  const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
@@ -161,7 +168,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
   uint64_t* acc_full = bars + 2 * STAGES;      // [2] MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * STAGES + 2; // [2] epilogue -> MMA
   uint32_t* tmem_base_smem = (uint32_t*)(bars + 2 * STAGES + 4);
-  __shared__ __align__(16) uint8_t epi_smem[L::EPI_BYTES];   // static: keeps the accesses in the shared window (LDS/STS)
+  // static: keeps the accesses in the shared window (LDS/STS)
+  __shared__ __align__(16) uint8_t epi_smem[EPI == EPIK_GENERIC ? L::EPI_BYTES : EPW_FAST * EPI_FAST_BYTES_PER_WARP];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -172,7 +180,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
     tma_prefetch_desc(&mapA1h); tma_prefetch_desc(&mapA1l);
     tma_prefetch_desc(&mapWh); tma_prefetch_desc(&mapWl);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], epi_warps(EPI)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -286,7 +294,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
     //   EPIK_ROWMAX  attention pass 1, EPIK_EXP attention pass 2, EPIK_GENERIC convolution row modes + V^T planes
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const Epilogue& e = p.ep;
-    float* stage = reinterpret_cast<float*>(epi_smem + q * EPI_BYTES_PER_WARP);
+    const int ew = warp - 2;                        // epilogue warp index
+    const int half = ew >> 2;                       // fast path: which 32-column chunks of a tile this warp takes
+    float* stage = reinterpret_cast<float*>(epi_smem + (EPI == EPIK_GENERIC ? q * EPI_BYTES_PER_WARP : ew * EPI_FAST_BYTES_PER_WARP));
     const int tr = lane >> 3, tc = (lane & 7) * 4;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -323,7 +333,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < NT; c0 += 32) {
+        for (int c0 = half * 32; c0 < NT; c0 += 64) {
           const int n = n0 + c0;
           if (n >= e.N) break;                         // warp-uniform
           uint32_t v[32];
@@ -341,21 +351,34 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
             row_acc = fmaxf(row_acc, mx * e.alpha);    // alpha > 0
           } else {
             if constexpr (EPI == EPIK_EXP) {
+              if (full) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float t[4];
+                for (int j = 0; j < 32; j += 4) {
+                  float t[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t[u]) : "f"(fmaf(__uint_as_float(v[j + u]), e.alpha, -row_sub)));
-                  if (!full) t[u] = (n + j + u < e.N) ? t[u] : 0.f;
-                  row_acc += t[u];
+                  for (int u = 0; u < 4; ++u) {
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t[u]) : "f"(fmaf(__uint_as_float(v[j + u]), e.alpha, -row_sub)));
+                    row_acc += t[u];
+                  }
+                  *reinterpret_cast<float4*>(stage + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) = make_float4(t[0], t[1], t[2], t[3]);
                 }
-                *reinterpret_cast<float4*>(stage + lane * EPI_STAGE_LD + j) = make_float4(t[0], t[1], t[2], t[3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float t[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t[u]) : "f"(fmaf(__uint_as_float(v[j + u]), e.alpha, -row_sub)));
+                    t[u] = (n + j + u < e.N) ? t[u] : 0.f;
+                    row_acc += t[u];
+                  }
+                  *reinterpret_cast<float4*>(stage + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) = make_float4(t[0], t[1], t[2], t[3]);
+                }
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(stage + lane * EPI_STAGE_LD + j) =
+                *reinterpret_cast<float4*>(stage + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) =
                     make_float4(__uint_as_float(v[j]) * e.alpha, __uint_as_float(v[j + 1]) * e.alpha,
                                 __uint_as_float(v[j + 2]) * e.alpha, __uint_as_float(v[j + 3]) * e.alpha);
             }
@@ -366,7 +389,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
             if (nv > 0) {
               float4 x4[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) x4[i] = *reinterpret_cast<const float4*>(stage + (i * 4 + tr) * EPI_STAGE_LD + tc);
+              for (int i = 0; i < 8; ++i) {
+                const int r = i * 4 + tr;
+                x4[i] = *reinterpret_cast<const float4*>(stage + r * 32 + ((((lane & 7)) ^ (r & 7)) << 2));
+              }
               if constexpr (EPI == EPIK_PLAIN) {
                 float bv[4] = {0.f, 0.f, 0.f, 0.f};
                 if (e.bias) {

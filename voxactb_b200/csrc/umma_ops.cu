@@ -289,7 +289,7 @@ static int launch_e(const CUtensorMap* maps, const Params& p, cudaStream_t st) {
   }
   const long long tiles = (long long)p.m_tiles * p.n_tiles * p.batches;
   const int grid = (int)std::min<long long>(tiles, num_sms);
-  umma_gemm_kernel<NT, STAGES, EPI><<<grid, THREADS, L::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  umma_gemm_kernel<NT, STAGES, EPI><<<grid, gemm_threads(EPI), L::TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }
