@@ -23,7 +23,9 @@ constexpr int PF_WBYTES = 128 * 128;
 constexpr int PF_SMEM = PF_ASTAGES * PF_ABYTES + PF_WSTAGES * PF_WBYTES + 1024;
 
 struct PatchifyParams {
-  const float* x;        // [B, V, V, V, 64]
+  const float* x;        // [B, V, V, V, 64] fp32, or null when the input comes as planes
+  const __nv_bfloat16* xhi;   // hi/lo planes of the replicate-padded grid [B, V+2, V+2, V+2, 64]
+  const __nv_bfloat16* xlo;
   const float* bias;     // [64]
   float* out;            // [B, S^3, 64]
   int B, V, S, k, s, pad;
@@ -53,6 +55,8 @@ __device__ __forceinline__ void split_store_row(uint8_t* hi_row, uint8_t* lo_row
   }
 }
 
+// PLANES = true: the input is already split (written by input_preprocess): the loaders only copy 2 x 128 bytes per row
+template <bool PLANES>
 __global__ void __launch_bounds__(PF_THREADS, 1)
 patchify_umma_kernel(const __grid_constant__ CUtensorMap mapW, const PatchifyParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -101,6 +105,49 @@ patchify_umma_kernel(const __grid_constant__ CUtensorMap mapW, const PatchifyPar
         ow = tok % S; oh = (tok / S) % S; od = (tok / (S * S)) % S; b = tok / (S * S * S);
       }
       const int d0 = od * p.s - p.pad, h0 = oh * p.s - p.pad, w0 = ow * p.s - p.pad;
+      if constexpr (PLANES) {
+        const int Vp = V + 2;
+        auto src = [&](int tap) -> size_t {
+          const int tw = tap % p.k, th = (tap / p.k) % p.k, td = tap / (p.k * p.k);
+          const int vd = min(max(d0 + td, 0), V - 1), vh = min(max(h0 + th, 0), V - 1), vw = min(max(w0 + tw, 0), V - 1);
+          return ((((size_t)b * Vp + vd + 1) * Vp + vh + 1) * Vp + vw + 1) * 64;
+        };
+        uint4 ch[8], cl[8];
+        {
+          const size_t o = src(0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            ch[j] = valid ? __ldg(reinterpret_cast<const uint4*>(p.xhi + o) + j) : make_uint4(0, 0, 0, 0);
+            cl[j] = valid ? __ldg(reinterpret_cast<const uint4*>(p.xlo + o) + j) : make_uint4(0, 0, 0, 0);
+          }
+        }
+        for (int tap = 0; tap < k3; ++tap) {
+          uint4 nh[8], nl[8];
+          if (tap + 1 < k3) {
+            const size_t o = src(tap + 1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              nh[j] = valid ? __ldg(reinterpret_cast<const uint4*>(p.xhi + o) + j) : make_uint4(0, 0, 0, 0);
+              nl[j] = valid ? __ldg(reinterpret_cast<const uint4*>(p.xlo + o) + j) : make_uint4(0, 0, 0, 0);
+            }
+          }
+          mbar_wait(&a_empty[st], ph ^ 1);
+          uint8_t* sa = a_base + st * PF_ABYTES;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int off = (c ^ (r & 7)) * 16;
+            *reinterpret_cast<uint4*>(sa + r * 128 + off) = ch[c];
+            *reinterpret_cast<uint4*>(sa + 128 * 128 + r * 128 + off) = cl[c];
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05
+          mbar_arrive(&a_full[st]);
+          if (++st == PF_ASTAGES) { st = 0; ph ^= 1; }
+          if (tap + 1 < k3) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ch[j] = nh[j]; cl[j] = nl[j]; }
+          }
+        }
+      } else {
       const float* xb = p.x + (size_t)b * V * V * V * 64;
       auto src = [&](int tap) -> const float4* {
         const int tw = tap % p.k, th = (tap / p.k) % p.k, td = tap / (p.k * p.k);
@@ -130,6 +177,7 @@ patchify_umma_kernel(const __grid_constant__ CUtensorMap mapW, const PatchifyPar
 #pragma unroll
           for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
         }
+      }
       }
       // ---- epilogue of this tile: out = act(D[:, 0:64] + D[:, 64:128] + bias)
       mbar_wait(acc_full, accph);

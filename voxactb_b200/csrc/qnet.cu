@@ -599,7 +599,8 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   // (1) d0 = act(conv1x1(grid)), fused with (2) feats[0:256] = [ss0(d0), maxpool(d0)]   perceiver_lang_io.py:357-360
   g_launches += 2;
   const bool fused_planes = d->math_mode == VXB_MATH_BF16X3;   // producers write the final conv's operand planes directly
-  VXB_TRY(input_preprocess_ss_run<10>(grid, P(VXB_P_INPRE_W), P(VXB_P_INPRE_B), slope, w.d0, B, m.V, m.V, m.V, 64,
+  // (split-bf16 path: d0 only ever exists as the hi/lo planes that the patchify and final convolutions consume)
+  VXB_TRY(input_preprocess_ss_run<10>(grid, P(VXB_P_INPRE_W), P(VXB_P_INPRE_B), slope, fused_planes ? nullptr : w.d0, B, m.V, m.V, m.V, 64,
                                       w.feats, m.flat, w.feats + 192, m.flat, w.ss_part, st,
                                       fused_planes ? w.d0p[0] : nullptr, fused_planes ? w.d0p[1] : nullptr));
   if (fused_planes) {
@@ -611,7 +612,8 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   // (3) patchify conv k, stride s, replicate pad                   :363
   COUNT_LAUNCH();
   if (mm == VXB_MATH_BF16X3) {
-    VXB_TRY(umma::patchify_f32(w.d0, pw.patch_wc, P(VXB_P_PATCH_B), slope, w.patch, B, m.V, m.k, m.s, st));
+    const umma::Planes d0p{w.d0p[0], w.d0p[1], 64};
+    VXB_TRY(umma::patchify_f32(nullptr, pw.patch_wc, P(VXB_P_PATCH_B), slope, w.patch, B, m.V, m.k, m.s, st, &d0p));
   } else {
     VXB_TRY(conv3d(w.d0, nullptr, 64, 0, pw.patch_wt, P(VXB_P_PATCH_B), w.patch, B, m.V, m.S, 64, m.k,
                    m.s, slope, mm, st, nullptr, nullptr));

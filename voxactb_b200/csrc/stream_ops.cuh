@@ -205,7 +205,7 @@ input_preprocess_ss_kernel(const float* __restrict__ x /*[B,P,CIN]*/, const floa
         for (int i = 0; i < CIN; ++i) a = fmaf(in[i], wr[j][i], a);
         o[j] = slope >= 0.f ? lrelu(a, slope) : a;
       }
-      yb[(size_t)p * G] = make_float4(o[0], o[1], o[2], o[3]);
+      if (y) yb[(size_t)p * G] = make_float4(o[0], o[1], o[2], o[3]);
       if (phi) {
         // hi/lo planes of the replicate-padded grid [B, D+2, H+2, W+2, C] (interior; the halo is filled afterwards)
         const size_t prow = (((size_t)b * (Dd + 2) + d + 1) * (Hh + 2) + h + 1) * (Ww + 2) + wv + 1;

@@ -143,8 +143,9 @@ int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_
 // weights: tap-major fp32 [64][k^3][64] -> bf16 [k^3][{hi,lo}][64][64]
 size_t patchify_weight_elems(int k);
 int patchify_prepare_weights(const float* w_tapmajor, int k, __nv_bfloat16* wc, cudaStream_t st);
+// x fp32 [B,V^3,64], or (xplanes != null) the hi/lo planes of the replicate-padded grid [B,(V+2)^3,64]
 int patchify_f32(const float* x, const __nv_bfloat16* wc, const float* bias, float act_slope, float* out, int B, int V,
-                 int k, int s, cudaStream_t st);
+                 int k, int s, cudaStream_t st, const Planes* xplanes = nullptr);
 
 // unit-test entry: fp32 q/k/v in, fp32 out, through the plane-domain attention (scratch sized by the _bytes query)
 size_t attention_f32_scratch_bytes(int B, int H, int Nq, int Nk, int dh);

@@ -720,12 +720,23 @@ int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_
   p.B = B; p.V = V; p.Vp = Vp;
   p.ncb = (C0 + C1) / CV_KC; p.cb_src0 = C0 / CV_KC;
   p.tiles = cdiv((long long)Vp * Vp, 128);
-  // z chunks: enough items for ~3 rounds per cluster, chunks of at least 8 planes
-  int zch = 1;
-  while ((long long)B * p.tiles * zch < 148 * 3 && V / (zch * 2) >= 8) zch *= 2;
-  if (V >= 64 && zch < 4) zch = 4;
-  p.lz = cdiv(V, zch);
-  p.zchunks = cdiv(V, p.lz);
+  // z chunking: each chunk of lz output planes stages lz + 2 input planes; pick the chunk count that minimises
+  // rounds(per cluster) x (lz + 2), i.e. halo re-reads against load imbalance of the persistent schedule
+  {
+    const int clusters = std::max(1, (cl == 4 ? 132 : 148) / cl);
+    const long long ncols = cdiv((long long)B * p.tiles, cl) * cl;
+    long long best = -1;
+    int best_lz = V;
+    for (int zch = 1; zch <= std::max(1, V / 4); ++zch) {
+      const int lz = cdiv(V, zch);
+      const int zc = cdiv(V, lz);
+      const long long rounds = cdiv(ncols * zc / cl, clusters);
+      const long long cost = rounds * (lz + 2);
+      if (best < 0 || cost < best) { best = cost; best_lz = lz; }
+    }
+    p.lz = best_lz;
+    p.zchunks = cdiv(V, p.lz);
+  }
   const int cols = B * p.tiles;
   const int cols_pad = cdiv(cols, cl) * cl;
   p.items = cols_pad * p.zchunks;
@@ -776,16 +787,18 @@ int patchify_prepare_weights(const float* w_tapmajor, int k, __nv_bfloat16* wc, 
 }
 
 int patchify_f32(const float* x, const __nv_bfloat16* wc, const float* bias, float act_slope, float* out, int B, int V,
-                 int k, int s, cudaStream_t st) {
+                 int k, int s, cudaStream_t st, const Planes* xplanes) {
   const int pad = k / 2;
   const int S = (V + 2 * pad - k) / s + 1;
-  if (S <= 0 || ((uintptr_t)x & 15) || ((uintptr_t)out & 15) || ((uintptr_t)bias & 15)) {
+  if (S <= 0 || (!xplanes && (!x || ((uintptr_t)x & 15))) || ((uintptr_t)out & 15) || ((uintptr_t)bias & 15) ||
+      (xplanes && xplanes->ld != 64)) {
     set_error("patchify: bad geometry or unaligned pointers");
     return VXB_E_BADARG;
   }
   PatchifyParams p;
   memset(&p, 0, sizeof(p));
-  p.x = x; p.bias = bias; p.out = out;
+  p.x = xplanes ? nullptr : x; p.bias = bias; p.out = out;
+  if (xplanes) { p.xhi = xplanes->hi; p.xlo = xplanes->lo; }
   p.B = B; p.V = V; p.S = S; p.k = k; p.s = s; p.pad = pad;
   p.tokens = B * S * S * S;
   p.tiles = cdiv(p.tokens, 128);
@@ -794,7 +807,8 @@ int patchify_f32(const float* x, const __nv_bfloat16* wc, const float* bias, flo
   VXB_TRY(make_map(&map, wc, (long long)k * k * k * 128, 64, 64, 128));
   static bool attr_set = false;
   if (!attr_set) {
-    VXB_CUDA(cudaFuncSetAttribute(patchify_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    VXB_CUDA(cudaFuncSetAttribute(patchify_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    VXB_CUDA(cudaFuncSetAttribute(patchify_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
     attr_set = true;
   }
   static int num_sms = 0;
@@ -804,7 +818,8 @@ int patchify_f32(const float* x, const __nv_bfloat16* wc, const float* bias, flo
     VXB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   ++g_umma_launches;
-  patchify_umma_kernel<<<std::min(p.tiles, num_sms), PF_THREADS, PF_SMEM, st>>>(map, p);
+  if (xplanes) patchify_umma_kernel<true><<<std::min(p.tiles, num_sms), PF_THREADS, PF_SMEM, st>>>(map, p);
+  else patchify_umma_kernel<false><<<std::min(p.tiles, num_sms), PF_THREADS, PF_SMEM, st>>>(map, p);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }
