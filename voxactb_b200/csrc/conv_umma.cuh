@@ -19,6 +19,7 @@
 // 3-6 = epilogue (TMEM -> registers -> smem transpose -> coalesced fp32 stores).
 #pragma once
 #include "umma_gemm.cuh"
+#include "stream_ops.cuh"
 
 namespace vxb {
 namespace umma {
@@ -43,8 +44,20 @@ struct ConvParams {
   int base_off_mode;    // descriptor base-offset policy for row-shifted operands (see make_desc64)
   const float* bias;
   float act_slope;
-  float* out;           // [B, V, V, V, 64] fp32
+  float* out;           // [B, V, V, V, 64] fp32 (null in tail mode)
+  // fused tail (trans_decoder taps + ss_final / max-pool partials computed from the accumulator rows; the
+  // convolution output itself is never written):
+  const float* tail_w;  // [27][64] tap-major weights of the 64 -> 1 convolution, or null
+  float* ptap;          // [B][27][V^3]: ptap[b][t][v] = <tail_w[t], u[b, v, :]>
+  float* ss_partial;    // [B][chunks][6][64], chunks = zchunks * tiles * 16 (one per item x warp x row group)
 };
+
+struct TailRowInfo {
+  long long orow[32];   // (y*V + x) of the row's voxel inside an output plane, -1 = halo / padding row
+  float px[32];         // SpatialSoftmax3D coordinates of the row (pos_x along H, pos_z along W)
+  float pz[32];
+};
+static_assert(sizeof(TailRowInfo) <= sizeof(RowInfo), "TailRowInfo must fit the RowInfo slot of the staging area");
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -104,6 +117,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(16) uint8_t epi_smem[4 * EPI_BYTES_PER_WARP];
   __shared__ __align__(8) uint64_t bars[2 * CV_SLABS + 2 * CV_WSTAGES + 8];
+  __shared__ __align__(16) float tail_sw[27 * 64 + 64];       // tail weights + conv bias (tail mode only)
   __shared__ uint32_t tmem_base_smem;
 
   const int plane_bytes = 2 * p.box_rows * 64;                 // one plane (hi or lo) of a slab
@@ -133,6 +147,10 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (p.tail_w) {
+    for (int i = threadIdx.x; i < 27 * 64; i += CV_THREADS) tail_sw[i] = p.tail_w[i];
+    for (int i = threadIdx.x; i < 64; i += CV_THREADS) tail_sw[27 * 64 + i] = p.bias[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -300,6 +318,102 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
       decode(item, b, t, z0, lz);
       const int per_chunk = p.items / p.zchunks;
       const bool real = (item % per_chunk) < p.B * p.tiles;
+      if (p.tail_w) {
+        // ---------------- fused tail: u = act(conv) stays in registers / smem
+        TailRowInfo* tri = reinterpret_cast<TailRowInfo*>(ri);
+        const int rr = t * 128 + q * 32 + lane;
+        const int yp = rr / Vp, xp = rr - yp * Vp;
+        const bool ok = real && rr < Vp2 && yp >= 1 && yp <= V && xp >= 1 && xp <= V;
+        const long long yx = ok ? ((long long)(yp - 1) * V + (xp - 1)) : -1;
+        tri->orow[lane] = yx;
+        tri->px[lane] = ok ? ss_lin_coord(yp - 1, V) : 0.f;
+        tri->pz[lane] = ok ? ss_lin_coord(xp - 1, V) : 0.f;
+        __syncwarp();
+        SSState st[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) st[k] = {-INFINITY, 0.f, 0.f, 0.f, 0.f, -INFINITY};
+        const size_t V3 = (size_t)V * V * V;
+        for (int zo = z0; zo < z0 + lz; ++zo) {
+          const int slot = (zo - z0) & 3;
+          const float py = ss_lin_coord(zo, V);
+          mbar_wait(&acc_full[slot], (full_ph >> slot) & 1u);
+          full_ph ^= 1u << slot;
+          tc_fence_after();
+          float pt[27];
+#pragma unroll
+          for (int tp = 0; tp < 27; ++tp) pt[tp] = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c0 = cc * 32;
+            uint32_t v0[32], v1[32];
+            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128 + c0), v0);
+            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128 + 64 + c0), v1);
+            float u[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(tail_sw + 27 * 64 + c0 + j);
+              u[j] = __uint_as_float(v0[j]) + __uint_as_float(v1[j]) + bv.x;
+              u[j + 1] = __uint_as_float(v0[j + 1]) + __uint_as_float(v1[j + 1]) + bv.y;
+              u[j + 2] = __uint_as_float(v0[j + 2]) + __uint_as_float(v1[j + 2]) + bv.z;
+              u[j + 3] = __uint_as_float(v0[j + 3]) + __uint_as_float(v1[j + 3]) + bv.w;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) u[j + k] = fmaxf(u[j + k], u[j + k] * slope);
+              *reinterpret_cast<float4*>(stage + lane * EPI_STAGE_LD + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
+            }
+            // the 27 tap dot products of this row (weights broadcast from shared memory)
+#pragma unroll
+            for (int tp = 0; tp < 27; ++tp) {
+              const float4* w4 = reinterpret_cast<const float4*>(tail_sw + tp * 64 + c0);
+              float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) {
+                const float4 wa = w4[j], wb = w4[j + 1];
+                a0 = fmaf(u[4 * j], wa.x, a0); a0 = fmaf(u[4 * j + 1], wa.y, a0);
+                a0 = fmaf(u[4 * j + 2], wa.z, a0); a0 = fmaf(u[4 * j + 3], wa.w, a0);
+                a1 = fmaf(u[4 * j + 4], wb.x, a1); a1 = fmaf(u[4 * j + 5], wb.y, a1);
+                a1 = fmaf(u[4 * j + 6], wb.z, a1); a1 = fmaf(u[4 * j + 7], wb.w, a1);
+              }
+              pt[tp] += a0 + a1;
+            }
+            __syncwarp();
+            // column domain: soft-argmax / max partials of ss_final (lane owns columns c0 + tc .. +3)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + tr;
+              if (tri->orow[r] >= 0) {
+                const float4 x = *reinterpret_cast<const float4*>(stage + r * EPI_STAGE_LD + tc);
+                const float px = tri->px[r], pz = tri->pz[r];
+                ss_update(st[cc * 4 + 0], x.x, px, py, pz);
+                ss_update(st[cc * 4 + 1], x.y, px, py, pz);
+                ss_update(st[cc * 4 + 2], x.z, px, py, pz);
+                ss_update(st[cc * 4 + 3], x.w, px, py, pz);
+              }
+            }
+            __syncwarp();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[slot]);
+          if (yx >= 0) {
+            float* dst = p.ptap + (size_t)b * 27 * V3 + (size_t)zo * V * V + yx;
+#pragma unroll
+            for (int tp = 0; tp < 27; ++tp) dst[(size_t)tp * V3] = pt[tp];
+          }
+        }
+        if (real) {
+          // one partial per (item, warp, row group): merged by ss_merge_kernel
+          const int zc = z0 / p.lz;
+          const int chunks = p.zchunks * p.tiles * 16;
+          const int chunk = ((zc * p.tiles + t) * 4 + q) * 4 + tr;
+          float* o = p.ss_partial + ((size_t)b * chunks + chunk) * 6 * 64;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int c = (k >> 2) * 32 + tc + (k & 3);
+            o[c] = st[k].m; o[64 + c] = st[k].s; o[128 + c] = st[k].sx; o[192 + c] = st[k].sy; o[256 + c] = st[k].sz;
+            o[320 + c] = st[k].rm;
+          }
+        }
+      } else {
       // row -> output voxel (fixed over z): flat plane row rr = t*128 + row -> (yp, xp)
       {
         const int rr = t * 128 + q * 32 + lane;
@@ -341,6 +455,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[slot]);
+      }
       }
       __syncwarp();
     }

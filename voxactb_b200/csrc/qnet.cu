@@ -172,6 +172,7 @@ struct Work {
   __nv_bfloat16 *px[2], *pq[2], *pk[2], *pvt[2], *pp[2], *po[2], *pg[2];
   __nv_bfloat16 *d0p[2], *u0p[2];   // hi/lo planes of the replicate-padded d0 / u0 grids [B,(V+2)^3,64]
   float *rowmax, *rowsum;
+  float *tail_part;                 // ss_final partials written by the fused conv tail
 };
 
 static size_t sim_floats(const Dims& m, int B) {
@@ -240,6 +241,7 @@ static void carve_work(const Dims& m, int B, Arena& a, Work& w) {
     w.rowsum = a.get<float>(n_rs);
     const size_t n_pad = Bz * (m.V + 2) * (m.V + 2) * (m.V + 2) * 64;
     for (int i = 0; i < 2; ++i) { w.d0p[i] = a.get<__nv_bfloat16>(n_pad); w.u0p[i] = a.get<__nv_bfloat16>(n_pad); }
+    w.tail_part = a.get<float>(umma::conv3_tail_partial_floats(B, m.V));
   }
 }
 
@@ -721,23 +723,34 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   STAGE_MARK();  // 8: final conv
   // (11) final: conv3 on cat[d0, u0] (128 -> 64)                               :462
   COUNT_LAUNCH();
+  const int off = 256 + 4 * m.C;
   if (mm == VXB_MATH_BF16X3) {
     // input-stationary tcgen05 convolution on the padded hi/lo planes of d0 and u0 (no concat, no re-fetch per tap)
+    // with the tail fused into its epilogue: the 27 trans_decoder tap products and the ss_final / max-pool partials
+    // are formed from the accumulator rows, u itself is never written (steps 12 and 13 below)     :462-470
     const umma::Planes d0p{w.d0p[0], w.d0p[1], 64}, u0p{w.u0p[0], w.u0p[1], 64};
-    VXB_TRY(umma::conv3_planes(d0p, &u0p, 64, 64, pw.final_wc, P(VXB_P_FINAL_B), slope, w.u, B, m.V, st));
+    umma::ConvTail tail;
+    tail.tail_w = pw.trans_wt; tail.tail_b = P(VXB_P_TRANS_B);
+    tail.ptap = w.u;                       // the u buffer is free: [B][27][V^3] fits in [B][V^3][64]
+    tail.ss_partial = w.tail_part;
+    tail.q_trans = q_trans;
+    tail.ss = w.feats + off; tail.ss_stride = m.flat; tail.mx = w.feats + off + 192; tail.mx_stride = m.flat;
+    g_launches += 2;
+    VXB_TRY(umma::conv3_planes(d0p, &u0p, 64, 64, pw.final_wc, P(VXB_P_FINAL_B), slope, nullptr, B, m.V, st, &tail));
+    STAGE_MARK();  // 9: (fused into stage 8)
+    STAGE_MARK();  // 10: heads
   } else {
     VXB_TRY(conv3d(w.d0, w.u0, 64, 64, pw.final_wt, P(VXB_P_FINAL_B), w.u, B, m.V, m.V, 64, 3, 1, slope, mm, st,
                    cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.final_wt)));
+    STAGE_MARK();  // 9: trans decoder
+    // (12) trans decoder: conv3 64 -> 1, no activation                            :465
+    COUNT_LAUNCH();
+    VXB_TRY(trans_stencil_run<64>(w.u, pw.trans_wt, P(VXB_P_TRANS_B), q_trans, B, m.V, st));
+    STAGE_MARK();  // 10: ss_final + heads
+    // (13) feats[256+4C :] = [ss_final(u), maxpool(u)], MLP heads                 :470-483
+    VXB_TRY(spatial_softmax(w.u, B, m.V, m.V, m.V, 64, w.feats + off, m.flat, w.feats + off + 192, m.flat,
+                            w.ss_part, st));
   }
-  STAGE_MARK();  // 9: trans decoder
-  // (12) trans decoder: conv3 64 -> 1, no activation                            :465
-  COUNT_LAUNCH();
-  VXB_TRY(trans_stencil_run<64>(w.u, pw.trans_wt, P(VXB_P_TRANS_B), q_trans, B, m.V, st));
-  STAGE_MARK();  // 10: ss_final + heads
-  // (13) feats[256+4C :] = [ss_final(u), maxpool(u)], MLP heads                 :470-483
-  const int off = 256 + 4 * m.C;
-  VXB_TRY(spatial_softmax(w.u, B, m.V, m.V, m.V, 64, w.feats + off, m.flat, w.feats + off + 192, m.flat,
-                          w.ss_part, st));
     VXB_TRY(lin(cx, w.feats, m.flat, P(VXB_P_DENSE0_W), m.flat, P(VXB_P_DENSE0_B), nullptr, 1, 0, w.h0, 256, B,
                  256, m.flat, 1.f, slope, VXB_MATH_FP32_SIMT));
     VXB_TRY(lin(cx, w.h0, 256, P(VXB_P_DENSE1_W), 256, P(VXB_P_DENSE1_B), nullptr, 1, 0, w.h1, 64, B, 64, 256,

@@ -136,8 +136,21 @@ int attention_planes(const Planes& Q, int q_batched, const Planes& K, const Plan
 size_t conv3_weight_elems(int Cin);
 int conv3_prepare_weights(const float* w_tapmajor, int Cin, __nv_bfloat16* wc, cudaStream_t st);
 // x0 / x1: hi-lo planes of the replicate-padded grids [B, V+2, V+2, V+2, 64]; out fp32 [B, V^3, 64]
+// Fused tail of the final convolution (trans_decoder taps + ss_final / max-pool): u = act(conv) is never stored.
+struct ConvTail {
+  const float* tail_w;   // [27][64] tap-major weights of the 64 -> 1 convolution
+  const float* tail_b;   // [1]
+  float* ptap;           // scratch [B][27][V^3] fp32
+  float* ss_partial;     // scratch, conv3_tail_partial_floats(B, V) floats
+  float* q_trans;        // out [B, V^3]
+  float* ss;             // out: soft-argmax [B, ss_stride] (3 per channel) and max [B, mx_stride]
+  int ss_stride;
+  float* mx;
+  int mx_stride;
+};
+size_t conv3_tail_partial_floats(int B, int V);
 int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_bfloat16* wc, const float* bias,
-                 float act_slope, float* out, int B, int V, cudaStream_t st);
+                 float act_slope, float* out, int B, int V, cudaStream_t st, const ConvTail* tail = nullptr);
 
 // ---- patchify (patchify_umma.cuh): Conv3d(64 -> 64, k, stride s, replicate pad k/2) + act on fp32 channels-last x
 // weights: tap-major fp32 [64][k^3][64] -> bf16 [k^3][{hi,lo}][64][64]

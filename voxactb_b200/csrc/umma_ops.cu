@@ -665,10 +665,10 @@ int conv3_prepare_weights(const float* w_tapmajor, int Cin, __nv_bfloat16* wc, c
 
 template <int CL>
 static int conv3_launch(const CUtensorMap* maps, const ConvParams& p, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    VXB_CUDA(cudaFuncSetAttribute(conv3_umma_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    VXB_CUDA(cudaFuncSetAttribute(conv3_umma_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
   }
   static int num_sms = 0;
   if (!num_sms) {
@@ -699,19 +699,81 @@ static int conv3_launch(const CUtensorMap* maps, const ConvParams& p, size_t sme
   return VXB_OK;
 }
 
+static int conv3_cluster() {
+  static int cl = 0;
+  if (!cl) {
+    const char* e = getenv("VXB_CONV_CLUSTER");
+    cl = e ? atoi(e) : 2;
+    if (cl != 1 && cl != 2 && cl != 4) cl = 2;
+  }
+  return cl;
+}
+// z chunking: each chunk of lz output planes stages lz + 2 input planes; pick the chunk count that minimises
+// rounds(per cluster) x (lz + 2), i.e. halo re-reads against load imbalance of the persistent schedule
+static void conv3_plan(int B, int V, int cl, int& tiles, int& lz, int& zchunks) {
+  const int Vp = V + 2;
+  tiles = cdiv((long long)Vp * Vp, 128);
+  const int clusters = std::max(1, (cl == 4 ? 132 : 148) / cl);
+  const long long ncols = cdiv((long long)B * tiles, cl) * cl;
+  long long best = -1;
+  int best_lz = V;
+  for (int zch = 1; zch <= std::max(1, V / 4); ++zch) {
+    const int l = cdiv(V, zch);
+    const int zc = cdiv(V, l);
+    const long long rounds = cdiv(ncols * zc / cl, clusters);
+    const long long cost = rounds * (l + 2);
+    if (best < 0 || cost < best) { best = cost; best_lz = l; }
+  }
+  lz = best_lz;
+  zchunks = cdiv(V, lz);
+}
+
+size_t conv3_tail_partial_floats(int B, int V) {
+  int tiles, lz, zchunks;
+  conv3_plan(B, V, conv3_cluster(), tiles, lz, zchunks);
+  return (size_t)B * zchunks * tiles * 16 * 6 * 64;
+}
+
+// trans[b, v] = bias + sum_t ptap[b][t][clamp(v + offset_t)]   (replicate padding of the 3x3x3 stencil)
+static __global__ void __launch_bounds__(256)
+trans_gather_kernel(const float* __restrict__ ptap, const float* __restrict__ bias, float* __restrict__ y, int B, int V) {
+  const size_t V3 = (size_t)V * V * V;
+  const size_t total = (size_t)B * V3;
+  const float bv = bias[0];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % V), yy = (int)((i / V) % V), z = (int)((i / ((size_t)V * V)) % V);
+    const int b = (int)(i / V3);
+    const float* pb = ptap + (size_t)b * 27 * V3;
+    float acc = bv;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz) {
+      const int zz = min(max(z + dz, 0), V - 1);
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int yc = min(max(yy + dy, 0), V - 1);
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int xc = min(max(x + dx, 0), V - 1);
+          const int tp = (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1);
+          acc += __ldg(pb + (size_t)tp * V3 + ((size_t)zz * V + yc) * V + xc);
+        }
+      }
+    }
+    y[i] = acc;
+  }
+}
+
 int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_bfloat16* wc, const float* bias,
-                 float act_slope, float* out, int B, int V, cudaStream_t st) {
+                 float act_slope, float* out, int B, int V, cudaStream_t st, const ConvTail* tail) {
   const int Vp = V + 2;
   const long long rows = (long long)B * Vp * Vp * Vp;
   if (C0 % CV_KC || C1 % CV_KC || x0.ld != 64 || (x1 && x1->ld != 64) || C0 > 64 || C1 > 64 || rows >= (1ll << 31) || Vp > 180) {
     set_error("conv3_planes: unsupported geometry (C0=%d C1=%d V=%d)", C0, C1, V);
     return VXB_E_UNSUPPORTED_SHAPE;
   }
-  static int cl = 0, desc_mode = -1;
-  if (!cl) {
-    const char* e = getenv("VXB_CONV_CLUSTER");
-    cl = e ? atoi(e) : 2;
-    if (cl != 1 && cl != 2 && cl != 4) cl = 2;
+  const int cl = conv3_cluster();
+  static int desc_mode = -1;
+  if (desc_mode < 0) {
     const char* d = getenv("VXB_CONV_DESC_MODE");
     desc_mode = d ? atoi(d) : 0;   // measured on B200: the swizzle is a function of the absolute smem address, base offset 0
   }
@@ -719,24 +781,7 @@ int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_
   memset(&p, 0, sizeof(p));
   p.B = B; p.V = V; p.Vp = Vp;
   p.ncb = (C0 + C1) / CV_KC; p.cb_src0 = C0 / CV_KC;
-  p.tiles = cdiv((long long)Vp * Vp, 128);
-  // z chunking: each chunk of lz output planes stages lz + 2 input planes; pick the chunk count that minimises
-  // rounds(per cluster) x (lz + 2), i.e. halo re-reads against load imbalance of the persistent schedule
-  {
-    const int clusters = std::max(1, (cl == 4 ? 132 : 148) / cl);
-    const long long ncols = cdiv((long long)B * p.tiles, cl) * cl;
-    long long best = -1;
-    int best_lz = V;
-    for (int zch = 1; zch <= std::max(1, V / 4); ++zch) {
-      const int lz = cdiv(V, zch);
-      const int zc = cdiv(V, lz);
-      const long long rounds = cdiv(ncols * zc / cl, clusters);
-      const long long cost = rounds * (lz + 2);
-      if (best < 0 || cost < best) { best = cost; best_lz = lz; }
-    }
-    p.lz = best_lz;
-    p.zchunks = cdiv(V, p.lz);
-  }
+  conv3_plan(B, V, cl, p.tiles, p.lz, p.zchunks);
   const int cols = B * p.tiles;
   const int cols_pad = cdiv(cols, cl) * cl;
   p.items = cols_pad * p.zchunks;
@@ -745,6 +790,7 @@ int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_
   p.box_rows = (cdiv(p.slab_rows, 2) + 7) / 8 * 8;
   p.base_off_mode = desc_mode;
   p.bias = bias; p.act_slope = act_slope; p.out = out;
+  if (tail) { p.tail_w = tail->tail_w; p.ptap = tail->ptap; p.ss_partial = tail->ss_partial; p.out = nullptr; }
   CUtensorMap maps[5];
   VXB_TRY(make_map(&maps[0], x0.hi, rows, 64, 64, p.box_rows, CV_KC));
   VXB_TRY(make_map(&maps[1], x0.lo, rows, 64, 64, p.box_rows, CV_KC));
@@ -754,13 +800,23 @@ int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_
   VXB_TRY(make_map(&maps[4], wc, (long long)p.ncb * 27 * 128, CV_KC, CV_KC, 128 / cl, CV_KC));
   const size_t smem = (size_t)CV_SLABS * 4 * p.box_rows * 64 + (size_t)CV_WSTAGES * CV_WBYTES + 1024;
   ++g_umma_launches;
+  int rc;
   switch (cl) {
-    case 1: return conv3_launch<1>(maps, p, smem, st);
-    case 4: return conv3_launch<4>(maps, p, smem, st);
-    default: return conv3_launch<2>(maps, p, smem, st);
+    case 1: rc = conv3_launch<1>(maps, p, smem, st); break;
+    case 4: rc = conv3_launch<4>(maps, p, smem, st); break;
+    default: rc = conv3_launch<2>(maps, p, smem, st); break;
   }
+  VXB_TRY(rc);
+  if (tail) {
+    const size_t total = (size_t)B * V * V * V;
+    trans_gather_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(tail->ptap, tail->tail_b, tail->q_trans, B, V);
+    VXB_LAUNCH_CHECK();
+    const int chunks = p.zchunks * p.tiles * 16;
+    ss_merge_kernel<<<dim3(cdiv(64, 32), B), 256, 0, st>>>(tail->ss_partial, chunks, 64, tail->ss, tail->ss_stride, tail->mx, tail->mx_stride);
+    VXB_LAUNCH_CHECK();
+  }
+  return VXB_OK;
 }
-
 
 // ------------------------------------------------------------------------------------------ patchify (patchify_umma.cuh)
 size_t patchify_weight_elems(int k) { return (size_t)k * k * k * 2 * 64 * 64; }
