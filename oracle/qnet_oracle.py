@@ -119,6 +119,11 @@ def qnet_forward(sd, cfg, ins, proprio, lang_token_embs):
                       sd['proprio_preprocess.linear.bias']), act)               # :371
     p = p[:, :, None, None, None].expand(-1, -1, d, h, w)
     x = torch.cat([x, p], dim=1)                                                # :373
+    if cfg.get('two_robots', False):
+        # PerceiverVoxelLang2RobotsEncoder.forward, perceiver_lang_io.py:723-729: the SAME proprio block on the left arm
+        p2 = _act(F.linear(cfg['proprio_left'], sd['proprio_preprocess.linear.weight'],
+                           sd['proprio_preprocess.linear.bias']), act)
+        x = torch.cat([x, p2[:, :, None, None, None].expand(-1, -1, d, h, w)], dim=1)
     if cfg.get('no_language', False):
         lang_token_embs = torch.zeros_like(lang_token_embs)                     # :376-378
     x = x.permute(0, 2, 3, 4, 1)                                                # :389
@@ -159,6 +164,14 @@ def qnet_forward(sd, cfg, ins, proprio, lang_token_embs):
     rgc = F.linear(h1, sd['rot_grip_collision_ff.linear.weight'], sd['rot_grip_collision_ff.linear.bias'])
     ncol = cfg.get('num_collision_classes', 2)
     out = {'trans': trans, 'rot_grip': rgc[:, :-ncol], 'collision': rgc[:, -ncol:], 'feats': flat}
+    if cfg.get('two_robots', False):                                                     # :842-858
+        out['trans_left'] = conv3d_block(u, sd['trans_decoder_left_arm.conv3d.weight'],
+                                         sd['trans_decoder_left_arm.conv3d.bias'], 1, None)
+        g0 = _act(F.linear(flat, sd['dense0_left_arm.linear.weight'], sd['dense0_left_arm.linear.bias']), act)
+        g1 = _act(F.linear(g0, sd['dense1_left_arm.linear.weight'], sd['dense1_left_arm.linear.bias']), act)
+        rgc2 = F.linear(g1, sd['rot_grip_collision_ff_left_arm.linear.weight'],
+                        sd['rot_grip_collision_ff_left_arm.linear.bias'])
+        out['rot_grip_left'], out['collision_left'] = rgc2[:, :-ncol], rgc2[:, -ncol:]
     if cfg.get('arm_pred_loss', False):                                                  # :479-483
         h2 = _act(F.linear(flat, sd['dense2.linear.weight'], sd['dense2.linear.bias']), act)
         out['arm'] = F.linear(h2, sd['arm_ff.linear.weight'], sd['arm_ff.linear.bias'])

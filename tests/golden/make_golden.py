@@ -28,6 +28,10 @@ QNET_CASES = {
     'qnet_v32_config1': dict(V=32, k=5, s=4, L=2048, depth=6, B=1, cameras=1, H=128, W=128, low_dim=4, arm=False, crop=False, seed=1235),
     'qnet_v100_b1': dict(V=100, k=5, s=5, L=2048, depth=6, B=1, cameras=4, H=128, W=128, low_dim=4, arm=False, crop=False, seed=1236),
 }
+# 2-robot encoder (PerceiverVoxelLang2RobotsEncoder, C = 192, two head sets)
+QNET2_CASES = {
+    'qnet2_v20': dict(V=20, k=5, s=5, L=64, depth=2, B=2, cameras=2, H=32, W=32, low_dim=4, arm=False, crop=False, seed=31),
+}
 VOXEL_CASES = {
     'voxel_v20': dict(V=20, B=2, cameras=2, H=32, W=32, crop=False, seed=21),
     'voxel_v32_crop': dict(V=32, B=3, cameras=1, H=48, W=40, crop=True, seed=22),
@@ -60,7 +64,37 @@ def encoder_kwargs(c):
                 no_perceiver=False, no_language=False, final_dim=64, arm_pred_loss=c['arm'])
 
 
+def proprio_left(c):
+    return torch.rand(c['B'], c['low_dim'], generator=torch.Generator().manual_seed(c['seed'] + 7))
+
+
+def main_two_robots():
+    RefVG, _ = refimport.load()
+    RefEnc2 = refimport.load2()
+    for name, c in QNET2_CASES.items():
+        obs = synth.make_observation(c['seed'], c['B'], c['cameras'], c['H'], c['W'], low_dim=c['low_dim'])
+        coords, feats = synth.flatten_cameras(obs)
+        vg = RefVG(synth.SCENE_BOUNDS, c['V'], 'cpu', c['B'], 3, coords.shape[1])
+        grid = vg.coords_to_bounding_voxel_grid(coords, feats, obs['bounds']).permute(0, 4, 1, 2, 3)
+        kw = encoder_kwargs(c)
+        kw.pop('arm_pred_loss')
+        net = RefEnc2(**kw).eval()
+        sd = synth.random_state_dict(net, c['seed'] + 1000)
+        missing = net.load_state_dict(sd, strict=False)
+        assert not missing.unexpected_keys, missing
+        with torch.no_grad():
+            outs = net(grid, obs['proprio'], proprio_left(c), obs['lang_goal_emb'], obs['lang_token_embs'], None,
+                       obs['bounds'], None)
+        out = dict(keys=np.array(sorted(net.state_dict().keys())),
+                   trans=outs[0].numpy(), rot_grip=outs[1].numpy(), collision=outs[2].numpy(),
+                   trans_left=outs[3].numpy(), rot_grip_left=outs[4].numpy(), collision_left=outs[5].numpy())
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+        print(name, 'rot_grip_left absmax', float(np.abs(out['rot_grip_left']).max()))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'two_robots':
+        return main_two_robots()
     RefVG, RefEnc = refimport.load()
     torch.set_num_threads(os.cpu_count())
     for name, c in VOXEL_CASES.items():

@@ -24,3 +24,10 @@ def load():
     from voxel.voxel_grid import VoxelGrid
     from agents.peract_bc.perceiver_lang_io import PerceiverVoxelLangEncoder
     return VoxelGrid, PerceiverVoxelLangEncoder
+
+
+def load2():
+    """PerceiverVoxelLang2RobotsEncoder from the unmodified reference tree."""
+    load()
+    from agents.peract_bc.perceiver_lang_io import PerceiverVoxelLang2RobotsEncoder
+    return PerceiverVoxelLang2RobotsEncoder

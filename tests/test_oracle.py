@@ -55,6 +55,20 @@ def test_qnet_oracle_matches_golden(name):
     assert np.array_equal(out['trans'].reshape(c['B'], -1).argmax(-1).numpy(), g['trans_argmax'])
 
 
+def test_two_robot_oracle_matches_golden_and_keys():
+    """PerceiverVoxelLang2RobotsEncoder: oracle vs the reference-generated fixture; checkpoint keys identical."""
+    name = 'qnet2_v20'
+    c = make_golden.QNET2_CASES[name]
+    g = util.golden(name)
+    obs, enc, sd = util.make_case_two_robots(c)
+    assert sorted(enc.state_dict().keys()) == list(g['keys'])
+    cfg = dict(util.oracle_cfg(c), two_robots=True, proprio_left=obs['proprio_left'])
+    out = qnet_oracle.qfunction_forward(sd, cfg, voxel_oracle.voxelize, obs['rgb'], obs['pcd'], obs['proprio'],
+                                        obs['lang_token_embs'], obs['bounds'], c['V'])
+    for k in ('trans', 'rot_grip', 'collision', 'trans_left', 'rot_grip_left', 'collision_left'):
+        assert util.rel_err(out[k], g[k]) < 1e-5, k
+
+
 def test_state_dict_keys_match_reference():
     """Checkpoint compatibility: our module exposes exactly the reference's state_dict keys."""
     for name in ('qnet_v20', 'qnet_v20_arm_crop'):

@@ -87,6 +87,31 @@ def test_forward_batch_invariance_full_size(cuda_lib, mode):
     assert util.rel_err(coll[2:3], c1o) < 1e-4
 
 
+@pytest.mark.parametrize('mode', MODES)
+def test_two_robots_forward_matches_golden(cuda_lib, mode):
+    """PerceiverVoxelLang2RobotsEncoder + QFunction2Robots (reference perceiver_lang_io.py:488-860,
+    agent :882-963): both arms' Q-values against the reference-generated fixture and the oracle."""
+    from voxactb_b200 import QFunction2Robots
+    name = 'qnet2_v20'
+    c = make_golden.QNET2_CASES[name]
+    g = util.golden(name)
+    obs, enc, sd = util.make_case_two_robots(c)
+    enc.math_mode = mode
+    dev = torch.device('cuda')
+    vg = VoxelGrid(synth.SCENE_BOUNDS, c['V'], dev, c['B'], 3, c['cameras'] * c['H'] * c['W'])
+    q = QFunction2Robots(enc, vg, 0.15, 5, dev, False).to(dev).eval()
+    rgb = [t.cuda() for t in obs['rgb']]
+    pcd = [t.cuda() for t in obs['pcd']]
+    out = q([[r, p] for r, p in zip(rgb, pcd)], obs['proprio'].cuda(), obs['proprio_left'].cuda(), pcd,
+            obs['lang_goal_emb'].cuda(), obs['lang_token_embs'].cuda(), obs['bounds'].cuda(), None, None)
+    torch.cuda.synchronize()
+    tr, rgr, cr, grid, tl, rgl, cl = out
+    assert grid.shape == (c['B'], 10, c['V'], c['V'], c['V'])
+    for ours, key in ((tr, 'trans'), (rgr, 'rot_grip'), (cr, 'collision'), (tl, 'trans_left'),
+                      (rgl, 'rot_grip_left'), (cl, 'collision_left')):
+        assert util.rel_err(ours, g[key]) < util.Q_REL_TOL, key
+
+
 def test_checkpoint_roundtrip_and_deepcopy(cuda_lib, tmp_path):
     import copy
     c = make_golden.QNET_CASES['qnet_v20']

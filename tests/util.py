@@ -46,3 +46,19 @@ def make_case(c):
     assert not missing.unexpected_keys
     assert all(k.endswith(('pos_x', 'pos_y', 'pos_z')) for k in missing.missing_keys)
     return obs, enc, sd
+
+
+def make_case_two_robots(c):
+    """Inputs + seeded state dict for a QNET2_CASES entry (2-robot encoder)."""
+    from voxactb_b200 import synth, PerceiverVoxelLang2RobotsEncoder
+    import make_golden
+    obs = synth.make_observation(c['seed'], c['B'], c['cameras'], c['H'], c['W'], low_dim=c['low_dim'])
+    obs['proprio_left'] = make_golden.proprio_left(c)
+    kw = make_golden.encoder_kwargs(c)
+    kw.pop('arm_pred_loss')
+    enc = PerceiverVoxelLang2RobotsEncoder(**kw).eval()
+    sd = synth.random_state_dict(enc, c['seed'] + 1000)
+    missing = enc.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
+    assert all(k.endswith(('pos_x', 'pos_y', 'pos_z')) for k in missing.missing_keys)
+    return obs, enc, sd

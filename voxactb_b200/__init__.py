@@ -7,11 +7,12 @@ Public surface mirrors the reference's classes for this path:
 All arithmetic runs in libvoxactb.so (hand-written CUDA behind the C ABI of include/voxactb.h).
 """
 from ._lib import MATH_BF16X3, MATH_FP32_SIMT, LIB_PATH, lib  # noqa: F401
-from .perceiver_lang_io import PerceiverVoxelLangEncoder  # noqa: F401
-from .qfunction import QFunction  # noqa: F401
+from .perceiver_lang_io import PerceiverVoxelLangEncoder, PerceiverVoxelLang2RobotsEncoder  # noqa: F401
+from .qfunction import QFunction, QFunction2Robots  # noqa: F401
 from .voxel_grid import VoxelGrid  # noqa: F401
 
-__all__ = ['VoxelGrid', 'PerceiverVoxelLangEncoder', 'QFunction', 'lib', 'install_shims']
+__all__ = ['VoxelGrid', 'PerceiverVoxelLangEncoder', 'PerceiverVoxelLang2RobotsEncoder', 'QFunction',
+           'QFunction2Robots', 'lib', 'install_shims']
 
 
 def install_shims():

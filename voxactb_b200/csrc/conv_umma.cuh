@@ -49,6 +49,8 @@ struct ConvParams {
   // convolution output itself is never written):
   const float* tail_w;  // [27][64] tap-major weights of the 64 -> 1 convolution, or null
   float* ptap;          // [B][27][V^3]: ptap[b][t][v] = <tail_w[t], u[b, v, :]>
+  const float* tail_w2; // optional second tap set (2 robots: trans_decoder_left_arm) and its products
+  float* ptap2;
   float* ss_partial;    // [B][chunks][6][64], chunks = zchunks * tiles * 16 (one per item x warp x row group)
 };
 
@@ -117,7 +119,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(16) uint8_t epi_smem[4 * EPI_BYTES_PER_WARP];
   __shared__ __align__(8) uint64_t bars[2 * CV_SLABS + 2 * CV_WSTAGES + 8];
-  __shared__ __align__(16) float tail_sw[27 * 64 + 64];       // tail weights + conv bias (tail mode only)
+  __shared__ __align__(16) float tail_sw[2 * 27 * 64 + 64];   // tail weights (2 sets) + conv bias (tail mode only)
   __shared__ uint32_t tmem_base_smem;
 
   const int plane_bytes = 2 * p.box_rows * 64;                 // one plane (hi or lo) of a slab
@@ -149,8 +151,11 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (p.tail_w) {
-    for (int i = threadIdx.x; i < 27 * 64; i += CV_THREADS) tail_sw[i] = p.tail_w[i];
-    for (int i = threadIdx.x; i < 64; i += CV_THREADS) tail_sw[27 * 64 + i] = p.bias[i];
+    for (int i = threadIdx.x; i < 27 * 64; i += CV_THREADS) {
+      tail_sw[i] = p.tail_w[i];
+      tail_sw[27 * 64 + i] = p.tail_w2 ? p.tail_w2[i] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 64; i += CV_THREADS) tail_sw[2 * 27 * 64 + i] = p.bias[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -339,9 +344,9 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
           mbar_wait(&acc_full[slot], (full_ph >> slot) & 1u);
           full_ph ^= 1u << slot;
           tc_fence_after();
-          float pt[27];
+          float pt[27], pt2[27];
 #pragma unroll
-          for (int tp = 0; tp < 27; ++tp) pt[tp] = 0.f;
+          for (int tp = 0; tp < 27; ++tp) { pt[tp] = 0.f; pt2[tp] = 0.f; }
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             const int c0 = cc * 32;
@@ -351,7 +356,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
             float u[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 bv = *reinterpret_cast<const float4*>(tail_sw + 27 * 64 + c0 + j);
+              const float4 bv = *reinterpret_cast<const float4*>(tail_sw + 2 * 27 * 64 + c0 + j);
               u[j] = __uint_as_float(v0[j]) + __uint_as_float(v1[j]) + bv.x;
               u[j + 1] = __uint_as_float(v0[j + 1]) + __uint_as_float(v1[j + 1]) + bv.y;
               u[j + 2] = __uint_as_float(v0[j + 2]) + __uint_as_float(v1[j + 2]) + bv.z;
@@ -374,6 +379,22 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
                 a1 = fmaf(u[4 * j + 6], wb.z, a1); a1 = fmaf(u[4 * j + 7], wb.w, a1);
               }
               pt[tp] += a0 + a1;
+            }
+            if (p.tail_w2) {
+#pragma unroll
+              for (int tp = 0; tp < 27; ++tp) {
+                const float4* w4 = reinterpret_cast<const float4*>(tail_sw + (27 + tp) * 64 + c0);
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                  const float4 wa = w4[j], wb = w4[j + 1];
+                  a0 = fmaf(u[4 * j], wa.x, a0); a0 = fmaf(u[4 * j + 1], wa.y, a0);
+                  a0 = fmaf(u[4 * j + 2], wa.z, a0); a0 = fmaf(u[4 * j + 3], wa.w, a0);
+                  a1 = fmaf(u[4 * j + 4], wb.x, a1); a1 = fmaf(u[4 * j + 5], wb.y, a1);
+                  a1 = fmaf(u[4 * j + 6], wb.z, a1); a1 = fmaf(u[4 * j + 7], wb.w, a1);
+                }
+                pt2[tp] += a0 + a1;
+              }
             }
             __syncwarp();
             // column domain: soft-argmax / max partials of ss_final (lane owns columns c0 + tc .. +3)
@@ -398,6 +419,11 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
             float* dst = p.ptap + (size_t)b * 27 * V3 + (size_t)zo * V * V + yx;
 #pragma unroll
             for (int tp = 0; tp < 27; ++tp) dst[(size_t)tp * V3] = pt[tp];
+            if (p.tail_w2) {
+              float* dst2 = p.ptap2 + (size_t)b * 27 * V3 + (size_t)zo * V * V + yx;
+#pragma unroll
+              for (int tp = 0; tp < 27; ++tp) dst2[(size_t)tp * V3] = pt2[tp];
+            }
           }
         }
         if (real) {

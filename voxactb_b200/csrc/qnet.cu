@@ -64,8 +64,8 @@ static int make_dims(const vxb_qnet_desc* d, Dims& m) {
     set_error("qnet: unsupported latent/head dimensions");
     return VXB_E_UNSUPPORTED_SHAPE;
   }
-  if (d->two_robots) {
-    set_error("qnet: PerceiverVoxelLang2RobotsEncoder is not built yet");
+  if (d->two_robots && d->arm_pred_loss) {
+    set_error("qnet: the 2-robot encoder has no arm-prediction head");
     return VXB_E_UNSUPPORTED_SHAPE;
   }
   if (d->math_mode != VXB_MATH_FP32_SIMT && d->math_mode != VXB_MATH_BF16X3) {
@@ -82,6 +82,7 @@ struct Prepared {
   float* up1_fold;   // [s^3][64][27][64]
   float* final_wt;   // [64][27][128]
   float* trans_wt;   // [27][64]
+  float* trans_wt2;  // [27][64] trans_decoder_left_arm (2 robots)
   __nv_bfloat16* final_wc;  // [4][27][{hi,lo}][64][32] weights of the input-stationary conv kernel
   __nv_bfloat16* patch_wc;  // [k^3][{hi,lo}][64][64] weights of the patchify kernel
   float* q_cross;    // [L][ch*cdh]  = to_q(LN(latents)), batch independent
@@ -105,6 +106,7 @@ static void carve_prepared(const Dims& m, Arena& a, Prepared& p, const void* con
   p.up1_fold = a.get<float>((size_t)m.s * m.s * m.s * 64 * 27 * 64);
   p.final_wt = a.get<float>((size_t)64 * 27 * 128);
   p.trans_wt = a.get<float>((size_t)27 * 64);
+  p.trans_wt2 = a.get<float>((size_t)27 * 64);
   p.final_wc = a.get<__nv_bfloat16>(umma::conv3_weight_elems(128));
   p.patch_wc = a.get<__nv_bfloat16>(umma::patchify_weight_elems(m.k));
   p.q_cross = a.get<float>((size_t)m.L * m.ch * m.cdh);
@@ -149,6 +151,7 @@ struct Work {
   float *d0, *u0, *u;            // [B,V^3,64]
   float *patch;                  // [B,T,64]
   float *pfeat;                  // [B,64]
+  float *pfeat2;                 // [B,64] left-arm proprio features (2 robots)
   float *lang_lin;               // [B,nl,C]
   float *ins;                    // [B,n,C]
   float *ctx_n;                  // [B,n,C]   LayerNorm'd tokens (cross attn context / decoder queries)
@@ -189,6 +192,7 @@ static void carve_work(const Dims& m, int B, Arena& a, Work& w) {
   w.u = a.get<float>((size_t)B * m.V3 * 64);
   w.patch = a.get<float>((size_t)B * m.T * 64);
   w.pfeat = a.get<float>((size_t)B * 64);
+  w.pfeat2 = a.get<float>((size_t)B * 64);
   w.lang_lin = a.get<float>((size_t)B * m.nl * m.C);
   w.ins = a.get<float>((size_t)B * m.n * m.C);
   w.ctx_n = a.get<float>((size_t)B * m.n * m.C);
@@ -562,6 +566,7 @@ extern "C" int vxb_qnet_prepare(const vxb_qnet_desc* d, const void* const* param
   VXB_TRY(conv_weight_prepare(P(VXB_P_UP0_W), p.up0_wt, 64, m.C, k3, st));
   VXB_TRY(conv_weight_prepare(P(VXB_P_FINAL_W), p.final_wt, 64, 128, 27, st));
   VXB_TRY(conv_weight_prepare(P(VXB_P_TRANS_W), p.trans_wt, 1, 64, 27, st));
+  if (d->two_robots) VXB_TRY(conv_weight_prepare(P(VXB_P_TRANS2_W), p.trans_wt2, 1, 64, 27, st));
   VXB_TRY(umma::conv3_prepare_weights(p.final_wt, 128, p.final_wc, st));
   VXB_TRY(umma::patchify_prepare_weights(p.patch_wt, m.k, p.patch_wc, st));
   {
@@ -585,8 +590,9 @@ extern "C" int vxb_qnet_prepare(const vxb_qnet_desc* d, const void* const* param
 
 static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* const* params,
                              const Prepared& pw, Work& w, const float* grid, const float* proprio,
-                             const float* lang_tokens, int B, float* q_trans, float* rot_grip,
-                             float* collision, float* arm_out, cudaStream_t st) {
+                             const float* proprio2, const float* lang_tokens, int B, float* q_trans, float* q_trans2,
+                             float* rot_grip, float* collision, float* rot_grip2, float* collision2, float* arm_out,
+                             cudaStream_t st) {
   Ctx cx(d->math_mode, st, d->math_mode == VXB_MATH_BF16X3 ? w.scratch : nullptr, w.scratch_bytes);
   cx.wp = pw.planes;
   auto P = [&](int slot) { return (const float*)params[slot]; };
@@ -633,8 +639,15 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
         VXB_TRY(lin(cx, lang_tokens, d->lang_emb_dim, P(VXB_P_LANG_W), d->lang_emb_dim, P(VXB_P_LANG_B),
                    nullptr, 1, 0, w.lang_lin, m.C, B * m.nl, m.C, d->lang_emb_dim, 1.f, -1.f, mm));
   }
+  if (d->two_robots) {
+    // the reference applies the SAME proprio_preprocess to both arms (perceiver_lang_io.py:723-729)
+    const float* pw2 = P(VXB_P_PROPRIO2_W) ? P(VXB_P_PROPRIO2_W) : P(VXB_P_PROPRIO_W);
+    const float* pb2 = P(VXB_P_PROPRIO2_B) ? P(VXB_P_PROPRIO2_B) : P(VXB_P_PROPRIO_B);
+    VXB_TRY(lin(cx, proprio2, m.low, pw2, m.low, pb2, nullptr, 1, 0, w.pfeat2, 64, B, 64, m.low, 1.f, slope,
+                VXB_MATH_FP32_SIMT));
+  }
   COUNT_LAUNCH();
-  assemble_tokens_kernel<<<148 * 8, 256, 0, st>>>(w.lang_lin, w.patch, w.pfeat, nullptr,
+  assemble_tokens_kernel<<<148 * 8, 256, 0, st>>>(w.lang_lin, w.patch, w.pfeat, d->two_robots ? w.pfeat2 : nullptr,
                                                   P(VXB_P_POS_ENCODING), w.ins, B, m.nl, m.T, m.C, 64);
   VXB_LAUNCH_CHECK();
 
@@ -734,6 +747,10 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
     tail.ptap = w.u;                       // the u buffer is free: [B][27][V^3] fits in [B][V^3][64]
     tail.ss_partial = w.tail_part;
     tail.q_trans = q_trans;
+    if (d->two_robots) {
+      tail.tail_w2 = pw.trans_wt2; tail.tail_b2 = P(VXB_P_TRANS2_B); tail.q_trans2 = q_trans2;
+      tail.ptap2 = w.u + (size_t)B * 27 * m.V3;
+    }
     tail.ss = w.feats + off; tail.ss_stride = m.flat; tail.mx = w.feats + off + 192; tail.mx_stride = m.flat;
     g_launches += 2;
     VXB_TRY(umma::conv3_planes(d0p, &u0p, 64, 64, pw.final_wc, P(VXB_P_FINAL_B), slope, nullptr, B, m.V, st, &tail));
@@ -746,6 +763,10 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
     // (12) trans decoder: conv3 64 -> 1, no activation                            :465
     COUNT_LAUNCH();
     VXB_TRY(trans_stencil_run<64>(w.u, pw.trans_wt, P(VXB_P_TRANS_B), q_trans, B, m.V, st));
+    if (d->two_robots) {
+      COUNT_LAUNCH();
+      VXB_TRY(trans_stencil_run<64>(w.u, pw.trans_wt2, P(VXB_P_TRANS2_B), q_trans2, B, m.V, st));
+    }
     STAGE_MARK();  // 10: ss_final + heads
     // (13) feats[256+4C :] = [ss_final(u), maxpool(u)], MLP heads                 :470-483
     VXB_TRY(spatial_softmax(w.u, B, m.V, m.V, m.V, 64, w.feats + off, m.flat, w.feats + off + 192, m.flat,
@@ -762,6 +783,19 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
                              (size_t)(nout - m.Cc) * 4, B, cudaMemcpyDeviceToDevice, st));
   VXB_CUDA(cudaMemcpy2DAsync(collision, (size_t)m.Cc * 4, w.rgc + (nout - m.Cc), (size_t)nout * 4,
                              (size_t)m.Cc * 4, B, cudaMemcpyDeviceToDevice, st));
+  if (d->two_robots) {
+    // left-arm head set on the SAME features (ss_final_left_arm(u) == ss_final(u); perceiver_lang_io.py:846-858)
+    VXB_TRY(lin(cx, w.feats, m.flat, P(VXB_P_DENSE2_W), m.flat, P(VXB_P_DENSE2_B), nullptr, 1, 0, w.h0, 256, B,
+                256, m.flat, 1.f, slope, VXB_MATH_FP32_SIMT));
+    VXB_TRY(lin(cx, w.h0, 256, P(VXB_P_DENSE1L_W), 256, P(VXB_P_DENSE1L_B), nullptr, 1, 0, w.h1, 64, B, 64, 256,
+                1.f, slope, VXB_MATH_FP32_SIMT));
+    VXB_TRY(lin(cx, w.h1, 64, P(VXB_P_ARM_W), 64, P(VXB_P_ARM_B), nullptr, 1, 0, w.rgc, nout, B, nout, 64, 1.f,
+                -1.f, VXB_MATH_FP32_SIMT));
+    VXB_CUDA(cudaMemcpy2DAsync(rot_grip2, (size_t)(nout - m.Cc) * 4, w.rgc, (size_t)nout * 4,
+                               (size_t)(nout - m.Cc) * 4, B, cudaMemcpyDeviceToDevice, st));
+    VXB_CUDA(cudaMemcpy2DAsync(collision2, (size_t)m.Cc * 4, w.rgc + (nout - m.Cc), (size_t)nout * 4,
+                               (size_t)m.Cc * 4, B, cudaMemcpyDeviceToDevice, st));
+  }
   if (d->arm_pred_loss && arm_out) {
         VXB_TRY(lin(cx, w.feats, m.flat, P(VXB_P_DENSE2_W), m.flat, P(VXB_P_DENSE2_B), nullptr, 1, 0, w.h2, 64, B,
                    64, m.flat, 1.f, slope, VXB_MATH_FP32_SIMT));
@@ -785,7 +819,8 @@ extern "C" int vxb_qnet_forward_f32(const vxb_qnet_desc* d, const void* const* p
                 "qnet_forward: null pointer argument");
   VXB_CHECK_ARG(d->no_language || lang_tokens, "qnet_forward: lang_tokens is null");
   VXB_CHECK_ARG(!d->arm_pred_loss || arm_out, "qnet_forward: arm_pred_loss set but arm_out is null");
-  (void)proprio2; (void)q_trans2; (void)rot_grip2; (void)collision2;
+  VXB_CHECK_ARG(!d->two_robots || (proprio2 && q_trans2 && rot_grip2 && collision2),
+                "qnet_forward: two_robots needs proprio2, q_trans2, rot_grip2 and collision2");
   Arena pa((void*)prepared, (size_t)-1);
   Prepared pw;
   carve_prepared(m, pa, pw, params);
@@ -798,8 +833,8 @@ extern "C" int vxb_qnet_forward_f32(const vxb_qnet_desc* d, const void* const* p
   }
   g_launches = 0;
   g_prof.begin_call();
-  int rc = qnet_forward_impl(d, m, params, pw, w, grid, proprio, lang_tokens, B, q_trans, rot_grip,
-                             collision, arm_out, (cudaStream_t)stream);
+  int rc = qnet_forward_impl(d, m, params, pw, w, grid, proprio, proprio2, lang_tokens, B, q_trans, q_trans2, rot_grip,
+                             collision, rot_grip2, collision2, arm_out, (cudaStream_t)stream);
   g_last_launches = g_launches;
   return rc;
 }

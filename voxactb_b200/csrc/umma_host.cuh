@@ -138,11 +138,16 @@ int conv3_prepare_weights(const float* w_tapmajor, int Cin, __nv_bfloat16* wc, c
 // x0 / x1: hi-lo planes of the replicate-padded grids [B, V+2, V+2, V+2, 64]; out fp32 [B, V^3, 64]
 // Fused tail of the final convolution (trans_decoder taps + ss_final / max-pool): u = act(conv) is never stored.
 struct ConvTail {
-  const float* tail_w;   // [27][64] tap-major weights of the 64 -> 1 convolution
-  const float* tail_b;   // [1]
-  float* ptap;           // scratch [B][27][V^3] fp32
-  float* ss_partial;     // scratch, conv3_tail_partial_floats(B, V) floats
+  const float* tail_w = nullptr;   // [27][64] tap-major weights of the 64 -> 1 convolution
+  const float* tail_b = nullptr;   // [1]
+  float* ptap = nullptr;           // scratch [B][27][V^3] fp32
+  float* ss_partial = nullptr;     // scratch, conv3_tail_partial_floats(B, V) floats
   float* q_trans;        // out [B, V^3]
+  // optional second 64 -> 1 head on the same u (2 robots: trans_decoder_left_arm)
+  const float* tail_w2 = nullptr;
+  const float* tail_b2 = nullptr;
+  float* ptap2 = nullptr;
+  float* q_trans2 = nullptr;
   float* ss;             // out: soft-argmax [B, ss_stride] (3 per channel) and max [B, mx_stride]
   int ss_stride;
   float* mx;

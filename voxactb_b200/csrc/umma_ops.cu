@@ -790,7 +790,10 @@ int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_
   p.box_rows = (cdiv(p.slab_rows, 2) + 7) / 8 * 8;
   p.base_off_mode = desc_mode;
   p.bias = bias; p.act_slope = act_slope; p.out = out;
-  if (tail) { p.tail_w = tail->tail_w; p.ptap = tail->ptap; p.ss_partial = tail->ss_partial; p.out = nullptr; }
+  if (tail) {
+    p.tail_w = tail->tail_w; p.ptap = tail->ptap; p.ss_partial = tail->ss_partial; p.out = nullptr;
+    p.tail_w2 = tail->tail_w2; p.ptap2 = tail->ptap2;
+  }
   CUtensorMap maps[5];
   VXB_TRY(make_map(&maps[0], x0.hi, rows, 64, 64, p.box_rows, CV_KC));
   VXB_TRY(make_map(&maps[1], x0.lo, rows, 64, 64, p.box_rows, CV_KC));
@@ -811,6 +814,10 @@ int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_
     const size_t total = (size_t)B * V * V * V;
     trans_gather_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(tail->ptap, tail->tail_b, tail->q_trans, B, V);
     VXB_LAUNCH_CHECK();
+    if (tail->tail_w2) {
+      trans_gather_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(tail->ptap2, tail->tail_b2, tail->q_trans2, B, V);
+      VXB_LAUNCH_CHECK();
+    }
     const int chunks = p.zchunks * p.tiles * 16;
     ss_merge_kernel<<<dim3(cdiv(64, 32), B), 256, 0, st>>>(tail->ss_partial, chunks, 64, tail->ss, tail->ss_stride, tail->mx, tail->mx_stride);
     VXB_LAUNCH_CHECK();

@@ -48,6 +48,14 @@ _FIXED_SLOTS = [
     'arm_ff.linear.weight', 'arm_ff.linear.bias',
     None, None,
 ]
+# 2-robot encoder: the slots that change meaning (include/voxactb.h, enum vxb_param_slot)
+_TWO_ROBOT_SLOTS = {
+    10: 'proprio_preprocess.linear.weight', 11: 'proprio_preprocess.linear.bias',   # same block for both arms
+    42: 'trans_decoder_left_arm.conv3d.weight', 43: 'trans_decoder_left_arm.conv3d.bias',
+    50: 'dense0_left_arm.linear.weight', 51: 'dense0_left_arm.linear.bias',
+    52: 'rot_grip_collision_ff_left_arm.linear.weight', 53: 'rot_grip_collision_ff_left_arm.linear.bias',
+    54: 'dense1_left_arm.linear.weight', 55: 'dense1_left_arm.linear.bias',
+}
 _LAYER_SLOTS = ['0.norm.weight', '0.norm.bias', '0.fn.to_q.weight', '0.fn.to_kv.weight',
                 '0.fn.to_out.weight', '0.fn.to_out.bias', '1.norm.weight', '1.norm.bias',
                 '1.fn.net.0.weight', '1.fn.net.0.bias', '1.fn.net.2.weight', '1.fn.net.2.bias']
@@ -108,6 +116,7 @@ class PerceiverVoxelLangEncoder(nn.Module):
     """Drop-in for reference perceiver_lang_io.py:136 (same keywords and defaults)."""
 
     math_mode = _lib.MATH_FP32_SIMT
+    TWO_ROBOTS = False     # PerceiverVoxelLang2RobotsEncoder: two proprio streams (C = 3 * im_channels), two head sets
 
     def __init__(self, depth, iterations, voxel_size, initial_dim, low_dim_size, layer=0,
                  num_rotation_classes=72, num_grip_classes=2, num_collision_classes=2, input_axis=3,
@@ -171,7 +180,9 @@ class PerceiverVoxelLangEncoder(nn.Module):
                 'not built: ' + ', '.join(unsupported))
 
         spatial = voxel_size // voxel_patch_stride
-        self.input_dim_before_seq = C = im_channels * 2
+        self.input_dim_before_seq = C = im_channels * (3 if self.TWO_ROBOTS else 2)
+        if self.TWO_ROBOTS and arm_pred_loss:
+            raise NotImplementedError('the 2-robot encoder has no arm-prediction head')
         k, D, L = voxel_patch_size, latent_dim, num_latents
         act = activation
         reg = lambda name, t: _register(self, name, t)
@@ -237,6 +248,18 @@ class PerceiverVoxelLangEncoder(nn.Module):
         reg('dense1.linear.bias', torch.zeros(final_dim))
         reg('rot_grip_collision_ff.linear.weight', _init_weight((nout, final_dim), final_dim, nout, None))
         reg('rot_grip_collision_ff.linear.bias', torch.zeros(nout))
+        if self.TWO_ROBOTS:
+            # left-arm head set (reference perceiver_lang_io.py:679-692)
+            reg('trans_decoder_left_arm.conv3d.weight', _init_weight((1, final_dim, 3, 3, 3), final_dim * 27, 27, None))
+            reg('trans_decoder_left_arm.conv3d.bias', torch.zeros(1))
+            for ax, t in zip('xyz', _spatial_positions(voxel_size)):
+                _register(self, 'ss_final_left_arm.pos_%s' % ax, t, buffer=True)
+            reg('dense0_left_arm.linear.weight', _init_weight((256, flat), flat, 256, act))
+            reg('dense0_left_arm.linear.bias', torch.zeros(256))
+            reg('dense1_left_arm.linear.weight', _init_weight((final_dim, 256), 256, final_dim, act))
+            reg('dense1_left_arm.linear.bias', torch.zeros(final_dim))
+            reg('rot_grip_collision_ff_left_arm.linear.weight', _init_weight((nout, final_dim), final_dim, nout, None))
+            reg('rot_grip_collision_ff_left_arm.linear.bias', torch.zeros(nout))
         if arm_pred_loss:
             reg('dense2.linear.weight', _init_weight((final_dim, flat), flat, final_dim, act))
             reg('dense2.linear.bias', torch.zeros(final_dim))
@@ -281,7 +304,7 @@ class PerceiverVoxelLangEncoder(nn.Module):
         d.initial_dim = self.init_dim
         d.im_channels = self.im_channels
         d.low_dim_size = self.low_dim_size
-        d.two_robots = 0
+        d.two_robots = int(self.TWO_ROBOTS)
         d.lang_seq_len = 77
         d.lang_emb_dim = 512
         d.num_latents = self.num_latents
@@ -302,7 +325,10 @@ class PerceiverVoxelLangEncoder(nn.Module):
 
     def _param_table(self):
         named = dict(self.named_parameters())
-        slots = [named.get(n) if n else None for n in _FIXED_SLOTS]
+        names = list(_FIXED_SLOTS)
+        if self.TWO_ROBOTS:
+            names = [_TWO_ROBOT_SLOTS.get(i, n) for i, n in enumerate(names)]
+        slots = [named.get(n) if n else None for n in names]
         for i in range(self.depth):
             slots += [named['layers.%d.%s' % (i, s)] for s in _LAYER_SLOTS]
         arr = (ctypes.c_void_p * len(slots))()
@@ -337,6 +363,13 @@ class PerceiverVoxelLangEncoder(nn.Module):
         """ins [B,10,V,V,V] (normally the permuted channels-last voxel grid QFunction.forward passes,
         qattention_peract_bc_agent.py:100); returns (trans [B,1,V,V,V], rot_and_grip [B,3R+G],
         collision [B,Cc][, arm [B,2]]) like perceiver_lang_io.py:465-485."""
+        out = self._run(ins, proprio, None, lang_token_embs, mask)
+        trans, rot_grip, coll, arm = out[0], out[1], out[2], out[6]
+        if self.arm_pred_loss:
+            return trans, rot_grip, coll, arm
+        return trans, rot_grip, coll
+
+    def _run(self, ins, proprio, proprio2, lang_token_embs, mask):
         if mask is not None:
             raise NotImplementedError('attention mask is never passed by the agent (always None)')
         if self.training and (self.input_dropout > 0 or self.attn_dropout > 0 or self.decoder_dropout > 0):
@@ -353,6 +386,10 @@ class PerceiverVoxelLangEncoder(nn.Module):
             lang = _lib.f32(lang_token_embs)
             if proprio.shape != (B, self.low_dim_size):
                 raise ValueError('proprio must be [%d,%d], got %s' % (B, self.low_dim_size, tuple(proprio.shape)))
+            if self.TWO_ROBOTS:
+                proprio2 = _lib.f32(proprio2)
+                if proprio2.shape != (B, self.low_dim_size):
+                    raise ValueError('proprio_left must be [%d,%d], got %s' % (B, self.low_dim_size, tuple(proprio2.shape)))
             if lang.shape != (B, 77, 512):
                 raise ValueError('lang_token_embs must be [%d,77,512], got %s' % (B, tuple(lang.shape)))
             L = _lib.lib()
@@ -367,17 +404,47 @@ class PerceiverVoxelLangEncoder(nn.Module):
                 self._workspace = None
                 self._workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             nrg = self.num_rotation_classes * 3 + self.num_grip_classes
-            trans = torch.empty(B, 1, V, V, V, dtype=torch.float32, device=dev)
-            rot_grip = torch.empty(B, nrg, dtype=torch.float32, device=dev)
-            coll = torch.empty(B, self.num_collision_classes, dtype=torch.float32, device=dev)
-            arm = torch.empty(B, 2, dtype=torch.float32, device=dev) if self.arm_pred_loss else None
+            new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+            trans, rot_grip, coll = new(B, 1, V, V, V), new(B, nrg), new(B, self.num_collision_classes)
+            trans2 = rot_grip2 = coll2 = None
+            if self.TWO_ROBOTS:
+                trans2, rot_grip2, coll2 = new(B, 1, V, V, V), new(B, nrg), new(B, self.num_collision_classes)
+            arm = new(B, 2) if self.arm_pred_loss else None
             rc = L.vxb_qnet_forward_f32(ctypes.byref(desc), arr, _lib.ptr(self._prepared), _lib.ptr(grid),
-                                        _lib.ptr(proprio), None, _lib.ptr(lang), B, _lib.ptr(trans), None,
-                                        _lib.ptr(rot_grip), _lib.ptr(coll), None, None, _lib.ptr(arm),
-                                        _lib.ptr(self._workspace), ws_bytes, _lib.stream())
+                                        _lib.ptr(proprio), _lib.ptr(proprio2) if self.TWO_ROBOTS else None,
+                                        _lib.ptr(lang), B, _lib.ptr(trans), _lib.ptr(trans2),
+                                        _lib.ptr(rot_grip), _lib.ptr(coll), _lib.ptr(rot_grip2), _lib.ptr(coll2),
+                                        _lib.ptr(arm), _lib.ptr(self._workspace), ws_bytes, _lib.stream())
             _lib.check(rc, 'vxb_qnet_forward_f32')
             self.last_launch_count = L.vxb_last_launch_count()
             del keep
-        if self.arm_pred_loss:
-            return trans, rot_grip, coll, arm
-        return trans, rot_grip, coll
+        return trans, rot_grip, coll, trans2, rot_grip2, coll2, arm
+
+
+class PerceiverVoxelLang2RobotsEncoder(PerceiverVoxelLangEncoder):
+    """Drop-in for reference perceiver_lang_io.py:488-860: one shared trunk with two proprio streams
+    (C = 192) and a second (left-arm) set of translation / rotation-grip-collision heads."""
+
+    TWO_ROBOTS = True
+
+    def __init__(self, depth, iterations, voxel_size, initial_dim, low_dim_size, layer=0,
+                 num_rotation_classes=72, num_grip_classes=2, num_collision_classes=2, input_axis=3,
+                 num_latents=512, im_channels=64, latent_dim=512, cross_heads=1, latent_heads=8,
+                 cross_dim_head=64, latent_dim_head=64, activation='relu', weight_tie_layers=False,
+                 pos_encoding_with_lang=True, input_dropout=0.1, attn_dropout=0.1,
+                 decoder_dropout=0.0, lang_fusion_type='seq', voxel_patch_size=9,
+                 voxel_patch_stride=8, no_skip_connection=False, no_perceiver=False,
+                 no_language=False, final_dim=64):
+        super().__init__(depth, iterations, voxel_size, initial_dim, low_dim_size, layer,
+                         num_rotation_classes, num_grip_classes, num_collision_classes, input_axis,
+                         num_latents, im_channels, latent_dim, cross_heads, latent_heads,
+                         cross_dim_head, latent_dim_head, activation, weight_tie_layers,
+                         pos_encoding_with_lang, input_dropout, attn_dropout, decoder_dropout,
+                         lang_fusion_type, voxel_patch_size, voxel_patch_stride, no_skip_connection,
+                         no_perceiver, no_language, final_dim, arm_pred_loss=False)
+
+    def forward(self, ins, proprio_right, proprio_left, lang_goal_emb, lang_token_embs,
+                prev_layer_voxel_grid, bounds, prev_layer_bounds, mask=None):
+        """Returns (trans_right, rot_and_grip_right, collision_right, trans_left, rot_and_grip_left,
+        collision_left), reference perceiver_lang_io.py:860."""
+        return self._run(ins, proprio_right, proprio_left, lang_token_embs, mask)[:6]

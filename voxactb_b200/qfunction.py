@@ -89,3 +89,32 @@ class QFunction(nn.Module):
             return q_trans, q_rot_and_grip, q_ignore_collisions, voxel_grid
         q_trans, q_rot_and_grip, q_ignore_collisions = out
         return q_trans, q_rot_and_grip, q_ignore_collisions, voxel_grid
+
+
+class QFunction2Robots(QFunction):
+    """Drop-in for reference qattention_peract_bc_agent.py:882-963 (the 2-robot / "one policy, more heads"
+    variant): same voxelisation, one ``PerceiverVoxelLang2RobotsEncoder`` pass, two head sets."""
+
+    def __init__(self, perceiver_encoder: nn.Module, voxelizer: VoxelGrid, bounds_offset: float,
+                 rotation_resolution: float, device, training):
+        super().__init__(perceiver_encoder, voxelizer, bounds_offset, rotation_resolution, device, training, False)
+
+    def forward(self, rgb_pcd, proprio_right, proprio_left, pcd, lang_goal_emb, lang_token_embs, bounds=None,
+                prev_bounds=None, prev_layer_voxel_grid=None):
+        b = rgb_pcd[0][0].shape[0]
+        pcd_flat = torch.cat([p.permute(0, 2, 3, 1).reshape(b, -1, 3) for p in pcd], 1)
+        rgb = [rp[0] for rp in rgb_pcd]
+        feat_size = rgb[0].shape[1]
+        flat_imag_features = torch.cat(
+            [p.permute(0, 2, 3, 1).reshape(b, -1, feat_size) for p in rgb], 1)
+        voxel_grid = self._voxelizer.coords_to_bounding_voxel_grid(
+            pcd_flat, coord_features=flat_imag_features, coord_bounds=bounds)
+        voxel_grid = voxel_grid.permute(0, 4, 1, 2, 3).detach()
+        if bounds.shape[0] != b:
+            bounds = bounds.repeat(b, 1)
+        (q_trans_right, q_rot_and_grip_right, q_ignore_collisions_right,
+         q_trans_left, q_rot_and_grip_left, q_ignore_collisions_left) = self._qnet(
+            voxel_grid, proprio_right, proprio_left, lang_goal_emb, lang_token_embs, prev_layer_voxel_grid,
+            bounds, prev_bounds)
+        return (q_trans_right, q_rot_and_grip_right, q_ignore_collisions_right, voxel_grid,
+                q_trans_left, q_rot_and_grip_left, q_ignore_collisions_left)
