@@ -227,6 +227,28 @@ int vxb_attention_f32(const float* q, int ldq, long long q_batch_stride, const f
                       long long o_batch_stride, int B, int H, int Nq, int Nk, int dh, float scale,
                       int math_mode, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- training tail building blocks (the Q-network backward is not built yet) ----
+ * Per-sample cross entropy of logits [B, N] (row pitch ld) against label indices, replacing
+ * nn.CrossEntropyLoss(reduction='none') on one-hot labels (reference qattention_peract_bc_agent.py:217,
+ * 391-392, 517-578): loss[b] = logsumexp(logits[b]) - logits[b, labels[b]];
+ * grad (optional, row pitch ldg) = grad_scale * (softmax(logits[b]) - onehot(labels[b])). */
+size_t vxb_ce_loss_workspace_bytes(int B, int N);
+int vxb_ce_loss_f32(const float* logits, long long ld, const int32_t* labels, int B, int N, float grad_scale,
+                    float* loss, float* grad, long long ldg, void* ws, size_t ws_bytes, void* stream);
+
+/* Fused multi-tensor optimizer steps.  params/grads/exp_avg/exp_avg_sq/sizes are HOST arrays of n_tensors
+ * device pointers / element counts; state tensors are updated in place.
+ * LAMB: reference peract/helpers/optim/lamb.py:60-122 (no bias correction, weight decay added to the
+ *       step, trust ratio clamp(|w|,0,10)/|step|, 1 when either norm is 0).
+ * Adam: torch.optim.Adam with L2 weight decay as the agent builds it (agent:263-268); step counts from 1. */
+size_t vxb_optimizer_workspace_bytes(int n_tensors, const long long* sizes /* host */);
+int vxb_lamb_step_f32(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                      float* const* exp_avg_sq, const long long* sizes, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, void* ws, size_t ws_bytes, void* stream);
+int vxb_adam_step_f32(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                      float* const* exp_avg_sq, const long long* sizes, int step, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,17 @@ SIGNATURES = {
     'vxb_attention_f32': (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_int, c_ll, c_void_p,
                                   c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
                                   c_void_p, c_size_t, c_void_p]),
+    'vxb_ce_loss_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'vxb_ce_loss_f32': (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_ll,
+                                c_void_p, c_size_t, c_void_p]),
+    'vxb_optimizer_workspace_bytes': (c_size_t, [c_int, ctypes.POINTER(c_ll)]),
+    'vxb_lamb_step_f32': (c_int, [c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                                  ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_ll),
+                                  c_float, c_float, c_float, c_float, c_float, c_void_p, c_size_t, c_void_p]),
+    'vxb_adam_step_f32': (c_int, [c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                                  ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_ll),
+                                  c_int, c_float, c_float, c_float, c_float, c_float, c_void_p, c_size_t,
+                                  c_void_p]),
 }
 
 _lib = None

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libvoxactb.so')
-SOURCES = ['voxelize.cu', 'qnet.cu', 'api_ops.cu', 'umma_ops.cu']
+SOURCES = ['voxelize.cu', 'qnet.cu', 'api_ops.cu', 'umma_ops.cu', 'train_ops.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 
