@@ -281,22 +281,22 @@ def run_ours(args):
     line = {
         'metric': 'policy fwd passes/sec at 100^3 voxels', 'value': value, 'unit': 'passes/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if math_mode == _lib.MATH_FP32_SIMT else 'bf16x3(split-bf16, fp32 accumulate)',
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if math_mode == _lib.MATH_FP32_SIMT else 'f16x3 (split-fp16 hi/lo planes, 3 tcgen05 kind::f16 MMAs per product, fp32 accumulate in TMEM)',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD.format(b=B), 'global_batch': world * B, 'parallelism': 'batch-sharded x%d, no collective' % world,
-                   'math_mode': 'fp32_simt' if math_mode == _lib.MATH_FP32_SIMT else 'bf16x3_tcgen05',
+                   'math_mode': 'fp32_simt' if math_mode == _lib.MATH_FP32_SIMT else 'split16x3_tcgen05',
                    'l2': 'no explicit flush: each step streams >10 GB of activations, far above the 126 MB L2'},
         'e2e': {'value': e2e_value, 'unit': 'passes/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': (launches_per_step) * args.steps,
         'clocks': clk,
-        'roofline': {'kernel': 'conv3_umma_kernel: final conv 3x3x3, 128->64 @100^3 (input-stationary tcgen05, split-bf16 x3)'
+        'roofline': {'kernel': 'conv3_umma_kernel: final conv 3x3x3, 128->64 @100^3 (input-stationary tcgen05, split-fp16 x3)'
                                if math_mode != _lib.MATH_FP32_SIMT else 'final conv 3x3x3, 128->64 @100^3 (fp32 FFMA implicit GEMM)',
                      'bound': 'tensor',
                      'achieved': achieved_tf, 'peak': pk['tensor'], 'unit': 'TFLOP/s', 'frac': achieved_tf / pk['tensor'],
                      'traffic': ncu_traffic(B) if math_mode != _lib.MATH_FP32_SIMT else None,
                      'algorithmic_flops_per_launch': FINAL_CONV_FLOPS * B,
-                     'note': 'achieved = direct-convolution FLOPs (442.4 GF/sample) / CUDA-event time; the kernel executes 3 bf16 MMAs per '
+                     'note': 'achieved = direct-convolution FLOPs (442.4 GF/sample) / CUDA-event time; the kernel executes 3 f16 MMAs per '
                              'logical product (fp32-class accuracy), so its own ceiling is 1/3 of this bf16 peak',
                      'peak_source': pk['source'] + ' bf16 sustained', 'ms_per_launch': final_ms,
                      'whole_forward_tflops': FLOPS_PER_PASS * B / (per_step * 1e-3) / 1e12,

@@ -39,11 +39,11 @@ __device__ __forceinline__ void split_store_row(uint8_t* hi_row, uint8_t* lo_row
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const float4 a = v[2 * c], b = v[2 * c + 1];
-    const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
-    const __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
-    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1), f2 = __bfloat1622float2(h2), f3 = __bfloat1622float2(h3);
-    const __nv_bfloat162 l0 = __floats2bfloat162_rn(a.x - f0.x, a.y - f0.y), l1 = __floats2bfloat162_rn(a.z - f1.x, a.w - f1.y);
-    const __nv_bfloat162 l2 = __floats2bfloat162_rn(b.x - f2.x, b.y - f2.y), l3 = __floats2bfloat162_rn(b.z - f3.x, b.w - f3.y);
+    const __nv_bfloat162 h0 = pl2_from_floats(a.x, a.y), h1 = pl2_from_floats(a.z, a.w);
+    const __nv_bfloat162 h2 = pl2_from_floats(b.x, b.y), h3 = pl2_from_floats(b.z, b.w);
+    const float2 f0 = pl2_to_float2(h0), f1 = pl2_to_float2(h1), f2 = pl2_to_float2(h2), f3 = pl2_to_float2(h3);
+    const __nv_bfloat162 l0 = pl2_from_floats(a.x - f0.x, a.y - f0.y), l1 = pl2_from_floats(a.z - f1.x, a.w - f1.y);
+    const __nv_bfloat162 l2 = pl2_from_floats(b.x - f2.x, b.y - f2.y), l3 = pl2_from_floats(b.z - f3.x, b.w - f3.y);
     uint4 hv, lv;
     hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
     hv.z = *reinterpret_cast<const uint32_t*>(&h2); hv.w = *reinterpret_cast<const uint32_t*>(&h3);

@@ -1,7 +1,7 @@
 // HBM-bound streaming kernels of the Q-network: spatial soft-argmax + global max pooling in one pass,
 // and the 3x3x3 conv to ONE channel (trans_decoder).  Every kernel reads its 256 MB/sample input once.
 #pragma once
-#include <cuda_bf16.h>
+#include "planes16.cuh"
 #include "common.cuh"
 
 namespace vxb {
@@ -193,10 +193,21 @@ input_preprocess_ss_kernel(const float* __restrict__ x /*[B,P,CIN]*/, const floa
     int d = p / (Hh * Ww), h = (p / Ww) % Hh, wv = p % Ww;
     const float* xb = x + (size_t)b * P * CIN;
     float4* yb = reinterpret_cast<float4*>(y + (size_t)b * P * C) + g;
+    // software pipeline: the next position's inputs are in flight while this one is computed
+    static_assert(CIN % 2 == 0, "input rows are read as float2");
+    float2 nxt[CIN / 2];
+    if (p < p_end) {
+#pragma unroll
+      for (int i = 0; i < CIN / 2; ++i) nxt[i] = __ldg(reinterpret_cast<const float2*>(xb + (size_t)p * CIN) + i);
+    }
     for (; p < p_end; p += PL) {
       float in[CIN];
 #pragma unroll
-      for (int i = 0; i < CIN; ++i) in[i] = __ldg(xb + (size_t)p * CIN + i);
+      for (int i = 0; i < CIN / 2; ++i) { in[2 * i] = nxt[i].x; in[2 * i + 1] = nxt[i].y; }
+      if (p + PL < p_end) {
+#pragma unroll
+        for (int i = 0; i < CIN / 2; ++i) nxt[i] = __ldg(reinterpret_cast<const float2*>(xb + (size_t)(p + PL) * CIN) + i);
+      }
       float o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -209,10 +220,10 @@ input_preprocess_ss_kernel(const float* __restrict__ x /*[B,P,CIN]*/, const floa
       if (phi) {
         // hi/lo planes of the replicate-padded grid [B, D+2, H+2, W+2, C] (interior; the halo is filled afterwards)
         const size_t prow = (((size_t)b * (Dd + 2) + d + 1) * (Hh + 2) + h + 1) * (Ww + 2) + wv + 1;
-        const __nv_bfloat162 h01 = __floats2bfloat162_rn(o[0], o[1]), h23 = __floats2bfloat162_rn(o[2], o[3]);
-        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-        const __nv_bfloat162 l01 = __floats2bfloat162_rn(o[0] - f01.x, o[1] - f01.y);
-        const __nv_bfloat162 l23 = __floats2bfloat162_rn(o[2] - f23.x, o[3] - f23.y);
+        const __nv_bfloat162 h01 = pl2_from_floats(o[0], o[1]), h23 = pl2_from_floats(o[2], o[3]);
+        const float2 f01 = pl2_to_float2(h01), f23 = pl2_to_float2(h23);
+        const __nv_bfloat162 l01 = pl2_from_floats(o[0] - f01.x, o[1] - f01.y);
+        const __nv_bfloat162 l23 = pl2_from_floats(o[2] - f23.x, o[3] - f23.y);
         uint2 hv, lv;
         hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
         lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);

@@ -121,7 +121,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
 }
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = NT
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  return (1u << 4) | VXB_IDESC_AB_FORMAT | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 // epilogue staging per warp: a 32 x 32 fp32 transpose tile (row pitch 36 floats: conflict-free 128-bit
@@ -357,7 +357,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
                   float t[4];
 #pragma unroll
                   for (int u = 0; u < 4; ++u) {
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t[u]) : "f"(fmaf(__uint_as_float(v[j + u]), e.alpha, -row_sub)));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t[u]) : "f"(fmaf(__uint_as_float(v[j + u]), e.alpha, VXB_P_EXP_BIAS - row_sub)));
                     row_acc += t[u];
                   }
                   *reinterpret_cast<float4*>(stage + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) = make_float4(t[0], t[1], t[2], t[3]);
@@ -368,7 +368,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
                   float t[4];
 #pragma unroll
                   for (int u = 0; u < 4; ++u) {
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t[u]) : "f"(fmaf(__uint_as_float(v[j + u]), e.alpha, -row_sub)));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t[u]) : "f"(fmaf(__uint_as_float(v[j + u]), e.alpha, VXB_P_EXP_BIAS - row_sub)));
                     t[u] = (n + j + u < e.N) ? t[u] : 0.f;
                     row_acc += t[u];
                   }
@@ -454,10 +454,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
                 for (int i = 0; i < 8; ++i) {
                   if (mw + i * 4 + tr < e.M) {
                     const float4 x = x4[i];
-                    const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
-                    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-                    const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - f01.x, x.y - f01.y);
-                    const __nv_bfloat162 l23 = __floats2bfloat162_rn(x.z - f23.x, x.w - f23.y);
+                    const __nv_bfloat162 h01 = pl2_from_floats(x.x, x.y), h23 = pl2_from_floats(x.z, x.w);
+                    const float2 f01 = pl2_to_float2(h01), f23 = pl2_to_float2(h23);
+                    const __nv_bfloat162 l01 = pl2_from_floats(x.x - f01.x, x.y - f01.y);
+                    const __nv_bfloat162 l23 = pl2_from_floats(x.z - f23.x, x.w - f23.y);
                     __nv_bfloat16* dh = e.out_hi + poff + (long long)(i * 4) * e.ldp;
                     __nv_bfloat16* dl = e.out_lo + poff + (long long)(i * 4) * e.ldp;
                     if (wide) {
@@ -549,7 +549,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float t;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(__uint_as_float(v[j]), e.alpha, -row_sub)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(__uint_as_float(v[j]), e.alpha, VXB_P_EXP_BIAS - row_sub)));
             t = (n + j < e.N) ? t : 0.f;
             row_acc += t;
             f[j] = t;
@@ -567,9 +567,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
                 float t = f[j];
                 if (e.bias) t += __ldg(e.bias + n + j);
                 if (e.act_slope >= 0.f) t = t > 0.f ? t : t * e.act_slope;
-                const __nv_bfloat16 hi = __float2bfloat16_rn(t);
+                const __nv_bfloat16 hi = pl_from_float(t);
                 out_hi[(long long)(n + j) * e.ldp + orow] = hi;
-                out_lo[(long long)(n + j) * e.ldp + orow] = __float2bfloat16_rn(t - __bfloat162float(hi));
+                out_lo[(long long)(n + j) * e.ldp + orow] = pl_from_float(t - pl_to_float(hi));
               }
             }
           }
@@ -652,10 +652,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
             if (out_hi && ok) {
               __nv_bfloat16* dh = out_hi + orow_r[i] * e.ldp + ncol;
               __nv_bfloat16* dl = out_lo + orow_r[i] * e.ldp + ncol;
-              const __nv_bfloat162 h01 = __floats2bfloat162_rn(x[0], x[1]), h23 = __floats2bfloat162_rn(x[2], x[3]);
-              const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-              const __nv_bfloat162 l01 = __floats2bfloat162_rn(x[0] - f01.x, x[1] - f01.y);
-              const __nv_bfloat162 l23 = __floats2bfloat162_rn(x[2] - f23.x, x[3] - f23.y);
+              const __nv_bfloat162 h01 = pl2_from_floats(x[0], x[1]), h23 = pl2_from_floats(x[2], x[3]);
+              const float2 f01 = pl2_to_float2(h01), f23 = pl2_to_float2(h23);
+              const __nv_bfloat162 l01 = pl2_from_floats(x[0] - f01.x, x[1] - f01.y);
+              const __nv_bfloat162 l23 = pl2_from_floats(x[2] - f23.x, x[3] - f23.y);
               // EXP mode: values beyond N are exact zeros and the row is padded to ld (a multiple of 8)
               if ((nv >= 4 || e.mode == EPI_EXP) && ((reinterpret_cast<uintptr_t>(dh) & 7) == 0)) {
                 uint2 hv, lv;

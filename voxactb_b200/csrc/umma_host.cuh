@@ -1,6 +1,6 @@
 // Host-visible types of the tcgen05 split-bf16 engine (kernel in umma_gemm.cuh, host code in umma_ops.cu).
 #pragma once
-#include <cuda_bf16.h>
+#include "planes16.cuh"
 #include "common.cuh"
 
 namespace vxb {

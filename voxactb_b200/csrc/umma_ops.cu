@@ -62,8 +62,8 @@ __device__ __forceinline__ void split8(const float* f, uint4& hi, uint4& lo) {
   __align__(16) __nv_bfloat16 h[8], l[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
-    h[t] = __float2bfloat16_rn(f[t]);
-    l[t] = __float2bfloat16_rn(f[t] - __bfloat162float(h[t]));
+    h[t] = pl_from_float(f[t]);
+    l[t] = pl_from_float(f[t] - pl_to_float(h[t]));
   }
   hi = *reinterpret_cast<const uint4*>(h);
   lo = *reinterpret_cast<const uint4*>(l);
@@ -122,11 +122,42 @@ pad_split_kernel(const float* __restrict__ x, int B, int V, int pad, int C,
   }
 }
 
-// replicate-fill the halo of padded bf16 planes in place: every halo voxel copies its nearest interior voxel
+// replicate-fill the halo of padded bf16 planes in place: every halo voxel copies its nearest interior voxel.
+// Only the halo voxels are enumerated (two full z planes + the border ring of every other plane), pad = 1 fast path.
 static __global__ void __launch_bounds__(256)
 halo_fill_kernel(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int B, int V, int pad, int C) {
   const int Vp = V + 2 * pad;
   const int cg = C / 8;
+  if (pad == 1) {
+    const long long plane = (long long)Vp * Vp, ring = 4ll * Vp - 4;
+    const long long per_b = 2 * plane + (long long)(Vp - 2) * ring;
+    const long long total = (long long)B * per_b * cg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const int c = (int)(i % cg) * 8;
+      long long v = i / cg;
+      const int b = (int)(v / per_b);
+      v -= (long long)b * per_b;
+      int pd, ph, pw;
+      if (v < 2 * plane) {
+        pd = v < plane ? 0 : Vp - 1;
+        const long long r = v % plane;
+        ph = (int)(r / Vp); pw = (int)(r % Vp);
+      } else {
+        const long long j = v - 2 * plane;
+        pd = 1 + (int)(j / ring);
+        const int r = (int)(j % ring);
+        if (r < Vp) { ph = 0; pw = r; }
+        else if (r < 2 * Vp) { ph = Vp - 1; pw = r - Vp; }
+        else { const int rr = r - 2 * Vp; ph = 1 + rr / 2; pw = (rr & 1) ? Vp - 1 : 0; }
+      }
+      const int sd = min(max(pd, 1), V), sh = min(max(ph, 1), V), sw = min(max(pw, 1), V);
+      const long long so = ((((long long)b * Vp + sd) * Vp + sh) * Vp + sw) * C + c;
+      const long long o = ((((long long)b * Vp + pd) * Vp + ph) * Vp + pw) * C + c;
+      *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(hi + so);
+      *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(lo + so);
+    }
+    return;
+  }
   const long long total = (long long)B * Vp * Vp * Vp * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % cg) * 8;
@@ -171,7 +202,8 @@ int pad_split(const float* x, int B, int V, int pad, int C, Planes out, cudaStre
 
 int halo_fill(Planes p, int B, int V, int pad, int C, cudaStream_t st) {
   const int Vp = V + 2 * pad;
-  const long long total = (long long)B * Vp * Vp * Vp * (C / 8);
+  long long total = (long long)B * Vp * Vp * Vp * (C / 8);
+  if (pad == 1) total = (long long)B * (2ll * Vp * Vp + (long long)(Vp - 2) * (4ll * Vp - 4)) * (C / 8);
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
   halo_fill_kernel<<<blocks, 256, 0, st>>>(p.hi, p.lo, B, V, pad, C);
   VXB_LAUNCH_CHECK();
@@ -576,8 +608,8 @@ static __global__ void split_gather_kernel(const float* __restrict__ x, int ld, 
     const int r = (int)((i / cols) % rows);
     const int b = (int)(i / ((long long)cols * rows));
     const float f = x[b * bs + (long long)r * ld + c];
-    const __nv_bfloat16 h = __float2bfloat16_rn(f);
-    const __nv_bfloat16 l = __float2bfloat16_rn(f - __bfloat162float(h));
+    const __nv_bfloat16 h = pl_from_float(f);
+    const __nv_bfloat16 l = pl_from_float(f - pl_to_float(h));
     const long long o = transposed ? ((long long)b * cols + c) * ldp + r : ((long long)b * rows + r) * ldp + c;
     hi[o] = h; lo[o] = l;
   }
@@ -591,7 +623,7 @@ static __global__ void merge_planes_kernel(const __nv_bfloat16* __restrict__ hi,
     const int r = (int)((i / cols) % rows);
     const int b = (int)(i / ((long long)cols * rows));
     const long long o = ((long long)b * rows + r) * ldp + c;
-    out[b * obs + (long long)r * ldo + c] = __bfloat162float(hi[o]) + __bfloat162float(lo[o]);
+    out[b * obs + (long long)r * ldo + c] = pl_to_float(hi[o]) + pl_to_float(lo[o]);
   }
 }
 
@@ -646,10 +678,10 @@ static __global__ void conv3_weight_kernel(const float* __restrict__ w /*[64][27
     const int tap = (int)((i / (CV_KC * 64)) % 27);
     const int cb = (int)(i / ((long long)CV_KC * 64 * 27));
     const float f = w[((long long)co * 27 + tap) * Cin + cb * CV_KC + kc];
-    const __nv_bfloat16 h = __float2bfloat16_rn(f);
+    const __nv_bfloat16 h = pl_from_float(f);
     const long long o = (((long long)(cb * 27 + tap) * 2) * 64 + co) * CV_KC + kc;
     wc[o] = h;
-    wc[o + 64 * CV_KC] = __float2bfloat16_rn(f - __bfloat162float(h));
+    wc[o + 64 * CV_KC] = pl_from_float(f - pl_to_float(h));
   }
 }
 
@@ -836,10 +868,10 @@ static __global__ void patchify_weight_kernel(const float* __restrict__ w /*[64]
     const int co = (int)((i / 64) % 64);
     const int tap = (int)(i / 4096);
     const float f = w[((long long)co * k3 + tap) * 64 + ci];
-    const __nv_bfloat16 h = __float2bfloat16_rn(f);
+    const __nv_bfloat16 h = pl_from_float(f);
     const long long o = ((long long)tap * 2 * 64 + co) * 64 + ci;
     wc[o] = h;
-    wc[o + 64 * 64] = __float2bfloat16_rn(f - __bfloat162float(h));
+    wc[o + 64 * 64] = pl_from_float(f - pl_to_float(h));
   }
 }
 
