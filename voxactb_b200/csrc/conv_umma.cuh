@@ -42,6 +42,7 @@ struct ConvParams {
   int slab_rows;        // 128 + 2 (Vp + 1)
   int box_rows;         // rows per slab TMA box (two boxes per plane)
   int base_off_mode;    // descriptor base-offset policy for row-shifted operands (see make_desc64)
+  int debug_skip;       // timing experiments only (wrong results): 1 = skip the lo*hi MMA, 2 = skip the hi*[hi;lo] MMA
   const float* bias;
   float act_slope;
   float* out;           // [B, V, V, V, 64] fp32 (null in tail mode)
@@ -250,6 +251,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
       int sb = 0, ws = 0;
       uint32_t sph = 0, wph = 0;
       uint32_t acc_ph = 0;                         // bit s: parity of the last completed acc_empty phase of slot s
+      uint32_t w_ready = 0;
       for (int g = cluster_id; g < groups; g += num_clusters) {
         int b, t, z0, lz;
         decode(g * CL + rank, b, t, z0, lz);
@@ -274,7 +276,9 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
               uint32_t accum = (dzc == 0 && cb == 0) ? 0u : 1u;
 #pragma unroll
               for (int dyc = 0; dyc < 3; ++dyc) {
-                mbar_wait(&w_full[ws], wph);
+                // the probe of this stage's barrier was issued right after the previous stage's MMAs (w_ready),
+                // so its latency overlaps their execution instead of sitting between two batches of MMAs
+                if (!w_ready) mbar_wait(&w_full[ws], wph);
                 tc_fence_after();
                 const uint32_t wlo = desc64_lo(smem_u32(w_base + ws * CV_WBYTES));
                 // row shift of tap (dy, dx): dyc * Vp + dxc rows of 64 bytes = 4 descriptor units per row
@@ -286,8 +290,8 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
                     for (int ks = 0; ks < CV_KC / 16; ++ks) {
                       const uint32_t aoff = arow + (uint32_t)(dxc * 4 + ks * 2);
                       const uint32_t boff = (uint32_t)(dxc * (CV_TAPBYTES >> 4) + ks * 2);
-                      tc_mma_bf16_w(d_tmem, a_hi_lo + aoff, wlo + boff, idesc128, (dxc | ks) ? 1u : accum);  // hi*hi | hi*lo
-                      tc_mma_bf16_w(d_tmem, a_lo_lo + aoff, wlo + boff, idesc64, 1u);                       // lo*hi
+                      if (p.debug_skip != 2) tc_mma_bf16_w(d_tmem, a_hi_lo + aoff, wlo + boff, idesc128, (dxc | ks) ? 1u : accum);  // hi*hi | hi*lo
+                      if (p.debug_skip != 1) tc_mma_bf16_w(d_tmem, a_lo_lo + aoff, wlo + boff, idesc64, 1u);                       // lo*hi
                     }
                   }
                   if (CL > 1) tc_commit_mc(&w_empty[ws], mask); else tc_commit(&w_empty[ws]);
@@ -295,6 +299,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
                 __syncwarp();
                 accum = 1u;
                 if (++ws == CV_WSTAGES) { ws = 0; wph ^= 1; }
+                w_ready = mbar_test(&w_full[ws], wph);
               }
             }
             if (leader) tc_commit(&slab_empty[sb]);

@@ -821,6 +821,11 @@ int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_
   p.slab_rows = 128 + 2 * (Vp + 1);
   p.box_rows = (cdiv(p.slab_rows, 2) + 7) / 8 * 8;
   p.base_off_mode = desc_mode;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("VXB_CONV_DEBUG_SKIP"); dbg = e ? atoi(e) : 0; }
+    p.debug_skip = dbg;
+  }
   p.bias = bias; p.act_slope = act_slope; p.out = out;
   if (tail) {
     p.tail_w = tail->tail_w; p.ptap = tail->ptap; p.ss_partial = tail->ss_partial; p.out = nullptr;
