@@ -306,9 +306,9 @@ def run_ours(args):
         'stages_ms': stages,
     }
     if world == 1 and not args.no_cpu_baseline:
-        rate, cores, spp = cpu_pass_rate(3, 1)
+        rate, cores, spp = cpu_pass_rate(8, 1)
         line['cpu_baseline'] = {'value': rate, 'unit': 'passes/s', 'cores': cores, 'kind': 'port',
-                                'sample': '3 timed single-sample passes (batch 1 of the workload) after 1 warm-up, torch CPU fp32 oracle port'}
+                                'sample': '8 timed single-sample passes (batch 1 of the workload) after 1 warm-up, torch CPU fp32 oracle port'}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -754,7 +754,8 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
     tail.ss = w.feats + off; tail.ss_stride = m.flat; tail.mx = w.feats + off + 192; tail.mx_stride = m.flat;
     g_launches += 2;
     VXB_TRY(umma::conv3_planes(d0p, &u0p, 64, 64, pw.final_wc, P(VXB_P_FINAL_B), slope, nullptr, B, m.V, st, &tail));
-    STAGE_MARK();  // 9: (fused into stage 8)
+    STAGE_MARK();  // 9: trans decoder gather + ss_final merge (their first halves ran in the conv epilogue)
+    VXB_TRY(umma::conv3_tail_finish(tail, B, m.V, st));
     STAGE_MARK();  // 10: heads
   } else {
     VXB_TRY(conv3d(w.d0, w.u0, 64, 64, pw.final_wt, P(VXB_P_FINAL_B), w.u, B, m.V, m.V, 64, 3, 1, slope, mm, st,

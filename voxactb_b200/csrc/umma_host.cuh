@@ -154,6 +154,7 @@ struct ConvTail {
   int mx_stride;
 };
 size_t conv3_tail_partial_floats(int B, int V);
+int conv3_tail_finish(const ConvTail& tail, int B, int V, cudaStream_t st);   // gather + merge after conv3_planes(tail)
 int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_bfloat16* wc, const float* bias,
                  float act_slope, float* out, int B, int V, cudaStream_t st, const ConvTail* tail = nullptr);
 

@@ -846,19 +846,24 @@ int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_
     case 4: rc = conv3_launch<4>(maps, p, smem, st); break;
     default: rc = conv3_launch<2>(maps, p, smem, st); break;
   }
-  VXB_TRY(rc);
-  if (tail) {
-    const size_t total = (size_t)B * V * V * V;
-    trans_gather_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(tail->ptap, tail->tail_b, tail->q_trans, B, V);
-    VXB_LAUNCH_CHECK();
-    if (tail->tail_w2) {
-      trans_gather_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(tail->ptap2, tail->tail_b2, tail->q_trans2, B, V);
-      VXB_LAUNCH_CHECK();
-    }
-    const int chunks = p.zchunks * p.tiles * 16;
-    ss_merge_kernel<<<dim3(cdiv(64, 32), B), 256, 0, st>>>(tail->ss_partial, chunks, 64, tail->ss, tail->ss_stride, tail->mx, tail->mx_stride);
+  return rc;
+}
+
+// second half of the fused tail: gather the 27 tap products per voxel into q_trans, merge the ss_final partials
+int conv3_tail_finish(const ConvTail& tail, int B, int V, cudaStream_t st) {
+  int tiles, lz, zchunks;
+  conv3_plan(B, V, conv3_cluster(), tiles, lz, zchunks);
+  const size_t total = (size_t)B * V * V * V;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  trans_gather_kernel<<<blocks, 256, 0, st>>>(tail.ptap, tail.tail_b, tail.q_trans, B, V);
+  VXB_LAUNCH_CHECK();
+  if (tail.tail_w2) {
+    trans_gather_kernel<<<blocks, 256, 0, st>>>(tail.ptap2, tail.tail_b2, tail.q_trans2, B, V);
     VXB_LAUNCH_CHECK();
   }
+  const int chunks = zchunks * tiles * 16;
+  ss_merge_kernel<<<dim3(cdiv(64, 32), B), 256, 0, st>>>(tail.ss_partial, chunks, 64, tail.ss, tail.ss_stride, tail.mx, tail.mx_stride);
+  VXB_LAUNCH_CHECK();
   return VXB_OK;
 }
 

@@ -115,7 +115,9 @@ def _spatial_positions(n):
 class PerceiverVoxelLangEncoder(nn.Module):
     """Drop-in for reference perceiver_lang_io.py:136 (same keywords and defaults)."""
 
-    math_mode = _lib.MATH_FP32_SIMT
+    # arithmetic of the dense contractions: the product path is the tcgen05 split-16-bit x3 mode (fp32-class
+    # accuracy, see DESIGN.md section 4); MATH_FP32_SIMT (fp32 FFMA everywhere) is the slow reference-arithmetic mode
+    math_mode = _lib.MATH_BF16X3
     TWO_ROBOTS = False     # PerceiverVoxelLang2RobotsEncoder: two proprio streams (C = 3 * im_channels), two head sets
 
     def __init__(self, depth, iterations, voxel_size, initial_dim, low_dim_size, layer=0,
