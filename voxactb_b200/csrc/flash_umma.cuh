@@ -1,0 +1,284 @@
+// Fused attention on tcgen05: softmax(scale q k^T) v per (batch, head) without materialising the probabilities.
+//
+// Pass 1 (the GEMM engine with the EPIK_ROWMAX epilogue) leaves the row maxima of the log2-domain scores;
+// this kernel is pass 2.  A CTA owns 128 queries of one (batch, head) and walks the keys in tiles of 64:
+//   S  = Q K^T           tcgen05, split-16 x3 as  S[:,0:128] = Q_hi [K_hi;K_lo]^T,  S[:,0:64] += Q_lo K_hi^T   (TMEM, 2 buffers)
+//   P  = 2^(a S - max)   softmax warps: tcgen05.ld, ex2, row sums, split into hi/lo and written straight into the
+//                        SWIZZLE_128B K-major A-operand tile of the next MMA (shared memory, 2 buffers)
+//   O += P V             tcgen05,  O[:,0:128] += P_hi [V_hi;V_lo],  O[:,0:64] += P_lo V_hi                       (TMEM)
+// and finally O (both halves added) / row sum is written as hi/lo planes for the output projection.
+// The QK^T MMAs of tile j are issued before the PV MMAs of tile j-1, so the tensor pipe works while the softmax
+// warps convert the previous tile.  Warps: 0 = TMA producer, 1 = MMA issuer, 2-5 = softmax + epilogue.
+#pragma once
+#include "umma_gemm.cuh"
+
+namespace vxb {
+namespace umma {
+
+constexpr int FA_THREADS = 192;
+constexpr int FA_KT = 64;                        // keys per tile
+constexpr int FA_KVSTAGES = 3;
+constexpr int FA_QBYTES = 2 * 128 * 128;         // Q hi + lo
+constexpr int FA_KVBYTES = 4 * FA_KT * 128;      // K hi, K lo, Vt hi, Vt lo (64 rows x 128 B each)
+constexpr int FA_PBYTES = 2 * 128 * 128;         // P hi + lo
+constexpr int FA_SMEM = FA_QBYTES + FA_KVSTAGES * FA_KVBYTES + 2 * FA_PBYTES + 1024;
+
+struct FlashParams {
+  int B, H, Nq, Nk, dh;
+  int q_batched;            // 0: one Q shared by all batches (first cross-attention iteration)
+  int q_tiles, k_tiles, items;
+  float alpha;              // scale * log2(e)
+  const float* rowmax;      // [B*H*Nq] log2-domain row maxima (stabiliser; cancels in P / sum P)
+  __nv_bfloat16* out_hi;    // O planes [B*Nq, ldo]
+  __nv_bfloat16* out_lo;
+  long long ldo;
+};
+
+__global__ void __launch_bounds__(FA_THREADS, 1)
+flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_constant__ CUtensorMap mapQl,
+                  const __grid_constant__ CUtensorMap mapKh, const __grid_constant__ CUtensorMap mapKl,
+                  const __grid_constant__ CUtensorMap mapVh, const __grid_constant__ CUtensorMap mapVl,
+                  const FlashParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bars[2 + 2 * FA_KVSTAGES + 8 + 2];
+  __shared__ uint32_t tmem_base_smem;
+  uint8_t* q_s = smem;
+  uint8_t* kv_s = smem + FA_QBYTES;
+  uint8_t* p_s = kv_s + FA_KVSTAGES * FA_KVBYTES;
+  uint64_t* q_full = bars;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;
+  uint64_t* kv_empty = kv_full + FA_KVSTAGES;
+  uint64_t* s_full = kv_empty + FA_KVSTAGES;
+  uint64_t* s_empty = s_full + 2;
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* p_empty = p_full + 2;
+  uint64_t* o_full = p_empty + 2;
+  uint64_t* o_empty = o_full + 1;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapQh); tma_prefetch_desc(&mapQl);
+    tma_prefetch_desc(&mapKh); tma_prefetch_desc(&mapKl);
+    tma_prefetch_desc(&mapVh); tma_prefetch_desc(&mapVl);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int i = 0; i < FA_KVSTAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(o_full, 1); mbar_init(o_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const int inner = p.H * p.dh;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0, n = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+        const int qt = item % p.q_tiles, bh = item / p.q_tiles;
+        const int h = bh % p.H, b = bh / p.H;
+        mbar_wait(q_empty, (n & 1) ^ 1);
+        mbar_expect_tx(q_full, FA_QBYTES);
+        const int qrow = (p.q_batched ? b * p.Nq : 0) + qt * 128;
+        tma_load_2d(&mapQh, q_full, q_s, h * p.dh, qrow);
+        tma_load_2d(&mapQl, q_full, q_s + 128 * 128, h * p.dh, qrow);
+        for (int j = 0; j < p.k_tiles; ++j) {
+          mbar_wait(&kv_empty[st], ph ^ 1);
+          uint8_t* s = kv_s + st * FA_KVBYTES;
+          mbar_expect_tx(&kv_full[st], FA_KVBYTES);
+          tma_load_2d(&mapKh, &kv_full[st], s, h * p.dh, b * p.Nk + j * FA_KT);
+          tma_load_2d(&mapKl, &kv_full[st], s + FA_KT * 128, h * p.dh, b * p.Nk + j * FA_KT);
+          tma_load_2d(&mapVh, &kv_full[st], s + 2 * FA_KT * 128, j * FA_KT, bh * p.dh);
+          tma_load_2d(&mapVl, &kv_full[st], s + 3 * FA_KT * 128, j * FA_KT, bh * p.dh);
+          if (++st == FA_KVSTAGES) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (uniform loops, one elected lane issues)
+    uint32_t leader;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.b32 %0, 1, 0, P;\n}\n" : "=r"(leader));
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    constexpr uint32_t idesc128 = make_idesc(128), idesc64 = make_idesc(64);
+    constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+    auto dlo = [](uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); };
+    const uint32_t q_hi = dlo(smem_u32(q_s)), q_lo = q_hi + ((128 * 128) >> 4);
+    int st = 0;             // kv stage of the tile whose QK^T is issued next
+    uint32_t ph = 0;
+    int st_pv = 0;          // kv stage of the tile whose PV is issued next
+    uint32_t it = 0;        // global key-tile counter (S / P double buffers)
+    uint32_t n = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+      mbar_wait(q_full, n & 1);
+      tc_fence_after();
+      for (int j = 0; j <= p.k_tiles; ++j) {
+        if (j < p.k_tiles) {
+          // ---- S(j) = Q K_j^T into S buffer (it & 1)
+          const uint32_t sb = it & 1u;
+          mbar_wait(&kv_full[st], ph);
+          mbar_wait(&s_empty[sb], ((it >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t kb = dlo(smem_u32(kv_s + st * FA_KVBYTES));
+          const uint32_t d_s = tmem_u + sb * 128u;
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              tc_mma_bf16_lo(d_s, q_hi + 2 * ks, kb + 2 * ks, kDescHi, idesc128, ks != 0);   // hi*hi | hi*lo
+              tc_mma_bf16_lo(d_s, q_lo + 2 * ks, kb + 2 * ks, kDescHi, idesc64, 1);          // lo*hi
+            }
+            tc_commit(&s_full[sb]);
+            if (j == p.k_tiles - 1) tc_commit(q_empty);        // Q tile free once the last QK^T retires
+          }
+          __syncwarp();
+          if (++st == FA_KVSTAGES) { st = 0; ph ^= 1; }
+        }
+        if (j >= 1) {
+          // ---- O += P(j-1) V_{j-1}
+          const uint32_t itp = it - 1u;                        // counter of tile j-1 (it = tiles whose QK^T has been issued, minus this one)
+          const uint32_t pb = itp & 1u;
+          if (j == 1) {
+            mbar_wait(o_empty, (n & 1) ^ 1);                   // previous item's O has been read out
+            tc_fence_after();
+          }
+          mbar_wait(&p_full[pb], (itp >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t p_hi = dlo(smem_u32(p_s + pb * FA_PBYTES)), p_lo = p_hi + ((128 * 128) >> 4);
+          const uint32_t vb = dlo(smem_u32(kv_s + st_pv * FA_KVBYTES + 2 * FA_KT * 128));
+          const uint32_t d_o = tmem_u + 256u;
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < FA_KT / 16; ++ks) {
+              tc_mma_bf16_lo(d_o, p_hi + 2 * ks, vb + 2 * ks, kDescHi, idesc128, (j > 1 || ks != 0));   // hi*hi | hi*lo
+              tc_mma_bf16_lo(d_o, p_lo + 2 * ks, vb + 2 * ks, kDescHi, idesc64, 1);                     // lo*hi
+            }
+            tc_commit(&p_empty[pb]);
+            tc_commit(&kv_empty[st_pv]);
+            if (j == p.k_tiles) tc_commit(o_full);
+          }
+          __syncwarp();
+          if (++st_pv == FA_KVSTAGES) st_pv = 0;
+        }
+        if (j < p.k_tiles) ++it;
+      }
+    }
+  } else {
+    // ===================================================== softmax + epilogue (thread = query row)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                               // row inside the 128-query tile
+    uint32_t it = 0, n = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+      const int qt = item % p.q_tiles, bh = item / p.q_tiles;
+      const int h = bh % p.H, b = bh / p.H;
+      const int qi = qt * 128 + r;
+      const bool row_ok = qi < p.Nq;
+      const float m = row_ok ? p.rowmax[(size_t)bh * p.Nq + qi] : 0.f;
+      const float bias = VXB_P_EXP_BIAS - m;
+      float row_sum = 0.f;
+      for (int j = 0; j < p.k_tiles; ++j, ++it) {
+        const uint32_t sb = it & 1u;
+        mbar_wait(&s_full[sb], (it >> 1) & 1u);
+        tc_fence_after();
+        mbar_wait(&p_empty[sb], ((it >> 1) & 1u) ^ 1u);        // PV of the tile two back has consumed this P buffer
+        uint8_t* ph_row = p_s + sb * FA_PBYTES + r * 128;
+        uint8_t* pl_row = ph_row + 128 * 128;
+        const int key0 = j * FA_KT;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v0[32], v1[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + sb * 128u + (uint32_t)(c * 32), v0);
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + sb * 128u + 64u + (uint32_t)(c * 32), v1);
+          const bool full = key0 + c * 32 + 31 < p.Nk;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {                        // 8 keys = one 16-byte chunk per plane
+            float pv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int jj = g * 8 + e;
+              const float s = __uint_as_float(v0[jj]) + __uint_as_float(v1[jj]);
+              float t;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(s, p.alpha, bias)));
+              if (!full) t = (key0 + c * 32 + jj < p.Nk) ? t : 0.f;
+              row_sum += t;
+              pv[e] = t;
+            }
+            uint4 hv, lv;
+            uint32_t* hp = reinterpret_cast<uint32_t*>(&hv);
+            uint32_t* lp = reinterpret_cast<uint32_t*>(&lv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __nv_bfloat162 hh = pl2_from_floats(pv[2 * e], pv[2 * e + 1]);
+              const float2 ff = pl2_to_float2(hh);
+              const __nv_bfloat162 ll = pl2_from_floats(pv[2 * e] - ff.x, pv[2 * e + 1] - ff.y);
+              hp[e] = *reinterpret_cast<const uint32_t*>(&hh);
+              lp[e] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            const int off = ((c * 4 + g) ^ (r & 7)) * 16;
+            *reinterpret_cast<uint4*>(ph_row + off) = hv;
+            *reinterpret_cast<uint4*>(pl_row + off) = lv;
+          }
+        }
+        tc_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&s_empty[sb]); mbar_arrive(&p_full[sb]); }
+      }
+      // ---- O / row_sum -> planes
+      mbar_wait(o_full, n & 1);
+      tc_fence_after();
+      const float inv = 1.f / row_sum;
+      __nv_bfloat16* oh = p.out_hi + ((size_t)b * p.Nq + qi) * p.ldo + (size_t)h * p.dh;
+      __nv_bfloat16* ol = p.out_lo + ((size_t)b * p.Nq + qi) * p.ldo + (size_t)h * p.dh;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v0[32], v1[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(c * 32), v0);
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 256u + 64u + (uint32_t)(c * 32), v1);
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 hv, lv;
+            uint32_t* hp = reinterpret_cast<uint32_t*>(&hv);
+            uint32_t* lp = reinterpret_cast<uint32_t*>(&lv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int jj = g * 8 + 2 * e;
+              const float a0 = (__uint_as_float(v0[jj]) + __uint_as_float(v1[jj])) * inv;
+              const float a1 = (__uint_as_float(v0[jj + 1]) + __uint_as_float(v1[jj + 1])) * inv;
+              const __nv_bfloat162 hh = pl2_from_floats(a0, a1);
+              const float2 ff = pl2_to_float2(hh);
+              const __nv_bfloat162 ll = pl2_from_floats(a0 - ff.x, a1 - ff.y);
+              hp[e] = *reinterpret_cast<const uint32_t*>(&hh);
+              lp[e] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            *reinterpret_cast<uint4*>(oh + c * 32 + g * 8) = hv;
+            *reinterpret_cast<uint4*>(ol + c * 32 + g * 8) = lv;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+}  // namespace umma
+}  // namespace vxb

@@ -3,6 +3,7 @@
 #include "umma_gemm.cuh"
 #include "conv_umma.cuh"
 #include "patchify_umma.cuh"
+#include "flash_umma.cuh"
 #include <cstdlib>
 #include "umma_host.cuh"
 #include <cudaTypedefs.h>
@@ -571,6 +572,40 @@ int attention_planes(const Planes& Q, int q_batched, const Planes& K, const Plan
   p1.terms = 1;
   p1.ep.mode = EPI_ROWMAX; p1.ep.row_stat = rowmax;
   VXB_TRY(gemm(q, nullptr, k, 256, p1, st));
+  static int use_flash = -1;
+  if (use_flash < 0) {
+    const char* e = getenv("VXB_ATTN");
+    use_flash = (e && !strcmp(e, "gemm")) ? 0 : 1;
+  }
+  if (use_flash) {
+    // (2+3) fused: P never leaves the SM (flash_umma.cuh)
+    FlashParams f;
+    memset(&f, 0, sizeof(f));
+    f.B = B; f.H = H; f.Nq = Nq; f.Nk = Nk; f.dh = dh; f.q_batched = q_batched;
+    f.q_tiles = cdiv(Nq, 128); f.k_tiles = cdiv(Nk, FA_KT); f.items = B * H * f.q_tiles;
+    f.alpha = scale * 1.4426950408889634f;
+    f.rowmax = rowmax;
+    f.out_hi = O.hi; f.out_lo = O.lo; f.ldo = O.ld;
+    CUtensorMap maps[6];
+    VXB_TRY(make_map(&maps[0], Q.hi, q.rows, q.cols, Q.ld, 128));
+    VXB_TRY(make_map(&maps[1], Q.lo, q.rows, q.cols, Q.ld, 128));
+    VXB_TRY(make_map(&maps[2], K.hi, k.rows, k.cols, K.ld, FA_KT));
+    VXB_TRY(make_map(&maps[3], K.lo, k.rows, k.cols, K.ld, FA_KT));
+    VXB_TRY(make_map(&maps[4], Vt.hi, (long long)B * H * dh, Nk, Vt.ld, 64));
+    VXB_TRY(make_map(&maps[5], Vt.lo, (long long)B * H * dh, Nk, Vt.ld, 64));
+    static bool attr_set = false;
+    if (!attr_set) {
+      VXB_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+      attr_set = true;
+    }
+    int dev = 0, sms = 148;
+    VXB_CUDA(cudaGetDevice(&dev));
+    VXB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    ++g_umma_launches;
+    flash_attn_kernel<<<std::min(f.items, sms), FA_THREADS, FA_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], f);
+    VXB_LAUNCH_CHECK();
+    return VXB_OK;
+  }
   // (2) P = 2^(s - max) as planes, row sums
   Params p2 = p;
   p2.ep.mode = EPI_EXP; p2.ep.row_sub = rowmax; p2.ep.row_stat = rowsum;
