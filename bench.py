@@ -296,6 +296,9 @@ def run_ours(args):
                      'achieved': achieved_tf, 'peak': pk['tensor'], 'unit': 'TFLOP/s', 'frac': achieved_tf / pk['tensor'],
                      'traffic': ncu_traffic(B) if math_mode != _lib.MATH_FP32_SIMT else None,
                      'algorithmic_flops_per_launch': FINAL_CONV_FLOPS * B,
+                     # what the tensor pipe actually executes: 3 f16 MMAs per product on the padded (102/100)^2 x (V+2)/V rows
+                     'executed_mma_tflops': (achieved_tf * 3 * (102 / 100) ** 2 * 1.02) if math_mode != _lib.MATH_FP32_SIMT else None,
+                     'executed_frac_of_peak': (achieved_tf * 3 * (102 / 100) ** 2 * 1.02 / pk['tensor']) if math_mode != _lib.MATH_FP32_SIMT else None,
                      'note': 'achieved = direct-convolution FLOPs (442.4 GF/sample) / CUDA-event time; the kernel executes 3 f16 MMAs per '
                              'logical product (fp32-class accuracy), so its own ceiling is 1/3 of this bf16 peak',
                      'peak_source': pk['source'] + ' bf16 sustained', 'ms_per_launch': final_ms,

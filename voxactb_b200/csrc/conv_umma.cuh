@@ -42,7 +42,7 @@ struct ConvParams {
   int slab_rows;        // 128 + 2 (Vp + 1)
   int box_rows;         // rows per slab TMA box (two boxes per plane)
   int base_off_mode;    // descriptor base-offset policy for row-shifted operands (see make_desc64)
-  int debug_skip;       // timing experiments only (wrong results): 1 = skip the lo*hi MMA, 2 = skip the hi*[hi;lo] MMA
+  int debug_skip;       // unused (was: timing experiments)
   const float* bias;
   float act_slope;
   float* out;           // [B, V, V, V, 64] fp32 (null in tail mode)
@@ -96,6 +96,23 @@ __device__ __forceinline__ uint64_t make_desc64(uint32_t saddr, int base_off_mod
   return d;
 }
 
+// ---- CTA-pair (cta_group::2) variants: one MMA spans the two CTAs of a cluster (M = 256: 128 rows from each CTA's
+// own shared memory), the N rows of the B operand are split between the two CTAs, so each SM reads only half of the
+// weights per MMA.  Loads of both CTAs signal the LEADER's (rank 0) mbarrier: clearing bit 24 of a shared-window
+// address selects the even CTA of the pair.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {   // arrives on the barrier of BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
 // low / high words of the SWIZZLE_64B K-major descriptor; the low word advances by (bytes >> 4)
 __device__ __forceinline__ uint32_t desc64_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
 constexpr uint32_t kDesc64Hi = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
@@ -111,7 +128,24 @@ __device__ __forceinline__ void tc_mma_bf16_w(uint32_t tmem_d, uint32_t a_lo, ui
       "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDesc64Hi) : "memory");
 }
 
-template <int CL>
+__device__ __forceinline__ void tc_mma_pair_w(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDesc64Hi) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_m256(int n) {
+  return (1u << 4) | VXB_IDESC_AB_FORMAT | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+constexpr int CV_PAIR_TAPBYTES = 96 * CV_KC * 2;      // per CTA and tap: 64 rows (its half of [W_hi;W_lo]) + 32 rows (its half of W_hi)
+constexpr int CV_PAIR_WBYTES = 3 * CV_PAIR_TAPBYTES;
+
+template <int CL, bool PAIR>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_constant__ CUtensorMap mapA0l,
                   const __grid_constant__ CUtensorMap mapA1h, const __grid_constant__ CUtensorMap mapA1l,
@@ -123,6 +157,8 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
   __shared__ __align__(16) float tail_sw[2 * 27 * 64 + 64];   // tail weights (2 sets) + conv bias (tail mode only)
   __shared__ uint32_t tmem_base_smem;
 
+  static_assert(!PAIR || CL == 2, "the CTA-pair variant runs on clusters of two");
+  constexpr int WBYTES = PAIR ? CV_PAIR_WBYTES : CV_WBYTES;
   const int plane_bytes = 2 * p.box_rows * 64;                 // one plane (hi or lo) of a slab
   const int slab_bytes = 2 * plane_bytes;
   uint8_t* slab_base = smem;
@@ -143,13 +179,18 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
     tma_prefetch_desc(&mapA1h); tma_prefetch_desc(&mapA1l);
     tma_prefetch_desc(&mapW);
     for (int i = 0; i < CV_SLABS; ++i) { mbar_init(&slab_full[i], 1); mbar_init(&slab_empty[i], 1); }
-    for (int i = 0; i < CV_WSTAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], CL); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < CV_WSTAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], PAIR ? 1 : CL); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if (p.tail_w) {
     for (int i = threadIdx.x; i < 27 * 64; i += CV_THREADS) {
@@ -196,11 +237,20 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
             const CUtensorMap* ml = s1 ? &mapA1l : &mapA0l;
             mbar_wait(&slab_empty[sb], sph ^ 1);
             uint8_t* s = slab_base + sb * slab_bytes;
-            mbar_expect_tx(&slab_full[sb], slab_bytes);
-            tma_load_2d(mh, &slab_full[sb], s, col, row0);
-            tma_load_2d(mh, &slab_full[sb], s + p.box_rows * 64, col, row0 + p.box_rows);
-            tma_load_2d(ml, &slab_full[sb], s + plane_bytes, col, row0);
-            tma_load_2d(ml, &slab_full[sb], s + plane_bytes + p.box_rows * 64, col, row0 + p.box_rows);
+            if constexpr (PAIR) {
+              // both CTAs' slabs complete on the leader's barrier
+              if (rank == 0) mbar_expect_tx(&slab_full[sb], 2 * slab_bytes);
+              tma_load_2d_pair(mh, &slab_full[sb], s, col, row0);
+              tma_load_2d_pair(mh, &slab_full[sb], s + p.box_rows * 64, col, row0 + p.box_rows);
+              tma_load_2d_pair(ml, &slab_full[sb], s + plane_bytes, col, row0);
+              tma_load_2d_pair(ml, &slab_full[sb], s + plane_bytes + p.box_rows * 64, col, row0 + p.box_rows);
+            } else {
+              mbar_expect_tx(&slab_full[sb], slab_bytes);
+              tma_load_2d(mh, &slab_full[sb], s, col, row0);
+              tma_load_2d(mh, &slab_full[sb], s + p.box_rows * 64, col, row0 + p.box_rows);
+              tma_load_2d(ml, &slab_full[sb], s + plane_bytes, col, row0);
+              tma_load_2d(ml, &slab_full[sb], s + plane_bytes + p.box_rows * 64, col, row0 + p.box_rows);
+            }
             if (++sb == CV_SLABS) { sb = 0; sph ^= 1; }
           }
         }
@@ -218,21 +268,39 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
         decode(g * CL + rank, b, t, z0, lz);
         for (int zi = z0 - 1; zi <= z0 + lz; ++zi) {
           for (int cb = 0; cb < p.ncb; ++cb) {
+            // a stage = the (up to) three dz taps of one in-plane tap (dy, dx): the MMA warp interleaves the three
+            // output planes (different TMEM accumulators) so that back-to-back MMAs never hit the same accumulator
+            int nvalid = 0;
             for (int dzc = 0; dzc < 3; ++dzc) {
               const int zo = zi - (dzc - 1);
-              if (zo < z0 || zo >= z0 + lz) continue;
-              for (int dyc = 0; dyc < 3; ++dyc) {
-                const int wrow = (cb * 27 + dzc * 9 + dyc * 3) * 128 + (int)rank * WROWS;
-                mbar_wait(&w_empty[ws], wph ^ 1);
-                uint8_t* s = w_base + ws * CV_WBYTES + rank * WROWS * 64;
-                mbar_expect_tx(&w_full[ws], CV_WBYTES);
-#pragma unroll
-                for (int dxc = 0; dxc < 3; ++dxc) {
-                  if (CL > 1) tma_load_2d_mc(&mapW, &w_full[ws], s + dxc * CV_TAPBYTES, 0, wrow + dxc * 128, mask);
-                  else tma_load_2d(&mapW, &w_full[ws], s + dxc * CV_TAPBYTES, 0, wrow + dxc * 128);
-                }
-                if (++ws == CV_WSTAGES) { ws = 0; wph ^= 1; }
+              nvalid += (zo >= z0 && zo < z0 + lz) ? 1 : 0;
+            }
+            for (int tap9 = 0; tap9 < 9; ++tap9) {
+              mbar_wait(&w_empty[ws], wph ^ 1);
+              uint8_t* s = w_base + ws * WBYTES;
+              if constexpr (PAIR) {
+                if (rank == 0) mbar_expect_tx(&w_full[ws], 2 * nvalid * CV_PAIR_TAPBYTES);
+              } else {
+                mbar_expect_tx(&w_full[ws], nvalid * CV_TAPBYTES);
               }
+              for (int dzc = 0; dzc < 3; ++dzc) {
+                const int zo = zi - (dzc - 1);
+                if (zo < z0 || zo >= z0 + lz) continue;
+                const int r0 = (cb * 27 + dzc * 9 + tap9) * 128;
+                if constexpr (PAIR) {
+                  // global rows of a tap: [W_hi 0..63][W_lo 64..127].  CTA r keeps its half of [W_hi;W_lo] (64 rows,
+                  // the N = 128 operand) followed by its half of W_hi (32 rows, the N = 64 operand); map box = 32 rows
+                  uint8_t* d = s + dzc * CV_PAIR_TAPBYTES;
+                  tma_load_2d_pair(&mapW, &w_full[ws], d, 0, r0 + (int)rank * 64);
+                  tma_load_2d_pair(&mapW, &w_full[ws], d + 32 * 64, 0, r0 + (int)rank * 64 + 32);
+                  tma_load_2d_pair(&mapW, &w_full[ws], d + 64 * 64, 0, r0 + (int)rank * 32);
+                } else {
+                  uint8_t* d = s + dzc * CV_TAPBYTES + rank * WROWS * 64;
+                  if (CL > 1) tma_load_2d_mc(&mapW, &w_full[ws], d, 0, r0 + (int)rank * WROWS, mask);
+                  else tma_load_2d(&mapW, &w_full[ws], d, 0, r0);
+                }
+              }
+              if (++ws == CV_WSTAGES) { ws = 0; wph ^= 1; }
             }
           }
         }
@@ -252,7 +320,9 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
       uint32_t sph = 0, wph = 0;
       uint32_t acc_ph = 0;                         // bit s: parity of the last completed acc_empty phase of slot s
       uint32_t w_ready = 0;
-      for (int g = cluster_id; g < groups; g += num_clusters) {
+      constexpr uint32_t idesc128p = make_idesc_m256(128), idesc64p = make_idesc_m256(64);
+      // CTA-pair mode: the leader issues every MMA for both CTAs; the peer's MMA warp has nothing to do
+      for (int g = cluster_id; g < ((PAIR && rank != 0) ? 0 : groups); g += num_clusters) {
         int b, t, z0, lz;
         decode(g * CL + rank, b, t, z0, lz);
         for (int zi = z0 - 1; zi <= z0 + lz; ++zi) {
@@ -261,54 +331,77 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
             tc_fence_after();
             const uint32_t a_hi_lo = desc64_lo(smem_u32(slab_base + sb * slab_bytes));
             const uint32_t a_lo_lo = desc64_lo(smem_u32(slab_base + sb * slab_bytes + plane_bytes));
+            // valid output planes of this input plane: zo = zi - (dzc - 1); accumulator slot = (zo - z0) & 3
+            uint32_t vmask = 0;
             for (int dzc = 0; dzc < 3; ++dzc) {
               const int zo = zi - (dzc - 1);
-              if (zo < z0 || zo >= z0 + lz) continue;
-              const int slot = (zo - z0) & 3;
-              // the first contribution to an output plane comes from input plane zo-1 (dzc = 0), channel block 0:
-              // the accumulator slot must have been drained by the epilogue
-              if (dzc == 0 && cb == 0) {
-                mbar_wait(&acc_empty[slot], ((acc_ph >> slot) & 1u) ^ 1u);
-                acc_ph ^= 1u << slot;
-                tc_fence_after();
-              }
-              const uint32_t d_tmem = tmem_u + (uint32_t)(slot * 128);
-              uint32_t accum = (dzc == 0 && cb == 0) ? 0u : 1u;
+              if (zo >= z0 && zo < z0 + lz) vmask |= 1u << dzc;
+            }
+            // the first contribution to an output plane comes from input plane zo-1 (dzc = 0), channel block 0:
+            // the accumulator slot must have been drained by the epilogue
+            if (cb == 0 && (vmask & 1u)) {
+              const int slot = (zi + 1 - z0) & 3;
+              mbar_wait(&acc_empty[slot], ((acc_ph >> slot) & 1u) ^ 1u);
+              acc_ph ^= 1u << slot;
+              tc_fence_after();
+            }
+            const uint32_t d0 = tmem_u + (uint32_t)(((zi + 1 - z0) & 3) * 128);   // dzc = 0 -> zo = zi + 1
+            const uint32_t d1 = tmem_u + (uint32_t)(((zi - z0) & 3) * 128);       // dzc = 1 -> zo = zi
+            const uint32_t d2 = tmem_u + (uint32_t)(((zi - 1 - z0) & 3) * 128);   // dzc = 2 -> zo = zi - 1
+            const uint32_t dt[3] = {d0, d1, d2};
+#pragma unroll 1
+            for (int tap9 = 0; tap9 < 9; ++tap9) {
+              // the probe of this stage's barrier was issued right after the previous stage's MMAs (w_ready),
+              // so its latency overlaps their execution instead of sitting between two batches of MMAs
+              if (!w_ready) mbar_wait(&w_full[ws], wph);
+              tc_fence_after();
+              const uint32_t wlo = desc64_lo(smem_u32(w_base + ws * WBYTES));
+              // row shift of tap (dy, dx): dyc * Vp + dxc rows of 64 bytes = 4 descriptor units per row
+              const uint32_t arow = (uint32_t)((tap9 / 3) * Vp + (tap9 % 3)) * 4u;
+              const uint32_t first = (cb == 0 && tap9 == 0) ? 1u : 0u;     // dzc = 0 starts its accumulator here
+              if (leader) {
 #pragma unroll
-              for (int dyc = 0; dyc < 3; ++dyc) {
-                // the probe of this stage's barrier was issued right after the previous stage's MMAs (w_ready),
-                // so its latency overlaps their execution instead of sitting between two batches of MMAs
-                if (!w_ready) mbar_wait(&w_full[ws], wph);
-                tc_fence_after();
-                const uint32_t wlo = desc64_lo(smem_u32(w_base + ws * CV_WBYTES));
-                // row shift of tap (dy, dx): dyc * Vp + dxc rows of 64 bytes = 4 descriptor units per row
-                const uint32_t arow = (uint32_t)(dyc * Vp) * 4u;
-                if (leader) {
+                for (int ks = 0; ks < CV_KC / 16; ++ks) {
+                  const uint32_t aoff = arow + (uint32_t)(ks * 2);
+                  // consecutive MMAs go to DIFFERENT accumulators (the three output planes): an MMA that accumulates
+                  // into the tile the previous one wrote waits for it (~100 clk for these small shapes)
 #pragma unroll
-                  for (int dxc = 0; dxc < 3; ++dxc) {
-#pragma unroll
-                    for (int ks = 0; ks < CV_KC / 16; ++ks) {
-                      const uint32_t aoff = arow + (uint32_t)(dxc * 4 + ks * 2);
-                      const uint32_t boff = (uint32_t)(dxc * (CV_TAPBYTES >> 4) + ks * 2);
-                      if (p.debug_skip != 2) tc_mma_bf16_w(d_tmem, a_hi_lo + aoff, wlo + boff, idesc128, (dxc | ks) ? 1u : accum);  // hi*hi | hi*lo
-                      if (p.debug_skip != 1) tc_mma_bf16_w(d_tmem, a_lo_lo + aoff, wlo + boff, idesc64, 1u);                       // lo*hi
+                  for (int dzc = 0; dzc < 3; ++dzc) {
+                    if (!(vmask & (1u << dzc))) continue;
+                    const uint32_t acc_on = (dzc == 0 && first && ks == 0) ? 0u : 1u;
+                    if constexpr (PAIR) {
+                      tc_mma_pair_w(dt[dzc], a_hi_lo + aoff, wlo + (uint32_t)(dzc * (CV_PAIR_TAPBYTES >> 4) + ks * 2), idesc128p, acc_on);
+                    } else {
+                      tc_mma_bf16_w(dt[dzc], a_hi_lo + aoff, wlo + (uint32_t)(dzc * (CV_TAPBYTES >> 4) + ks * 2), idesc128, acc_on);
                     }
                   }
-                  if (CL > 1) tc_commit_mc(&w_empty[ws], mask); else tc_commit(&w_empty[ws]);
+#pragma unroll
+                  for (int dzc = 0; dzc < 3; ++dzc) {
+                    if (!(vmask & (1u << dzc))) continue;
+                    if constexpr (PAIR) {
+                      tc_mma_pair_w(dt[dzc], a_lo_lo + aoff, wlo + (uint32_t)(dzc * (CV_PAIR_TAPBYTES >> 4) + ks * 2) + ((64 * 64) >> 4), idesc64p, 1u);
+                    } else {
+                      tc_mma_bf16_w(dt[dzc], a_lo_lo + aoff, wlo + (uint32_t)(dzc * (CV_TAPBYTES >> 4) + ks * 2), idesc64, 1u);
+                    }
+                  }
                 }
-                __syncwarp();
-                accum = 1u;
-                if (++ws == CV_WSTAGES) { ws = 0; wph ^= 1; }
-                w_ready = mbar_test(&w_full[ws], wph);
+                if constexpr (PAIR) tc_commit_pair(&w_empty[ws]);
+                else if (CL > 1) tc_commit_mc(&w_empty[ws], mask);
+                else tc_commit(&w_empty[ws]);
               }
+              __syncwarp();
+              if (++ws == CV_WSTAGES) { ws = 0; wph ^= 1; }
+              w_ready = mbar_test(&w_full[ws], wph);
             }
-            if (leader) tc_commit(&slab_empty[sb]);
+            if (leader) { if constexpr (PAIR) tc_commit_pair(&slab_empty[sb]); else tc_commit(&slab_empty[sb]); }
             __syncwarp();
             if (++sb == CV_SLABS) { sb = 0; sph ^= 1; }
           }
           // input plane zi done: output plane zi-1 has all of its three input planes
           const int zdone = zi - 1;
-          if (zdone >= z0 && zdone < z0 + lz && leader) tc_commit(&acc_full[(zdone - z0) & 3]);
+          if (zdone >= z0 && zdone < z0 + lz && leader) {
+            if constexpr (PAIR) tc_commit_pair(&acc_full[(zdone - z0) & 3]); else tc_commit(&acc_full[(zdone - z0) & 3]);
+          }
           __syncwarp();
         }
       }
@@ -419,7 +512,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[slot]);
+          if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(&acc_empty[slot]); else mbar_arrive(&acc_empty[slot]); }
           if (yx >= 0) {
             float* dst = p.ptap + (size_t)b * 27 * V3 + (size_t)zo * V * V + yx;
 #pragma unroll
@@ -485,7 +578,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[slot]);
+        if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(&acc_empty[slot]); else mbar_arrive(&acc_empty[slot]); }
       }
       }
       __syncwarp();
@@ -496,7 +589,8 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
   if (CL > 1) cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }
 

@@ -15,7 +15,7 @@
 namespace vxb {
 namespace umma {
 
-constexpr int FA_THREADS = 192;
+constexpr int FA_THREADS = 320;               // TMA warp, MMA warp, 8 softmax warps (two per TMEM lane quarter)
 constexpr int FA_KT = 64;                        // keys per tile
 constexpr int FA_KVSTAGES = 3;
 constexpr int FA_QBYTES = 2 * 128 * 128;         // Q hi + lo
@@ -43,6 +43,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t bars[2 + 2 * FA_KVSTAGES + 8 + 2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float rs_part[2][128];              // row-sum partials of the two key halves
   uint8_t* q_s = smem;
   uint8_t* kv_s = smem + FA_QBYTES;
   uint8_t* p_s = kv_s + FA_KVSTAGES * FA_KVBYTES;
@@ -65,10 +66,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
     mbar_init(q_full, 1); mbar_init(q_empty, 1);
     for (int i = 0; i < FA_KVSTAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
-      mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
+      mbar_init(&p_full[i], 8); mbar_init(&p_empty[i], 1);
     }
-    mbar_init(o_full, 1); mbar_init(o_empty, 4);
+    mbar_init(o_full, 1); mbar_init(o_empty, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -176,6 +177,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
   } else {
     // ===================================================== softmax + epilogue (thread = query row)
     const int q = warp & 3;
+    const int c = (warp - 2) >> 2;                             // which 32-key half of every tile / 32-channel half of O
     const int r = q * 32 + lane;                               // row inside the 128-query tile
     uint32_t it = 0, n = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
@@ -194,8 +196,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
         uint8_t* ph_row = p_s + sb * FA_PBYTES + r * 128;
         uint8_t* pl_row = ph_row + 128 * 128;
         const int key0 = j * FA_KT;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        {
           uint32_t v0[32], v1[32];
           tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + sb * 128u + (uint32_t)(c * 32), v0);
           tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + sb * 128u + 64u + (uint32_t)(c * 32), v1);
@@ -237,11 +238,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       // ---- O / row_sum -> planes
       mbar_wait(o_full, n & 1);
       tc_fence_after();
-      const float inv = 1.f / row_sum;
+      // the two key halves of a row live in different warps: exchange the partial sums through shared memory
+      rs_part[c][r] = row_sum;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float inv = 1.f / (rs_part[0][r] + rs_part[1][r]);
       __nv_bfloat16* oh = p.out_hi + ((size_t)b * p.Nq + qi) * p.ldo + (size_t)h * p.dh;
       __nv_bfloat16* ol = p.out_lo + ((size_t)b * p.Nq + qi) * p.ldo + (size_t)h * p.dh;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         uint32_t v0[32], v1[32];
         tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(c * 32), v0);
         tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 256u + 64u + (uint32_t)(c * 32), v1);
@@ -270,6 +273,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
+      asm volatile("bar.sync 1, 256;" ::: "memory");           // rs_part is rewritten by the next item
     }
   }
   tc_fence_before();

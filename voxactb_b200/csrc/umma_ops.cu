@@ -730,11 +730,11 @@ int conv3_prepare_weights(const float* w_tapmajor, int Cin, __nv_bfloat16* wc, c
   return VXB_OK;
 }
 
-template <int CL>
+template <int CL, bool PAIR>
 static int conv3_launch(const CUtensorMap* maps, const ConvParams& p, size_t smem, cudaStream_t st) {
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    VXB_CUDA(cudaFuncSetAttribute(conv3_umma_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VXB_CUDA(cudaFuncSetAttribute(conv3_umma_kernel<CL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
   static int num_sms = 0;
@@ -757,12 +757,12 @@ static int conv3_launch(const CUtensorMap* maps, const ConvParams& p, size_t sme
   if (CL > 1) {
     cfg.gridDim = dim3(num_sms / CL * CL);
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, conv3_umma_kernel<CL>, &cfg) == cudaSuccess && n > 0) max_clusters = std::min(max_clusters, n);
+    if (cudaOccupancyMaxActiveClusters(&n, conv3_umma_kernel<CL, PAIR>, &cfg) == cudaSuccess && n > 0) max_clusters = std::min(max_clusters, n);
     else cudaGetLastError();
   }
   const int groups = p.items / CL;
   cfg.gridDim = dim3(std::min(groups, max_clusters) * CL);
-  VXB_CUDA(cudaLaunchKernelEx(&cfg, conv3_umma_kernel<CL>, maps[0], maps[1], maps[2], maps[3], maps[4], p));
+  VXB_CUDA(cudaLaunchKernelEx(&cfg, conv3_umma_kernel<CL, PAIR>, maps[0], maps[1], maps[2], maps[3], maps[4], p));
   return VXB_OK;
 }
 
@@ -872,14 +872,24 @@ int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_
   const Planes& xb = x1 ? *x1 : x0;
   VXB_TRY(make_map(&maps[2], xb.hi, rows, 64, 64, p.box_rows, CV_KC));
   VXB_TRY(make_map(&maps[3], xb.lo, rows, 64, 64, p.box_rows, CV_KC));
-  VXB_TRY(make_map(&maps[4], wc, (long long)p.ncb * 27 * 128, CV_KC, CV_KC, 128 / cl, CV_KC));
-  const size_t smem = (size_t)CV_SLABS * 4 * p.box_rows * 64 + (size_t)CV_WSTAGES * CV_WBYTES + 1024;
+  static int pair = -1;
+  if (pair < 0) {
+    const char* e = getenv("VXB_CONV_PAIR");
+    pair = e ? atoi(e) : 0;   // measured: the kernel is limited by the chip's sustained tensor throughput either way
+  }
+  const bool use_pair = pair && cl == 2;
+  VXB_TRY(make_map(&maps[4], wc, (long long)p.ncb * 27 * 128, CV_KC, CV_KC, use_pair ? 32 : 128 / cl, CV_KC));
+  const size_t smem = (size_t)CV_SLABS * 4 * p.box_rows * 64 + (size_t)CV_WSTAGES * (use_pair ? CV_PAIR_WBYTES : CV_WBYTES) + 1024;
   ++g_umma_launches;
   int rc;
-  switch (cl) {
-    case 1: rc = conv3_launch<1>(maps, p, smem, st); break;
-    case 4: rc = conv3_launch<4>(maps, p, smem, st); break;
-    default: rc = conv3_launch<2>(maps, p, smem, st); break;
+  if (use_pair) {
+    rc = conv3_launch<2, true>(maps, p, smem, st);
+  } else {
+    switch (cl) {
+      case 1: rc = conv3_launch<1, false>(maps, p, smem, st); break;
+      case 4: rc = conv3_launch<4, false>(maps, p, smem, st); break;
+      default: rc = conv3_launch<2, false>(maps, p, smem, st); break;
+    }
   }
   return rc;
 }
