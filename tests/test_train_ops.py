@@ -84,7 +84,7 @@ def test_peract_losses_match_reference_formulation(cuda_lib):
     lr_ = sum(ce(qrg_r[:, a * R:(a + 1) * R], arg[:, a]) for a in range(3))
     ref_total = (lt + lr_ + ce(qrg_r[:, 3 * R:], arg[:, 3]) + ce(qc_r, aic[:, 0])).mean()
     ref_total.backward()
-    assert abs(float(total) - float(ref_total)) < 1e-5 * abs(float(ref_total))
+    assert abs(float(total) - float(ref_total.detach())) < 1e-5 * abs(float(ref_total.detach()))
     assert float((grads['q_trans'] - qt_r.grad).abs().max()) < 1e-7
     assert float((grads['q_rot_grip'] - qrg_r.grad).abs().max()) < 1e-6
     assert float((grads['q_collision'] - qc_r.grad).abs().max()) < 1e-6
