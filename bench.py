@@ -170,8 +170,18 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = os.environ.get('VXB_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its version banner to fd 1 while the communicator is created: keep stdout to the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     L = _lib.lib()
     _lib.check(L.vxb_check_device(), 'vxb_check_device')
     math_mode = {'fp32': _lib.MATH_FP32_SIMT, 'bf16x3': _lib.MATH_BF16X3,
