@@ -87,6 +87,8 @@ struct Prepared {
   __nv_bfloat16* patch_wc;  // [k^3][{hi,lo}][64][64] weights of the patchify kernel
   float* q_cross;    // [L][ch*cdh]  = to_q(LN(latents)), batch independent
   float* lat_norm;   // [L][D] scratch for the above
+  float* ff_perm_w;  // [8D][D] scratch: FF net.0 weight with the GEGLU [a | gate] 32-row interleave (split into planes)
+  float* ff_perm_b;  // [depth + 1][8D] permuted FF net.0 biases (index 0 = cross block, 1.. = layers)
   // bf16 hi/lo planes of every weight that feeds a tcgen05 GEMM, keyed by the fp32 weight pointer
   std::vector<std::pair<const float*, umma::Planes>> planes;
 };
@@ -111,6 +113,8 @@ static void carve_prepared(const Dims& m, Arena& a, Prepared& p, const void* con
   p.patch_wc = a.get<__nv_bfloat16>(umma::patchify_weight_elems(m.k));
   p.q_cross = a.get<float>((size_t)m.L * m.ch * m.cdh);
   p.lat_norm = a.get<float>((size_t)m.L * m.D);
+  p.ff_perm_w = a.get<float>((size_t)8 * m.D * m.D);
+  p.ff_perm_b = a.get<float>((size_t)(m.depth + 1) * 8 * m.D);
   std::vector<WeightSpec> specs;
   weight_specs(m, params, p, specs);
   p.planes.clear();
@@ -362,17 +366,18 @@ static int need(const umma::Planes* p, const char* what) {
 
 // x = x + FF(LN(x))
 static int feed_forward_planes(Ctx& cx, const Dims& m, int B, Work& w, const float* nw, const float* nb,
-                               const float* w0, const float* b0, const float* w2, const float* b2) {
+                               const float* w0, const float* b0_perm, const float* w2, const float* b2) {
   const long long rows = (long long)B * m.L;
   WPLANES(W0, w0);
   WPLANES(W2, w2);
   const umma::Planes xn = planes_of(w.px, m.D), pg = planes_of(w.pg, 4 * m.D);
-  g_launches += 4;
+  g_launches += 3;
   VXB_TRY(umma::layernorm_planes(w.x, 0, (int)rows, nw, nb, xn, rows, m.D, cx.st));
+  // net.0 + GEGLU in one GEMM: weights / bias are interleaved [a | gate] per 32 columns at prepare time and the
+  // epilogue writes a * gelu(gate) straight into the planes net.2 consumes (no fp32 hidden tensor)
   umma::LinOut o1;
-  o1.bias = b0; o1.out_f32 = w.ffh; o1.ldc = 8 * m.D;
+  o1.bias = b0_perm; o1.out_planes = &pg; o1.geglu = 1;
   VXB_TRY(umma::linear_planes(xn, rows, m.D, *W0, 8 * m.D, o1, cx.st));
-  VXB_TRY(umma::geglu_planes(w.ffh, pg, rows, 4 * m.D, cx.st));
   umma::LinOut o2;
   o2.bias = b2; o2.residual = w.x; o2.res_rows = (int)rows; o2.ldr = m.D; o2.out_f32 = w.x; o2.ldc = m.D;
   return umma::linear_planes(pg, rows, 4 * m.D, *W2, m.D, o2, cx.st);
@@ -388,9 +393,7 @@ static int project_kv(Ctx& cx, Work& w, const umma::Planes& ctx, int B, int Nk, 
   umma::LinOut ok;
   ok.out_planes = &pk;
   VXB_TRY(umma::linear_planes(ctx, (long long)B * Nk, Kdim, *Wkv, inner, ok, cx.st));
-  umma::LinOut ov;
-  ov.out_planes = &pvt; ov.transposed = 1; ov.batches = B;
-  return umma::linear_planes(ctx, (long long)B * Nk, Kdim, sub_rows(*Wkv, inner), inner, ov, cx.st);
+  return umma::project_vt(ctx, B, Nk, Kdim, sub_rows(*Wkv, inner), inner, pvt, cx.st);
 }
 
 static int transformer_planes(Ctx& cx, const vxb_qnet_desc* d, const Dims& m, const void* const* params,
@@ -439,7 +442,7 @@ static int transformer_planes(Ctx& cx, const vxb_qnet_desc* d, const Dims& m, co
       VXB_TRY(umma::linear_planes(po, rowsL, cq, *Wo, m.D, oo, st));
     }
     VXB_TRY(feed_forward_planes(cx, m, B, w, P(VXB_P_CROSS_FF_NORM_W), P(VXB_P_CROSS_FF_NORM_B), P(VXB_P_CROSS_FF0_W),
-                                P(VXB_P_CROSS_FF0_B), P(VXB_P_CROSS_FF2_W), P(VXB_P_CROSS_FF2_B)));
+                                pw.ff_perm_b, P(VXB_P_CROSS_FF2_W), P(VXB_P_CROSS_FF2_B)));
     // latent self-attention stack                                                       :435-437
     for (int l = 0; l < m.depth; ++l) {
       const umma::Planes xn = planes_of(w.px, m.D);
@@ -463,7 +466,7 @@ static int transformer_planes(Ctx& cx, const vxb_qnet_desc* d, const Dims& m, co
       ++g_launches;
       VXB_TRY(umma::linear_planes(pol, rowsL, lq, *Wo, m.D, oo, st));
       VXB_TRY(feed_forward_planes(cx, m, B, w, PL(l, VXB_PL_FF_NORM_W), PL(l, VXB_PL_FF_NORM_B), PL(l, VXB_PL_FF0_W),
-                                  PL(l, VXB_PL_FF0_B), PL(l, VXB_PL_FF2_W), PL(l, VXB_PL_FF2_B)));
+                                  pw.ff_perm_b + (size_t)(l + 1) * 8 * m.D, PL(l, VXB_PL_FF2_W), PL(l, VXB_PL_FF2_B)));
     }
   }
   return VXB_OK;
@@ -494,6 +497,21 @@ static int decoder_planes(Ctx& cx, const Dims& m, const void* const* params, Wor
   umma::LinOut oo;
   oo.bias = P(VXB_P_DEC_OUT_B); oo.out_f32 = w.dec; oo.ldc = m.C;
   return umma::linear_planes(po, rowsT, cq, *Wo, m.C, oo, st);
+}
+
+// GEGLU fusion: the FF net.0 output columns [a (4D) | gate (4D)] are re-ordered into 32-column chunks
+// [a_0..31 | g_0..31 | a_32..63 | g_32..63 | ...] so that a GEMM epilogue sees a value and its gate together
+static __global__ void geglu_permute_kernel(const float* __restrict__ w, const float* __restrict__ b, int D4, int K,
+                                            float* __restrict__ wp, float* __restrict__ bp) {
+  const long long total = (long long)2 * D4 * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % K);
+    const int r = (int)(i / K);                      // permuted row
+    const int blk = r / 64, within = r % 64;
+    const int src = within < 32 ? blk * 32 + within : D4 + blk * 32 + (within - 32);
+    wp[i] = w[(long long)src * K + c];
+    if (c == 0) bp[r] = b[src];
+  }
 }
 
 static int conv_weight_prepare(const float* w, float* o, int Co, int Ci, int k3, cudaStream_t st) {
@@ -584,6 +602,17 @@ extern "C" int vxb_qnet_prepare(const vxb_qnet_desc* d, const void* const* param
     weight_specs(m, params, p, specs);
     for (size_t i = 0; i < specs.size(); ++i)
       VXB_TRY(umma::split_rows(specs[i].w, specs[i].cols, specs[i].rows, (int)specs[i].cols, p.planes[i].second, st));
+    // FF net.0 weights: replace their planes by the GEGLU-interleaved version (the fused epilogue's layout)
+    if (m.D % 32 == 0) {
+      for (int f = 0; f <= m.depth; ++f) {
+        const float* w0 = f == 0 ? P(VXB_P_CROSS_FF0_W) : (const float*)params[VXB_P_FIXED_COUNT + (f - 1) * VXB_P_LAYER_STRIDE + VXB_PL_FF0_W];
+        const float* b0 = f == 0 ? P(VXB_P_CROSS_FF0_B) : (const float*)params[VXB_P_FIXED_COUNT + (f - 1) * VXB_P_LAYER_STRIDE + VXB_PL_FF0_B];
+        geglu_permute_kernel<<<148 * 4, 256, 0, st>>>(w0, b0, 4 * m.D, m.D, p.ff_perm_w, p.ff_perm_b + (size_t)f * 8 * m.D);
+        VXB_LAUNCH_CHECK();
+        for (size_t i = 0; i < specs.size(); ++i)
+          if (specs[i].w == w0) VXB_TRY(umma::split_rows(p.ff_perm_w, m.D, 8ll * m.D, m.D, p.planes[i].second, st));
+      }
+    }
   }
   return VXB_OK;
 }
@@ -653,7 +682,7 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
 
   STAGE_MARK();  // 4: transformer (cross + latent self-attention + FF)
   // (5) latents: x = repeat(latents) is never materialised; the first residual reads latents[m % L]   :425
-  const bool planes_path = mm == VXB_MATH_BF16X3 && m.cdh == 64 && m.ldh == 64 && m.C % 8 == 0 && m.D % 8 == 0;
+  const bool planes_path = mm == VXB_MATH_BF16X3 && m.cdh == 64 && m.ldh == 64 && m.C % 8 == 0 && m.D % 32 == 0;
   if (planes_path) {
     VXB_TRY(transformer_planes(cx, d, m, params, pw, w, B));
     STAGE_MARK();  // 5: decoder cross attention + ss1

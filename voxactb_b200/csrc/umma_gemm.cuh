@@ -162,7 +162,7 @@ struct SmemLayout {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /* alignment slack */;   // dynamic part
 };
 
-enum { EPIK_GENERIC = 0, EPIK_PLAIN = 1, EPIK_ROWMAX = 2, EPIK_EXP = 3 };
+enum { EPIK_GENERIC = 0, EPIK_PLAIN = 1, EPIK_ROWMAX = 2, EPIK_EXP = 3, EPIK_GEGLU = 4 };
 
 template <int NT, int STAGES, int EPI>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
@@ -343,6 +343,59 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
         }
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
+        if constexpr (EPI == EPIK_GEGLU) {
+          // pairs of 32-column chunks: [a | gate] of the same 32 output columns; the warps of a lane quarter alternate pairs
+#pragma unroll 1
+          for (int c0 = half * 64; c0 < NT; c0 += 128) {
+            const int n = n0 + c0;
+            if (n >= e.N) break;
+            float4 xa[8], xg[8];
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+              uint32_t v[32];
+              tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + c0 + part * 32), v);
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(stage + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) =
+                    make_float4(__uint_as_float(v[j]) * e.alpha, __uint_as_float(v[j + 1]) * e.alpha,
+                                __uint_as_float(v[j + 2]) * e.alpha, __uint_as_float(v[j + 3]) * e.alpha);
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = i * 4 + tr;
+                const float4 x = *reinterpret_cast<const float4*>(stage + r * 32 + ((((lane & 7)) ^ (r & 7)) << 2));
+                if (part == 0) xa[i] = x; else xg[i] = x;
+              }
+              __syncwarp();
+            }
+            const int nn = n + tc;
+            float ba[4] = {0.f, 0.f, 0.f, 0.f}, bg[4] = {0.f, 0.f, 0.f, 0.f};
+            if (e.bias) {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) { ba[t] = __ldg(e.bias + nn + t); bg[t] = __ldg(e.bias + nn + 32 + t); }
+            }
+            const long long poff = zb * p.p_zb + zh * p.p_zh + (long long)(mw + tr) * e.ldp + (n >> 1) + tc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (mw + i * 4 + tr < e.M) {
+                const float a[4] = {xa[i].x + ba[0], xa[i].y + ba[1], xa[i].z + ba[2], xa[i].w + ba[3]};
+                const float g[4] = {xg[i].x + bg[0], xg[i].y + bg[1], xg[i].z + bg[2], xg[i].w + bg[3]};
+                float o[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) o[t] = a[t] * (0.5f * g[t] * (1.f + erff(g[t] * 0.70710678118654752f)));
+                const __nv_bfloat162 h01 = pl2_from_floats(o[0], o[1]), h23 = pl2_from_floats(o[2], o[3]);
+                const float2 f01 = pl2_to_float2(h01), f23 = pl2_to_float2(h23);
+                const __nv_bfloat162 l01 = pl2_from_floats(o[0] - f01.x, o[1] - f01.y);
+                const __nv_bfloat162 l23 = pl2_from_floats(o[2] - f23.x, o[3] - f23.y);
+                uint2 hv, lv;
+                hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                *reinterpret_cast<uint2*>(e.out_hi + poff + (long long)(i * 4) * e.ldp) = hv;
+                *reinterpret_cast<uint2*>(e.out_lo + poff + (long long)(i * 4) * e.ldp) = lv;
+              }
+            }
+          }
+        } else {
 #pragma unroll 1
         for (int c0 = half * 32; c0 < NT; c0 += 64) {
           const int n = n0 + c0;
@@ -489,6 +542,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
             __syncwarp();
           }
         }
+        }   // !GEGLU
         if constexpr (EPI == EPIK_ROWMAX) {
           if (row_ok) {
             float* a = e.row_stat + rs_off + m;

@@ -28,7 +28,9 @@ enum { ROWS_PLAIN = 0, ROWS_CONV_FLAT = 1, ROWS_PHASE = 2 };
 //   EPI_STORE   out = act(alpha*acc + bias) + residual, optionally divided by row_div[row]
 //   EPI_ROWMAX  row_stat[row] = max(row_stat[row], max_n alpha*acc)            (atomic, nothing stored)
 //   EPI_EXP     p = 2^(alpha*acc - row_sub[row]); row_stat[row] += sum_n p (atomic); p stored as planes
-enum { EPI_STORE = 0, EPI_ROWMAX = 1, EPI_EXP = 2 };
+//   EPI_GEGLU   out[:, j] = (acc_a + bias_a) * gelu_erf(acc_g + bias_g) as planes; the GEMM's N columns come in
+//               interleaved 32-column chunks [a | gate] (weights / bias permuted at prepare time), N_out = N / 2
+enum { EPI_STORE = 0, EPI_ROWMAX = 1, EPI_EXP = 2, EPI_GEGLU = 3 };
 
 struct Epilogue {
   int M, N;                   // logical extents (rows beyond M / cols beyond N are not stored)
@@ -121,9 +123,13 @@ struct LinOut {
   const Planes* out_planes = nullptr;   // planes [M, ld] or, with transposed, [batches][N][ld] (ld >= rows per batch)
   int transposed = 0;
   int batches = 1;                      // transposed only: M = batches * rows_per_batch
+  int geglu = 0;                        // fused GEGLU epilogue (out_planes has N / 2 columns; W and bias pre-permuted)
 };
 // C[M,N] = A[M,K] W[N,K]^T with plane operands
 int linear_planes(const Planes& A, long long M, int K, const Planes& W, int N, const LinOut& o, cudaStream_t st);
+// V^T planes [B][inner][ld >= Nk] = Wv[inner, K] ctx_b[Nk, K]^T per batch: the projection written directly in the
+// layout the attention kernel consumes (the weight matrix is the M operand, so the stores stay row-contiguous)
+int project_vt(const Planes& ctx, int B, int Nk, int K, const Planes& Wv, int inner, const Planes& vt, cudaStream_t st);
 // softmax(scale q k^T) v per (batch, head) as three tcgen05 GEMMs (row max, exp + row sum -> P planes, P V / sum).
 // Q [(B or 1)*Nq, H*dh] (q_batched = 0: one Q shared by all batches), K [B*Nk, H*dh], Vt [B*H*dh, pad8(Nk)],
 // P scratch planes [B*H*Nq, pad8(Nk)], O planes [B*Nq, H*dh]; rowmax / rowsum: B*H*Nq floats each.

@@ -334,6 +334,7 @@ static int launch_t(const CUtensorMap* maps, const Params& p, cudaStream_t st) {
   if (e.row_mode == ROWS_PLAIN && !e.transpose_planes) {
     if (e.mode == EPI_ROWMAX) return launch_e<NT, STAGES, EPIK_ROWMAX>(maps, p, st);
     if (e.mode == EPI_EXP) return launch_e<NT, STAGES, EPIK_EXP>(maps, p, st);
+    if (e.mode == EPI_GEGLU) return launch_e<NT, STAGES, EPIK_GEGLU>(maps, p, st);
     return launch_e<NT, STAGES, EPIK_PLAIN>(maps, p, st);
   }
   return launch_e<NT, STAGES, EPIK_GENERIC>(maps, p, st);
@@ -525,6 +526,13 @@ int linear_planes(const Planes& A, long long M, int K, const Planes& W, int N, c
     p.ep.out_hi = o.out_planes->hi; p.ep.out_lo = o.out_planes->lo; p.ep.ldp = o.out_planes->ld;
     p.ep.transpose_planes = o.transposed;
   }
+  if (o.geglu) {
+    if (N % 128 || !o.out_planes || o.transposed || o.out_f32) {
+      set_error("linear_planes: the GEGLU epilogue needs N %% 128 == 0 and a plane output only");
+      return VXB_E_BADARG;
+    }
+    p.ep.mode = EPI_GEGLU;
+  }
   if (o.transposed && o.batches > 1) {
     if (M % o.batches) {
       set_error("linear_planes: M=%lld not divisible by batches=%d", M, o.batches);
@@ -541,6 +549,24 @@ int linear_planes(const Planes& A, long long M, int K, const Planes& W, int N, c
     p.ep.M = (int)M;
   }
   Operand a{A, M, K}, w{W, N, K};
+  return gemm(a, nullptr, w, nt, p, st);
+}
+
+int project_vt(const Planes& ctx, int B, int Nk, int K, const Planes& Wv, int inner, const Planes& vt, cudaStream_t st) {
+  Params p;
+  params_init(p);
+  const int nt = pick_ntile(Nk);
+  p.m_tiles = cdiv(inner, BM);
+  p.n_tiles = cdiv(Nk, nt);
+  p.plan.num_kb = cdiv(K, BK);
+  p.batches = B; p.Hz = 1;
+  p.a_row_zb = 0;                 // the weights are shared by every batch
+  p.w_row_zb = Nk;                // the context rows of batch b are the N operand
+  p.p_zb = (long long)inner * vt.ld;
+  p.ep.M = inner; p.ep.N = Nk; p.ep.row_mode = ROWS_PLAIN;
+  p.ep.out_hi = vt.hi; p.ep.out_lo = vt.lo; p.ep.ldp = vt.ld;
+  const Operand a{Wv, inner, K};
+  const Operand w{ctx, (long long)B * Nk, K};
   return gemm(a, nullptr, w, nt, p, st);
 }
 
