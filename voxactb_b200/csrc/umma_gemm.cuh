@@ -216,7 +216,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
         const int z = tile / tiles_per_z, tz = tile % tiles_per_z;
         const int zb = z / p.Hz, zh = z % p.Hz;
         const int mt = tz / p.n_tiles, nt = tz % p.n_tiles;
-        const int m0 = mt * BM + zb * p.a_row_zb + zh * p.a_row_zh;
+        const int m0 = mt * BM + zb * p.a_row_zb + zh * p.a_row_zh + p.a_row_off;
         const int n0 = nt * NT + zb * p.w_row_zb + zh * p.w_row_zh;
         for (int kb = 0; kb < pl.num_kb; ++kb) {
           int a_row = 0, a_col = kb * BK, a_src = 0;
@@ -575,8 +575,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
       if (e.row_mode != ROWS_PLAIN) {
         const int Vp = e.Vp, V = Vp - 2 * e.pad;
         const int vp3 = Vp * Vp * Vp;
-        qb = m / vp3;
-        const int r = m - qb * vp3;
+        const int mabs = m + zb * p.a_row_zb + p.a_row_off;   // flat row of the padded grid (all batches)
+        qb = mabs / vp3;
+        const int r = mabs - qb * vp3;
         qd = r / (Vp * Vp) - e.pad; qh = (r / Vp) % Vp - e.pad; qw = r % Vp - e.pad;
         row_ok = row_ok && qd >= 0 && qd < V && qh >= 0 && qh < V && qw >= 0 && qw < V;
         if (e.row_mode == ROWS_CONV_FLAT && !e.out_padded) orow = (((long long)qb * V + qd) * V + qh) * V + qw;

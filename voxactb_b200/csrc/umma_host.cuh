@@ -65,6 +65,7 @@ struct Params {
   int batches, Hz;
   int a_row_zb, a_col_zh;        // A: rows per zb, columns per zh
   int a_row_zh;                  // A: rows per zh
+  int a_row_off;                 // A: first row of every batch entry (conv modes skip the all-halo leading z planes)
   int terms;                     // 3 = hi*hi + hi*lo + lo*hi (default), 1 = hi*hi only (lo planes are not loaded)
   long long rs_zb, rs_zh;        // row statistic element offsets per zb / zh
   int w_row_zb, w_row_zh, w_col_zh;

@@ -448,11 +448,17 @@ int conv3d_f32(const float* x0, const float* x1, int C0, int C1, const Planes& W
   Params p;
   params_init(p);
   const int nt = pick_ntile(Co);
-  p.m_tiles = cdiv(rows, BM);
+  // one batch entry per sample; the leading / trailing `pad` z planes of the padded grid hold no output voxel:
+  // start at the first row that can be valid and stop after the last one
+  const long long vp3 = Vp * Vp * Vp;
+  const long long row_lo = ((long long)pad * Vp + pad) * Vp + pad;
+  const long long row_hi = vp3 - row_lo;                       // one past the last interior row
+  p.batches = B; p.a_row_zb = (int)vp3; p.a_row_off = (int)row_lo;
+  p.m_tiles = cdiv(row_hi - row_lo, BM);
   p.n_tiles = cdiv(Co, nt);
   p.plan.taps = k; p.plan.Vp = (int)Vp; p.plan.cpb = (C0 + C1) / 64; p.plan.cb_src0 = C0 / 64;
   p.plan.num_kb = k * k * k * p.plan.cpb;
-  p.ep.M = (int)rows; p.ep.N = Co; p.ep.row_mode = ROWS_CONV_FLAT; p.ep.Vp = (int)Vp; p.ep.pad = pad;
+  p.ep.M = (int)(row_hi - row_lo); p.ep.N = Co; p.ep.row_mode = ROWS_CONV_FLAT; p.ep.Vp = (int)Vp; p.ep.pad = pad;
   p.ep.out_padded = 0;
   p.ep.bias = bias; p.ep.act_slope = act_slope;
   p.ep.out_f32 = out; p.ep.ldc = Co;
@@ -488,11 +494,16 @@ int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out
   params_init(p);
   const int N = s * s * s * 64;
   const int nt = 256;
-  p.m_tiles = cdiv(rows, BM);
+  // one batch entry per sample, restricted to the rows between the first and the last interior voxel (the two
+  // all-halo z planes of the padded low-resolution grid are skipped)
+  const long long sp3 = Sp * Sp * Sp;
+  const long long row_lo = (Sp + 1) * Sp + 1, row_hi = sp3 - row_lo;
+  p.batches = B; p.a_row_zb = (int)sp3; p.a_row_off = (int)row_lo;
+  p.m_tiles = cdiv(row_hi - row_lo, BM);
   p.n_tiles = cdiv(N, nt);
   p.plan.taps = 3; p.plan.Vp = (int)Sp; p.plan.cpb = Ci / 64; p.plan.cb_src0 = Ci / 64;
   p.plan.num_kb = 27 * p.plan.cpb;
-  p.ep.M = (int)rows; p.ep.N = N; p.ep.row_mode = ROWS_PHASE; p.ep.Vp = (int)Sp; p.ep.pad = 1;
+  p.ep.M = (int)(row_hi - row_lo); p.ep.N = N; p.ep.row_mode = ROWS_PHASE; p.ep.Vp = (int)Sp; p.ep.pad = 1;
   p.ep.phase_s = s;
   p.ep.bias = bias; p.ep.act_slope = act_slope;
   if (out_planes) {
