@@ -66,8 +66,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
     mbar_init(q_full, 1); mbar_init(q_empty, 1);
     for (int i = 0; i < FA_KVSTAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
-      mbar_init(&p_full[i], 8); mbar_init(&p_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_full, 1); mbar_init(o_empty, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -177,7 +177,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
   } else {
     // ===================================================== softmax + epilogue (thread = query row)
     const int q = warp & 3;
-    const int c = (warp - 2) >> 2;                             // which 32-key half of every tile / 32-channel half of O
+    const int c = (warp - 2) >> 2;                             // softmax group = S/P buffer it owns = 32-channel half of O it writes
     const int r = q * 32 + lane;                               // row inside the 128-query tile
     uint32_t it = 0, n = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
@@ -190,17 +190,19 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       float row_sum = 0.f;
       for (int j = 0; j < p.k_tiles; ++j, ++it) {
         const uint32_t sb = it & 1u;
+        if (sb != (uint32_t)c) continue;                       // the other group's tile
         mbar_wait(&s_full[sb], (it >> 1) & 1u);
         tc_fence_after();
-        mbar_wait(&p_empty[sb], ((it >> 1) & 1u) ^ 1u);        // PV of the tile two back has consumed this P buffer
+        mbar_wait(&p_empty[sb], ((it >> 1) & 1u) ^ 1u);        // PV of this group's previous tile has consumed the P buffer
         uint8_t* ph_row = p_s + sb * FA_PBYTES + r * 128;
         uint8_t* pl_row = ph_row + 128 * 128;
         const int key0 = j * FA_KT;
-        {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
           uint32_t v0[32], v1[32];
-          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + sb * 128u + (uint32_t)(c * 32), v0);
-          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + sb * 128u + 64u + (uint32_t)(c * 32), v1);
-          const bool full = key0 + c * 32 + 31 < p.Nk;
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + sb * 128u + (uint32_t)(cc * 32), v0);
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + sb * 128u + 64u + (uint32_t)(cc * 32), v1);
+          const bool full = key0 + cc * 32 + 31 < p.Nk;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {                        // 8 keys = one 16-byte chunk per plane
             float pv[8];
@@ -210,7 +212,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
               const float s = __uint_as_float(v0[jj]) + __uint_as_float(v1[jj]);
               float t;
               asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(s, p.alpha, bias)));
-              if (!full) t = (key0 + c * 32 + jj < p.Nk) ? t : 0.f;
+              if (!full) t = (key0 + cc * 32 + jj < p.Nk) ? t : 0.f;
               row_sum += t;
               pv[e] = t;
             }
@@ -225,7 +227,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
               hp[e] = *reinterpret_cast<const uint32_t*>(&hh);
               lp[e] = *reinterpret_cast<const uint32_t*>(&ll);
             }
-            const int off = ((c * 4 + g) ^ (r & 7)) * 16;
+            const int off = ((cc * 4 + g) ^ (r & 7)) * 16;
             *reinterpret_cast<uint4*>(ph_row + off) = hv;
             *reinterpret_cast<uint4*>(pl_row + off) = lv;
           }
