@@ -112,6 +112,21 @@ def test_two_robots_forward_matches_golden(cuda_lib, mode):
         assert util.rel_err(ours, g[key]) < util.Q_REL_TOL, key
 
 
+def test_full_size_tensor_core_path_matches_fp32_path(cuda_lib):
+    """BASELINE geometry (100^3, 4 cameras, 2048 latents, depth 6) at B=2 with per-sample VLM-crop bounds: the
+    tcgen05 split-precision path against the library's own fp32 FFMA path on the same inputs (size-independent
+    cross-check at a shape the CPU oracle is too slow for), plus identical argmax voxels."""
+    c = dict(make_golden.QNET_CASES['qnet_v100_b1'], B=2, seed=777, crop=True)
+    obs, enc, sd = util.make_case(c)
+    _, (t0, r0, c0, g0) = run_qfunction(c, obs, enc, _lib.MATH_FP32_SIMT)
+    t0, r0, c0, g0 = t0.clone(), r0.clone(), c0.clone(), g0.clone()
+    _, (t1, r1, c1, g1) = run_qfunction(c, obs, enc, _lib.MATH_BF16X3)
+    assert torch.equal(g0[:, 6:], g1[:, 6:])                 # index-grid + occupancy channels bit-exact
+    assert torch.allclose(g0[:, :6], g1[:, :6], rtol=2e-6, atol=2e-6)   # means: atomic fp32 sums, order differs
+    assert util.rel_err(t1, t0) < 5e-4 and util.rel_err(r1, r0) < util.Q_REL_TOL and util.rel_err(c1, c0) < util.Q_REL_TOL
+    assert torch.equal(t0.reshape(2, -1).argmax(-1), t1.reshape(2, -1).argmax(-1))
+
+
 def test_checkpoint_roundtrip_and_deepcopy(cuda_lib, tmp_path):
     import copy
     c = make_golden.QNET_CASES['qnet_v20']
