@@ -47,6 +47,10 @@ def parse():
     ap.add_argument('--batch', type=int, default=16, help='samples per GPU')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--math', default=os.environ.get('VXB_MATH', 'auto'), choices=['auto', 'fp32', 'bf16x3'])
+    ap.add_argument('--workload', default='single', choices=['single', 'dual', 'crop'],
+                    help='single = BASELINE config 2 geometry at --batch (headline); dual = config 3 (acting + stabilizing '
+                         'encoders, low_dim 7 + arm head, on the same observations; value counts agent-passes); '
+                         'crop = config 4 (per-sample VLM-crop bounds [B,6])')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
@@ -75,6 +79,11 @@ def peaks():
     return dict(hbm=6650.0, tensor=1400.0, tensor_burst=1590.0, source='fallback (B200_PROFILING.md)')
 
 
+WORKLOADS = {
+    'dual': 'batch={b}/GPU, 100^3 voxels, 4 cameras 128x128 RGB-D, CLIP lang tokens [77,512], bimanual acting + stabilizing dual-agent forward '
+            '(two encoders, low_dim 7, arm head; 2 agent-passes per sample; bimanual steps/s = value / 2)',
+    'crop': 'batch={b}/GPU, 100^3 voxels, 4 cameras 128x128 RGB-D, CLIP lang tokens [77,512], single-arm PerAct forward with per-sample VLM-crop bounds [B,6]',
+}
 WORKLOAD = 'batch={b}/GPU, 100^3 voxels, 4 cameras 128x128 RGB-D, CLIP lang tokens [77,512], single-arm PerAct forward (voxelize + Q-net, 2048 latents, depth 6)'
 
 
@@ -188,18 +197,30 @@ def run_ours(args):
                  'auto': PerceiverVoxelLangEncoder.math_mode}[args.math]
     B, V = args.batch, 100
     torch.manual_seed(1234 + rank)
-    enc = PerceiverVoxelLangEncoder(
-        depth=6, iterations=1, voxel_size=V, initial_dim=10, low_dim_size=4, layer=0, num_rotation_classes=72,
-        num_grip_classes=2, num_collision_classes=2, input_axis=3, num_latents=2048, latent_dim=512, cross_heads=1,
-        latent_heads=8, cross_dim_head=64, latent_dim_head=64, activation='lrelu', weight_tie_layers=False,
-        pos_encoding_with_lang=True, input_dropout=0.1, attn_dropout=0.1, decoder_dropout=0.0,
-        lang_fusion_type='seq', voxel_patch_size=5, voxel_patch_stride=5, final_dim=64).eval()
-    enc.load_state_dict(synth.random_state_dict(enc, 2234), strict=False)
-    enc.math_mode = math_mode
-    vg = VoxelGrid(synth.SCENE_BOUNDS, V, dev, B, 3, 4 * 128 * 128)
-    q = QFunction(enc, vg, 0.15, 5, dev, False, False).to(dev).eval()
+    dual = args.workload == 'dual'
+    low_dim = 7 if dual else 4
+    workload = WORKLOADS.get(args.workload, WORKLOAD).format(b=B)
 
-    obs = synth.make_observation(1234 + rank, B, 4, 128, 128, low_dim=4)
+    def make_agent(seed):
+        enc = PerceiverVoxelLangEncoder(
+            depth=6, iterations=1, voxel_size=V, initial_dim=10, low_dim_size=low_dim, layer=0, num_rotation_classes=72,
+            num_grip_classes=2, num_collision_classes=2, input_axis=3, num_latents=2048, latent_dim=512, cross_heads=1,
+            latent_heads=8, cross_dim_head=64, latent_dim_head=64, activation='lrelu', weight_tie_layers=False,
+            pos_encoding_with_lang=True, input_dropout=0.1, attn_dropout=0.1, decoder_dropout=0.0,
+            lang_fusion_type='seq', voxel_patch_size=5, voxel_patch_stride=5, final_dim=64,
+            **({'arm_pred_loss': True} if dual else {})).eval()
+        enc.load_state_dict(synth.random_state_dict(enc, seed), strict=False)
+        enc.math_mode = math_mode
+        vg = VoxelGrid(synth.SCENE_BOUNDS, V, dev, B, 3, 4 * 128 * 128)
+        return enc, vg, QFunction(enc, vg, 0.15, 5, dev, False, dual).to(dev).eval()
+
+    enc, vg, q = make_agent(2234)                      # single-arm / acting agent
+    agents = [q]
+    if dual:
+        agents.append(make_agent(3234)[2])             # stabilizing agent: its own weights, same observations
+    passes_per_sample = len(agents)
+
+    obs = synth.make_observation(1234 + rank, B, 4, 128, 128, low_dim=low_dim, per_sample_crop=args.workload == 'crop')
     host = {k: [t.pin_memory() for t in obs[k]] for k in ('rgb', 'pcd')}
     for k in ('proprio', 'lang_goal_emb', 'lang_token_embs', 'bounds'):
         host[k] = obs[k].pin_memory()
@@ -218,23 +239,25 @@ def run_ours(args):
 
     def step_device(d):
         rgb_pcd = [[r, p] for r, p in zip(d['rgb'], d['pcd'])]
-        return q(rgb_pcd, d['proprio'], d['pcd'], resident['lang_goal_emb'], d['lang_token_embs'], d['bounds'], None, None)
+        return [a(rgb_pcd, d['proprio'], d['pcd'], resident['lang_goal_emb'], d['lang_token_embs'], d['bounds'], None, None)
+                for a in agents]
 
-    out_host = {'coords': torch.empty(B, 3, dtype=torch.int32).pin_memory(),
-                'rg': torch.empty(B, 4, dtype=torch.int32).pin_memory(),
-                'coll': torch.empty(B, dtype=torch.int32).pin_memory(),
-                'xyz': torch.empty(B, 3, dtype=torch.float32).pin_memory()}
-    d2h_bytes = sum(t.numel() * 4 for t in out_host.values())
+    out_hosts = [{'coords': torch.empty(B, 3, dtype=torch.int32).pin_memory(),
+                  'rg': torch.empty(B, 4, dtype=torch.int32).pin_memory(),
+                  'coll': torch.empty(B, dtype=torch.int32).pin_memory(),
+                  'xyz': torch.empty(B, 3, dtype=torch.float32).pin_memory()} for _ in agents]
+    d2h_bytes = sum(t.numel() * 4 for oh in out_hosts for t in oh.values())
 
     def step_e2e():
         d = upload()
-        trans, rot_grip, coll, _ = step_device(d)
-        coords, rg, ic, xyz = q.select_action(trans, rot_grip, coll, d['bounds'])
-        out_host['coords'].copy_(coords, non_blocking=True)
-        out_host['rg'].copy_(rg, non_blocking=True)
-        out_host['coll'].copy_(ic, non_blocking=True)
-        out_host['xyz'].copy_(xyz, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller needs the action before the next step
+        for a, out, out_host in zip(agents, step_device(d), out_hosts):
+            trans, rot_grip, coll = out[0], out[1], out[2]
+            coords, rg, ic, xyz = a.select_action(trans, rot_grip, coll, d['bounds'])
+            out_host['coords'].copy_(coords, non_blocking=True)
+            out_host['rg'].copy_(rg, non_blocking=True)
+            out_host['coll'].copy_(ic, non_blocking=True)
+            out_host['xyz'].copy_(xyz, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller needs the actions before the next step
 
     def timed(fn, steps, warmup, profile=False):
         for _ in range(warmup):
@@ -273,7 +296,7 @@ def run_ours(args):
     clocks = ClockSampler(local)
     ms_dev, stages = timed(lambda: step_device(resident), args.steps, args.warmup, profile=True)
     clk = clocks.stop()
-    launches_per_step = L.vxb_voxelize_launches() + enc.last_launch_count
+    launches_per_step = passes_per_sample * (L.vxb_voxelize_launches() + enc.last_launch_count)
     ms_vox, _ = timed(lambda: vg.coords_to_bounding_voxel_grid(cf, ff, bb), max(args.steps, 10), 3)
     ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
 
@@ -283,8 +306,8 @@ def run_ours(args):
         return
     pk = peaks()
     per_step = ms_dev / args.steps
-    value = world * B / (per_step * 1e-3)
-    e2e_value = world * B / (ms_e2e / args.steps * 1e-3)
+    value = world * B * passes_per_sample / (per_step * 1e-3)
+    e2e_value = world * B * passes_per_sample / (ms_e2e / args.steps * 1e-3)
     final_ms = stages['final_conv']
     achieved_tf = FINAL_CONV_FLOPS * B / (final_ms * 1e-3) / 1e12
     vox_ms = ms_vox / max(args.steps, 10)
@@ -293,7 +316,7 @@ def run_ours(args):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if math_mode == _lib.MATH_FP32_SIMT else 'f16x3 (split-fp16 hi/lo planes, 3 tcgen05 kind::f16 MMAs per product, fp32 accumulate in TMEM)',
         'data': 'synthetic',
-        'config': {'workload': WORKLOAD.format(b=B), 'global_batch': world * B, 'parallelism': 'batch-sharded x%d, no collective' % world,
+        'config': {'workload': workload, 'global_batch': world * B, 'parallelism': 'batch-sharded x%d, no collective' % world,
                    'math_mode': 'fp32_simt' if math_mode == _lib.MATH_FP32_SIMT else 'split16x3_tcgen05',
                    'l2': 'no explicit flush: each step streams >10 GB of activations, far above the 126 MB L2'},
         'e2e': {'value': e2e_value, 'unit': 'passes/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
@@ -312,7 +335,7 @@ def run_ours(args):
                      'note': 'achieved = direct-convolution FLOPs (442.4 GF/sample) / CUDA-event time; the kernel executes 3 f16 MMAs per '
                              'logical product (fp32-class accuracy), so its own ceiling is 1/3 of this bf16 peak',
                      'peak_source': pk['source'] + ' bf16 sustained', 'ms_per_launch': final_ms,
-                     'whole_forward_tflops': FLOPS_PER_PASS * B / (per_step * 1e-3) / 1e12,
+                     'whole_forward_tflops': FLOPS_PER_PASS * B * passes_per_sample / (per_step * 1e-3) / 1e12,
                      'voxelize': {'bound': 'hbm', 'achieved': VOXELIZE_BYTES * B / (vox_ms * 1e-3) / 1e9, 'peak': pk['hbm'],
                                   'unit': 'GB/s', 'frac': VOXELIZE_BYTES * B / (vox_ms * 1e-3) / 1e9 / pk['hbm'],
                                   'ms_per_call': vox_ms}},

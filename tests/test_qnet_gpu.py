@@ -127,6 +127,35 @@ def test_full_size_tensor_core_path_matches_fp32_path(cuda_lib):
     assert torch.equal(t0.reshape(2, -1).argmax(-1), t1.reshape(2, -1).argmax(-1))
 
 
+def test_dual_agent_acting_and_stabilizing_share_observations(cuda_lib):
+    """BASELINE config 3 shape of use: two encoders (low_dim 7, arm head; different weights) evaluated alternately
+    on the same observation batch.  Each must match the oracle run with ITS weights -- no state leaks between the
+    two instances (prepared weights, workspaces) across interleaved calls."""
+    c = make_golden.QNET_CASES['qnet_v20_arm_crop']
+    obs, enc_a, sd_a = util.make_case(c)
+    _, enc_s, sd_s = util.make_case(dict(c, seed=c['seed'] + 77))
+    obs_s = obs                                              # the stabilizing agent sees the same observations
+    dev = torch.device('cuda')
+    agents = []
+    for enc in (enc_a, enc_s):
+        vg = VoxelGrid(synth.SCENE_BOUNDS, c['V'], dev, c['B'], 3, c['cameras'] * c['H'] * c['W'])
+        agents.append(QFunction(enc, vg, 0.15, 5, dev, False, True).to(dev).eval())
+    rgb = [t.cuda() for t in obs_s['rgb']]
+    pcd = [t.cuda() for t in obs_s['pcd']]
+    rgb_pcd = [[r, p] for r, p in zip(rgb, pcd)]
+    args = (rgb_pcd, obs['proprio'].cuda(), pcd, obs['lang_goal_emb'].cuda(), obs['lang_token_embs'].cuda(),
+            obs['bounds'].cuda(), None, None)
+    outs = []
+    for _ in range(2):                                       # interleave: a, s, a, s
+        outs = [[t.clone() for t in a(*args)[:3]] for a in agents]
+    for (trans, rot_grip, coll), sd in zip(outs, (sd_a, sd_s)):
+        ref = qnet_oracle.qfunction_forward(sd, util.oracle_cfg(c), voxel_oracle.voxelize, obs['rgb'], obs['pcd'],
+                                            obs['proprio'], obs['lang_token_embs'], obs['bounds'], c['V'])
+        for ours, key in ((trans, 'trans'), (rot_grip, 'rot_grip'), (coll, 'collision')):
+            assert util.rel_err(ours, ref[key]) < util.Q_REL_TOL, key
+    assert util.rel_err(outs[0][0], outs[1][0]) > 1e-2       # the two agents really are different networks
+
+
 def test_checkpoint_roundtrip_and_deepcopy(cuda_lib, tmp_path):
     import copy
     c = make_golden.QNET_CASES['qnet_v20']

@@ -46,6 +46,45 @@ __device__ __forceinline__ void ss_update(SSState& st, float raw, float px, floa
   st.sy = fmaf(e, py, st.sy);
   st.sz = fmaf(e, pz, st.sz);
 }
+// Four channels at one position, lazily rescaled: the reference exponent m only moves when a value exceeds it by
+// more than kSSLazySlack (log2 domain), so e = 2^(t - m) <= 2^slack and the sums stay far inside the fp32 range
+// (<= 2^20 positions x 2^64); the common path is branch-free and the sums run as packed FFMA2 over channel pairs.
+constexpr float kSSLazySlack = 64.f;
+__device__ __forceinline__ void ss_update4_lazy(SSState (&st)[4], const float (&raw)[4], float px, float py, float pz) {
+  float t[4];
+  bool grow = false;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    st[j].rm = fmaxf(st[j].rm, raw[j]);
+    t[j] = raw[j] * kSSLog2eOverT;
+    grow |= t[j] > st[j].m + kSSLazySlack;      // m = -inf on the first element
+  }
+  // lanes of a warp may leave the position loop one iteration apart: vote over the lanes that are here (a lane's own
+  // flag is always part of its vote, so any subset is correct)
+  if (__any_sync(__activemask(), grow)) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (t[j] > st[j].m) {
+        const float sc = fast_exp2(st[j].m - t[j]);
+        st[j].s *= sc; st[j].sx *= sc; st[j].sy *= sc; st[j].sz *= sc;
+        st[j].m = t[j];
+      }
+    }
+  }
+  const float2 pxx = make_float2(px, px), pyy = make_float2(py, py), pzz = make_float2(pz, pz);
+#pragma unroll
+  for (int j = 0; j < 4; j += 2) {
+    const float2 e = make_float2(fast_exp2(t[j] - st[j].m), fast_exp2(t[j + 1] - st[j + 1].m));
+    const float2 s = __fadd2_rn(make_float2(st[j].s, st[j + 1].s), e);
+    const float2 sx = __ffma2_rn(e, pxx, make_float2(st[j].sx, st[j + 1].sx));
+    const float2 sy = __ffma2_rn(e, pyy, make_float2(st[j].sy, st[j + 1].sy));
+    const float2 sz = __ffma2_rn(e, pzz, make_float2(st[j].sz, st[j + 1].sz));
+    st[j].s = s.x; st[j + 1].s = s.y;
+    st[j].sx = sx.x; st[j + 1].sx = sx.y;
+    st[j].sy = sy.x; st[j + 1].sy = sy.y;
+    st[j].sz = sz.x; st[j + 1].sz = sz.y;
+  }
+}
 __device__ __forceinline__ void ss_merge(SSState& a, const SSState& b) {
   a.rm = fmaxf(a.rm, b.rm);
   const float M = fmaxf(a.m, b.m);
@@ -158,6 +197,11 @@ ss_merge_kernel(const float* __restrict__ partial, int chunks, int C, float* __r
 // their CIN x 4 weights live in registers), the activation is stored once and its soft-argmax / max
 // partials are accumulated on the fly -- d0 is never re-read.
 // ------------------------------------------------------------------------------------------------
+constexpr int IPP_ITERS = 8;     // positions per thread and tile
+constexpr int IPP_STAGES = 3;    // cp.async stages (prefetch distance 2 tiles)
+__host__ __device__ inline int ipp_stage_offset_floats(int lut_floats, int lanes) {
+  return (lut_floats + lanes * 24 + 3) & ~3;   // after the LUTs and the [PL][G][4][6] reduction buffer, 16-byte aligned
+}
 template <int CIN>
 static __global__ void __launch_bounds__(SS_THREADS)
 input_preprocess_ss_kernel(const float* __restrict__ x /*[B,P,CIN]*/, const float* __restrict__ w /*[C,CIN]*/,
@@ -181,65 +225,94 @@ input_preprocess_ss_kernel(const float* __restrict__ x /*[B,P,CIN]*/, const floa
 #pragma unroll
   for (int j = 0; j < 4; ++j) st[j] = {-INFINITY, 0.f, 0.f, 0.f, 0.f, -INFINITY};
   const int p_begin = ck * chunk, p_end = min(P, p_begin + chunk);
+  // The input rows of a tile of IPP_ITERS * PL consecutive positions are staged in shared memory with cp.async, two
+  // tiles ahead of the one being computed (the 40-byte rows are shared by the G threads of a position; loading them
+  // straight into registers one position ahead left the kernel waiting on DRAM latency).
+  const int TP = IPP_ITERS * PL;
+  float* stages = ss_smem + ipp_stage_offset_floats(Dd + Hh + Ww, PL * G);
+  const float* xb = x + (size_t)b * P * CIN;
+  const int tiles = (p_end - p_begin + TP - 1) / TP;
+  auto issue = [&](int t) {
+    if (t < tiles) {
+      const int tp0 = p_begin + t * TP;
+      const int n8 = min(TP, p_end - tp0) * (CIN / 2);            // 8-byte units (rows are CIN * 4 = 8-byte multiples)
+      const float* src = xb + (size_t)tp0 * CIN;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stages + (size_t)(t % IPP_STAGES) * TP * CIN);
+      for (int k = threadIdx.x; k < n8; k += SS_THREADS)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * k), "l"(src + 2 * k) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0);
+  issue(1);
+  // weights as (even, odd) input-channel pairs: the dot product runs as CIN/2 packed FFMA2 per output channel
+  static_assert(CIN % 2 == 0, "input rows are read as float2");
+  float2 wr[4][CIN / 2];
+  float br[4];
+  int p = p_begin + pl;
+  int d = p / (Hh * Ww), h = (p / Ww) % Hh, wv = p % Ww;
+  float4* yb = reinterpret_cast<float4*>(y + (size_t)b * P * C) + g;
+  // hi/lo planes of the replicate-padded grid [B, D+2, H+2, W+2, C] (interior; the halo is filled afterwards):
+  // the padded row offset is carried along with (d, h, wv) instead of being recomputed
+  const size_t pbase = (size_t)b * (Dd + 2) * (Hh + 2) * (Ww + 2) * C + g * 4;   // this sample, this channel group
+  __nv_bfloat16* phb = phi ? phi + pbase : nullptr;
+  __nv_bfloat16* plb = plo ? plo + pbase : nullptr;
+  // element offset of this position's padded row inside the sample (< 2^31 for any grid that fits the planes)
+  uint32_t poff = ((uint32_t)((d + 1) * (Hh + 2) + h + 1) * (uint32_t)(Ww + 2) + (uint32_t)wv + 1u) * (uint32_t)C;
+  const uint32_t step_w = (uint32_t)PL * C, wrap_w = 2u * C, wrap_h = 2u * (uint32_t)(Ww + 2) * C;
+  const float sl = slope >= 0.f ? slope : 1.f;          // max(v, v * sl) == LeakyReLU for 0 <= sl <= 1, identity for sl = 1
   if (pl < PL) {
-    float wr[4][CIN], br[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       br[j] = bias[g * 4 + j];
 #pragma unroll
-      for (int i = 0; i < CIN; ++i) wr[j][i] = w[(g * 4 + j) * CIN + i];
+      for (int i = 0; i < CIN / 2; ++i)
+        wr[j][i] = make_float2(w[(g * 4 + j) * CIN + 2 * i], w[(g * 4 + j) * CIN + 2 * i + 1]);
     }
-    int p = p_begin + pl;
-    int d = p / (Hh * Ww), h = (p / Ww) % Hh, wv = p % Ww;
-    const float* xb = x + (size_t)b * P * CIN;
-    float4* yb = reinterpret_cast<float4*>(y + (size_t)b * P * C) + g;
-    // software pipeline: the next position's inputs are in flight while this one is computed
-    static_assert(CIN % 2 == 0, "input rows are read as float2");
-    float2 nxt[CIN / 2];
-    if (p < p_end) {
+  }
+  for (int t = 0; t < tiles; ++t) {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");     // this thread's copies of tile t have landed
+    __syncthreads();                                          // everyone's have, and tile t-1 is fully consumed
+    issue(t + 2);                                             // into the stage tile t-1 used
+    if (pl < PL) {
+      const float2* xs = reinterpret_cast<const float2*>(stages + (size_t)(t % IPP_STAGES) * TP * CIN) + pl * (CIN / 2);
+#pragma unroll 2
+      for (int it = 0; it < IPP_ITERS; ++it) {
+        if (p >= p_end) break;
+        float2 in[CIN / 2];
 #pragma unroll
-      for (int i = 0; i < CIN / 2; ++i) nxt[i] = __ldg(reinterpret_cast<const float2*>(xb + (size_t)p * CIN) + i);
-    }
-    for (; p < p_end; p += PL) {
-      float in[CIN];
+        for (int i = 0; i < CIN / 2; ++i) in[i] = xs[(size_t)it * PL * (CIN / 2) + i];
+        float o[4];
 #pragma unroll
-      for (int i = 0; i < CIN / 2; ++i) { in[2 * i] = nxt[i].x; in[2 * i + 1] = nxt[i].y; }
-      if (p + PL < p_end) {
+        for (int j = 0; j < 4; ++j) {
+          float2 a = make_float2(br[j], 0.f);
 #pragma unroll
-        for (int i = 0; i < CIN / 2; ++i) nxt[i] = __ldg(reinterpret_cast<const float2*>(xb + (size_t)(p + PL) * CIN) + i);
-      }
-      float o[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float a = br[j];
-#pragma unroll
-        for (int i = 0; i < CIN; ++i) a = fmaf(in[i], wr[j][i], a);
-        o[j] = slope >= 0.f ? lrelu(a, slope) : a;
-      }
-      if (y) yb[(size_t)p * G] = make_float4(o[0], o[1], o[2], o[3]);
-      if (phi) {
-        // hi/lo planes of the replicate-padded grid [B, D+2, H+2, W+2, C] (interior; the halo is filled afterwards)
-        const size_t prow = (((size_t)b * (Dd + 2) + d + 1) * (Hh + 2) + h + 1) * (Ww + 2) + wv + 1;
-        const __nv_bfloat162 h01 = pl2_from_floats(o[0], o[1]), h23 = pl2_from_floats(o[2], o[3]);
-        const float2 f01 = pl2_to_float2(h01), f23 = pl2_to_float2(h23);
-        const __nv_bfloat162 l01 = pl2_from_floats(o[0] - f01.x, o[1] - f01.y);
-        const __nv_bfloat162 l23 = pl2_from_floats(o[2] - f23.x, o[3] - f23.y);
-        uint2 hv, lv;
-        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-        lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-        *reinterpret_cast<uint2*>(phi + prow * C + g * 4) = hv;
-        *reinterpret_cast<uint2*>(plo + prow * C + g * 4) = lv;
-      }
-      const float px = lutH[h], py = lutD[d], pz = lutW[wv];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) ss_update(st[j], o[j], px, py, pz);
-      wv += PL;
-      while (wv >= Ww) {
-        wv -= Ww;
-        if (++h >= Hh) { h = 0; ++d; }
+          for (int i = 0; i < CIN / 2; ++i) a = __ffma2_rn(in[i], wr[j][i], a);
+          const float v = a.x + a.y;
+          o[j] = fmaxf(v, v * sl);
+        }
+        if (y) yb[(size_t)p * G] = make_float4(o[0], o[1], o[2], o[3]);
+        if (phb) {
+          const __nv_bfloat162 h01 = pl2_from_floats(o[0], o[1]), h23 = pl2_from_floats(o[2], o[3]);
+          const float2 f01 = pl2_to_float2(h01), f23 = pl2_to_float2(h23);
+          const __nv_bfloat162 l01 = pl2_from_floats(o[0] - f01.x, o[1] - f01.y);
+          const __nv_bfloat162 l23 = pl2_from_floats(o[2] - f23.x, o[3] - f23.y);
+          uint2 hv, lv;
+          hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+          lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+          *reinterpret_cast<uint2*>(phb + poff) = hv;
+          *reinterpret_cast<uint2*>(plb + poff) = lv;
+        }
+        ss_update4_lazy(st, o, lutH[h], lutD[d], lutW[wv]);
+        p += PL; wv += PL; poff += step_w;
+        while (wv >= Ww) {
+          wv -= Ww; poff += wrap_w;
+          if (++h >= Hh) { h = 0; ++d; poff += wrap_h; }
+        }
       }
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   float* red = ss_smem + (Dd + Hh + Ww);
   if (pl < PL) {
 #pragma unroll
@@ -293,11 +366,13 @@ inline int input_preprocess_ss_run(const float* x, const float* w, const float* 
                                    float* partial, cudaStream_t st, __nv_bfloat16* phi = nullptr,
                                    __nv_bfloat16* plo = nullptr) {
   VXB_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 1024, "input_preprocess: C=%d must be a multiple of 4, <= 1024", C);
+  VXB_CHECK_ARG(slope <= 1.f, "input_preprocess: LeakyReLU slope %g must be <= 1 (negative = no activation)", (double)slope);
   const size_t P = (size_t)Dd * Hh * Ww;
   const int chunks = ss_num_chunks(P, B);
   const int chunk = (int)((P + chunks - 1) / chunks);
   const int G = C / 4, PL = SS_THREADS / G;
-  const size_t smem = ((size_t)(Dd + Hh + Ww) + (size_t)PL * G * 24) * sizeof(float);
+  const size_t smem = ((size_t)ipp_stage_offset_floats(Dd + Hh + Ww, PL * G) + (size_t)IPP_STAGES * IPP_ITERS * PL * CIN) * sizeof(float);
+  VXB_CHECK_ARG(smem <= 48 * 1024, "input_preprocess: %zu bytes of shared memory needed (C=%d, grid %dx%dx%d)", smem, C, Dd, Hh, Ww);
   input_preprocess_ss_kernel<CIN><<<dim3(chunks, B), SS_THREADS, smem, st>>>(x, w, bias, slope, y, (int)P, C, Dd, Hh, Ww,
                                                                             chunk, partial, phi, plo);
   VXB_LAUNCH_CHECK();
