@@ -17,7 +17,8 @@ namespace umma {
 
 constexpr int FA_THREADS = 320;               // TMA warp, MMA warp, 8 softmax warps (two per TMEM lane quarter)
 constexpr int FA_KT = 64;                        // keys per tile
-constexpr int FA_KVSTAGES = 3;
+constexpr int FA_KVSTAGES = 4;                   // K/V tiles j-2 .. j+1 are live while QK^T(j) and PV(j-2) are issued
+constexpr int FA_PV_LAG = 2;                     // PV trails QK^T by two key tiles
 constexpr int FA_QBYTES = 2 * 128 * 128;         // Q hi + lo
 constexpr int FA_KVBYTES = 4 * FA_KT * 128;      // K hi, K lo, Vt hi, Vt lo (64 rows x 128 B each)
 constexpr int FA_PBYTES = 2 * 128 * 128;         // P hi + lo
@@ -119,12 +120,16 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
     int st = 0;             // kv stage of the tile whose QK^T is issued next
     uint32_t ph = 0;
     int st_pv = 0;          // kv stage of the tile whose PV is issued next
-    uint32_t it = 0;        // global key-tile counter (S / P double buffers)
+    uint32_t it = 0;        // global counter of the tile whose QK^T is issued next (S / P double buffers)
+    uint32_t itp = 0;       // global counter of the tile whose PV is issued next
     uint32_t n = 0;
+    // Issue order per item: QK(0) QK(1) | QK(2) PV(0) | QK(3) PV(1) | ... | PV(kt-2) PV(kt-1).  PV trails QK^T by TWO
+    // tiles: the softmax of a tile (TMEM load, exp, split, st.shared, proxy fence ~ 2 MMA tile times) then has two
+    // issue slots to finish before its P is needed, and the two softmax groups (alternate tiles) both stay busy.
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
       mbar_wait(q_full, n & 1);
       tc_fence_after();
-      for (int j = 0; j <= p.k_tiles; ++j) {
+      for (int j = 0; j < p.k_tiles + FA_PV_LAG; ++j) {
         if (j < p.k_tiles) {
           // ---- S(j) = Q K_j^T into S buffer (it & 1)
           const uint32_t sb = it & 1u;
@@ -144,12 +149,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
           }
           __syncwarp();
           if (++st == FA_KVSTAGES) { st = 0; ph ^= 1; }
+          ++it;
         }
-        if (j >= 1) {
-          // ---- O += P(j-1) V_{j-1}
-          const uint32_t itp = it - 1u;                        // counter of tile j-1 (it = tiles whose QK^T has been issued, minus this one)
+        if (j >= FA_PV_LAG) {
+          // ---- O += P(jt) V_jt, jt = j - FA_PV_LAG
+          const int jt = j - FA_PV_LAG;
           const uint32_t pb = itp & 1u;
-          if (j == 1) {
+          if (jt == 0) {
             mbar_wait(o_empty, (n & 1) ^ 1);                   // previous item's O has been read out
             tc_fence_after();
           }
@@ -161,17 +167,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
           if (leader) {
 #pragma unroll
             for (int ks = 0; ks < FA_KT / 16; ++ks) {
-              tc_mma_bf16_lo(d_o, p_hi + 2 * ks, vb + 2 * ks, kDescHi, idesc128, (j > 1 || ks != 0));   // hi*hi | hi*lo
-              tc_mma_bf16_lo(d_o, p_lo + 2 * ks, vb + 2 * ks, kDescHi, idesc64, 1);                     // lo*hi
+              tc_mma_bf16_lo(d_o, p_hi + 2 * ks, vb + 2 * ks, kDescHi, idesc128, (jt > 0 || ks != 0));   // hi*hi | hi*lo
+              tc_mma_bf16_lo(d_o, p_lo + 2 * ks, vb + 2 * ks, kDescHi, idesc64, 1);                      // lo*hi
             }
             tc_commit(&p_empty[pb]);
             tc_commit(&kv_empty[st_pv]);
-            if (j == p.k_tiles) tc_commit(o_full);
+            if (jt == p.k_tiles - 1) tc_commit(o_full);
           }
           __syncwarp();
           if (++st_pv == FA_KVSTAGES) st_pv = 0;
+          ++itp;
         }
-        if (j < p.k_tiles) ++it;
       }
     }
   } else {
@@ -193,7 +199,6 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
         if (sb != (uint32_t)c) continue;                       // the other group's tile
         mbar_wait(&s_full[sb], (it >> 1) & 1u);
         tc_fence_after();
-        mbar_wait(&p_empty[sb], ((it >> 1) & 1u) ^ 1u);        // PV of this group's previous tile has consumed the P buffer
         uint8_t* ph_row = p_s + sb * FA_PBYTES + r * 128;
         uint8_t* pl_row = ph_row + 128 * 128;
         const int key0 = j * FA_KT;
@@ -202,6 +207,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
           uint32_t v0[32], v1[32];
           tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + sb * 128u + (uint32_t)(cc * 32), v0);
           tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + sb * 128u + 64u + (uint32_t)(cc * 32), v1);
+          if (cc == 0) mbar_wait(&p_empty[sb], ((it >> 1) & 1u) ^ 1u);   // PV of this group's previous tile has consumed the P buffer
           const bool full = key0 + cc * 32 + 31 < p.Nk;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {                        // 8 keys = one 16-byte chunk per plane

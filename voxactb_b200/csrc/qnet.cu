@@ -781,7 +781,7 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
       tail.ptap2 = w.u + (size_t)B * 27 * m.V3;
     }
     tail.ss = w.feats + off; tail.ss_stride = m.flat; tail.mx = w.feats + off + 192; tail.mx_stride = m.flat;
-    g_launches += 2;
+    g_launches += 4 + (d->two_robots ? 1 : 0);   // conv + gather(s) + two-level partial merge
     VXB_TRY(umma::conv3_planes(d0p, &u0p, 64, 64, pw.final_wc, P(VXB_P_FINAL_B), slope, nullptr, B, m.V, st, &tail));
     STAGE_MARK();  // 9: trans decoder gather + ss_final merge (their first halves ran in the conv epilogue)
     VXB_TRY(umma::conv3_tail_finish(tail, B, m.V, st));

@@ -160,16 +160,21 @@ ss_partial_kernel(const float* __restrict__ x, int P, int C, int Dd, int Hh, int
   }
 }
 
-// grid (ceil(C/32), B), 256 threads = 32 channels x 8 chunk lanes
+// grid (ceil(C/32), B, splits), 256 threads = 32 channels x 8 chunk lanes.  splits == 1: final result (soft-argmax
+// coordinates + max).  splits > 1: block z folds its share of the chunks into partial_out [B][splits][6][C] (same
+// layout, merged by a second launch) -- the fused conv tail leaves thousands of chunk partials per sample.
 static __global__ void __launch_bounds__(256)
 ss_merge_kernel(const float* __restrict__ partial, int chunks, int C, float* __restrict__ ss,
-                int ss_stride, float* __restrict__ mx, int mx_stride) {
+                int ss_stride, float* __restrict__ mx, int mx_stride, float* __restrict__ partial_out) {
   const int b = blockIdx.y;
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int kl = threadIdx.x >> 5;
+  const int splits = gridDim.z;
+  const int per = (chunks + splits - 1) / splits;
+  const int k_lo = blockIdx.z * per, k_hi = min(chunks, k_lo + per);
   SSState a = {-INFINITY, 0.f, 0.f, 0.f, 0.f, -INFINITY};
   if (c < C) {
-    for (int k = kl; k < chunks; k += 8) {
+    for (int k = k_lo + kl; k < k_hi; k += 8) {
       const float* q = partial + (((size_t)b * chunks + k) * 6) * C + c;
       const SSState o = {q[0], q[C], q[2 * C], q[3 * C], q[4 * C], q[5 * C]};
       ss_merge(a, o);
@@ -185,9 +190,14 @@ ss_merge_kernel(const float* __restrict__ partial, int chunks, int C, float* __r
       const SSState o = {q[0], q[1], q[2], q[3], q[4], q[5]};
       ss_merge(a, o);
     }
-    float* o = ss + (size_t)b * ss_stride + c * 3;
-    o[0] = a.sx / a.s; o[1] = a.sy / a.s; o[2] = a.sz / a.s;
-    if (mx) mx[(size_t)b * mx_stride + c] = a.rm;  // AdaptiveMaxPool3d(1)
+    if (partial_out) {
+      float* o = partial_out + (((size_t)b * splits + blockIdx.z) * 6) * C + c;
+      o[0] = a.m; o[C] = a.s; o[2 * C] = a.sx; o[3 * C] = a.sy; o[4 * C] = a.sz; o[5 * C] = a.rm;
+    } else {
+      float* o = ss + (size_t)b * ss_stride + c * 3;
+      o[0] = a.sx / a.s; o[1] = a.sy / a.s; o[2] = a.sz / a.s;
+      if (mx) mx[(size_t)b * mx_stride + c] = a.rm;  // AdaptiveMaxPool3d(1)
+    }
   }
 }
 
@@ -354,7 +364,7 @@ inline int spatial_softmax_run(const float* x, int B, int Dd, int Hh, int Ww, in
   const size_t smem = ((size_t)(Dd + Hh + Ww) + (size_t)PL * G * 24) * sizeof(float);
   ss_partial_kernel<<<dim3(chunks, B), SS_THREADS, smem, st>>>(x, (int)P, C, Dd, Hh, Ww, chunk, partial);
   VXB_LAUNCH_CHECK();
-  ss_merge_kernel<<<dim3(cdiv(C, 32), B), 256, 0, st>>>(partial, chunks, C, ss, ss_stride, mx, mx_stride);
+  ss_merge_kernel<<<dim3(cdiv(C, 32), B), 256, 0, st>>>(partial, chunks, C, ss, ss_stride, mx, mx_stride, nullptr);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }
@@ -376,7 +386,7 @@ inline int input_preprocess_ss_run(const float* x, const float* w, const float* 
   input_preprocess_ss_kernel<CIN><<<dim3(chunks, B), SS_THREADS, smem, st>>>(x, w, bias, slope, y, (int)P, C, Dd, Hh, Ww,
                                                                             chunk, partial, phi, plo);
   VXB_LAUNCH_CHECK();
-  ss_merge_kernel<<<dim3(cdiv(C, 32), B), 256, 0, st>>>(partial, chunks, C, ss, ss_stride, mx, mx_stride);
+  ss_merge_kernel<<<dim3(cdiv(C, 32), B), 256, 0, st>>>(partial, chunks, C, ss, ss_stride, mx, mx_stride, nullptr);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }

@@ -247,14 +247,72 @@ layernorm_planes_kernel(const float* __restrict__ x, size_t x_batch_stride, int 
   }
 }
 
+// Same arithmetic with the row held in registers (n = CH * 256): x is read once instead of three times.
+template <int CH>
+static __global__ void __launch_bounds__(256)
+layernorm_planes_reg_kernel(const float* __restrict__ x, size_t x_batch_stride, int rows_per_batch,
+                            const float* __restrict__ w, const float* __restrict__ b,
+                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldp, long long rows) {
+  constexpr int n = CH * 256;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)(row / rows_per_batch) * x_batch_stride + (size_t)(row % rows_per_batch) * n;
+  float4 v[CH][2];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    v[c][0] = *reinterpret_cast<const float4*>(xr + c * 256 + lane * 8);
+    v[c][1] = *reinterpret_cast<const float4*>(xr + c * 256 + lane * 8 + 4);
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+    s += (v[c][0].x + v[c][0].y + v[c][0].z + v[c][0].w) + (v[c][1].x + v[c][1].y + v[c][1].z + v[c][1].w);
+  s = warp_sum(s);
+  const float mean = s / (float)n;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const float d0 = v[c][0].x - mean, d1 = v[c][0].y - mean, d2 = v[c][0].z - mean, d3 = v[c][0].w - mean;
+    const float d4 = v[c][1].x - mean, d5 = v[c][1].y - mean, d6 = v[c][1].z - mean, d7 = v[c][1].w - mean;
+    q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3 + d4 * d4 + d5 * d5 + d6 * d6 + d7 * d7;
+  }
+  q = warp_sum(q);
+  const float rstd = rsqrtf(q / (float)n + 1e-5f);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int i = c * 256 + lane * 8;
+    const float4 w0 = *reinterpret_cast<const float4*>(w + i), w1 = *reinterpret_cast<const float4*>(w + i + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(b + i), b1 = *reinterpret_cast<const float4*>(b + i + 4);
+    float f[8];
+    f[0] = (v[c][0].x - mean) * rstd * w0.x + b0.x; f[1] = (v[c][0].y - mean) * rstd * w0.y + b0.y;
+    f[2] = (v[c][0].z - mean) * rstd * w0.z + b0.z; f[3] = (v[c][0].w - mean) * rstd * w0.w + b0.w;
+    f[4] = (v[c][1].x - mean) * rstd * w1.x + b1.x; f[5] = (v[c][1].y - mean) * rstd * w1.y + b1.y;
+    f[6] = (v[c][1].z - mean) * rstd * w1.z + b1.z; f[7] = (v[c][1].w - mean) * rstd * w1.w + b1.w;
+    uint4 hh, ll;
+    split8(f, hh, ll);
+    *reinterpret_cast<uint4*>(hi + row * ldp + i) = hh;
+    *reinterpret_cast<uint4*>(lo + row * ldp + i) = ll;
+  }
+}
+
 int layernorm_planes(const float* x, size_t x_batch_stride, int rows_per_batch, const float* w, const float* b,
                      Planes out, long long rows, int n, cudaStream_t st) {
   if (n % 8 || out.ld < n) {
     set_error("layernorm_planes: n must be a multiple of 8 (n=%d)", n);
     return VXB_E_BADARG;
   }
-  layernorm_planes_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, x_batch_stride, rows_per_batch, w, b, out.hi, out.lo, out.ld,
-                                                        rows, n);
+  const bool aligned = !(((uintptr_t)w | (uintptr_t)b) & 15);
+  if (n == 512 && aligned) {
+    layernorm_planes_reg_kernel<2><<<cdiv(rows, 8), 256, 0, st>>>(x, x_batch_stride, rows_per_batch, w, b, out.hi, out.lo,
+                                                                  out.ld, rows);
+  } else if (n == 256 && aligned) {
+    layernorm_planes_reg_kernel<1><<<cdiv(rows, 8), 256, 0, st>>>(x, x_batch_stride, rows_per_batch, w, b, out.hi, out.lo,
+                                                                  out.ld, rows);
+  } else {
+    layernorm_planes_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, x_batch_stride, rows_per_batch, w, b, out.hi, out.lo, out.ld,
+                                                          rows, n);
+  }
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }
@@ -832,10 +890,11 @@ static void conv3_plan(int B, int V, int cl, int& tiles, int& lz, int& zchunks) 
   zchunks = cdiv(V, lz);
 }
 
+constexpr int kTailMergeSplits = 32;
 size_t conv3_tail_partial_floats(int B, int V) {
   int tiles, lz, zchunks;
   conv3_plan(B, V, conv3_cluster(), tiles, lz, zchunks);
-  return (size_t)B * zchunks * tiles * 16 * 6 * 64;
+  return (size_t)B * (zchunks * tiles * 16 + kTailMergeSplits) * 6 * 64;   // chunk partials + the first merge level
 }
 
 // trans[b, v] = bias + sum_t ptap[b][t][clamp(v + offset_t)]   (replicate padding of the 3x3x3 stencil)
@@ -944,7 +1003,11 @@ int conv3_tail_finish(const ConvTail& tail, int B, int V, cudaStream_t st) {
     VXB_LAUNCH_CHECK();
   }
   const int chunks = zchunks * tiles * 16;
-  ss_merge_kernel<<<dim3(cdiv(64, 32), B), 256, 0, st>>>(tail.ss_partial, chunks, 64, tail.ss, tail.ss_stride, tail.mx, tail.mx_stride);
+  // two-level merge: 32 slices of the chunk list per sample, then the slices
+  float* level1 = tail.ss_partial + (size_t)B * chunks * 6 * 64;
+  ss_merge_kernel<<<dim3(cdiv(64, 32), B, kTailMergeSplits), 256, 0, st>>>(tail.ss_partial, chunks, 64, nullptr, 0, nullptr, 0, level1);
+  VXB_LAUNCH_CHECK();
+  ss_merge_kernel<<<dim3(cdiv(64, 32), B), 256, 0, st>>>(level1, kTailMergeSplits, 64, tail.ss, tail.ss_stride, tail.mx, tail.mx_stride, nullptr);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }
