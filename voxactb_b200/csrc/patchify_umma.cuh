@@ -16,7 +16,8 @@ namespace vxb {
 namespace umma {
 
 constexpr int PF_THREADS = 192;
-constexpr int PF_ASTAGES = 3;                 // 32 KB each (hi + lo planes of 128 rows x 128 B)
+constexpr int PF_ASTAGES = 5;                 // 32 KB each (hi + lo planes of 128 rows x 128 B)
+constexpr int PF_DIST = 4;                    // cp.async prefetch distance in stages (< PF_ASTAGES)
 constexpr int PF_WSTAGES = 3;                 // 16 KB each ([W_hi ; W_lo] x 64 channels)
 constexpr int PF_ABYTES = 2 * 128 * 128;
 constexpr int PF_WBYTES = 128 * 128;
@@ -97,6 +98,43 @@ patchify_umma_kernel(const __grid_constant__ CUtensorMap mapW, const PatchifyPar
     int st = 0;
     uint32_t ph = 0, accph = 0;
     const int S = p.S, V = p.V;
+    // PLANES: the gather runs as cp.async (16 B, straight into the swizzled stage) PF_DIST (tile, tap) steps ahead of
+    // the step being handed to the MMA warp, across tile boundaries -- PF_DIST x 32 KB in flight per SM.
+    [[maybe_unused]] int is_tile = blockIdx.x, is_tap = 0, is_st = 0;
+    [[maybe_unused]] uint32_t is_ph = 0;
+    [[maybe_unused]] auto issue = [&]() {
+      if constexpr (PLANES) {
+        if (is_tile < p.tiles) {
+          const int tk = is_tile * 128 + r;
+          const bool ok = tk < p.tokens;
+          const int tkc = ok ? tk : 0;
+          const int ow_ = tkc % S, oh_ = (tkc / S) % S, od_ = (tkc / (S * S)) % S, b_ = tkc / (S * S * S);
+          const int tw = is_tap % p.k, th = (is_tap / p.k) % p.k, td = is_tap / (p.k * p.k);
+          const int vd = min(max(od_ * p.s - p.pad + td, 0), V - 1), vh = min(max(oh_ * p.s - p.pad + th, 0), V - 1),
+                    vw = min(max(ow_ * p.s - p.pad + tw, 0), V - 1);
+          const int Vp = V + 2;
+          const size_t o = ((((size_t)b_ * Vp + vd + 1) * Vp + vh + 1) * Vp + vw + 1) * 64;
+          const uint32_t nbytes = ok ? 16u : 0u;                   // src-size 0 = zero fill (rows past the last token)
+          mbar_wait(&a_empty[is_st], is_ph ^ 1);
+          const uint32_t sa = smem_u32(a_base + is_st * PF_ABYTES) + r * 128;
+          const __nv_bfloat16* gh = p.xhi + o;
+          const __nv_bfloat16* gl = p.xlo + o;
+#pragma unroll
+          for (int cidx = 0; cidx < 8; ++cidx) {
+            const uint32_t off = (uint32_t)((cidx ^ (r & 7)) * 16);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa + off), "l"(gh + cidx * 8), "r"(nbytes) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa + 128 * 128 + off), "l"(gl + cidx * 8), "r"(nbytes) : "memory");
+          }
+          if (++is_st == PF_ASTAGES) { is_st = 0; is_ph ^= 1; }
+          if (++is_tap == k3) { is_tap = 0; is_tile += gridDim.x; }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+    };
+    if constexpr (PLANES) {
+#pragma unroll 1
+      for (int i = 0; i < PF_DIST; ++i) issue();
+    }
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
       const int tok = tile * 128 + r;
       const bool valid = tok < p.tokens;
@@ -106,46 +144,13 @@ patchify_umma_kernel(const __grid_constant__ CUtensorMap mapW, const PatchifyPar
       }
       const int d0 = od * p.s - p.pad, h0 = oh * p.s - p.pad, w0 = ow * p.s - p.pad;
       if constexpr (PLANES) {
-        const int Vp = V + 2;
-        auto src = [&](int tap) -> size_t {
-          const int tw = tap % p.k, th = (tap / p.k) % p.k, td = tap / (p.k * p.k);
-          const int vd = min(max(d0 + td, 0), V - 1), vh = min(max(h0 + th, 0), V - 1), vw = min(max(w0 + tw, 0), V - 1);
-          return ((((size_t)b * Vp + vd + 1) * Vp + vh + 1) * Vp + vw + 1) * 64;
-        };
-        uint4 ch[8], cl[8];
-        {
-          const size_t o = src(0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            ch[j] = valid ? __ldg(reinterpret_cast<const uint4*>(p.xhi + o) + j) : make_uint4(0, 0, 0, 0);
-            cl[j] = valid ? __ldg(reinterpret_cast<const uint4*>(p.xlo + o) + j) : make_uint4(0, 0, 0, 0);
-          }
-        }
+#pragma unroll 1
         for (int tap = 0; tap < k3; ++tap) {
-          uint4 nh[8], nl[8];
-          if (tap + 1 < k3) {
-            const size_t o = src(tap + 1);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              nh[j] = valid ? __ldg(reinterpret_cast<const uint4*>(p.xhi + o) + j) : make_uint4(0, 0, 0, 0);
-              nl[j] = valid ? __ldg(reinterpret_cast<const uint4*>(p.xlo + o) + j) : make_uint4(0, 0, 0, 0);
-            }
-          }
-          mbar_wait(&a_empty[st], ph ^ 1);
-          uint8_t* sa = a_base + st * PF_ABYTES;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int off = (c ^ (r & 7)) * 16;
-            *reinterpret_cast<uint4*>(sa + r * 128 + off) = ch[c];
-            *reinterpret_cast<uint4*>(sa + 128 * 128 + r * 128 + off) = cl[c];
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05
+          asm volatile("cp.async.wait_group %0;" ::"n"(PF_DIST - 1) : "memory");   // this step's rows have landed
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");             // generic-proxy writes -> visible to tcgen05
           mbar_arrive(&a_full[st]);
           if (++st == PF_ASTAGES) { st = 0; ph ^= 1; }
-          if (tap + 1 < k3) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { ch[j] = nh[j]; cl[j] = nl[j]; }
-          }
+          issue();                                                                 // step + PF_DIST, into the stage the MMA of step - 1 frees
         }
       } else {
       const float* xb = p.x + (size_t)b * V * V * V * 64;
