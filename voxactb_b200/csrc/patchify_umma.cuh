@@ -100,30 +100,42 @@ patchify_umma_kernel(const __grid_constant__ CUtensorMap mapW, const PatchifyPar
     const int S = p.S, V = p.V;
     // PLANES: the gather runs as cp.async (16 B, straight into the swizzled stage) PF_DIST (tile, tap) steps ahead of
     // the step being handed to the MMA warp, across tile boundaries -- PF_DIST x 32 KB in flight per SM.
+    // Eight consecutive lanes fetch the eight 16-byte chunks of one token row (a full 128-byte line per plane), so a
+    // warp-wide cp.async touches 4 rows x 128 B; a thread serves rows (warp*32 + i*4 + lane/8), i = 0..7.
     [[maybe_unused]] int is_tile = blockIdx.x, is_tap = 0, is_st = 0;
     [[maybe_unused]] uint32_t is_ph = 0;
+    [[maybe_unused]] uint32_t rs_pos[8];       // per served row: od*s | oh*s << 10 | ow*s << 20 | valid << 31
+    [[maybe_unused]] int rs_b[8];              // batch index
     [[maybe_unused]] auto issue = [&]() {
       if constexpr (PLANES) {
         if (is_tile < p.tiles) {
-          const int tk = is_tile * 128 + r;
-          const bool ok = tk < p.tokens;
-          const int tkc = ok ? tk : 0;
-          const int ow_ = tkc % S, oh_ = (tkc / S) % S, od_ = (tkc / (S * S)) % S, b_ = tkc / (S * S * S);
-          const int tw = is_tap % p.k, th = (is_tap / p.k) % p.k, td = is_tap / (p.k * p.k);
-          const int vd = min(max(od_ * p.s - p.pad + td, 0), V - 1), vh = min(max(oh_ * p.s - p.pad + th, 0), V - 1),
-                    vw = min(max(ow_ * p.s - p.pad + tw, 0), V - 1);
-          const int Vp = V + 2;
-          const size_t o = ((((size_t)b_ * Vp + vd + 1) * Vp + vh + 1) * Vp + vw + 1) * 64;
-          const uint32_t nbytes = ok ? 16u : 0u;                   // src-size 0 = zero fill (rows past the last token)
-          mbar_wait(&a_empty[is_st], is_ph ^ 1);
-          const uint32_t sa = smem_u32(a_base + is_st * PF_ABYTES) + r * 128;
-          const __nv_bfloat16* gh = p.xhi + o;
-          const __nv_bfloat16* gl = p.xlo + o;
+          const int chunk = lane & 7, sub = lane >> 3;
+          if (is_tap == 0) {
 #pragma unroll
-          for (int cidx = 0; cidx < 8; ++cidx) {
-            const uint32_t off = (uint32_t)((cidx ^ (r & 7)) * 16);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa + off), "l"(gh + cidx * 8), "r"(nbytes) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa + 128 * 128 + off), "l"(gl + cidx * 8), "r"(nbytes) : "memory");
+            for (int i = 0; i < 8; ++i) {
+              const int tk = is_tile * 128 + warp * 32 + i * 4 + sub;
+              const bool ok = tk < p.tokens;
+              const int tkc = ok ? tk : 0;
+              const int ow_ = tkc % S, oh_ = (tkc / S) % S, od_ = (tkc / (S * S)) % S;
+              rs_b[i] = tkc / (S * S * S);
+              rs_pos[i] = (uint32_t)(od_ * p.s) | ((uint32_t)(oh_ * p.s) << 10) | ((uint32_t)(ow_ * p.s) << 20) | (ok ? 0x80000000u : 0u);
+            }
+          }
+          const int tw = is_tap % p.k - p.pad, th = (is_tap / p.k) % p.k - p.pad, td = is_tap / (p.k * p.k) - p.pad;
+          const int Vp = V + 2;
+          mbar_wait(&a_empty[is_st], is_ph ^ 1);
+          const uint32_t sa = smem_u32(a_base + is_st * PF_ABYTES);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = warp * 32 + i * 4 + sub;
+            const uint32_t ps = rs_pos[i];
+            const int vd = min(max((int)(ps & 1023u) + td, 0), V - 1), vh = min(max((int)((ps >> 10) & 1023u) + th, 0), V - 1),
+                      vw = min(max((int)((ps >> 20) & 1023u) + tw, 0), V - 1);
+            const size_t o = ((((size_t)rs_b[i] * Vp + vd + 1) * Vp + vh + 1) * Vp + vw + 1) * 64 + chunk * 8;
+            const uint32_t nbytes = (ps >> 31) ? 16u : 0u;         // src-size 0 = zero fill (rows past the last token)
+            const uint32_t dst = sa + row * 128 + (uint32_t)((chunk ^ (row & 7)) * 16);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(p.xhi + o), "r"(nbytes) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 128 * 128), "l"(p.xlo + o), "r"(nbytes) : "memory");
           }
           if (++is_st == PF_ASTAGES) { is_st = 0; is_ph ^= 1; }
           if (++is_tap == k3) { is_tap = 0; is_tile += gridDim.x; }

@@ -1041,7 +1041,7 @@ int patchify_f32(const float* x, const __nv_bfloat16* wc, const float* bias, flo
   const int pad = k / 2;
   const int S = (V + 2 * pad - k) / s + 1;
   if (S <= 0 || (!xplanes && (!x || ((uintptr_t)x & 15))) || ((uintptr_t)out & 15) || ((uintptr_t)bias & 15) ||
-      (xplanes && xplanes->ld != 64)) {
+      (xplanes && (xplanes->ld != 64 || V > 1023))) {      // plane gather packs voxel coordinates in 10 bits
     set_error("patchify: bad geometry or unaligned pointers");
     return VXB_E_BADARG;
   }
