@@ -10,6 +10,7 @@
 // The QK^T MMAs of tile j are issued before the PV MMAs of tile j-1, so the tensor pipe works while the softmax
 // warps convert the previous tile.  Warps: 0 = TMA producer, 1 = MMA issuer, 2-5 = softmax + epilogue.
 #pragma once
+#include <type_traits>
 #include "umma_gemm.cuh"
 
 namespace vxb {
@@ -193,7 +194,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       const bool row_ok = qi < p.Nq;
       const float m = row_ok ? p.rowmax[(size_t)bh * p.Nq + qi] : 0.f;
       const float bias = VXB_P_EXP_BIAS - m;
-      float row_sum = 0.f;
+      float2 rs2 = make_float2(0.f, 0.f);                      // row sum as two interleaved partials (packed adds)
       for (int j = 0; j < p.k_tiles; ++j, ++it) {
         const uint32_t sb = it & 1u;
         if (sb != (uint32_t)c) continue;                       // the other group's tile
@@ -208,35 +209,43 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
           tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + sb * 128u + (uint32_t)(cc * 32), v0);
           tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + sb * 128u + 64u + (uint32_t)(cc * 32), v1);
           if (cc == 0) mbar_wait(&p_empty[sb], ((it >> 1) & 1u) ^ 1u);   // PV of this group's previous tile has consumed the P buffer
-          const bool full = key0 + cc * 32 + 31 < p.Nk;
+          // The softmax warps are issue-bound (two warps per scheduler): everything runs on register PAIRS with the
+          // packed fp32 instructions (FADD2 / FFMA2), and the key mask only exists in the ragged last tile.
+          const float2 alpha2 = make_float2(p.alpha, p.alpha), bias2 = make_float2(bias, bias), neg1 = make_float2(-1.f, -1.f);
+          auto chunk = [&](auto masked_tag) {
+            constexpr bool kMasked = decltype(masked_tag)::value;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {                        // 8 keys = one 16-byte chunk per plane
-            float pv[8];
+            for (int g = 0; g < 4; ++g) {                      // 8 keys = one 16-byte chunk per plane
+              uint4 hv, lv;
+              uint32_t* hp = reinterpret_cast<uint32_t*>(&hv);
+              uint32_t* lp = reinterpret_cast<uint32_t*>(&lv);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int jj = g * 8 + e;
-              const float s = __uint_as_float(v0[jj]) + __uint_as_float(v1[jj]);
-              float t;
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(s, p.alpha, bias)));
-              if (!full) t = (key0 + cc * 32 + jj < p.Nk) ? t : 0.f;
-              row_sum += t;
-              pv[e] = t;
+              for (int e = 0; e < 4; ++e) {
+                const int jj = g * 8 + 2 * e;
+                const float2 sv = __fadd2_rn(make_float2(__uint_as_float(v0[jj]), __uint_as_float(v0[jj + 1])),
+                                             make_float2(__uint_as_float(v1[jj]), __uint_as_float(v1[jj + 1])));
+                const float2 ar = __ffma2_rn(sv, alpha2, bias2);
+                float2 t;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(ar.x));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(ar.y));
+                if constexpr (kMasked) {
+                  t.x = (key0 + cc * 32 + jj < p.Nk) ? t.x : 0.f;
+                  t.y = (key0 + cc * 32 + jj + 1 < p.Nk) ? t.y : 0.f;
+                }
+                rs2 = __fadd2_rn(rs2, t);
+                const __nv_bfloat162 hh = pl2_from_floats(t.x, t.y);
+                const float2 lo2 = __ffma2_rn(pl2_to_float2(hh), neg1, t);      // t - float(hi), exact
+                const __nv_bfloat162 ll = pl2_from_floats(lo2.x, lo2.y);
+                hp[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                lp[e] = *reinterpret_cast<const uint32_t*>(&ll);
+              }
+              const int off = ((cc * 4 + g) ^ (r & 7)) * 16;
+              *reinterpret_cast<uint4*>(ph_row + off) = hv;
+              *reinterpret_cast<uint4*>(pl_row + off) = lv;
             }
-            uint4 hv, lv;
-            uint32_t* hp = reinterpret_cast<uint32_t*>(&hv);
-            uint32_t* lp = reinterpret_cast<uint32_t*>(&lv);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const __nv_bfloat162 hh = pl2_from_floats(pv[2 * e], pv[2 * e + 1]);
-              const float2 ff = pl2_to_float2(hh);
-              const __nv_bfloat162 ll = pl2_from_floats(pv[2 * e] - ff.x, pv[2 * e + 1] - ff.y);
-              hp[e] = *reinterpret_cast<const uint32_t*>(&hh);
-              lp[e] = *reinterpret_cast<const uint32_t*>(&ll);
-            }
-            const int off = ((cc * 4 + g) ^ (r & 7)) * 16;
-            *reinterpret_cast<uint4*>(ph_row + off) = hv;
-            *reinterpret_cast<uint4*>(pl_row + off) = lv;
-          }
+          };
+          if (key0 + cc * 32 + 31 < p.Nk) chunk(std::false_type{});
+          else chunk(std::true_type{});
         }
         tc_fence_before();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P writes -> visible to the tensor core
@@ -247,7 +256,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       mbar_wait(o_full, n & 1);
       tc_fence_after();
       // the two key halves of a row live in different warps: exchange the partial sums through shared memory
-      rs_part[c][r] = row_sum;
+      rs_part[c][r] = rs2.x + rs2.y;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float inv = 1.f / (rs_part[0][r] + rs_part[1][r]);
       __nv_bfloat16* oh = p.out_hi + ((size_t)b * p.Nq + qi) * p.ldo + (size_t)h * p.dh;
