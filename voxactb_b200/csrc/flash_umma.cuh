@@ -203,12 +203,26 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
         uint8_t* ph_row = p_s + sb * FA_PBYTES + r * 128;
         uint8_t* pl_row = ph_row + 128 * 128;
         const int key0 = j * FA_KT;
+        // S(tile) -> registers: both 32-key halves, hi*hi|lo*hi columns + hi*lo columns summed on the way in, then the
+        // S buffer goes straight back to the MMA warp (QK^T of this group's next tile does not wait for the exps)
+        float2 sv2[2][16];
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           uint32_t v0[32], v1[32];
-          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + sb * 128u + (uint32_t)(cc * 32), v0);
-          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + sb * 128u + 64u + (uint32_t)(cc * 32), v1);
-          if (cc == 0) mbar_wait(&p_empty[sb], ((it >> 1) & 1u) ^ 1u);   // PV of this group's previous tile has consumed the P buffer
+          tc_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + sb * 128u + (uint32_t)(cc * 32), v0);
+          tc_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + sb * 128u + 64u + (uint32_t)(cc * 32), v1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            sv2[cc][e] = __fadd2_rn(make_float2(__uint_as_float(v0[2 * e]), __uint_as_float(v0[2 * e + 1])),
+                                    make_float2(__uint_as_float(v1[2 * e]), __uint_as_float(v1[2 * e + 1])));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[sb]);
+        mbar_wait(&p_empty[sb], ((it >> 1) & 1u) ^ 1u);        // PV of this group's previous tile has consumed the P buffer
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
           // The softmax warps are issue-bound (two warps per scheduler): everything runs on register PAIRS with the
           // packed fp32 instructions (FADD2 / FFMA2), and the key mask only exists in the ragged last tile.
           const float2 alpha2 = make_float2(p.alpha, p.alpha), bias2 = make_float2(bias, bias), neg1 = make_float2(-1.f, -1.f);
@@ -222,9 +236,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int jj = g * 8 + 2 * e;
-                const float2 sv = __fadd2_rn(make_float2(__uint_as_float(v0[jj]), __uint_as_float(v0[jj + 1])),
-                                             make_float2(__uint_as_float(v1[jj]), __uint_as_float(v1[jj + 1])));
-                const float2 ar = __ffma2_rn(sv, alpha2, bias2);
+                const float2 ar = __ffma2_rn(sv2[cc][g * 4 + e], alpha2, bias2);
                 float2 t;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(ar.x));
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(ar.y));
@@ -250,7 +262,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
         tc_fence_before();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P writes -> visible to the tensor core
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&s_empty[sb]); mbar_arrive(&p_full[sb]); }
+        if (lane == 0) mbar_arrive(&p_full[sb]);
       }
       // ---- O / row_sum -> planes
       mbar_wait(o_full, n & 1);
