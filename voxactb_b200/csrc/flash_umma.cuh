@@ -22,8 +22,9 @@ constexpr int FA_KVSTAGES = 4;                   // K/V tiles j-2 .. j+1 are liv
 constexpr int FA_PV_LAG = 2;                     // PV trails QK^T by two key tiles
 constexpr int FA_QBYTES = 2 * 128 * 128;         // Q hi + lo
 constexpr int FA_KVBYTES = 4 * FA_KT * 128;      // K hi, K lo, Vt hi, Vt lo (64 rows x 128 B each)
-constexpr int FA_PBYTES = 2 * 128 * 128;         // P hi + lo
-constexpr int FA_SMEM = FA_QBYTES + FA_KVSTAGES * FA_KVBYTES + 2 * FA_PBYTES + 1024;
+constexpr int FA_SMEM = FA_QBYTES + FA_KVSTAGES * FA_KVBYTES + 1024;   // P lives in tensor memory
+// TMEM columns: S0 @0, S1 @128 (hi*hi+lo*hi | hi*lo), O @256, P0 @384 (hi 32 cols, lo 32 cols), P1 @448
+constexpr uint32_t FA_TMEM_O = 256, FA_TMEM_P = 384;
 
 struct FlashParams {
   int B, H, Nq, Nk, dh;
@@ -48,7 +49,6 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
   __shared__ float rs_part[2][128];              // row-sum partials of the two key halves
   uint8_t* q_s = smem;
   uint8_t* kv_s = smem + FA_QBYTES;
-  uint8_t* p_s = kv_s + FA_KVSTAGES * FA_KVBYTES;
   uint64_t* q_full = bars;
   uint64_t* q_empty = bars + 1;
   uint64_t* kv_full = bars + 2;
@@ -162,14 +162,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
           }
           mbar_wait(&p_full[pb], (itp >> 1) & 1u);
           tc_fence_after();
-          const uint32_t p_hi = dlo(smem_u32(p_s + pb * FA_PBYTES)), p_lo = p_hi + ((128 * 128) >> 4);
+          const uint32_t p_hi = tmem_u + FA_TMEM_P + pb * 64u, p_lo = p_hi + 32u;   // A operand in TMEM: 8 columns per K = 16
           const uint32_t vb = dlo(smem_u32(kv_s + st_pv * FA_KVBYTES + 2 * FA_KT * 128));
-          const uint32_t d_o = tmem_u + 256u;
+          const uint32_t d_o = tmem_u + FA_TMEM_O;
           if (leader) {
 #pragma unroll
             for (int ks = 0; ks < FA_KT / 16; ++ks) {
-              tc_mma_bf16_lo(d_o, p_hi + 2 * ks, vb + 2 * ks, kDescHi, idesc128, (jt > 0 || ks != 0));   // hi*hi | hi*lo
-              tc_mma_bf16_lo(d_o, p_lo + 2 * ks, vb + 2 * ks, kDescHi, idesc64, 1);                      // lo*hi
+              tc_mma_f16_ts(d_o, p_hi + 8 * ks, vb + 2 * ks, kDescHi, idesc128, (jt > 0 || ks != 0));   // hi*hi | hi*lo
+              tc_mma_f16_ts(d_o, p_lo + 8 * ks, vb + 2 * ks, kDescHi, idesc64, 1);                      // lo*hi
             }
             tc_commit(&p_empty[pb]);
             tc_commit(&kv_empty[st_pv]);
@@ -200,8 +200,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
         if (sb != (uint32_t)c) continue;                       // the other group's tile
         mbar_wait(&s_full[sb], (it >> 1) & 1u);
         tc_fence_after();
-        uint8_t* ph_row = p_s + sb * FA_PBYTES + r * 128;
-        uint8_t* pl_row = ph_row + 128 * 128;
+        uint32_t phv[32], plv[32];                             // this row's P as packed fp16 pairs: hi and lo planes, 64 keys
         const int key0 = j * FA_KT;
         // S(tile) -> registers: both 32-key halves, hi*hi|lo*hi columns + hi*lo columns summed on the way in, then the
         // S buffer goes straight back to the MMA warp (QK^T of this group's next tile does not wait for the exps)
@@ -229,10 +228,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
           auto chunk = [&](auto masked_tag) {
             constexpr bool kMasked = decltype(masked_tag)::value;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {                      // 8 keys = one 16-byte chunk per plane
-              uint4 hv, lv;
-              uint32_t* hp = reinterpret_cast<uint32_t*>(&hv);
-              uint32_t* lp = reinterpret_cast<uint32_t*>(&lv);
+            for (int g = 0; g < 4; ++g) {
+              uint32_t* hp = phv + cc * 16 + g * 4;
+              uint32_t* lp = plv + cc * 16 + g * 4;
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int jj = g * 8 + 2 * e;
@@ -251,16 +249,16 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
                 hp[e] = *reinterpret_cast<const uint32_t*>(&hh);
                 lp[e] = *reinterpret_cast<const uint32_t*>(&ll);
               }
-              const int off = ((cc * 4 + g) ^ (r & 7)) * 16;
-              *reinterpret_cast<uint4*>(ph_row + off) = hv;
-              *reinterpret_cast<uint4*>(pl_row + off) = lv;
             }
           };
           if (key0 + cc * 32 + 31 < p.Nk) chunk(std::false_type{});
           else chunk(std::true_type{});
         }
+        // P -> tensor memory (the A operand of the PV MMAs): lane = query row, two keys per 32-bit column
+        tc_st32(tmem_base + ((uint32_t)(q * 32) << 16) + FA_TMEM_P + sb * 64u, phv);
+        tc_st32(tmem_base + ((uint32_t)(q * 32) << 16) + FA_TMEM_P + sb * 64u + 32u, plv);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P writes -> visible to the tensor core
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[sb]);
       }
@@ -275,8 +273,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       __nv_bfloat16* ol = p.out_lo + ((size_t)b * p.Nq + qi) * p.ldo + (size_t)h * p.dh;
       {
         uint32_t v0[32], v1[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(c * 32), v0);
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 256u + 64u + (uint32_t)(c * 32), v1);
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + FA_TMEM_O + (uint32_t)(c * 32), v0);
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + FA_TMEM_O + 64u + (uint32_t)(c * 32), v1);
         if (row_ok) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {

@@ -105,6 +105,32 @@ __device__ __forceinline__ void tc_mma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
       "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi) : "memory");
 }
+// A operand from tensor memory (row m = TMEM lane m, two 16-bit K elements per 32-bit column, 8 columns per K = 16
+// step; cute SM100_MMA_F16BF16_TS), B from a shared-memory descriptor
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 db;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns written from registers (thread t -> TMEM lane lane_base + t)
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
+      ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]),
+        "r"(taddr)
+      : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets columns [col, col+32) of TMEM lane (lane_base + t)
 // issue only: the caller batches several loads behind one tcgen05.wait::ld
 __device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
