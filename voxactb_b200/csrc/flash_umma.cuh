@@ -219,7 +219,6 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[sb]);
-        mbar_wait(&p_empty[sb], ((it >> 1) & 1u) ^ 1u);        // PV of this group's previous tile has consumed the P buffer
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           // The softmax warps are issue-bound (two warps per scheduler): everything runs on register PAIRS with the
@@ -255,6 +254,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
           else chunk(std::true_type{});
         }
         // P -> tensor memory (the A operand of the PV MMAs): lane = query row, two keys per 32-bit column
+        mbar_wait(&p_empty[sb], ((it >> 1) & 1u) ^ 1u);        // PV of this group's previous tile has consumed the P buffer
+        tc_fence_after();
         tc_st32(tmem_base + ((uint32_t)(q * 32) << 16) + FA_TMEM_P + sb * 64u, phv);
         tc_st32(tmem_base + ((uint32_t)(q * 32) << 16) + FA_TMEM_P + sb * 64u + 32u, plv);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
