@@ -32,6 +32,11 @@ QNET_CASES = {
 QNET2_CASES = {
     'qnet2_v20': dict(V=20, k=5, s=5, L=64, depth=2, B=2, cameras=2, H=32, W=32, low_dim=4, arm=False, crop=False, seed=31),
 }
+# one training step (agent.update): forward in train mode with zero dropout, reference losses, autograd, reference LAMB
+TRAIN_CASES = {
+    'train_v20': dict(V=20, k=5, s=5, L=64, depth=2, B=2, cameras=2, H=32, W=32, low_dim=4, arm=False, crop=False, seed=41),
+    'train_v20_arm': dict(V=20, k=5, s=5, L=48, depth=1, B=3, cameras=2, H=32, W=32, low_dim=7, arm=True, crop=True, seed=42),
+}
 VOXEL_CASES = {
     'voxel_v20': dict(V=20, B=2, cameras=2, H=32, W=32, crop=False, seed=21),
     'voxel_v32_crop': dict(V=32, B=3, cameras=1, H=48, W=40, crop=True, seed=22),
@@ -92,9 +97,101 @@ def main_two_robots():
         print(name, 'rot_grip_left absmax', float(np.abs(out['rot_grip_left']).max()))
 
 
+def train_labels(c):
+    """Seeded label indices of one replay batch."""
+    g = torch.Generator().manual_seed(c['seed'] + 5000)
+    lab = dict(trans=torch.randint(0, c['V'], (c['B'], 3), generator=g, dtype=torch.int32),
+               rot_grip=torch.cat([torch.randint(0, 72, (c['B'], 3), generator=g, dtype=torch.int32),
+                                   torch.randint(0, 2, (c['B'], 1), generator=g, dtype=torch.int32)], 1),
+               collision=torch.randint(0, 2, (c['B'], 1), generator=g, dtype=torch.int32))
+    if c['arm']:
+        lab['arm'] = torch.randint(0, 2, (c['B'], 1), generator=g, dtype=torch.int32)
+    return lab
+
+
+def train_encoder_kwargs(c):
+    kw = encoder_kwargs(c)
+    kw.update(input_dropout=0.0, attn_dropout=0.0, decoder_dropout=0.0)   # dropout off for gradient parity
+    return kw
+
+
+def main_train():
+    """agent.update (qattention_peract_bc_agent.py:484-582) re-enacted with the reference's own modules."""
+    import importlib.util
+    import torch.nn as nn
+    RefVG, RefEnc = refimport.load()
+    spec = importlib.util.spec_from_file_location('ref_lamb', os.path.join(refimport.REF, 'helpers', 'optim', 'lamb.py'))
+    lamb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(lamb)
+    torch.set_num_threads(os.cpu_count())
+    celoss_fn = nn.CrossEntropyLoss(reduction='none')
+
+    def celoss(pred, labels):                                  # agent:391-392
+        return celoss_fn(pred, labels.argmax(-1))
+
+    for name, c in TRAIN_CASES.items():
+        obs = synth.make_observation(c['seed'], c['B'], c['cameras'], c['H'], c['W'], low_dim=c['low_dim'],
+                                     per_sample_crop=c['crop'])
+        lab = train_labels(c)
+        coords, feats = synth.flatten_cameras(obs)
+        vg = RefVG(synth.SCENE_BOUNDS, c['V'], 'cpu', c['B'], 3, coords.shape[1])
+        grid = vg.coords_to_bounding_voxel_grid(coords, feats, obs['bounds']).permute(0, 4, 1, 2, 3).detach()
+        net = RefEnc(**train_encoder_kwargs(c)).train()
+        sd = synth.random_state_dict(net, c['seed'] + 1000)
+        assert not net.load_state_dict(sd, strict=False).unexpected_keys
+        outs = net(grid, obs['proprio'], obs['lang_goal_emb'], obs['lang_token_embs'], None, obs['bounds'], None)
+        q_trans, q_rot_grip, q_collision = outs[0], outs[1], outs[2]
+        bs, V, R = c['B'], c['V'], 72
+        onehot = torch.zeros(bs, 1, V, V, V)
+        for b in range(bs):                                    # agent:517-522
+            gt = lab['trans'][b].int()
+            onehot[b, :, gt[0], gt[1], gt[2]] = 1
+        terms = {'trans': celoss(q_trans.view(bs, -1), onehot.view(bs, -1))}
+        rx, ry, rz, gr, ic = (torch.zeros(bs, R), torch.zeros(bs, R), torch.zeros(bs, R), torch.zeros(bs, 2), torch.zeros(bs, 2))
+        for b in range(bs):                                    # agent:538-546
+            g = lab['rot_grip'][b].int()
+            rx[b, g[0]] = 1; ry[b, g[1]] = 1; rz[b, g[2]] = 1; gr[b, g[3]] = 1
+            ic[b, lab['collision'][b].int()[0]] = 1
+        terms['rot'] = celoss(q_rot_grip[:, 0:R], rx) + celoss(q_rot_grip[:, R:2 * R], ry) + celoss(q_rot_grip[:, 2 * R:3 * R], rz)
+        terms['grip'] = celoss(q_rot_grip[:, 3 * R:], gr)
+        terms['collision'] = celoss(q_collision, ic)
+        combined = terms['trans'] + terms['rot'] + terms['grip'] + terms['collision']      # all loss weights 1.0
+        if c['arm']:
+            arm1h = torch.zeros(bs, 2)
+            for b in range(bs):                                # agent:565-570
+                arm1h[b, lab['arm'][b].long()] = 1
+            terms['arm'] = celoss(outs[3], arm1h)
+            combined = combined + terms['arm']
+        total = combined.mean()
+        opt = lamb.Lamb(net.parameters(), lr=5e-4, weight_decay=1e-6, betas=(0.9, 0.999), adam=False)
+        opt.zero_grad()
+        total.backward()
+        grads = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
+        opt.step()
+        new = {k: p.detach().clone() for k, p in net.named_parameters() if k in grads}
+        keys = sorted(grads.keys())
+        out = dict(total=np.array([float(total)]), keys=np.array(keys),
+                   label_checksum=np.array([int(sum(int(v.long().sum()) for v in lab.values()))]),
+                   grad_sum=np.array([float(grads[k].double().sum()) for k in keys]),
+                   grad_abs=np.array([float(grads[k].double().abs().sum()) for k in keys]),
+                   grad_max=np.array([float(grads[k].abs().max()) for k in keys]),
+                   param_sum=np.array([float(new[k].double().sum()) for k in keys]),
+                   param_delta_abs=np.array([float((new[k].double() - sd[k].double()).abs().sum()) for k in keys]),
+                   no_grad_keys=np.array(sorted(k for k, p in net.named_parameters() if p.grad is None)))
+        for t, v in terms.items():
+            out['loss_' + t] = v.detach().numpy()
+        for k in keys:                                         # full tensors for the small ones, strided samples otherwise
+            g = grads[k].reshape(-1)
+            out['g:' + k] = (g if g.numel() <= 4096 else g[:: max(1, g.numel() // 2048)]).numpy()
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+        print(name, 'total', float(total), 'params with grad', len(keys), 'without', len(out['no_grad_keys']))
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == 'two_robots':
         return main_two_robots()
+    if len(sys.argv) > 1 and sys.argv[1] == 'train':
+        return main_train()
     RefVG, RefEnc = refimport.load()
     torch.set_num_threads(os.cpu_count())
     for name, c in VOXEL_CASES.items():

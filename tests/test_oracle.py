@@ -6,7 +6,7 @@ import torch
 
 import refimport
 import util
-from oracle import qnet_oracle, voxel_oracle
+from oracle import qnet_oracle, train_oracle, voxel_oracle
 from voxactb_b200 import synth
 
 import make_golden
@@ -67,6 +67,36 @@ def test_two_robot_oracle_matches_golden_and_keys():
                                         obs['lang_token_embs'], obs['bounds'], c['V'])
     for k in ('trans', 'rot_grip', 'collision', 'trans_left', 'rot_grip_left', 'collision_left'):
         assert util.rel_err(out[k], g[k]) < 1e-5, k
+
+
+@pytest.mark.parametrize('name', ['train_v20', 'train_v20_arm'])
+def test_training_step_oracle_matches_reference_golden(name):
+    """Row a18: losses, EVERY parameter gradient and the LAMB-updated parameters of one `update` step, against the
+    fixture the reference produced (its modules in train mode with zero dropout, torch autograd, its Lamb class)."""
+    c = make_golden.TRAIN_CASES[name]
+    g = util.golden(name)
+    obs, enc, sd = util.make_case(c)
+    lab = make_golden.train_labels(c)
+    assert int(sum(int(v.long().sum()) for v in lab.values())) == int(g['label_checksum'][0])
+    sd = {k: v for k, v in sd.items() if k in set(g['keys'].tolist())}        # parameters only (no pos_x/y/z buffers)
+    res = train_oracle.training_step(sd, util.oracle_cfg(c), obs['rgb'], obs['pcd'], obs['proprio'], obs['lang_token_embs'],
+                                     obs['bounds'], c['V'], lab)
+    assert abs(float(res['total']) - float(g['total'][0])) <= 2e-5 * abs(float(g['total'][0]))
+    for t in ('trans', 'rot', 'grip', 'collision') + (('arm',) if c['arm'] else ()):
+        np.testing.assert_allclose(res['terms'][t].numpy(), g['loss_' + t], rtol=2e-5, atol=2e-5)
+    keys = g['keys'].tolist()
+    assert sorted(res['grads'].keys()) == keys and len(g['no_grad_keys']) == 0
+    for i, k in enumerate(keys):
+        gr = res['grads'][k]
+        scale = max(float(g['grad_max'][i]), 1e-12)
+        flat = gr.reshape(-1)
+        samp = flat if flat.numel() <= 4096 else flat[:: max(1, flat.numel() // 2048)]
+        assert float((samp - torch.from_numpy(g['g:' + k])).abs().max()) <= 2e-4 * scale, k
+        assert abs(float(gr.double().abs().sum()) - float(g['grad_abs'][i])) <= 2e-4 * max(float(g['grad_abs'][i]), 1e-12), k
+        # LAMB step from zero state: the update magnitude |p_new - p| (trust-ratio scaled) and the new parameter sum
+        delta = float((res['params'][k].double() - sd[k].double()).abs().sum())
+        assert abs(delta - float(g['param_delta_abs'][i])) <= 2e-3 * max(float(g['param_delta_abs'][i]), 1e-12), k
+        assert abs(float(res['params'][k].double().sum()) - float(g['param_sum'][i])) <= 1e-4 * max(1.0, abs(float(g['param_sum'][i]))), k
 
 
 def test_state_dict_keys_match_reference():
