@@ -142,6 +142,7 @@ __device__ __forceinline__ void tc_mma_pair_w(uint32_t tmem_d, uint32_t a_lo, ui
 __host__ __device__ constexpr uint32_t make_idesc_m256(int n) {
   return (1u << 4) | VXB_IDESC_AB_FORMAT | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
+constexpr int CV_TAILW_BYTES = 64 * 128;           // one tail weight set as a tcgen05 B operand (64 rows x 128 B)
 constexpr int CV_PAIR_TAPBYTES = 96 * CV_KC * 2;      // per CTA and tap: 64 rows (its half of [W_hi;W_lo]) + 32 rows (its half of W_hi)
 constexpr int CV_PAIR_WBYTES = 3 * CV_PAIR_TAPBYTES;
 
@@ -153,8 +154,10 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(16) uint8_t epi_smem[4 * EPI_BYTES_PER_WARP];
-  __shared__ __align__(8) uint64_t bars[2 * CV_SLABS + 2 * CV_WSTAGES + 8];
-  __shared__ __align__(16) float tail_sw[2 * 27 * 64 + 64];   // tail weights (2 sets) + conv bias (tail mode only)
+  __shared__ __align__(8) uint64_t bars[2 * CV_SLABS + 2 * CV_WSTAGES + 8 + 4];
+  // tail mode: conv bias (+ the fp32 tail weights of the CUDA-core tail the CTA-pair variant still uses)
+  constexpr int TAIL_BIAS_OFF = PAIR ? 2 * 27 * 64 : 0;
+  __shared__ __align__(16) float tail_sw[TAIL_BIAS_OFF + 64];
   __shared__ uint32_t tmem_base_smem;
 
   static_assert(!PAIR || CL == 2, "the CTA-pair variant runs on clusters of two");
@@ -169,6 +172,9 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
   uint64_t* w_empty = w_full + CV_WSTAGES;
   uint64_t* acc_full = w_empty + CV_WSTAGES;
   uint64_t* acc_empty = acc_full + 4;
+  uint64_t* tail_done = acc_empty + 4;           // tensor-core tail: the tap-product MMAs of a slot have retired
+  // tensor-core tail (PAIR = false): [W_hi (32 tap rows) ; W_lo (32 rows)] x 64 channels fp16, SWIZZLE_128B K-major, per weight set
+  uint8_t* tailw_s = (uint8_t*)(((uintptr_t)(w_base + CV_WSTAGES * WBYTES) + 1023) & ~(uintptr_t)1023);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = (CL > 1) ? cluster_ctarank() : 0;
@@ -180,7 +186,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
     tma_prefetch_desc(&mapW);
     for (int i = 0; i < CV_SLABS; ++i) { mbar_init(&slab_full[i], 1); mbar_init(&slab_empty[i], 1); }
     for (int i = 0; i < CV_WSTAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], PAIR ? 1 : CL); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], PAIR ? 8 : 4); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], PAIR ? 8 : 4); mbar_init(&tail_done[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -193,11 +199,27 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
     }
   }
   if (p.tail_w) {
-    for (int i = threadIdx.x; i < 27 * 64; i += CV_THREADS) {
-      tail_sw[i] = p.tail_w[i];
-      tail_sw[27 * 64 + i] = p.tail_w2 ? p.tail_w2[i] : 0.f;
+    if constexpr (PAIR) {
+      for (int i = threadIdx.x; i < 27 * 64; i += CV_THREADS) {
+        tail_sw[i] = p.tail_w[i];
+        tail_sw[27 * 64 + i] = p.tail_w2 ? p.tail_w2[i] : 0.f;
+      }
+    } else {
+      // split the 27 x 64 tail weights into fp16 hi / lo rows of the B operand (tap rows 27..31 are zero)
+      for (int i = threadIdx.x; i < 2 * 32 * 64; i += CV_THREADS) {
+        const int set = i >> 11, tap = (i >> 6) & 31, ch = i & 63;
+        const float* src = set ? p.tail_w2 : p.tail_w;
+        const float f = (src && tap < 27) ? src[tap * 64 + ch] : 0.f;
+        const __nv_bfloat16 h = pl_from_float(f);
+        const __nv_bfloat16 l = pl_from_float(f - pl_to_float(h));
+        uint8_t* base = tailw_s + set * CV_TAILW_BYTES;
+        const int rl = 32 + tap;
+        *reinterpret_cast<__nv_bfloat16*>(base + tap * 128 + (((ch >> 3) ^ (tap & 7)) << 4) + (ch & 7) * 2) = h;
+        *reinterpret_cast<__nv_bfloat16*>(base + rl * 128 + (((ch >> 3) ^ (rl & 7)) << 4) + (ch & 7) * 2) = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05
     }
-    for (int i = threadIdx.x; i < 64; i += CV_THREADS) tail_sw[2 * 27 * 64 + i] = p.bias[i];
+    for (int i = threadIdx.x; i < 64; i += CV_THREADS) tail_sw[TAIL_BIAS_OFF + i] = p.bias[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -414,6 +436,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
     const int tr = lane >> 3, tc = (lane & 7) * 4;
     const float slope = p.act_slope >= 0.f ? p.act_slope : 1.f;
     uint32_t full_ph = 0;                          // bit s: parity to wait for on acc_full[s]
+    [[maybe_unused]] uint32_t tail_ph = 0;         // bit s: parity to wait for on tail_done[s]
     const int V = p.V;
     for (int g = cluster_id; g < groups; g += num_clusters) {
       int b, t, z0, lz;
@@ -445,6 +468,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
           float pt[27], pt2[27];
 #pragma unroll
           for (int tp = 0; tp < 27; ++tp) { pt[tp] = 0.f; pt2[tp] = 0.f; }
+          [[maybe_unused]] uint32_t uh[32], ul[32];            // tensor-core tail: this row's 64 channels as packed fp16 pairs (hi, lo)
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             const int c0 = cc * 32;
@@ -454,7 +478,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
             float u[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 bv = *reinterpret_cast<const float4*>(tail_sw + 2 * 27 * 64 + c0 + j);
+              const float4 bv = *reinterpret_cast<const float4*>(tail_sw + TAIL_BIAS_OFF + c0 + j);
               u[j] = __uint_as_float(v0[j]) + __uint_as_float(v1[j]) + bv.x;
               u[j + 1] = __uint_as_float(v0[j + 1]) + __uint_as_float(v1[j + 1]) + bv.y;
               u[j + 2] = __uint_as_float(v0[j + 2]) + __uint_as_float(v1[j + 2]) + bv.z;
@@ -463,7 +487,18 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
               for (int k = 0; k < 4; ++k) u[j + k] = fmaxf(u[j + k], u[j + k] * slope);
               *reinterpret_cast<float4*>(stage + lane * EPI_STAGE_LD + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
             }
-            // the 27 tap dot products of this row (weights broadcast from shared memory)
+            if constexpr (!PAIR) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const __nv_bfloat162 hh = pl2_from_floats(u[2 * j], u[2 * j + 1]);
+                const float2 ff = pl2_to_float2(hh);
+                const __nv_bfloat162 ll = pl2_from_floats(u[2 * j] - ff.x, u[2 * j + 1] - ff.y);
+                uh[cc * 16 + j] = *reinterpret_cast<const uint32_t*>(&hh);
+                ul[cc * 16 + j] = *reinterpret_cast<const uint32_t*>(&ll);
+              }
+            }
+            // CTA-pair variant: the 27 tap dot products of this row on the CUDA cores (weights broadcast from shared memory)
+            if constexpr (PAIR) {
 #pragma unroll
             for (int tp = 0; tp < 27; ++tp) {
               const float4* w4 = reinterpret_cast<const float4*>(tail_sw + tp * 64 + c0);
@@ -494,6 +529,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
                 pt2[tp] += a0 + a1;
               }
             }
+            }   // PAIR
             __syncwarp();
             // column domain: soft-argmax / max partials of ss_final (lane owns columns c0 + tc .. +3)
 #pragma unroll
@@ -509,6 +545,46 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_const
               }
             }
             __syncwarp();
+          }
+          if constexpr (!PAIR) {
+            // ---- tap products on the tensor core: P[128 rows x 32 taps] = U[128 x 64] . Wt^T with the same three-term
+            // split.  U goes back into columns 0..63 of this (already drained) accumulator slot as the TMEM A operand,
+            // the products land in columns 64..127: [U_hi.W_hi + U_lo.W_hi | U_hi.W_lo].
+            const uint32_t t_slot = tmem_base + (uint32_t)(slot * 128);
+            const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+            constexpr uint32_t kDescHi128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+            constexpr uint32_t idesc_t64 = make_idesc(64), idesc_t32 = make_idesc(32);
+            tc_st32(t_slot + t_lane, uh);
+            tc_st32(t_slot + t_lane + 32u, ul);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            const int nsets = p.tail_w2 ? 2 : 1;
+            for (int set = 0; set < nsets; ++set) {
+              asm volatile("bar.sync 1, 128;" ::: "memory");     // all four lane quarters of U are in place (set 1: D has been read)
+              if (warp == 3 && lane == 0) {
+                tc_fence_after();
+                const uint32_t wb = ((smem_u32(tailw_s + set * CV_TAILW_BYTES) >> 4) & 0x3FFFu) | (1u << 16);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  tc_mma_f16_ts(t_slot + 64u, t_slot + 8u * ks, wb + 2u * ks, kDescHi128, idesc_t64, ks != 0);
+                  tc_mma_f16_ts(t_slot + 64u, t_slot + 32u + 8u * ks, wb + 2u * ks, kDescHi128, idesc_t32, 1u);
+                }
+                tc_commit(&tail_done[slot]);
+              }
+              mbar_wait(&tail_done[slot], (tail_ph >> slot) & 1u);
+              tail_ph ^= 1u << slot;
+              tc_fence_after();
+              uint32_t d0[32], d1[32];
+              tc_ld32_nowait(t_slot + t_lane + 64u, d0);
+              tc_ld32_nowait(t_slot + t_lane + 96u, d1);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              tc_fence_before();
+#pragma unroll
+              for (int tp = 0; tp < 27; ++tp) {
+                const float v = __uint_as_float(d0[tp]) + __uint_as_float(d1[tp]);
+                if (set == 0) pt[tp] = v; else pt2[tp] = v;
+              }
+            }
           }
           tc_fence_before();
           __syncwarp();

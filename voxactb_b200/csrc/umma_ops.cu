@@ -975,7 +975,8 @@ int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_
   }
   const bool use_pair = pair && cl == 2;
   VXB_TRY(make_map(&maps[4], wc, (long long)p.ncb * 27 * 128, CV_KC, CV_KC, use_pair ? 32 : 128 / cl, CV_KC));
-  const size_t smem = (size_t)CV_SLABS * 4 * p.box_rows * 64 + (size_t)CV_WSTAGES * (use_pair ? CV_PAIR_WBYTES : CV_WBYTES) + 1024;
+  const size_t smem = (size_t)CV_SLABS * 4 * p.box_rows * 64 + (size_t)CV_WSTAGES * (use_pair ? CV_PAIR_WBYTES : CV_WBYTES) + 1024 +
+                      ((tail && !use_pair) ? 1024 + 2 * CV_TAILW_BYTES : 0);   // + the tail weights as a tcgen05 B operand
   ++g_umma_launches;
   int rc;
   if (use_pair) {
