@@ -16,10 +16,9 @@
 namespace vxb {
 namespace umma {
 
-constexpr int FA_THREADS = 320;               // TMA warp, MMA warp, 8 softmax warps (two per TMEM lane quarter)
+constexpr int FA_THREADS = 352;               // TMA warp, QK^T issuer, PV issuer, 8 softmax warps (two per TMEM lane quarter)
 constexpr int FA_KT = 64;                        // keys per tile
-constexpr int FA_KVSTAGES = 4;                   // K/V tiles j-2 .. j+1 are live while QK^T(j) and PV(j-2) are issued
-constexpr int FA_PV_LAG = 2;                     // PV trails QK^T by two key tiles
+constexpr int FA_KVSTAGES = 4;                   // K/V tiles between the PV issuer (behind) and the TMA prefetch (ahead)
 constexpr int FA_QBYTES = 2 * 128 * 128;         // Q hi + lo
 constexpr int FA_KVBYTES = 4 * FA_KT * 128;      // K hi, K lo, Vt hi, Vt lo (64 rows x 128 B each)
 constexpr int FA_SMEM = FA_QBYTES + FA_KVSTAGES * FA_KVBYTES + 1024;   // P lives in tensor memory
@@ -110,7 +109,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (uniform loops, one elected lane issues)
+    // ===================================================== QK^T issuer (uniform loops, one elected lane issues)
+    // Two issuing warps: S = Q K^T runs ahead as far as the two S buffers allow, independently of the PV warp's waits
+    // for the softmax (a single in-order issuer coupled QK^T(j) to the softmax of tile j-3).
     uint32_t leader;
     asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.b32 %0, 1, 0, P;\n}\n" : "=r"(leader));
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -120,71 +121,75 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
     const uint32_t q_hi = dlo(smem_u32(q_s)), q_lo = q_hi + ((128 * 128) >> 4);
     int st = 0;             // kv stage of the tile whose QK^T is issued next
     uint32_t ph = 0;
-    int st_pv = 0;          // kv stage of the tile whose PV is issued next
-    uint32_t it = 0;        // global counter of the tile whose QK^T is issued next (S / P double buffers)
-    uint32_t itp = 0;       // global counter of the tile whose PV is issued next
+    uint32_t it = 0;        // global key-tile counter (S double buffer)
     uint32_t n = 0;
-    // Issue order per item: QK(0) QK(1) | QK(2) PV(0) | QK(3) PV(1) | ... | PV(kt-2) PV(kt-1).  PV trails QK^T by TWO
-    // tiles: the softmax of a tile (TMEM load, exp, split, st.shared, proxy fence ~ 2 MMA tile times) then has two
-    // issue slots to finish before its P is needed, and the two softmax groups (alternate tiles) both stay busy.
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
       mbar_wait(q_full, n & 1);
       tc_fence_after();
-      for (int j = 0; j < p.k_tiles + FA_PV_LAG; ++j) {
-        if (j < p.k_tiles) {
-          // ---- S(j) = Q K_j^T into S buffer (it & 1)
-          const uint32_t sb = it & 1u;
-          mbar_wait(&kv_full[st], ph);
-          mbar_wait(&s_empty[sb], ((it >> 1) & 1u) ^ 1u);
-          tc_fence_after();
-          const uint32_t kb = dlo(smem_u32(kv_s + st * FA_KVBYTES));
-          const uint32_t d_s = tmem_u + sb * 128u;
-          if (leader) {
+      for (int j = 0; j < p.k_tiles; ++j, ++it) {
+        // ---- S(j) = Q K_j^T into S buffer (it & 1)
+        const uint32_t sb = it & 1u;
+        mbar_wait(&kv_full[st], ph);
+        mbar_wait(&s_empty[sb], ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t kb = dlo(smem_u32(kv_s + st * FA_KVBYTES));
+        const uint32_t d_s = tmem_u + sb * 128u;
+        if (leader) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              tc_mma_bf16_lo(d_s, q_hi + 2 * ks, kb + 2 * ks, kDescHi, idesc128, ks != 0);   // hi*hi | hi*lo
-              tc_mma_bf16_lo(d_s, q_lo + 2 * ks, kb + 2 * ks, kDescHi, idesc64, 1);          // lo*hi
-            }
-            tc_commit(&s_full[sb]);
-            if (j == p.k_tiles - 1) tc_commit(q_empty);        // Q tile free once the last QK^T retires
+          for (int ks = 0; ks < 4; ++ks) {
+            tc_mma_bf16_lo(d_s, q_hi + 2 * ks, kb + 2 * ks, kDescHi, idesc128, ks != 0);   // hi*hi | hi*lo
+            tc_mma_bf16_lo(d_s, q_lo + 2 * ks, kb + 2 * ks, kDescHi, idesc64, 1);          // lo*hi
           }
-          __syncwarp();
-          if (++st == FA_KVSTAGES) { st = 0; ph ^= 1; }
-          ++it;
+          tc_commit(&s_full[sb]);
+          if (j == p.k_tiles - 1) tc_commit(q_empty);          // Q tile free once the last QK^T retires
         }
-        if (j >= FA_PV_LAG) {
-          // ---- O += P(jt) V_jt, jt = j - FA_PV_LAG
-          const int jt = j - FA_PV_LAG;
-          const uint32_t pb = itp & 1u;
-          if (jt == 0) {
-            mbar_wait(o_empty, (n & 1) ^ 1);                   // previous item's O has been read out
-            tc_fence_after();
-          }
-          mbar_wait(&p_full[pb], (itp >> 1) & 1u);
+        __syncwarp();
+        if (++st == FA_KVSTAGES) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================================== PV issuer: O += P(j) V_j as soon as the softmax hands P(j) over
+    uint32_t leader;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.b32 %0, 1, 0, P;\n}\n" : "=r"(leader));
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    constexpr uint32_t idesc128 = make_idesc(128), idesc64 = make_idesc(64);
+    constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+    auto dlo = [](uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); };
+    int st_pv = 0;          // kv stage of the tile whose PV is issued next
+    uint32_t itp = 0;       // global key-tile counter (P double buffer)
+    uint32_t n = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+      for (int jt = 0; jt < p.k_tiles; ++jt, ++itp) {
+        const uint32_t pb = itp & 1u;
+        if (jt == 0) {
+          mbar_wait(o_empty, (n & 1) ^ 1);                     // previous item's O has been read out
           tc_fence_after();
-          const uint32_t p_hi = tmem_u + FA_TMEM_P + pb * 64u, p_lo = p_hi + 32u;   // A operand in TMEM: 8 columns per K = 16
-          const uint32_t vb = dlo(smem_u32(kv_s + st_pv * FA_KVBYTES + 2 * FA_KT * 128));
-          const uint32_t d_o = tmem_u + FA_TMEM_O;
-          if (leader) {
-#pragma unroll
-            for (int ks = 0; ks < FA_KT / 16; ++ks) {
-              tc_mma_f16_ts(d_o, p_hi + 8 * ks, vb + 2 * ks, kDescHi, idesc128, (jt > 0 || ks != 0));   // hi*hi | hi*lo
-              tc_mma_f16_ts(d_o, p_lo + 8 * ks, vb + 2 * ks, kDescHi, idesc64, 1);                      // lo*hi
-            }
-            tc_commit(&p_empty[pb]);
-            tc_commit(&kv_empty[st_pv]);
-            if (jt == p.k_tiles - 1) tc_commit(o_full);
-          }
-          __syncwarp();
-          if (++st_pv == FA_KVSTAGES) st_pv = 0;
-          ++itp;
         }
+        // p_full(j) implies s_full(j) (the softmax read S(j)), i.e. K_j / V_j have landed and QK^T(j) has retired:
+        // committing kv_empty after these MMAs releases the stage for both uses
+        mbar_wait(&p_full[pb], (itp >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t p_hi = tmem_u + FA_TMEM_P + pb * 64u, p_lo = p_hi + 32u;   // A operand in TMEM: 8 columns per K = 16
+        const uint32_t vb = dlo(smem_u32(kv_s + st_pv * FA_KVBYTES + 2 * FA_KT * 128));
+        const uint32_t d_o = tmem_u + FA_TMEM_O;
+        if (leader) {
+#pragma unroll
+          for (int ks = 0; ks < FA_KT / 16; ++ks) {
+            tc_mma_f16_ts(d_o, p_hi + 8 * ks, vb + 2 * ks, kDescHi, idesc128, (jt > 0 || ks != 0));   // hi*hi | hi*lo
+            tc_mma_f16_ts(d_o, p_lo + 8 * ks, vb + 2 * ks, kDescHi, idesc64, 1);                      // lo*hi
+          }
+          tc_commit(&p_empty[pb]);
+          tc_commit(&kv_empty[st_pv]);
+          if (jt == p.k_tiles - 1) tc_commit(o_full);
+        }
+        __syncwarp();
+        if (++st_pv == FA_KVSTAGES) st_pv = 0;
       }
     }
   } else {
     // ===================================================== softmax + epilogue (thread = query row)
     const int q = warp & 3;
-    const int c = (warp - 2) >> 2;                             // softmax group = S/P buffer it owns = 32-channel half of O it writes
+    const int c = (warp - 3) >> 2;                             // softmax group = S/P buffer it owns = 32-channel half of O it writes
     const int r = q * 32 + lane;                               // row inside the 128-query tile
     uint32_t it = 0, n = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
