@@ -9,6 +9,7 @@ from oracle import qnet_oracle as Q
 
 
 def close(a, b, tol=2e-5):
+    a, b = a.detach(), b.detach()
     scale = max(float(b.abs().max()), 1e-12)
     assert float((a - b).abs().max()) <= tol * scale, (float((a - b).abs().max()), scale)
 
@@ -82,3 +83,22 @@ def test_spatial_softmax_and_maxpool_and_ce():
     lg, idx = rnd(4, 9, seed=27), torch.tensor([0, 3, 8, 3])
     (F.cross_entropy(lg, idx, reduction='none') * 0.25).sum().backward()
     close(G.cross_entropy_backward(lg.detach(), idx, 0.25), lg.grad)
+
+
+@pytest.mark.parametrize('scale,k,n', [(5, 5, 4), (4, 5, 3), (2, 3, 5), (5, 3, 3)])
+def test_polyphase_fold_identity_and_transpose(scale, k, n):
+    """K6b: Upsample(x s, trilinear, align_corners=False) followed by the replicate-padded k^3 convolution equals the
+    s^3 folded 3x3x3 phase convolutions with clamped coarse neighbours -- borders included; the fold's transpose is the
+    weight gradient."""
+    from oracle import fold_oracle as FO
+    x, w, b = rnd(2, 3, n, n, n, seed=31, grad=False), rnd(4, 3, k, k, k, seed=32), rnd(4, seed=33, grad=False)
+    up = F.interpolate(x, scale_factor=scale, mode='trilinear', align_corners=False)
+    ref = F.conv3d(F.pad(up, [k // 2] * 6, mode='replicate'), w, b)
+    wf = FO.fold_upconv_weights(w, scale)
+    close(FO.folded_upconv(x, wf, b, scale), ref.detach(), 1e-10)
+    gy = rnd(*ref.shape, seed=34, grad=False)
+    ref.backward(gy)
+    # weight gradient through the folded form: phase-kernel gradients, then the fold transpose
+    wf2 = wf.detach().clone().requires_grad_(True)
+    FO.folded_upconv(x, wf2, b, scale).backward(gy)
+    close(FO.fold_upconv_weights_backward(wf2.grad, scale, k), w.grad, 1e-9)
