@@ -1,8 +1,8 @@
-// Input-stationary 3x3x3 convolution on tcgen05 (split-bf16, fp32 accumulate in TMEM) for sm_100a.
+// Input-stationary 3x3x3 convolution on tcgen05 (split-fp16 x3, fp32 accumulate in TMEM) for sm_100a.
 //
 //   out[b,z,y,x,:] = act(bias + sum_{src,dz,dy,dx} W[:, tap, src ch] . in_src[b, z+dz, y+dy, x+dx, :])     (Co = 64)
 //
-// Inputs are bf16 hi/lo planes of the replicate-PADDED channels-last grids [B, Vp, Vp, Vp, 64] (Vp = V + 2), so
+// Inputs are 16-bit hi/lo planes (planes16.cuh) of the replicate-PADDED channels-last grids [B, Vp, Vp, Vp, 64] (Vp = V + 2), so
 // a tap is a constant shift of the flat padded row index.  The GEMM engine in umma_gemm.cuh re-fetches a
 // 128-row operand tile from L2 for every tap (27x) and is L2-bandwidth bound; this kernel instead
 //   * stages ONE slab per (z plane, 32-channel block): the 128 output rows of a (y,x)-plane tile plus a
@@ -13,10 +13,19 @@
 //   * streams the weights [W_hi ; W_lo] (N = 128 rows) through a deep ring, multicast across a thread-block
 //     cluster so the L2 -> SM weight traffic is divided by the cluster size;
 //   * issues per 16-wide k step   D[:, 0:128] += A_hi [W_hi ; W_lo]^T   and   D[:, 0:64] += A_lo W_hi^T
-//     (the three split-bf16 terms in two MMAs); the epilogue adds the two column halves.
+//     (the three split terms in two MMAs); the epilogue adds the two column halves.
+//
+// Fused tail (ConvParams::tail_w): the activation u = act(conv) is never stored.  Per output plane the epilogue
+//   * accumulates the SpatialSoftmax3D / max-pool partials of u (column domain, through a per-warp smem transpose);
+//   * writes u back as fp16 hi/lo pairs into columns 0..63 of the accumulator slot it has just drained (tcgen05.st)
+//     and has one of its threads issue eight small MMAs with the A operand READ FROM TENSOR MEMORY
+//     (P[128 rows x 32 taps] = U . Wt^T, same three-term split; B = the 27 x 64 trans_decoder weights, split once
+//     per CTA into a SWIZZLE_128B tile) into columns 64..127; the 27 tap products per voxel go to `ptap`
+//     (trans_gather_kernel sums them over the 3x3x3 neighbourhood afterwards).
+//   The CTA-pair experiment (PAIR = true) keeps the older CUDA-core tail (weights broadcast from shared memory).
 //
 // Warp roles (224 threads): 0 = slab TMA producer, 1 = weight TMA producer, 2 = MMA issuer (+ TMEM alloc),
-// 3-6 = epilogue (TMEM -> registers -> smem transpose -> coalesced fp32 stores).
+// 3-6 = epilogue (TMEM -> registers -> smem transpose -> coalesced fp32 stores, or the fused tail).
 #pragma once
 #include "umma_gemm.cuh"
 #include "stream_ops.cuh"

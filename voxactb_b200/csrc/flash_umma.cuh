@@ -3,12 +3,14 @@
 // Pass 1 (the GEMM engine with the EPIK_ROWMAX epilogue) leaves the row maxima of the log2-domain scores;
 // this kernel is pass 2.  A CTA owns 128 queries of one (batch, head) and walks the keys in tiles of 64:
 //   S  = Q K^T           tcgen05, split-16 x3 as  S[:,0:128] = Q_hi [K_hi;K_lo]^T,  S[:,0:64] += Q_lo K_hi^T   (TMEM, 2 buffers)
-//   P  = 2^(a S - max)   softmax warps: tcgen05.ld, ex2, row sums, split into hi/lo and written straight into the
-//                        SWIZZLE_128B K-major A-operand tile of the next MMA (shared memory, 2 buffers)
-//   O += P V             tcgen05,  O[:,0:128] += P_hi [V_hi;V_lo],  O[:,0:64] += P_lo V_hi                       (TMEM)
+//   P  = 2^(a S - max)   softmax warps: tcgen05.ld (both column halves summed on the way in, the S buffer is handed
+//                        back at once), ex2 / row sums / hi-lo split on register pairs (FADD2 / FFMA2), then
+//                        tcgen05.st into tensor memory: lane = query row, two keys per 32-bit column (TMEM, 2 buffers)
+//   O += P V             tcgen05 with the A operand read from TMEM:  O[:,0:128] += P_hi [V_hi;V_lo],  O[:,0:64] += P_lo V_hi
 // and finally O (both halves added) / row sum is written as hi/lo planes for the output projection.
-// The QK^T MMAs of tile j are issued before the PV MMAs of tile j-1, so the tensor pipe works while the softmax
-// warps convert the previous tile.  Warps: 0 = TMA producer, 1 = MMA issuer, 2-5 = softmax + epilogue.
+// Warps: 0 = TMA producer (Q once per item, K / V^T tiles through a 4-stage ring), 1 = QK^T issuer, 2 = PV issuer
+// (two issuing threads: S runs ahead as far as its two buffers allow, PV follows the softmax), 3-10 = softmax +
+// epilogue in two groups that take alternate key tiles (group = S / P buffer = 32-channel half of O it writes out).
 #pragma once
 #include <type_traits>
 #include "umma_gemm.cuh"

@@ -4,10 +4,13 @@
 // With stride >= kernel - (a few) every input voxel is read about once, so the op is a streaming read of d0
 // (256 MB/sample) feeding a [128 tokens] x [64] x [K = k^3 * 64] GEMM per tile.  The operand rows of a token tile
 // are not an affine box (stride-s windows, clamped at the borders), so instead of TMA the four loader warps gather
-// them: thread r owns token row r, loads the 64 fp32 channels of its (clamped) tap voxel with 128-bit loads,
-// splits them into bf16 hi/lo and writes the SWIZZLE_128B K-major rows of the A stage itself; weights
-// [W_hi ; W_lo] (N = 128) arrive by TMA; one elected lane issues  D[:,0:128] += A_hi [W_hi;W_lo]^T  and
-// D[:,0:64] += A_lo W_hi^T  per 16-wide k step (split-bf16 x3, fp32 accumulation in TMEM).
+// them.  fp32 input (PLANES = false): thread r owns token row r, loads the 64 fp32 channels of its (clamped) tap voxel
+// with 128-bit loads, splits them into 16-bit hi/lo and writes the SWIZZLE_128B K-major rows of the A stage itself.
+// Plane input (PLANES = true, the forward's path: d0 already exists as padded hi/lo planes): the rows are copied with
+// cp.async (16 B) straight into the swizzled stage, eight consecutive lanes per 128-byte row so that every request
+// is a full line, PF_DIST (tile, tap) steps ahead of the step handed to the MMA warp and across tile boundaries.
+// Weights [W_hi ; W_lo] (N = 128) arrive by TMA; one elected lane issues  D[:,0:128] += A_hi [W_hi;W_lo]^T  and
+// D[:,0:64] += A_lo W_hi^T  per 16-wide k step (split x3, fp32 accumulation in TMEM).
 // Warps: 0-3 = loaders (+ epilogue of their TMEM lane quarter), 4 = weight TMA producer, 5 = MMA issuer.
 #pragma once
 #include "umma_gemm.cuh"

@@ -204,8 +204,10 @@ ss_merge_kernel(const float* __restrict__ partial, int chunks, int C, float* __r
 // ------------------------------------------------------------------------------------------------
 // input_preprocess (Conv3d CIN -> C, k=1, + LeakyReLU; perceiver_lang_io.py:217-220,357) fused with
 // ss0 + global max pool (:360): same thread layout as ss_partial_kernel (a thread owns 4 output channels,
-// their CIN x 4 weights live in registers), the activation is stored once and its soft-argmax / max
-// partials are accumulated on the fly -- d0 is never re-read.
+// their CIN x 4 weights live in registers as (even, odd) pairs for packed FFMA2), the activation is stored once --
+// as fp32 and / or directly as the padded 16-bit hi/lo planes the tensor-core kernels read -- and its soft-argmax /
+// max partials are accumulated on the fly (lazily rescaled online softmax): d0 is never re-read.  The 40-byte input
+// rows, shared by the 16 threads of a position, are staged through shared memory with cp.async two tiles ahead.
 // ------------------------------------------------------------------------------------------------
 constexpr int IPP_ITERS = 8;     // positions per thread and tile
 constexpr int IPP_STAGES = 3;    // cp.async stages (prefetch distance 2 tiles)
