@@ -39,6 +39,38 @@ def _worker(rank, world, port, n, out_dir):
         dist.destroy_process_group()
 
 
+def _grad_worker(rank, world, port, out_dir):
+    """DDP-equivalent gradient averaging of the training step (voxactb_b200.train.allreduce_gradients; the reference
+    wraps the Q-network in DDP over gloo, agent:50-54): several buckets, ragged sizes, a parameter without a gradient."""
+    from voxactb_b200 import train
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(7)
+        shapes = [(3, 5), (17,), (2, 2, 2), (1,), (64, 9)]
+        params = [torch.nn.Parameter(torch.zeros(*s)) for s in shapes] + [torch.nn.Parameter(torch.zeros(4))]
+        base = [torch.randn(*s, generator=g) for s in shapes]
+        for p, b in zip(params, base):
+            p.grad = b * (rank + 1)                           # rank-dependent gradient; the last parameter has none
+        train.allreduce_gradients(params, bucket_bytes=128)   # tiny buckets: exercise the flush logic
+        mean_factor = sum(r + 1 for r in range(world)) / world
+        for p, b in zip(params, base):
+            assert torch.allclose(p.grad, b * mean_factor, rtol=1e-6, atol=1e-6)
+        assert params[-1].grad is None
+        torch.save([p.grad for p in params[:-1]], os.path.join(out_dir, 'grads%d.pt' % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_allreduce(tmp_path):
+    world = 2
+    mp.spawn(_grad_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a = torch.load(tmp_path / 'grads0.pt')
+    b = torch.load(tmp_path / 'grads1.pt')
+    assert all(torch.equal(x, y) for x, y in zip(a, b))      # every rank ends with the same averaged gradients
+
+
 def test_shard_range_partitions():
     for n in (1, 5, 16, 17, 64):
         for world in (1, 2, 3, 8):
