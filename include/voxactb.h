@@ -186,18 +186,19 @@ int vxb_select_action_f32(const float* q_trans, const float* rot_grip, const flo
                           float* attention_xyz, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------ building blocks (exported for the per-op parity tests) */
-/* number of tcgen05 (split-bf16) GEMM kernels launched so far by this process: lets tests prove that
+/* number of tcgen05 (split 16-bit x3) GEMM kernels launched so far by this process: lets tests prove that
  * VXB_MATH_BF16X3 really ran on the tensor cores and did not fall back to the FFMA path */
 long long vxb_umma_launch_count(void);
 
 /* C[M,N] = act(alpha * A[M,K] * W[N,K]^T + bias[N]) (+ residual[(m % res_rows),N]); row-major fp32.
- * ws (vxb_linear_workspace_bytes) holds the bf16 hi/lo operand planes of the tcgen05 path. */
+ * Replaces nn.Linear / DenseBlock (perceiver_lang_io.py:85-90,100-104,229-238,321-334; network_utils.py:257-289).
+ * ws (vxb_linear_workspace_bytes) holds the 16-bit hi/lo operand planes of the tcgen05 path. */
 size_t vxb_linear_workspace_bytes(int M, int N, int K);
 int vxb_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
                    const float* residual, int res_rows, float* C, int ldc,
                    int M, int N, int K, float alpha, float act_slope /* <0: no activation */,
                    int math_mode, void* ws, size_t ws_bytes, void* stream);
-/* rows of length n: y = (x-mean)/sqrt(var+1e-5)*w+b */
+/* rows of length n: y = (x-mean)/sqrt(var+1e-5)*w+b -- nn.LayerNorm of PreNorm (perceiver_lang_io.py:56-71) */
 int vxb_layernorm_f32(const float* x, const float* w, const float* b, float* y, int rows, int n,
                       void* stream);
 /* spatial soft-argmax (T=0.01) + max over P = Dd*Hh*Ww positions of channels-last x [B,P,C]:
@@ -208,7 +209,8 @@ int vxb_spatial_softmax_f32(const float* x, int B, int Dd, int Hh, int Ww, int C
                             int ss_stride, float* mx, int mx_stride, void* ws, size_t ws_bytes,
                             void* stream);
 /* channels-last conv3d, replicate padding k/2, stride s, weight in PyTorch layout [Co,Ci,k,k,k];
- * x [B,Di,Di,Di,Ci] -> y [B,Do,Do,Do,Co]; ws >= vxb_conv3d_workspace_bytes. */
+ * x [B,Di,Di,Di,Ci] -> y [B,Do,Do,Do,Co]; ws >= vxb_conv3d_workspace_bytes.
+ * Replaces Conv3DBlock (network_utils.py:128-170) as used at perceiver_lang_io.py:217-226,302-311. */
 size_t vxb_conv3d_workspace_bytes(int B, int Di, int Ci, int Co, int k);
 int vxb_conv3d_f32(const float* x, const float* w, const float* bias, float* y, int B, int Di,
                    int Ci, int Co, int k, int s, float act_slope, int math_mode, void* ws,
@@ -220,7 +222,8 @@ size_t vxb_upconv3d_workspace_bytes(int B, int S, int Ci, int Co, int k, int s);
 int vxb_upconv3d_f32(const float* x, const float* w, const float* bias, float* y, int B, int S,
                      int Ci, int Co, int k, int s, float act_slope, int math_mode, void* ws,
                      size_t ws_bytes, void* stream);
-/* softmax(scale * Q K^T) V per (batch, head); q [B,Nq,H*dh] (ldq), k/v rows [B,Nk,*] (ldkv). */
+/* softmax(scale * Q K^T) V per (batch, head); q [B,Nq,H*dh] (ldq), k/v rows [B,Nk,*] (ldkv).
+ * Replaces the einsum / softmax / einsum core of Attention.forward (perceiver_lang_io.py:111-128). */
 size_t vxb_attention_workspace_bytes(int B, int H, int Nq, int Nk);
 int vxb_attention_f32(const float* q, int ldq, long long q_batch_stride, const float* k,
                       const float* v, int ldkv, long long kv_batch_stride, float* out, int ldo,
