@@ -191,7 +191,7 @@ int vxb_select_action_f32(const float* q_trans, const float* rot_grip, const flo
 long long vxb_umma_launch_count(void);
 
 /* C[M,N] = act(alpha * A[M,K] * W[N,K]^T + bias[N]) (+ residual[(m % res_rows),N]); row-major fp32.
- * Replaces nn.Linear / DenseBlock (perceiver_lang_io.py:85-90,100-104,229-238,321-334; network_utils.py:257-289).
+ * Replaces nn.Linear / DenseBlock (perceiver_lang_io.py:80-90,100-104,229-238,321-334; network_utils.py:257-289).
  * ws (vxb_linear_workspace_bytes) holds the 16-bit hi/lo operand planes of the tcgen05 path. */
 size_t vxb_linear_workspace_bytes(int M, int N, int K);
 int vxb_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
@@ -223,7 +223,7 @@ int vxb_upconv3d_f32(const float* x, const float* w, const float* bias, float* y
                      int Ci, int Co, int k, int s, float act_slope, int math_mode, void* ws,
                      size_t ws_bytes, void* stream);
 /* softmax(scale * Q K^T) V per (batch, head); q [B,Nq,H*dh] (ldq), k/v rows [B,Nk,*] (ldkv).
- * Replaces the einsum / softmax / einsum core of Attention.forward (perceiver_lang_io.py:111-128). */
+ * Replaces the einsum / softmax / einsum core of Attention.forward (perceiver_lang_io.py:107-132). */
 size_t vxb_attention_workspace_bytes(int B, int H, int Nq, int Nk);
 int vxb_attention_f32(const float* q, int ldq, long long q_batch_stride, const float* k,
                       const float* v, int ldkv, long long kv_batch_stride, float* out, int ldo,
