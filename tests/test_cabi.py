@@ -65,3 +65,22 @@ def test_no_cpu_fallback():
                                     voxel_patch_stride=5).eval()
     with pytest.raises(RuntimeError, match='CUDA only'):
         enc(torch.zeros(1, 10, 20, 20, 20), torch.zeros(1, 4), None, torch.zeros(1, 77, 512), None, None, None)
+
+
+def test_install_shims_redirects_the_reference_import_sites():
+    """INTEGRATION.md route 1: after install_shims() the import statements of the reference's agent modules
+    (qattention_peract_bc_agent.py:17, launch_utils.py:21) resolve to this package's classes."""
+    import subprocess
+    import sys
+    code = (
+        "import voxactb_b200\n"
+        "voxactb_b200.install_shims()\n"
+        "from voxel.voxel_grid import VoxelGrid\n"
+        "from agents.peract_bc.perceiver_lang_io import PerceiverVoxelLangEncoder, PerceiverVoxelLang2RobotsEncoder\n"
+        "assert VoxelGrid is voxactb_b200.VoxelGrid\n"
+        "assert PerceiverVoxelLangEncoder is voxactb_b200.PerceiverVoxelLangEncoder\n"
+        "assert PerceiverVoxelLang2RobotsEncoder is voxactb_b200.PerceiverVoxelLang2RobotsEncoder\n"
+        "print('ok')\n")
+    r = subprocess.run([sys.executable, '-c', code], cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == 'ok', r.stderr[-1500:]
