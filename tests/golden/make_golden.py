@@ -27,10 +27,24 @@ QNET_CASES = {
     'qnet_v20_arm_crop': dict(V=20, k=5, s=5, L=96, depth=1, B=3, cameras=2, H=32, W=32, low_dim=7, arm=True, crop=True, seed=12),
     'qnet_v32_config1': dict(V=32, k=5, s=4, L=2048, depth=6, B=1, cameras=1, H=128, W=128, low_dim=4, arm=False, crop=False, seed=1235),
     'qnet_v100_b1': dict(V=100, k=5, s=5, L=2048, depth=6, B=1, cameras=4, H=128, W=128, low_dim=4, arm=False, crop=False, seed=1236),
+    # BASELINE.json configurations at their stated size (the reference runs them in chunks of `chunk` samples: samples
+    # are independent, there is no batch coupling anywhere on the path)
+    'qnet_v100_b16': dict(V=100, k=5, s=5, L=2048, depth=6, B=16, cameras=4, H=128, W=128, low_dim=4, arm=False, crop=False,
+                          seed=1240, chunk=2, tstride=997),
+    # config 3: acting + stabilizing agents (low_dim 7, arm head present) on the same observations, different weights
+    'qnet_v100_acting': dict(V=100, k=5, s=5, L=2048, depth=6, B=2, cameras=4, H=128, W=128, low_dim=7, arm=True, crop=False,
+                             seed=1241, wseed=2241),
+    'qnet_v100_stabilizing': dict(V=100, k=5, s=5, L=2048, depth=6, B=2, cameras=4, H=128, W=128, low_dim=7, arm=True,
+                                  crop=False, seed=1241, wseed=3241),
+    # config 4: per-sample VLM-crop bounds
+    'qnet_v100_crop': dict(V=100, k=5, s=5, L=2048, depth=6, B=2, cameras=4, H=128, W=128, low_dim=4, arm=False, crop=True,
+                           seed=1242),
 }
 # 2-robot encoder (PerceiverVoxelLang2RobotsEncoder, C = 192, two head sets)
 QNET2_CASES = {
     'qnet2_v20': dict(V=20, k=5, s=5, L=64, depth=2, B=2, cameras=2, H=32, W=32, low_dim=4, arm=False, crop=False, seed=31),
+    'qnet2_v100_b1': dict(V=100, k=5, s=5, L=2048, depth=6, B=1, cameras=4, H=128, W=128, low_dim=4, arm=False, crop=False,
+                          seed=1243),
 }
 # one training step (agent.update): forward in train mode with zero dropout, reference losses, autograd, reference LAMB
 TRAIN_CASES = {
@@ -69,6 +83,16 @@ def encoder_kwargs(c):
                 no_perceiver=False, no_language=False, final_dim=64, arm_pred_loss=c['arm'])
 
 
+def weight_seed(c):
+    return c.get('wseed', c['seed'] + 1000)
+
+
+def chunked(fn, B, chunk):
+    """Run fn(slice) over the batch in chunks and concatenate each output along dim 0."""
+    parts = [fn(slice(i, min(B, i + chunk))) for i in range(0, B, chunk)]
+    return [torch.cat([p[j] for p in parts], 0) for j in range(len(parts[0]))]
+
+
 def proprio_left(c):
     return torch.rand(c['B'], c['low_dim'], generator=torch.Generator().manual_seed(c['seed'] + 7))
 
@@ -76,7 +100,10 @@ def proprio_left(c):
 def main_two_robots():
     RefVG, _ = refimport.load()
     RefEnc2 = refimport.load2()
+    only = sys.argv[2:]
     for name, c in QNET2_CASES.items():
+        if only and name not in only:
+            continue
         obs = synth.make_observation(c['seed'], c['B'], c['cameras'], c['H'], c['W'], low_dim=c['low_dim'])
         coords, feats = synth.flatten_cameras(obs)
         vg = RefVG(synth.SCENE_BOUNDS, c['V'], 'cpu', c['B'], 3, coords.shape[1])
@@ -91,8 +118,16 @@ def main_two_robots():
             outs = net(grid, obs['proprio'], proprio_left(c), obs['lang_goal_emb'], obs['lang_token_embs'], None,
                        obs['bounds'], None)
         out = dict(keys=np.array(sorted(net.state_dict().keys())),
-                   trans=outs[0].numpy(), rot_grip=outs[1].numpy(), collision=outs[2].numpy(),
-                   trans_left=outs[3].numpy(), rot_grip_left=outs[4].numpy(), collision_left=outs[5].numpy())
+                   rot_grip=outs[1].numpy(), collision=outs[2].numpy(),
+                   rot_grip_left=outs[4].numpy(), collision_left=outs[5].numpy())
+        for key, t in (('trans', outs[0]), ('trans_left', outs[3])):
+            if c['V'] <= 32:
+                out[key] = t.numpy()
+            else:
+                out[key + '_strided'] = t.reshape(c['B'], -1)[:, ::97].numpy()
+                out[key + '_argmax'] = t.reshape(c['B'], -1).argmax(-1).numpy()
+                out[key + '_stats'] = np.array([float(t.double().sum()), float(t.double().abs().sum()), float(t.max()),
+                                                float(t.min())])
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
         print(name, 'rot_grip_left absmax', float(np.abs(out['rot_grip_left']).max()))
 
@@ -192,9 +227,12 @@ def main():
         return main_two_robots()
     if len(sys.argv) > 1 and sys.argv[1] == 'train':
         return main_train()
+    only = sys.argv[2:] if len(sys.argv) > 2 and sys.argv[1] == 'qnet' else []
     RefVG, RefEnc = refimport.load()
     torch.set_num_threads(os.cpu_count())
     for name, c in VOXEL_CASES.items():
+        if only:
+            continue
         obs = synth.make_observation(c['seed'], c['B'], c['cameras'], c['H'], c['W'], per_sample_crop=c['crop'])
         coords, feats = synth.flatten_cameras(obs)
         vg = RefVG(synth.SCENE_BOUNDS, c['V'], 'cpu', c['B'], 3, coords.shape[1])
@@ -217,17 +255,26 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
         print(name, 'occupied', out['occupied'])
     for name, c in QNET_CASES.items():
+        if only and name not in only:
+            continue
         obs = synth.make_observation(c['seed'], c['B'], c['cameras'], c['H'], c['W'], low_dim=c['low_dim'],
                                      per_sample_crop=c['crop'])
         coords, feats = synth.flatten_cameras(obs)
-        vg = RefVG(synth.SCENE_BOUNDS, c['V'], 'cpu', c['B'], 3, coords.shape[1])
-        grid = vg.coords_to_bounding_voxel_grid(coords, feats, obs['bounds']).permute(0, 4, 1, 2, 3)
         net = RefEnc(**encoder_kwargs(c)).eval()
-        sd = synth.random_state_dict(net, c['seed'] + 1000)
+        sd = synth.random_state_dict(net, weight_seed(c))
         missing = net.load_state_dict(sd, strict=False)
         assert not missing.unexpected_keys, missing
-        with torch.no_grad():
-            outs = net(grid, obs['proprio'], obs['lang_goal_emb'], obs['lang_token_embs'], None, obs['bounds'], None)
+
+        def run(sl):
+            n = sl.stop - sl.start
+            vg = RefVG(synth.SCENE_BOUNDS, c['V'], 'cpu', n, 3, coords.shape[1])
+            bnd = obs['bounds'] if obs['bounds'].shape[0] == 1 else obs['bounds'][sl]
+            grid = vg.coords_to_bounding_voxel_grid(coords[sl], feats[sl], bnd).permute(0, 4, 1, 2, 3)
+            with torch.no_grad():
+                return list(net(grid, obs['proprio'][sl], obs['lang_goal_emb'][sl], obs['lang_token_embs'][sl], None, bnd,
+                                None))
+
+        outs = chunked(run, c['B'], c.get('chunk', c['B']))
         trans = outs[0]
         out = dict(in_checksum=np.array([checksum(coords), checksum(feats), checksum(obs['proprio']),
                                          checksum(obs['lang_token_embs']), checksum(obs['bounds'])]),
@@ -242,7 +289,8 @@ def main():
         if c['V'] <= 32:
             out['trans'] = trans.numpy()
         else:
-            out['trans_strided'] = trans.reshape(c['B'], -1)[:, ::97].numpy()
+            out['trans_strided'] = trans.reshape(c['B'], -1)[:, ::c.get('tstride', 97)].numpy()
+            out['trans_sums'] = trans.reshape(c['B'], -1).double().sum(-1).numpy()
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
         print(name, 'trans range', out['trans_stats'][2:], 'rot_grip absmax', float(np.abs(out['rot_grip']).max()))
 

@@ -69,6 +69,66 @@ def test_forward_v100_against_golden(cuda_lib, mode):
     assert int(t.argmax()) == int(g['trans_argmax'][0])
 
 
+def check_strided_trans(trans, g, c, key='trans'):
+    B = c['B']
+    t = trans.reshape(B, -1).cpu()
+    stats = g[key + '_stats']
+    scale = float(np.abs(stats[2:]).max())
+    ref = torch.from_numpy(g[key + '_strided'])
+    got = t[:, ::c.get('tstride', 97)]
+    assert float((got - ref).abs().max()) / scale < util.Q_REL_TOL, key
+    assert util.frac_outside(got, ref) < 1e-3, key                      # elementwise reading of the gate
+    assert abs(float(t.double().sum()) - stats[0]) / stats[1] < 1e-4, key
+    assert torch.equal(t.argmax(-1), torch.from_numpy(g[key + '_argmax'])), key
+
+
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('name', ['qnet_v100_b16', 'qnet_v100_acting', 'qnet_v100_stabilizing', 'qnet_v100_crop'])
+def test_baseline_configs_full_size_against_reference_goldens(cuda_lib, mode, name):
+    """BASELINE.json configs at their stated geometry (100^3, 4 cameras, 2048 latents, depth 6) against outputs of the
+    reference itself: config 2/headline (B=16 single-arm), config 3 (acting and stabilizing agents, low_dim 7 + arm
+    head, same observations, different weights), config 4 (per-sample VLM-crop bounds)."""
+    c = make_golden.QNET_CASES[name]
+    g = util.golden(name)
+    obs, enc, sd = util.make_case(c)
+    _, out = run_qfunction(c, obs, enc, mode)
+    trans, rot_grip, coll = out[0], out[1], out[2]
+    assert util.rel_err(rot_grip, g['rot_grip']) < util.Q_REL_TOL
+    assert util.rel_err(coll, g['collision']) < util.Q_REL_TOL
+    assert util.frac_outside(rot_grip, g['rot_grip']) < 1e-2
+    check_strided_trans(trans, g, c)
+    sums = trans.reshape(c['B'], -1).double().sum(-1).cpu().numpy()
+    assert np.abs(sums - g['trans_sums']).max() / g['trans_stats'][1] * c['B'] < 1e-4   # every sample, not only the total
+    if c['arm']:
+        enc.math_mode = mode
+        arm = enc(out[3], obs['proprio'].cuda(), None, obs['lang_token_embs'].cuda(), None, None, None)[3]
+        assert util.rel_err(arm, g['arm']) < util.Q_REL_TOL
+
+
+@pytest.mark.parametrize('mode', MODES)
+def test_two_robots_full_size_against_reference_golden(cuda_lib, mode):
+    """PerceiverVoxelLang2RobotsEncoder (C = 192) at 100^3 / 2048 latents / depth 6 against the reference."""
+    from voxactb_b200 import QFunction2Robots
+    name = 'qnet2_v100_b1'
+    c = make_golden.QNET2_CASES[name]
+    g = util.golden(name)
+    obs, enc, sd = util.make_case_two_robots(c)
+    enc.math_mode = mode
+    dev = torch.device('cuda')
+    vg = VoxelGrid(synth.SCENE_BOUNDS, c['V'], dev, c['B'], 3, c['cameras'] * c['H'] * c['W'])
+    q = QFunction2Robots(enc, vg, 0.15, 5, dev, False).to(dev).eval()
+    rgb = [t.cuda() for t in obs['rgb']]
+    pcd = [t.cuda() for t in obs['pcd']]
+    tr, rgr, cr, grid, tl, rgl, cl = q([[r, p] for r, p in zip(rgb, pcd)], obs['proprio'].cuda(), obs['proprio_left'].cuda(),
+                                       pcd, obs['lang_goal_emb'].cuda(), obs['lang_token_embs'].cuda(),
+                                       obs['bounds'].cuda(), None, None)
+    torch.cuda.synchronize()
+    for ours, key in ((rgr, 'rot_grip'), (cr, 'collision'), (rgl, 'rot_grip_left'), (cl, 'collision_left')):
+        assert util.rel_err(ours, g[key]) < util.Q_REL_TOL, key
+    check_strided_trans(tr, g, c, 'trans')
+    check_strided_trans(tl, g, c, 'trans_left')
+
+
 @pytest.mark.parametrize('mode', MODES)
 def test_forward_batch_invariance_full_size(cuda_lib, mode):
     """B=4 at 100^3: every sample's result equals the same sample run alone (batch sharding is exact)."""

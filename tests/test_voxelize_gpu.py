@@ -77,6 +77,32 @@ def test_voxelize_edge_cases(cuda_lib):
     compare(grid, idx, coords, feats, b2, 12)
 
 
+def test_voxelize_non_finite_and_huge_coordinates(cuda_lib):
+    """|q| >= 2^31, +-inf and NaN coordinates.  The reference converts floor(q) with `.int()` (voxel_grid.py:160-163):
+    on CUDA (where train.py / eval.py run it) that conversion saturates (+huge -> V+1 after the min, -huge and NaN -> 0),
+    on x86 every invalid conversion gives INT_MIN -> 0.  Both cells are border cells that voxel_grid.py:184 crops, so
+    the GRID is identical either way; the kernel follows the CUDA semantics for the raw index."""
+    gen = torch.Generator().manual_seed(5)
+    bounds = torch.tensor([[-1., -1., -1., 1., 1., 1.]])
+    V = 16
+    coords = torch.rand(1, 512, 3, generator=gen) * 2 - 1
+    feats = torch.rand(1, 512, 3, generator=gen)
+    clean_grid, _ = run_cuda(coords[:, 8:].contiguous(), feats[:, 8:].contiguous(), bounds, V)
+    inf, nan = float('inf'), float('nan')
+    bad = torch.tensor([[1e30, 0., 0.], [-1e30, 0., 0.], [0., inf, 0.], [0., -inf, 0.], [0., 0., nan],
+                        [3e9, -3e9, 0.], [nan, nan, nan], [inf, -inf, nan]])
+    coords[0, :8] = bad
+    grid, idx = run_cuda(coords, feats, bounds, V)
+    expect = torch.tensor([[V + 1, -1, -1], [0, -1, -1], [-1, V + 1, -1], [-1, 0, -1], [-1, -1, 0],
+                           [V + 1, 0, -1], [0, 0, 0], [V + 1, 0, 0]])
+    got = torch.from_numpy(idx[0, :8]).long()
+    assert torch.equal(got[expect >= 0], expect[expect >= 0])
+    # every such point falls in a cropped border cell: the grid is the one of the remaining points
+    assert np.isfinite(grid).all()
+    assert np.array_equal(grid[..., -4:], clean_grid[..., -4:])
+    np.testing.assert_allclose(grid[..., :-4], clean_grid[..., :-4], rtol=2e-6, atol=2e-6)
+
+
 def test_voxelize_full_size_properties(cuda_lib):
     """BASELINE.json size (B=16, V=100, 4 cameras): size-independent properties."""
     B, V = 16, 100

@@ -20,10 +20,23 @@ def install_shims():
     ``from voxel.voxel_grid import VoxelGrid`` and
     ``from agents.peract_bc.perceiver_lang_io import PerceiverVoxelLangEncoder``.
     Call before importing the reference's agent modules."""
+    import importlib
     import sys
     import types
     from . import perceiver_lang_io as _p, voxel_grid as _v
-    pkg = sys.modules.setdefault('voxel', types.ModuleType('voxel'))
+    # keep the reference's real `voxel` package (voxel.augmentation is imported by the agent,
+    # qattention_peract_bc_agent.py:18) and replace only its voxel_grid submodule
+    pkg = sys.modules.get('voxel')
+    if pkg is None:
+        try:
+            pkg = importlib.import_module('voxel')
+        except ImportError:
+            pkg = types.ModuleType('voxel')
+            pkg.__path__ = []          # a package without other submodules
+            sys.modules['voxel'] = pkg
     pkg.voxel_grid = _v
     sys.modules['voxel.voxel_grid'] = _v
     sys.modules['agents.peract_bc.perceiver_lang_io'] = _p
+    agents = sys.modules.get('agents.peract_bc')
+    if agents is not None:
+        agents.perceiver_lang_io = _p

@@ -12,6 +12,13 @@ namespace vxb {
 // ---------------------------------------------------------------- action selection
 // argmax over V^3 per sample: (value, index) pairs, ties -> lowest index (torch.argmax on CPU
 // returns the first maximal element).  Pass 1: per-chunk, pass 2: merge + heads.
+// torch.argmax order: NaN counts as the maximum, ties (and NaN ties) go to the lowest index
+__device__ __forceinline__ bool argmax_better(float v, int i, float best, int bi) {
+  if (v != v) return best == best || i < bi;
+  if (best != best) return false;
+  return v > best || (v == best && i < bi);
+}
+
 __global__ void __launch_bounds__(256)
 argmax_partial_kernel(const float* __restrict__ q, size_t n, int chunks, float* __restrict__ pv,
                       int* __restrict__ pi) {
@@ -22,7 +29,7 @@ argmax_partial_kernel(const float* __restrict__ q, size_t n, int chunks, float* 
   int bi = 0x7fffffff;
   for (size_t i = beg + threadIdx.x; i < end; i += 256) {
     const float v = q[(size_t)b * n + i];
-    if (v > best || (v == best && (int)i < bi)) { best = v; bi = (int)i; }
+    if (argmax_better(v, (int)i, best, bi)) { best = v; bi = (int)i; }
   }
   __shared__ float sv[256];
   __shared__ int si[256];
@@ -32,7 +39,7 @@ argmax_partial_kernel(const float* __restrict__ q, size_t n, int chunks, float* 
     if (threadIdx.x < o) {
       const float v2 = sv[threadIdx.x + o];
       const int i2 = si[threadIdx.x + o];
-      if (v2 > sv[threadIdx.x] || (v2 == sv[threadIdx.x] && i2 < si[threadIdx.x])) {
+      if (argmax_better(v2, i2, sv[threadIdx.x], si[threadIdx.x])) {
         sv[threadIdx.x] = v2; si[threadIdx.x] = i2;
       }
     }
@@ -45,7 +52,7 @@ __device__ __forceinline__ int small_argmax(const float* v, int n) {
   int bi = 0;
   float best = v[0];
   for (int i = 1; i < n; ++i)
-    if (v[i] > best) { best = v[i]; bi = i; }
+    if (argmax_better(v[i], i, best, bi)) { best = v[i]; bi = i; }
   return bi;
 }
 
@@ -63,7 +70,7 @@ __global__ void select_action_final_kernel(const float* __restrict__ pv, const i
   for (int k = 0; k < chunks; ++k) {
     const float v = pv[b * chunks + k];
     const int i = pi[b * chunks + k];
-    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    if (argmax_better(v, i, best, bi)) { best = v; bi = i; }
   }
   // _argmax_3d (qattention_peract_bc_agent.py:57-63): ((idx // h) // d, (idx // h) % w, idx % w)
   const int c0 = (bi / V) / V, c1 = (bi / V) % V, c2 = bi % V;

@@ -58,8 +58,10 @@ static __global__ void ce_finish_kernel(const float* __restrict__ x, long long l
   }
   const float l = M + logf(S);
   lse[b] = l;
-  const int lab = min(max(labels[b], 0), N - 1);
-  loss[b] = l - x[(long long)b * ld + lab];
+  // an out-of-range label poisons the sample (NaN loss and gradient) instead of being clamped silently:
+  // nn.CrossEntropyLoss raises "Target out of bounds" there; the Python wrapper raises for host-side labels
+  const int lab = labels[b];
+  loss[b] = (lab >= 0 && lab < N) ? l - x[(long long)b * ld + lab] : __int_as_float(0x7fc00000);
 }
 
 // grad[b, i] = scale * (softmax(x)[b, i] - [i == label])
@@ -69,6 +71,7 @@ ce_grad_kernel(const float* __restrict__ x, long long ld, const int32_t* __restr
   const int b = blockIdx.y;
   const float l = lse[b];
   const int lab = labels[b];
+  if (lab < 0 || lab >= N) scale = __int_as_float(0x7fc00000);
   for (int i = blockIdx.x * CE_THREADS + threadIdx.x; i < N; i += gridDim.x * CE_THREADS) {
     const float p = expf(x[(long long)b * ld + i] - l);
     g[(long long)b * ldg + i] = scale * (p - (i == lab ? 1.f : 0.f));

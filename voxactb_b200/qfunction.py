@@ -42,6 +42,12 @@ class QFunction(nn.Module):
         coll = torch.empty(B, dtype=torch.int32, device=dev) if q_collision is not None else None
         xyz = torch.empty(B, 3, dtype=torch.float32, device=dev) if bounds is not None else None
         R = int(360 // self._rotation_resolution)
+        # the kernel reads rows of 3R + 2 rotation/gripper logits and 2 collision logits (reference :65-80)
+        if q_rot_grip is not None and tuple(q_rot_grip.shape) != (B, 3 * R + 2):
+            raise ValueError('q_rot_grip must be [%d,%d] (3 x %d rotation bins + 2 gripper), got %s'
+                             % (B, 3 * R + 2, R, tuple(q_rot_grip.shape)))
+        if q_collision is not None and tuple(q_collision.shape) != (B, 2):
+            raise ValueError('q_collision must be [%d,2], got %s' % (B, tuple(q_collision.shape)))
         bnd = _lib.f32(bounds.reshape(-1, 6)) if bounds is not None else None
         rc = L.vxb_select_action_f32(
             _lib.ptr(_lib.f32(q_trans)), _lib.ptr(_lib.f32(q_rot_grip)) if q_rot_grip is not None else None,

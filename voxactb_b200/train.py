@@ -17,6 +17,9 @@ def cross_entropy(logits, labels, grad_scale=None):
     if logits.dim() != 2 or logits.stride(1) != 1 or logits.dtype != torch.float32 or not logits.is_cuda:
         raise ValueError('cross_entropy: logits must be a CUDA fp32 [B, N] view with unit column stride')
     B, N = logits.shape
+    if not labels.is_cuda and labels.numel() and (int(labels.min()) < 0 or int(labels.max()) >= N):
+        raise IndexError('cross_entropy: Target %d is out of bounds for %d classes'
+                         % (int(labels.max()) if int(labels.max()) >= N else int(labels.min()), N))
     lab = labels.to(device=logits.device, dtype=torch.int32).contiguous()
     if lab.shape != (B,):
         raise ValueError('cross_entropy: labels must be [B]')
@@ -73,7 +76,7 @@ class _FusedOptimizer(torch.optim.Optimizer):
                 st['step'] = 0
                 st['exp_avg'] = torch.zeros_like(p)
                 st['exp_avg_sq'] = torch.zeros_like(p)
-            st['step'] += 1
+            st['step'] = int(st['step']) + 1
         n = len(ps)
         arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])
         sizes = (ctypes.c_longlong * n)(*[p.numel() for p in ps])
@@ -104,6 +107,7 @@ class Lamb(_FusedOptimizer):
             rc = _lib.lib().vxb_lamb_step_f32(n, w, g, m, v, sizes, group['lr'], group['betas'][0], group['betas'][1],
                                               group['eps'], group['weight_decay'], _lib.ptr(ws), nbytes, _lib.stream())
             _lib.check(rc, 'vxb_lamb_step_f32')
+            torch._C._increment_version(ps)   # the kernel wrote through raw pointers: invalidate prepared-weight caches
         return loss
 
 
@@ -120,7 +124,7 @@ class Adam(_FusedOptimizer):
             ps, n, w, g, m, v, sizes = self._tables(group)
             if not n:
                 continue
-            steps = {self.state[p]['step'] for p in ps}
+            steps = {int(self.state[p]['step']) for p in ps}   # a torch.optim.Adam checkpoint stores tensors
             if len(steps) != 1:
                 raise RuntimeError('fused Adam needs all parameters of a group at the same step')
             ws, nbytes = self._ws(n, sizes, ps[0].device)
@@ -128,6 +132,7 @@ class Adam(_FusedOptimizer):
                                               group['betas'][1], group['eps'], group['weight_decay'], _lib.ptr(ws),
                                               nbytes, _lib.stream())
             _lib.check(rc, 'vxb_adam_step_f32')
+            torch._C._increment_version(ps)
         return loss
 
 
