@@ -171,6 +171,38 @@ const char* vxb_profile_stage_name(int i);
 int vxb_profile_enable(int on);
 int vxb_profile_read(double* ms /* host */);
 
+/* ------------------------------------------------------------------ training step of the Q-network (row a18)
+ * Device side of `total_loss.backward()` in QAttentionPerActBCAgent.update (reference
+ * qattention_peract_bc_agent.py:484-582) for PerceiverVoxelLangEncoder.forward (perceiver_lang_io.py:345-485):
+ * vxb_qnet_forward_train_f32 runs the forward and keeps the activations in `ws`; vxb_qnet_backward_f32, called
+ * with the SAME ws / params / prepared / inputs / opts, writes d loss / d parameter for every parameter.  The voxel
+ * grid is detached (agent:107-108): nothing is propagated past input_preprocess.  Single-arm encoder (optionally
+ * with the arm head), iterations == 1, voxel_patch_size == voxel_patch_stride. */
+typedef struct vxb_train_opts {
+  int32_t struct_bytes;          /* sizeof(vxb_train_opts) */
+  float input_dropout;           /* nn.Dropout on the attention probabilities of the encoder cross attention */
+  float attn_dropout;            /* ... of the latent self-attention layers */
+  float decoder_dropout;         /* ... of the decoder cross attention (perceiver_lang_io.py:127-128,258,265,284) */
+  uint64_t seed;                 /* counter-based mask stream; the backward regenerates the forward's masks from it */
+} vxb_train_opts;
+
+size_t vxb_qnet_train_workspace_bytes(const vxb_qnet_desc* d, int B);
+int vxb_qnet_forward_train_f32(const vxb_qnet_desc* d, const void* const* params, const void* prepared,
+                               const float* grid, const float* proprio, const float* lang_tokens, int B,
+                               float* q_trans, float* rot_grip, float* collision, float* arm_out,
+                               const vxb_train_opts* opts, void* ws, size_t ws_bytes, void* stream);
+/* g_trans [B,V^3], g_rot_grip [B,3R+G], g_collision [B,Cc], g_arm [B,2] or NULL: d loss / d output.
+ * grads: HOST array parallel to `params` (vxb_param_slot order) of device buffers with the parameters' shapes;
+ * every gradient is ASSIGNED (not accumulated).  debug: NULL, or a HOST array of 8 device buffers (NULL entries
+ * allowed) receiving activation gradients for the parity tests: 0 feats [B,flat], 1 u [B,V^3,64], 2 u0 [B,V^3,64],
+ * 3 low [B,S^3,64], 4 dec [B,S^3,C], 5 final latents [B,L,D], 6 tokens [B,77+S^3,C], 7 d0 [B,V^3,64]
+ * (1-3 and 7: gradient of the block OUTPUT, i.e. before the activation adjoint). */
+int vxb_qnet_backward_f32(const vxb_qnet_desc* d, const void* const* params, const void* prepared,
+                          const float* grid, const float* proprio, const float* lang_tokens, int B,
+                          const float* g_trans, const float* g_rot_grip, const float* g_collision, const float* g_arm,
+                          float* const* grads, const vxb_train_opts* opts, float* const* debug, void* ws,
+                          size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ action selection */
 /*
  * softmax-free argmax of the translation grid (softmax is monotone: agent:709-718), per-axis-group

@@ -149,7 +149,7 @@ def qnet_forward(sd, cfg, ins, proprio, lang_token_embs):
     dec = dec.view(b, *seq_shape[1:-1], dec.shape[-1]).permute(0, 4, 1, 2, 3)           # :447-448
     feats.extend([spatial_softmax3d(dec.contiguous()), dec.amax(dim=(2, 3, 4))])        # :451
     # up0 = Conv3DUpsampleBlock: conv -> trilinear upsample -> conv  (network_utils.py:237-254)
-    u0 = conv3d_block(dec, sd['up0.conv_up.0.conv3d.weight'], sd['up0.conv_up.0.conv3d.bias'], 1, act)
+    u0 = low = conv3d_block(dec, sd['up0.conv_up.0.conv3d.weight'], sd['up0.conv_up.0.conv3d.bias'], 1, act)
     if stride > 1:
         u0 = F.interpolate(u0, scale_factor=stride, mode='trilinear', align_corners=False)
         u0 = conv3d_block(u0, sd['up0.conv_up.2.conv3d.weight'], sd['up0.conv_up.2.conv3d.bias'], 1, act)
@@ -159,6 +159,9 @@ def qnet_forward(sd, cfg, ins, proprio, lang_token_embs):
     trans = conv3d_block(u, sd['trans_decoder.conv3d.weight'], sd['trans_decoder.conv3d.bias'], 1, None)     # :465
     feats.extend([spatial_softmax3d(u), u.amax(dim=(2, 3, 4))])                          # :470
     flat = torch.cat(feats, dim=1)
+    if cfg.get('tap') is not None:
+        # intermediate activations for the backward parity tests (tests call .retain_grad() on them)
+        cfg['tap'].update(d0=d0, u0=u0, u=u, low=low, dec=dec, latents=lat, tokens=seq, feats=flat)
     h0 = _act(F.linear(flat, sd['dense0.linear.weight'], sd['dense0.linear.bias']), act)
     h1 = _act(F.linear(h0, sd['dense1.linear.weight'], sd['dense1.linear.bias']), act)
     rgc = F.linear(h1, sd['rot_grip_collision_ff.linear.weight'], sd['rot_grip_collision_ff.linear.bias'])
@@ -186,7 +189,7 @@ def qfunction_forward(sd, cfg, voxelize_fn, rgb, pcd, proprio, lang_token_embs, 
     pcd_flat = torch.cat([p.permute(0, 2, 3, 1).reshape(b, -1, 3) for p in pcd], 1)
     feat = torch.cat([p.permute(0, 2, 3, 1).reshape(b, -1, 3) for p in rgb], 1)
     grid = voxelize_fn(pcd_flat.numpy(), feat.numpy(), bounds.numpy(), voxel_size)
-    grid = torch.from_numpy(grid).permute(0, 4, 1, 2, 3)
+    grid = torch.from_numpy(grid).permute(0, 4, 1, 2, 3).to(proprio.dtype)   # float64 when the caller asks for a double-precision run
     out = qnet_forward(sd, cfg, grid, proprio, lang_token_embs)
     out['voxel_grid'] = grid
     return out

@@ -29,6 +29,12 @@ class QnetDesc(ctypes.Structure):
         'arm_pred_loss', 'no_language')] + [('act_slope', ctypes.c_float), ('math_mode', ctypes.c_int32)]
 
 
+class TrainOpts(ctypes.Structure):
+    """struct vxb_train_opts (include/voxactb.h)."""
+    _fields_ = [('struct_bytes', ctypes.c_int32), ('input_dropout', ctypes.c_float), ('attn_dropout', ctypes.c_float),
+                ('decoder_dropout', ctypes.c_float), ('seed', ctypes.c_uint64)]
+
+
 # name -> (restype, argtypes); every symbol include/voxactb.h declares
 SIGNATURES = {
     'vxb_version': (c_int, []),
@@ -46,6 +52,13 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_size_t, c_void_p]),
+    'vxb_qnet_train_workspace_bytes': (c_size_t, [ctypes.POINTER(QnetDesc), c_int]),
+    'vxb_qnet_forward_train_f32': (c_int, [ctypes.POINTER(QnetDesc), ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           ctypes.POINTER(TrainOpts), c_void_p, c_size_t, c_void_p]),
+    'vxb_qnet_backward_f32': (c_int, [ctypes.POINTER(QnetDesc), ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_void_p),
+                                      ctypes.POINTER(TrainOpts), ctypes.POINTER(c_void_p), c_void_p, c_size_t, c_void_p]),
     'vxb_last_launch_count': (c_int, []),
     'vxb_voxelize_launches': (c_int, []),
     'vxb_profile_stage_count': (c_int, []),

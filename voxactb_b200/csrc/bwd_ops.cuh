@@ -1,0 +1,667 @@
+// Backward (adjoint) kernels of the Q-network's building blocks -- SURVEY.md section 8 row a18.
+// The reference obtains these from torch autograd (`total_loss.backward()`, qattention_peract_bc_agent.py:581) over
+// perceiver_lang_io.py / helpers/network_utils.py; every kernel here implements the closed-form adjoint that
+// oracle/grad_oracle.py restates and checks against autograd.  Dense contractions (dgrad / wgrad of linears and
+// convolutions, attention) go through the GEMM engine with transposed / transposed-im2col operand modes; everything
+// else is an HBM-bound streaming kernel.
+#pragma once
+#include "common.cuh"
+#include "ops.cuh"
+#include "simt_gemm.cuh"
+#include "stream_ops.cuh"
+
+namespace vxb {
+namespace bwd {
+
+// ------------------------------------------------------------------------------------------------ GEMM forms
+// C[M,N] (+)= A[M,K] W[K,N]            (dgrad of a linear: dX = dY W)
+inline int gemm_nn(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
+                   bool accumulate, cudaStream_t st) {
+  GemmParams p;
+  gemm_params_init(p);
+  p.M = M; p.N = N; p.K = K;
+  p.A = A; p.lda = lda; p.W = W; p.ldw = ldw; p.C = C; p.ldc = ldc;
+  if (accumulate) { p.residual = C; p.res_rows = M; p.ldr = ldc; }
+  return launch_simt_gemm<A_PLAIN, B_NN, O_PLAIN>(p, 1, st);
+}
+// C[M,N] (+)= A[M,K] W[N,K]^T
+inline int gemm_nt(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
+                   bool accumulate, cudaStream_t st) {
+  GemmParams p;
+  gemm_params_init(p);
+  p.M = M; p.N = N; p.K = K;
+  p.A = A; p.lda = lda; p.W = W; p.ldw = ldw; p.C = C; p.ldc = ldc;
+  if (accumulate) { p.residual = C; p.res_rows = M; p.ldr = ldc; }
+  return launch_simt_gemm<A_PLAIN, B_NT, O_PLAIN>(p, 1, st);
+}
+inline int pick_ksplit(int M, int N, int K) {
+  const long long tiles = (long long)cdiv(M, GBM) * cdiv(N, GBN);
+  if (tiles >= 148 * 2 || K < 4096) return 1;
+  long long want = (148 * 4 + tiles - 1) / tiles;
+  want = std::min<long long>(want, K / 1024);
+  return (int)std::max<long long>(1, want);
+}
+// C[M,N] (+)= At[K,M]^T W[K,N]          (wgrad of a linear: dW = dY^T X); C contiguous (ldc == N) when split-K is used
+inline int gemm_tn(const float* At, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
+                   bool accumulate, cudaStream_t st) {
+  GemmParams p;
+  gemm_params_init(p);
+  p.M = M; p.N = N; p.K = K;
+  p.A = At; p.lda = lda; p.W = W; p.ldw = ldw; p.C = C; p.ldc = ldc;
+  const int ks = (ldc == N) ? pick_ksplit(M, N, K) : 1;
+  if (ks > 1) {
+    if (!accumulate) VXB_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st));
+    p.kchunk = cdiv(cdiv(K, ks), GBK) * GBK;
+    return launch_simt_gemm<A_TRANS, B_NN, O_ATOMIC>(p, cdiv(K, p.kchunk), st);
+  }
+  if (accumulate) { p.residual = C; p.res_rows = M; p.ldr = ldc; }
+  return launch_simt_gemm<A_TRANS, B_NN, O_PLAIN>(p, 1, st);
+}
+
+// ------------------------------------------------------------------------------------------------ small reductions
+// out[n] (+)= sum_m g[m * ld + n]   (bias gradients); out zeroed here unless accumulate
+static __global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ g, long long ld, long long M, int N, long long rows_per_block,
+              float* __restrict__ out) {
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  const long long m0 = (long long)blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float acc = 0.f;
+  if (n < N)
+    for (long long m = m0 + rl; m < m1; m += 8) acc += g[m * ld + n];
+  __shared__ float red[8][32];
+  red[rl][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (rl == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    atomicAdd(out + n, s);
+  }
+}
+inline int colsum(const float* g, long long ld, long long M, int N, float* out, bool accumulate, cudaStream_t st) {
+  if (!accumulate) VXB_CUDA(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st));
+  const int xb = cdiv(N, 32);
+  long long yb = std::max<long long>(1, std::min<long long>((148 * 8 + xb - 1) / xb, (M + 63) / 64));
+  const long long rpb = (M + yb - 1) / yb;
+  yb = (M + rpb - 1) / rpb;
+  colsum_kernel<<<dim3(xb, (unsigned)yb), 256, 0, st>>>(g, ld, M, N, rpb, out);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// out[i] (+)= sum_b x[b * stride + i], i < per   (gradients of batch-broadcast parameters: latents, pos_encoding)
+static __global__ void __launch_bounds__(256)
+batch_sum_kernel(const float* __restrict__ x, long long stride, int B, long long per, float* __restrict__ out, int accumulate) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
+    float s = accumulate ? out[i] : 0.f;
+    for (int b = 0; b < B; ++b) s += x[b * stride + i];
+    out[i] = s;
+  }
+}
+inline int batch_sum(const float* x, long long stride, int B, long long per, float* out, bool accumulate, cudaStream_t st) {
+  batch_sum_kernel<<<(int)std::min<long long>((per + 255) / 256, 148 * 8), 256, 0, st>>>(x, stride, B, per, out, accumulate ? 1 : 0);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise adjoints
+// LeakyReLU: g = y > 0 ? g : slope * g, in place (y > 0 <=> pre-activation > 0)
+static __global__ void __launch_bounds__(256)
+lrelu_bwd_kernel(float* __restrict__ g, const float* __restrict__ y, long long n4, float slope) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 gv = reinterpret_cast<float4*>(g)[i];
+    const float4 yv = reinterpret_cast<const float4*>(y)[i];
+    gv.x = yv.x > 0.f ? gv.x : gv.x * slope;
+    gv.y = yv.y > 0.f ? gv.y : gv.y * slope;
+    gv.z = yv.z > 0.f ? gv.z : gv.z * slope;
+    gv.w = yv.w > 0.f ? gv.w : gv.w * slope;
+    reinterpret_cast<float4*>(g)[i] = gv;
+  }
+}
+inline int lrelu_bwd(float* g, const float* y, long long n, float slope, cudaStream_t st) {
+  if (slope < 0.f) return VXB_OK;   // no activation
+  if (n % 4) {
+    set_error("lrelu_bwd: element count must be a multiple of 4");
+    return VXB_E_BADARG;
+  }
+  lrelu_bwd_kernel<<<(int)std::min<long long>((n / 4 + 255) / 256, 148 * 16), 256, 0, st>>>(g, y, n / 4, slope);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// GEGLU (perceiver_lang_io.py:74-77): y = a * gelu_erf(g), h = [a | g] rows of 2n; gh = [gy * gelu(g) | gy * a * gelu'(g)]
+static __global__ void __launch_bounds__(256)
+geglu_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ h, float* __restrict__ gh, long long rows, int n) {
+  const long long total = rows * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / n;
+    const int c = (int)(i % n);
+    const float a = h[r * 2 * n + c], g = h[r * 2 * n + n + c], go = gy[i];
+    const float cdf = 0.5f * (1.f + erff(g * 0.70710678118654752f));
+    const float pdf = expf(-0.5f * g * g) * 0.3989422804014327f;
+    gh[r * 2 * n + c] = go * g * cdf;
+    gh[r * 2 * n + n + c] = go * a * (cdf + g * pdf);
+  }
+}
+inline int geglu_bwd(const float* gy, const float* h, float* gh, long long rows, int n, cudaStream_t st) {
+  geglu_bwd_kernel<<<148 * 16, 256, 0, st>>>(gy, h, gh, rows, n);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// LayerNorm (eps 1e-5, biased variance).  Warp per row.  gx (=|+=) per the closed form of grad_oracle.layernorm_backward;
+// dw / db are accumulated with atomics (zeroed by the caller).  x and gx rows may be a strided slice per batch.
+static __global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, size_t x_batch_stride, int rows_per_batch,
+                     const float* __restrict__ w, float* __restrict__ gx, int accumulate, float* __restrict__ dw,
+                     float* __restrict__ db, long long rows, int n) {
+  extern __shared__ float ln_smem[];   // [2][n] block partials of dw, db
+  for (int i = threadIdx.x; i < 2 * n; i += 256) ln_smem[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * 8) {
+    const size_t xo = (size_t)(row / rows_per_batch) * x_batch_stride + (size_t)(row % rows_per_batch) * n;
+    const float* xr = x + xo;
+    const float* gr = gy + (size_t)row * n;
+    float s = 0.f;
+    for (int i = lane; i < n; i += 32) s += xr[i];
+    s = warp_sum(s);
+    const float mean = s / (float)n;
+    float q = 0.f;
+    for (int i = lane; i < n; i += 32) { const float d = xr[i] - mean; q += d * d; }
+    q = warp_sum(q);
+    const float rstd = rsqrtf(q / (float)n + 1e-5f);
+    float c1 = 0.f, c2 = 0.f;
+    for (int i = lane; i < n; i += 32) {
+      const float xh = (xr[i] - mean) * rstd, gh = gr[i] * w[i];
+      c1 += gh; c2 += gh * xh;
+    }
+    c1 = warp_sum(c1) / (float)n;
+    c2 = warp_sum(c2) / (float)n;
+    float* gxr = gx + xo;
+    for (int i = lane; i < n; i += 32) {
+      const float xh = (xr[i] - mean) * rstd, g = gr[i];
+      const float v = (g * w[i] - c1 - xh * c2) * rstd;
+      gxr[i] = accumulate ? gxr[i] + v : v;
+      atomicAdd(&ln_smem[i], g * xh);
+      atomicAdd(&ln_smem[n + i], g);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 256) {
+    atomicAdd(dw + i, ln_smem[i]);
+    atomicAdd(db + i, ln_smem[n + i]);
+  }
+}
+inline int layernorm_bwd(const float* gy, const float* x, size_t x_batch_stride, int rows_per_batch, const float* w, float* gx,
+                         bool accumulate, float* dw, float* db, long long rows, int n, cudaStream_t st) {
+  VXB_CUDA(cudaMemsetAsync(dw, 0, (size_t)n * sizeof(float), st));
+  VXB_CUDA(cudaMemsetAsync(db, 0, (size_t)n * sizeof(float), st));
+  const int blocks = (int)std::min<long long>((rows + 7) / 8, 148 * 4);
+  layernorm_bwd_kernel<<<blocks, 256, 2 * n * sizeof(float), st>>>(gy, x, x_batch_stride, rows_per_batch, w, gx,
+                                                                    accumulate ? 1 : 0, dw, db, rows, n);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ attention
+// counter-based dropout mask (train-mode nn.Dropout on the attention probabilities, perceiver_lang_io.py:127-128): element
+// `idx` of stream `seed` is kept when its hashed 32-bit value >= p * 2^32.  Recomputed (never stored) in the backward.
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long idx, unsigned int thresh) {
+  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (unsigned int)(z >> 32) >= thresh;
+}
+inline unsigned int dropout_threshold(float p) {
+  const double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 0xffffffffu : (unsigned int)t;
+}
+// out = dropout(P): rows of n valid columns, leading dimension ld (in place allowed)
+static __global__ void __launch_bounds__(256)
+dropout_rows_kernel(const float* __restrict__ P, float* __restrict__ out, long long rows, int n, int ld,
+                    unsigned long long seed, unsigned int thresh, float inv_keep) {
+  const long long total = rows * ld;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ld);
+    float v = 0.f;
+    if (c < n) v = dropout_keep(seed, (unsigned long long)i, thresh) ? P[i] * inv_keep : 0.f;
+    out[i] = v;
+  }
+}
+// softmax backward in place on gA (gradient w.r.t. the dropped attention): gS = P * (gP - sum(gP * P)) * scale,
+// gP = gA * mask / keep.  Block per row.
+static __global__ void __launch_bounds__(256)
+softmax_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ gA, int n, int ld, float scale,
+                        unsigned long long seed, unsigned int thresh, float inv_keep) {
+  const long long row = blockIdx.x;
+  const float* pr = P + row * ld;
+  float* gr = gA + row * ld;
+  __shared__ float red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float d = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    float g = gr[i];
+    if (thresh) g = dropout_keep(seed, (unsigned long long)(row * ld + i), thresh) ? g * inv_keep : 0.f;
+    d += g * pr[i];
+  }
+  d = warp_sum(d);
+  if (lane == 0) red[warp] = d;
+  __syncthreads();
+  d = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d += red[i];
+  for (int i = threadIdx.x; i < ld; i += 256) {
+    float v = 0.f;
+    if (i < n) {
+      float g = gr[i];
+      if (thresh) g = dropout_keep(seed, (unsigned long long)(row * ld + i), thresh) ? g * inv_keep : 0.f;
+      v = pr[i] * (g - d) * scale;
+    }
+    gr[i] = v;
+  }
+}
+
+struct AttnDropout { float p; unsigned long long seed; };
+
+// forward with materialised probabilities (dispatch.cuh attention_materialized) + train-mode dropout on them
+inline int dropout_rows(const float* P, float* out, long long rows, int n, int ld, const AttnDropout& dr, cudaStream_t st) {
+  dropout_rows_kernel<<<148 * 16, 256, 0, st>>>(P, out, rows, n, ld, dr.seed, dropout_threshold(dr.p), 1.f / (1.f - dr.p));
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// Adjoint of softmax(scale q k^T) v per (batch, head) (grad_oracle.attention_core_backward); probabilities recomputed.
+// q [B or 1 (qbs = 0)][Nq][H*dh] (ldq), k / v rows [B][Nk][...] (ldkv, kvbs), go [B][Nq][H*dh] (ldo, obs).
+// Outputs: gq [B][Nq][H*dh] (ldgq, gqbs: always per batch), gk / gv [B][Nk][...] (ldgkv, gkvbs).
+// bufP / bufG / bufA: [B*H*Nq][pad4(Nk)] floats each (bufA only used with dropout).
+inline int attention_bwd(const float* q, int ldq, long long qbs, const float* k, const float* v, int ldkv, long long kvbs,
+                         const float* go, int ldo, long long obs, float* gq, int ldgq, long long gqbs, float* gk, float* gv,
+                         int ldgkv, long long gkvbs, int B, int H, int Nq, int Nk, int dh, float scale, float* bufP,
+                         float* bufG, float* bufA, const AttnDropout& dr, cudaStream_t st) {
+  const int Nkp = (Nk + 3) / 4 * 4;
+  const long long szb = (long long)H * Nq * Nkp, szh = (long long)Nq * Nkp;
+  GemmParams p;
+  // (1) P = softmax(scale q k^T)
+  gemm_params_init(p);
+  p.M = Nq; p.N = Nk; p.K = dh;
+  p.A = q; p.lda = ldq; p.a_stride_zb = qbs; p.a_stride_zh = dh;
+  p.W = k; p.ldw = ldkv; p.w_stride_zb = kvbs; p.w_stride_zh = dh;
+  p.C = bufP; p.ldc = Nkp; p.c_stride_zb = szb; p.c_stride_zh = szh;
+  p.Hz = H; p.alpha = scale;
+  VXB_TRY((launch_simt_gemm<A_PLAIN, B_NT, O_PLAIN>(p, B * H, st)));
+  softmax_rows_kernel<<<(unsigned)((size_t)B * H * Nq), 256, 0, st>>>(bufP, Nk, Nkp);
+  VXB_LAUNCH_CHECK();
+  // (2) gA = go v^T
+  gemm_params_init(p);
+  p.M = Nq; p.N = Nk; p.K = dh;
+  p.A = go; p.lda = ldo; p.a_stride_zb = obs; p.a_stride_zh = dh;
+  p.W = v; p.ldw = ldkv; p.w_stride_zb = kvbs; p.w_stride_zh = dh;
+  p.C = bufG; p.ldc = Nkp; p.c_stride_zb = szb; p.c_stride_zh = szh;
+  p.Hz = H;
+  VXB_TRY((launch_simt_gemm<A_PLAIN, B_NT, O_PLAIN>(p, B * H, st)));
+  // (3) gv = A^T go, A = dropout(P)
+  const float* A = bufP;
+  const bool drop = dr.p > 0.f;
+  if (drop) {
+    VXB_TRY(dropout_rows(bufP, bufA, (long long)B * H * Nq, Nk, Nkp, dr, st));
+    A = bufA;
+  }
+  gemm_params_init(p);
+  p.M = Nk; p.N = dh; p.K = Nq;
+  p.A = A; p.lda = Nkp; p.a_stride_zb = szb; p.a_stride_zh = szh;
+  p.W = go; p.ldw = ldo; p.w_stride_zb = obs; p.w_stride_zh = dh;
+  p.C = gv; p.ldc = ldgkv; p.c_stride_zb = gkvbs; p.c_stride_zh = dh;
+  p.Hz = H;
+  VXB_TRY((launch_simt_gemm<A_TRANS, B_NN, O_PLAIN>(p, B * H, st)));
+  // (4) gS in place of gA
+  softmax_bwd_rows_kernel<<<(unsigned)((size_t)B * H * Nq), 256, 0, st>>>(bufP, bufG, Nk, Nkp, scale, dr.seed,
+                                                                         drop ? dropout_threshold(dr.p) : 0u,
+                                                                         drop ? 1.f / (1.f - dr.p) : 1.f);
+  VXB_LAUNCH_CHECK();
+  // (5) gq = gS k
+  gemm_params_init(p);
+  p.M = Nq; p.N = dh; p.K = Nk;
+  p.A = bufG; p.lda = Nkp; p.a_stride_zb = szb; p.a_stride_zh = szh;
+  p.W = k; p.ldw = ldkv; p.w_stride_zb = kvbs; p.w_stride_zh = dh;
+  p.C = gq; p.ldc = ldgq; p.c_stride_zb = gqbs; p.c_stride_zh = dh;
+  p.Hz = H;
+  VXB_TRY((launch_simt_gemm<A_PLAIN, B_NN, O_PLAIN>(p, B * H, st)));
+  // (6) gk = gS^T q
+  gemm_params_init(p);
+  p.M = Nk; p.N = dh; p.K = Nq;
+  p.A = bufG; p.lda = Nkp; p.a_stride_zb = szb; p.a_stride_zh = szh;
+  p.W = q; p.ldw = ldq; p.w_stride_zb = qbs; p.w_stride_zh = dh;
+  p.C = gk; p.ldc = ldgkv; p.c_stride_zb = gkvbs; p.c_stride_zh = dh;
+  p.Hz = H;
+  return launch_simt_gemm<A_TRANS, B_NN, O_PLAIN>(p, B * H, st);
+}
+
+// ------------------------------------------------------------------------------------------------ pooling heads
+// first arg-max position of every (b, c) of channels-last x [B, P, C], given the maxima mx[b * mx_stride + c]
+static __global__ void __launch_bounds__(256)
+channel_argmax_kernel(const float* __restrict__ x, const float* __restrict__ mx, int mx_stride, int B, long long P, int C,
+                      int* __restrict__ idx) {
+  const long long total = (long long)B * P * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pos = (i / C) % P;
+    const int b = (int)(i / (P * C));
+    if (x[i] == mx[(size_t)b * mx_stride + c]) atomicMin(idx + b * C + c, (int)pos);
+  }
+}
+inline int channel_argmax(const float* x, const float* mx, int mx_stride, int B, long long P, int C, int* idx, cudaStream_t st) {
+  VXB_CUDA(cudaMemsetAsync(idx, 0x7f, (size_t)B * C * sizeof(int), st));
+  channel_argmax_kernel<<<148 * 16, 256, 0, st>>>(x, mx, mx_stride, B, P, C, idx);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// SpatialSoftmax3D + AdaptiveMaxPool3d(1) adjoint (grad_oracle.spatial_softmax3d_backward / global_maxpool_backward):
+// g[b,v,c] (=|+=) p[v] / T * sum_k ge[b,c,k] (pos[v,k] - e[b,c,k]) + [v == argmax] gm[b,c],
+// p[v] = 2^(x k - m) / s with the forward's own (m, s) (stats [B][2][C]), e = the forward's soft-argmax output.
+static __global__ void __launch_bounds__(256)
+ss_bwd_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ e, int e_stride,
+              const float* __restrict__ ge, int ge_stride, const float* __restrict__ gm, int gm_stride,
+              const int* __restrict__ argidx, float* __restrict__ g, int accumulate, int B, int Dd, int Hh, int Ww, int C) {
+  const long long P = (long long)Dd * Hh * Ww;
+  const long long total = (long long)B * P * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pos = (i / C) % P;
+    const int b = (int)(i / (P * C));
+    const int w = (int)(pos % Ww), h = (int)((pos / Ww) % Hh), d = (int)(pos / ((long long)Ww * Hh));
+    // meshgrid('xy') quirk of network_utils.py:782-792: pos_x along H, pos_y along D, pos_z along W
+    const float px = ss_lin_coord(h, Hh), py = ss_lin_coord(d, Dd), pz = ss_lin_coord(w, Ww);
+    const float m = stats[((size_t)b * 2) * C + c], s = stats[((size_t)b * 2 + 1) * C + c];
+    const float p = exp2f(x[i] * kSSLog2eOverT - m) / s;
+    const float* eb = e + (size_t)b * e_stride + c * 3;
+    const float* gb = ge + (size_t)b * ge_stride + c * 3;
+    const float inner = gb[0] * (px - eb[0]) + gb[1] * (py - eb[1]) + gb[2] * (pz - eb[2]);
+    float v = p * inner * 100.f;   // 1 / T, T = 0.01
+    if ((int)pos == argidx[b * C + c]) v += gm[(size_t)b * gm_stride + c];
+    g[i] = accumulate ? g[i] + v : v;
+  }
+}
+inline int ss_bwd(const float* x, const float* stats, const float* e, int e_stride, const float* ge, int ge_stride,
+                  const float* gm, int gm_stride, const int* argidx, float* g, bool accumulate, int B, int Dd, int Hh, int Ww,
+                  int C, cudaStream_t st) {
+  ss_bwd_kernel<<<148 * 16, 256, 0, st>>>(x, stats, e, e_stride, ge, ge_stride, gm, gm_stride, argidx, g, accumulate ? 1 : 0, B,
+                                          Dd, Hh, Ww, C);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ convolutions
+// Adjoint of replicate padding (grad_oracle.replicate_pad_backward) generalised to a padded-gradient grid of extent
+// Pn per axis (Pn = V + 2 pad for stride-1 convolutions, Pn = S * s for the stride-s patchify windows):
+//   g[b, v, c] (=|+=) sum_{p in [0, Pn)^3 : clamp(p - pad, 0, V-1) == v} gxp[b, p, c0 + c]
+static __global__ void __launch_bounds__(256)
+fold_pad_kernel(const float* __restrict__ gxp, int Cx, int c0, int Pn, int pad, float* __restrict__ g, int Cg, int V, int B,
+                int accumulate) {
+  const int cg = Cg / 4;
+  const long long total = (long long)B * V * V * V * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cg) * 4;
+    long long r = i / cg;
+    const int x = (int)(r % V); r /= V;
+    const int y = (int)(r % V); r /= V;
+    const int z = (int)(r % V);
+    const int b = (int)(r / V);
+    const int zlo = z == 0 ? 0 : z + pad, zhi = min(z == V - 1 ? Pn - 1 : z + pad, Pn - 1);
+    const int ylo = y == 0 ? 0 : y + pad, yhi = min(y == V - 1 ? Pn - 1 : y + pad, Pn - 1);
+    const int xlo = x == 0 ? 0 : x + pad, xhi = min(x == V - 1 ? Pn - 1 : x + pad, Pn - 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int pz = zlo; pz <= zhi; ++pz)
+      for (int py = ylo; py <= yhi; ++py)
+        for (int px = xlo; px <= xhi; ++px) {
+          const float4 v = *reinterpret_cast<const float4*>(gxp + ((((size_t)b * Pn + pz) * Pn + py) * Pn + px) * Cx + c0 + c);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    float4* o = reinterpret_cast<float4*>(g + (i / cg) * Cg + c);
+    if (accumulate) { const float4 t = *o; acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
+    *o = acc;
+  }
+}
+inline int fold_pad(const float* gxp, int Cx, int c0, int Pn, int pad, float* g, int Cg, int V, int B, bool accumulate,
+                    cudaStream_t st) {
+  fold_pad_kernel<<<148 * 16, 256, 0, st>>>(gxp, Cx, c0, Pn, pad, g, Cg, V, B, accumulate ? 1 : 0);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// dgrad weights of a stride-1 convolution from the PyTorch layout w[Co][Ci][k^3]:
+//   wd[ci][t'][co] = w[co][ci][k^3 - 1 - t']   (all three axes flipped: gxp[p] = sum_t w_t^T gz[p - t])
+static __global__ void conv_dgrad_weight_kernel(const float* __restrict__ w, float* __restrict__ wd, int Co, int Ci, int k3) {
+  const size_t total = (size_t)Co * Ci * k3;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Co);
+    const int t = (int)((i / Co) % k3);
+    const int ci = (int)(i / ((size_t)Co * k3));
+    wd[i] = w[((size_t)co * Ci + ci) * k3 + (k3 - 1 - t)];
+  }
+}
+// the same for the folded up-convolution: wfold[r][co][nb][ci] -> wd[ci][nb'][r * Co + co] = wfold[r][co][26 - nb'][ci]
+static __global__ void fold_dgrad_weight_kernel(const float* __restrict__ wf, float* __restrict__ wd, int R, int Co, int Ci) {
+  const size_t total = (size_t)R * Co * 27 * Ci;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int rc = (int)(i % ((size_t)R * Co));
+    const int nb = (int)((i / ((size_t)R * Co)) % 27);
+    const int ci = (int)(i / ((size_t)R * Co * 27));
+    const int r = rc / Co, co = rc % Co;
+    wd[i] = wf[(((size_t)r * Co + co) * 27 + (26 - nb)) * Ci + ci];
+  }
+}
+// patchify (stride == k) dgrad weights: wd[t][ci][co] = w[co][ci][t]
+static __global__ void patch_dgrad_weight_kernel(const float* __restrict__ w, float* __restrict__ wd, int Co, int Ci, int k3) {
+  const size_t total = (size_t)Co * Ci * k3;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Co);
+    const int ci = (int)((i / Co) % Ci);
+    const int t = (int)(i / ((size_t)Co * Ci));
+    wd[i] = w[((size_t)co * Ci + ci) * k3 + t];
+  }
+}
+// wgrad GEMM output [k^3][Ci][Co] -> PyTorch layout dw[Co][Ci][k^3]
+static __global__ void wgrad_to_torch_kernel(const float* __restrict__ t, float* __restrict__ dw, int Co, int Ci, int k3) {
+  const size_t total = (size_t)Co * Ci * k3;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % k3);
+    const int ci = (int)((i / k3) % Ci);
+    const int co = (int)(i / ((size_t)k3 * Ci));
+    dw[i] = t[((size_t)tap * Ci + ci) * Co + co];
+  }
+}
+
+// gxp[b, p, 0:Ci] = sum_t w_t^T gz[b, p - t] on the padded-gradient grid (V + 2 pad)^3, gz zero outside [0, V)^3:
+// implicit GEMM with the zero-out-of-bounds gather.  wd from conv_dgrad_weight_kernel ([Ci][k^3][Co]).
+inline int conv_dgrad_padded(const float* gz, int Co, const float* wd, int Ci, float* gxp, int B, int V, int k, cudaStream_t st) {
+  if (Co % GBK || Co % 4) {
+    set_error("conv_dgrad: Co=%d must be a multiple of %d", Co, GBK);
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  const int pad = k / 2, Pn = V + 2 * pad;
+  GemmParams p;
+  gemm_params_init(p);
+  p.M = B * Pn * Pn * Pn; p.N = Ci; p.K = k * k * k * Co;
+  p.src0 = gz; p.src1 = nullptr; p.C0 = Co; p.C1 = 0;
+  p.Di = V; p.Do = Pn; p.kk = k; p.cstride = 1; p.pad = 2 * pad; p.zero_oob = 1;
+  p.W = wd; p.ldw = p.K;
+  p.C = gxp; p.ldc = Ci;
+  return launch_simt_gemm<A_CONV, B_NT, O_PLAIN>(p, 1, st);
+}
+
+// dwt[(tap, ci)][co] = sum_rows x[clamp(o * stride - pad + tap)][ci] gz[row][co]   (transposed-im2col GEMM, split-K)
+// x = concat(src0[C0], src1[C1]) channels-last on a Di^3 grid, gz [B, Do^3, Co]; dwt zeroed here.
+inline int conv_wgrad(const float* src0, const float* src1, int C0, int C1, const float* gz, int Co, float* dwt, int B, int Di,
+                      int Do, int k, int stride, cudaStream_t st) {
+  const int Cin = C0 + C1;
+  if (Cin % 4 || C0 % 4) {
+    set_error("conv_wgrad: channel counts must be multiples of 4");
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  GemmParams p;
+  gemm_params_init(p);
+  p.M = k * k * k * Cin; p.N = Co; p.K = B * Do * Do * Do;
+  p.src0 = src0; p.src1 = src1; p.C0 = C0; p.C1 = C1;
+  p.Di = Di; p.Do = Do; p.kk = k; p.cstride = stride; p.pad = k / 2;
+  p.W = gz; p.ldw = Co;
+  p.C = dwt; p.ldc = Co;
+  VXB_CUDA(cudaMemsetAsync(dwt, 0, (size_t)p.M * Co * sizeof(float), st));
+  const int ks = pick_ksplit(p.M, p.N, p.K);
+  p.kchunk = cdiv(cdiv(p.K, ks), GBK) * GBK;
+  return launch_simt_gemm<A_CONV_T, B_NN, O_ATOMIC>(p, cdiv(p.K, p.kchunk), st);
+}
+
+// fine grid [B, (S s)^3, C] -> coarse-major phases [B, S^3, s^3 * C]: out[b, q, r * C + c] = in[b, s q + r, c],
+// r = (rd s + rh) s + rw (the phase order of fold_upconv_weights_kernel)
+static __global__ void __launch_bounds__(256)
+phase_gather_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int S, int s, int C) {
+  const int cg = C / 4, R = s * s * s, V = S * s;
+  const long long total = (long long)B * S * S * S * R * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cg) * 4;
+    long long t = i / cg;
+    const int r = (int)(t % R); t /= R;
+    const int qw = (int)(t % S); t /= S;
+    const int qh = (int)(t % S); t /= S;
+    const int qd = (int)(t % S);
+    const int b = (int)(t / S);
+    const int rd = r / (s * s), rh = (r / s) % s, rw = r % s;
+    const size_t src = ((((size_t)b * V + qd * s + rd) * V + qh * s + rh) * V + qw * s + rw) * C + c;
+    *reinterpret_cast<float4*>(out + (i / cg) * C + c) = *reinterpret_cast<const float4*>(in + src);
+  }
+}
+
+// transpose of fold_upconv_weights_kernel: dwt[(nb, ci)][(r, co)] (the wgrad GEMM output of the folded form)
+// -> dw[co][ci][k^3] of the original k x k x k convolution applied after the trilinear x s upsampling
+static __global__ void fold_upconv_weights_bwd_kernel(const float* __restrict__ dwt, float* __restrict__ dw, int Co, int Ci,
+                                                      int k, int s) {
+  const int pad = k / 2, k3 = k * k * k, R = s * s * s;
+  const size_t total = (size_t)Co * Ci * k3;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % k3);
+    const int ci = (int)((i / k3) % Ci);
+    const int co = (int)(i / ((size_t)k3 * Ci));
+    const int td = t / (k * k), th = (t / k) % k, tw = t % k;
+    float acc = 0.f;
+    for (int rd = 0; rd < s; ++rd)
+      for (int nd = -1; nd <= 1; ++nd) {
+        const float ud = upsample_tap_weight(rd + td - pad, nd, s);
+        if (ud == 0.f) continue;
+        for (int rh = 0; rh < s; ++rh)
+          for (int nh = -1; nh <= 1; ++nh) {
+            const float uh = upsample_tap_weight(rh + th - pad, nh, s);
+            if (uh == 0.f) continue;
+            for (int rw = 0; rw < s; ++rw)
+              for (int nw = -1; nw <= 1; ++nw) {
+                const float uw = upsample_tap_weight(rw + tw - pad, nw, s);
+                if (uw == 0.f) continue;
+                const int nb = ((nd + 1) * 3 + (nh + 1)) * 3 + (nw + 1);
+                const int r = (rd * s + rh) * s + rw;
+                acc += dwt[((size_t)nb * Ci + ci) * ((size_t)R * Co) + (size_t)r * Co + co] * (ud * uh * uw);
+              }
+          }
+      }
+    dw[i] = acc;
+  }
+}
+
+// trans_decoder (Conv3d 64 -> 1, k3, replicate pad, no activation) adjoint, gather form:
+//   G[v][t] = sum_{o : clamp(o + t - 1) == v} g[o];   gu[v][c] (+)= sum_t w[t][c] G[v][t];   dw[t][c] += u[v][c] G[v][t]
+// 16 threads per voxel (4 channels each); dw accumulated per block in shared memory, then atomically (dw zeroed by caller).
+template <int C>
+static __global__ void __launch_bounds__(256)
+trans_bwd_kernel(const float* __restrict__ g, const float* __restrict__ u, const float* __restrict__ wt /*[27][C]*/,
+                 float* __restrict__ gu, int accumulate, float* __restrict__ dwt /*[27][C]*/, int B, int V) {
+  constexpr int G4 = C / 4;
+  __shared__ float sdw[27 * C];
+  for (int i = threadIdx.x; i < 27 * C; i += 256) sdw[i] = 0.f;
+  __syncthreads();
+  const long long total = (long long)B * V * V * V * G4;
+  float acc[27][4];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+  int cgrp = -1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % G4) * 4;
+    cgrp = c;                                   // gridDim.x * 256 is a multiple of G4: a thread keeps its channel group
+    long long r = i / G4;
+    const int x = (int)(r % V); r /= V;
+    const int y = (int)(r % V); r /= V;
+    const int z = (int)(r % V);
+    const int b = (int)(r / V);
+    const float* gb = g + (size_t)b * V * V * V;
+    const float4 uv = *reinterpret_cast<const float4*>(u + (i / G4) * C + c);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dz = 0; dz < 3; ++dz) {
+      int zs[2], nz = 0;
+      { const int a = z - dz + 1; if (a >= 0 && a < V) zs[nz++] = a; if (z == 0 && dz == 0) zs[nz++] = 0; if (z == V - 1 && dz == 2) zs[nz++] = V - 1; }
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        int ys[2], ny = 0;
+        { const int a = y - dy + 1; if (a >= 0 && a < V) ys[ny++] = a; if (y == 0 && dy == 0) ys[ny++] = 0; if (y == V - 1 && dy == 2) ys[ny++] = V - 1; }
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          int xs[2], nx = 0;
+          { const int a = x - dx + 1; if (a >= 0 && a < V) xs[nx++] = a; if (x == 0 && dx == 0) xs[nx++] = 0; if (x == V - 1 && dx == 2) xs[nx++] = V - 1; }
+          float G = 0.f;
+          for (int a = 0; a < nz; ++a)
+            for (int bb = 0; bb < ny; ++bb)
+              for (int cc = 0; cc < nx; ++cc) G += __ldg(gb + ((size_t)zs[a] * V + ys[bb]) * V + xs[cc]);
+          const int t = (dz * 3 + dy) * 3 + dx;
+          const float4 wv = *reinterpret_cast<const float4*>(wt + t * C + c);
+          o.x = fmaf(wv.x, G, o.x); o.y = fmaf(wv.y, G, o.y); o.z = fmaf(wv.z, G, o.z); o.w = fmaf(wv.w, G, o.w);
+          acc[t][0] = fmaf(uv.x, G, acc[t][0]); acc[t][1] = fmaf(uv.y, G, acc[t][1]);
+          acc[t][2] = fmaf(uv.z, G, acc[t][2]); acc[t][3] = fmaf(uv.w, G, acc[t][3]);
+        }
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(gu + (i / G4) * C + c);
+    if (accumulate) { const float4 t4 = *dst; o.x += t4.x; o.y += t4.y; o.z += t4.z; o.w += t4.w; }
+    *dst = o;
+  }
+  if (cgrp >= 0) {
+#pragma unroll
+    for (int t = 0; t < 27; ++t)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&sdw[t * C + cgrp + j], acc[t][j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * C; i += 256) atomicAdd(dwt + i, sdw[i]);
+}
+
+// token disassembly (adjoint of assemble_tokens_kernel): g_ins [B, nl+T, C] ->
+//   g_lang [B, nl, C], g_patch [B, T, im], g_p1 [B, im] (+ g_p2) = sum over the T voxel tokens of the proprio channels
+static __global__ void __launch_bounds__(256)
+disassemble_tokens_kernel(const float* __restrict__ gins, float* __restrict__ glang, float* __restrict__ gpatch, int B, int nl,
+                          int T, int C, int im) {
+  const size_t total = (size_t)B * (nl + T) * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const size_t row = i / C;
+    const int j = (int)(row % (nl + T));
+    const int b = (int)(row / (nl + T));
+    if (j < nl) glang[((size_t)b * nl + j) * C + c] = gins[i];
+    else if (c < im) gpatch[((size_t)b * T + (j - nl)) * im + c] = gins[i];
+  }
+}
+// g_p[b, c] = sum_t gins[b, nl + t, c_off + c]
+static __global__ void __launch_bounds__(256)
+proprio_token_sum_kernel(const float* __restrict__ gins, float* __restrict__ gp, int nl, int T, int C, int c_off, int im) {
+  const int b = blockIdx.x;
+  const int c = threadIdx.x & 63, tl = threadIdx.x >> 6;   // im == 64: 4 token lanes
+  float acc = 0.f;
+  if (c < im)
+    for (int t = tl; t < T; t += 4) acc += gins[((size_t)b * (nl + T) + nl + t) * C + c_off + c];
+  __shared__ float red[4][64];
+  red[tl][c] = acc;
+  __syncthreads();
+  if (tl == 0 && c < im) gp[(size_t)b * im + c] = red[0][c] + red[1][c] + red[2][c] + red[3][c];
+}
+
+}  // namespace bwd
+}  // namespace vxb

@@ -221,6 +221,7 @@ static void carve_work(const Dims& m, int B, Arena& a, Work& w) {
   // scratch for operand planes: the largest of the GEMM / conv shapes of the forward
   size_t sb = 0;
   sb = std::max(sb, umma::linear_scratch_bytes((long long)B * m.L, 8 * m.D, 4 * m.D, false));
+  sb = std::max(sb, umma::linear_scratch_bytes((long long)B * m.L, 8 * m.D, m.D, true));   // training: FF net.0 weights split on the fly
   sb = std::max(sb, umma::linear_scratch_bytes((long long)B * m.n, 8 * m.D, std::max(m.C, 512), false));
   sb = std::max(sb, umma::conv3d_scratch_bytes(B, m.V, 64, 64, 3));
   sb = std::max(sb, umma::conv3d_scratch_bytes(B, m.S, m.C, 0, m.k));
@@ -521,6 +522,8 @@ static int conv_weight_prepare(const float* w, float* o, int Co, int Ci, int k3,
 }
 
 }  // namespace vxb
+
+#include "qnet_train.cuh"
 
 using namespace vxb;
 
@@ -901,4 +904,90 @@ extern "C" int vxb_profile_read(double* ms) {
   g_prof.calls.clear();
   g_prof.cur = nullptr;
   return ncalls;
+}
+
+// ---- training step: forward that keeps the activations + backward
+static int train_setup(const vxb_qnet_desc* d, const vxb_train_opts* o, Dims& m, TrainDropout& drop) {
+  VXB_TRY(make_dims(d, m));
+  VXB_TRY(train_supported(d, m));
+  VXB_CHECK_ARG(o && o->struct_bytes == (int)sizeof(vxb_train_opts), "qnet training: bad vxb_train_opts");
+  VXB_CHECK_ARG(o->input_dropout >= 0.f && o->input_dropout < 1.f && o->attn_dropout >= 0.f && o->attn_dropout < 1.f &&
+                o->decoder_dropout >= 0.f && o->decoder_dropout < 1.f, "qnet training: dropout probabilities must be in [0, 1)");
+  drop.input = o->input_dropout; drop.attn = o->attn_dropout; drop.decoder = o->decoder_dropout; drop.seed = o->seed;
+  return VXB_OK;
+}
+
+extern "C" size_t vxb_qnet_train_workspace_bytes(const vxb_qnet_desc* d, int B) {
+  Dims m;
+  if (make_dims(d, m) != VXB_OK || B <= 0 || train_supported(d, m) != VXB_OK) return 0;
+  Arena a(nullptr, 0);
+  Work w;
+  carve_work(m, B, a, w);
+  TrainBufs t;
+  carve_train(m, B, a, t);
+  return a.off;
+}
+
+extern "C" int vxb_qnet_forward_train_f32(const vxb_qnet_desc* d, const void* const* params, const void* prepared,
+                                          const float* grid, const float* proprio, const float* lang_tokens, int B,
+                                          float* q_trans, float* rot_grip, float* collision, float* arm_out,
+                                          const vxb_train_opts* opts, void* ws, size_t ws_bytes, void* stream) {
+  Dims m;
+  TrainDropout drop;
+  VXB_TRY(train_setup(d, opts, m, drop));
+  VXB_CHECK_ARG(B > 0 && params && prepared && grid && proprio && q_trans && rot_grip && collision && ws,
+                "qnet_forward_train: null pointer argument");
+  VXB_CHECK_ARG(d->no_language || lang_tokens, "qnet_forward_train: lang_tokens is null");
+  VXB_CHECK_ARG(!d->arm_pred_loss || arm_out, "qnet_forward_train: arm_pred_loss set but arm_out is null");
+  Arena pa((void*)prepared, (size_t)-1);
+  Prepared pw;
+  carve_prepared(m, pa, pw, params);
+  Arena wa(ws, ws_bytes);
+  Work w;
+  carve_work(m, B, wa, w);
+  TrainBufs t;
+  carve_train(m, B, wa, t);
+  if (!wa.ok) {
+    set_error("qnet_forward_train: workspace too small (%zu < %zu)", ws_bytes, wa.off);
+    return VXB_E_WORKSPACE_TOO_SMALL;
+  }
+  return qnet_forward_train_impl(d, m, params, pw, w, t, grid, proprio, lang_tokens, B, q_trans, rot_grip, collision, arm_out,
+                                 drop, (cudaStream_t)stream);
+}
+
+extern "C" int vxb_qnet_backward_f32(const vxb_qnet_desc* d, const void* const* params, const void* prepared,
+                                     const float* grid, const float* proprio, const float* lang_tokens, int B,
+                                     const float* g_trans, const float* g_rot_grip, const float* g_collision, const float* g_arm,
+                                     float* const* grads, const vxb_train_opts* opts, float* const* debug, void* ws,
+                                     size_t ws_bytes, void* stream) {
+  Dims m;
+  TrainDropout drop;
+  VXB_TRY(train_setup(d, opts, m, drop));
+  VXB_CHECK_ARG(B > 0 && params && prepared && grid && proprio && g_trans && g_rot_grip && g_collision && grads && ws,
+                "qnet_backward: null pointer argument");
+  const int np = vxb_qnet_num_params(d);
+  for (int i = 0; i < np; ++i)
+    VXB_CHECK_ARG((params[i] == nullptr) == (grads[i] == nullptr) || grads[i] == nullptr || params[i] != nullptr,
+                  "qnet_backward: gradient buffer for a missing parameter (slot %d)", i);
+  for (int i = 0; i < np; ++i) {
+    const bool used = params[i] != nullptr && !(i == VXB_P_DENSE2_W || i == VXB_P_DENSE2_B || i == VXB_P_ARM_W || i == VXB_P_ARM_B) ;
+    VXB_CHECK_ARG(!used || grads[i] != nullptr, "qnet_backward: missing gradient buffer for parameter slot %d", i);
+  }
+  VXB_CHECK_ARG(!(d->arm_pred_loss && g_arm) || (grads[VXB_P_DENSE2_W] && grads[VXB_P_DENSE2_B] && grads[VXB_P_ARM_W] && grads[VXB_P_ARM_B]),
+                "qnet_backward: g_arm given without gradient buffers for dense2 / arm_ff");
+  Arena pa((void*)prepared, (size_t)-1);
+  Prepared pw;
+  carve_prepared(m, pa, pw, params);
+  Arena wa(ws, ws_bytes);
+  Work w;
+  carve_work(m, B, wa, w);
+  TrainBufs t;
+  carve_train(m, B, wa, t);
+  if (!wa.ok) {
+    set_error("qnet_backward: workspace too small (%zu < %zu)", ws_bytes, wa.off);
+    return VXB_E_WORKSPACE_TOO_SMALL;
+  }
+  Grads G{grads};
+  return qnet_backward_impl(d, m, params, pw, w, t, grid, proprio, lang_tokens, B, g_trans, g_rot_grip, g_collision, g_arm, G,
+                            debug, drop, (cudaStream_t)stream);
 }

@@ -165,7 +165,8 @@ ss_partial_kernel(const float* __restrict__ x, int P, int C, int Dd, int Hh, int
 // layout, merged by a second launch) -- the fused conv tail leaves thousands of chunk partials per sample.
 static __global__ void __launch_bounds__(256)
 ss_merge_kernel(const float* __restrict__ partial, int chunks, int C, float* __restrict__ ss,
-                int ss_stride, float* __restrict__ mx, int mx_stride, float* __restrict__ partial_out) {
+                int ss_stride, float* __restrict__ mx, int mx_stride, float* __restrict__ partial_out,
+                float* __restrict__ stats /* optional [B][2][C]: (m, s) of the softmax, kept for the backward */) {
   const int b = blockIdx.y;
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int kl = threadIdx.x >> 5;
@@ -197,6 +198,7 @@ ss_merge_kernel(const float* __restrict__ partial, int chunks, int C, float* __r
       float* o = ss + (size_t)b * ss_stride + c * 3;
       o[0] = a.sx / a.s; o[1] = a.sy / a.s; o[2] = a.sz / a.s;
       if (mx) mx[(size_t)b * mx_stride + c] = a.rm;  // AdaptiveMaxPool3d(1)
+      if (stats) { stats[((size_t)b * 2) * C + c] = a.m; stats[((size_t)b * 2 + 1) * C + c] = a.s; }
     }
   }
 }
@@ -356,7 +358,7 @@ inline size_t ss_partial_floats(size_t P, int B, int C) { return (size_t)B * ss_
 
 // launches 2 kernels
 inline int spatial_softmax_run(const float* x, int B, int Dd, int Hh, int Ww, int C, float* ss, int ss_stride,
-                               float* mx, int mx_stride, float* partial, cudaStream_t st) {
+                               float* mx, int mx_stride, float* partial, cudaStream_t st, float* stats = nullptr) {
   VXB_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 1024, "spatial_softmax: C=%d must be a multiple of 4, <= 1024", C);
   VXB_CHECK_ARG(((uintptr_t)x & 15) == 0, "spatial_softmax: input must be 16-byte aligned");
   const size_t P = (size_t)Dd * Hh * Ww;
@@ -366,7 +368,7 @@ inline int spatial_softmax_run(const float* x, int B, int Dd, int Hh, int Ww, in
   const size_t smem = ((size_t)(Dd + Hh + Ww) + (size_t)PL * G * 24) * sizeof(float);
   ss_partial_kernel<<<dim3(chunks, B), SS_THREADS, smem, st>>>(x, (int)P, C, Dd, Hh, Ww, chunk, partial);
   VXB_LAUNCH_CHECK();
-  ss_merge_kernel<<<dim3(cdiv(C, 32), B), 256, 0, st>>>(partial, chunks, C, ss, ss_stride, mx, mx_stride, nullptr);
+  ss_merge_kernel<<<dim3(cdiv(C, 32), B), 256, 0, st>>>(partial, chunks, C, ss, ss_stride, mx, mx_stride, nullptr, stats);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }
@@ -376,7 +378,7 @@ template <int CIN>
 inline int input_preprocess_ss_run(const float* x, const float* w, const float* bias, float slope, float* y, int B,
                                    int Dd, int Hh, int Ww, int C, float* ss, int ss_stride, float* mx, int mx_stride,
                                    float* partial, cudaStream_t st, __nv_bfloat16* phi = nullptr,
-                                   __nv_bfloat16* plo = nullptr) {
+                                   __nv_bfloat16* plo = nullptr, float* stats = nullptr) {
   VXB_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 1024, "input_preprocess: C=%d must be a multiple of 4, <= 1024", C);
   VXB_CHECK_ARG(slope <= 1.f, "input_preprocess: LeakyReLU slope %g must be <= 1 (negative = no activation)", (double)slope);
   const size_t P = (size_t)Dd * Hh * Ww;
@@ -388,7 +390,7 @@ inline int input_preprocess_ss_run(const float* x, const float* w, const float* 
   input_preprocess_ss_kernel<CIN><<<dim3(chunks, B), SS_THREADS, smem, st>>>(x, w, bias, slope, y, (int)P, C, Dd, Hh, Ww,
                                                                             chunk, partial, phi, plo);
   VXB_LAUNCH_CHECK();
-  ss_merge_kernel<<<dim3(cdiv(C, 32), B), 256, 0, st>>>(partial, chunks, C, ss, ss_stride, mx, mx_stride, nullptr);
+  ss_merge_kernel<<<dim3(cdiv(C, 32), B), 256, 0, st>>>(partial, chunks, C, ss, ss_stride, mx, mx_stride, nullptr, stats);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }

@@ -1006,9 +1006,9 @@ int conv3_tail_finish(const ConvTail& tail, int B, int V, cudaStream_t st) {
   const int chunks = zchunks * tiles * 16;
   // two-level merge: 32 slices of the chunk list per sample, then the slices
   float* level1 = tail.ss_partial + (size_t)B * chunks * 6 * 64;
-  ss_merge_kernel<<<dim3(cdiv(64, 32), B, kTailMergeSplits), 256, 0, st>>>(tail.ss_partial, chunks, 64, nullptr, 0, nullptr, 0, level1);
+  ss_merge_kernel<<<dim3(cdiv(64, 32), B, kTailMergeSplits), 256, 0, st>>>(tail.ss_partial, chunks, 64, nullptr, 0, nullptr, 0, level1, nullptr);
   VXB_LAUNCH_CHECK();
-  ss_merge_kernel<<<dim3(cdiv(64, 32), B), 256, 0, st>>>(level1, kTailMergeSplits, 64, tail.ss, tail.ss_stride, tail.mx, tail.mx_stride, nullptr);
+  ss_merge_kernel<<<dim3(cdiv(64, 32), B), 256, 0, st>>>(level1, kTailMergeSplits, 64, tail.ss, tail.ss_stride, tail.mx, tail.mx_stride, nullptr, nullptr);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }

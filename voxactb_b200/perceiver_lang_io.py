@@ -112,6 +112,26 @@ def _spatial_positions(n):
     return [torch.from_numpy(a.reshape(-1)).float() for a in (px, py, pz)]
 
 
+class _QnetTrainFn(torch.autograd.Function):
+    """Training-mode forward/backward of the encoder as ONE autograd node: `total_loss.backward()` in the reference's
+    agent.update (qattention_peract_bc_agent.py:581) reaches vxb_qnet_backward_f32 through it, and the parameter
+    gradients come back as ordinary `.grad` tensors (so torch optimizers, the reference's Lamb and DDP hooks all work)."""
+
+    @staticmethod
+    def forward(ctx, enc, grid, proprio, lang, *params):
+        outs, gen = enc._forward_train(grid, proprio, lang)
+        ctx.enc, ctx.gen = enc, gen
+        ctx.inputs = (grid, proprio, lang)
+        ctx.n_params = len(params)
+        ctx.set_materialize_grads(False)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        grads = ctx.enc._backward_train(ctx.gen, ctx.inputs, gouts)
+        return (None, None, None, None) + tuple(grads)
+
+
 class PerceiverVoxelLangEncoder(nn.Module):
     """Drop-in for reference perceiver_lang_io.py:136 (same keywords and defaults)."""
 
@@ -272,6 +292,10 @@ class PerceiverVoxelLangEncoder(nn.Module):
         self._prepared = None
         self._prepared_key = None
         self._workspace = None
+        self._train_ws = None
+        self._train_gen = 0
+        self._train_opts = None
+        self.dropout_seed = None      # None: derived from torch.initial_seed(); advanced by one per training forward
         self.last_launch_count = 0
 
     # ------------------------------------------------------------------ plumbing
@@ -280,6 +304,8 @@ class PerceiverVoxelLangEncoder(nn.Module):
         state['_prepared'] = None
         state['_prepared_key'] = None
         state['_workspace'] = None
+        state['_train_ws'] = None
+        state['_train_opts'] = None
         return state
 
     def __deepcopy__(self, memo):
@@ -292,10 +318,17 @@ class PerceiverVoxelLangEncoder(nn.Module):
         return new
 
     def _apply(self, fn, *a, **kw):
-        self._prepared = None
-        self._prepared_key = None
+        self.invalidate_prepared()
         self._workspace = None
+        self._train_ws = None
         return super()._apply(fn, *a, **kw)
+
+    def invalidate_prepared(self):
+        """Drop the prepared-weight cache (fp16 hi/lo planes, folded up-conv weights, to_q(LN(latents))).  The cache is
+        keyed on each parameter's (data_ptr, _version), which catches in-place updates, load_state_dict and this
+        package's fused optimizers; call this after writing through `p.data` (e.g. the reference's lamb.py) in EVAL
+        mode -- in training mode the weights are re-prepared on every forward anyway."""
+        self._prepared_key = None
 
     def _desc(self):
         d = _lib.QnetDesc()
@@ -347,7 +380,7 @@ class PerceiverVoxelLangEncoder(nn.Module):
     def _ensure_prepared(self, desc, arr, slots, device):
         key = (device, int(self.math_mode),
                tuple((p.data_ptr(), p._version) for p in slots if p is not None))
-        if self._prepared is not None and self._prepared_key == key:
+        if self._prepared is not None and self._prepared_key == key and not self.training:
             return
         L = _lib.lib()
         nbytes = L.vxb_qnet_prepared_bytes(ctypes.byref(desc))
@@ -374,14 +407,20 @@ class PerceiverVoxelLangEncoder(nn.Module):
     def _run(self, ins, proprio, proprio2, lang_token_embs, mask):
         if mask is not None:
             raise NotImplementedError('attention mask is never passed by the agent (always None)')
-        if self.training and (self.input_dropout > 0 or self.attn_dropout > 0 or self.decoder_dropout > 0):
-            raise NotImplementedError(
-                'training-mode dropout / backward are not built yet: call .eval() (inference path)')
         if not ins.is_cuda:
             raise RuntimeError('voxactb_b200.PerceiverVoxelLangEncoder runs on CUDA only (no CPU fallback)')
         B, C10, V = ins.shape[0], ins.shape[1], ins.shape[2]
         if C10 != self.init_dim or V != self.voxel_size:
             raise ValueError('expected ins [B,%d,%d,%d,%d], got %s' % (self.init_dim, self.voxel_size, self.voxel_size, self.voxel_size, tuple(ins.shape)))
+        if self.training and torch.is_grad_enabled():
+            # training step (row a18): one autograd node around vxb_qnet_forward_train_f32 / vxb_qnet_backward_f32
+            if self.TWO_ROBOTS:
+                raise NotImplementedError('the 2-robot encoder is inference-only in voxactb_b200 (training: single-arm encoders)')
+            grid = _lib.f32(ins.detach().permute(0, 2, 3, 4, 1))
+            plist = [p for p in self._param_table()[2] if p is not None]
+            outs = _QnetTrainFn.apply(self, grid, _lib.f32(proprio.detach()), _lib.f32(lang_token_embs.detach()), *plist)
+            arm = outs[3] if self.arm_pred_loss else None
+            return outs[0], outs[1], outs[2], None, None, None, arm
         with torch.no_grad():
             grid = _lib.f32(ins.permute(0, 2, 3, 4, 1))      # no copy when ins is the permuted view
             proprio = _lib.f32(proprio)
@@ -421,6 +460,89 @@ class PerceiverVoxelLangEncoder(nn.Module):
             self.last_launch_count = L.vxb_last_launch_count()
             del keep
         return trans, rot_grip, coll, trans2, rot_grip2, coll2, arm
+
+
+def _train_methods():
+    def _train_setup(self, grid, proprio, lang):
+        B, V = grid.shape[0], grid.shape[1]
+        if proprio.shape != (B, self.low_dim_size):
+            raise ValueError('proprio must be [%d,%d], got %s' % (B, self.low_dim_size, tuple(proprio.shape)))
+        if lang.shape != (B, 77, 512):
+            raise ValueError('lang_token_embs must be [%d,77,512], got %s' % (B, tuple(lang.shape)))
+        L = _lib.lib()
+        desc = self._desc()
+        arr, keep, slots = self._param_table()
+        dev = grid.device
+        ws_bytes = L.vxb_qnet_train_workspace_bytes(ctypes.byref(desc), B)
+        if ws_bytes == 0:
+            _lib.check(-2, 'vxb_qnet_train_workspace_bytes')
+        if self._train_ws is None or self._train_ws.numel() < ws_bytes or self._train_ws.device != dev:
+            self._train_ws = None
+            self._train_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        return L, desc, arr, keep, slots, ws_bytes
+
+    def _forward_train(self, grid, proprio, lang):
+        """grid [B,V,V,V,10] channels-last.  Returns ((trans, rot_grip, collision[, arm]), generation)."""
+        with torch.no_grad():
+            B, V = grid.shape[0], grid.shape[1]
+            dev = grid.device
+            L, desc, arr, keep, slots, ws_bytes = _train_setup(self, grid, proprio, lang)
+            self._ensure_prepared(desc, arr, slots, dev)          # training mode: always re-prepared
+            if self.dropout_seed is None:
+                self.dropout_seed = int(torch.initial_seed()) & 0xffffffffffff
+            self._train_gen += 1
+            o = _lib.TrainOpts()
+            o.struct_bytes = ctypes.sizeof(_lib.TrainOpts)
+            o.input_dropout, o.attn_dropout, o.decoder_dropout = self.input_dropout, self.attn_dropout, self.decoder_dropout
+            o.seed = (self.dropout_seed + self._train_gen) & 0xffffffffffffffff
+            self._train_opts = o
+            nrg = self.num_rotation_classes * 3 + self.num_grip_classes
+            new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+            trans, rot_grip, coll = new(B, 1, V, V, V), new(B, nrg), new(B, self.num_collision_classes)
+            arm = new(B, 2) if self.arm_pred_loss else None
+            rc = L.vxb_qnet_forward_train_f32(ctypes.byref(desc), arr, _lib.ptr(self._prepared), _lib.ptr(grid),
+                                              _lib.ptr(proprio), _lib.ptr(lang), B, _lib.ptr(trans), _lib.ptr(rot_grip),
+                                              _lib.ptr(coll), _lib.ptr(arm), ctypes.byref(o), _lib.ptr(self._train_ws),
+                                              ws_bytes, _lib.stream())
+            _lib.check(rc, 'vxb_qnet_forward_train_f32')
+            del keep
+        outs = (trans, rot_grip, coll) + ((arm,) if self.arm_pred_loss else ())
+        return outs, self._train_gen
+
+    def _backward_train(self, gen, inputs, gouts, debug=None):
+        """Gradients of every parameter (slot order, Nones skipped) from d loss / d outputs."""
+        if gen != self._train_gen:
+            raise RuntimeError('voxactb_b200: backward through a training forward whose saved activations were overwritten by '
+                               'a later forward of the same encoder (one forward/backward pair at a time per encoder)')
+        grid, proprio, lang = inputs
+        with torch.no_grad():
+            B, V = grid.shape[0], grid.shape[1]
+            dev = grid.device
+            L, desc, arr, keep, slots, ws_bytes = _train_setup(self, grid, proprio, lang)
+            nrg = self.num_rotation_classes * 3 + self.num_grip_classes
+            shapes = [(B, 1, V, V, V), (B, nrg), (B, self.num_collision_classes), (B, 2)]
+            g = []
+            for i in range(3 + int(bool(self.arm_pred_loss))):
+                t = gouts[i] if i < len(gouts) else None
+                g.append(torch.zeros(shapes[i], dtype=torch.float32, device=dev) if t is None else _lib.f32(t))
+            grads = [None if p is None else torch.empty_like(p, memory_format=torch.contiguous_format) for p in slots]
+            garr = (ctypes.c_void_p * len(slots))(*[None if t is None else t.data_ptr() for t in grads])
+            darr = None
+            if debug is not None:
+                darr = (ctypes.c_void_p * 8)(*[None if t is None else t.data_ptr() for t in debug])
+            rc = L.vxb_qnet_backward_f32(ctypes.byref(desc), arr, _lib.ptr(self._prepared), _lib.ptr(grid), _lib.ptr(proprio),
+                                         _lib.ptr(lang), B, _lib.ptr(g[0]), _lib.ptr(g[1]), _lib.ptr(g[2]),
+                                         _lib.ptr(g[3]) if self.arm_pred_loss else None, garr, ctypes.byref(self._train_opts),
+                                         darr, _lib.ptr(self._train_ws), ws_bytes, _lib.stream())
+            _lib.check(rc, 'vxb_qnet_backward_f32')
+            del keep
+        return [t for t in grads if t is not None]
+
+    PerceiverVoxelLangEncoder._forward_train = _forward_train
+    PerceiverVoxelLangEncoder._backward_train = _backward_train
+
+
+_train_methods()
 
 
 class PerceiverVoxelLang2RobotsEncoder(PerceiverVoxelLangEncoder):

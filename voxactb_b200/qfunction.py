@@ -24,10 +24,6 @@ class QFunction(nn.Module):
         self._qnet = perceiver_encoder.to(device)
         self._arm_pred_loss = arm_pred_loss
         self._is_training = training
-        if training:
-            raise NotImplementedError(
-                'voxactb_b200.QFunction: the training step (backward + optimizer + NCCL all-reduce, '
-                'SURVEY.md section 8 row a18) is not built yet; build with training=False')
         self._select_ws = None
 
     def _select(self, q_trans, q_rot_grip, q_collision, bounds=None):

@@ -1,7 +1,8 @@
-"""Training-tail building blocks behind the C ABI: the agent's per-sample
-cross-entropy losses with their logit gradients, fused multi-tensor LAMB / Adam steps with the reference's
-semantics, and the DDP-equivalent gradient all-reduce (NCCL through torch.distributed: sum, then / world).
-The backward pass of the Q-network is NOT built yet, so these are not wired into an ``update()``."""
+"""Training step behind the C ABI: the agent's per-sample cross-entropy losses with their
+logit gradients, the Q-network backward (vxb_qnet_backward_f32, reached either through torch autograd -- the encoder's
+training forward is one autograd node, so the reference's own ``agent.update`` works unchanged -- or directly by
+``PerActTrainer.update`` below), the DDP-equivalent gradient all-reduce over NCCL and fused multi-tensor LAMB / Adam
+steps with the reference's semantics."""
 import ctypes
 
 import torch
@@ -161,3 +162,96 @@ def allreduce_gradients(params, bucket_bytes=25 << 20):
             flush()
             bucket, size = [], 0
     flush()
+
+
+class PerActTrainer:
+    """Host-side mirror of the training half of QAttentionPerActBCAgent (reference qattention_peract_bc_agent.py:418-641)
+    for one QFunction: ``update`` = forward (training mode) -> the four (five with the arm head) cross-entropy losses on
+    label indices (:517-578) -> Q-network backward -> gradient all-reduce across ranks (DDP semantics, :50-54) ->
+    optimizer step (LAMB by default, lamb.py:60-122).  No autograd graph is built: the loss gradients w.r.t. the logits
+    come from the fused CE kernel and go straight into vxb_qnet_backward_f32."""
+
+    def __init__(self, q, lr=5e-4, weight_decay=1e-6, optimizer='lamb', loss_weights=(1.0, 1.0, 1.0, 1.0), arm_loss_weight=1.0,
+                 num_rotation_classes=72):
+        self.q = q
+        self.enc = q._qnet
+        self.params = [p for p in self.enc._param_table()[2] if p is not None]
+        if optimizer == 'lamb':
+            self.optimizer = Lamb(self.params, lr=lr, weight_decay=weight_decay, betas=(0.9, 0.999))
+        elif optimizer == 'adam':
+            self.optimizer = Adam(self.params, lr=lr, weight_decay=weight_decay)
+        else:
+            raise Exception('Unknown optimizer type')
+        self.loss_weights = tuple(loss_weights)
+        self.arm_loss_weight = arm_loss_weight
+        self.R = num_rotation_classes
+        self.reducer = None
+        self.last = {}
+
+    def losses_and_logit_grads(self, q_trans, q_rot_grip, q_collision, arm_out, labels):
+        B = q_trans.shape[0]
+        total, terms, grads = peract_losses(q_trans, q_rot_grip, q_collision, labels['trans'], labels['rot_grip'],
+                                            labels['collision'], self.R, self.loss_weights, with_grad=True)
+        g_arm = None
+        if arm_out is not None and 'arm' in labels:
+            la, g_arm = cross_entropy(arm_out, labels['arm'].reshape(B), self.arm_loss_weight / B)
+            terms['arm'] = la
+            total = total + (la * self.arm_loss_weight).mean()
+        return total, terms, grads, g_arm
+
+    def update(self, rgb_pcd, proprio, pcd, lang_goal_emb, lang_token_embs, bounds, labels):
+        """One training step on a replay batch already on the device.  labels: dict(trans [B,3], rot_grip [B,4],
+        collision [B,1][, arm [B,1]]) of integer indices (agent:419-423).  Returns dict(total_loss, terms)."""
+        enc = self.enc
+        if not enc.training:
+            raise RuntimeError('PerActTrainer.update needs the encoder in training mode (QFunction.train())')
+        with torch.no_grad():
+            b = rgb_pcd[0][0].shape[0]
+            pcd_flat = torch.cat([p.permute(0, 2, 3, 1).reshape(b, -1, 3) for p in pcd], 1)
+            feats = torch.cat([rp[0].permute(0, 2, 3, 1).reshape(b, -1, rp[0].shape[1]) for rp in rgb_pcd], 1)
+            grid = self.q._voxelizer.coords_to_bounding_voxel_grid(pcd_flat, coord_features=feats, coord_bounds=bounds)
+            inputs = (_lib.f32(grid), _lib.f32(proprio), _lib.f32(lang_token_embs))
+            outs, gen = enc._forward_train(*inputs)
+            arm = outs[3] if enc.arm_pred_loss else None
+            total, terms, g, g_arm = self.losses_and_logit_grads(outs[0], outs[1], outs[2], arm, labels)
+            grads = enc._backward_train(gen, inputs, (g['q_trans'], g['q_rot_grip'], g['q_collision'], g_arm))
+            for p, gr in zip(self.params, grads):
+                p.grad = gr
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                if self.reducer is None:
+                    self.reducer = GradientReducer(self.params)
+                self.reducer.allreduce()
+            self.optimizer.step()
+        self.last = {'total_loss': total, 'terms': terms, 'voxel_grid': grid}
+        return self.last
+
+
+class GradientReducer:
+    """DDP-equivalent gradient averaging (reference agent:50-54) on a flat, pre-allocated gradient arena: the per-parameter
+    `.grad` tensors are views into ONE contiguous fp32 buffer (133 MB for the PerAct Q-network), all-reduced in
+    `bucket_bytes` slices over NCCL (NVLink / NVSwitch) on a side stream and scaled by 1 / world in the same pass."""
+
+    def __init__(self, params, bucket_bytes=32 << 20):
+        self.params = list(params)
+        self.world = dist.get_world_size()
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
+        self.views = []
+        o = 0
+        for p in self.params:
+            self.views.append(self.flat[o:o + p.numel()].view_as(p))
+            o += p.numel()
+        self.bucket_elems = max(1, bucket_bytes // 4)
+
+    def allreduce(self):
+        for p, v in zip(self.params, self.views):
+            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+                p.grad = v
+        works = []
+        n = self.flat.numel()
+        for o in range(0, n, self.bucket_elems):
+            works.append(dist.all_reduce(self.flat[o:min(n, o + self.bucket_elems)], op=dist.ReduceOp.SUM, async_op=True))
+        for w in works:
+            w.wait()
+        self.flat.div_(self.world)
