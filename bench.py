@@ -47,10 +47,12 @@ def parse():
     ap.add_argument('--batch', type=int, default=16, help='samples per GPU')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--math', default=os.environ.get('VXB_MATH', 'auto'), choices=['auto', 'fp32', 'bf16x3'])
-    ap.add_argument('--workload', default='single', choices=['single', 'dual', 'crop'],
+    ap.add_argument('--workload', default='single', choices=['single', 'dual', 'crop', 'train'],
                     help='single = BASELINE config 2 geometry at --batch (headline); dual = config 3 (acting + stabilizing '
                          'encoders, low_dim 7 + arm head, on the same observations; value counts agent-passes); '
-                         'crop = config 4 (per-sample VLM-crop bounds [B,6])')
+                         'crop = config 4 (per-sample VLM-crop bounds [B,6]); train = config 5 (training step: forward + '
+                         'losses + backward + NCCL gradient all-reduce + LAMB, --batch samples per GPU; value = samples/s)')
+    ap.add_argument('--optimizer', default='lamb', choices=['lamb', 'adam'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
@@ -350,10 +352,179 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+TRAIN_FLOPS_PER_SAMPLE = 3 * FLOPS_PER_PASS      # forward + dgrad + wgrad (~5.0e12 / sample)
+
+
+def cpu_train_rate(steps):
+    """The reference's CPU training step (oracle port: torch CPU forward + autograd + LAMB) on one sample."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+    from oracle import train_oracle
+    import make_golden
+    import util
+    torch.set_num_threads(os.cpu_count())
+    c = dict(make_golden.QNET_CASES['qnet_v100_b1'])
+    obs, enc, sd = util.make_case(c)
+    sd = {k: v for k, v in sd.items() if not k.endswith(('pos_x', 'pos_y', 'pos_z'))}
+    lab = make_golden.train_labels(c)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        train_oracle.training_step(sd, util.oracle_cfg(c), obs['rgb'], obs['pcd'], obs['proprio'], obs['lang_token_embs'],
+                                   obs['bounds'], c['V'], lab)
+    dt = time.perf_counter() - t0
+    return steps / dt, torch.get_num_threads()
+
+
+def run_train(args):
+    """BASELINE config 5: training step = voxelize + forward (train mode, dropout 0.1) + CE losses + backward + NCCL gradient
+    all-reduce (DDP semantics) + LAMB, --batch samples per GPU (weak scaling).  value = samples/s over all ranks."""
+    import torch
+    import torch.distributed as dist
+    from voxactb_b200 import QFunction, VoxelGrid, PerceiverVoxelLangEncoder, _lib, synth, train
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+    L = _lib.lib()
+    _lib.check(L.vxb_check_device(), 'vxb_check_device')
+    math_mode = {'fp32': _lib.MATH_FP32_SIMT, 'bf16x3': _lib.MATH_BF16X3, 'auto': PerceiverVoxelLangEncoder.math_mode}[args.math]
+    B, V = args.batch, 100
+    torch.manual_seed(4321)                                # identical initial weights on every rank (DDP broadcast equivalent)
+    enc = PerceiverVoxelLangEncoder(
+        depth=6, iterations=1, voxel_size=V, initial_dim=10, low_dim_size=4, layer=0, num_rotation_classes=72,
+        num_grip_classes=2, num_collision_classes=2, input_axis=3, num_latents=2048, latent_dim=512, cross_heads=1,
+        latent_heads=8, cross_dim_head=64, latent_dim_head=64, activation='lrelu', weight_tie_layers=False,
+        pos_encoding_with_lang=True, input_dropout=0.1, attn_dropout=0.1, decoder_dropout=0.0, lang_fusion_type='seq',
+        voxel_patch_size=5, voxel_patch_stride=5, final_dim=64)
+    enc.load_state_dict(synth.random_state_dict(enc, 2234), strict=False)
+    enc.math_mode = math_mode
+    vg = VoxelGrid(synth.SCENE_BOUNDS, V, dev, B, 3, 4 * 128 * 128)
+    q = QFunction(enc, vg, 0.15, 5, dev, True, False).to(dev).train(True)
+    tr = train.PerActTrainer(q, lr=5e-4, weight_decay=1e-6, optimizer=args.optimizer)
+    obs = synth.make_observation(1234 + rank, B, 4, 128, 128, low_dim=4)
+    g = torch.Generator().manual_seed(99 + rank)
+    labels = {'trans': torch.randint(0, V, (B, 3), generator=g, dtype=torch.int32).to(dev),
+              'rot_grip': torch.cat([torch.randint(0, 72, (B, 3), generator=g, dtype=torch.int32),
+                                     torch.randint(0, 2, (B, 1), generator=g, dtype=torch.int32)], 1).to(dev),
+              'collision': torch.randint(0, 2, (B, 1), generator=g, dtype=torch.int32).to(dev)}
+    host = {k: [t.pin_memory() for t in obs[k]] for k in ('rgb', 'pcd')}
+    for k in ('proprio', 'lang_goal_emb', 'lang_token_embs', 'bounds'):
+        host[k] = obs[k].pin_memory()
+    h2d_bytes = sum(t.numel() * 4 for k in ('rgb', 'pcd') for t in host[k]) + sum(
+        host[k].numel() * 4 for k in ('proprio', 'lang_token_embs', 'bounds')) + sum(v.numel() * 4 for v in labels.values())
+
+    def upload():
+        d = {k: [t.to(dev, non_blocking=True) for t in host[k]] for k in ('rgb', 'pcd')}
+        for k in ('proprio', 'lang_goal_emb', 'lang_token_embs', 'bounds'):
+            d[k] = host[k].to(dev, non_blocking=True)
+        return d
+
+    resident = upload()
+    torch.cuda.synchronize()
+    loss_host = torch.empty(1).pin_memory()
+    marks = []
+
+    def step(d, record=False):
+        rgb_pcd = [[r, p] for r, p in zip(d['rgb'], d['pcd'])]
+        res = tr.update(rgb_pcd, d['proprio'], d['pcd'], d['lang_goal_emb'], d['lang_token_embs'], d['bounds'], labels)
+        return res['total_loss']
+
+    def step_e2e():
+        loss = step(upload())
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    clocks = ClockSampler(local)
+    ms_dev = timed(lambda: step(resident), args.steps, args.warmup)
+    clk = clocks.stop()
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    # stage split of one step (CUDA events on the launching stream)
+    tr.profile = True
+    step(resident)
+    torch.cuda.synchronize()
+    stages = dict(tr.last_stage_ms)
+    tr.profile = False
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    per_step = ms_dev / args.steps
+    value = world * B / (per_step * 1e-3)
+    tf = TRAIN_FLOPS_PER_SAMPLE * B / (per_step * 1e-3) / 1e12
+    bwd_ms = stages.get('backward', 0.0)
+    line = {
+        'metric': 'training samples/sec at 100^3 voxels (fwd + loss + bwd + NCCL grad all-reduce + %s)' % args.optimizer.upper(),
+        'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32' if math_mode == _lib.MATH_FP32_SIMT else 'f16x3 forward contractions (split-fp16 tcgen05), fp32 FFMA backward',
+        'data': 'synthetic',
+        'config': {'workload': 'BASELINE config 5: batch=%d/GPU, 100^3 voxels, 4 cameras 128x128 RGB-D, training step (train-mode '
+                               'dropout 0.1, CE losses, backward, gradient all-reduce over NCCL, %s)' % (B, args.optimizer.upper()),
+                   'global_batch': world * B, 'parallelism': 'data-parallel x%d, one fp32 gradient all-reduce (133 MB) per step' % world,
+                   'l2': 'no explicit flush: each step streams >50 GB of activations and gradients'},
+        'e2e': {'value': world * B / (ms_e2e / args.steps * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes,
+                'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': None, 'clocks': clk,
+        'roofline': {'kernel': 'whole training step (forward + dgrad + wgrad ~ 3 x forward FLOPs)', 'bound': 'tensor',
+                     'achieved': tf, 'peak': pk['tensor'], 'unit': 'TFLOP/s', 'frac': tf / pk['tensor'], 'traffic': None,
+                     'algorithmic_flops_per_step': TRAIN_FLOPS_PER_SAMPLE * B, 'peak_source': pk['source'] + ' bf16 sustained',
+                     'backward_ms': bwd_ms},
+        'stages_ms': stages,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        rate, cores = cpu_train_rate(1)
+        line['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                                'sample': '1 single-sample training step (forward + autograd + LAMB) of the torch CPU fp32 oracle port'}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'train':
+        run_train(args)
     else:
         run_ours(args)
 

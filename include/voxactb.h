@@ -35,7 +35,8 @@ typedef enum vxb_status {
   VXB_E_UNSUPPORTED_SHAPE = -2,
   VXB_E_WORKSPACE_TOO_SMALL = -3,
   VXB_E_CUDA = -4,
-  VXB_E_NO_DEVICE = -5
+  VXB_E_NO_DEVICE = -5,
+  VXB_E_NCCL = -6
 } vxb_status;
 
 int vxb_version(void);
@@ -283,6 +284,18 @@ int vxb_lamb_step_f32(int n_tensors, float* const* params, const float* const* g
 int vxb_adam_step_f32(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                       float* const* exp_avg_sq, const long long* sizes, int step, float lr, float beta1,
                       float beta2, float eps, float weight_decay, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- gradient all-reduce of the training step over NCCL (NVLink 5 / NVSwitch), replacing the DistributedDataParallel wrap
+ * of the reference (qattention_peract_bc_agent.py:50-54, process group from run_seed_fn.py:34).  The library resolves
+ * libnccl.so.2 at run time (dlopen; the copy PyTorch has loaded) and owns its communicator:
+ *   rank 0 calls vxb_nccl_unique_id and ships the 128 bytes to the other ranks (any side channel, e.g. a
+ *   torch.distributed broadcast); every rank then calls vxb_nccl_init(id, rank, world, &comm).
+ * vxb_allreduce_grads: flat[0:n] <- scale * sum over ranks (DDP: scale = 1 / world), issued as `bucket_elems`-sized
+ * ncclAllReduce calls (0 = one call) inside one NCCL group on `stream`. */
+int vxb_nccl_unique_id(char* id128 /* host, 128 bytes */);
+int vxb_nccl_init(const char* id128, int rank, int world, void** comm /* out: opaque communicator */);
+int vxb_nccl_destroy(void* comm);
+int vxb_allreduce_grads(void* comm, float* flat, size_t n, float scale, size_t bucket_elems, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_r02_train.csv \
+  python bench.py --workload train --batch 16 --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_train.log 2>&1
+python tools/summarize_launches.py gpurun_out/launches_r02_train.csv | head -50

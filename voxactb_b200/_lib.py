@@ -99,6 +99,10 @@ SIGNATURES = {
                                   ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_ll),
                                   c_int, c_float, c_float, c_float, c_float, c_float, c_void_p, c_size_t,
                                   c_void_p]),
+    'vxb_nccl_unique_id': (c_int, [ctypes.c_char_p]),
+    'vxb_nccl_init': (c_int, [ctypes.c_char_p, c_int, c_int, ctypes.POINTER(c_void_p)]),
+    'vxb_nccl_destroy': (c_int, [c_void_p]),
+    'vxb_allreduce_grads': (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -9,14 +9,34 @@
 #include "ops.cuh"
 #include "simt_gemm.cuh"
 #include "stream_ops.cuh"
+#include "umma_host.cuh"
 
 namespace vxb {
 namespace bwd {
+
+// Arithmetic of the backward contractions for the current vxb_qnet_backward_f32 call: VXB_MATH_BF16X3 routes the large
+// GEMMs / convolution dgrads to the tcgen05 split-fp16 engine (operands scaled per tensor, umma::gemm_any_f32), anything
+// small -- and everything in VXB_MATH_FP32_SIMT -- runs as fp32 FFMA.
+struct TensorCtx { int mm; void* scratch; size_t scratch_bytes; };
+static thread_local TensorCtx g_tc = {VXB_MATH_FP32_SIMT, nullptr, 0};
+inline bool use_tensor(int M, int N, int K) {
+  return g_tc.mm == VXB_MATH_BF16X3 && g_tc.scratch && M >= 128 && N >= 32 && K >= 64;
+}
+// returns VXB_OK when the tensor path ran, 1 when the caller should run the FFMA path, < 0 on error
+inline int try_tensor_gemm(const float* A, long long lda, bool at, const float* W, long long ldw, bool wt, float* C, int ldc,
+                           int M, int N, int K, bool accumulate, cudaStream_t st) {
+  if (!use_tensor(M, N, K)) return 1;
+  Arena local(g_tc.scratch, g_tc.scratch_bytes);
+  const int rc = umma::gemm_any_f32(A, lda, at, W, ldw, wt, C, ldc, M, N, K, accumulate, local, st);
+  return rc == VXB_E_WORKSPACE_TOO_SMALL ? 1 : rc;
+}
 
 // ------------------------------------------------------------------------------------------------ GEMM forms
 // C[M,N] (+)= A[M,K] W[K,N]            (dgrad of a linear: dX = dY W)
 inline int gemm_nn(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
                    bool accumulate, cudaStream_t st) {
+  const int rc = try_tensor_gemm(A, lda, false, W, ldw, true, C, ldc, M, N, K, accumulate, st);
+  if (rc <= 0) return rc;
   GemmParams p;
   gemm_params_init(p);
   p.M = M; p.N = N; p.K = K;
@@ -27,6 +47,8 @@ inline int gemm_nn(const float* A, int lda, const float* W, int ldw, float* C, i
 // C[M,N] (+)= A[M,K] W[N,K]^T
 inline int gemm_nt(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
                    bool accumulate, cudaStream_t st) {
+  const int rc = try_tensor_gemm(A, lda, false, W, ldw, false, C, ldc, M, N, K, accumulate, st);
+  if (rc <= 0) return rc;
   GemmParams p;
   gemm_params_init(p);
   p.M = M; p.N = N; p.K = K;
@@ -44,6 +66,8 @@ inline int pick_ksplit(int M, int N, int K) {
 // C[M,N] (+)= At[K,M]^T W[K,N]          (wgrad of a linear: dW = dY^T X); C contiguous (ldc == N) when split-K is used
 inline int gemm_tn(const float* At, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
                    bool accumulate, cudaStream_t st) {
+  const int rc = try_tensor_gemm(At, lda, true, W, ldw, true, C, ldc, M, N, K, accumulate, st);
+  if (rc <= 0) return rc;
   GemmParams p;
   gemm_params_init(p);
   p.M = M; p.N = N; p.K = K;
@@ -397,11 +421,13 @@ inline int ss_bwd(const float* x, const float* stats, const float* e, int e_stri
 // ------------------------------------------------------------------------------------------------ convolutions
 // Adjoint of replicate padding (grad_oracle.replicate_pad_backward) generalised to a padded-gradient grid of extent
 // Pn per axis (Pn = V + 2 pad for stride-1 convolutions, Pn = S * s for the stride-s patchify windows):
-//   g[b, v, c] (=|+=) sum_{p in [0, Pn)^3 : clamp(p - pad, 0, V-1) == v} gxp[b, p, c0 + c]
+//   g[b, v, gc0 + c] (=|+=) inv * sum_{p in [0, Pn)^3 : clamp(p - pad, 0, V-1) == v} gxp[b, p, c0 + c],  c < nch
+// (inv = 1 / *scale when the padded gradient was produced from scaled tensor-core operands)
 static __global__ void __launch_bounds__(256)
-fold_pad_kernel(const float* __restrict__ gxp, int Cx, int c0, int Pn, int pad, float* __restrict__ g, int Cg, int V, int B,
-                int accumulate) {
-  const int cg = Cg / 4;
+fold_pad_kernel(const float* __restrict__ gxp, int Cx, int c0, int Pn, int pad, float* __restrict__ g, int Cg, int gc0, int nch,
+                int V, int B, int accumulate, const float* __restrict__ scale) {
+  const float inv = scale ? 1.f / *scale : 1.f;
+  const int cg = nch / 4;
   const long long total = (long long)B * V * V * V * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % cg) * 4;
@@ -420,15 +446,41 @@ fold_pad_kernel(const float* __restrict__ gxp, int Cx, int c0, int Pn, int pad, 
           const float4 v = *reinterpret_cast<const float4*>(gxp + ((((size_t)b * Pn + pz) * Pn + py) * Pn + px) * Cx + c0 + c);
           acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
-    float4* o = reinterpret_cast<float4*>(g + (i / cg) * Cg + c);
+    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    float4* o = reinterpret_cast<float4*>(g + (i / cg) * Cg + gc0 + c);
     if (accumulate) { const float4 t = *o; acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
     *o = acc;
   }
 }
 inline int fold_pad(const float* gxp, int Cx, int c0, int Pn, int pad, float* g, int Cg, int V, int B, bool accumulate,
-                    cudaStream_t st) {
-  fold_pad_kernel<<<148 * 16, 256, 0, st>>>(gxp, Cx, c0, Pn, pad, g, Cg, V, B, accumulate ? 1 : 0);
+                    cudaStream_t st, int gc0 = 0, int nch = -1, const float* scale = nullptr) {
+  fold_pad_kernel<<<148 * 16, 256, 0, st>>>(gxp, Cx, c0, Pn, pad, g, Cg, gc0, nch < 0 ? Cg : nch, V, B, accumulate ? 1 : 0, scale);
   VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// dgrad of a stride-1 replicate-padded convolution followed by the padding adjoint: destination d (of n) receives the
+// input channels [64 d, 64 d + 64) ... (tensor path) or channel slices of the interleaved padded gradient (FFMA path).
+struct FoldDst { float* g; int ld; int c0; };   // gradient tensor [B, V^3, ld], first channel of the 64-channel slice
+inline int conv_dgrad_padded(const float* gz, int Co, const float* wd, int Ci, float* gxp, int B, int V, int k, cudaStream_t st);
+inline int conv_dgrad_fold(const float* gz, int Cz, const float* wd, int Cx, float* gxp, int B, int V, int k, const FoldDst* dst,
+                           bool accumulate, cudaStream_t st) {
+  const int pad = k / 2, Pn = V + 2 * pad;
+  if (g_tc.mm == VXB_MATH_BF16X3 && g_tc.scratch && Cz % 64 == 0 && Cx % 64 == 0) {
+    Arena local(g_tc.scratch, g_tc.scratch_bytes);
+    float* scale = local.get<float>(64);
+    const int rc = umma::conv_dgrad_f32(gz, Cz, wd, Cx, gxp, B, V, k, scale, local, st);
+    if (rc == VXB_OK) {
+      const size_t block = (size_t)B * Pn * Pn * Pn * 64;
+      for (int j = 0; j < Cx / 64; ++j)
+        VXB_TRY(fold_pad(gxp + j * block, 64, 0, Pn, pad, dst[j].g, dst[j].ld, V, B, accumulate, st, dst[j].c0, 64, scale));
+      return VXB_OK;
+    }
+    if (rc != VXB_E_WORKSPACE_TOO_SMALL) return rc;
+  }
+  VXB_TRY(conv_dgrad_padded(gz, Cz, wd, Cx, gxp, B, V, k, st));
+  for (int j = 0; j < Cx / 64; ++j)
+    VXB_TRY(fold_pad(gxp, Cx, 64 * j, Pn, pad, dst[j].g, dst[j].ld, V, B, accumulate, st, dst[j].c0, 64, nullptr));
   return VXB_OK;
 }
 
@@ -577,6 +629,7 @@ static __global__ void __launch_bounds__(256)
 trans_bwd_kernel(const float* __restrict__ g, const float* __restrict__ u, const float* __restrict__ wt /*[27][C]*/,
                  float* __restrict__ gu, int accumulate, float* __restrict__ dwt /*[27][C]*/, int B, int V) {
   constexpr int G4 = C / 4;
+  static_assert(G4 == 16, "one half-warp per voxel");
   __shared__ float sdw[27 * C];
   for (int i = threadIdx.x; i < 27 * C; i += 256) sdw[i] = 0.f;
   __syncthreads();
@@ -584,54 +637,81 @@ trans_bwd_kernel(const float* __restrict__ g, const float* __restrict__ u, const
   float acc[27][4];
 #pragma unroll
   for (int t = 0; t < 27; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
-  int cgrp = -1;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % G4) * 4;
-    cgrp = c;                                   // gridDim.x * 256 is a multiple of G4: a thread keeps its channel group
-    long long r = i / G4;
+  const int hl = threadIdx.x & 15;              // lane within the half-warp = channel group
+  const int c = hl * 4;
+  // warp-uniform trip count: every lane of a warp runs the same iterations (shuffles below), tails are predicated
+  const long long wbase = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  for (long long i0 = wbase; i0 < total; i0 += (long long)gridDim.x * blockDim.x) {
+    const long long i = i0 + (threadIdx.x & 31);
+    const bool valid = i < total;
+    long long r = (valid ? i : 0) / G4;
+    const long long vox = r;
     const int x = (int)(r % V); r /= V;
     const int y = (int)(r % V); r /= V;
     const int z = (int)(r % V);
     const int b = (int)(r / V);
     const float* gb = g + (size_t)b * V * V * V;
-    const float4 uv = *reinterpret_cast<const float4*>(u + (i / G4) * C + c);
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    // the 27 gathered sums G[t] of this voxel: lane hl forms taps hl and hl + 16, the half-warp shares them by shuffle
+    float gpart[2] = {0.f, 0.f};
 #pragma unroll
-    for (int dz = 0; dz < 3; ++dz) {
-      int zs[2], nz = 0;
-      { const int a = z - dz + 1; if (a >= 0 && a < V) zs[nz++] = a; if (z == 0 && dz == 0) zs[nz++] = 0; if (z == V - 1 && dz == 2) zs[nz++] = V - 1; }
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy) {
-        int ys[2], ny = 0;
+    for (int k = 0; k < 2; ++k) {
+      const int t = hl + 16 * k;
+      if (t < 27 && valid) {
+        const int dz = t / 9, dy = (t / 3) % 3, dx = t % 3;
+        int zs[2], ys[2], xs[2], nz = 0, ny = 0, nx = 0;
+        { const int a = z - dz + 1; if (a >= 0 && a < V) zs[nz++] = a; if (z == 0 && dz == 0) zs[nz++] = 0; if (z == V - 1 && dz == 2) zs[nz++] = V - 1; }
         { const int a = y - dy + 1; if (a >= 0 && a < V) ys[ny++] = a; if (y == 0 && dy == 0) ys[ny++] = 0; if (y == V - 1 && dy == 2) ys[ny++] = V - 1; }
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          int xs[2], nx = 0;
-          { const int a = x - dx + 1; if (a >= 0 && a < V) xs[nx++] = a; if (x == 0 && dx == 0) xs[nx++] = 0; if (x == V - 1 && dx == 2) xs[nx++] = V - 1; }
-          float G = 0.f;
-          for (int a = 0; a < nz; ++a)
-            for (int bb = 0; bb < ny; ++bb)
-              for (int cc = 0; cc < nx; ++cc) G += __ldg(gb + ((size_t)zs[a] * V + ys[bb]) * V + xs[cc]);
-          const int t = (dz * 3 + dy) * 3 + dx;
-          const float4 wv = *reinterpret_cast<const float4*>(wt + t * C + c);
-          o.x = fmaf(wv.x, G, o.x); o.y = fmaf(wv.y, G, o.y); o.z = fmaf(wv.z, G, o.z); o.w = fmaf(wv.w, G, o.w);
-          acc[t][0] = fmaf(uv.x, G, acc[t][0]); acc[t][1] = fmaf(uv.y, G, acc[t][1]);
-          acc[t][2] = fmaf(uv.z, G, acc[t][2]); acc[t][3] = fmaf(uv.w, G, acc[t][3]);
-        }
+        { const int a = x - dx + 1; if (a >= 0 && a < V) xs[nx++] = a; if (x == 0 && dx == 0) xs[nx++] = 0; if (x == V - 1 && dx == 2) xs[nx++] = V - 1; }
+        float G = 0.f;
+        for (int a = 0; a < nz; ++a)
+          for (int bb = 0; bb < ny; ++bb)
+            for (int cc = 0; cc < nx; ++cc) G += __ldg(gb + ((size_t)zs[a] * V + ys[bb]) * V + xs[cc]);
+        gpart[k] = G;
       }
     }
-    float4* dst = reinterpret_cast<float4*>(gu + (i / G4) * C + c);
-    if (accumulate) { const float4 t4 = *dst; o.x += t4.x; o.y += t4.y; o.z += t4.z; o.w += t4.w; }
-    *dst = o;
-  }
-  if (cgrp >= 0) {
+    float4 uv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) uv = *reinterpret_cast<const float4*>(u + vox * C + c);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int t = 0; t < 27; ++t)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) atomicAdd(&sdw[t * C + cgrp + j], acc[t][j]);
+    for (int t = 0; t < 27; ++t) {
+      const float G = __shfl_sync(0xffffffffu, gpart[t >> 4], t & 15, 16);
+      const float4 wv = *reinterpret_cast<const float4*>(wt + t * C + c);
+      o.x = fmaf(wv.x, G, o.x); o.y = fmaf(wv.y, G, o.y); o.z = fmaf(wv.z, G, o.z); o.w = fmaf(wv.w, G, o.w);
+      acc[t][0] = fmaf(uv.x, G, acc[t][0]); acc[t][1] = fmaf(uv.y, G, acc[t][1]);
+      acc[t][2] = fmaf(uv.z, G, acc[t][2]); acc[t][3] = fmaf(uv.w, G, acc[t][3]);
+    }
+    if (valid) {
+      float4* dst = reinterpret_cast<float4*>(gu + vox * C + c);
+      if (accumulate) { const float4 t4 = *dst; o.x += t4.x; o.y += t4.y; o.z += t4.z; o.w += t4.w; }
+      *dst = o;
+    }
   }
+#pragma unroll
+  for (int t = 0; t < 27; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(&sdw[t * C + c + j], acc[t][j]);
   __syncthreads();
   for (int i = threadIdx.x; i < 27 * C; i += 256) atomicAdd(dwt + i, sdw[i]);
+}
+
+// replicate-padded 3x3x3 im2col of a channels-last grid: out[(b, q)][(nb, c)] = x[b, clamp(q + nb - 1), c]
+static __global__ void __launch_bounds__(256)
+im2col3_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int S, int C) {
+  const int cg = C / 4;
+  const long long total = (long long)B * S * S * S * 27 * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cg) * 4;
+    long long r = i / cg;
+    const int nb = (int)(r % 27); r /= 27;
+    const int qw = (int)(r % S); r /= S;
+    const int qh = (int)(r % S); r /= S;
+    const int qd = (int)(r % S);
+    const int b = (int)(r / S);
+    const int d = min(max(qd + nb / 9 - 1, 0), S - 1), h = min(max(qh + (nb / 3) % 3 - 1, 0), S - 1),
+              w = min(max(qw + nb % 3 - 1, 0), S - 1);
+    *reinterpret_cast<float4*>(out + (i / cg) * C + c) =
+        *reinterpret_cast<const float4*>(x + ((((size_t)b * S + d) * S + h) * S + w) * C + c);
+  }
 }
 
 // token disassembly (adjoint of assemble_tokens_kernel): g_ins [B, nl+T, C] ->

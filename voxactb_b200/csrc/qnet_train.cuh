@@ -41,8 +41,28 @@ struct TrainBufs {
   float *g_ins, *g_ctx, *g_kv_c, *g_qcb, *g_qc, *g_latn, *g_qd, *g_qn, *g_att_d, *g_kv_d;
   float *g_lang, *g_patch, *g_pfeat;
   float *dwt;                                 // wgrad GEMM output ([taps][Ci][Co]) before the layout change
+  float *im2col;                              // [B*S^3][27*64] low-resolution im2col (folded up-conv weight gradient)
   float *tmp_small;
+  char *tc_scratch;                           // operand planes of the tensor-core backward contractions
+  size_t tc_scratch_bytes;
 };
+
+static size_t train_tc_scratch_bytes(const Dims& m, int B) {
+  const int R = B * m.L, Bn = B * m.n, BT = B * m.T, cq = m.ch * m.cdh, lq = m.lh * m.ldh;
+  size_t sb = 0;
+  auto g = [&](int M, int N, int K, bool acc) { sb = std::max(sb, umma::gemm_any_scratch_bytes(M, N, K, acc)); };
+  g(8 * m.D, m.D, R, false); g(m.D, 4 * m.D, R, false); g(R, 4 * m.D, m.D, false); g(R, m.D, 8 * m.D, false);   // FF
+  g(m.D, lq, R, false); g(R, lq, m.D, false); g(2 * lq, m.D, R, false); g(R, m.D, 2 * lq, true); g(lq, m.D, R, false);
+  g(2 * cq, m.C, Bn, false); g(Bn, m.C, 2 * cq, false); g(m.C, cq, BT, false); g(BT, cq, m.C, false); g(cq, m.C, BT, false);
+  g(BT, m.C, cq, false); g(2 * cq, m.D, R, false); g(R, m.D, 2 * cq, false); g(m.D, cq, R, false); g(R, cq, m.D, false);
+  g(m.C, 512, B * m.nl, false);
+  g(27 * 64, m.s * m.s * m.s * 64, BT, false);                                                                     // folded wgrad
+  sb = std::max(sb, umma::conv3_wgrad_scratch_bytes(B, m.V));
+  sb = std::max(sb, umma::conv_dgrad_scratch_bytes(B, m.V, 64, 128, 3));
+  sb = std::max(sb, umma::conv_dgrad_scratch_bytes(B, m.S, m.s * m.s * m.s * 64, 64, 3));
+  sb = std::max(sb, umma::conv_dgrad_scratch_bytes(B, m.S, 64, m.C, m.k));
+  return sb + 8192;
+}
 
 static size_t sim_train_floats(const Dims& m, int B) {
   auto pad4 = [](size_t v) { return (v + 3) / 4 * 4; };
@@ -125,6 +145,9 @@ static void carve_train(const Dims& m, int B, Arena& a, TrainBufs& t) {
   t.g_pfeat = a.get<float>(Bz * 64);
   t.dwt = a.get<float>(std::max(std::max(k3 * m.C * 64, (size_t)27 * 128 * 64), (size_t)27 * 64 * s3 * 64));
   t.tmp_small = a.get<float>(4096);
+  t.im2col = a.get<float>(Bz * m.T * 27 * 64);
+  t.tc_scratch_bytes = train_tc_scratch_bytes(m, B);
+  t.tc_scratch = a.get<char>(t.tc_scratch_bytes);
 }
 
 static int train_supported(const vxb_qnet_desc* d, const Dims& m) {
@@ -358,6 +381,7 @@ static int qnet_backward_impl(const vxb_qnet_desc* d, const Dims& m, const void*
     if (dbg && dbg[i]) VXB_CUDA(cudaMemcpyAsync(dbg[i], src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return VXB_OK;
   };
+  bwd::g_tc = bwd::TensorCtx{d->math_mode, d->math_mode == VXB_MATH_BF16X3 ? (void*)t.tc_scratch : nullptr, t.tc_scratch_bytes};
   const float slope = d->act_slope;
   const int cq = m.ch * m.cdh, lq = m.lh * m.ldh;
   const long long rowsL = (long long)B * m.L;
@@ -410,13 +434,21 @@ static int qnet_backward_impl(const vxb_qnet_desc* d, const Dims& m, const void*
   VXB_TRY(bwd::lrelu_bwd(t.g_u, w.u, (long long)full, slope, st));            // g_u := gradient of the pre-activation
   if (G.at(VXB_P_FINAL_B)) VXB_TRY(bwd::colsum(t.g_u, 64, (long long)B * m.V3, 64, G.at(VXB_P_FINAL_B), false, st));
   if (G.at(VXB_P_FINAL_W)) {
-    VXB_TRY(bwd::conv_wgrad(w.d0, w.u0, 64, 64, t.g_u, 64, t.dwt, B, m.V, m.V, 3, 1, st));
+    int rc = 1;
+    if (bwd::g_tc.mm == VXB_MATH_BF16X3 && bwd::g_tc.scratch) {
+      Arena local(bwd::g_tc.scratch, bwd::g_tc.scratch_bytes);
+      rc = umma::conv3_wgrad_f32(w.d0, w.u0, t.g_u, t.dwt, B, m.V, local, st);
+      if (rc == VXB_E_WORKSPACE_TOO_SMALL) rc = 1;
+      if (rc < 0) return rc;
+    }
+    if (rc == 1) VXB_TRY(bwd::conv_wgrad(w.d0, w.u0, 64, 64, t.g_u, 64, t.dwt, B, m.V, m.V, 3, 1, st));
     bwd::wgrad_to_torch_kernel<<<148 * 2, 256, 0, st>>>(t.dwt, G.at(VXB_P_FINAL_W), 64, 128, 27);
     VXB_LAUNCH_CHECK();
   }
-  VXB_TRY(bwd::conv_dgrad_padded(t.g_u, 64, t.wd_final, 128, t.gxp_big, B, m.V, 3, st));
-  VXB_TRY(bwd::fold_pad(t.gxp_big, 128, 0, m.V + 2, 1, t.g_d0, 64, m.V, B, false, st));
-  VXB_TRY(bwd::fold_pad(t.gxp_big, 128, 64, m.V + 2, 1, t.g_u0, 64, m.V, B, false, st));
+  {
+    const bwd::FoldDst dst[2] = {{t.g_d0, 64, 0}, {t.g_u0, 64, 0}};
+    VXB_TRY(bwd::conv_dgrad_fold(t.g_u, 64, t.wd_final, 128, t.gxp_big, B, m.V, 3, dst, false, st));
+  }
   VXB_TRY(DBG(2, t.g_u0, full));
 
   // ---- up0, second half: conv_k o upsample_s in its folded (polyphase) form         network_utils.py:245-251
@@ -425,12 +457,17 @@ static int qnet_backward_impl(const vxb_qnet_desc* d, const Dims& m, const void*
   bwd::phase_gather_kernel<<<148 * 16, 256, 0, st>>>(t.g_u0, t.g_ph, B, m.S, m.s, 64);
   VXB_LAUNCH_CHECK();
   if (G.at(VXB_P_UP1_W)) {
-    VXB_TRY(bwd::conv_wgrad(w.low, nullptr, 64, 0, t.g_ph, s3 * 64, t.dwt, B, m.S, m.S, 3, 1, st));
+    // dwt[(nb, ci)][(r, co)] = im2col(low)^T g_ph: one GEMM with K = B * S^3 (explicit low-resolution im2col, 27 x 64 columns)
+    bwd::im2col3_kernel<<<148 * 8, 256, 0, st>>>(w.low, t.im2col, B, m.S, 64);
+    VXB_LAUNCH_CHECK();
+    VXB_TRY(bwd::gemm_tn(t.im2col, 27 * 64, t.g_ph, s3 * 64, t.dwt, s3 * 64, 27 * 64, s3 * 64, B * m.T, false, st));
     bwd::fold_upconv_weights_bwd_kernel<<<148 * 8, 256, 0, st>>>(t.dwt, G.at(VXB_P_UP1_W), 64, 64, m.k, m.s);
     VXB_LAUNCH_CHECK();
   }
-  VXB_TRY(bwd::conv_dgrad_padded(t.g_ph, s3 * 64, t.wd_fold, 64, t.g_lowp, B, m.S, 3, st));
-  VXB_TRY(bwd::fold_pad(t.g_lowp, 64, 0, m.S + 2, 1, t.g_low, 64, m.S, B, false, st));
+  {
+    const bwd::FoldDst dst[1] = {{t.g_low, 64, 0}};
+    VXB_TRY(bwd::conv_dgrad_fold(t.g_ph, s3 * 64, t.wd_fold, 64, t.g_lowp, B, m.S, 3, dst, false, st));
+  }
   VXB_TRY(DBG(3, t.g_low, (size_t)B * m.T * 64));
   // ---- up0, first half: conv k (C -> 64) at S^3
   VXB_TRY(bwd::lrelu_bwd(t.g_low, w.low, (long long)B * m.T * 64, slope, st));
@@ -440,8 +477,11 @@ static int qnet_backward_impl(const vxb_qnet_desc* d, const Dims& m, const void*
     bwd::wgrad_to_torch_kernel<<<148 * 4, 256, 0, st>>>(t.dwt, G.at(VXB_P_UP0_W), 64, m.C, k3);
     VXB_LAUNCH_CHECK();
   }
-  VXB_TRY(bwd::conv_dgrad_padded(t.g_low, 64, t.wd_up0, m.C, t.gxp_low, B, m.S, m.k, st));
-  VXB_TRY(bwd::fold_pad(t.gxp_low, m.C, 0, m.S + 2 * (m.k / 2), m.k / 2, t.g_dec, m.C, m.S, B, false, st));
+  {
+    bwd::FoldDst dst[8];
+    for (int j = 0; j < m.C / 64; ++j) dst[j] = bwd::FoldDst{t.g_dec, m.C, 64 * j};
+    VXB_TRY(bwd::conv_dgrad_fold(t.g_low, 64, t.wd_up0, m.C, t.gxp_low, B, m.S, m.k, dst, false, st));
+  }
   // ---- ss1 / max-pool over dec                                                       :451
   VXB_TRY(bwd::ss_bwd(w.dec, t.stats1, w.feats + 256, m.flat, t.g_feats + 256, m.flat, t.g_feats + 256 + 3 * m.C, m.flat, t.arg1,
                       t.g_dec, true, B, m.S, m.S, m.S, m.C, st));

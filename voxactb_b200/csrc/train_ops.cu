@@ -285,3 +285,114 @@ extern "C" int vxb_adam_step_f32(int n_tensors, float* const* params, const floa
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ NCCL gradient all-reduce
+// DDP-equivalent gradient averaging (reference qattention_peract_bc_agent.py:50-54 wraps the Q-network in
+// DistributedDataParallel; run_seed_fn.py:34 creates the process group): one all-reduce of the flat fp32 gradient arena
+// per step over NVLink / NVSwitch.  libnccl is resolved at run time (dlopen of the copy the host process -- PyTorch --
+// already loaded), so the library has no link-time NCCL dependency and CPU-only hosts can still load it.
+#include <dlfcn.h>
+#include <mutex>
+
+struct Id128 { char bytes[128]; };   // ncclUniqueId (passed by value to ncclCommInitRank)
+namespace {
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi g_nccl;
+static std::once_flag g_nccl_once;
+
+static bool nccl_load() {
+  std::call_once(g_nccl_once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW);
+    if (!h) return;
+    g_nccl.handle = h;
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  });
+  return g_nccl.handle && g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce &&
+         g_nccl.GroupStart && g_nccl.GroupEnd;
+}
+static int nccl_fail(const char* what, int rc) {
+  set_error("%s failed: NCCL error %d (%s)", what, rc, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  return VXB_E_NCCL;
+}
+#define VXB_NCCL(call, what)                    \
+  do {                                          \
+    const int _r = (call);                      \
+    if (_r != 0) return nccl_fail(what, _r);    \
+  } while (0)
+
+extern "C" int vxb_nccl_unique_id(char* id128) {
+  VXB_CHECK_ARG(id128, "nccl_unique_id: null pointer");
+  if (!nccl_load()) {
+    set_error("libnccl.so.2 could not be loaded");
+    return VXB_E_NCCL;
+  }
+  VXB_NCCL(g_nccl.GetUniqueId(id128), "ncclGetUniqueId");
+  return VXB_OK;
+}
+
+extern "C" int vxb_nccl_init(const char* id128, int rank, int world, void** comm) {
+  VXB_CHECK_ARG(id128 && comm && world > 0 && rank >= 0 && rank < world, "nccl_init: bad arguments");
+  if (!nccl_load()) {
+    set_error("libnccl.so.2 could not be loaded");
+    return VXB_E_NCCL;
+  }
+  Id128 id;
+  memcpy(id.bytes, id128, 128);
+  VXB_NCCL(g_nccl.CommInitRank(comm, world, id, rank), "ncclCommInitRank");
+  return VXB_OK;
+}
+
+extern "C" int vxb_nccl_destroy(void* comm) {
+  if (!comm) return VXB_OK;
+  if (!nccl_load()) return VXB_E_NCCL;
+  VXB_NCCL(g_nccl.CommDestroy(comm), "ncclCommDestroy");
+  return VXB_OK;
+}
+
+static __global__ void scale_kernel(float* __restrict__ x, size_t n, float s) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= s;
+}
+
+extern "C" int vxb_allreduce_grads(void* comm, float* flat, size_t n, float scale, size_t bucket_elems, void* stream) {
+  VXB_CHECK_ARG(comm && flat && n > 0, "allreduce_grads: bad arguments");
+  if (!nccl_load()) {
+    set_error("libnccl.so.2 could not be loaded");
+    return VXB_E_NCCL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bucket_elems == 0) bucket_elems = n;
+  const int kFloat32 = 7, kSum = 0;
+  VXB_NCCL(g_nccl.GroupStart(), "ncclGroupStart");
+  for (size_t o = 0; o < n; o += bucket_elems) {
+    const size_t cnt = std::min(bucket_elems, n - o);
+    const int r = g_nccl.AllReduce(flat + o, flat + o, cnt, kFloat32, kSum, comm, st);
+    if (r != 0) {
+      g_nccl.GroupEnd();
+      return nccl_fail("ncclAllReduce", r);
+    }
+  }
+  VXB_NCCL(g_nccl.GroupEnd(), "ncclGroupEnd");
+  if (scale != 1.f) {
+    scale_kernel<<<148 * 8, 256, 0, st>>>(flat, n, scale);
+    VXB_LAUNCH_CHECK();
+  }
+  return VXB_OK;
+}

@@ -266,8 +266,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
             a_src = cb >= pl.cb_src0;
             a_col = (a_src ? cb - pl.cb_src0 : cb) * BK;
           }
-          a_col += zh * p.a_col_zh;
-          const int w_col = kb * BK + zh * p.w_col_zh;
+          a_col += zh * p.a_col_zh + (int)p.a_col_off;
+          const int w_col = kb * BK + zh * p.w_col_zh + (int)p.w_col_off;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = smem + stage * L::STAGE_BYTES;
           const CUtensorMap* ah = a_src ? &mapA1h : &mapA0h;

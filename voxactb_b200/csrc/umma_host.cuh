@@ -66,6 +66,7 @@ struct Params {
   int a_row_zb, a_col_zh;        // A: rows per zb, columns per zh
   int a_row_zh;                  // A: rows per zh
   int a_row_off;                 // A: first row of every batch entry (conv modes skip the all-halo leading z planes)
+  long long a_col_off, w_col_off; // plain GEMM: constant K offsets of the two operands (weight gradients: a tap = a K shift)
   int terms;                     // 3 = hi*hi + hi*lo + lo*hi (default), 1 = hi*hi only (lo planes are not loaded)
   long long rs_zb, rs_zh;        // row statistic element offsets per zb / zh
   int w_row_zb, w_row_zh, w_col_zh;
@@ -107,6 +108,29 @@ int conv3d_f32(const float* x0, const float* x1, int C0, int C1, const Planes& W
 size_t upconv_scratch_bytes(int B, int S, int Ci);
 int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out, int B, int S, int Ci, int Co, int s,
                float act_slope, Arena& scratch, cudaStream_t st, const Planes* out_planes = nullptr);
+
+// ---- backward (training) contractions on the tensor cores ------------------------------------------------------------
+// Gradient tensors span many decades (softmax-over-10^6 logit gradients are ~1e-8), below the fp16 planes' range, so every
+// operand of these wrappers is scaled by a power of two derived on the device from its max-abs (no host sync) and the
+// result is unscaled by a small post pass.
+// C[M,N] (+)= opA(A) opW(W)^T with K-major products: A is [M,K] (a_trans = false) or stored [K,M] (a_trans = true),
+// W is [N,K] (w_trans = false) or stored [K,N] (w_trans = true).  Returns VXB_E_WORKSPACE_TOO_SMALL if scratch is short.
+int gemm_any_f32(const float* A, long long lda, bool a_trans, const float* W, long long ldw, bool w_trans, float* C, int ldc,
+                 int M, int N, int K, bool accumulate, Arena& scratch, cudaStream_t st);
+size_t gemm_any_scratch_bytes(int M, int N, int K, bool accumulate);
+// Weight gradient of the 3x3x3 convolution on cat[x0, x1] (64 channels each, fp32 compact [B, V^3, 64]) given the
+// pre-activation gradient gz [B, V^3, 64]:  dwt[(tap, ci)][co] = sum_rows xpad[row + shift(tap)][ci] gz[row][co]
+// (tap-major, the layout bwd::wgrad_to_torch_kernel converts).  Runs as 27 split-K GEMMs on channel-major (transposed)
+// planes of the replicate-padded inputs and the zero-padded gradient: a tap is a constant K offset of the A operand.
+int conv3_wgrad_f32(const float* x0, const float* x1, const float* gz, float* dwt, int B, int V, Arena& scratch, cudaStream_t st);
+size_t conv3_wgrad_scratch_bytes(int B, int V);
+// Padded-gradient grid of a stride-1 convolution: gxp[j][b, p, 0:64] = sum_t w_t^T gz[b, p - t] for the j-th block of 64
+// input channels, p in (V + 2 (k/2))^3, gz [B, V^3, Cz] zero outside the grid.  wd: fp32 tap-major dgrad weights
+// [Cx][k^3][Cz] (bwd::conv_dgrad_weight_kernel).  gxp blocks are consecutive [B, (V+2pad)^3, 64] tensors, multiplied by
+// the device scalar *scale_out (the caller's fold divides it out).
+int conv_dgrad_f32(const float* gz, int Cz, const float* wd, int Cx, float* gxp, int B, int V, int k, float* scale_out,
+                   Arena& scratch, cudaStream_t st);
+size_t conv_dgrad_scratch_bytes(int B, int V, int Cz, int Cx, int k);
 
 // ---- plane-domain building blocks of the transformer (no fp32 round trips between GEMMs)
 // y = LayerNorm(x) written as planes [rows, n]; input rows may be a strided slice per batch

@@ -796,6 +796,378 @@ int attention_f32(const float* q, int ldq, long long qbs, const float* k, const 
 }
 
 
+// ------------------------------------------------------------------------------------------ backward contractions
+// max |x| of a strided matrix -> power-of-two scale that puts it near 2^12 (fp16 planes: max 65504, normals from 6e-5)
+static __global__ void __launch_bounds__(256)
+amax_kernel(const float* __restrict__ x, long long ld, long long rows, int cols, unsigned int* __restrict__ out) {
+  const long long total = rows * cols;
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[(i / cols) * ld + (i % cols)]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));     // non-negative floats order like their bit patterns
+}
+static __global__ void scale_from_amax_kernel(const unsigned int* __restrict__ amax, float* __restrict__ scale) {
+  const float m = __uint_as_float(*amax);
+  float s = 1.f;
+  if (m > 0.f && m < INFINITY) {
+    int e;
+    frexpf(m, &e);                       // m = f * 2^e, f in [0.5, 1)
+    s = ldexpf(1.f, 12 - e);             // m * s in [2^11, 2^12)
+  }
+  *scale = s;
+}
+// device scalar scale for x (written to scale[0]); amax_tmp: one uint of scratch
+static int operand_scale(const float* x, long long ld, long long rows, int cols, unsigned int* amax_tmp, float* scale,
+                         cudaStream_t st) {
+  VXB_CUDA(cudaMemsetAsync(amax_tmp, 0, sizeof(unsigned int), st));
+  const long long total = rows * cols;
+  amax_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 8), 256, 0, st>>>(x, ld, rows, cols, amax_tmp);
+  scale_from_amax_kernel<<<1, 1, 0, st>>>(amax_tmp, scale);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// fp32 [rows, cols] (ldx) * scale -> planes [rows, ldp]
+static __global__ void __launch_bounds__(256)
+split_rows_scaled_kernel(const float* __restrict__ x, long long ldx, long long rows, int cols, const float* __restrict__ scale,
+                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldp) {
+  const float sc = *scale;
+  const long long groups_per_row = ldp / 8;
+  const long long total = rows * groups_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups_per_row;
+    const int c = (int)(i % groups_per_row) * 8;
+    float f[8];
+    const float* src = x + r * ldx + c;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) f[t] = (c + t < cols) ? src[t] * sc : 0.f;
+    uint4 h, l;
+    split8(f, h, l);
+    *reinterpret_cast<uint4*>(hi + r * ldp + c) = h;
+    *reinterpret_cast<uint4*>(lo + r * ldp + c) = l;
+  }
+}
+// fp32 x stored [R, Cc] (ldx) * scale -> TRANSPOSED planes [Cc, ldp] (ldp >= R); 32 x 32 tiles through shared memory
+static __global__ void __launch_bounds__(256)
+split_transpose_scaled_kernel(const float* __restrict__ x, long long ldx, int R, int Cc, const float* __restrict__ scale,
+                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldp) {
+  __shared__ float tile[32][33];
+  const float sc = *scale;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    tile[j][tx] = (r < R && c < Cc) ? x[(long long)r * ldx + c] * sc : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;              // output row c, column r
+    if (c < Cc && r < ldp) {
+      const float f = r < R ? tile[tx][j] : 0.f;
+      const __nv_bfloat16 h = pl_from_float(f);
+      hi[(long long)c * ldp + r] = h;
+      lo[(long long)c * ldp + r] = pl_from_float(f - pl_to_float(h));
+    }
+  }
+}
+// C[m, n] = (accumulate ? C : 0) + tmp[m, n] / (sa * sw)   (tmp == C allowed when not accumulating)
+static __global__ void __launch_bounds__(256)
+unscale_kernel(float* __restrict__ C, int ldc, const float* __restrict__ tmp, int ldt, long long M, int N,
+               const float* __restrict__ sa, const float* __restrict__ sw, int accumulate) {
+  const float inv = 1.f / (*sa * *sw);
+  const long long total = M * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / N;
+    const int n = (int)(i % N);
+    const float v = tmp[m * ldt + n] * inv;
+    float* d = C + m * ldc + n;
+    *d = accumulate ? *d + v : v;
+  }
+}
+
+size_t gemm_any_scratch_bytes(int M, int N, int K, bool accumulate) {
+  Arena a(nullptr, 0);
+  alloc_planes(a, M, pad8(K));
+  alloc_planes(a, N, pad8(K));
+  a.get<float>(64);
+  if (accumulate) a.get<float>((size_t)M * N);
+  return a.off;
+}
+
+int gemm_any_f32(const float* A, long long lda, bool a_trans, const float* W, long long ldw, bool w_trans, float* C, int ldc,
+                 int M, int N, int K, bool accumulate, Arena& scratch, cudaStream_t st) {
+  const long long Kp = pad8(K);
+  Planes Ap = alloc_planes(scratch, M, Kp), Wp = alloc_planes(scratch, N, Kp);
+  float* sc = scratch.get<float>(64);           // [0] sa, [1] sw, [2..3] amax temporaries
+  float* tmp = accumulate ? scratch.get<float>((size_t)M * N) : C;
+  if (!scratch.ok) return VXB_E_WORKSPACE_TOO_SMALL;
+  auto split_op = [&](const float* X, long long ldx, bool trans, int rows /*M or N*/, Planes P, float* scale, unsigned int* amax) -> int {
+    // stored extent: [rows, K] (plain) or [K, rows] (transposed)
+    VXB_TRY(operand_scale(X, ldx, trans ? K : rows, trans ? rows : K, amax, scale, st));
+    if (!trans) {
+      const long long total = (long long)rows * (P.ld / 8);
+      split_rows_scaled_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(X, ldx, rows, K, scale, P.hi,
+                                                                                                        P.lo, P.ld);
+    } else {
+      split_transpose_scaled_kernel<<<dim3(cdiv(rows, 32), cdiv(P.ld, 32)), 256, 0, st>>>(X, ldx, K, rows, scale, P.hi, P.lo, P.ld);
+    }
+    VXB_LAUNCH_CHECK();
+    return VXB_OK;
+  };
+  VXB_TRY(split_op(A, lda, a_trans, M, Ap, sc, reinterpret_cast<unsigned int*>(sc + 2)));
+  VXB_TRY(split_op(W, ldw, w_trans, N, Wp, sc + 1, reinterpret_cast<unsigned int*>(sc + 3)));
+  Params p;
+  params_init(p);
+  const int nt = pick_ntile(N);
+  p.m_tiles = cdiv(M, BM);
+  p.n_tiles = cdiv(N, nt);
+  p.plan.num_kb = cdiv(K, BK);
+  p.ep.M = M; p.ep.N = N; p.ep.row_mode = ROWS_PLAIN;
+  p.ep.out_f32 = tmp; p.ep.ldc = accumulate ? N : ldc;
+  Operand a{Ap, M, K}, w{Wp, N, K};
+  VXB_TRY(gemm(a, nullptr, w, nt, p, st));
+  const long long total = (long long)M * N;
+  unscale_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(C, ldc, tmp, accumulate ? N : ldc, M, N, sc,
+                                                                                         sc + 1, accumulate ? 1 : 0);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// channels-last fp32 x [B, V^3, 64] * scale -> CHANNEL-MAJOR planes [64][ldp] over the flat wgrad grid
+// (B, V+2, V+2, Vx), Vx = V+2 rounded up to a multiple of 8 (TMA needs 16-byte aligned K offsets, so the (dz, dy) taps
+// become K shifts of whole x-rows and the dx taps are taken from `dxs`-shifted copies of the gradient).
+// Element (b, pz, py, px) = padded-grid value at (pz, py, px - dxs): halo = nearest interior voxel (replicate = 1) or zero.
+static __global__ void __launch_bounds__(256)
+pad_transpose_split_kernel(const float* __restrict__ x, int B, int V, int Vx, int dxs, int replicate,
+                           const float* __restrict__ scale, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                           long long ldp, long long rows) {
+  __shared__ float tile[64][65];
+  __shared__ long long src[64];
+  const float sc = *scale;
+  const int Vp = V + 2;
+  const long long r0 = (long long)blockIdx.x * 64;
+  if (threadIdx.x < 64) {
+    const long long r = r0 + threadIdx.x;
+    long long s = -1;
+    if (r < rows) {
+      long long v = r;
+      const int pw = (int)(v % Vx) - dxs; v /= Vx;
+      const int ph = (int)(v % Vp); v /= Vp;
+      const int pd = (int)(v % Vp);
+      const int b = (int)(v / Vp);
+      const int d = min(max(pd - 1, 0), V - 1), h = min(max(ph - 1, 0), V - 1), w = min(max(pw - 1, 0), V - 1);
+      const bool interior = (d == pd - 1) && (h == ph - 1) && (w == pw - 1);
+      if (interior || replicate) s = (((long long)b * V + d) * V + h) * V + w;
+    }
+    src[threadIdx.x] = s;
+  }
+  __syncthreads();
+  const int c = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  for (int j = rl; j < 64; j += 4) {
+    const long long s = src[j];
+    tile[j][c] = s >= 0 ? x[s * 64 + c] * sc : 0.f;
+  }
+  __syncthreads();
+  const int rr = threadIdx.x & 63;
+  for (int ch = rl; ch < 64; ch += 4) {
+    const long long r = r0 + rr;
+    if (r < ldp) {
+      const float f = r < rows ? tile[rr][ch] : 0.f;
+      const __nv_bfloat16 h = pl_from_float(f);
+      hi[(long long)ch * ldp + r] = h;
+      lo[(long long)ch * ldp + r] = pl_from_float(f - pl_to_float(h));
+    }
+  }
+}
+// dwt[(tap, ci)][co] = inv * sum_split partial[tap][split][ci][co]
+static __global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ sa, const float* __restrict__ sw,
+                    float* __restrict__ dwt, int taps, int mn) {
+  const float inv = 1.f / (*sa * *sw);
+  const long long total = (long long)taps * mn;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / mn), e = (int)(i % mn);
+    const float* p = partial + ((long long)t * nsplit) * mn + e;
+    float acc = 0.f;
+    for (int s = 0; s < nsplit; ++s) acc += p[(long long)s * mn];
+    dwt[i] = acc * inv;
+  }
+}
+static __global__ void max2_kernel(unsigned int* a, const unsigned int* b) { if (*b > *a) *a = *b; }
+
+constexpr int kWgradSplits = 296;
+static long long wgrad_rows(int B, int V, long long* Vx_out) {
+  const long long Vp = V + 2, Vx = (Vp + 7) / 8 * 8;
+  if (Vx_out) *Vx_out = Vx;
+  return (long long)B * Vp * Vp * Vx;
+}
+size_t conv3_wgrad_scratch_bytes(int B, int V) {
+  Arena a(nullptr, 0);
+  const long long ld = pad8(wgrad_rows(B, V, nullptr));
+  alloc_planes(a, 128, ld);
+  for (int i = 0; i < 3; ++i) alloc_planes(a, 64, ld);
+  a.get<float>((size_t)27 * kWgradSplits * 128 * 64);
+  a.get<float>(64);
+  return a.off;
+}
+
+int conv3_wgrad_f32(const float* x0, const float* x1, const float* gz, float* dwt, int B, int V, Arena& scratch, cudaStream_t st) {
+  long long Vx;
+  const long long Vp = V + 2, rows = wgrad_rows(B, V, &Vx), ld = pad8(rows);
+  if (rows >= (1ll << 31)) {
+    set_error("conv3_wgrad: grid too large");
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  Planes xt = alloc_planes(scratch, 128, ld);
+  Planes gt[3];
+  for (int i = 0; i < 3; ++i) gt[i] = alloc_planes(scratch, 64, ld);     // gradient shifted by dx = -1, 0, +1 along x
+  float* partial = scratch.get<float>((size_t)27 * kWgradSplits * 128 * 64);
+  float* sc = scratch.get<float>(64);          // [0] sx, [1] sg, [2..4] amax temporaries
+  if (!scratch.ok) return VXB_E_WORKSPACE_TOO_SMALL;
+  unsigned int* am = reinterpret_cast<unsigned int*>(sc + 2);
+  const long long nvox = (long long)B * V * V * V;
+  // one scale for both input halves (they share the A operand), one for the gradient
+  VXB_CUDA(cudaMemsetAsync(am, 0, 3 * sizeof(unsigned int), st));
+  const int ab = (int)std::min<long long>((nvox * 64 + 255) / 256, 148 * 8);
+  amax_kernel<<<ab, 256, 0, st>>>(x0, 64, nvox, 64, am);
+  amax_kernel<<<ab, 256, 0, st>>>(x1, 64, nvox, 64, am + 1);
+  amax_kernel<<<ab, 256, 0, st>>>(gz, 64, nvox, 64, am + 2);
+  max2_kernel<<<1, 1, 0, st>>>(am, am + 1);
+  scale_from_amax_kernel<<<1, 1, 0, st>>>(am, sc);
+  scale_from_amax_kernel<<<1, 1, 0, st>>>(am + 2, sc + 1);
+  VXB_LAUNCH_CHECK();
+  const int tb = (int)((ld + 63) / 64);
+  pad_transpose_split_kernel<<<tb, 256, 0, st>>>(x0, B, V, (int)Vx, 0, 1, sc, xt.hi, xt.lo, ld, rows);
+  pad_transpose_split_kernel<<<tb, 256, 0, st>>>(x1, B, V, (int)Vx, 0, 1, sc, xt.hi + 64 * ld, xt.lo + 64 * ld, ld, rows);
+  // sum_r X[r + S + dx] G[r] = sum_r' X[r' + S] G[r' - dx]: the copy for tap dx holds the gradient moved by +dx
+  for (int i = 0; i < 3; ++i)
+    pad_transpose_split_kernel<<<tb, 256, 0, st>>>(gz, B, V, (int)Vx, i - 1, 0, sc + 1, gt[i].hi, gt[i].lo, ld, rows);
+  VXB_LAUNCH_CHECK();
+  const long long Kc = (rows + kWgradSplits - 1) / kWgradSplits;
+  const long long Kcb = (Kc + BK - 1) / BK * BK;
+  const int nsplit = (int)((rows + Kcb - 1) / Kcb);
+  for (int tap = 0; tap < 27; ++tap) {
+    const int dz = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dx = tap % 3 - 1;
+    Params p;
+    params_init(p);
+    p.m_tiles = 1; p.n_tiles = 1;
+    p.plan.num_kb = (int)(Kcb / BK);
+    p.batches = nsplit; p.Hz = nsplit;
+    p.a_col_zh = (int)Kcb; p.w_col_zh = (int)Kcb;
+    p.a_col_off = ((long long)dz * Vp + dy) * Vx;        // multiple of 8 elements; out-of-range columns read as zero
+    p.w_col_off = 0;
+    p.c_zh = 128 * 64;
+    p.ep.M = 128; p.ep.N = 64; p.ep.row_mode = ROWS_PLAIN;
+    p.ep.out_f32 = partial + (size_t)tap * kWgradSplits * 128 * 64; p.ep.ldc = 64;
+    Operand a{xt, 128, rows}, w{gt[dx + 1], 64, rows};
+    VXB_TRY(gemm(a, nullptr, w, 64, p, st));
+  }
+  if (nsplit < kWgradSplits) {
+    // unused split slots must not contribute
+    for (int tap = 0; tap < 27; ++tap)
+      VXB_CUDA(cudaMemsetAsync(partial + ((size_t)tap * kWgradSplits + nsplit) * 128 * 64, 0,
+                               (size_t)(kWgradSplits - nsplit) * 128 * 64 * sizeof(float), st));
+  }
+  wgrad_reduce_kernel<<<148 * 2, 256, 0, st>>>(partial, kWgradSplits, sc, sc + 1, dwt, 27, 128 * 64);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// gz [B, V^3, C] * scale -> planes of the zero-embedded grid [B, (V + 2e)^3, C] (e rings of zeros around the data)
+static __global__ void __launch_bounds__(256)
+embed_split_scaled_kernel(const float* __restrict__ x, int B, int V, int e, int C, const float* __restrict__ scale,
+                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const float sc = *scale;
+  const int Vp = V + 2 * e;
+  const int cg = C / 8;
+  const long long total = (long long)B * Vp * Vp * Vp * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cg) * 8;
+    long long v = i / cg;
+    const int pw = (int)(v % Vp) - e; v /= Vp;
+    const int ph = (int)(v % Vp) - e; v /= Vp;
+    const int pd = (int)(v % Vp) - e;
+    const int b = (int)(v / Vp);
+    uint4 hh = make_uint4(0, 0, 0, 0), ll = make_uint4(0, 0, 0, 0);
+    if ((unsigned)pd < (unsigned)V && (unsigned)ph < (unsigned)V && (unsigned)pw < (unsigned)V) {
+      const float* src = x + ((((long long)b * V + pd) * V + ph) * V + pw) * C + c;
+      const float4 a = *reinterpret_cast<const float4*>(src);
+      const float4 bb = *reinterpret_cast<const float4*>(src + 4);
+      const float f[8] = {a.x * sc, a.y * sc, a.z * sc, a.w * sc, bb.x * sc, bb.y * sc, bb.z * sc, bb.w * sc};
+      split8(f, hh, ll);
+    }
+    const long long o = (i / cg) * C + c;
+    *reinterpret_cast<uint4*>(hi + o) = hh;
+    *reinterpret_cast<uint4*>(lo + o) = ll;
+  }
+}
+
+size_t conv_dgrad_scratch_bytes(int B, int V, int Cz, int Cx, int k) {
+  Arena a(nullptr, 0);
+  const long long Vp = V + 4 * (k / 2);
+  alloc_planes(a, (long long)B * Vp * Vp * Vp, Cz);
+  a.get<float>(64);
+  a.get<__nv_bfloat16>(std::max<size_t>(conv3_weight_elems(64), (size_t)2 * 64 * k * k * k * Cz));
+  a.get<float>(64);
+  return a.off;
+}
+
+int conv_dgrad_f32(const float* gz, int Cz, const float* wd, int Cx, float* gxp, int B, int V, int k, float* scale_out,
+                   Arena& scratch, cudaStream_t st) {
+  const int pad = k / 2;
+  const int Vo = V + 2 * pad;                 // output (padded-gradient) grid
+  const long long Vp = Vo + 2 * pad;          // zero-embedded input grid = replicate-padded view of the zero ring
+  const long long rows = (long long)B * Vp * Vp * Vp;
+  const long long Kt = (long long)k * k * k * Cz;
+  if (Cz % 64 || Cx % 64 || rows >= (1ll << 31)) {
+    set_error("conv_dgrad: unsupported channels/size (Cz=%d Cx=%d)", Cz, Cx);
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  Planes zp = alloc_planes(scratch, rows, Cz);
+  unsigned int* amax = reinterpret_cast<unsigned int*>(scratch.get<float>(64));
+  const bool fast = (k == 3 && Cz == 64 && Vp <= 180);
+  __nv_bfloat16* wbuf = scratch.get<__nv_bfloat16>(std::max<size_t>(conv3_weight_elems(64), (size_t)2 * 64 * Kt));
+  float* zero_bias = scratch.get<float>(64);
+  if (!scratch.ok) return VXB_E_WORKSPACE_TOO_SMALL;
+  VXB_TRY(operand_scale(gz, Cz, (long long)B * V * V * V, Cz, amax, scale_out, st));
+  {
+    const long long total = rows * (Cz / 8);
+    embed_split_scaled_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(gz, B, V, 2 * pad, Cz, scale_out,
+                                                                                                      zp.hi, zp.lo);
+    VXB_LAUNCH_CHECK();
+  }
+  VXB_CUDA(cudaMemsetAsync(zero_bias, 0, 64 * sizeof(float), st));
+  const size_t block_elems = (size_t)B * Vo * Vo * Vo * 64;
+  for (int j = 0; j < Cx / 64; ++j) {
+    const float* wj = wd + (size_t)j * 64 * Kt;          // rows [64 j, 64 j + 64) of the tap-major dgrad weights
+    float* out = gxp + (size_t)j * block_elems;
+    if (fast) {
+      VXB_TRY(conv3_prepare_weights(wj, 64, wbuf, st));
+      VXB_TRY(conv3_planes(zp, nullptr, 64, 0, wbuf, zero_bias, -1.f, out, B, Vo, st, nullptr));
+    } else {
+      Planes wp{wbuf, wbuf + (size_t)64 * Kt, Kt};
+      VXB_TRY(split_rows(wj, Kt, 64, (int)Kt, wp, st));
+      Params p;
+      params_init(p);
+      const long long vp3 = Vp * Vp * Vp;
+      const long long row_lo = ((long long)pad * Vp + pad) * Vp + pad, row_hi = vp3 - row_lo;
+      p.batches = B; p.a_row_zb = (int)vp3; p.a_row_off = (int)row_lo;
+      p.m_tiles = cdiv(row_hi - row_lo, BM);
+      p.n_tiles = 1;
+      p.plan.taps = k; p.plan.Vp = (int)Vp; p.plan.cpb = Cz / 64; p.plan.cb_src0 = Cz / 64;
+      p.plan.num_kb = k * k * k * p.plan.cpb;
+      p.ep.M = (int)(row_hi - row_lo); p.ep.N = 64; p.ep.row_mode = ROWS_CONV_FLAT; p.ep.Vp = (int)Vp; p.ep.pad = pad;
+      p.ep.out_padded = 0;
+      p.ep.out_f32 = out; p.ep.ldc = 64;
+      Operand A0{zp, rows, Cz};
+      Operand w{wp, 64, Kt};
+      VXB_TRY(gemm(A0, nullptr, w, 64, p, st));
+    }
+  }
+  return VXB_OK;
+}
+
 // ------------------------------------------------------------------------------------------ conv3 (conv_umma.cuh)
 size_t conv3_weight_elems(int Cin) { return (size_t)(Cin / CV_KC) * 27 * 2 * 64 * CV_KC; }
 

@@ -509,8 +509,9 @@ def _train_methods():
         outs = (trans, rot_grip, coll) + ((arm,) if self.arm_pred_loss else ())
         return outs, self._train_gen
 
-    def _backward_train(self, gen, inputs, gouts, debug=None):
-        """Gradients of every parameter (slot order, Nones skipped) from d loss / d outputs."""
+    def _backward_train(self, gen, inputs, gouts, debug=None, out=None):
+        """Gradients of every parameter (slot order, Nones skipped) from d loss / d outputs.  out: optional list of
+        pre-allocated contiguous gradient buffers (e.g. views of a flat all-reduce arena), one per parameter."""
         if gen != self._train_gen:
             raise RuntimeError('voxactb_b200: backward through a training forward whose saved activations were overwritten by '
                                'a later forward of the same encoder (one forward/backward pair at a time per encoder)')
@@ -525,7 +526,14 @@ def _train_methods():
             for i in range(3 + int(bool(self.arm_pred_loss))):
                 t = gouts[i] if i < len(gouts) else None
                 g.append(torch.zeros(shapes[i], dtype=torch.float32, device=dev) if t is None else _lib.f32(t))
-            grads = [None if p is None else torch.empty_like(p, memory_format=torch.contiguous_format) for p in slots]
+            if out is not None:
+                it = iter(out)
+                grads = [None if p is None else next(it) for p in slots]
+                for p, t in zip(slots, grads):
+                    if p is not None and (t.shape != p.shape or not t.is_contiguous() or t.dtype != torch.float32):
+                        raise ValueError('gradient buffer does not match its parameter')
+            else:
+                grads = [None if p is None else torch.empty_like(p, memory_format=torch.contiguous_format) for p in slots]
             garr = (ctypes.c_void_p * len(slots))(*[None if t is None else t.data_ptr() for t in grads])
             darr = None
             if debug is not None:

@@ -185,8 +185,10 @@ class PerActTrainer:
         self.loss_weights = tuple(loss_weights)
         self.arm_loss_weight = arm_loss_weight
         self.R = num_rotation_classes
-        self.reducer = None
+        self.reducer = GradientReducer(self.params)   # flat fp32 gradient arena; the backward writes straight into its views
         self.last = {}
+        self.profile = False          # True: CUDA-event stage times of the next update in last_stage_ms
+        self.last_stage_ms = {}
 
     def losses_and_logit_grads(self, q_trans, q_rot_grip, q_collision, arm_out, labels):
         B = q_trans.shape[0]
@@ -205,23 +207,38 @@ class PerActTrainer:
         enc = self.enc
         if not enc.training:
             raise RuntimeError('PerActTrainer.update needs the encoder in training mode (QFunction.train())')
+        evs = []
+
+        def mark(name):
+            if self.profile:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                evs.append((name, e))
+
         with torch.no_grad():
+            mark('start')
             b = rgb_pcd[0][0].shape[0]
             pcd_flat = torch.cat([p.permute(0, 2, 3, 1).reshape(b, -1, 3) for p in pcd], 1)
             feats = torch.cat([rp[0].permute(0, 2, 3, 1).reshape(b, -1, rp[0].shape[1]) for rp in rgb_pcd], 1)
             grid = self.q._voxelizer.coords_to_bounding_voxel_grid(pcd_flat, coord_features=feats, coord_bounds=bounds)
             inputs = (_lib.f32(grid), _lib.f32(proprio), _lib.f32(lang_token_embs))
+            mark('voxelize')
             outs, gen = enc._forward_train(*inputs)
+            mark('forward')
             arm = outs[3] if enc.arm_pred_loss else None
             total, terms, g, g_arm = self.losses_and_logit_grads(outs[0], outs[1], outs[2], arm, labels)
-            grads = enc._backward_train(gen, inputs, (g['q_trans'], g['q_rot_grip'], g['q_collision'], g_arm))
-            for p, gr in zip(self.params, grads):
-                p.grad = gr
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                if self.reducer is None:
-                    self.reducer = GradientReducer(self.params)
-                self.reducer.allreduce()
+            mark('losses')
+            enc._backward_train(gen, inputs, (g['q_trans'], g['q_rot_grip'], g['q_collision'], g_arm), out=self.reducer.views)
+            for p, v in zip(self.params, self.reducer.views):
+                p.grad = v
+            mark('backward')
+            self.reducer.allreduce()
+            mark('allreduce')
             self.optimizer.step()
+            mark('optimizer')
+        if self.profile:
+            torch.cuda.synchronize()
+            self.last_stage_ms = {evs[i][0]: evs[i - 1][1].elapsed_time(evs[i][1]) for i in range(1, len(evs))}
         self.last = {'total_loss': total, 'terms': terms, 'voxel_grid': grid}
         return self.last
 
@@ -233,7 +250,7 @@ class GradientReducer:
 
     def __init__(self, params, bucket_bytes=32 << 20):
         self.params = list(params)
-        self.world = dist.get_world_size()
+        self.comm = None
         n = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
         self.views = []
@@ -244,14 +261,35 @@ class GradientReducer:
         self.bucket_elems = max(1, bucket_bytes // 4)
 
     def allreduce(self):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        world = dist.get_world_size()
         for p, v in zip(self.params, self.views):
             if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
                 v.copy_(p.grad)
                 p.grad = v
-        works = []
         n = self.flat.numel()
+        if self.flat.is_cuda:
+            # the library's own NCCL communicator (vxb_allreduce_grads): one bucketed all-reduce group + 1/world scaling on the
+            # caller's stream.  The 128-byte unique id travels through the existing torch.distributed group once.
+            L = _lib.lib()
+            if self.comm is None:
+                idbuf = ctypes.create_string_buffer(128)
+                if dist.get_rank() == 0:
+                    _lib.check(L.vxb_nccl_unique_id(idbuf), 'vxb_nccl_unique_id')
+                t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).to(self.flat.device)
+                dist.broadcast(t, src=0)
+                idbytes = bytes(t.cpu().tolist())
+                comm = ctypes.c_void_p()
+                torch.cuda.synchronize()
+                _lib.check(L.vxb_nccl_init(idbytes, dist.get_rank(), world, ctypes.byref(comm)), 'vxb_nccl_init')
+                self.comm = comm
+            _lib.check(L.vxb_allreduce_grads(self.comm, _lib.ptr(self.flat), n, 1.0 / world, self.bucket_elems, _lib.stream()),
+                       'vxb_allreduce_grads')
+            return
+        works = []
         for o in range(0, n, self.bucket_elems):
             works.append(dist.all_reduce(self.flat[o:min(n, o + self.bucket_elems)], op=dist.ReduceOp.SUM, async_op=True))
         for w in works:
             w.wait()
-        self.flat.div_(self.world)
+        self.flat.div_(world)
