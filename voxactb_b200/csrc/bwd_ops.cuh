@@ -386,34 +386,76 @@ inline int channel_argmax(const float* x, const float* mx, int mx_stride, int B,
 // SpatialSoftmax3D + AdaptiveMaxPool3d(1) adjoint (grad_oracle.spatial_softmax3d_backward / global_maxpool_backward):
 // g[b,v,c] (=|+=) p[v] / T * sum_k ge[b,c,k] (pos[v,k] - e[b,c,k]) + [v == argmax] gm[b,c],
 // p[v] = 2^(x k - m) / s with the forward's own (m, s) (stats [B][2][C]), e = the forward's soft-argmax output.
+// grid (chunks, B): a thread owns 4 channels and walks the positions of its chunk (same layout as ss_partial_kernel).
 static __global__ void __launch_bounds__(256)
 ss_bwd_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ e, int e_stride,
               const float* __restrict__ ge, int ge_stride, const float* __restrict__ gm, int gm_stride,
-              const int* __restrict__ argidx, float* __restrict__ g, int accumulate, int B, int Dd, int Hh, int Ww, int C) {
-  const long long P = (long long)Dd * Hh * Ww;
-  const long long total = (long long)B * P * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const long long pos = (i / C) % P;
-    const int b = (int)(i / (P * C));
-    const int w = (int)(pos % Ww), h = (int)((pos / Ww) % Hh), d = (int)(pos / ((long long)Ww * Hh));
+              const int* __restrict__ argidx, float* __restrict__ g, int accumulate, int Dd, int Hh, int Ww, int C, int chunk) {
+  extern __shared__ float ssb_lut[];   // coordinate LUTs [Dd + Hh + Ww]
+  const int b = blockIdx.y;
+  const int P = Dd * Hh * Ww;
+  for (int i = threadIdx.x; i < Dd + Hh + Ww; i += 256)
+    ssb_lut[i] = i < Dd ? ss_lin_coord(i, Dd) : (i < Dd + Hh ? ss_lin_coord(i - Dd, Hh) : ss_lin_coord(i - Dd - Hh, Ww));
+  __syncthreads();
+  const float* lutD = ssb_lut;
+  const float* lutH = ssb_lut + Dd;
+  const float* lutW = ssb_lut + Dd + Hh;
+  const int G = C >> 2, PL = 256 / G;
+  const int gq = threadIdx.x % G, pl = threadIdx.x / G;
+  if (pl >= PL) return;
+  const int c = gq * 4;
+  float m[4], is[4], ex[4], ey[4], ez[4], gx[4], gy[4], gz[4], gmx[4];
+  int am[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    m[j] = stats[((size_t)b * 2) * C + c + j];
+    is[j] = 1.f / stats[((size_t)b * 2 + 1) * C + c + j];
+    const float* eb = e + (size_t)b * e_stride + (c + j) * 3;
+    const float* gb = ge + (size_t)b * ge_stride + (c + j) * 3;
+    ex[j] = eb[0]; ey[j] = eb[1]; ez[j] = eb[2];
+    gx[j] = gb[0] * 100.f; gy[j] = gb[1] * 100.f; gz[j] = gb[2] * 100.f;     // 1 / T, T = 0.01
+    gmx[j] = gm[(size_t)b * gm_stride + c + j];
+    am[j] = argidx[b * C + c + j];
+  }
+  const int p_begin = blockIdx.x * chunk, p_end = min(P, p_begin + chunk);
+  int p = p_begin + pl;
+  int d = p / (Hh * Ww), h = (p / Ww) % Hh, w = p % Ww;
+  const float4* xp = reinterpret_cast<const float4*>(x + ((size_t)b * P) * C) + gq;
+  float4* gp = reinterpret_cast<float4*>(g + ((size_t)b * P) * C) + gq;
+  for (; p < p_end; p += PL) {
+    const float4 v = __ldg(xp + (size_t)p * G);
     // meshgrid('xy') quirk of network_utils.py:782-792: pos_x along H, pos_y along D, pos_z along W
-    const float px = ss_lin_coord(h, Hh), py = ss_lin_coord(d, Dd), pz = ss_lin_coord(w, Ww);
-    const float m = stats[((size_t)b * 2) * C + c], s = stats[((size_t)b * 2 + 1) * C + c];
-    const float p = exp2f(x[i] * kSSLog2eOverT - m) / s;
-    const float* eb = e + (size_t)b * e_stride + c * 3;
-    const float* gb = ge + (size_t)b * ge_stride + c * 3;
-    const float inner = gb[0] * (px - eb[0]) + gb[1] * (py - eb[1]) + gb[2] * (pz - eb[2]);
-    float v = p * inner * 100.f;   // 1 / T, T = 0.01
-    if ((int)pos == argidx[b * C + c]) v += gm[(size_t)b * gm_stride + c];
-    g[i] = accumulate ? g[i] + v : v;
+    const float px = lutH[h], py = lutD[d], pz = lutW[w];
+    const float xv[4] = {v.x, v.y, v.z, v.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float pr = exp2f(xv[j] * kSSLog2eOverT - m[j]) * is[j];
+      o[j] = pr * (gx[j] * (px - ex[j]) + gy[j] * (py - ey[j]) + gz[j] * (pz - ez[j]));
+      if (p == am[j]) o[j] += gmx[j];
+    }
+    float4 r = make_float4(o[0], o[1], o[2], o[3]);
+    if (accumulate) { const float4 t = gp[(size_t)p * G]; r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w; }
+    gp[(size_t)p * G] = r;
+    w += PL;
+    while (w >= Ww) {
+      w -= Ww;
+      if (++h >= Hh) { h = 0; ++d; }
+    }
   }
 }
 inline int ss_bwd(const float* x, const float* stats, const float* e, int e_stride, const float* ge, int ge_stride,
                   const float* gm, int gm_stride, const int* argidx, float* g, bool accumulate, int B, int Dd, int Hh, int Ww,
                   int C, cudaStream_t st) {
-  ss_bwd_kernel<<<148 * 16, 256, 0, st>>>(x, stats, e, e_stride, ge, ge_stride, gm, gm_stride, argidx, g, accumulate ? 1 : 0, B,
-                                          Dd, Hh, Ww, C);
+  if (C % 4 || C > 1024) {
+    set_error("ss_bwd: C=%d must be a multiple of 4, <= 1024", C);
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  const size_t P = (size_t)Dd * Hh * Ww;
+  const int chunks = ss_num_chunks(P, B);
+  const int chunk = (int)((P + chunks - 1) / chunks);
+  ss_bwd_kernel<<<dim3(chunks, B), 256, (size_t)(Dd + Hh + Ww) * sizeof(float), st>>>(x, stats, e, e_stride, ge, ge_stride, gm, gm_stride,
+                                                                                      argidx, g, accumulate ? 1 : 0, Dd, Hh, Ww, C, chunk);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }
@@ -506,6 +548,55 @@ static __global__ void fold_dgrad_weight_kernel(const float* __restrict__ wf, fl
     wd[i] = wf[(((size_t)r * Co + co) * 27 + (26 - nb)) * Ci + ci];
   }
 }
+// folded up-convolution dgrad as GEMM + col2im: wt2[(nb, ci)][(r, co)] = wfold[r][co][nb][ci], so that
+// T[q][(nb, ci)] = sum_(r,co) g_ph[q][(r,co)] wt2[(nb,ci)][(r,co)] is output q's contribution to low[clamp(q + nb - 1)][ci]
+static __global__ void fold_gemm_weight_kernel(const float* __restrict__ wf, float* __restrict__ wt2, int R, int Co, int Ci) {
+  const size_t total = (size_t)R * Co * 27 * Ci;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int rc = (int)(i % ((size_t)R * Co));
+    const int ci = (int)((i / ((size_t)R * Co)) % Ci);
+    const int nb = (int)(i / ((size_t)R * Co * Ci));
+    wt2[i] = wf[((size_t)rc * 27 + nb) * Ci + ci];
+  }
+}
+// g[b, v, c] = sum_{nb} sum_{q : clamp(q + nb - 1, 0, S-1) == v} T[(b, q)][nb][c]   (col2im with the replicate-padding
+// adjoint folded in; same source enumeration as trans_bwd_kernel)
+static __global__ void __launch_bounds__(256)
+col2im3_fold_kernel(const float* __restrict__ T, float* __restrict__ g, int B, int S, int C) {
+  const int cg = C / 4;
+  const long long total = (long long)B * S * S * S * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cg) * 4;
+    long long r = i / cg;
+    const int x = (int)(r % S); r /= S;
+    const int y = (int)(r % S); r /= S;
+    const int z = (int)(r % S);
+    const int b = (int)(r / S);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int dz = 0; dz < 3; ++dz) {
+      int zs[2], nz = 0;
+      { const int a = z - dz + 1; if (a >= 0 && a < S) zs[nz++] = a; if (z == 0 && dz == 0) zs[nz++] = 0; if (z == S - 1 && dz == 2) zs[nz++] = S - 1; }
+      for (int dy = 0; dy < 3; ++dy) {
+        int ys[2], ny = 0;
+        { const int a = y - dy + 1; if (a >= 0 && a < S) ys[ny++] = a; if (y == 0 && dy == 0) ys[ny++] = 0; if (y == S - 1 && dy == 2) ys[ny++] = S - 1; }
+        for (int dx = 0; dx < 3; ++dx) {
+          int xs[2], nx = 0;
+          { const int a = x - dx + 1; if (a >= 0 && a < S) xs[nx++] = a; if (x == 0 && dx == 0) xs[nx++] = 0; if (x == S - 1 && dx == 2) xs[nx++] = S - 1; }
+          const int nb = (dz * 3 + dy) * 3 + dx;
+          for (int a = 0; a < nz; ++a)
+            for (int bb = 0; bb < ny; ++bb)
+              for (int cc = 0; cc < nx; ++cc) {
+                const size_t q = (((size_t)b * S + zs[a]) * S + ys[bb]) * S + xs[cc];
+                const float4 v = *reinterpret_cast<const float4*>(T + (q * 27 + nb) * C + c);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+              }
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(g + (i / cg) * C + c) = acc;
+  }
+}
+
 // patchify (stride == k) dgrad weights: wd[t][ci][co] = w[co][ci][t]
 static __global__ void patch_dgrad_weight_kernel(const float* __restrict__ w, float* __restrict__ wd, int Co, int Ci, int k3) {
   const size_t total = (size_t)Co * Ci * k3;

@@ -56,7 +56,7 @@ static size_t train_tc_scratch_bytes(const Dims& m, int B) {
   g(2 * cq, m.C, Bn, false); g(Bn, m.C, 2 * cq, false); g(m.C, cq, BT, false); g(BT, cq, m.C, false); g(cq, m.C, BT, false);
   g(BT, m.C, cq, false); g(2 * cq, m.D, R, false); g(R, m.D, 2 * cq, false); g(m.D, cq, R, false); g(R, cq, m.D, false);
   g(m.C, 512, B * m.nl, false);
-  g(27 * 64, m.s * m.s * m.s * 64, BT, false);                                                                     // folded wgrad
+  g(27 * 64, m.s * m.s * m.s * 64, BT, false); g(BT, 27 * 64, m.s * m.s * m.s * 64, false);                       // folded wgrad / dgrad
   sb = std::max(sb, umma::conv3_wgrad_scratch_bytes(B, m.V));
   sb = std::max(sb, umma::conv_dgrad_scratch_bytes(B, m.V, 64, 128, 3));
   sb = std::max(sb, umma::conv_dgrad_scratch_bytes(B, m.S, m.s * m.s * m.s * 64, 64, 3));
@@ -393,7 +393,7 @@ static int qnet_backward_impl(const vxb_qnet_desc* d, const Dims& m, const void*
   // ---- dgrad weights from the current parameters
   bwd::conv_dgrad_weight_kernel<<<148 * 2, 256, 0, st>>>(P(VXB_P_FINAL_W), t.wd_final, 64, 128, 27);
   bwd::conv_dgrad_weight_kernel<<<148 * 4, 256, 0, st>>>(P(VXB_P_UP0_W), t.wd_up0, 64, m.C, k3);
-  bwd::fold_dgrad_weight_kernel<<<148 * 8, 256, 0, st>>>(pw.up1_fold, t.wd_fold, s3, 64, 64);
+  bwd::fold_gemm_weight_kernel<<<148 * 8, 256, 0, st>>>(pw.up1_fold, t.wd_fold, s3, 64, 64);
   bwd::patch_dgrad_weight_kernel<<<148 * 2, 256, 0, st>>>(P(VXB_P_PATCH_W), t.wd_patch, 64, 64, k3);
   VXB_LAUNCH_CHECK();
 
@@ -464,10 +464,11 @@ static int qnet_backward_impl(const vxb_qnet_desc* d, const Dims& m, const void*
     bwd::fold_upconv_weights_bwd_kernel<<<148 * 8, 256, 0, st>>>(t.dwt, G.at(VXB_P_UP1_W), 64, 64, m.k, m.s);
     VXB_LAUNCH_CHECK();
   }
-  {
-    const bwd::FoldDst dst[1] = {{t.g_low, 64, 0}};
-    VXB_TRY(bwd::conv_dgrad_fold(t.g_ph, s3 * 64, t.wd_fold, 64, t.g_lowp, B, m.S, 3, dst, false, st));
-  }
+  // dgrad as GEMM + col2im: T[q][(nb, ci)] = g_ph[q] . wt2[(nb, ci)], then every low-resolution voxel gathers the taps that
+  // touched it (replicate-padding adjoint included)
+  VXB_TRY(bwd::gemm_nt(t.g_ph, s3 * 64, t.wd_fold, s3 * 64, t.im2col, 27 * 64, B * m.T, 27 * 64, s3 * 64, false, st));
+  bwd::col2im3_fold_kernel<<<148 * 8, 256, 0, st>>>(t.im2col, t.g_low, B, m.S, 64);
+  VXB_LAUNCH_CHECK();
   VXB_TRY(DBG(3, t.g_low, (size_t)B * m.T * 64));
   // ---- up0, first half: conv k (C -> 64) at S^3
   VXB_TRY(bwd::lrelu_bwd(t.g_low, w.low, (long long)B * m.T * 64, slope, st));

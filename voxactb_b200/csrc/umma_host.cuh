@@ -115,8 +115,9 @@ int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out
 // result is unscaled by a small post pass.
 // C[M,N] (+)= opA(A) opW(W)^T with K-major products: A is [M,K] (a_trans = false) or stored [K,M] (a_trans = true),
 // W is [N,K] (w_trans = false) or stored [K,N] (w_trans = true).  Returns VXB_E_WORKSPACE_TOO_SMALL if scratch is short.
+// A (the gradient operand) is always scaled dynamically; W (weights / forward activations) only with w_dynamic_scale.
 int gemm_any_f32(const float* A, long long lda, bool a_trans, const float* W, long long ldw, bool w_trans, float* C, int ldc,
-                 int M, int N, int K, bool accumulate, Arena& scratch, cudaStream_t st);
+                 int M, int N, int K, bool accumulate, Arena& scratch, cudaStream_t st, bool w_dynamic_scale = false);
 size_t gemm_any_scratch_bytes(int M, int N, int K, bool accumulate);
 // Weight gradient of the 3x3x3 convolution on cat[x0, x1] (64 channels each, fp32 compact [B, V^3, 64]) given the
 // pre-activation gradient gz [B, V^3, 64]:  dwt[(tap, ci)][co] = sum_rows xpad[row + shift(tap)][ci] gz[row][co]

@@ -895,16 +895,23 @@ size_t gemm_any_scratch_bytes(int M, int N, int K, bool accumulate) {
   return a.off;
 }
 
+static __global__ void set_one_kernel(float* p) { *p = 1.f; }
+
 int gemm_any_f32(const float* A, long long lda, bool a_trans, const float* W, long long ldw, bool w_trans, float* C, int ldc,
-                 int M, int N, int K, bool accumulate, Arena& scratch, cudaStream_t st) {
+                 int M, int N, int K, bool accumulate, Arena& scratch, cudaStream_t st, bool w_dynamic_scale) {
   const long long Kp = pad8(K);
   Planes Ap = alloc_planes(scratch, M, Kp), Wp = alloc_planes(scratch, N, Kp);
   float* sc = scratch.get<float>(64);           // [0] sa, [1] sw, [2..3] amax temporaries
   float* tmp = accumulate ? scratch.get<float>((size_t)M * N) : C;
   if (!scratch.ok) return VXB_E_WORKSPACE_TOO_SMALL;
-  auto split_op = [&](const float* X, long long ldx, bool trans, int rows /*M or N*/, Planes P, float* scale, unsigned int* amax) -> int {
+  auto split_op = [&](const float* X, long long ldx, bool trans, int rows /*M or N*/, Planes P, float* scale, unsigned int* amax,
+                      bool dynamic) -> int {
     // stored extent: [rows, K] (plain) or [K, rows] (transposed)
-    VXB_TRY(operand_scale(X, ldx, trans ? K : rows, trans ? rows : K, amax, scale, st));
+    if (dynamic) {
+      VXB_TRY(operand_scale(X, ldx, trans ? K : rows, trans ? rows : K, amax, scale, st));
+    } else {
+      set_one_kernel<<<1, 1, 0, st>>>(scale);       // weights / forward activations: O(1), as in the inference path
+    }
     if (!trans) {
       const long long total = (long long)rows * (P.ld / 8);
       split_rows_scaled_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(X, ldx, rows, K, scale, P.hi,
@@ -915,8 +922,8 @@ int gemm_any_f32(const float* A, long long lda, bool a_trans, const float* W, lo
     VXB_LAUNCH_CHECK();
     return VXB_OK;
   };
-  VXB_TRY(split_op(A, lda, a_trans, M, Ap, sc, reinterpret_cast<unsigned int*>(sc + 2)));
-  VXB_TRY(split_op(W, ldw, w_trans, N, Wp, sc + 1, reinterpret_cast<unsigned int*>(sc + 3)));
+  VXB_TRY(split_op(A, lda, a_trans, M, Ap, sc, reinterpret_cast<unsigned int*>(sc + 2), true));
+  VXB_TRY(split_op(W, ldw, w_trans, N, Wp, sc + 1, reinterpret_cast<unsigned int*>(sc + 3), w_dynamic_scale));
   Params p;
   params_init(p);
   const int nt = pick_ntile(N);
