@@ -61,6 +61,19 @@ int vxb_voxelize_f32(const float* coords, const float* feats, const float* bound
                      int B, int N, int F, int V, float* out, int layout, int32_t* out_idx,
                      void* ws, size_t ws_bytes, void* stream);
 
+/*
+ * Raw-depth entry: the depth -> world point cloud back-projection that the reference does on
+ * the host per camera per step (PyRep pyrep/objects/vision_sensor.py:155-175, 381-412) is fused into the scatter kernel, so
+ * the path ingests depth images + camera matrices and the 3 MB/sample point cloud never crosses PCIe.
+ * depth    [B,cams,H,W] fp32 metres; proj_inv [B,cams,3,4] FLOAT64 = inv(K [R^T | -R^T C])[0:3] (one 4x4 inverse per
+ * camera on the host, as vision_sensor.py:165-171 does); rgb [B,cams,F,H,W] planar image features (NULL when F == 0).
+ * Point n = cam*H*W + y*W + x: pc = (x d, y d, d) in fp32, world = proj_inv . (pc, 1) in float64, rounded to fp32 -- the
+ * reference's arithmetic -- then voxelized exactly like vxb_voxelize_f32.  out_points: NULL or [B,N,3] (parity tests).
+ */
+int vxb_voxelize_depth_f32(const float* depth, const double* proj_inv, const float* rgb, const float* bounds, int Bb,
+                           int B, int cams, int H, int W, int F, int V, float* out, int layout, float* out_points,
+                           int32_t* out_idx, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ Q-network */
 typedef struct vxb_qnet_desc {
   int32_t struct_bytes;     /* sizeof(vxb_qnet_desc), for ABI checking */
@@ -217,6 +230,14 @@ int vxb_select_action_f32(const float* q_trans, const float* rot_grip, const flo
                           const float* bounds, int Bb, int B, int V, int R,
                           int32_t* coords, int32_t* rot_grip_idx, int32_t* coll_idx,
                           float* attention_xyz, void* ws, size_t ws_bytes, void* stream);
+
+/* act() tail: the 9-D continuous action QAttentionStackAgent.act assembles on the host
+ * (reference qattention_stack_agent.py:78-89): action [B,9] = [attention_xyz(3), quaternion x,y,z,w (4) =
+ * Rotation.from_euler('xyz', rot_idx * rotation_resolution - 180, degrees=True).as_quat() (helpers/utils.py:103-105),
+ * gripper index (1), ignore-collision index (1)], from vxb_select_action_f32's outputs, on the device. */
+int vxb_act_tail_f32(const int32_t* rot_grip_idx /*[B,4]*/, const int32_t* coll_idx /*[B]*/,
+                     const float* attention_xyz /*[B,3]*/, float rotation_resolution, float* action /*[B,9]*/, int B,
+                     void* stream);
 
 /* ------------------------------------------------------------------ building blocks (exported for the per-op parity tests) */
 /* number of tcgen05 (split 16-bit x3) GEMM kernels launched so far by this process: lets tests prove that

@@ -222,7 +222,46 @@ def main_train():
         print(name, 'total', float(total), 'params with grad', len(keys), 'without', len(out['no_grad_keys']))
 
 
+DEPTH_CASES = {
+    'depth_v20': dict(V=20, B=2, cameras=2, H=24, W=32, seed=51),
+}
+
+
+def main_depth():
+    """Raw-depth fixtures (row f1): the reference's OWN back-projection (PyRep vision_sensor.py, loaded from the unmodified
+    file with the simulator bindings stubbed) followed by the reference VoxelGrid."""
+    import importlib.util
+    from unittest import mock
+    for name in ('pyrep', 'pyrep.backend', 'pyrep.backend.sim', 'pyrep.objects', 'pyrep.objects.object', 'pyrep.const'):
+        sys.modules.setdefault(name, mock.MagicMock())
+    sys.modules['pyrep.objects.object'].Object = object
+    spec = importlib.util.spec_from_file_location('ref_vision_sensor', '/root/reference/PyRep/pyrep/objects/vision_sensor.py')
+    vs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vs)
+    RefVG, _ = refimport.load()
+    for name, c in DEPTH_CASES.items():
+        o = synth.make_depth_observation(c['seed'], c['B'], c['cameras'], c['H'], c['W'])
+        B, cams, H, W = o['depth'].shape
+        pts = np.empty((B, cams * H * W, 3), dtype=np.float32)
+        for b in range(B):
+            for cam in range(cams):
+                wc = vs.VisionSensor.pointcloud_from_depth_and_camera_params(o['depth'][b, cam].numpy(), o['extrinsics'][b, cam],
+                                                                             o['intrinsics'][b, cam])
+                pts[b, cam * H * W:(cam + 1) * H * W] = wc.reshape(-1, 3)
+        coords = torch.from_numpy(pts)
+        feats = o['rgb'].permute(0, 1, 3, 4, 2).reshape(B, -1, 3)
+        vg = RefVG(synth.SCENE_BOUNDS, c['V'], 'cpu', B, 3, coords.shape[1])
+        grid = vg.coords_to_bounding_voxel_grid(coords, feats, o['bounds'])
+        idx = ref_indices(vg, coords, o['bounds'])
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), points=pts, idx=idx.numpy().astype(np.int16), grid=grid.numpy(),
+                            in_checksum=np.array([checksum(o['depth']), float(np.abs(o['intrinsics']).sum()),
+                                                  float(np.abs(o['extrinsics']).sum())]))
+        print(name, 'occupied', int((grid[..., -1] > 0).sum()), 'in-bounds points', int(((idx > 0) & (idx < c['V'] + 1)).all(-1).sum()))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'depth':
+        return main_depth()
     if len(sys.argv) > 1 and sys.argv[1] == 'two_robots':
         return main_two_robots()
     if len(sys.argv) > 1 and sys.argv[1] == 'train':

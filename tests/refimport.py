@@ -21,13 +21,25 @@ def load():
             m = types.ModuleType(name)
             m.__path__ = [os.path.join(REF, name.replace('.', '/'))]
             sys.modules[name] = m
-    from voxel.voxel_grid import VoxelGrid
-    from agents.peract_bc.perceiver_lang_io import PerceiverVoxelLangEncoder
-    return VoxelGrid, PerceiverVoxelLangEncoder
+    # by file path under private names: voxactb_b200.install_shims() (tests/test_agent_dropin.py) rebinds the public module
+    # names `voxel.voxel_grid` / `agents.peract_bc.perceiver_lang_io` to this package for the rest of the process
+    return _by_path('voxel/voxel_grid.py').VoxelGrid, _by_path('agents/peract_bc/perceiver_lang_io.py').PerceiverVoxelLangEncoder
+
+
+_LOADED = {}
+
+
+def _by_path(rel):
+    import importlib.util
+    if rel not in _LOADED:
+        spec = importlib.util.spec_from_file_location('_vxb_ref_' + rel.replace('/', '_')[:-3], os.path.join(REF, rel))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _LOADED[rel] = mod
+    return _LOADED[rel]
 
 
 def load2():
     """PerceiverVoxelLang2RobotsEncoder from the unmodified reference tree."""
     load()
-    from agents.peract_bc.perceiver_lang_io import PerceiverVoxelLang2RobotsEncoder
-    return PerceiverVoxelLang2RobotsEncoder
+    return _by_path('agents/peract_bc/perceiver_lang_io.py').PerceiverVoxelLang2RobotsEncoder

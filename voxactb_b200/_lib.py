@@ -43,6 +43,8 @@ SIGNATURES = {
     'vxb_voxelize_workspace_bytes': (c_size_t, [c_int] * 4),
     'vxb_voxelize_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'vxb_voxelize_depth_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'vxb_qnet_num_params': (c_int, [ctypes.POINTER(QnetDesc)]),
     'vxb_qnet_prepared_bytes': (c_size_t, [ctypes.POINTER(QnetDesc)]),
     'vxb_qnet_workspace_bytes': (c_size_t, [ctypes.POINTER(QnetDesc), c_int]),
@@ -69,6 +71,7 @@ SIGNATURES = {
     'vxb_select_action_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_size_t, c_void_p]),
+    'vxb_act_tail_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p]),
     'vxb_umma_launch_count': (c_ll, []),
     'vxb_linear_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'vxb_linear_f32': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,

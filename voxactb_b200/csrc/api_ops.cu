@@ -128,6 +128,49 @@ extern "C" int vxb_select_action_f32(const float* q_trans, const float* rot_grip
   return VXB_OK;
 }
 
+// ---------------------------------------------------------------- act() tail
+// continuous_action = [attention_coordinate(3), quaternion(4), gripper(1), ignore_collision(1)] as QAttentionStackAgent.act
+// assembles it on the host through numpy / scipy (reference qattention_stack_agent.py:78-89 with
+// helpers/utils.py:103-105 discrete_euler_to_quaternion = Rotation.from_euler('xyz', idx*res - 180, degrees).as_quat()):
+// extrinsic x-y-z Euler angles -> q = qz * (qy * qx), scalar-last, evaluated in float64 like scipy.
+namespace vxb {
+__device__ __forceinline__ void quat_mul(const double a[4], const double b[4], double o[4]) {   // (x, y, z, w), o = a * b
+  o[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  o[1] = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0];
+  o[2] = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3];
+  o[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+}
+__global__ void act_tail_kernel(const int32_t* __restrict__ rg, const int32_t* __restrict__ coll, const float* __restrict__ xyz,
+                                double resolution, float* __restrict__ action, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double q[3][4];
+  for (int a = 0; a < 3; ++a) {
+    const double half = ((double)rg[b * 4 + a] * resolution - 180.0) * (3.14159265358979323846 / 180.0) * 0.5;
+    q[a][0] = q[a][1] = q[a][2] = 0.0;
+    q[a][a] = sin(half);
+    q[a][3] = cos(half);
+  }
+  double t[4], r[4];
+  quat_mul(q[1], q[0], t);      // qy * qx
+  quat_mul(q[2], t, r);         // qz * (qy * qx)
+  float* o = action + (size_t)b * 9;
+  o[0] = xyz[b * 3 + 0]; o[1] = xyz[b * 3 + 1]; o[2] = xyz[b * 3 + 2];
+  o[3] = (float)r[0]; o[4] = (float)r[1]; o[5] = (float)r[2]; o[6] = (float)r[3];
+  o[7] = (float)rg[b * 4 + 3];
+  o[8] = (float)coll[b];
+}
+}  // namespace vxb
+
+extern "C" int vxb_act_tail_f32(const int32_t* rot_grip_idx, const int32_t* coll_idx, const float* attention_xyz,
+                                float rotation_resolution, float* action, int B, void* stream) {
+  VXB_CHECK_ARG(rot_grip_idx && coll_idx && attention_xyz && action && B > 0, "act_tail: bad arguments");
+  act_tail_kernel<<<cdiv(B, 64), 64, 0, (cudaStream_t)stream>>>(rot_grip_idx, coll_idx, attention_xyz,
+                                                                (double)rotation_resolution, action, B);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
 // ---------------------------------------------------------------- building blocks
 extern "C" long long vxb_umma_launch_count(void) { return umma::launches(); }
 

@@ -57,13 +57,26 @@ __device__ __forceinline__ int axis_index(float p, const AxisMap& m, int V) {
   return (int)f;
 }
 
-template <int F>
+// Raw-depth source: the world-frame point of pixel (x, y) of camera `cam` is formed here instead
+// of on the host -- VisionSensor.pointcloud_from_depth_and_camera_params (reference PyRep/pyrep/objects/vision_sensor.py:
+// 155-175 with _create_uniform_pixel_coords_image / _pixel_to_world_coords :381-412): pc = (x d, y d, d) in the depth dtype
+// (fp32), then world = inv(K [R^T | -R^T C])[0:3] . (pc, 1) in float64, stored as fp32.  The 3x4 float64 matrix per
+// (sample, camera) comes from the host (a 4x4 inverse per camera per step, as in the reference).
+struct DepthSrc {
+  const float* depth;       // [B, cams, H, W] metres
+  const double* minv;       // [B, cams, 3, 4]
+  const float* rgb;         // [B, cams, F, H, W] planar image features, or null when F == 0
+  float* out_points;        // optional [B, N, 3] back-projected points (parity tests), N = cams * H * W
+  int cams, H, W;
+};
+
+template <int F, bool DEPTH>
 __global__ void __launch_bounds__(256)
 vox_scatter_kernel(const float* __restrict__ coords, const float* __restrict__ feats,
                    const float* __restrict__ bounds, int Bb, int N, int V,
                    float* __restrict__ table, int slots, int entry_floats,
                    uint32_t* __restrict__ bitmap, int bitmap_words,
-                   int32_t* __restrict__ out_idx) {
+                   int32_t* __restrict__ out_idx, const DepthSrc ds) {
   const int b = blockIdx.y;
   __shared__ AxisMap maps[3];
   if (threadIdx.x == 0) make_axis_maps(bounds + (Bb == 1 ? 0 : b) * 6, V, maps);
@@ -73,10 +86,31 @@ vox_scatter_kernel(const float* __restrict__ coords, const float* __restrict__ f
   float val[3 + F];
   int key = 0;
   if (in_range) {
+    if constexpr (DEPTH) {
+      const int hw = ds.H * ds.W;
+      const int cam = n / hw, pix = n - cam * hw;
+      const int y = pix / ds.W, x = pix - y * ds.W;
+      const size_t img = (size_t)b * ds.cams + cam;
+      const float d = ds.depth[img * hw + pix];
+      const float xd = __fmul_rn((float)x, d), yd = __fmul_rn((float)y, d);     // upc * depth in fp32 (vision_sensor.py:165)
+      const double* M = ds.minv + img * 12;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const double w = fma(M[a * 4 + 2], (double)d, fma(M[a * 4 + 1], (double)yd, fma(M[a * 4 + 0], (double)xd, M[a * 4 + 3])));
+        val[a] = (float)w;
+      }
+      if (ds.out_points) {
+        float* o = ds.out_points + ((size_t)b * N + n) * 3;
+        o[0] = val[0]; o[1] = val[1]; o[2] = val[2];
+      }
+#pragma unroll
+      for (int f = 0; f < F; ++f) val[3 + f] = ds.rgb[(img * F + f) * hw + pix];
+    } else {
     const float* c = coords + ((size_t)b * N + n) * 3;
     val[0] = c[0]; val[1] = c[1]; val[2] = c[2];
 #pragma unroll
     for (int f = 0; f < F; ++f) val[3 + f] = feats[((size_t)b * N + n) * F + f];
+    }
     int ix = axis_index(val[0], maps[0], V);
     int iy = axis_index(val[1], maps[1], V);
     int iz = axis_index(val[2], maps[2], V);
@@ -203,10 +237,10 @@ extern "C" size_t vxb_voxelize_workspace_bytes(int B, int N, int V, int F) {
 
 extern "C" int vxb_voxelize_launches(void) { return 3; }
 
-template <int F>
+template <int F, bool DEPTH>
 static int voxelize_impl(const float* coords, const float* feats, const float* bounds, int Bb,
                          int B, int N, int V, float* out, int32_t* out_idx, void* ws,
-                         cudaStream_t st) {
+                         cudaStream_t st, const DepthSrc& ds) {
   const int slots = table_slots(N);
   const int ef = entry_floats_for(F);
   const size_t tab_bytes = align_up((size_t)B * slots * ef * sizeof(float), 256);
@@ -215,8 +249,8 @@ static int voxelize_impl(const float* coords, const float* feats, const float* b
   uint32_t* bitmap = (uint32_t*)((char*)ws + tab_bytes);
   VXB_CUDA(cudaMemsetAsync(ws, 0, tab_bytes + (size_t)B * words * 4, st));
   dim3 g1(cdiv(N, 256), B);
-  vox_scatter_kernel<F><<<g1, 256, 0, st>>>(coords, feats, bounds, Bb, N, V, table, slots, ef,
-                                            bitmap, words, out_idx);
+  vox_scatter_kernel<F, DEPTH><<<g1, 256, 0, st>>>(coords, feats, bounds, Bb, N, V, table, slots, ef,
+                                                   bitmap, words, out_idx, ds);
   VXB_LAUNCH_CHECK();
   dim3 g2(cdiv((long long)V * V * V, 256), B);
   vox_fill_kernel<F><<<g2, 256, 0, st>>>(table, slots, ef, bitmap, words, V, out);
@@ -242,11 +276,43 @@ extern "C" int vxb_voxelize_f32(const float* coords, const float* feats, const f
     return VXB_E_WORKSPACE_TOO_SMALL;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  DepthSrc none;
+  memset(&none, 0, sizeof(none));
   switch (F) {
-    case 0: return voxelize_impl<0>(coords, feats, bounds, Bb, B, N, V, out, out_idx, ws, st);
-    case 3: return voxelize_impl<3>(coords, feats, bounds, Bb, B, N, V, out, out_idx, ws, st);
+    case 0: return voxelize_impl<0, false>(coords, feats, bounds, Bb, B, N, V, out, out_idx, ws, st, none);
+    case 3: return voxelize_impl<3, false>(coords, feats, bounds, Bb, B, N, V, out, out_idx, ws, st, none);
     default:
       set_error("voxelize: feature_size %d not compiled (0 or 3)", F);
+      return VXB_E_UNSUPPORTED_SHAPE;
+  }
+}
+
+extern "C" int vxb_voxelize_depth_f32(const float* depth, const double* proj_inv, const float* rgb, const float* bounds, int Bb,
+                                      int B, int cams, int H, int W, int F, int V, float* out, int layout, float* out_points,
+                                      int32_t* out_idx, void* ws, size_t ws_bytes, void* stream) {
+  VXB_CHECK_ARG(depth && proj_inv && bounds && out && ws, "voxelize_depth: null pointer argument");
+  VXB_CHECK_ARG(B > 0 && cams > 0 && H > 0 && W > 0 && V > 0, "voxelize_depth: sizes must be positive");
+  VXB_CHECK_ARG((long long)cams * H * W < (1ll << 30), "voxelize_depth: too many pixels");
+  VXB_CHECK_ARG(Bb == 1 || Bb == B, "voxelize_depth: bounds batch must be 1 or B (got %d, B=%d)", Bb, B);
+  VXB_CHECK_ARG(layout == VXB_LAYOUT_CHANNELS_LAST, "voxelize_depth: unknown layout %d", layout);
+  VXB_CHECK_ARG(F == 0 || rgb, "voxelize_depth: rgb is null but F=%d", F);
+  const int N = cams * H * W;
+  if ((long long)V * V * V >= (1ll << 30)) {
+    set_error("voxelize_depth: V=%d too large", V);
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  if (ws_bytes < vxb_voxelize_workspace_bytes(B, N, V, F)) {
+    set_error("voxelize_depth: workspace too small (%zu < %zu)", ws_bytes, vxb_voxelize_workspace_bytes(B, N, V, F));
+    return VXB_E_WORKSPACE_TOO_SMALL;
+  }
+  DepthSrc ds;
+  ds.depth = depth; ds.minv = proj_inv; ds.rgb = rgb; ds.out_points = out_points; ds.cams = cams; ds.H = H; ds.W = W;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (F) {
+    case 0: return voxelize_impl<0, true>(nullptr, nullptr, bounds, Bb, B, N, V, out, out_idx, ws, st, ds);
+    case 3: return voxelize_impl<3, true>(nullptr, nullptr, bounds, Bb, B, N, V, out, out_idx, ws, st, ds);
+    default:
+      set_error("voxelize_depth: feature_size %d not compiled (0 or 3)", F);
       return VXB_E_UNSUPPORTED_SHAPE;
   }
 }

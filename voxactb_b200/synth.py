@@ -112,3 +112,40 @@ def random_state_dict(encoder, seed, scale_bias=0.05):
             t = (2.0 / max(fan_in, 1)) ** 0.5 * r
         sd[name] = t.float()
     return sd
+
+
+def make_depth_observation(seed, B, cameras=4, H=128, W=128, bounds=None):
+    """Raw-depth observations: per camera a depth image in metres, RLBench-style intrinsics
+    (negative focal lengths, vision_sensor.py:176-189) and a camera-to-world pose looking at the scene centre, such that the
+    back-projected points fall in and around the scene bounds.  Returns dict(depth [B,cams,H,W] fp32, intrinsics
+    [B,cams,3,3] f64, extrinsics [B,cams,4,4] f64, rgb [B,cams,3,H,W] fp32 in [-1,1], bounds [1,6])."""
+    import math
+    import numpy as np
+    gen = torch.Generator().manual_seed(int(seed))
+    scene = list(SCENE_BOUNDS if bounds is None else bounds)
+    centre = np.array([(scene[i] + scene[i + 3]) / 2 for i in range(3)])
+    depth = torch.empty(B, cameras, H, W)
+    K = np.zeros((B, cameras, 3, 3))
+    E = np.zeros((B, cameras, 4, 4))
+    for b in range(B):
+        for c in range(cameras):
+            ang = float(torch.rand(1, generator=gen)) * 2 * math.pi
+            elev = 0.3 + 0.6 * float(torch.rand(1, generator=gen))
+            dist = 1.2 + 0.4 * float(torch.rand(1, generator=gen))
+            pos = centre + dist * np.array([math.cos(ang) * math.cos(elev), math.sin(ang) * math.cos(elev), math.sin(elev)])
+            fwd = (centre - pos) / np.linalg.norm(centre - pos)          # camera +z looks at the scene
+            right = np.cross(fwd, np.array([0., 0., 1.]))
+            right /= np.linalg.norm(right)
+            up = np.cross(right, fwd)
+            R = np.stack([-right, -up, fwd], 1)                           # negative focal lengths flip x / y
+            E[b, c, :3, :3] = R
+            E[b, c, :3, 3] = pos
+            E[b, c, 3, 3] = 1.0
+            f = -W / (2 * math.tan(math.radians(60.0) / 2))
+            K[b, c] = np.array([[f, 0., W / 2], [0., f * H / W if H != W else f, H / 2], [0., 0., 1.]])
+            base = dist - 0.5 + 1.0 * torch.rand(H, W, generator=gen)     # a slab of depths through the workspace
+            plane = dist + 0.1 * torch.rand(1, generator=gen)              # plus a surface (contention)
+            sel = torch.rand(H, W, generator=gen) < 0.6
+            depth[b, c] = torch.where(sel, plane.expand(H, W) + 0.002 * torch.rand(H, W, generator=gen), base)
+    rgb = torch.randint(0, 256, (B, cameras, 3, H, W), generator=gen).float() / 255.0 * 2.0 - 1.0
+    return dict(depth=depth, intrinsics=K, extrinsics=E, rgb=rgb, bounds=torch.tensor([scene], dtype=torch.float32))

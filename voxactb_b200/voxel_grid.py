@@ -89,3 +89,56 @@ class VoxelGrid(nn.Module):
         if return_indices:
             return out, idx
         return out
+
+    def depth_to_bounding_voxel_grid(self, depth, intrinsics, extrinsics, rgb=None, coord_bounds=None, return_points=False,
+                                     return_indices=False):
+        """Raw-depth entry: depth [B,cams,H,W] (CUDA fp32, metres), intrinsics [B,cams,3,3] and
+        extrinsics [B,cams,4,4] (HOST arrays / CPU tensors, as they sit in every observation, launch_utils.py:84-87), rgb
+        [B,cams,F,H,W] (CUDA fp32, already normalised) -> the same [B,V,V,V,3+F+3+1] grid coords_to_bounding_voxel_grid
+        gives for the reference's host-side back-projection (PyRep vision_sensor.py:155-175) of those images, with the
+        back-projection fused into the scatter kernel.  The per-camera 4x4 inverse stays on the host in float64, as in the
+        reference."""
+        import numpy as np
+        if not depth.is_cuda:
+            raise RuntimeError('voxactb_b200.VoxelGrid runs on CUDA only (no CPU fallback); got %s' % depth.device)
+        depth = _lib.f32(depth)
+        B, cams, H, W = depth.shape
+        Kh = np.asarray(intrinsics.cpu() if torch.is_tensor(intrinsics) else intrinsics, dtype=np.float64).reshape(B, cams, 3, 3)
+        Eh = np.asarray(extrinsics.cpu() if torch.is_tensor(extrinsics) else extrinsics, dtype=np.float64).reshape(B, cams, 4, 4)
+        minv = np.empty((B, cams, 3, 4), dtype=np.float64)
+        for b in range(B):
+            for c in range(cams):
+                # vision_sensor.py:166-172
+                Cc = np.expand_dims(Eh[b, c, :3, 3], 0).T
+                R_inv = Eh[b, c, :3, :3].T
+                ext = np.concatenate((R_inv, -np.matmul(R_inv, Cc)), -1)
+                homo = np.concatenate([np.matmul(Kh[b, c], ext), [np.array([0, 0, 0, 1])]])
+                minv[b, c] = np.linalg.inv(homo)[0:3]
+        minv_d = torch.from_numpy(minv).to(depth.device)
+        F = 0
+        if rgb is not None:
+            rgb = _lib.f32(rgb)
+            F = rgb.shape[2]
+            if rgb.shape != (B, cams, F, H, W):
+                raise ValueError('rgb must be [B,cams,F,H,W]')
+        if F != self._feature_size:
+            raise ValueError('feature size %d != constructor feature_size %d' % (F, self._feature_size))
+        bounds = self._coord_bounds if coord_bounds is None else coord_bounds
+        bounds = _lib.f32(bounds.to(depth.device).reshape(-1, 6))
+        Bb = bounds.shape[0]
+        if Bb not in (1, B):
+            raise ValueError('coord_bounds batch must be 1 or %d, got %d' % (B, Bb))
+        V, N = self._voxel_size, cams * H * W
+        L = _lib.lib()
+        ws_bytes = L.vxb_voxelize_workspace_bytes(B, N, V, F)
+        if self._workspace is None or self._workspace.numel() < ws_bytes or self._workspace.device != depth.device:
+            self._workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=depth.device)
+        out = torch.empty(B, V, V, V, 7 + F, dtype=torch.float32, device=depth.device)
+        pts = torch.empty(B, N, 3, dtype=torch.float32, device=depth.device) if return_points else None
+        idx = torch.empty(B, N, 3, dtype=torch.int32, device=depth.device) if return_indices else None
+        rc = L.vxb_voxelize_depth_f32(_lib.ptr(depth), _lib.ptr(minv_d), _lib.ptr(rgb), _lib.ptr(bounds), Bb, B, cams, H, W, F, V,
+                                      _lib.ptr(out), 0, _lib.ptr(pts), _lib.ptr(idx), _lib.ptr(self._workspace), ws_bytes,
+                                      _lib.stream())
+        _lib.check(rc, 'vxb_voxelize_depth_f32')
+        res = (out,) + ((pts,) if return_points else ()) + ((idx,) if return_indices else ())
+        return res if len(res) > 1 else out
