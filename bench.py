@@ -46,7 +46,7 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=16, help='samples per GPU')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--math', default=os.environ.get('VXB_MATH', 'auto'), choices=['auto', 'fp32', 'bf16x3'])
+    ap.add_argument('--math', default=os.environ.get('VXB_MATH', 'auto'), choices=['auto', 'fp32', 'bf16x3', 'f16f8c'])
     ap.add_argument('--workload', default='single', choices=['single', 'dual', 'crop', 'train'],
                     help='single = BASELINE config 2 geometry at --batch (headline); dual = config 3 (acting + stabilizing '
                          'encoders, low_dim 7 + arm head, on the same observations; value counts agent-passes); '
@@ -195,7 +195,7 @@ def run_ours(args):
             os.close(saved)
     L = _lib.lib()
     _lib.check(L.vxb_check_device(), 'vxb_check_device')
-    math_mode = {'fp32': _lib.MATH_FP32_SIMT, 'bf16x3': _lib.MATH_BF16X3,
+    math_mode = {'fp32': _lib.MATH_FP32_SIMT, 'bf16x3': _lib.MATH_BF16X3, 'f16f8c': _lib.MATH_F16F8C,
                  'auto': PerceiverVoxelLangEncoder.math_mode}[args.math]
     B, V = args.batch, 100
     torch.manual_seed(1234 + rank)
@@ -402,7 +402,8 @@ def run_train(args):
             os.close(saved)
     L = _lib.lib()
     _lib.check(L.vxb_check_device(), 'vxb_check_device')
-    math_mode = {'fp32': _lib.MATH_FP32_SIMT, 'bf16x3': _lib.MATH_BF16X3, 'auto': PerceiverVoxelLangEncoder.math_mode}[args.math]
+    math_mode = {'fp32': _lib.MATH_FP32_SIMT, 'bf16x3': _lib.MATH_BF16X3, 'f16f8c': _lib.MATH_F16F8C,
+                 'auto': PerceiverVoxelLangEncoder.math_mode}[args.math]
     B, V = args.batch, 100
     torch.manual_seed(4321)                                # identical initial weights on every rank (DDP broadcast equivalent)
     enc = PerceiverVoxelLangEncoder(

@@ -100,7 +100,10 @@ typedef struct vxb_qnet_desc {
 } vxb_qnet_desc;
 
 #define VXB_MATH_FP32_SIMT 0  /* fp32 FFMA everywhere (reference arithmetic, slow path for parity) */
-#define VXB_MATH_BF16X3    1  /* tcgen05 split-bf16 (hi*hi + hi*lo + lo*hi), fp32 accumulate in TMEM */
+#define VXB_MATH_BF16X3    1  /* tcgen05 split-16-bit (hi*hi + hi*lo + lo*hi; fp16 planes), fp32 accumulate in TMEM */
+#define VXB_MATH_F16F8C    2  /* as VXB_MATH_BF16X3, but the 3x3x3 final convolution forms x.w as fp16 hi*hi plus ONE E4M3 MMA that
+                               * carries both 2^-11 correction terms (conv_f8c.cuh): 2 MMA units per product instead of 3, same
+                               * accuracy class (the corrections only need ~4 bits).  Training entries treat it as VXB_MATH_BF16X3. */
 
 /* Parameter slots: device pointers to contiguous fp32 tensors with the reference's shapes
  * (perceiver_lang_io.py:137-334; state-dict names in the comments). */

@@ -108,6 +108,26 @@ def test_conv3d(cuda_lib, mode, Di, Ci, Co, k, s):
     assert util.rel_err(y, ref) < TOL[mode]
 
 
+@pytest.mark.parametrize('Di,scale', [(12, 1.0), (20, 1.0), (37, 1.0), (20, 300.0), (20, 1e-3)])
+def test_conv3d_f16_fp8_corrected(cuda_lib, Di, scale):
+    """VXB_MATH_F16F8C: fp16 hi*hi + one E4M3 MMA for both 2^-11 correction terms (conv_f8c.cuh) holds the same tolerance as
+    the three-term split, also for activations far from O(1) (the e4m3 scales are derived from the data on the device)."""
+    g = torch.Generator().manual_seed(Di)
+    x = torch.randn(2, 64, Di, Di, Di, generator=g) * scale
+    x[0, :, 0, 0, 0] *= 7.0                               # a few outliers: the scale follows the maximum
+    w = torch.randn(64, 64, 3, 3, 3, generator=g) / (64 * 27) ** 0.5
+    b = torch.randn(64, generator=g) * scale
+    ref = qnet_oracle.conv3d_block(x, w, b, 1, 'lrelu').permute(0, 2, 3, 4, 1)
+    y = torch.empty(ref.shape, device='cuda')
+    wk = ws(cuda_lib.vxb_conv3d_workspace_bytes(2, Di, 64, 64, 3))
+    xc, wc, bc = x.permute(0, 2, 3, 4, 1).contiguous().cuda(), w.cuda(), b.cuda()
+    before = cuda_lib.vxb_umma_launch_count()
+    _lib.check(cuda_lib.vxb_conv3d_f32(_lib.ptr(xc), _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(y), 2, Di, 64, 64, 3, 1, 0.02,
+                                       _lib.MATH_F16F8C, _lib.ptr(wk), wk.numel(), _lib.stream()), 'conv3d f8c')
+    assert cuda_lib.vxb_umma_launch_count() > before
+    assert util.rel_err(y, ref) < 1e-4
+
+
 @pytest.mark.parametrize('V', [20, 32, 50, 37])
 def test_trans_decoder_stencil(cuda_lib, V):
     """Conv3d(64 -> 1, k3, replicate pad, no activation) = trans_decoder (perceiver_lang_io.py:308-311)."""

@@ -12,7 +12,7 @@ import make_golden
 
 pytestmark = pytest.mark.gpu
 
-MODES = [_lib.MATH_FP32_SIMT, _lib.MATH_BF16X3]
+MODES = [_lib.MATH_FP32_SIMT, _lib.MATH_BF16X3, _lib.MATH_F16F8C]
 
 
 def run_qfunction(c, obs, enc, mode):

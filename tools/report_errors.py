@@ -22,13 +22,13 @@ def run(c, obs, enc, mode, two=False):
     return dict(trans=o[0], rot_grip=o[1], collision=o[2])
 for name in ['qnet_v20', 'qnet_v20_arm_crop', 'qnet_v32_config1']:
     c = make_golden.QNET_CASES[name]; g = util.golden(name)
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         for rep in range(2):
             obs, enc, sd = util.make_case(c)
             o = run(c, obs, enc, mode)
             print(name, 'mode', mode, {k: '%.2e' % util.rel_err(v, g[k]) for k, v in o.items()})
 c = make_golden.QNET2_CASES['qnet2_v20']; g = util.golden('qnet2_v20')
-for mode in (0, 1):
+for mode in (0, 1, 2):
     for rep in range(3):
         obs, enc, sd = util.make_case_two_robots(c)
         o = run(c, obs, enc, mode, True)

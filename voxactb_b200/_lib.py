@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libvoxactb.so')
 
 MATH_FP32_SIMT = 0
 MATH_BF16X3 = 1
+MATH_F16F8C = 2
 
 c_int, c_float, c_size_t, c_void_p, c_ll = (ctypes.c_int, ctypes.c_float, ctypes.c_size_t,
                                             ctypes.c_void_p, ctypes.c_longlong)

@@ -216,7 +216,7 @@ static size_t conv_w_bytes(int Ci, int Co, int k) { return align_up((size_t)Ci *
 
 extern "C" size_t vxb_conv3d_workspace_bytes(int B, int Di, int Ci, int Co, int k) {
   // tap-major fp32 weight + (bf16x3 path) its planes and the padded input planes
-  return 2 * conv_w_bytes(Ci, Co, k) + umma::conv3d_scratch_bytes(B, Di, Ci, 0, k) + 1024;
+  return 2 * conv_w_bytes(Ci, Co, k) + std::max(umma::conv3d_scratch_bytes(B, Di, Ci, 0, k), umma::conv3_f8c_scratch_bytes(B, Di)) + 1024;
 }
 
 extern "C" int vxb_conv3d_f32(const float* x, const float* w, const float* bias, float* y, int B,
@@ -244,6 +244,11 @@ extern "C" int vxb_conv3d_f32(const float* x, const float* w, const float* bias,
     }
     VXB_TRY(umma::patchify_prepare_weights((const float*)ws, k, wc, st));
     return umma::patchify_f32(x, wc, bias, act_slope, y, B, Di, k, s, st);
+  }
+  if (math_mode == VXB_MATH_F16F8C) {
+    // fp16 + E4M3-corrected input-stationary convolution (conv_f8c.cuh); only the final-convolution geometry exists
+    VXB_CHECK_ARG(k == 3 && s == 1 && Co == 64 && Ci == 64 && bias, "conv3d: VXB_MATH_F16F8C needs k=3, s=1, Ci=Co=64 and a bias");
+    return umma::conv3_f8c_f32(x, (const float*)ws, bias, act_slope, y, B, Di, scratch, st);
   }
   if (math_mode == VXB_MATH_BF16X3 && k == 3 && s == 1 && Co == 64 && Ci == 64 && bias) {
     // input-stationary tcgen05 convolution (conv_umma.cuh): padded hi/lo planes + re-laid weights

@@ -62,6 +62,7 @@ struct ConvParams {
   const float* tail_w2; // optional second tap set (2 robots: trans_decoder_left_arm) and its products
   float* ptap2;
   float* ss_partial;    // [B][chunks][6][64], chunks = zchunks * tiles * 16 (one per item x warp x row group)
+  const float* f8s;     // conv_f8c.cuh only: device scalars of the fp8 correction terms ([2] = 2^-s, see umma_ops.cu f8c_*)
 };
 
 struct TailRowInfo {

@@ -48,4 +48,12 @@ __device__ __forceinline__ __nv_bfloat162 pl2_from_floats(float a, float b) { re
 __device__ __forceinline__ float2 pl2_to_float2(__nv_bfloat162 p) { return __bfloat1622float2(p); }
 #endif
 
+// c8 plane of the f16 + fp8-corrected convolution (conv_f8c.cuh): four consecutive channels -> 4 bytes of e4m3(scale * x)
+__device__ __forceinline__ uint32_t pl_e4m3x4(float x0, float x1, float x2, float x3, float scale) {
+  unsigned short a, b;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(a) : "f"(x1 * scale), "f"(x0 * scale));   // first source -> upper byte
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(b) : "f"(x3 * scale), "f"(x2 * scale));
+  return (uint32_t)a | ((uint32_t)b << 16);
+}
+
 }  // namespace vxb

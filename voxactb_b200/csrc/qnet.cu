@@ -68,7 +68,7 @@ static int make_dims(const vxb_qnet_desc* d, Dims& m) {
     set_error("qnet: the 2-robot encoder has no arm-prediction head");
     return VXB_E_UNSUPPORTED_SHAPE;
   }
-  if (d->math_mode != VXB_MATH_FP32_SIMT && d->math_mode != VXB_MATH_BF16X3) {
+  if (d->math_mode != VXB_MATH_FP32_SIMT && d->math_mode != VXB_MATH_BF16X3 && d->math_mode != VXB_MATH_F16F8C) {
     set_error("qnet: unknown math_mode %d", d->math_mode);
     return VXB_E_BADARG;
   }
@@ -85,6 +85,10 @@ struct Prepared {
   float* trans_wt2;  // [27][64] trans_decoder_left_arm (2 robots)
   __nv_bfloat16* final_wc;  // [4][27][{hi,lo}][64][32] weights of the input-stationary conv kernel
   __nv_bfloat16* patch_wc;  // [k^3][{hi,lo}][64][64] weights of the patchify kernel
+  // VXB_MATH_F16F8C (conv_f8c.cuh): static half of the final-conv weights, max |W| per source, folded up-conv |tap| sums
+  __nv_bfloat16* final_w16; // [4][9][3][64][32] fp16 W_hi
+  unsigned int* final_wmax; // [2] float bits
+  float* up1_abs;           // [s^3 * 64][64]
   float* q_cross;    // [L][ch*cdh]  = to_q(LN(latents)), batch independent
   float* lat_norm;   // [L][D] scratch for the above
   float* ff_perm_w;  // [8D][D] scratch: FF net.0 weight with the GEGLU [a | gate] 32-row interleave (split into planes)
@@ -111,6 +115,9 @@ static void carve_prepared(const Dims& m, Arena& a, Prepared& p, const void* con
   p.trans_wt2 = a.get<float>((size_t)27 * 64);
   p.final_wc = a.get<__nv_bfloat16>(umma::conv3_weight_elems(128));
   p.patch_wc = a.get<__nv_bfloat16>(umma::patchify_weight_elems(m.k));
+  p.final_w16 = a.get<__nv_bfloat16>(umma::conv3_f8c_w16_elems(128));
+  p.final_wmax = a.get<unsigned int>(2);
+  p.up1_abs = a.get<float>((size_t)m.s * m.s * m.s * 64 * 64);
   p.q_cross = a.get<float>((size_t)m.L * m.ch * m.cdh);
   p.lat_norm = a.get<float>((size_t)m.L * m.D);
   p.ff_perm_w = a.get<float>((size_t)8 * m.D * m.D);
@@ -180,6 +187,11 @@ struct Work {
   __nv_bfloat16 *d0p[2], *u0p[2];   // hi/lo planes of the replicate-padded d0 / u0 grids [B,(V+2)^3,64]
   float *rowmax, *rowsum;
   float *tail_part;                 // ss_final partials written by the fused conv tail
+  // VXB_MATH_F16F8C: c8 plane of d0 (u0's replaces its lo plane), per-call fp8 weights, scale scalars, abs-max scratch
+  __nv_bfloat16 *d0c8;
+  uint8_t *final_w8;
+  float *f8s;
+  unsigned int *f8max;
 };
 
 static size_t sim_floats(const Dims& m, int B) {
@@ -251,6 +263,10 @@ static void carve_work(const Dims& m, int B, Arena& a, Work& w) {
     const size_t n_pad = Bz * (m.V + 2) * (m.V + 2) * (m.V + 2) * 64;
     for (int i = 0; i < 2; ++i) { w.d0p[i] = a.get<__nv_bfloat16>(n_pad); w.u0p[i] = a.get<__nv_bfloat16>(n_pad); }
     w.tail_part = a.get<float>(umma::conv3_tail_partial_floats(B, m.V));
+    w.d0c8 = a.get<__nv_bfloat16>(n_pad);
+    w.final_w8 = a.get<uint8_t>(umma::conv3_f8c_w8_bytes(128));
+    w.f8s = a.get<float>(16);
+    w.f8max = a.get<unsigned int>(256 + 16);
   }
 }
 
@@ -595,6 +611,8 @@ extern "C" int vxb_qnet_prepare(const vxb_qnet_desc* d, const void* const* param
     fold_upconv_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(P(VXB_P_UP1_W), p.up1_fold, 64, 64, m.k, m.s);
     VXB_LAUNCH_CHECK();
   }
+  VXB_TRY(umma::conv3_f8c_prepare(p.final_wt, 128, 64, p.final_w16, p.final_wmax, st));
+  VXB_TRY(umma::conv3_f8c_fold_abs(p.up1_fold, (long long)m.s * m.s * m.s * 64, 64, p.up1_abs, st));
   // q of the encoder cross-attention depends only on parameters: to_q(LN(latents))
   VXB_TRY(layernorm(P(VXB_P_LATENTS), P(VXB_P_CROSS_NORM_W), P(VXB_P_CROSS_NORM_B), p.lat_norm, m.L, m.D, st));
   VXB_TRY(linear(p.lat_norm, m.D, P(VXB_P_CROSS_Q_W), m.D, nullptr, nullptr, 1, 0, p.q_cross,
@@ -625,27 +643,35 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
                              const float* proprio2, const float* lang_tokens, int B, float* q_trans, float* q_trans2,
                              float* rot_grip, float* collision, float* rot_grip2, float* collision2, float* arm_out,
                              cudaStream_t st) {
-  Ctx cx(d->math_mode, st, d->math_mode == VXB_MATH_BF16X3 ? w.scratch : nullptr, w.scratch_bytes);
+  // VXB_MATH_F16F8C = VXB_MATH_BF16X3 everywhere except the final 3x3x3 convolution (conv_f8c.cuh)
+  const bool f8c = d->math_mode == VXB_MATH_F16F8C;
+  const int mm = f8c ? VXB_MATH_BF16X3 : d->math_mode;
+  Ctx cx(mm, st, mm == VXB_MATH_BF16X3 ? w.scratch : nullptr, w.scratch_bytes);
   cx.wp = pw.planes;
   auto P = [&](int slot) { return (const float*)params[slot]; };
   auto PL = [&](int layer, int slot) {
     return (const float*)params[VXB_P_FIXED_COUNT + layer * VXB_P_LAYER_STRIDE + slot];
   };
-  const int mm = d->math_mode;
   const float slope = d->act_slope;
   const size_t MV = (size_t)B * m.V3;
 
   STAGE_MARK();  // 0: input_preprocess
   // (1) d0 = act(conv1x1(grid)), fused with (2) feats[0:256] = [ss0(d0), maxpool(d0)]   perceiver_lang_io.py:357-360
   g_launches += 2;
-  const bool fused_planes = d->math_mode == VXB_MATH_BF16X3;   // producers write the final conv's operand planes directly
+  const bool fused_planes = mm == VXB_MATH_BF16X3;   // producers write the final conv's operand planes directly
+  if (f8c) {
+    // e4m3 scale of d0 from a bound of |d0|: per-channel maxima of the voxel grid x |weights| of the 1x1 convolution
+    g_launches += 2;
+    VXB_TRY(umma::conv3_f8c_bound_ipp(grid, (long long)MV, 10, P(VXB_P_INPRE_W), P(VXB_P_INPRE_B), 64, w.f8max, w.f8s, st));
+  }
   // (split-bf16 path: d0 only ever exists as the hi/lo planes that the patchify and final convolutions consume)
   VXB_TRY(input_preprocess_ss_run<10>(grid, P(VXB_P_INPRE_W), P(VXB_P_INPRE_B), slope, fused_planes ? nullptr : w.d0, B, m.V, m.V, m.V, 64,
                                       w.feats, m.flat, w.feats + 192, m.flat, w.ss_part, st,
-                                      fused_planes ? w.d0p[0] : nullptr, fused_planes ? w.d0p[1] : nullptr));
+                                      fused_planes ? w.d0p[0] : nullptr, fused_planes ? w.d0p[1] : nullptr, nullptr,
+                                      f8c ? reinterpret_cast<uint8_t*>(w.d0c8) : nullptr, f8c ? w.f8s : nullptr));
   if (fused_planes) {
     ++g_launches;
-    VXB_TRY(umma::halo_fill(umma::Planes{w.d0p[0], w.d0p[1], 64}, B, m.V, 1, 64, st));
+    VXB_TRY(umma::halo_fill(umma::Planes{w.d0p[0], w.d0p[1], 64}, B, m.V, 1, 64, st, f8c ? w.d0c8 : nullptr));
   }
   STAGE_MARK();  // 1: (fused into stage 0)
   STAGE_MARK();  // 2: patchify
@@ -760,10 +786,18 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   STAGE_MARK();  // 7: folded upsample-conv
   COUNT_LAUNCH();
   {
-    const umma::Planes u0p{w.u0p[0], w.u0p[1], 64};
+    const umma::Planes u0p{w.u0p[0], w.u0p[1], 64};      // f8c: the second plane holds c8 instead of the fp16 lo values
     if (fused_planes) ++g_launches;
+    if (f8c) {
+      // bound of |u0| (low-res channel maxima x folded |weights|), then the joint scales and the per-call fp8 weights
+      g_launches += 3;
+      VXB_TRY(umma::conv3_f8c_bound_up(w.low, (long long)B * m.T, 64, pw.up1_abs, (long long)m.s * m.s * m.s * 64, P(VXB_P_UP1_B),
+                                       pw.final_wmax, w.f8max + 16, w.f8s, st));
+      VXB_TRY(umma::conv3_f8c_quantize_weights(pw.final_wt, 128, 64, w.f8s, w.final_w8, st));
+    }
     VXB_TRY(upconv3d_folded(w.low, pw.up1_fold, P(VXB_P_UP1_B), w.u0, B, m.S, 64, 64, m.s, slope, mm, st,
-                            cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.up1_fold), fused_planes ? &u0p : nullptr));
+                            cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.up1_fold), fused_planes ? &u0p : nullptr,
+                            f8c ? w.f8s + 1 : nullptr));
   }
   STAGE_MARK();  // 8: final conv
   // (11) final: conv3 on cat[d0, u0] (128 -> 64)                               :462
@@ -785,7 +819,13 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
     }
     tail.ss = w.feats + off; tail.ss_stride = m.flat; tail.mx = w.feats + off + 192; tail.mx_stride = m.flat;
     g_launches += 4 + (d->two_robots ? 1 : 0);   // conv + gather(s) + two-level partial merge
-    VXB_TRY(umma::conv3_planes(d0p, &u0p, 64, 64, pw.final_wc, P(VXB_P_FINAL_B), slope, nullptr, B, m.V, st, &tail));
+    if (f8c) {
+      const umma::Planes d0c{w.d0p[0], w.d0c8, 64};
+      VXB_TRY(umma::conv3_f8c_planes(d0c, &u0p, 64, 64, pw.final_w16, w.final_w8, w.f8s, P(VXB_P_FINAL_B), slope, nullptr, B, m.V,
+                                     st, &tail));
+    } else {
+      VXB_TRY(umma::conv3_planes(d0p, &u0p, 64, 64, pw.final_wc, P(VXB_P_FINAL_B), slope, nullptr, B, m.V, st, &tail));
+    }
     STAGE_MARK();  // 9: trans decoder gather + ss_final merge (their first halves ran in the conv epilogue)
     VXB_TRY(umma::conv3_tail_finish(tail, B, m.V, st));
     STAGE_MARK();  // 10: heads
@@ -907,6 +947,12 @@ extern "C" int vxb_profile_read(double* ms) {
 }
 
 // ---- training step: forward that keeps the activations + backward
+// the training step has no f16 + fp8 convolution: VXB_MATH_F16F8C trains as VXB_MATH_BF16X3
+static vxb_qnet_desc train_desc(const vxb_qnet_desc* d) {
+  vxb_qnet_desc t = *d;
+  if (t.math_mode == VXB_MATH_F16F8C) t.math_mode = VXB_MATH_BF16X3;
+  return t;
+}
 static int train_setup(const vxb_qnet_desc* d, const vxb_train_opts* o, Dims& m, TrainDropout& drop) {
   VXB_TRY(make_dims(d, m));
   VXB_TRY(train_supported(d, m));
@@ -932,6 +978,9 @@ extern "C" int vxb_qnet_forward_train_f32(const vxb_qnet_desc* d, const void* co
                                           const float* grid, const float* proprio, const float* lang_tokens, int B,
                                           float* q_trans, float* rot_grip, float* collision, float* arm_out,
                                           const vxb_train_opts* opts, void* ws, size_t ws_bytes, void* stream) {
+  VXB_CHECK_ARG(d && d->struct_bytes == (int)sizeof(vxb_qnet_desc), "qnet_forward_train: bad descriptor");
+  const vxb_qnet_desc td = train_desc(d);
+  d = &td;
   Dims m;
   TrainDropout drop;
   VXB_TRY(train_setup(d, opts, m, drop));
@@ -960,6 +1009,9 @@ extern "C" int vxb_qnet_backward_f32(const vxb_qnet_desc* d, const void* const* 
                                      const float* g_trans, const float* g_rot_grip, const float* g_collision, const float* g_arm,
                                      float* const* grads, const vxb_train_opts* opts, float* const* debug, void* ws,
                                      size_t ws_bytes, void* stream) {
+  VXB_CHECK_ARG(d && d->struct_bytes == (int)sizeof(vxb_qnet_desc), "qnet_backward: bad descriptor");
+  const vxb_qnet_desc td = train_desc(d);
+  d = &td;
   Dims m;
   TrainDropout drop;
   VXB_TRY(train_setup(d, opts, m, drop));

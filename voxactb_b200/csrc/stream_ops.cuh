@@ -221,7 +221,8 @@ static __global__ void __launch_bounds__(SS_THREADS)
 input_preprocess_ss_kernel(const float* __restrict__ x /*[B,P,CIN]*/, const float* __restrict__ w /*[C,CIN]*/,
                            const float* __restrict__ bias, float slope, float* __restrict__ y /*[B,P,C]*/,
                            int P, int C, int Dd, int Hh, int Ww, int chunk, float* __restrict__ partial,
-                           __nv_bfloat16* __restrict__ phi, __nv_bfloat16* __restrict__ plo /*padded planes or null*/) {
+                           __nv_bfloat16* __restrict__ phi, __nv_bfloat16* __restrict__ plo /*padded planes or null*/,
+                           uint8_t* __restrict__ pc8 /*c8 plane of conv_f8c.cuh or null*/, const float* __restrict__ f8a) {
   extern __shared__ float ss_smem[];
   const int b = blockIdx.y, ck = blockIdx.x, chunks = gridDim.x;
   const int G = C >> 2;
@@ -271,6 +272,9 @@ input_preprocess_ss_kernel(const float* __restrict__ x /*[B,P,CIN]*/, const floa
   const size_t pbase = (size_t)b * (Dd + 2) * (Hh + 2) * (Ww + 2) * C + g * 4;   // this sample, this channel group
   __nv_bfloat16* phb = phi ? phi + pbase : nullptr;
   __nv_bfloat16* plb = plo ? plo + pbase : nullptr;
+  // c8 plane: the row's 128 bytes are two 32-channel blocks of [32 x e4m3(2^11 a lo) | 32 x e4m3(a x)]; this thread's 4 channels
+  uint8_t* pcb = pc8 ? pc8 + ((size_t)b * (Dd + 2) * (Hh + 2) * (Ww + 2) * C) * 2 + (g >> 3) * 64 + (g & 7) * 4 : nullptr;
+  const float fa = pc8 ? __ldg(f8a) : 0.f;
   // element offset of this position's padded row inside the sample (< 2^31 for any grid that fits the planes)
   uint32_t poff = ((uint32_t)((d + 1) * (Hh + 2) + h + 1) * (uint32_t)(Ww + 2) + (uint32_t)wv + 1u) * (uint32_t)C;
   const uint32_t step_w = (uint32_t)PL * C, wrap_w = 2u * C, wrap_h = 2u * (uint32_t)(Ww + 2) * C;
@@ -316,6 +320,11 @@ input_preprocess_ss_kernel(const float* __restrict__ x /*[B,P,CIN]*/, const floa
           lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
           *reinterpret_cast<uint2*>(phb + poff) = hv;
           *reinterpret_cast<uint2*>(plb + poff) = lv;
+          if (pcb) {
+            uint8_t* rowb = pcb + (size_t)poff * 2;        // poff counts 2-byte elements of a C-channel row
+            *reinterpret_cast<uint32_t*>(rowb) = pl_e4m3x4(o[0] - f01.x, o[1] - f01.y, o[2] - f23.x, o[3] - f23.y, fa * 2048.f);
+            *reinterpret_cast<uint32_t*>(rowb + 32) = pl_e4m3x4(o[0], o[1], o[2], o[3], fa);
+          }
         }
         ss_update4_lazy(st, o, lutH[h], lutD[d], lutW[wv]);
         p += PL; wv += PL; poff += step_w;
@@ -378,9 +387,11 @@ template <int CIN>
 inline int input_preprocess_ss_run(const float* x, const float* w, const float* bias, float slope, float* y, int B,
                                    int Dd, int Hh, int Ww, int C, float* ss, int ss_stride, float* mx, int mx_stride,
                                    float* partial, cudaStream_t st, __nv_bfloat16* phi = nullptr,
-                                   __nv_bfloat16* plo = nullptr, float* stats = nullptr) {
+                                   __nv_bfloat16* plo = nullptr, float* stats = nullptr, uint8_t* pc8 = nullptr,
+                                   const float* f8a = nullptr) {
   VXB_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 1024, "input_preprocess: C=%d must be a multiple of 4, <= 1024", C);
   VXB_CHECK_ARG(slope <= 1.f, "input_preprocess: LeakyReLU slope %g must be <= 1 (negative = no activation)", (double)slope);
+  VXB_CHECK_ARG(!pc8 || (C == 64 && phi && plo && f8a), "input_preprocess: the c8 plane needs C = 64 and the hi/lo planes");
   const size_t P = (size_t)Dd * Hh * Ww;
   const int chunks = ss_num_chunks(P, B);
   const int chunk = (int)((P + chunks - 1) / chunks);
@@ -388,7 +399,7 @@ inline int input_preprocess_ss_run(const float* x, const float* w, const float* 
   const size_t smem = ((size_t)ipp_stage_offset_floats(Dd + Hh + Ww, PL * G) + (size_t)IPP_STAGES * IPP_ITERS * PL * CIN) * sizeof(float);
   VXB_CHECK_ARG(smem <= 48 * 1024, "input_preprocess: %zu bytes of shared memory needed (C=%d, grid %dx%dx%d)", smem, C, Dd, Hh, Ww);
   input_preprocess_ss_kernel<CIN><<<dim3(chunks, B), SS_THREADS, smem, st>>>(x, w, bias, slope, y, (int)P, C, Dd, Hh, Ww,
-                                                                            chunk, partial, phi, plo);
+                                                                            chunk, partial, phi, plo, pc8, f8a);
   VXB_LAUNCH_CHECK();
   ss_merge_kernel<<<dim3(cdiv(C, 32), B), 256, 0, st>>>(partial, chunks, C, ss, ss_stride, mx, mx_stride, nullptr, stats);
   VXB_LAUNCH_CHECK();

@@ -760,6 +760,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
               const float2 f01 = pl2_to_float2(h01), f23 = pl2_to_float2(h23);
               const __nv_bfloat162 l01 = pl2_from_floats(x[0] - f01.x, x[1] - f01.y);
               const __nv_bfloat162 l23 = pl2_from_floats(x[2] - f23.x, x[3] - f23.y);
+              if (e.f8a) {
+                // c8 plane (conv_f8c.cuh): bytes [32 x lo8 | 32 x hi8] per 32-channel block of the 64-channel row
+                const float fa = __ldg(e.f8a);
+                uint8_t* rowb = reinterpret_cast<uint8_t*>(out_lo + orow_r[i] * e.ldp) + (ncol >> 5) * 64 + (ncol & 31);
+                uint2 hv;
+                hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(dh) = hv;
+                *reinterpret_cast<uint32_t*>(rowb) = pl_e4m3x4(x[0] - f01.x, x[1] - f01.y, x[2] - f23.x, x[3] - f23.y, fa * 2048.f);
+                *reinterpret_cast<uint32_t*>(rowb + 32) = pl_e4m3x4(x[0], x[1], x[2], x[3], fa);
+              } else
               // EXP mode: values beyond N are exact zeros and the row is padded to ld (a multiple of 8)
               if ((nv >= 4 || e.mode == EPI_EXP) && ((reinterpret_cast<uintptr_t>(dh) & 7) == 0)) {
                 uint2 hv, lv;

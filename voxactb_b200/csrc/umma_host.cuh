@@ -51,6 +51,8 @@ struct Epilogue {
   __nv_bfloat16* out_hi;      // bf16 plane outputs or null
   __nv_bfloat16* out_lo;
   long long ldp;
+  const float* f8a;           // non-null (generic epilogue, ldp = 64 only): out_lo receives the c8 plane of conv_f8c.cuh instead
+                              // of the fp16 lo plane -- per 32-channel block 32 B of e4m3(2^11 a x_lo) then 32 B of e4m3(a x), a = *f8a
   int transpose_planes;       // planes written transposed: element (row, col) -> out[(col) * ldp + row] (V^T for attention)
   int mode;                   // EPI_*
   float* row_stat;            // EPI_ROWMAX / EPI_EXP: per-row statistic, indexed rs offset(z) + row
@@ -92,7 +94,7 @@ inline long long pad8(long long v) { return (v + 7) / 8 * 8; }
 
 int split_rows(const float* x, long long ldx, long long rows, int cols, Planes out, cudaStream_t st);
 int pad_split(const float* x, int B, int V, int pad, int C, Planes out, cudaStream_t st);
-int halo_fill(Planes p, int B, int V, int pad, int C, cudaStream_t st);
+int halo_fill(Planes p, int B, int V, int pad, int C, cudaStream_t st, __nv_bfloat16* third = nullptr);   // lo / third may be null
 // D = A W^T on tcgen05; A1 is the optional second A source (fused channel concat in convolutions)
 int gemm(const Operand& A0, const Operand* A1, const Operand& W, int n_tile, Params p, cudaStream_t st);
 long long launches();   // tcgen05 GEMM launches so far in this process
@@ -107,7 +109,7 @@ int conv3d_f32(const float* x0, const float* x1, int C0, int C1, const Planes& W
                int B, int V, int Co, int k, float act_slope, Arena& scratch, cudaStream_t st);
 size_t upconv_scratch_bytes(int B, int S, int Ci);
 int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out, int B, int S, int Ci, int Co, int s,
-               float act_slope, Arena& scratch, cudaStream_t st, const Planes* out_planes = nullptr);
+               float act_slope, Arena& scratch, cudaStream_t st, const Planes* out_planes = nullptr, const float* f8a = nullptr);
 
 // ---- backward (training) contractions on the tensor cores ------------------------------------------------------------
 // Gradient tensors span many decades (softmax-over-10^6 logit gradients are ~1e-8), below the fp16 planes' range, so every
@@ -189,6 +191,23 @@ size_t conv3_tail_partial_floats(int B, int V);
 int conv3_tail_finish(const ConvTail& tail, int B, int V, cudaStream_t st);   // gather + merge after conv3_planes(tail)
 int conv3_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_bfloat16* wc, const float* bias,
                  float act_slope, float* out, int B, int V, cudaStream_t st, const ConvTail* tail = nullptr);
+
+// ---- f16 + fp8-corrected variant of the input-stationary convolution (conv_f8c.cuh; scalars and layouts in umma_ops.cu f8c_*)
+size_t conv3_f8c_w16_elems(int Cin);
+size_t conv3_f8c_w8_bytes(int Cin);
+int conv3_f8c_prepare(const float* w_tapmajor, int Cin, int C0, __nv_bfloat16* w16, unsigned int* wmax, cudaStream_t st);
+int conv3_f8c_fold_abs(const float* wfold, long long rows, int Ci, float* S, cudaStream_t st);
+int conv3_f8c_bound_ipp(const float* grid, long long rows, int CIN, const float* w, const float* bias, int C, unsigned int* gmax,
+                        float* f8s, cudaStream_t st);
+int conv3_f8c_bound_up(const float* low, long long rows, int Ci, const float* S, long long srows, const float* bias,
+                       const unsigned int* wmax, unsigned int* lmax, float* f8s, cudaStream_t st);
+int conv3_f8c_quantize_weights(const float* w_tapmajor, int Cin, int C0, const float* f8s, uint8_t* w8, cudaStream_t st);
+int conv3_f8c_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_bfloat16* w16, const uint8_t* w8, const float* f8s,
+                     const float* bias, float act_slope, float* out, int B, int V, cudaStream_t st, const ConvTail* tail = nullptr);
+size_t conv3_f8c_scratch_bytes(int B, int V);
+int conv3_f8c_f32(const float* x, const float* w_tapmajor, const float* bias, float act_slope, float* out, int B, int V,
+                  Arena& scratch, cudaStream_t st);
+int absmax_cols(const float* x, long long rows, int C, unsigned int* out, cudaStream_t st);
 
 // ---- patchify (patchify_umma.cuh): Conv3d(64 -> 64, k, stride s, replicate pad k/2) + act on fp32 channels-last x
 // weights: tap-major fp32 [64][k^3][64] -> bf16 [k^3][{hi,lo}][64][64]

@@ -2,6 +2,7 @@
 // and the launch wrappers used by dispatch.cuh.
 #include "umma_gemm.cuh"
 #include "conv_umma.cuh"
+#include "conv_f8c.cuh"
 #include "patchify_umma.cuh"
 #include "flash_umma.cuh"
 #include <cstdlib>
@@ -126,7 +127,7 @@ pad_split_kernel(const float* __restrict__ x, int B, int V, int pad, int C,
 // replicate-fill the halo of padded bf16 planes in place: every halo voxel copies its nearest interior voxel.
 // Only the halo voxels are enumerated (two full z planes + the border ring of every other plane), pad = 1 fast path.
 static __global__ void __launch_bounds__(256)
-halo_fill_kernel(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int B, int V, int pad, int C) {
+halo_fill_kernel(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, __nv_bfloat16* __restrict__ third, int B, int V, int pad, int C) {
   const int Vp = V + 2 * pad;
   const int cg = C / 8;
   if (pad == 1) {
@@ -155,7 +156,8 @@ halo_fill_kernel(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
       const long long so = ((((long long)b * Vp + sd) * Vp + sh) * Vp + sw) * C + c;
       const long long o = ((((long long)b * Vp + pd) * Vp + ph) * Vp + pw) * C + c;
       *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(hi + so);
-      *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(lo + so);
+      if (lo) *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(lo + so);
+      if (third) *reinterpret_cast<uint4*>(third + o) = *reinterpret_cast<const uint4*>(third + so);
     }
     return;
   }
@@ -172,7 +174,8 @@ halo_fill_kernel(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
     const long long so = ((((long long)b * Vp + sd) * Vp + sh) * Vp + sw) * C + c;
     const long long o = (i / cg) * C + c;
     *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(hi + so);
-    *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(lo + so);
+    if (lo) *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(lo + so);
+    if (third) *reinterpret_cast<uint4*>(third + o) = *reinterpret_cast<const uint4*>(third + so);
   }
 }
 
@@ -201,12 +204,12 @@ int pad_split(const float* x, int B, int V, int pad, int C, Planes out, cudaStre
   return VXB_OK;
 }
 
-int halo_fill(Planes p, int B, int V, int pad, int C, cudaStream_t st) {
+int halo_fill(Planes p, int B, int V, int pad, int C, cudaStream_t st, __nv_bfloat16* third) {
   const int Vp = V + 2 * pad;
   long long total = (long long)B * Vp * Vp * Vp * (C / 8);
   if (pad == 1) total = (long long)B * (2ll * Vp * Vp + (long long)(Vp - 2) * (4ll * Vp - 4)) * (C / 8);
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-  halo_fill_kernel<<<blocks, 256, 0, st>>>(p.hi, p.lo, B, V, pad, C);
+  halo_fill_kernel<<<blocks, 256, 0, st>>>(p.hi, p.lo, third, B, V, pad, C);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }
@@ -535,7 +538,7 @@ size_t upconv_scratch_bytes(int B, int S, int Ci) {
 // folded upsample-conv: low [B,S^3,Ci] fp32 -> out [B,(S*s)^3,64] fp32 and/or out_planes = hi/lo planes of the
 // replicate-padded fine grid [B,(S*s+2)^3,64] (interior written here, halo by halo_fill); Wp planes of [s^3*64][27*Ci]
 int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out, int B, int S, int Ci, int Co, int s,
-               float act_slope, Arena& scratch, cudaStream_t st, const Planes* out_planes) {
+               float act_slope, Arena& scratch, cudaStream_t st, const Planes* out_planes, const float* f8a) {
   if (Ci % 64 || Co != 64) {
     set_error("umma upconv: needs Ci %% 64 == 0 and Co == 64");
     return VXB_E_UNSUPPORTED_SHAPE;
@@ -568,6 +571,7 @@ int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out
     // fine voxel (d,h,w) -> row of the padded grid: the epilogue adds out_pad to every coordinate
     p.ep.out_Vp = S * s + 2; p.ep.out_pad = 1;
     p.ep.out_hi = out_planes->hi; p.ep.out_lo = out_planes->lo; p.ep.ldp = 64;
+    p.ep.f8a = f8a;                       // non-null: out_planes->lo is the c8 plane of conv_f8c.cuh
   } else {
     p.ep.out_Vp = S * s; p.ep.out_pad = 0;
     p.ep.out_f32 = out; p.ep.ldc = 64;
@@ -1390,6 +1394,361 @@ int conv3_tail_finish(const ConvTail& tail, int B, int V, cudaStream_t st) {
   ss_merge_kernel<<<dim3(cdiv(64, 32), B), 256, 0, st>>>(level1, kTailMergeSplits, 64, tail.ss, tail.ss_stride, tail.mx, tail.mx_stride, nullptr, nullptr);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ f16 + fp8-corrected conv (conv_f8c.cuh)
+// Device scalars f8s[F8S_COUNT] of one convolution call (all powers of two except the bounds):
+//   [0] alpha of source 0, [1] alpha of source 1 (activation -> e4m3 scale of the A_hi8 half; the A_lo8 half uses 2^11 alpha)
+//   [2] 2^-s (scale of the fp8 accumulator), [3] beta of source 0, [4] beta of source 1 (W_lo -> e4m3; W_hi8 uses 2^-11 beta)
+//   [5], [6] the activation bounds the alphas were derived from (diagnostics)
+size_t conv3_f8c_w16_elems(int Cin) { return (size_t)(Cin / CV_KC) * 9 * F8_WROWS * CV_KC; }
+size_t conv3_f8c_w8_bytes(int Cin) { return (size_t)(Cin / CV_KC) * 9 * F8_WROWS * 64; }
+
+// static half of the weights: fp16 W_hi, rows [cb][tap9][j = 0,1,2 <-> dz = +1,0,-1 <-> tap index dzc = 2,1,0][co], 32 channels each
+static __global__ void f8c_w16_kernel(const float* __restrict__ w /*[64][27][Cin]*/, int Cin, __nv_bfloat16* __restrict__ w16) {
+  const long long total = (long long)(Cin / CV_KC) * 9 * F8_WROWS * CV_KC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kc = (int)(i % CV_KC);
+    const int co = (int)((i / CV_KC) % 64);
+    const int j = (int)((i / (CV_KC * 64)) % 3);
+    const int tap9 = (int)((i / (CV_KC * F8_WROWS)) % 9);
+    const int cb = (int)(i / ((long long)CV_KC * F8_WROWS * 9));
+    const int tap = (2 - j) * 9 + tap9;
+    w16[i] = pl_from_float(w[((long long)co * 27 + tap) * Cin + cb * CV_KC + kc]);
+  }
+}
+// max |w| per source (channels [0, C0) and [C0, Cin)) as float bits; out[2] zeroed by the caller
+static __global__ void f8c_wmax_kernel(const float* __restrict__ w, long long rows, int Cin, int C0, unsigned int* __restrict__ out) {
+  float m0 = 0.f, m1 = 0.f;
+  const long long total = rows * Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float a = fabsf(w[i]);
+    if ((int)(i % Cin) < C0) m0 = fmaxf(m0, a); else m1 = fmaxf(m1, a);
+  }
+  m0 = warp_max(m0); m1 = warp_max(m1);
+  if ((threadIdx.x & 31) == 0) { atomicMax(out, __float_as_uint(m0)); atomicMax(out + 1, __float_as_uint(m1)); }
+}
+__device__ __forceinline__ uint8_t f8c_e4m3(float x) {
+  unsigned short a;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(a) : "f"(0.f), "f"(x));
+  return (uint8_t)(a & 0xff);
+}
+// per-call half of the weights: rows as above, 64 bytes each = [32 x e4m3(2^-11 beta W) | 32 x e4m3(beta W_lo)]
+static __global__ void f8c_w8_kernel(const float* __restrict__ w, int Cin, int cb_src0, const float* __restrict__ f8s,
+                                     uint8_t* __restrict__ w8) {
+  const long long total = (long long)(Cin / CV_KC) * 9 * F8_WROWS * CV_KC;
+  const float beta0 = f8s[3], beta1 = f8s[4];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kc = (int)(i % CV_KC);
+    const long long row = i / CV_KC;
+    const int co = (int)(row % 64);
+    const int j = (int)((row / 64) % 3);
+    const int tap9 = (int)((row / F8_WROWS) % 9);
+    const int cb = (int)(row / (F8_WROWS * 9));
+    const int tap = (2 - j) * 9 + tap9;
+    const float f = w[((long long)co * 27 + tap) * Cin + cb * CV_KC + kc];
+    const float lo = f - pl_to_float(pl_from_float(f));
+    const float beta = cb >= cb_src0 ? beta1 : beta0;
+    w8[row * 64 + kc] = f8c_e4m3(f * (beta * (1.f / 2048.f)));
+    w8[row * 64 + 32 + kc] = f8c_e4m3(lo * beta);
+  }
+}
+
+// per-column max |x| of a row-major [rows, C] fp32 matrix as float bits (out[C] zeroed by the caller): every thread keeps to
+// one column phase (the grid stride is a multiple of C), 128-bit loads when the layout allows
+static __global__ void __launch_bounds__(256)
+absmax_cols_kernel(const float* __restrict__ x, long long total, int C, unsigned int* __restrict__ out, int vec4) {
+  extern __shared__ unsigned int am_s[];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) am_s[i] = 0u;
+  __syncthreads();
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const long long stride = (nthreads + C - 1) / C * C;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec4) {
+    float m[4] = {0.f, 0.f, 0.f, 0.f};
+    const long long n4 = total >> 2;
+    for (long long i = t0; i < n4; i += stride) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+      m[0] = fmaxf(m[0], fabsf(v.x)); m[1] = fmaxf(m[1], fabsf(v.y));
+      m[2] = fmaxf(m[2], fabsf(v.z)); m[3] = fmaxf(m[3], fabsf(v.w));
+    }
+    const int c0 = (int)((4 * t0) % C);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) atomicMax(&am_s[(c0 + k) % C], __float_as_uint(m[k]));
+  } else {
+    float m = 0.f;
+    for (long long i = t0; i < total; i += stride) m = fmaxf(m, fabsf(__ldg(x + i)));
+    atomicMax(&am_s[(int)(t0 % C)], __float_as_uint(m));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) if (am_s[i]) atomicMax(out + i, am_s[i]);
+}
+int absmax_cols(const float* x, long long rows, int C, unsigned int* out, cudaStream_t st) {
+  if (C <= 0 || C > 4096) { set_error("absmax_cols: C=%d", C); return VXB_E_BADARG; }
+  const long long total = rows * C;
+  const int vec4 = (total % 4 == 0) && (((uintptr_t)x & 15) == 0);
+  const int blocks = (int)std::min<long long>((total / (vec4 ? 4 : 1) + 255) / 256 + 1, 148 * 8);
+  absmax_cols_kernel<<<blocks, 256, C * sizeof(unsigned int), st>>>(x, total, C, out, vec4);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+__device__ __forceinline__ int f8c_floor_log2(float x) {      // floor(log2 x) clamped to a range that keeps every product finite
+  if (!(x > 0.f) || !isfinite(x)) return 0;
+  return max(-60, min(60, ilogbf(x)));
+}
+// alpha of one source from a bound of |x|: the largest power of two with alpha * bound <= 240 (e4m3 saturates at 448)
+__device__ __forceinline__ float f8c_alpha(float bound) { return bound > 0.f ? scalbnf(1.f, f8c_floor_log2(240.f / bound)) : 1.f; }
+
+// bound of |act(W g + b)| for the 1x1 input_preprocess convolution from the per-channel maxima of the voxel grid
+static __global__ void f8c_bound_ipp_kernel(const unsigned int* __restrict__ gmax /*[CIN]*/, const float* __restrict__ w /*[C][CIN]*/,
+                                            const float* __restrict__ bias, int CIN, int C, float* __restrict__ f8s) {
+  __shared__ unsigned int mx;
+  if (threadIdx.x == 0) mx = 0u;
+  __syncthreads();
+  for (int o = threadIdx.x; o < C; o += blockDim.x) {
+    float bnd = fabsf(bias[o]);
+    for (int c = 0; c < CIN; ++c) bnd = fmaf(fabsf(w[o * CIN + c]), __uint_as_float(gmax[c]), bnd);
+    atomicMax(&mx, __float_as_uint(bnd * 1.0001f));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float bnd = __uint_as_float(mx);
+    f8s[5] = bnd;
+    f8s[0] = f8c_alpha(bnd);
+  }
+}
+// bound of the folded up-convolution output from the per-channel maxima of its low-resolution input and the per-(phase, co, ci)
+// absolute tap sums of the folded weights; then the joint scales of the two sources of the final convolution:
+//   beta_max(src) = largest power of two with beta * 2^-11 max|W_src| <= 240;  s = min_src log2(alpha_src beta_max(src));
+//   beta_src = 2^s / alpha_src (<= beta_max: nothing saturates);  f8s[2] = 2^-s
+static __global__ void __launch_bounds__(256)
+f8c_bound_up_kernel(const unsigned int* __restrict__ lmax /*[Ci]*/, const float* __restrict__ S /*[rows][Ci]*/, int rows, int Ci,
+                    const float* __restrict__ bias /*[64]*/, const unsigned int* __restrict__ wmax /*[2]*/, float* __restrict__ f8s) {
+  __shared__ unsigned int mx;
+  __shared__ float lm[256];
+  if (threadIdx.x == 0) mx = 0u;
+  for (int i = threadIdx.x; i < Ci; i += blockDim.x) lm[i] = __uint_as_float(lmax[i]);
+  __syncthreads();
+  float m = 0.f;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    float bnd = fabsf(bias[r & 63]);
+    const float* sr = S + (size_t)r * Ci;
+    for (int c = 0; c < Ci; ++c) bnd = fmaf(sr[c], lm[c], bnd);
+    m = fmaxf(m, bnd);
+  }
+  atomicMax(&mx, __float_as_uint(m * 1.001f));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float bnd = __uint_as_float(mx);
+    f8s[6] = bnd;
+    const float a0 = f8s[0], a1 = f8c_alpha(bnd);
+    f8s[1] = a1;
+    const int b0 = f8c_floor_log2(240.f * 2048.f / fmaxf(__uint_as_float(wmax[0]), 1e-30f));
+    const int b1 = f8c_floor_log2(240.f * 2048.f / fmaxf(__uint_as_float(wmax[1]), 1e-30f));
+    const int s = min(ilogbf(a0) + b0, ilogbf(a1) + b1);
+    f8s[2] = scalbnf(1.f, -s);
+    f8s[3] = scalbnf(1.f, s - ilogbf(a0));
+    f8s[4] = scalbnf(1.f, s - ilogbf(a1));
+  }
+}
+// per-op entry: exact maxima of the two sources (amax[0], amax[1]) instead of bounds
+static __global__ void f8c_scales_exact_kernel(const unsigned int* __restrict__ amax, const unsigned int* __restrict__ wmax,
+                                               int two_src, float* __restrict__ f8s) {
+  const float a0 = f8c_alpha(__uint_as_float(amax[0]) * 1.0001f);
+  const float a1 = two_src ? f8c_alpha(__uint_as_float(amax[1]) * 1.0001f) : a0;
+  const int b0 = f8c_floor_log2(240.f * 2048.f / fmaxf(__uint_as_float(wmax[0]), 1e-30f));
+  const int b1 = two_src ? f8c_floor_log2(240.f * 2048.f / fmaxf(__uint_as_float(wmax[1]), 1e-30f)) : b0;
+  const int s = min(ilogbf(a0) + b0, ilogbf(a1) + b1);
+  f8s[0] = a0; f8s[1] = a1;
+  f8s[2] = scalbnf(1.f, -s);
+  f8s[3] = scalbnf(1.f, s - ilogbf(a0));
+  f8s[4] = scalbnf(1.f, s - ilogbf(a1));
+  f8s[5] = __uint_as_float(amax[0]); f8s[6] = __uint_as_float(amax[two_src ? 1 : 0]);
+}
+// S[row][ci] = sum over the 27 taps of |wfold[row][tap][ci]|  (row = phase * 64 + co)
+static __global__ void f8c_fold_abs_kernel(const float* __restrict__ wfold, long long rows, int Ci, float* __restrict__ S) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * Ci; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / Ci;
+    const int c = (int)(i % Ci);
+    float a = 0.f;
+    for (int t = 0; t < 27; ++t) a += fabsf(wfold[(r * 27 + t) * Ci + c]);
+    S[i] = a;
+  }
+}
+
+int conv3_f8c_prepare(const float* w_tapmajor, int Cin, int C0, __nv_bfloat16* w16, unsigned int* wmax, cudaStream_t st) {
+  if (Cin % CV_KC || C0 % CV_KC) { set_error("conv3_f8c: channels must be multiples of %d", CV_KC); return VXB_E_UNSUPPORTED_SHAPE; }
+  f8c_w16_kernel<<<148 * 4, 256, 0, st>>>(w_tapmajor, Cin, w16);
+  VXB_LAUNCH_CHECK();
+  VXB_CUDA(cudaMemsetAsync(wmax, 0, 2 * sizeof(unsigned int), st));
+  f8c_wmax_kernel<<<64, 256, 0, st>>>(w_tapmajor, 64ll * 27, Cin, C0, wmax);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+int conv3_f8c_fold_abs(const float* wfold, long long rows, int Ci, float* S, cudaStream_t st) {
+  f8c_fold_abs_kernel<<<148 * 4, 256, 0, st>>>(wfold, rows, Ci, S);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+int conv3_f8c_bound_ipp(const float* grid, long long rows, int CIN, const float* w, const float* bias, int C, unsigned int* gmax,
+                        float* f8s, cudaStream_t st) {
+  VXB_CUDA(cudaMemsetAsync(gmax, 0, (size_t)CIN * sizeof(unsigned int), st));
+  VXB_TRY(absmax_cols(grid, rows, CIN, gmax, st));
+  f8c_bound_ipp_kernel<<<1, 64, 0, st>>>(gmax, w, bias, CIN, C, f8s);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+int conv3_f8c_bound_up(const float* low, long long rows, int Ci, const float* S, long long srows, const float* bias,
+                       const unsigned int* wmax, unsigned int* lmax, float* f8s, cudaStream_t st) {
+  if (Ci > 256) { set_error("conv3_f8c: Ci=%d", Ci); return VXB_E_UNSUPPORTED_SHAPE; }
+  VXB_CUDA(cudaMemsetAsync(lmax, 0, (size_t)Ci * sizeof(unsigned int), st));
+  VXB_TRY(absmax_cols(low, rows, Ci, lmax, st));
+  f8c_bound_up_kernel<<<1, 256, 0, st>>>(lmax, S, (int)srows, Ci, bias, wmax, f8s);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+int conv3_f8c_quantize_weights(const float* w_tapmajor, int Cin, int C0, const float* f8s, uint8_t* w8, cudaStream_t st) {
+  f8c_w8_kernel<<<148 * 2, 256, 0, st>>>(w_tapmajor, Cin, C0 / CV_KC, f8s, w8);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+template <int CL>
+static int conv3_f8c_launch(const CUtensorMap* maps, const ConvParams& p, size_t smem, cudaStream_t st) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    VXB_CUDA(cudaFuncSetAttribute(conv3_f8c_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    VXB_CUDA(cudaGetDevice(&dev));
+    VXB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(CV_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int max_clusters = num_sms / CL;
+  if (CL > 1) {
+    cfg.gridDim = dim3(num_sms / CL * CL);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv3_f8c_kernel<CL>, &cfg) == cudaSuccess && n > 0) max_clusters = std::min(max_clusters, n);
+    else cudaGetLastError();
+  }
+  const int groups = p.items / CL;
+  cfg.gridDim = dim3(std::min(groups, max_clusters) * CL);
+  VXB_CUDA(cudaLaunchKernelEx(&cfg, conv3_f8c_kernel<CL>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p));
+  return VXB_OK;
+}
+
+// x0 / x1: Planes{hi, c8} of the replicate-padded grids (the `lo` member holds the c8 plane); w16 / w8: conv3_f8c_prepare /
+// conv3_f8c_quantize_weights; f8s: the device scalars both were derived from
+int conv3_f8c_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_bfloat16* w16, const uint8_t* w8, const float* f8s,
+                     const float* bias, float act_slope, float* out, int B, int V, cudaStream_t st, const ConvTail* tail) {
+  const int Vp = V + 2;
+  const long long rows = (long long)B * Vp * Vp * Vp;
+  if (C0 % CV_KC || C1 % CV_KC || x0.ld != 64 || (x1 && x1->ld != 64) || C0 > 64 || C1 > 64 || rows >= (1ll << 31) || Vp > 180) {
+    set_error("conv3_f8c_planes: unsupported geometry (C0=%d C1=%d V=%d)", C0, C1, V);
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  int cl = conv3_cluster();
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.V = V; p.Vp = Vp;
+  p.ncb = (C0 + C1) / CV_KC; p.cb_src0 = C0 / CV_KC;
+  conv3_plan(B, V, cl, p.tiles, p.lz, p.zchunks);
+  const int cols = B * p.tiles;
+  const int cols_pad = cdiv(cols, cl) * cl;
+  p.items = cols_pad * p.zchunks;
+  p.items_real = cols * p.zchunks;
+  p.slab_rows = 128 + 2 * (Vp + 1);
+  p.box_rows = (cdiv(p.slab_rows, 2) + 7) / 8 * 8;
+  p.bias = bias; p.act_slope = act_slope; p.out = out; p.f8s = f8s;
+  if (tail) {
+    p.tail_w = tail->tail_w; p.ptap = tail->ptap; p.ss_partial = tail->ss_partial; p.out = nullptr;
+    p.tail_w2 = tail->tail_w2; p.ptap2 = tail->ptap2;
+  }
+  CUtensorMap maps[6];
+  VXB_TRY(make_map(&maps[0], x0.hi, rows, 64, 64, p.box_rows, CV_KC));
+  VXB_TRY(make_map(&maps[1], x0.lo, rows, 64, 64, p.box_rows, CV_KC));
+  const Planes& xb = x1 ? *x1 : x0;
+  VXB_TRY(make_map(&maps[2], xb.hi, rows, 64, 64, p.box_rows, CV_KC));
+  VXB_TRY(make_map(&maps[3], xb.lo, rows, 64, 64, p.box_rows, CV_KC));
+  const long long wrows = (long long)p.ncb * 9 * F8_WROWS;
+  VXB_TRY(make_map(&maps[4], w16, wrows, CV_KC, CV_KC, F8_WCHUNK_ROWS, CV_KC));
+  VXB_TRY(make_map(&maps[5], reinterpret_cast<const __nv_bfloat16*>(w8), wrows, CV_KC, CV_KC, F8_WCHUNK_ROWS, CV_KC));
+  const size_t smem = (size_t)CV_SLABS * 4 * p.box_rows * 64 + (size_t)CV_WSTAGES * F8_WBYTES + 1024 + 1024 + 2 * CV_TAILW_BYTES;
+  ++g_umma_launches;
+  switch (cl) {
+    case 1: return conv3_f8c_launch<1>(maps, p, smem, st);
+    case 4: return conv3_f8c_launch<4>(maps, p, smem, st);
+    default: return conv3_f8c_launch<2>(maps, p, smem, st);
+  }
+}
+
+// fp32 [B,V,V,V,64] -> Planes{hi, c8} of the replicate-padded grid (per-op entry of the f8c convolution); alpha = f8s[src]
+static __global__ void __launch_bounds__(256)
+pad_split_c8_kernel(const float* __restrict__ x, int B, int V, __nv_bfloat16* __restrict__ hi, uint8_t* __restrict__ c8,
+                    const float* __restrict__ alpha) {
+  const int Vp = V + 2;
+  const long long total = (long long)B * Vp * Vp * Vp * 16;
+  const float fa = __ldg(alpha);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i & 15);
+    long long v = i >> 4;
+    const long long row = v;
+    const int pw = (int)(v % Vp); v /= Vp;
+    const int ph = (int)(v % Vp); v /= Vp;
+    const int pd = (int)(v % Vp);
+    const int b = (int)(v / Vp);
+    const int d = min(max(pd - 1, 0), V - 1), h = min(max(ph - 1, 0), V - 1), w = min(max(pw - 1, 0), V - 1);
+    const float4 a = *reinterpret_cast<const float4*>(x + ((((long long)b * V + d) * V + h) * V + w) * 64 + g * 4);
+    const __nv_bfloat162 h01 = pl2_from_floats(a.x, a.y), h23 = pl2_from_floats(a.z, a.w);
+    const float2 f01 = pl2_to_float2(h01), f23 = pl2_to_float2(h23);
+    uint2 hv;
+    hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+    *reinterpret_cast<uint2*>(hi + row * 64 + g * 4) = hv;
+    uint8_t* rowb = c8 + row * 128 + (g >> 3) * 64 + (g & 7) * 4;
+    *reinterpret_cast<uint32_t*>(rowb) = pl_e4m3x4(a.x - f01.x, a.y - f01.y, a.z - f23.x, a.w - f23.y, fa * 2048.f);
+    *reinterpret_cast<uint32_t*>(rowb + 32) = pl_e4m3x4(a.x, a.y, a.z, a.w, fa);
+  }
+}
+size_t conv3_f8c_scratch_bytes(int B, int V) {
+  const size_t prow = (size_t)B * (V + 2) * (V + 2) * (V + 2);
+  return 2 * align_up(prow * 128, 256) + align_up(conv3_f8c_w16_elems(64) * 2, 256) + align_up(conv3_f8c_w8_bytes(64), 256) + 4096;
+}
+// per-op entry (tests): y = act(conv3(x) + bias), x fp32 [B,V,V,V,64], tap-major weights [64][27][64]
+int conv3_f8c_f32(const float* x, const float* w_tapmajor, const float* bias, float act_slope, float* out, int B, int V,
+                  Arena& scratch, cudaStream_t st) {
+  const long long prow = (long long)B * (V + 2) * (V + 2) * (V + 2);
+  Planes xp;
+  xp.hi = scratch.get<__nv_bfloat16>((size_t)prow * 64);
+  xp.lo = scratch.get<__nv_bfloat16>((size_t)prow * 64);
+  xp.ld = 64;
+  __nv_bfloat16* w16 = scratch.get<__nv_bfloat16>(conv3_f8c_w16_elems(64));
+  uint8_t* w8 = scratch.get<uint8_t>(conv3_f8c_w8_bytes(64));
+  float* f8s = scratch.get<float>(16);
+  unsigned int* stat = scratch.get<unsigned int>(8);
+  if (!scratch.ok) { set_error("conv3_f8c: workspace too small"); return VXB_E_WORKSPACE_TOO_SMALL; }
+  VXB_TRY(conv3_f8c_prepare(w_tapmajor, 64, 64, w16, stat, st));                 // stat[0..1] = max |w|
+  VXB_CUDA(cudaMemsetAsync(stat + 2, 0, 2 * sizeof(unsigned int), st));
+  VXB_TRY(absmax_cols(x, (long long)B * V * V * V * 64, 1, stat + 2, st));       // stat[2] = max |x|
+  f8c_scales_exact_kernel<<<1, 1, 0, st>>>(stat + 2, stat, 0, f8s);
+  VXB_LAUNCH_CHECK();
+  VXB_TRY(conv3_f8c_quantize_weights(w_tapmajor, 64, 64, f8s, w8, st));
+  const long long total = prow * 16;
+  pad_split_c8_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(x, B, V, xp.hi, reinterpret_cast<uint8_t*>(xp.lo), f8s);
+  VXB_LAUNCH_CHECK();
+  return conv3_f8c_planes(xp, nullptr, 64, 0, w16, w8, f8s, bias, act_slope, out, B, V, st, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------ patchify (patchify_umma.cuh)
