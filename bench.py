@@ -57,13 +57,15 @@ def parse():
     return ap.parse_args()
 
 
-def ncu_traffic(batch):
+def ncu_traffic(batch, f8c=True):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
-    (taken at batch 16); None for any other batch."""
-    path = os.path.join(ROOT, 'profiles', 'ncu_r01_conv3_umma_b16_summary.json')
+    (taken at batch 16 on the kernel that is timed); None for any other batch."""
+    name = 'ncu_r02_conv3_f8c_b16_summary.json' if f8c else 'ncu_r01_conv3_umma_b16_summary.json'
+    path = os.path.join(ROOT, 'profiles', name)
     if batch != 16 or not os.path.exists(path):
         return None
     d = json.load(open(path))
+    d = d[0] if isinstance(d, list) else d
     unit = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
     tot = 0.0
     for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
@@ -313,31 +315,52 @@ def run_ours(args):
     final_ms = stages['final_conv']
     achieved_tf = FINAL_CONV_FLOPS * B / (final_ms * 1e-3) / 1e12
     vox_ms = ms_vox / max(args.steps, 10)
+    simt = math_mode == _lib.MATH_FP32_SIMT
+    f8c = math_mode == _lib.MATH_F16F8C
+    # MMA "units" (fp16-MMA-equivalents of tensor-pipe time) per logical product of the final conv / folded up-conv:
+    # 3 = hi*hi + hi*lo + lo*hi in fp16; 2 = fp16 hi*hi + one E4M3 MMA (twice the rate, twice the K) for both corrections
+    units = 2 if f8c else 3
+    padded = (102 / 100) ** 2 * 1.02            # rows the kernel multiplies / useful rows (replicate halo of the flat plane tiles)
+    whole_tf = FLOPS_PER_PASS * B * passes_per_sample / (per_step * 1e-3) / 1e12
+    dtype = {_lib.MATH_FP32_SIMT: 'f32',
+             _lib.MATH_BF16X3: 'f16x3 (split-fp16 hi/lo planes, 3 tcgen05 kind::f16 MMAs per product, fp32 accumulate in TMEM)',
+             _lib.MATH_F16F8C: 'f16x3 (split-fp16 hi/lo planes, fp32 accumulate in TMEM); final conv + folded up-conv: fp16 hi*hi '
+                               '+ one kind::f8f6f4 E4M3 MMA carrying both 2^-11 correction terms'}[math_mode]
+    kernel = {_lib.MATH_FP32_SIMT: 'final conv 3x3x3, 128->64 @100^3 (fp32 FFMA implicit GEMM)',
+              _lib.MATH_BF16X3: 'conv3_umma_kernel: final conv 3x3x3, 128->64 @100^3 (input-stationary tcgen05, split-fp16 x3)',
+              _lib.MATH_F16F8C: 'conv3_f8c_kernel: final conv 3x3x3, 128->64 @100^3 (input-stationary tcgen05, fp16 + E4M3-corrected, '
+                                'dz taps merged into N=192 MMAs)'}[math_mode]
     line = {
         'metric': 'policy fwd passes/sec at 100^3 voxels', 'value': value, 'unit': 'passes/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if math_mode == _lib.MATH_FP32_SIMT else 'f16x3 (split-fp16 hi/lo planes, 3 tcgen05 kind::f16 MMAs per product, fp32 accumulate in TMEM)',
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': dtype,
         'data': 'synthetic',
         'config': {'workload': workload, 'global_batch': world * B, 'parallelism': 'batch-sharded x%d, no collective' % world,
-                   'math_mode': 'fp32_simt' if math_mode == _lib.MATH_FP32_SIMT else 'split16x3_tcgen05',
+                   'math_mode': {_lib.MATH_FP32_SIMT: 'fp32_simt', _lib.MATH_BF16X3: 'split16x3_tcgen05',
+                                 _lib.MATH_F16F8C: 'split16x3_tcgen05 + f16_fp8c convs'}[math_mode],
+                   'parity_gate': 'max|a-b| / max|b| per output tensor < 1e-3 vs the reference goldens (tests/util.py rel_err); '
+                                  'voxel indices and arg-max actions bit-exact',
                    'l2': 'no explicit flush: each step streams >10 GB of activations, far above the 126 MB L2'},
         'e2e': {'value': e2e_value, 'unit': 'passes/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': (launches_per_step) * args.steps,
         'clocks': clk,
-        'roofline': {'kernel': 'conv3_umma_kernel: final conv 3x3x3, 128->64 @100^3 (input-stationary tcgen05, split-fp16 x3)'
-                               if math_mode != _lib.MATH_FP32_SIMT else 'final conv 3x3x3, 128->64 @100^3 (fp32 FFMA implicit GEMM)',
+        'roofline': {'kernel': kernel,
                      'bound': 'tensor',
                      'achieved': achieved_tf, 'peak': pk['tensor'], 'unit': 'TFLOP/s', 'frac': achieved_tf / pk['tensor'],
-                     'traffic': ncu_traffic(B) if math_mode != _lib.MATH_FP32_SIMT else None,
+                     'frac_of_burst_peak': achieved_tf / pk['tensor_burst'], 'peak_burst': pk['tensor_burst'],
+                     'traffic': ncu_traffic(B, f8c) if not simt else None,
                      'algorithmic_flops_per_launch': FINAL_CONV_FLOPS * B,
-                     # what the tensor pipe actually executes: 3 f16 MMAs per product on the padded (102/100)^2 x (V+2)/V rows
-                     'executed_mma_tflops': (achieved_tf * 3 * (102 / 100) ** 2 * 1.02) if math_mode != _lib.MATH_FP32_SIMT else None,
-                     'executed_frac_of_peak': (achieved_tf * 3 * (102 / 100) ** 2 * 1.02 / pk['tensor']) if math_mode != _lib.MATH_FP32_SIMT else None,
-                     'note': 'achieved = direct-convolution FLOPs (442.4 GF/sample) / CUDA-event time; the kernel executes 3 f16 MMAs per '
-                             'logical product (fp32-class accuracy), so its own ceiling is 1/3 of this bf16 peak',
-                     'peak_source': pk['source'] + ' bf16 sustained', 'ms_per_launch': final_ms,
-                     'whole_forward_tflops': FLOPS_PER_PASS * B * passes_per_sample / (per_step * 1e-3) / 1e12,
+                     # what the tensor pipe actually executes, in fp16-MMA-equivalents, on the padded (102/100)^2 x (V+2)/V rows
+                     'mma_units_per_product': None if simt else units,
+                     'executed_mma_tflops': None if simt else achieved_tf * units * padded,
+                     'executed_frac_of_peak': None if simt else achieved_tf * units * padded / pk['tensor'],
+                     'note': 'achieved = direct-convolution FLOPs (442.4 GF/sample) / CUDA-event time of the kernel inside the step; the '
+                             'kernel spends %d fp16-MMA-equivalents per logical product for fp32-class accuracy, so its own ceiling is '
+                             '1/%d of this peak' % (units, units),
+                     'peak_source': pk['source'] + ' bf16 sustained (frac) and burst (frac_of_burst_peak)', 'ms_per_launch': final_ms,
+                     'whole_forward_tflops': whole_tf,
+                     'whole_forward_frac': whole_tf / pk['tensor'], 'whole_forward_frac_of_burst_peak': whole_tf / pk['tensor_burst'],
                      'voxelize': {'bound': 'hbm', 'achieved': VOXELIZE_BYTES * B / (vox_ms * 1e-3) / 1e9, 'peak': pk['hbm'],
                                   'unit': 'GB/s', 'frac': VOXELIZE_BYTES * B / (vox_ms * 1e-3) / 1e9 / pk['hbm'],
                                   'ms_per_call': vox_ms}},

@@ -164,7 +164,7 @@ conv3_f8c_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
   if (warp == 0) {
     // ===================================================== slab producer
     if (lane == 0) {
-      int sb = 0;
+      int sb = 0, dbg_n = 0;
       uint32_t sph = 0;
       for (int g = cluster_id; g < groups; g += num_clusters) {
         int b, t, z0, lz;
@@ -178,6 +178,12 @@ conv3_f8c_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
             const CUtensorMap* mc = s1 ? &mapA1c : &mapA0c;
             mbar_wait(&slab_empty[sb], sph ^ 1);
             uint8_t* s = slab_base + sb * slab_bytes;
+            if ((p.debug_skip & 2) && dbg_n >= CV_SLABS) {           // timing experiment: never refill the slabs (wrong results)
+              mbar_expect_tx(&slab_full[sb], 0);
+              if (++sb == CV_SLABS) { sb = 0; sph ^= 1; }
+              continue;
+            }
+            ++dbg_n;
             mbar_expect_tx(&slab_full[sb], slab_bytes);
             tma_load_2d(mh, &slab_full[sb], s, col, row0);
             tma_load_2d(mh, &slab_full[sb], s + p.box_rows * 64, col, row0 + p.box_rows);
@@ -191,7 +197,7 @@ conv3_f8c_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
   } else if (warp == 1) {
     // ===================================================== weight producer: 4 chunks of 96 rows per stage, 4 / CL per CTA, multicast
     if (lane == 0) {
-      int ws = 0;
+      int ws = 0, dbg_n = 0;
       uint32_t wph = 0;
       constexpr int CHUNKS = 4 / CL;
       const uint16_t mask = (uint16_t)((1u << CL) - 1);
@@ -203,6 +209,12 @@ conv3_f8c_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
             for (int tap9 = 0; tap9 < 9; ++tap9) {
               mbar_wait(&w_empty[ws], wph ^ 1);
               uint8_t* s = w_base + ws * F8_WBYTES;
+              if ((p.debug_skip & 1) && dbg_n >= CV_WSTAGES) {       // timing experiment: never refill the ring (wrong results)
+                mbar_expect_tx(&w_full[ws], 0);
+                if (++ws == CV_WSTAGES) { ws = 0; wph ^= 1; }
+                continue;
+              }
+              ++dbg_n;
               mbar_expect_tx(&w_full[ws], F8_WBYTES);
               const int r0 = (cb * 9 + tap9) * F8_WROWS;
 #pragma unroll

@@ -89,6 +89,8 @@ struct Prepared {
   __nv_bfloat16* final_w16; // [4][9][3][64][32] fp16 W_hi
   unsigned int* final_wmax; // [2] float bits
   float* up1_abs;           // [s^3 * 64][64]
+  __nv_bfloat16* up1_f8[2]; // folded up-conv weights as the f8c operand of the GEMM engine (upconv_f8c_prepare)
+  float* up1_beta;          // [1] their e4m3 scale
   float* q_cross;    // [L][ch*cdh]  = to_q(LN(latents)), batch independent
   float* lat_norm;   // [L][D] scratch for the above
   float* ff_perm_w;  // [8D][D] scratch: FF net.0 weight with the GEGLU [a | gate] 32-row interleave (split into planes)
@@ -118,6 +120,8 @@ static void carve_prepared(const Dims& m, Arena& a, Prepared& p, const void* con
   p.final_w16 = a.get<__nv_bfloat16>(umma::conv3_f8c_w16_elems(128));
   p.final_wmax = a.get<unsigned int>(2);
   p.up1_abs = a.get<float>((size_t)m.s * m.s * m.s * 64 * 64);
+  for (int i = 0; i < 2; ++i) p.up1_f8[i] = a.get<__nv_bfloat16>((size_t)m.s * m.s * m.s * 64 * 27 * 64);
+  p.up1_beta = a.get<float>(4);
   p.q_cross = a.get<float>((size_t)m.L * m.ch * m.cdh);
   p.lat_norm = a.get<float>((size_t)m.L * m.D);
   p.ff_perm_w = a.get<float>((size_t)8 * m.D * m.D);
@@ -613,6 +617,8 @@ extern "C" int vxb_qnet_prepare(const vxb_qnet_desc* d, const void* const* param
   }
   VXB_TRY(umma::conv3_f8c_prepare(p.final_wt, 128, 64, p.final_w16, p.final_wmax, st));
   VXB_TRY(umma::conv3_f8c_fold_abs(p.up1_fold, (long long)m.s * m.s * m.s * 64, 64, p.up1_abs, st));
+  VXB_TRY(umma::upconv_f8c_prepare(p.up1_fold, (long long)m.s * m.s * m.s * 64, 27 * 64, umma::Planes{p.up1_f8[0], p.up1_f8[1], 27 * 64},
+                                   p.up1_beta, reinterpret_cast<unsigned int*>(p.up1_beta + 2), st));
   // q of the encoder cross-attention depends only on parameters: to_q(LN(latents))
   VXB_TRY(layernorm(P(VXB_P_LATENTS), P(VXB_P_CROSS_NORM_W), P(VXB_P_CROSS_NORM_B), p.lat_norm, m.L, m.D, st));
   VXB_TRY(linear(p.lat_norm, m.D, P(VXB_P_CROSS_Q_W), m.D, nullptr, nullptr, 1, 0, p.q_cross,
@@ -790,14 +796,16 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
     if (fused_planes) ++g_launches;
     if (f8c) {
       // bound of |u0| (low-res channel maxima x folded |weights|), then the joint scales and the per-call fp8 weights
-      g_launches += 3;
+      g_launches += 5;
       VXB_TRY(umma::conv3_f8c_bound_up(w.low, (long long)B * m.T, 64, pw.up1_abs, (long long)m.s * m.s * m.s * 64, P(VXB_P_UP1_B),
-                                       pw.final_wmax, w.f8max + 16, w.f8s, st));
+                                       pw.final_wmax, w.f8max + 16, w.f8s, st, pw.up1_beta));
       VXB_TRY(umma::conv3_f8c_quantize_weights(pw.final_wt, 128, 64, w.f8s, w.final_w8, st));
     }
+    const umma::Planes up8{pw.up1_f8[0], pw.up1_f8[1], 27 * 64};
+    const umma::F8cGemm f8g{w.f8s + 8, w.f8s + 9};
     VXB_TRY(upconv3d_folded(w.low, pw.up1_fold, P(VXB_P_UP1_B), w.u0, B, m.S, 64, 64, m.s, slope, mm, st,
-                            cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.up1_fold), fused_planes ? &u0p : nullptr,
-                            f8c ? w.f8s + 1 : nullptr));
+                            cx.scratch.base ? &cx.scratch : nullptr, f8c ? &up8 : cx.find(pw.up1_fold), fused_planes ? &u0p : nullptr,
+                            f8c ? w.f8s + 1 : nullptr, f8c ? &f8g : nullptr));
   }
   STAGE_MARK();  // 8: final conv
   // (11) final: conv3 on cat[d0, u0] (128 -> 64)                               :462

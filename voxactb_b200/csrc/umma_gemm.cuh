@@ -105,6 +105,20 @@ __device__ __forceinline__ void tc_mma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
       "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi) : "memory");
 }
+// kind::f8f6f4 (E4M3 x E4M3, K = 32 bytes per instruction) with the same descriptor convention: the correction MMA of the
+// f16 + fp8-corrected product (terms == 2, see conv_f8c.cuh for the arithmetic)
+__device__ __forceinline__ void tc_mma_f8_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi) : "memory");
+}
 // A operand from tensor memory (row m = TMEM lane m, two 16-bit K elements per 32-bit column, 8 columns per K = 16
 // step; cute SM100_MMA_F16BF16_TS), B from a shared-memory descriptor
 __device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
@@ -303,6 +317,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
       uint32_t acc_phase = 0;
       const int num_kb = p.plan.num_kb;
       const bool three = p.terms == 3;
+      // terms == 2: the "lo" tiles hold E4M3 bytes ([x_lo8 | x_hi8] against [w_hi8 | w_lo8] along K) and ONE fp8 MMA per 32 bytes
+      // of K adds both correction terms to the same accumulator (operands pre-scaled so that all products share one scale)
+      const bool f8c = p.terms == 2;
+      constexpr uint32_t idesc8 = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator stage
         tc_fence_after();
@@ -323,6 +341,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
                 tc_mma_bf16_lo(d_tmem, a_hi + 2 * k, b_lo + 2 * k, kDescHi, idesc, 1);
                 tc_mma_bf16_lo(d_tmem, a_lo + 2 * k, b_hi + 2 * k, kDescHi, idesc, 1);
               }
+              if (f8c) tc_mma_f8_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc8, 1);
             }
             tc_commit(&empty_bar[stage]);             // smem slot reusable once these MMAs retire
             if (kb == num_kb - 1) tc_commit(&acc_full[acc]);   // accumulator complete -> epilogue
@@ -596,6 +615,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
       }
     } else {
     RowInfo* ri = reinterpret_cast<RowInfo*>(stage + 32 * EPI_STAGE_LD);
+    const float alpha_g = e.alpha_dev ? e.alpha * __ldg(e.alpha_dev) : e.alpha;   // device-side factor (f8c operand un-scaling)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int tiles_per_z = p.m_tiles * p.n_tiles;
       const int z = tile / tiles_per_z, tz = tile % tiles_per_z;
@@ -660,7 +680,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * e.alpha;
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha_g;
         }
         if (e.transpose_planes) {
           // element (row, col) -> plane[col * ldp + row]: lanes are consecutive rows, already contiguous

@@ -43,6 +43,7 @@ struct Epilogue {
   int out_Vp, out_pad;        // ROWS_PHASE: geometry of the fine output grid (padded)
   const float* bias;          // [N] (ROWS_PHASE: [64], shared by all phases)
   float alpha;
+  const float* alpha_dev;     // generic epilogue: optional device scalar multiplied into alpha
   float act_slope;            // < 0: none
   const float* residual;      // fp32 [(row % res_rows), ldr] added after the activation, or null
   int res_rows, ldr;
@@ -69,7 +70,8 @@ struct Params {
   int a_row_zh;                  // A: rows per zh
   int a_row_off;                 // A: first row of every batch entry (conv modes skip the all-halo leading z planes)
   long long a_col_off, w_col_off; // plain GEMM: constant K offsets of the two operands (weight gradients: a tap = a K shift)
-  int terms;                     // 3 = hi*hi + hi*lo + lo*hi (default), 1 = hi*hi only (lo planes are not loaded)
+  int terms;                     // 3 = hi*hi + hi*lo + lo*hi (default), 1 = hi*hi only (lo planes are not loaded),
+                                 // 2 = fp16 hi*hi + one E4M3 MMA on the "lo" planes (c8 layout, 64-channel blocks)
   long long rs_zb, rs_zh;        // row statistic element offsets per zb / zh
   int w_row_zb, w_row_zh, w_col_zh;
   long long c_zb, c_zh;          // fp32 output element offsets per zb / zh
@@ -108,8 +110,15 @@ size_t conv3d_scratch_bytes(int B, int V, int C0, int C1, int k);
 int conv3d_f32(const float* x0, const float* x1, int C0, int C1, const Planes& Wp, const float* bias, float* out,
                int B, int V, int Co, int k, float act_slope, Arena& scratch, cudaStream_t st);
 size_t upconv_scratch_bytes(int B, int S, int Ci);
+// f8c form of the folded up-convolution GEMM: Wp = upconv_f8c_prepare planes, sc = device scalars {alpha of `low`, 1/(alpha beta)}
+struct F8cGemm { const float* alpha; const float* unscale; };
 int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out, int B, int S, int Ci, int Co, int s,
-               float act_slope, Arena& scratch, cudaStream_t st, const Planes* out_planes = nullptr, const float* f8a = nullptr);
+               float act_slope, Arena& scratch, cudaStream_t st, const Planes* out_planes = nullptr, const float* f8a = nullptr,
+               const F8cGemm* f8g = nullptr);
+// static operand of that GEMM: hi = fp16(2^-5 beta W), lo = per 64 columns [64 x e4m3(2^-11 beta W) | 64 x e4m3(beta W_lo)];
+// beta (largest power of two with 2^-11 beta max|W| <= 240) is left in *beta_out
+int upconv_f8c_prepare(const float* wfold, long long rows, long long cols, Planes out, float* beta_out, unsigned int* tmp,
+                       cudaStream_t st);
 
 // ---- backward (training) contractions on the tensor cores ------------------------------------------------------------
 // Gradient tensors span many decades (softmax-over-10^6 logit gradients are ~1e-8), below the fp16 planes' range, so every
@@ -200,7 +209,7 @@ int conv3_f8c_fold_abs(const float* wfold, long long rows, int Ci, float* S, cud
 int conv3_f8c_bound_ipp(const float* grid, long long rows, int CIN, const float* w, const float* bias, int C, unsigned int* gmax,
                         float* f8s, cudaStream_t st);
 int conv3_f8c_bound_up(const float* low, long long rows, int Ci, const float* S, long long srows, const float* bias,
-                       const unsigned int* wmax, unsigned int* lmax, float* f8s, cudaStream_t st);
+                       const unsigned int* wmax, unsigned int* lmax, float* f8s, cudaStream_t st, const float* up_beta = nullptr);
 int conv3_f8c_quantize_weights(const float* w_tapmajor, int Cin, int C0, const float* f8s, uint8_t* w8, cudaStream_t st);
 int conv3_f8c_planes(const Planes& x0, const Planes* x1, int C0, int C1, const __nv_bfloat16* w16, const uint8_t* w8, const float* f8s,
                      const float* bias, float act_slope, float* out, int B, int V, cudaStream_t st, const ConvTail* tail = nullptr);

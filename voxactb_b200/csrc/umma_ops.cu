@@ -535,10 +535,92 @@ size_t upconv_scratch_bytes(int B, int S, int Ci) {
   return a.off;
 }
 
+// ---- f8c operands of the GEMM engine (terms == 2): 64-channel blocks of 128 bytes, [64 x lo8 | 64 x hi8] against [64 x w_hi8 | 64 x w_lo8]
+constexpr float F8C_P16 = 32.f;      // the fp16 planes carry 2^5 x (A side) and 2^-5 x (W side) of the fp8 scales: both stay inside fp16
+__device__ __forceinline__ uint32_t f8c_pack4(float a, float b, float c, float d, float sc) { return pl_e4m3x4(a, b, c, d, sc); }
+// fp32 [B,V,V,V,C] -> planes of the replicate-padded grid: hi = fp16(32 alpha x), c8 as above with alpha, 2^11 alpha
+static __global__ void __launch_bounds__(256)
+pad_split_f8c64_kernel(const float* __restrict__ x, int B, int V, int C, __nv_bfloat16* __restrict__ hi, uint8_t* __restrict__ c8,
+                       const float* __restrict__ alpha) {
+  const int Vp = V + 2, cg = C / 4;
+  const long long total = (long long)B * Vp * Vp * Vp * cg;
+  const float fa = __ldg(alpha);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long v = i / cg;
+    const long long row = v;
+    const int pw = (int)(v % Vp); v /= Vp;
+    const int ph = (int)(v % Vp); v /= Vp;
+    const int pd = (int)(v % Vp);
+    const int b = (int)(v / Vp);
+    const int d = min(max(pd - 1, 0), V - 1), h = min(max(ph - 1, 0), V - 1), w = min(max(pw - 1, 0), V - 1);
+    const float4 a = *reinterpret_cast<const float4*>(x + ((((long long)b * V + d) * V + h) * V + w) * C + g * 4);
+    const __nv_bfloat162 u01 = pl2_from_floats(a.x, a.y), u23 = pl2_from_floats(a.z, a.w);      // unscaled split: x = hi + lo
+    const float2 f01 = pl2_to_float2(u01), f23 = pl2_to_float2(u23);
+    const float s16 = fa * F8C_P16;
+    const __nv_bfloat162 h01 = pl2_from_floats(f01.x * s16, f01.y * s16), h23 = pl2_from_floats(f23.x * s16, f23.y * s16);   // exact
+    uint2 hv;
+    hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+    *reinterpret_cast<uint2*>(hi + row * C + g * 4) = hv;
+    uint8_t* rowb = c8 + row * C * 2 + (g >> 4) * 128 + (g & 15) * 4;
+    *reinterpret_cast<uint32_t*>(rowb) = f8c_pack4(a.x - f01.x, a.y - f01.y, a.z - f23.x, a.w - f23.y, fa * 2048.f);
+    *reinterpret_cast<uint32_t*>(rowb + 64) = f8c_pack4(a.x, a.y, a.z, a.w, fa);
+  }
+}
+static int pad_split_f8c64(const float* x, int B, int V, int C, Planes out, const float* alpha, cudaStream_t st) {
+  if (C % 64) { set_error("pad_split_f8c64: C must be a multiple of 64"); return VXB_E_BADARG; }
+  const long long total = (long long)B * (V + 2) * (V + 2) * (V + 2) * (C / 4);
+  pad_split_f8c64_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(x, B, V, C, out.hi,
+                                                                                                reinterpret_cast<uint8_t*>(out.lo), alpha);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+static __global__ void f8c_beta_kernel(const unsigned int* __restrict__ wmax, float* __restrict__ beta) {
+  const float m = __uint_as_float(wmax[0]);
+  int e = 0;
+  if (m > 0.f && isfinite(m)) e = max(-60, min(60, ilogbf(240.f * 2048.f / m)));
+  beta[0] = scalbnf(1.f, e);
+}
+// static weights [rows, cols] (cols % 64 == 0, ld = cols): hi = fp16(beta / 32 w), c8 blocks [64 x e4m3(2^-11 beta w) | 64 x e4m3(beta w_lo)]
+static __global__ void __launch_bounds__(256)
+split_rows_f8c_kernel(const float* __restrict__ x, long long rows, long long cols, __nv_bfloat16* __restrict__ hi,
+                      uint8_t* __restrict__ c8, const float* __restrict__ beta) {
+  const long long cg = cols / 4, total = rows * cg;
+  const float fb = __ldg(beta);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cg;
+    const int g = (int)(i % cg);
+    const float4 a = *reinterpret_cast<const float4*>(x + r * cols + g * 4);
+    const __nv_bfloat162 u01 = pl2_from_floats(a.x, a.y), u23 = pl2_from_floats(a.z, a.w);
+    const float2 f01 = pl2_to_float2(u01), f23 = pl2_to_float2(u23);
+    const float s16 = fb * (1.f / F8C_P16);
+    const __nv_bfloat162 h01 = pl2_from_floats(f01.x * s16, f01.y * s16), h23 = pl2_from_floats(f23.x * s16, f23.y * s16);
+    uint2 hv;
+    hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+    *reinterpret_cast<uint2*>(hi + r * cols + g * 4) = hv;
+    uint8_t* rowb = c8 + r * cols * 2 + (g >> 4) * 128 + (g & 15) * 4;
+    *reinterpret_cast<uint32_t*>(rowb) = f8c_pack4(a.x, a.y, a.z, a.w, fb * (1.f / 2048.f));
+    *reinterpret_cast<uint32_t*>(rowb + 64) = f8c_pack4(a.x - f01.x, a.y - f01.y, a.z - f23.x, a.w - f23.y, fb);
+  }
+}
+int absmax_cols(const float* x, long long rows, int C, unsigned int* out, cudaStream_t st);
+int upconv_f8c_prepare(const float* wfold, long long rows, long long cols, Planes out, float* beta_out, unsigned int* tmp,
+                       cudaStream_t st) {
+  if (cols % 64 || out.ld != cols) { set_error("upconv_f8c_prepare: cols must be a multiple of 64 with ld == cols"); return VXB_E_BADARG; }
+  VXB_CUDA(cudaMemsetAsync(tmp, 0, sizeof(unsigned int), st));
+  VXB_TRY(absmax_cols(wfold, rows * cols, 1, tmp, st));
+  f8c_beta_kernel<<<1, 1, 0, st>>>(tmp, beta_out);
+  VXB_LAUNCH_CHECK();
+  split_rows_f8c_kernel<<<148 * 8, 256, 0, st>>>(wfold, rows, cols, out.hi, reinterpret_cast<uint8_t*>(out.lo), beta_out);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
 // folded upsample-conv: low [B,S^3,Ci] fp32 -> out [B,(S*s)^3,64] fp32 and/or out_planes = hi/lo planes of the
 // replicate-padded fine grid [B,(S*s+2)^3,64] (interior written here, halo by halo_fill); Wp planes of [s^3*64][27*Ci]
 int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out, int B, int S, int Ci, int Co, int s,
-               float act_slope, Arena& scratch, cudaStream_t st, const Planes* out_planes, const float* f8a) {
+               float act_slope, Arena& scratch, cudaStream_t st, const Planes* out_planes, const float* f8a,
+               const F8cGemm* f8g) {
   if (Ci % 64 || Co != 64) {
     set_error("umma upconv: needs Ci %% 64 == 0 and Co == 64");
     return VXB_E_UNSUPPORTED_SHAPE;
@@ -550,9 +632,11 @@ int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out
     set_error("umma upconv: scratch too small");
     return VXB_E_WORKSPACE_TOO_SMALL;
   }
-  VXB_TRY(pad_split(low, B, S, 1, Ci, a0, st));
+  if (f8g) VXB_TRY(pad_split_f8c64(low, B, S, Ci, a0, f8g->alpha, st));
+  else VXB_TRY(pad_split(low, B, S, 1, Ci, a0, st));
   Params p;
   params_init(p);
+  if (f8g) { p.terms = 2; p.ep.alpha_dev = f8g->unscale; }
   const int N = s * s * s * 64;
   const int nt = 256;
   // one batch entry per sample, restricted to the rows between the first and the last interior voxel (the two
@@ -1522,25 +1606,27 @@ static __global__ void f8c_bound_ipp_kernel(const unsigned int* __restrict__ gma
 // absolute tap sums of the folded weights; then the joint scales of the two sources of the final convolution:
 //   beta_max(src) = largest power of two with beta * 2^-11 max|W_src| <= 240;  s = min_src log2(alpha_src beta_max(src));
 //   beta_src = 2^s / alpha_src (<= beta_max: nothing saturates);  f8s[2] = 2^-s
+// (a) one warp per weight row: bound of that output channel and phase, max over rows into *bmax (float bits, zeroed by the caller)
 static __global__ void __launch_bounds__(256)
-f8c_bound_up_kernel(const unsigned int* __restrict__ lmax /*[Ci]*/, const float* __restrict__ S /*[rows][Ci]*/, int rows, int Ci,
-                    const float* __restrict__ bias /*[64]*/, const unsigned int* __restrict__ wmax /*[2]*/, float* __restrict__ f8s) {
-  __shared__ unsigned int mx;
-  __shared__ float lm[256];
-  if (threadIdx.x == 0) mx = 0u;
-  for (int i = threadIdx.x; i < Ci; i += blockDim.x) lm[i] = __uint_as_float(lmax[i]);
-  __syncthreads();
+f8c_bound_rows_kernel(const unsigned int* __restrict__ lmax /*[Ci]*/, const float* __restrict__ S /*[rows][Ci]*/, int rows, int Ci,
+                      const float* __restrict__ bias /*[64]*/, unsigned int* __restrict__ bmax) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float m = 0.f;
-  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
-    float bnd = fabsf(bias[r & 63]);
+  for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
     const float* sr = S + (size_t)r * Ci;
-    for (int c = 0; c < Ci; ++c) bnd = fmaf(sr[c], lm[c], bnd);
-    m = fmaxf(m, bnd);
+    float a = 0.f;
+    for (int c = lane; c < Ci; c += 32) a = fmaf(sr[c], __uint_as_float(lmax[c]), a);
+    a = warp_sum(a) + fabsf(bias[r & 63]);
+    m = fmaxf(m, a);
   }
-  atomicMax(&mx, __float_as_uint(m * 1.001f));
-  __syncthreads();
+  if (lane == 0) atomicMax(bmax, __float_as_uint(m * 1.001f));
+}
+// (b) the scalars
+static __global__ void f8c_bound_up_kernel(const unsigned int* __restrict__ lmax /*[Ci]*/, int Ci, const unsigned int* __restrict__ bmax,
+                                           const unsigned int* __restrict__ wmax /*[2]*/, float* __restrict__ f8s,
+                                           const float* __restrict__ up_beta /*beta of the folded up-conv weights, or null*/) {
   if (threadIdx.x == 0) {
-    const float bnd = __uint_as_float(mx);
+    const float bnd = __uint_as_float(bmax[0]);
     f8s[6] = bnd;
     const float a0 = f8s[0], a1 = f8c_alpha(bnd);
     f8s[1] = a1;
@@ -1550,6 +1636,14 @@ f8c_bound_up_kernel(const unsigned int* __restrict__ lmax /*[Ci]*/, const float*
     f8s[2] = scalbnf(1.f, -s);
     f8s[3] = scalbnf(1.f, s - ilogbf(a0));
     f8s[4] = scalbnf(1.f, s - ilogbf(a1));
+    if (up_beta) {
+      // operands of the folded up-convolution GEMM itself (terms == 2): alpha of `low` from its exact maximum
+      float lmx = 0.f;
+      for (int c = 0; c < Ci; ++c) lmx = fmaxf(lmx, __uint_as_float(lmax[c]));
+      const float al = f8c_alpha(lmx * 1.0001f);
+      f8s[8] = al;
+      f8s[9] = 1.f / (al * up_beta[0]);
+    }
   }
 }
 // per-op entry: exact maxima of the two sources (amax[0], amax[1]) instead of bounds
@@ -1600,11 +1694,13 @@ int conv3_f8c_bound_ipp(const float* grid, long long rows, int CIN, const float*
   return VXB_OK;
 }
 int conv3_f8c_bound_up(const float* low, long long rows, int Ci, const float* S, long long srows, const float* bias,
-                       const unsigned int* wmax, unsigned int* lmax, float* f8s, cudaStream_t st) {
+                       const unsigned int* wmax, unsigned int* lmax, float* f8s, cudaStream_t st, const float* up_beta) {
   if (Ci > 256) { set_error("conv3_f8c: Ci=%d", Ci); return VXB_E_UNSUPPORTED_SHAPE; }
-  VXB_CUDA(cudaMemsetAsync(lmax, 0, (size_t)Ci * sizeof(unsigned int), st));
+  VXB_CUDA(cudaMemsetAsync(lmax, 0, (size_t)(Ci + 1) * sizeof(unsigned int), st));      // lmax[Ci] = max row bound
   VXB_TRY(absmax_cols(low, rows, Ci, lmax, st));
-  f8c_bound_up_kernel<<<1, 256, 0, st>>>(lmax, S, (int)srows, Ci, bias, wmax, f8s);
+  f8c_bound_rows_kernel<<<(int)std::min<long long>((srows + 7) / 8, 148 * 8), 256, 0, st>>>(lmax, S, (int)srows, Ci, bias, lmax + Ci);
+  VXB_LAUNCH_CHECK();
+  f8c_bound_up_kernel<<<1, 32, 0, st>>>(lmax, Ci, lmax + Ci, wmax, f8s, up_beta);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }
@@ -1673,6 +1769,11 @@ int conv3_f8c_planes(const Planes& x0, const Planes* x1, int C0, int C1, const _
   p.slab_rows = 128 + 2 * (Vp + 1);
   p.box_rows = (cdiv(p.slab_rows, 2) + 7) / 8 * 8;
   p.bias = bias; p.act_slope = act_slope; p.out = out; p.f8s = f8s;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("VXB_CONV_DEBUG_SKIP"); dbg = e ? atoi(e) : 0; }   // timing experiments only (wrong results)
+    p.debug_skip = dbg;
+  }
   if (tail) {
     p.tail_w = tail->tail_w; p.ptap = tail->ptap; p.ss_partial = tail->ss_partial; p.out = nullptr;
     p.tail_w2 = tail->tail_w2; p.ptap2 = tail->ptap2;

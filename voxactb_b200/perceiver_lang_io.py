@@ -135,9 +135,10 @@ class _QnetTrainFn(torch.autograd.Function):
 class PerceiverVoxelLangEncoder(nn.Module):
     """Drop-in for reference perceiver_lang_io.py:136 (same keywords and defaults)."""
 
-    # arithmetic of the dense contractions: the product path is the tcgen05 split-16-bit x3 mode (fp32-class
-    # accuracy, see DESIGN.md section 4); MATH_FP32_SIMT (fp32 FFMA everywhere) is the slow reference-arithmetic mode
-    math_mode = _lib.MATH_BF16X3
+    # arithmetic of the dense contractions: tcgen05 split-16-bit products with fp32-class accuracy (DESIGN.md section 4).
+    # MATH_F16F8C (default): three fp16 MMAs per product in the transformer, fp16 hi*hi + one E4M3 correction MMA in the two
+    # large convolutions; MATH_BF16X3: three fp16 MMAs everywhere; MATH_FP32_SIMT: fp32 FFMA everywhere (slow reference mode)
+    math_mode = _lib.MATH_F16F8C
     TWO_ROBOTS = False     # PerceiverVoxelLang2RobotsEncoder: two proprio streams (C = 3 * im_channels), two head sets
 
     def __init__(self, depth, iterations, voxel_size, initial_dim, low_dim_size, layer=0,
