@@ -54,6 +54,7 @@ def parse():
                          'losses + backward + NCCL gradient all-reduce + LAMB, --batch samples per GPU; value = samples/s)')
     ap.add_argument('--optimizer', default='lamb', choices=['lamb', 'adam'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpu-comparator', action='store_true', help='skip the informational torch-eager run of the Q-network on the same GPU')
     return ap.parse_args()
 
 
@@ -89,6 +90,63 @@ WORKLOADS = {
     'crop': 'batch={b}/GPU, 100^3 voxels, 4 cameras 128x128 RGB-D, CLIP lang tokens [77,512], single-arm PerAct forward with per-sample VLM-crop bounds [B,6]',
 }
 WORKLOAD = 'batch={b}/GPU, 100^3 voxels, 4 cameras 128x128 RGB-D, CLIP lang tokens [77,512], single-arm PerAct forward (voxelize + Q-net, 2048 latents, depth 6)'
+
+
+def cpu_model():
+    try:
+        for l in open('/proc/cpuinfo'):
+            if l.startswith('model name'):
+                return l.split(':', 1)[1].strip()
+    except OSError:
+        pass
+    import platform
+    return platform.processor() or 'unknown'
+
+
+def gpu_torch_comparator(agent_enc, grid_cl, proprio, lang, B, dev, steps=2):
+    """Informational: the reference's Q-network as plain PyTorch modules' functional restatement (oracle.qnet_oracle.qnet_forward,
+    cuDNN / cuBLAS eager, fp32) on the SAME GPU and the same voxel grid, with TF32 off and on."""
+    import torch
+    from oracle import qnet_oracle
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import util
+    sd = {k: v.detach().to(dev) for k, v in agent_enc.state_dict().items()}
+    cfg = dict(voxel_patch_size=5, voxel_patch_stride=5, depth=6, iterations=1, cross_heads=1, latent_heads=8, activation='lrelu',
+               num_collision_classes=2, arm_pred_loss=False, no_language=False)
+    out = {}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for tf32 in (False, True):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            b = B
+            while True:
+                try:
+                    g = grid_cl[:b]
+                    with torch.no_grad():
+                        qnet_oracle.qnet_forward(sd, cfg, g, proprio[:b], lang[:b])          # warm-up (cuDNN autotune, allocator)
+                        torch.cuda.synchronize()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        for _ in range(steps):
+                            qnet_oracle.qnet_forward(sd, cfg, g, proprio[:b], lang[:b])
+                        e1.record()
+                        torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / steps
+                    out['tf32_on' if tf32 else 'tf32_off'] = {'passes_per_s': b / (ms * 1e-3), 'ms_per_step': ms, 'batch': b}
+                    break
+                except torch.cuda.OutOfMemoryError:
+                    torch.cuda.empty_cache()
+                    if b == 1:
+                        out['tf32_on' if tf32 else 'tf32_off'] = {'error': 'out of memory at batch 1'}
+                        break
+                    b //= 2
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+        torch.cuda.empty_cache()
+    out['what'] = ('oracle.qnet_oracle.qnet_forward (torch eager fp32: cuDNN conv3d, cuBLAS matmul, materialised softmax) on this GPU, '
+                   'Q-network only (voxel grid given), %d timed steps after 1 warm-up' % steps)
+    return out
 
 
 def cpu_pass_rate(steps, warmup, threads=None):
@@ -127,9 +185,10 @@ def run_reference(args):
         'impl': 'reference', 'metric': 'policy fwd passes/sec at 100^3 voxels', 'value': rate, 'unit': 'passes/s',
         'n_gpus': args.gpus, 'steps': steps, 'warmup': max(1, min(args.warmup, 2)), 'ms_per_step': spp * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD.format(b=args.batch),
+        'config': {'workload': WORKLOAD.format(b=args.batch) + ' -- reference arm: 1 sample of that batch per step',
                    'note': 'reference CPU PyTorch path (oracle port) on the host cores; each step = 1 sample of the batch'},
-        'cpu_baseline': {'value': rate, 'unit': 'passes/s', 'cores': cores, 'kind': 'port',
+        'cpu_baseline': {'value': rate, 'unit': 'passes/s', 'cores': cores, 'kind': 'port', 'cpu_model': cpu_model(),
+                         'torch_threads': cores,
                          'sample': 'batch 1 of the workload per step (voxelize + Q-net forward), torch CPU fp32'},
         'e2e': {'value': rate, 'unit': 'passes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
@@ -263,6 +322,26 @@ def run_ours(args):
             out_host['xyz'].copy_(xyz, non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the caller needs the actions before the next step
 
+    # end-to-end with the NEXT step's host->device copies on a copy stream (voxactb_b200.act.HostStager): the copies of step
+    # i+1 overlap the Q-network of step i; every step still uploads its own inputs and reads its own actions back
+    from voxactb_b200.act import HostStager
+    stager = HostStager(dev, slots=2)
+    host_in = {k: host[k] for k in ('rgb', 'pcd', 'proprio', 'lang_token_embs', 'bounds')}
+    stager.stage(host_in)
+
+    def step_e2e_pipelined():
+        d = stager.acquire()
+        stager.stage(host_in)                        # upload of the next step, overlapped with this step's compute
+        for a, out, out_host in zip(agents, step_device(d), out_hosts):
+            trans, rot_grip, coll = out[0], out[1], out[2]
+            coords, rg, ic, xyz = a.select_action(trans, rot_grip, coll, d['bounds'])
+            out_host['coords'].copy_(coords, non_blocking=True)
+            out_host['rg'].copy_(rg, non_blocking=True)
+            out_host['coll'].copy_(ic, non_blocking=True)
+            out_host['xyz'].copy_(xyz, non_blocking=True)
+        stager.release()
+        torch.cuda.current_stream().synchronize()
+
     def timed(fn, steps, warmup, profile=False):
         for _ in range(warmup):
             fn()
@@ -302,7 +381,8 @@ def run_ours(args):
     clk = clocks.stop()
     launches_per_step = passes_per_sample * (L.vxb_voxelize_launches() + enc.last_launch_count)
     ms_vox, _ = timed(lambda: vg.coords_to_bounding_voxel_grid(cf, ff, bb), max(args.steps, 10), 3)
-    ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    ms_e2e_serial, _ = timed(step_e2e, args.steps, args.warmup)
+    ms_e2e, _ = timed(step_e2e_pipelined, args.steps, args.warmup)
 
     if rank != 0:
         if world > 1:
@@ -342,7 +422,11 @@ def run_ours(args):
                                   'voxel indices and arg-max actions bit-exact',
                    'l2': 'no explicit flush: each step streams >10 GB of activations, far above the 126 MB L2'},
         'e2e': {'value': e2e_value, 'unit': 'passes/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
-                'ms_per_step': ms_e2e / args.steps},
+                'ms_per_step': ms_e2e / args.steps,
+                'mode': 'pinned host buffers -> HostStager (the next step\'s H2D copies run on a copy stream while this step computes) -> '
+                        'QFunction.forward -> select_action -> D2H of the chosen actions, synchronised every step',
+                'serial_value': world * B * passes_per_sample / (ms_e2e_serial / args.steps * 1e-3),
+                'serial_ms_per_step': ms_e2e_serial / args.steps},
         'gpu_launches': (launches_per_step) * args.steps,
         'clocks': clk,
         'roofline': {'kernel': kernel,
@@ -368,8 +452,14 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         rate, cores, spp = cpu_pass_rate(8, 1)
-        line['cpu_baseline'] = {'value': rate, 'unit': 'passes/s', 'cores': cores, 'kind': 'port',
+        line['cpu_baseline'] = {'value': rate, 'unit': 'passes/s', 'cores': cores, 'kind': 'port', 'cpu_model': cpu_model(),
+                                'torch_threads': cores,
                                 'sample': '8 timed single-sample passes (batch 1 of the workload) after 1 warm-up, torch CPU fp32 oracle port'}
+    if world == 1 and not args.no_gpu_comparator and not dual:
+        with torch.no_grad():
+            grid_cl = vg.coords_to_bounding_voxel_grid(cf, ff, bb).permute(0, 4, 1, 2, 3).contiguous()
+        line['gpu_torch_comparator'] = gpu_torch_comparator(enc, grid_cl, resident['proprio'], resident['lang_token_embs'], B, dev)
+        del grid_cl
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

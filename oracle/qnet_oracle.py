@@ -57,9 +57,9 @@ def spatial_softmax3d(x, temperature=0.01):
     b, c, d, h, w = x.shape
     pos_x, pos_y, pos_z = np.meshgrid(np.linspace(-1., 1., d), np.linspace(-1., 1., h),
                                       np.linspace(-1., 1., w))
-    pos_x = torch.from_numpy(pos_x.reshape(-1)).float()
-    pos_y = torch.from_numpy(pos_y.reshape(-1)).float()
-    pos_z = torch.from_numpy(pos_z.reshape(-1)).float()
+    pos_x = torch.from_numpy(pos_x.reshape(-1)).float().to(x.device)
+    pos_y = torch.from_numpy(pos_y.reshape(-1)).float().to(x.device)
+    pos_z = torch.from_numpy(pos_z.reshape(-1)).float().to(x.device)
     feat = x.contiguous().view(-1, h * w * d)
     att = F.softmax(feat / temperature, dim=-1)
     ex = torch.sum(pos_x * att, dim=1, keepdim=True)

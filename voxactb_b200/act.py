@@ -61,3 +61,60 @@ class FusedActor:
         self._host.copy_(action, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self._host, {'coords': coords, 'rot_grip': rg, 'collision': coll, 'attention_xyz': xyz, 'voxel_grid': out[3]}
+
+
+class HostStager:
+    """Double-buffered host -> device staging of observation batches (the device side of the
+    replay / observation pipeline): ``stage(host)`` enqueues the copies of the NEXT batch on a private copy stream, so they
+    overlap the Q-network of the current one; ``acquire()`` makes the compute stream wait for the oldest staged batch and
+    returns its device tensors.  ``host`` is a dict of pinned CPU tensors or lists of them; the device buffers are allocated
+    once per slot and reused, guarded by events in both directions (a slot is not overwritten before the step that read it
+    has finished)."""
+
+    def __init__(self, device, slots=2):
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.slots = [dict(buf=None, ready=torch.cuda.Event(), free=torch.cuda.Event(), staged=False) for _ in range(slots)]
+        self._w = self._r = 0
+
+    def _like(self, v):
+        if isinstance(v, (list, tuple)):
+            return [self._like(t) for t in v]
+        return torch.empty(v.shape, dtype=v.dtype, device=self.device)
+
+    @staticmethod
+    def _copy(dst, src):
+        if isinstance(src, (list, tuple)):
+            for d, t in zip(dst, src):
+                HostStager._copy(d, t)
+        else:
+            dst.copy_(src, non_blocking=True)
+
+    def stage(self, host):
+        slot = self.slots[self._w]
+        if slot['staged']:
+            raise RuntimeError('HostStager: every slot holds a batch that has not been acquired yet')
+        if slot['buf'] is None:
+            slot['buf'] = {k: self._like(v) for k, v in host.items()}
+        else:
+            self.copy_stream.wait_event(slot['free'])             # the step that read this slot has finished
+        with torch.cuda.stream(self.copy_stream):
+            for k, v in host.items():
+                self._copy(slot['buf'][k], v)
+            slot['ready'].record(self.copy_stream)
+        slot['staged'] = True
+        self._w = (self._w + 1) % len(self.slots)
+
+    def acquire(self):
+        slot = self.slots[self._r]
+        if not slot['staged']:
+            raise RuntimeError('HostStager: acquire() without a staged batch')
+        torch.cuda.current_stream(self.device).wait_event(slot['ready'])
+        slot['staged'] = False
+        self._cur = slot
+        self._r = (self._r + 1) % len(self.slots)
+        return slot['buf']
+
+    def release(self):
+        """Call after the last kernel that reads the acquired batch has been enqueued on the compute stream."""
+        self._cur['free'].record(torch.cuda.current_stream(self.device))
