@@ -450,6 +450,23 @@ def run_ours(args):
                                   'ms_per_call': vox_ms}},
         'stages_ms': stages,
     }
+    if world == 1 and B <= 2 and args.workload != 'crop':
+        # closed-loop acting latency (eval.py runs batch 1; the dual workload alternates the two agents as
+        # rollout_generator does): observations arrive on the host, the 9-D action is needed on the host
+        from voxactb_b200.act import GraphedActor
+        actors = [GraphedActor(a, 5) for a in agents]
+
+        def step_act():
+            d = upload()
+            rgb_pcd = [[r, p] for r, p in zip(d['rgb'], d['pcd'])]
+            for ga in actors:
+                ga.act(rgb_pcd, d['proprio'], d['pcd'], resident['lang_goal_emb'], d['lang_token_embs'], d['bounds'])
+        ms_act, _ = timed(step_act, max(args.steps, 20), max(args.warmup, 3))
+        ms_act /= max(args.steps, 20)
+        line['act_latency'] = {'ms_per_step': ms_act, 'agent_calls_per_step': len(actors), 'batch': B,
+                               'ungraphed_ms_per_step': ms_e2e_serial / args.steps,
+                               'mode': 'H2D of the observation -> GraphedActor.act (CUDA-graph replay of voxelize + Q-net + select + act '
+                                       'tail) -> 9-D action on the host, per agent'}
     if world == 1 and not args.no_cpu_baseline:
         rate, cores, spp = cpu_pass_rate(8, 1)
         line['cpu_baseline'] = {'value': rate, 'unit': 'passes/s', 'cores': cores, 'kind': 'port', 'cpu_model': cpu_model(),

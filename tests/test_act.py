@@ -83,3 +83,35 @@ def test_fused_actor_matches_oracle_pipeline(cuda_lib):
     xyz = qnet_oracle.attention_coordinate(coords, obs['bounds'].expand(c['B'], 6), c['V']).numpy()
     expect = act_oracle.continuous_action(xyz, rg.numpy(), ic.numpy(), 5)
     np.testing.assert_allclose(action.numpy(), expect, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_graphed_actor_replays_one_graph_for_new_observations(cuda_lib):
+    """The CUDA-graph actor (batch-1 closed loop): one capture, then every replay on NEW observations matches the oracle
+    pipeline; a parameter update forces a re-capture."""
+    from voxactb_b200 import QFunction, VoxelGrid, synth
+    from voxactb_b200.act import GraphedActor
+    c = dict(make_golden.QNET_CASES['qnet_v20'], B=1)
+    obs, enc, sd = util.make_case(c)
+    dev = torch.device('cuda')
+    vg = VoxelGrid(synth.SCENE_BOUNDS, c['V'], dev, c['B'], 3, c['cameras'] * c['H'] * c['W'])
+    q = QFunction(enc, vg, 0.15, 5, dev, False, False).to(dev).eval()
+    actor = GraphedActor(q, 5)
+    for seed in (c['seed'], c['seed'] + 1, c['seed'] + 2):
+        o = synth.make_observation(seed, 1, c['cameras'], c['H'], c['W'], low_dim=c['low_dim'], per_sample_crop=c['crop'])
+        rgb = [t.cuda() for t in o['rgb']]
+        pcd = [t.cuda() for t in o['pcd']]
+        action, extra = actor.act([[r, p] for r, p in zip(rgb, pcd)], o['proprio'].cuda(), pcd, o['lang_goal_emb'].cuda(),
+                                  o['lang_token_embs'].cuda(), o['bounds'].cuda())
+        ref = qnet_oracle.qfunction_forward(sd, util.oracle_cfg(c), voxel_oracle.voxelize, o['rgb'], o['pcd'], o['proprio'],
+                                            o['lang_token_embs'], o['bounds'], c['V'])
+        assert util.rel_err(extra['q_trans'], ref['trans']) < util.Q_REL_TOL
+        coords, rg, ic = qnet_oracle.choose_highest_action(ref['trans'], ref['rot_grip'], ref['collision'])
+        xyz = qnet_oracle.attention_coordinate(coords, o['bounds'].expand(1, 6), c['V']).numpy()
+        np.testing.assert_allclose(action.numpy(), act_oracle.continuous_action(xyz, rg.numpy(), ic.numpy(), 5), rtol=1e-5, atol=1e-5)
+    assert actor.captures == 1
+    with torch.no_grad():
+        next(q.parameters()).mul_(1.0)             # bumps the version: prepared weights and the graph are stale
+    actor.act([[r, p] for r, p in zip(rgb, pcd)], o['proprio'].cuda(), pcd, o['lang_goal_emb'].cuda(), o['lang_token_embs'].cuda(),
+              o['bounds'].cuda())
+    assert actor.captures == 2

@@ -443,6 +443,13 @@ static Planes alloc_planes(Arena& a, long long rows, long long ld) {
 }
 
 static int pick_ntile(int N) { return N >= 256 ? 256 : (N > 64 ? 128 : 64); }
+// small-M GEMMs (batch-1 acting: M = 2048 latent rows) leave most SMs idle with 128 x 256 tiles: halve the N tile until the
+// launch has at least one tile per SM
+static int pick_ntile_mn(long long m_tiles, int N) {
+  int nt = pick_ntile(N);
+  while (nt > 64 && m_tiles * cdiv(N, nt) < 148) nt >>= 1;
+  return nt;
+}
 
 size_t linear_scratch_bytes(long long M, long long N, long long K, bool split_w) {
   Arena a(nullptr, 0);
@@ -672,7 +679,7 @@ int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out
 int linear_planes(const Planes& A, long long M, int K, const Planes& W, int N, const LinOut& o, cudaStream_t st) {
   Params p;
   params_init(p);
-  const int nt = pick_ntile(N);
+  const int nt = pick_ntile_mn(cdiv(M, (long long)BM), N);
   p.n_tiles = cdiv(N, nt);
   p.plan.num_kb = cdiv(K, BK);
   p.ep.N = N; p.ep.row_mode = ROWS_PLAIN;
