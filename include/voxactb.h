@@ -242,6 +242,13 @@ int vxb_act_tail_f32(const int32_t* rot_grip_idx /*[B,4]*/, const int32_t* coll_
                      const float* attention_xyz /*[B,3]*/, float rotation_resolution, float* action /*[B,9]*/, int B,
                      void* stream);
 
+/* SE(3) augmentation of a planar point cloud: perturb_se3 of the reference
+ * (peract/voxel/augmentation.py:7-65) as one streaming kernel.  pcd, out [B,3,N] fp32 (one camera, N = H*W; out may alias pcd);
+ * xform [B,15] = keyframe gripper position a(3), rot_shift[0:3,0:3] row-major (9), c(3) = clamp(a + trans_shift, bounds):
+ * p' = (p - a) . R + c.  The sampling / rejection of the perturbation (augmentation.py:68-185) stays on the host
+ * (voxactb_b200/augmentation.py), it touches a few floats per sample. */
+int vxb_se3_perturb_f32(const float* pcd, const float* xform, float* out, int B, long long N, void* stream);
+
 /* ------------------------------------------------------------------ building blocks (exported for the per-op parity tests) */
 /* number of tcgen05 (split 16-bit x3) GEMM kernels launched so far by this process: lets tests prove that
  * VXB_MATH_BF16X3 really ran on the tensor cores and did not fall back to the FFMA path */

@@ -37,6 +37,17 @@ def install_shims():
     pkg.voxel_grid = _v
     sys.modules['voxel.voxel_grid'] = _v
     sys.modules['agents.peract_bc.perceiver_lang_io'] = _p
+    # the SE(3) augmentation entry points the agent imports by name (qattention_peract_bc_agent.py:18): the real module keeps
+    # everything else it defines
+    from . import augmentation as _a
+    try:
+        aug = importlib.import_module('voxel.augmentation')
+        aug.perturb_se3 = _a.perturb_se3
+        aug.apply_se3_augmentation = _a.apply_se3_augmentation
+        aug.apply_se3_augmentation_2Robots = _a.apply_se3_augmentation_2Robots
+    except ImportError:                 # reference tree (or pytorch3d) absent: this package's module stands in
+        sys.modules['voxel.augmentation'] = _a
+        pkg.augmentation = _a
     agents = sys.modules.get('agents.peract_bc')
     if agents is not None:
         agents.perceiver_lang_io = _p

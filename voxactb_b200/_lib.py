@@ -72,6 +72,7 @@ SIGNATURES = {
     'vxb_select_action_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_size_t, c_void_p]),
+    'vxb_se3_perturb_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p]),
     'vxb_act_tail_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p]),
     'vxb_umma_launch_count': (c_ll, []),
     'vxb_linear_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),

@@ -171,6 +171,39 @@ extern "C" int vxb_act_tail_f32(const int32_t* rot_grip_idx, const int32_t* coll
   return VXB_OK;
 }
 
+// ---------------------------------------------------------------- SE(3) augmentation of the point clouds
+// perturb_se3 (reference peract/voxel/augmentation.py:7-65) on one camera's planar point cloud [B, 3, N]:
+//   p' = (p - a) . R + c,   a = keyframe gripper position, R = rot_shift[0:3, 0:3] (row vector times matrix, :40-41),
+//   c = clamp(a + trans_shift, scene bounds) (:44-58) -- one fused streaming pass instead of ~10 full-size torch temporaries
+//   (ones, repeat, transpose, bmm, transpose, stack, add) per camera.  xform [B,15] = a(3), R(9, row-major), c(3).
+namespace vxb {
+__global__ void __launch_bounds__(256)
+se3_perturb_kernel(const float* __restrict__ pcd, const float* __restrict__ xform, float* __restrict__ out, long long N) {
+  const int b = blockIdx.y;
+  __shared__ float xf[15];
+  if (threadIdx.x < 15) xf[threadIdx.x] = xform[b * 15 + threadIdx.x];
+  __syncthreads();
+  const float* px = pcd + (size_t)b * 3 * N;
+  float* ox = out + (size_t)b * 3 * N;
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    const float d0 = __fsub_rn(px[n], xf[0]), d1 = __fsub_rn(px[N + n], xf[1]), d2 = __fsub_rn(px[2 * N + n], xf[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float r = fmaf(d2, xf[3 + 6 + k], fmaf(d1, xf[3 + 3 + k], __fmul_rn(d0, xf[3 + k])));
+      ox[k * N + n] = __fadd_rn(r, xf[12 + k]);
+    }
+  }
+}
+}  // namespace vxb
+
+extern "C" int vxb_se3_perturb_f32(const float* pcd, const float* xform, float* out, int B, long long N, void* stream) {
+  VXB_CHECK_ARG(pcd && xform && out && B > 0 && N > 0, "se3_perturb: bad arguments");
+  const int bx = (int)std::max<long long>(1, std::min<long long>((N + 255) / 256, (148 * 8 + B - 1) / B));
+  se3_perturb_kernel<<<dim3(bx, B), 256, 0, (cudaStream_t)stream>>>(pcd, xform, out, N);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
 // ---------------------------------------------------------------- building blocks
 extern "C" long long vxb_umma_launch_count(void) { return umma::launches(); }
 
