@@ -331,8 +331,9 @@ def run_ours(args):
 
     def step_e2e_pipelined():
         d = stager.acquire()
-        stager.stage(host_in)                        # upload of the next step, overlapped with this step's compute
-        for a, out, out_host in zip(agents, step_device(d), out_hosts):
+        outs = step_device(d)                        # this step's kernels are enqueued first ...
+        stager.stage(host_in)                        # ... then the next step's uploads (copy stream): they overlap the compute
+        for a, out, out_host in zip(agents, outs, out_hosts):
             trans, rot_grip, coll = out[0], out[1], out[2]
             coords, rg, ic, xyz = a.select_action(trans, rot_grip, coll, d['bounds'])
             out_host['coords'].copy_(coords, non_blocking=True)
@@ -341,6 +342,19 @@ def run_ours(args):
             out_host['xyz'].copy_(xyz, non_blocking=True)
         stager.release()
         torch.cuda.current_stream().synchronize()
+
+    # the same loop through the CUDA-graph actor (voxactb_b200.act.GraphedActor.act: the public closed-loop call): one graph
+    # launch per agent instead of ~120 kernel launches behind the per-step synchronisation
+    from voxactb_b200.act import GraphedActor
+    gactors = [GraphedActor(a, 5) for a in agents]
+
+    def step_e2e_graphed():
+        d = stager.acquire()
+        stager.stage(host_in)
+        rgb_pcd = [[r, p] for r, p in zip(d['rgb'], d['pcd'])]
+        for ga in gactors:
+            ga.act(rgb_pcd, d['proprio'], d['pcd'], resident['lang_goal_emb'], d['lang_token_embs'], d['bounds'])
+        stager.release()
 
     def timed(fn, steps, warmup, profile=False):
         for _ in range(warmup):
@@ -383,6 +397,7 @@ def run_ours(args):
     ms_vox, _ = timed(lambda: vg.coords_to_bounding_voxel_grid(cf, ff, bb), max(args.steps, 10), 3)
     ms_e2e_serial, _ = timed(step_e2e, args.steps, args.warmup)
     ms_e2e, _ = timed(step_e2e_pipelined, args.steps, args.warmup)
+    ms_e2e_graph, _ = timed(step_e2e_graphed, args.steps, args.warmup)
 
     if rank != 0:
         if world > 1:
@@ -425,6 +440,7 @@ def run_ours(args):
                 'ms_per_step': ms_e2e / args.steps,
                 'mode': 'pinned host buffers -> HostStager (the next step\'s H2D copies run on a copy stream while this step computes) -> '
                         'QFunction.forward -> select_action -> D2H of the chosen actions, synchronised every step',
+                'cuda_graph_actor_value': world * B * passes_per_sample / (ms_e2e_graph / args.steps * 1e-3),
                 'serial_value': world * B * passes_per_sample / (ms_e2e_serial / args.steps * 1e-3),
                 'serial_ms_per_step': ms_e2e_serial / args.steps},
         'gpu_launches': (launches_per_step) * args.steps,

@@ -370,6 +370,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
     uint32_t acc_phase = 0;
     if constexpr (EPI != EPIK_GENERIC) {
       const float slope = e.act_slope >= 0.f ? e.act_slope : 1.f;   // max(x, x*slope) == LeakyReLU for slope in [0,1]
+      [[maybe_unused]] const float alpha_f = e.alpha_dev ? e.alpha * __ldg(e.alpha_dev) : e.alpha;   // PLAIN / GEGLU: f8c un-scaling
       const bool f32_vec = e.out_f32 && ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0) &&
                            ((p.c_zb & 3) == 0) && ((p.c_zh & 3) == 0);
       const bool res_vec = e.residual && ((e.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.residual) & 15) == 0);
@@ -414,8 +415,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
                 *reinterpret_cast<float4*>(stage + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) =
-                    make_float4(__uint_as_float(v[j]) * e.alpha, __uint_as_float(v[j + 1]) * e.alpha,
-                                __uint_as_float(v[j + 2]) * e.alpha, __uint_as_float(v[j + 3]) * e.alpha);
+                    make_float4(__uint_as_float(v[j]) * alpha_f, __uint_as_float(v[j + 1]) * alpha_f,
+                                __uint_as_float(v[j + 2]) * alpha_f, __uint_as_float(v[j + 3]) * alpha_f);
               __syncwarp();
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -500,8 +501,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
                 *reinterpret_cast<float4*>(stage + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) =
-                    make_float4(__uint_as_float(v[j]) * e.alpha, __uint_as_float(v[j + 1]) * e.alpha,
-                                __uint_as_float(v[j + 2]) * e.alpha, __uint_as_float(v[j + 3]) * e.alpha);
+                    make_float4(__uint_as_float(v[j]) * alpha_f, __uint_as_float(v[j + 1]) * alpha_f,
+                                __uint_as_float(v[j + 2]) * alpha_f, __uint_as_float(v[j + 3]) * alpha_f);
             }
             __syncwarp();
             // ---- column domain

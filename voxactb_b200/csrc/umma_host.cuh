@@ -146,8 +146,13 @@ size_t conv_dgrad_scratch_bytes(int B, int V, int Cz, int Cx, int k);
 
 // ---- plane-domain building blocks of the transformer (no fp32 round trips between GEMMs)
 // y = LayerNorm(x) written as planes [rows, n]; input rows may be a strided slice per batch
+// f8alpha != null (n % 64 == 0): f8c A-operand planes -- hi = fp16(32 a y), out.lo = c8 blocks [64 x e4m3(2^11 a y_lo) | 64 x e4m3(a y)]
 int layernorm_planes(const float* x, size_t x_batch_stride, int rows_per_batch, const float* w, const float* b,
-                     Planes out, long long rows, int n, cudaStream_t st);
+                     Planes out, long long rows, int n, cudaStream_t st, const float* f8alpha = nullptr);
+// device scalar a = largest power of two with a * (sqrt(n - 1) max|w| + max|b|) <= 240: the bound of |LayerNorm(x)|
+int layernorm_f8c_alpha(const float* w, const float* b, int n, float* alpha_out, cudaStream_t st);
+// out[0] = 1 / (alpha[0] * beta[0])
+int f8c_unscale(const float* alpha, const float* beta, float* out, cudaStream_t st);
 // out = h[:, :n] * gelu_erf(h[:, n:]) written as planes [rows, n]
 int geglu_planes(const float* h, Planes out, long long rows, int n, cudaStream_t st);
 struct LinOut {
@@ -161,12 +166,17 @@ struct LinOut {
   int transposed = 0;
   int batches = 1;                      // transposed only: M = batches * rows_per_batch
   int geglu = 0;                        // fused GEGLU epilogue (out_planes has N / 2 columns; W and bias pre-permuted)
+  // terms == 2 (fp16 hi*hi + one E4M3 MMA, see umma_gemm.cuh): A and W are f8c planes (layernorm_planes with f8alpha /
+  // upconv_f8c_prepare), alpha_dev = device scalar 1 / (alpha_A beta_W) multiplied into the accumulator
+  int terms = 3;
+  const float* alpha_dev = nullptr;
 };
 // C[M,N] = A[M,K] W[N,K]^T with plane operands
 int linear_planes(const Planes& A, long long M, int K, const Planes& W, int N, const LinOut& o, cudaStream_t st);
 // V^T planes [B][inner][ld >= Nk] = Wv[inner, K] ctx_b[Nk, K]^T per batch: the projection written directly in the
 // layout the attention kernel consumes (the weight matrix is the M operand, so the stores stay row-contiguous)
-int project_vt(const Planes& ctx, int B, int Nk, int K, const Planes& Wv, int inner, const Planes& vt, cudaStream_t st);
+int project_vt(const Planes& ctx, int B, int Nk, int K, const Planes& Wv, int inner, const Planes& vt, cudaStream_t st,
+               int terms = 3, const float* alpha_dev = nullptr);
 // softmax(scale q k^T) v per (batch, head) as three tcgen05 GEMMs (row max, exp + row sum -> P planes, P V / sum).
 // Q [(B or 1)*Nq, H*dh] (q_batched = 0: one Q shared by all batches), K [B*Nk, H*dh], Vt [B*H*dh, pad8(Nk)],
 // P scratch planes [B*H*Nq, pad8(Nk)], O planes [B*Nq, H*dh]; rowmax / rowsum: B*H*Nq floats each.

@@ -214,11 +214,41 @@ int halo_fill(Planes p, int B, int V, int pad, int C, cudaStream_t st, __nv_bflo
   return VXB_OK;
 }
 
+// 8 consecutive values of a row -> plane stores.  f8a == 0: fp16 hi / lo planes.  f8a > 0 (f8c A operand, see umma_gemm.cuh
+// terms == 2): hi = fp16(32 f8a x) (an exact power-of-two multiple of fp16(x)), lo plane = c8 blocks per 64 columns.
+__device__ __forceinline__ void store8_planes(const float* f, __nv_bfloat16* hi, __nv_bfloat16* lo, long long row, long long ldp,
+                                              int i, float f8a) {
+  if (f8a == 0.f) {
+    uint4 hh, ll;
+    split8(f, hh, ll);
+    *reinterpret_cast<uint4*>(hi + row * ldp + i) = hh;
+    *reinterpret_cast<uint4*>(lo + row * ldp + i) = ll;
+    return;
+  }
+  __align__(16) __nv_bfloat16 h[8];
+  float l[8];
+  const float s16 = f8a * 32.f;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const float hf = pl_to_float(pl_from_float(f[t]));
+    l[t] = f[t] - hf;
+    h[t] = pl_from_float(hf * s16);
+  }
+  *reinterpret_cast<uint4*>(hi + row * ldp + i) = *reinterpret_cast<const uint4*>(h);
+  uint8_t* rowb = reinterpret_cast<uint8_t*>(lo + row * ldp) + (i >> 6) * 128 + (i & 63);
+  uint2 lo8, hi8;
+  lo8.x = pl_e4m3x4(l[0], l[1], l[2], l[3], f8a * 2048.f); lo8.y = pl_e4m3x4(l[4], l[5], l[6], l[7], f8a * 2048.f);
+  hi8.x = pl_e4m3x4(f[0], f[1], f[2], f[3], f8a); hi8.y = pl_e4m3x4(f[4], f[5], f[6], f[7], f8a);
+  *reinterpret_cast<uint2*>(rowb) = lo8;
+  *reinterpret_cast<uint2*>(rowb + 64) = hi8;
+}
+
 // LayerNorm (eps 1e-5, biased variance; reference PreNorm, perceiver_lang_io.py:56-71) -> planes; warp per row
 static __global__ void __launch_bounds__(256)
 layernorm_planes_kernel(const float* __restrict__ x, size_t x_batch_stride, int rows_per_batch,
                         const float* __restrict__ w, const float* __restrict__ b,
-                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldp, long long rows, int n) {
+                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldp, long long rows, int n, const float* __restrict__ f8alpha) {
+  const float f8a = f8alpha ? __ldg(f8alpha) : 0.f;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -243,10 +273,7 @@ layernorm_planes_kernel(const float* __restrict__ x, size_t x_batch_stride, int 
     float f[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) f[t] = (xr[i + t] - mean) * rstd * w[i + t] + b[i + t];
-    uint4 hh, ll;
-    split8(f, hh, ll);
-    *reinterpret_cast<uint4*>(hi + row * ldp + i) = hh;
-    *reinterpret_cast<uint4*>(lo + row * ldp + i) = ll;
+    store8_planes(f, hi, lo, row, ldp, i, f8a);
   }
 }
 
@@ -255,8 +282,10 @@ template <int CH>
 static __global__ void __launch_bounds__(256)
 layernorm_planes_reg_kernel(const float* __restrict__ x, size_t x_batch_stride, int rows_per_batch,
                             const float* __restrict__ w, const float* __restrict__ b,
-                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldp, long long rows) {
+                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldp, long long rows,
+                            const float* __restrict__ f8alpha) {
   constexpr int n = CH * 256;
+  const float f8a = f8alpha ? __ldg(f8alpha) : 0.f;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -292,29 +321,54 @@ layernorm_planes_reg_kernel(const float* __restrict__ x, size_t x_batch_stride, 
     f[2] = (v[c][0].z - mean) * rstd * w0.z + b0.z; f[3] = (v[c][0].w - mean) * rstd * w0.w + b0.w;
     f[4] = (v[c][1].x - mean) * rstd * w1.x + b1.x; f[5] = (v[c][1].y - mean) * rstd * w1.y + b1.y;
     f[6] = (v[c][1].z - mean) * rstd * w1.z + b1.z; f[7] = (v[c][1].w - mean) * rstd * w1.w + b1.w;
-    uint4 hh, ll;
-    split8(f, hh, ll);
-    *reinterpret_cast<uint4*>(hi + row * ldp + i) = hh;
-    *reinterpret_cast<uint4*>(lo + row * ldp + i) = ll;
+    store8_planes(f, hi, lo, row, ldp, i, f8a);
   }
 }
 
+static __global__ void ln_f8c_alpha_kernel(const float* __restrict__ w, const float* __restrict__ b, int n, float* __restrict__ out) {
+  __shared__ unsigned int mx;
+  if (threadIdx.x == 0) mx = 0u;
+  __syncthreads();
+  const float r = sqrtf((float)(n - 1));
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fmaf(fabsf(w[i]), r, fabsf(b[i])));
+  atomicMax(&mx, __float_as_uint(m * 1.0001f));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float bound = __uint_as_float(mx);
+    int e = 0;
+    if (bound > 0.f && isfinite(bound)) e = max(-60, min(60, ilogbf(240.f / bound)));
+    out[0] = scalbnf(1.f, e);
+  }
+}
+int layernorm_f8c_alpha(const float* w, const float* b, int n, float* alpha_out, cudaStream_t st) {
+  ln_f8c_alpha_kernel<<<1, 256, 0, st>>>(w, b, n, alpha_out);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+static __global__ void f8c_unscale_kernel(const float* a, const float* b, float* o) { o[0] = 1.f / (a[0] * b[0]); }
+int f8c_unscale(const float* alpha, const float* beta, float* out, cudaStream_t st) {
+  f8c_unscale_kernel<<<1, 1, 0, st>>>(alpha, beta, out);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
 int layernorm_planes(const float* x, size_t x_batch_stride, int rows_per_batch, const float* w, const float* b,
-                     Planes out, long long rows, int n, cudaStream_t st) {
-  if (n % 8 || out.ld < n) {
-    set_error("layernorm_planes: n must be a multiple of 8 (n=%d)", n);
+                     Planes out, long long rows, int n, cudaStream_t st, const float* f8alpha) {
+  if (n % 8 || out.ld < n || (f8alpha && (n % 64 || out.ld != n))) {
+    set_error("layernorm_planes: n must be a multiple of 8 (64 with ld == n for f8c planes) (n=%d)", n);
     return VXB_E_BADARG;
   }
   const bool aligned = !(((uintptr_t)w | (uintptr_t)b) & 15);
   if (n == 512 && aligned) {
     layernorm_planes_reg_kernel<2><<<cdiv(rows, 8), 256, 0, st>>>(x, x_batch_stride, rows_per_batch, w, b, out.hi, out.lo,
-                                                                  out.ld, rows);
+                                                                  out.ld, rows, f8alpha);
   } else if (n == 256 && aligned) {
     layernorm_planes_reg_kernel<1><<<cdiv(rows, 8), 256, 0, st>>>(x, x_batch_stride, rows_per_batch, w, b, out.hi, out.lo,
-                                                                  out.ld, rows);
+                                                                  out.ld, rows, f8alpha);
   } else {
     layernorm_planes_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, x_batch_stride, rows_per_batch, w, b, out.hi, out.lo, out.ld,
-                                                          rows, n);
+                                                          rows, n, f8alpha);
   }
   VXB_LAUNCH_CHECK();
   return VXB_OK;
@@ -684,6 +738,7 @@ int linear_planes(const Planes& A, long long M, int K, const Planes& W, int N, c
   p.plan.num_kb = cdiv(K, BK);
   p.ep.N = N; p.ep.row_mode = ROWS_PLAIN;
   p.ep.bias = o.bias; p.ep.alpha = o.alpha; p.ep.act_slope = o.act_slope;
+  p.terms = o.terms; p.ep.alpha_dev = o.alpha_dev;
   p.ep.residual = o.residual; p.ep.res_rows = o.res_rows > 0 ? o.res_rows : 1; p.ep.ldr = o.ldr;
   p.ep.out_f32 = o.out_f32; p.ep.ldc = o.ldc;
   if (o.out_planes) {
@@ -716,9 +771,11 @@ int linear_planes(const Planes& A, long long M, int K, const Planes& W, int N, c
   return gemm(a, nullptr, w, nt, p, st);
 }
 
-int project_vt(const Planes& ctx, int B, int Nk, int K, const Planes& Wv, int inner, const Planes& vt, cudaStream_t st) {
+int project_vt(const Planes& ctx, int B, int Nk, int K, const Planes& Wv, int inner, const Planes& vt, cudaStream_t st,
+               int terms, const float* alpha_dev) {
   Params p;
   params_init(p);
+  p.terms = terms; p.ep.alpha_dev = alpha_dev;
   const int nt = pick_ntile(Nk);
   p.m_tiles = cdiv(inner, BM);
   p.n_tiles = cdiv(Nk, nt);
