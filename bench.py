@@ -42,8 +42,8 @@ VOXELIZE_BYTES = 65536 * 24 + 100 ** 3 * 10 * 4      # 41 572 864 B / sample
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--batch', type=int, default=16, help='samples per GPU')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--math', default=os.environ.get('VXB_MATH', 'auto'), choices=['auto', 'fp32', 'bf16x3', 'f16f8c'])
@@ -235,6 +235,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from voxactb_b200 import QFunction, VoxelGrid, PerceiverVoxelLangEncoder, _lib, synth
+    from voxactb_b200 import distributed as vdist
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -381,10 +382,7 @@ def run_ours(args):
             n = L.vxb_profile_read(buf)
             L.vxb_profile_enable(0)
             stages = {L.vxb_profile_stage_name(i).decode(): buf[i] / max(n, 1) for i in range(len(buf))}
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = vdist.max_over_ranks(ms, dev)          # whole-job time of the step = the slowest rank's device time
         return ms, stages
 
     # voxelize-only timing (HBM-bound kernel of the path), same stream, CUDA events

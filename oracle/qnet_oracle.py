@@ -20,7 +20,7 @@ tolerance rather than bit equality).
 
 Parity pin: no reference test holds golden vectors for this path.
 This restatement is pinned against the reference's own modules, imported live in the
-authoring container (tests/test_oracle_vs_reference.py), and through
+authoring container (tests/test_oracle.py), and through
 tests/golden/*.npz produced by tests/golden/make_golden.py from those modules.
 """
 import math

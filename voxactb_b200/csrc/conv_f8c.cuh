@@ -62,7 +62,7 @@ struct F8Segs {
   uint32_t brow[3];      // first weight row, in descriptor units (rows * 64 B >> 4)
   uint32_t cols[3];      // N of the MMA (64, 128 or 192)
 };
-__device__ __forceinline__ F8Segs f8c_segments(int s2, uint32_t vmask, bool split_first) {
+__device__ __forceinline__ F8Segs f8c_segments(int s2, uint32_t vmask, bool split_first, int dbg = 0) {
   F8Segs sg;
   sg.n = 0;
   int prev = -2;
@@ -70,7 +70,7 @@ __device__ __forceinline__ F8Segs f8c_segments(int s2, uint32_t vmask, bool spli
   for (int j = 0; j < 3; ++j) {                        // j = 0, 1, 2 <-> dz tap index dzc = 2, 1, 0 <-> output plane zi-1, zi, zi+1
     if (!(vmask & (1u << (2 - j)))) continue;
     const int slot = (s2 + j) & 3;
-    if (sg.n > 0 && prev == j - 1 && slot != 0 && !(split_first && j == 2)) {
+    if (sg.n > 0 && prev == j - 1 && (slot != 0 || (dbg & 8)) && !(dbg & 4) && !(split_first && j == 2)) {   // dbg: timing experiments
       sg.cols[sg.n - 1] += 64;
     } else {
       sg.col[sg.n] = (uint32_t)slot * 64u;
@@ -252,8 +252,8 @@ conv3_f8c_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
           if (zo >= z0 && zo < z0 + lz) vmask |= 1u << dzc;
         }
         const int s2 = (zi - 1 - z0) & 3;                       // slot of output plane zi - 1 (dz tap index 2)
-        const F8Segs seg = f8c_segments(s2, vmask, false);
-        const F8Segs seg0 = f8c_segments(s2, vmask, true);      // first step of the plane: the new output plane zi + 1 starts from zero
+        const F8Segs seg = f8c_segments(s2, vmask, false, p.debug_skip);
+        const F8Segs seg0 = f8c_segments(s2, vmask, true, p.debug_skip);      // first step of the plane: the new output plane zi + 1 starts from zero
         for (int cb = 0; cb < p.ncb; ++cb) {
           mbar_wait(&slab_full[sb], sph);
           tc_fence_after();

@@ -1,11 +1,15 @@
-// tcgen05 split-bf16 ("bf16x3") GEMM / implicit-GEMM convolution engine for sm_100a.
+// tcgen05 split-16-bit GEMM / implicit-GEMM convolution engine for sm_100a.
 //
-//   D[M,N] (fp32, TMEM) = A_hi*B_hi + A_hi*B_lo + A_lo*B_hi        (A = A_hi + A_lo, B = B_hi + B_lo)
+//   terms == 3:  D[M,N] (fp32, TMEM) = A_hi*B_hi + A_hi*B_lo + A_lo*B_hi        (A = A_hi + A_lo, B = B_hi + B_lo)
+//   terms == 2:  D = A_hi*B_hi (kind::f16) + [A_lo8 | A_hi8]*[B_hi8 | B_lo8] (one kind::f8f6f4 MMA for both corrections)
+//   terms == 1:  D = A_hi*B_hi
 //
-// Every fp32 operand is stored as two bf16 planes (hi = rn(x), lo = rn(x - hi)): 16 mantissa bits,
-// the same 4 bytes per element as fp32, three kind::f16 MMAs per logical product -- fp32-class
-// accuracy (~2^-16 relative) at 1/3 of the bf16 tensor peak, which is what the 1e-3 Q-value gate
-// needs (single-pass TF32/bf16 miss it).
+// Every fp32 operand is stored as two 16-bit planes (hi = fp16(x), lo = fp16(x - hi), planes16.cuh: 22 significant bits in
+// the same 4 bytes per element as fp32; the containers are typed __nv_bfloat16 for historical reasons).  Three kind::f16
+// MMAs per logical product give fp32-class accuracy (~2^-22 relative per product) at 1/3 of the 16-bit tensor peak, which
+// is what the 1e-3 Q-value gate needs (single-pass TF32 / bf16 miss it).  In the f8c form the "lo"
+// plane holds E4M3 bytes (64-column blocks) and the fp16 planes are pre-scaled so that all products share one scale
+// (un-scaling by Epilogue::alpha_dev).
 //
 // Structure (one persistent CTA per SM, 192 threads):
 //   warp 0      TMA producer: per k-block loads A_hi/A_lo [128 x 64] and B_hi/B_lo [NT x 64] tiles

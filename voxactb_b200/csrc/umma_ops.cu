@@ -97,7 +97,7 @@ split_rows_kernel(const float* __restrict__ x, long long ldx, long long rows, in
   }
 }
 
-// fp32 channels-last [B, V, V, V, C] -> bf16 planes of the replicate-padded grid [B, Vp, Vp, Vp, C], Vp = V + 2*pad
+// fp32 channels-last [B, V, V, V, C] -> 16-bit hi/lo planes of the replicate-padded grid [B, Vp, Vp, Vp, C], Vp = V + 2*pad
 static __global__ void __launch_bounds__(256)
 pad_split_kernel(const float* __restrict__ x, int B, int V, int pad, int C,
                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
@@ -124,7 +124,7 @@ pad_split_kernel(const float* __restrict__ x, int B, int V, int pad, int C,
   }
 }
 
-// replicate-fill the halo of padded bf16 planes in place: every halo voxel copies its nearest interior voxel.
+// replicate-fill the halo of padded 16-bit planes in place: every halo voxel copies its nearest interior voxel.
 // Only the halo voxels are enumerated (two full z planes + the border ring of every other plane), pad = 1 fast path.
 static __global__ void __launch_bounds__(256)
 halo_fill_kernel(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, __nv_bfloat16* __restrict__ third, int B, int V, int pad, int C) {
@@ -484,7 +484,7 @@ int gemm(const Operand& A0, const Operand* A1, const Operand& W, int n_tile, Par
 }  // namespace vxb
 
 // ========================================================================================== fp32-in / fp32-out wrappers
-// (operands are split into bf16 planes in `scratch`; weights may come pre-split from vxb_qnet_prepare)
+// (operands are split into 16-bit hi/lo planes in `scratch`; weights may come pre-split from vxb_qnet_prepare)
 namespace vxb {
 namespace umma {
 
