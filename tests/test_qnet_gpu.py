@@ -196,6 +196,30 @@ def test_full_size_tensor_core_path_matches_fp32_path(cuda_lib):
     assert torch.equal(t0.reshape(2, -1).argmax(-1), t1.reshape(2, -1).argmax(-1))
 
 
+@pytest.mark.parametrize('rgb_scale,weight_scale', [(1.0, 1.0), (127.0, 1.0), (1e-3, 1.0), (1.0, 8.0), (1.0, 0.05)])
+def test_f16_fp8_mode_tracks_the_scale_of_its_operands(cuda_lib, rgb_scale, weight_scale):
+    """VXB_MATH_F16F8C derives its E4M3 scales on the device from bounds of d0 / u0 and from the weights: un-normalised RGB
+    (0..255-like features), tiny features, and final-conv / up-conv weights far from He scale must not cost accuracy against the
+    library's own fp32 FFMA mode on the same inputs."""
+    c = dict(make_golden.QNET_CASES['qnet_v20'])
+    obs, enc, sd = util.make_case(c)
+    obs = dict(obs, rgb=[t * rgb_scale for t in obs['rgb']])
+    with torch.no_grad():
+        for name, p in enc.named_parameters():
+            if name.startswith(('final.conv3d.weight', 'up0.conv_up.2.conv3d.weight', 'input_preprocess.conv3d.weight')):
+                p.mul_(weight_scale)
+    _, (t0, r0, c0, _) = run_qfunction(c, obs, enc, _lib.MATH_FP32_SIMT)
+    t0, r0, c0 = t0.clone(), r0.clone(), c0.clone()
+    _, (t1, r1, c1, _) = run_qfunction(c, obs, enc, _lib.MATH_BF16X3)
+    t1, r1, c1 = t1.clone(), r1.clone(), c1.clone()
+    _, (t2, r2, c2, _) = run_qfunction(c, obs, enc, _lib.MATH_F16F8C)
+    assert torch.isfinite(t2).all() and torch.isfinite(r2).all()
+    for a, b3, b in ((t2, t1, t0), (r2, r1, r0), (c2, c1, c0)):
+        # within the gate, and not materially worse than the three-term split on the same inputs
+        assert util.rel_err(a, b) < util.Q_REL_TOL
+        assert util.rel_err(a, b) < 3.0 * util.rel_err(b3, b) + 2e-4
+
+
 def test_dual_agent_acting_and_stabilizing_share_observations(cuda_lib):
     """BASELINE config 3 shape of use: two encoders (low_dim 7, arm head; different weights) evaluated alternately
     on the same observation batch.  Each must match the oracle run with ITS weights -- no state leaks between the
