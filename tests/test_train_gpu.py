@@ -27,7 +27,8 @@ import make_golden
 pytestmark = pytest.mark.gpu
 
 GRAD_TOL = {_lib.MATH_FP32_SIMT: 3e-3, _lib.MATH_BF16X3: 3e-2}          # full loss, nearer reference
-TRANS_ONLY_TOL = {_lib.MATH_FP32_SIMT: 2e-4, _lib.MATH_BF16X3: 5e-3}    # translation loss only, float64 oracle
+TRANS_ONLY_TOL = {_lib.MATH_FP32_SIMT: 3e-4, _lib.MATH_BF16X3: 5e-3}    # translation loss only, float64 oracle (fp32 atomics: the
+#                                                                         bias column sums vary by ~1e-4 of their maximum run to run)
 
 
 def make_train_case(c, mode, dropout=False):

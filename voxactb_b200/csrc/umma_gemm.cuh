@@ -272,9 +272,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
         const int z = tile / tiles_per_z, tz = tile % tiles_per_z;
         const int zb = z / p.Hz, zh = z % p.Hz;
         const int mt = tz / p.n_tiles, nt = tz % p.n_tiles;
-        const int m0 = mt * BM + zb * p.a_row_zb + zh * p.a_row_zh + p.a_row_off;
-        const int n0 = nt * NT + zb * p.w_row_zb + zh * p.w_row_zh;
-        for (int kb = 0; kb < pl.num_kb; ++kb) {
+        int m0 = mt * BM + zb * p.a_row_zb + zh * p.a_row_zh + p.a_row_off;
+        int n0 = nt * NT + zb * p.w_row_zb + zh * p.w_row_zh;
+        int tap_col = 0, tap_rot = 0;
+        if (p.tap_m) { m0 -= mt * BM; tap_col = p.tap_acol[mt]; n0 += p.tap_wrow[mt]; tap_rot = p.tap_rot[mt]; }
+        for (int kb0 = 0; kb0 < pl.num_kb; ++kb0) {
+          int kb = kb0 + tap_rot;
+          if (kb >= pl.num_kb) kb -= pl.num_kb;
           int a_row = 0, a_col = kb * BK, a_src = 0;
           if (pl.taps) {
             const int tap = kb / pl.cpb, cb = kb - tap * pl.cpb;
@@ -284,22 +288,27 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
             a_src = cb >= pl.cb_src0;
             a_col = (a_src ? cb - pl.cb_src0 : cb) * BK;
           }
-          a_col += zh * p.a_col_zh + (int)p.a_col_off;
-          const int w_col = kb * BK + zh * p.w_col_zh + (int)p.w_col_off;
+          a_col += zh * p.a_col_zh + (int)p.a_col_off + tap_col;
+          int w_col = kb * BK + zh * p.w_col_zh + (int)p.w_col_off;
+          int a_rowk = 0, w_rowk = 0;
+          if (p.kblk_a) {            // K-blocked storage: the K block index selects a group of rows, columns 0..63 (offsets are multiples of 64)
+            a_rowk = (a_col / BK) * p.kblk_a; a_col = 0;
+            w_rowk = (w_col / BK) * p.kblk_w; w_col = 0;
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = smem + stage * L::STAGE_BYTES;
           const CUtensorMap* ah = a_src ? &mapA1h : &mapA0h;
           const CUtensorMap* al = a_src ? &mapA1l : &mapA0l;
           if (p.terms == 1) {
             mbar_expect_tx(&full_bar[stage], L::A_BYTES + L::B_BYTES);
-            tma_load_2d(ah, &full_bar[stage], s, a_col, m0 + a_row);
-            tma_load_2d(&mapWh, &full_bar[stage], s + 2 * L::A_BYTES, w_col, n0);
+            tma_load_2d(ah, &full_bar[stage], s, a_col, m0 + a_row + a_rowk);
+            tma_load_2d(&mapWh, &full_bar[stage], s + 2 * L::A_BYTES, w_col, n0 + w_rowk);
           } else {
             mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-            tma_load_2d(ah, &full_bar[stage], s, a_col, m0 + a_row);
-            tma_load_2d(al, &full_bar[stage], s + L::A_BYTES, a_col, m0 + a_row);
-            tma_load_2d(&mapWh, &full_bar[stage], s + 2 * L::A_BYTES, w_col, n0);
-            tma_load_2d(&mapWl, &full_bar[stage], s + 2 * L::A_BYTES + L::B_BYTES, w_col, n0);
+            tma_load_2d(ah, &full_bar[stage], s, a_col, m0 + a_row + a_rowk);
+            tma_load_2d(al, &full_bar[stage], s + L::A_BYTES, a_col, m0 + a_row + a_rowk);
+            tma_load_2d(&mapWh, &full_bar[stage], s + 2 * L::A_BYTES, w_col, n0 + w_rowk);
+            tma_load_2d(&mapWl, &full_bar[stage], s + 2 * L::A_BYTES + L::B_BYTES, w_col, n0 + w_rowk);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }

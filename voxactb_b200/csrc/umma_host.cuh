@@ -74,6 +74,19 @@ struct Params {
                                  // 2 = fp16 hi*hi + one E4M3 MMA on the "lo" planes (c8 layout, 64-channel blocks)
   long long rs_zb, rs_zh;        // row statistic element offsets per zb / zh
   int w_row_zb, w_row_zh, w_col_zh;
+  // tap_m != 0 (convolution weight gradients): every M tile multiplies the SAME A rows at its own K offset against its own W
+  // rows -- M tile t reads A columns shifted by tap_acol[t] and W rows tap_wrow[t]..; its output rows are t * BM.. as usual.
+  // All taps of one K chunk are adjacent in the tile order, so the chunk is fetched from HBM once and re-read from L2.
+  // tap_rot[t]: M tile t walks its K blocks rotated by that many blocks (sum order is free), chosen so that ALL taps read the
+  // same A columns at the same time -- the A chunk then comes from HBM once and from L2 26 times.
+  // kblk_a / kblk_w != 0: K-blocked operand storage [K / 64][rows][64] (a K block of all rows is one contiguous 16 KB box; the
+  // plain [rows][K] layout of a 17M-column operand puts every row of a TMA box into its own 2 MB page: the weight-gradient GEMM
+  // ran at 15 % tensor-pipe activity with DRAM at 14 % -- translation-bound).  Values = rows per K block of A / W.
+  int kblk_a, kblk_w;
+  int tap_m;
+  int tap_acol[27];
+  int tap_wrow[27];
+  int tap_rot[27];
   long long c_zb, c_zh;          // fp32 output element offsets per zb / zh
   long long p_zb, p_zh;          // plane output element offsets per zb / zh
   Epilogue ep;
