@@ -444,7 +444,7 @@ static int project_kv(Ctx& cx, Work& w, const umma::Planes& ctx, int B, int Nk, 
 }
 
 static int transformer_planes(Ctx& cx, const vxb_qnet_desc* d, const Dims& m, const void* const* params,
-                              const Prepared& pw, Work& w, int B, bool f8c) {
+                              const Prepared& pw, Work& w, int B, int f8c /* bit 0: q / k / v projections, bit 1: FF net.0 */) {
   auto P = [&](int slot) { return (const float*)params[slot]; };
   auto PL = [&](int layer, int slot) {
     return (const float*)params[VXB_P_FIXED_COUNT + layer * VXB_P_LAYER_STRIDE + slot];
@@ -494,7 +494,8 @@ static int transformer_planes(Ctx& cx, const vxb_qnet_desc* d, const Dims& m, co
     for (int l = 0; l < m.depth; ++l) {
       // VXB_MATH_F16F8C: the LayerNorm-fed GEMMs (q, k, v, FF net.0: 69 % of the layer's linear FLOPs) run as fp16 hi*hi + one
       // E4M3 MMA; LayerNorm outputs are bounded by sqrt(D - 1) max|gamma| + max|beta|, so every scale is fixed at prepare time
-      const Prepared::LayerF8* f8 = (f8c && l < (int)pw.lf8.size()) ? &pw.lf8[l] : nullptr;
+      const Prepared::LayerF8* f8 = ((f8c & 1) && l < (int)pw.lf8.size()) ? &pw.lf8[l] : nullptr;
+      const Prepared::LayerF8* f8ff = ((f8c & 2) && l < (int)pw.lf8.size()) ? &pw.lf8[l] : nullptr;
       const umma::Planes xn = planes_of(w.px, m.D);
       umma::Planes ql = planes_of(w.pq, lq);
       WPLANES(Wq, PL(l, VXB_PL_Q_W));
@@ -517,7 +518,7 @@ static int transformer_planes(Ctx& cx, const vxb_qnet_desc* d, const Dims& m, co
       ++g_launches;
       VXB_TRY(umma::linear_planes(pol, rowsL, lq, *Wo, m.D, oo, st));
       VXB_TRY(feed_forward_planes(cx, m, B, w, PL(l, VXB_PL_FF_NORM_W), PL(l, VXB_PL_FF_NORM_B), PL(l, VXB_PL_FF0_W),
-                                  pw.ff_perm_b + (size_t)(l + 1) * 8 * m.D, PL(l, VXB_PL_FF2_W), PL(l, VXB_PL_FF2_B), f8));
+                                  pw.ff_perm_b + (size_t)(l + 1) * 8 * m.D, PL(l, VXB_PL_FF2_W), PL(l, VXB_PL_FF2_B), f8ff));
     }
   }
   return VXB_OK;
@@ -769,10 +770,10 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   if (planes_path) {
     // fp16 + E4M3 for the LayerNorm-fed transformer GEMMs is built but OFF by default: measured -0.53 ms of 9.7 (B=16), but the
     // rotation / collision heads move from 1.5e-4 .. 4.7e-4 to 2.2e-4 .. 9.6e-4 of the reference goldens (tools/report_errors.py,
-    // DESIGN.md section 4) -- too close to the 1e-3 gate.  VXB_TRANSFORMER_F8C=1 enables it for experiments.
+    // DESIGN.md section 4) -- too close to the 1e-3 gate.  VXB_TRANSFORMER_F8C=<mask> enables it for experiments (1: q / k / v, 2: FF net.0).
     static int tf8 = -1;
     if (tf8 < 0) { const char* e = getenv("VXB_TRANSFORMER_F8C"); tf8 = e ? atoi(e) : 0; }
-    VXB_TRY(transformer_planes(cx, d, m, params, pw, w, B, f8c && tf8));
+    VXB_TRY(transformer_planes(cx, d, m, params, pw, w, B, f8c ? tf8 : 0));
     STAGE_MARK();  // 5: decoder cross attention + ss1
     VXB_TRY(decoder_planes(cx, m, params, w, B));
   } else {
