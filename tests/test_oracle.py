@@ -108,6 +108,34 @@ def test_state_dict_keys_match_reference():
 
 
 @needs_ref
+def test_weight_tied_encoder_matches_the_reference_class_and_the_oracle():
+    """weight_tie_layers=True (perceiver_lang_io.py:263-276, cache_fn): same state-dict keys as the reference class, every
+    layers.<i> entry aliasing layers.0; the oracle run on that state dict equals the reference forward."""
+    _, RefEnc = refimport.load()
+    from voxactb_b200 import PerceiverVoxelLangEncoder
+    c = dict(make_golden.QNET_CASES['qnet_v20'], depth=3)
+    kw = dict(make_golden.encoder_kwargs(c), weight_tie_layers=True)
+    ref, ours = RefEnc(**kw).eval(), PerceiverVoxelLangEncoder(**kw).eval()
+    assert sorted(ref.state_dict().keys()) == sorted(ours.state_dict().keys())
+    sd = synth.random_state_dict(ref, 91)
+    ref.load_state_dict(sd, strict=False)
+    ours.load_state_dict(sd, strict=False)
+    got = ours.state_dict()
+    for k, v in ref.state_dict().items():
+        if not k.endswith(('pos_x', 'pos_y', 'pos_z')):
+            assert torch.equal(v, got[k]), k
+    assert got['layers.2.1.fn.net.0.weight'].data_ptr() == got['layers.0.1.fn.net.0.weight'].data_ptr()
+    obs = synth.make_observation(c['seed'], c['B'], c['cameras'], c['H'], c['W'], low_dim=c['low_dim'])
+    coords, feats = synth.flatten_cameras(obs)
+    grid = torch.from_numpy(voxel_oracle.voxelize(coords.numpy(), feats.numpy(), obs['bounds'].numpy(), c['V'])).permute(0, 4, 1, 2, 3)
+    with torch.no_grad():
+        want = ref(grid, obs['proprio'], obs['lang_goal_emb'], obs['lang_token_embs'], None, obs['bounds'], None)
+        have = qnet_oracle.qnet_forward(dict(ref.state_dict()), util.oracle_cfg(c), grid, obs['proprio'], obs['lang_token_embs'])
+    for w, k in zip(want[:3], ('trans', 'rot_grip', 'collision')):
+        assert util.rel_err(have[k], w) < 2e-5, k
+
+
+@needs_ref
 def test_voxel_oracle_vs_live_reference():
     RefVG, _ = refimport.load()
     for seed, V, crop in ((5, 16, False), (6, 24, True)):

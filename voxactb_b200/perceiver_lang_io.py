@@ -186,8 +186,6 @@ class PerceiverVoxelLangEncoder(nn.Module):
             unsupported.append('pos_encoding_with_lang=False')
         if no_skip_connection or no_perceiver:
             unsupported.append('no_skip_connection/no_perceiver ablations')
-        if weight_tie_layers:
-            unsupported.append('weight_tie_layers=True')
         if activation not in ('lrelu', 'relu'):
             unsupported.append('activation=%r' % activation)
         if num_rotation_classes <= 0:
@@ -245,7 +243,13 @@ class PerceiverVoxelLangEncoder(nn.Module):
         reg('cross_attend_blocks.0.norm_context.weight', torch.ones(C))
         reg('cross_attend_blocks.0.norm_context.bias', torch.zeros(C))
         feedforward('cross_attend_blocks.1', D)
+        self.weight_tie_layers = bool(weight_tie_layers)
         for i in range(depth):
+            if weight_tie_layers and i > 0:
+                # reference perceiver_lang_io.py:263-276 (cache_fn): every latent layer IS the first layer's modules -- the
+                # state dict carries layers.<i>.* keys for all i, aliasing the same tensors
+                self._modules['layers'].add_module(str(i), self._modules['layers']._modules['0'])
+                continue
             attention('layers.%d.0' % i, D, D, latent_heads, latent_dim_head)
             feedforward('layers.%d.1' % i, D)
         attention('decoder_cross_attn', C, D, cross_heads, cross_dim_head)
@@ -360,7 +364,7 @@ class PerceiverVoxelLangEncoder(nn.Module):
         return d
 
     def _param_table(self):
-        named = dict(self.named_parameters())
+        named = dict(self.named_parameters(remove_duplicate=False))       # weight_tie_layers: layers.<i> alias layers.0
         names = list(_FIXED_SLOTS)
         if self.TWO_ROBOTS:
             names = [_TWO_ROBOT_SLOTS.get(i, n) for i, n in enumerate(names)]
@@ -417,6 +421,9 @@ class PerceiverVoxelLangEncoder(nn.Module):
             # training step (row a18): one autograd node around vxb_qnet_forward_train_f32 / vxb_qnet_backward_f32
             if self.TWO_ROBOTS:
                 raise NotImplementedError('the 2-robot encoder is inference-only in voxactb_b200 (training: single-arm encoders)')
+            if self.weight_tie_layers and self.depth > 1:
+                raise NotImplementedError('weight_tie_layers=True is inference-only in voxactb_b200 (the backward writes one '
+                                          'gradient buffer per layer slot; tied layers would need their sum)')
             grid = _lib.f32(ins.detach().permute(0, 2, 3, 4, 1))
             plist = [p for p in self._param_table()[2] if p is not None]
             outs = _QnetTrainFn.apply(self, grid, _lib.f32(proprio.detach()), _lib.f32(lang_token_embs.detach()), *plist)
