@@ -640,7 +640,7 @@ def run_train(args):
         'metric': 'training samples/sec at 100^3 voxels (fwd + loss + bwd + NCCL grad all-reduce + %s)' % args.optimizer.upper(),
         'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32' if math_mode == _lib.MATH_FP32_SIMT else 'f16x3 forward contractions (split-fp16 tcgen05), fp32 FFMA backward',
+        'dtype': 'f32' if math_mode == _lib.MATH_FP32_SIMT else 'f16x3 (split-fp16 tcgen05: forward incl. fused attention with dropout, conv / linear dgrad + wgrad); attention backward fp32 FFMA',
         'data': 'synthetic',
         'config': {'workload': 'BASELINE config 5: batch=%d/GPU, 100^3 voxels, 4 cameras 128x128 RGB-D, training step (train-mode '
                                'dropout 0.1, CE losses, backward, gradient all-reduce over NCCL, %s)' % (B, args.optimizer.upper()),

@@ -232,13 +232,7 @@ inline int layernorm_bwd(const float* gy, const float* x, size_t x_batch_stride,
 // ------------------------------------------------------------------------------------------------ attention
 // counter-based dropout mask (train-mode nn.Dropout on the attention probabilities, perceiver_lang_io.py:127-128): element
 // `idx` of stream `seed` is kept when its hashed 32-bit value >= p * 2^32.  Recomputed (never stored) in the backward.
-__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long idx, unsigned int thresh) {
-  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (unsigned int)(z >> 32) >= thresh;
-}
+// (dropout_keep itself lives in common.cuh: the fused attention kernel of the training forward applies the same mask)
 inline unsigned int dropout_threshold(float p) {
   const double t = (double)p * 4294967296.0;
   return t >= 4294967295.0 ? 0xffffffffu : (unsigned int)t;

@@ -71,6 +71,17 @@ struct Arena {
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
+// counter-based dropout mask of the attention probabilities (train mode, perceiver_lang_io.py:127-128): element `idx` of stream
+// `seed` is kept when its hashed 32-bit value >= p * 2^32.  idx = flat index into the [B*H*Nq, ld] probability matrix
+// (ld = Nk rounded up to 4).  Never stored: the forward (flash_umma.cuh / bwd_ops.cuh) and the backward regenerate it.
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long idx, unsigned int thresh) {
+  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (unsigned int)(z >> 32) >= thresh;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

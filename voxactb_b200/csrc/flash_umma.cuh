@@ -36,6 +36,12 @@ struct FlashParams {
   __nv_bfloat16* out_hi;    // O planes [B*Nq, ldo]
   __nv_bfloat16* out_lo;
   long long ldo;
+  // train-mode dropout on the probabilities (0 = off): P_ij is multiplied by keep_ij / (1 - p) AFTER the row sum, exactly
+  // softmax -> dropout -> @ v of the reference (perceiver_lang_io.py:124-130); mask = dropout_keep(seed, row * ld + j)
+  unsigned int drop_thresh;
+  float drop_inv_keep;
+  unsigned long long drop_seed;
+  int drop_ld;
 };
 
 __global__ void __launch_bounds__(FA_THREADS, 1)
@@ -231,8 +237,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
           // The softmax warps are issue-bound (two warps per scheduler): everything runs on register PAIRS with the
           // packed fp32 instructions (FADD2 / FFMA2), and the key mask only exists in the ragged last tile.
           const float2 alpha2 = make_float2(p.alpha, p.alpha), bias2 = make_float2(bias, bias), neg1 = make_float2(-1.f, -1.f);
-          auto chunk = [&](auto masked_tag) {
+          const unsigned long long drop_row = ((unsigned long long)bh * p.Nq + (unsigned long long)qi) * (unsigned long long)p.drop_ld;
+          auto chunk = [&](auto masked_tag, auto drop_tag) {
             constexpr bool kMasked = decltype(masked_tag)::value;
+            constexpr bool kDrop = decltype(drop_tag)::value;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint32_t* hp = phv + cc * 16 + g * 4;
@@ -249,6 +257,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
                   t.y = (key0 + cc * 32 + jj + 1 < p.Nk) ? t.y : 0.f;
                 }
                 rs2 = __fadd2_rn(rs2, t);
+                if constexpr (kDrop) {
+                  const unsigned long long kc = drop_row + (unsigned long long)(key0 + cc * 32 + jj);
+                  t.x = dropout_keep(p.drop_seed, kc, p.drop_thresh) ? t.x * p.drop_inv_keep : 0.f;
+                  t.y = dropout_keep(p.drop_seed, kc + 1ull, p.drop_thresh) ? t.y * p.drop_inv_keep : 0.f;
+                }
                 const __nv_bfloat162 hh = pl2_from_floats(t.x, t.y);
                 const float2 lo2 = __ffma2_rn(pl2_to_float2(hh), neg1, t);      // t - float(hi), exact
                 const __nv_bfloat162 ll = pl2_from_floats(lo2.x, lo2.y);
@@ -257,8 +270,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_consta
               }
             }
           };
-          if (key0 + cc * 32 + 31 < p.Nk) chunk(std::false_type{});
-          else chunk(std::true_type{});
+          if (p.drop_thresh) {                                   // training forward only (uniform branch)
+            if (key0 + cc * 32 + 31 < p.Nk) chunk(std::false_type{}, std::true_type{});
+            else chunk(std::true_type{}, std::true_type{});
+          } else {
+            if (key0 + cc * 32 + 31 < p.Nk) chunk(std::false_type{}, std::false_type{});
+            else chunk(std::true_type{}, std::false_type{});
+          }
         }
         // P -> tensor memory (the A operand of the PV MMAs): lane = query row, two keys per 32-bit column
         mbar_wait(&p_empty[sb], ((it >> 1) & 1u) ^ 1u);        // PV of this group's previous tile has consumed the P buffer

@@ -61,6 +61,10 @@ static size_t train_tc_scratch_bytes(const Dims& m, int B) {
   sb = std::max(sb, umma::conv_dgrad_scratch_bytes(B, m.V, 64, 128, 3));
   sb = std::max(sb, umma::conv_dgrad_scratch_bytes(B, m.S, m.s * m.s * m.s * 64, 64, 3));
   sb = std::max(sb, umma::conv_dgrad_scratch_bytes(B, m.S, 64, m.C, m.k));
+  // forward attention through the fused tensor-core kernel (operand planes of q / k / v^T, O planes)
+  sb = std::max(sb, umma::attention_f32_scratch_bytes(B, m.lh, m.L, m.L, m.ldh));
+  sb = std::max(sb, umma::attention_f32_scratch_bytes(B, m.ch, m.L, m.n, m.cdh));
+  sb = std::max(sb, umma::attention_f32_scratch_bytes(B, m.ch, m.T, m.L, m.cdh));
   return sb + 8192;
 }
 
@@ -186,8 +190,16 @@ static bwd::AttnDropout layer_dropout(const TrainDropout& d, int block /*0 = cro
 // attention forward with materialised probabilities + train-mode dropout on them (simA is the probability buffer)
 static int attention_train(const float* q, int ldq, long long qbs, const float* k, const float* v, int ldkv, long long kvbs,
                            float* out, int ldo, long long obs, int B, int H, int Nq, int Nk, int dh, float scale, float* sim,
-                           const bwd::AttnDropout& dr, cudaStream_t st) {
+                           const bwd::AttnDropout& dr, cudaStream_t st, Arena* tc = nullptr) {
   const int Nkp = (Nk + 3) / 4 * 4;
+  if (tc && dh == 64) {
+    // tensor-core forward: the fused attention kernel of the inference path with the dropout mask applied to P in its softmax
+    // warps (the probabilities are recomputed by the backward anyway): 42 ms of FFMA GEMMs + softmax + dropout passes -> ~6 ms
+    Arena local(tc->base, tc->cap);
+    umma::AttnDrop ad{dr.seed, dr.p > 0.f ? bwd::dropout_threshold(dr.p) : 0u, dr.p > 0.f ? 1.f / (1.f - dr.p) : 1.f, Nkp};
+    const int rc = umma::attention_f32(q, ldq, qbs, k, v, ldkv, kvbs, out, ldo, obs, B, H, Nq, Nk, dh, scale, local, st, &ad);
+    if (rc != VXB_E_WORKSPACE_TOO_SMALL) return rc;
+  }
   GemmParams p;
   gemm_params_init(p);
   p.M = Nq; p.N = Nk; p.K = dh;
@@ -244,6 +256,8 @@ static int qnet_forward_train_impl(const vxb_qnet_desc* d, const Dims& m, const 
   assemble_tokens_kernel<<<148 * 8, 256, 0, st>>>(w.lang_lin, w.patch, w.pfeat, nullptr, P(VXB_P_POS_ENCODING), w.ins, B, m.nl,
                                                   m.T, m.C, 64);
   VXB_LAUNCH_CHECK();
+  Arena tc_arena(t.tc_scratch, t.tc_scratch_bytes);
+  Arena* tcp = (mm == VXB_MATH_BF16X3 && t.tc_scratch) ? &tc_arena : nullptr;      // tensor-core attention forward
   // (4) encoder cross attention block                                                              :431-432
   {
     BlockSaved& s = t.blk[0];
@@ -252,7 +266,7 @@ static int qnet_forward_train_impl(const vxb_qnet_desc* d, const Dims& m, const 
                 -1.f, mm));
     VXB_TRY(attention_train(pw.q_cross, cq, 0, w.kv_c, w.kv_c + cq, 2 * cq, (long long)m.n * 2 * cq, s.att, cq,
                             (long long)m.L * cq, B, m.ch, m.L, m.n, m.cdh, 1.f / sqrtf((float)m.cdh), t.simA,
-                            layer_dropout(drop, 0), st));
+                            layer_dropout(drop, 0), st, tcp));
     VXB_TRY(lin(cx, s.att, cq, P(VXB_P_CROSS_OUT_W), cq, P(VXB_P_CROSS_OUT_B), P(VXB_P_LATENTS), m.L, m.D, s.x_mid, m.D,
                 rowsL, m.D, cq, 1.f, -1.f, mm));
     VXB_TRY(layernorm(s.x_mid, P(VXB_P_CROSS_FF_NORM_W), P(VXB_P_CROSS_FF_NORM_B), s.xn_f, (size_t)rowsL, m.D, st));
@@ -273,7 +287,7 @@ static int qnet_forward_train_impl(const vxb_qnet_desc* d, const Dims& m, const 
                 mm));
     VXB_TRY(attention_train(s.q, lq, (long long)m.L * lq, s.kv, s.kv + lq, 2 * lq, (long long)m.L * 2 * lq, s.att, lq,
                             (long long)m.L * lq, B, m.lh, m.L, m.L, m.ldh, 1.f / sqrtf((float)m.ldh), t.simA,
-                            layer_dropout(drop, l + 1), st));
+                            layer_dropout(drop, l + 1), st, tcp));
     VXB_TRY(lin(cx, s.att, lq, PL(l, VXB_PL_OUT_W), lq, PL(l, VXB_PL_OUT_B), s.x_in, rowsL, m.D, s.x_mid, m.D, rowsL, m.D, lq,
                 1.f, -1.f, mm));
     VXB_TRY(layernorm(s.x_mid, PL(l, VXB_PL_FF_NORM_W), PL(l, VXB_PL_FF_NORM_B), s.xn_f, (size_t)rowsL, m.D, st));
@@ -293,7 +307,7 @@ static int qnet_forward_train_impl(const vxb_qnet_desc* d, const Dims& m, const 
               mm));
   VXB_TRY(attention_train(t.qd, cq, (long long)m.T * cq, t.kv_d, t.kv_d + cq, 2 * cq, (long long)m.L * 2 * cq, t.att_d, cq,
                           (long long)m.T * cq, B, m.ch, m.T, m.L, m.cdh, 1.f / sqrtf((float)m.cdh), t.simA,
-                          layer_dropout(drop, -1), st));
+                          layer_dropout(drop, -1), st, tcp));
   VXB_TRY(lin(cx, t.att_d, cq, P(VXB_P_DEC_OUT_W), cq, P(VXB_P_DEC_OUT_B), nullptr, 1, 0, w.dec, m.C, B * m.T, m.C, cq, 1.f,
               -1.f, mm));
   // (7) ss1 / max1                                                                                  :451

@@ -193,9 +193,11 @@ int project_vt(const Planes& ctx, int B, int Nk, int K, const Planes& Wv, int in
 // softmax(scale q k^T) v per (batch, head) as three tcgen05 GEMMs (row max, exp + row sum -> P planes, P V / sum).
 // Q [(B or 1)*Nq, H*dh] (q_batched = 0: one Q shared by all batches), K [B*Nk, H*dh], Vt [B*H*dh, pad8(Nk)],
 // P scratch planes [B*H*Nq, pad8(Nk)], O planes [B*Nq, H*dh]; rowmax / rowsum: B*H*Nq floats each.
+// drop (training forward): softmax -> dropout -> @ v with the counter-based mask of common.cuh dropout_keep
+struct AttnDrop { unsigned long long seed; unsigned int thresh; float inv_keep; int ld; };
 int attention_planes(const Planes& Q, int q_batched, const Planes& K, const Planes& Vt, int B, int H, int Nq, int Nk,
                      int dh, float scale, float* rowmax, float* rowsum, const Planes& P, const Planes& O,
-                     cudaStream_t st);
+                     cudaStream_t st, const AttnDrop* drop = nullptr);
 
 // ---- input-stationary 3x3x3 convolution (conv_umma.cuh), Co = 64, channels a multiple of 32
 // weights: tap-major fp32 [64][27][C0+C1] -> bf16 [ncb][27][{hi,lo}][64][32]
@@ -253,7 +255,7 @@ int patchify_f32(const float* x, const __nv_bfloat16* wc, const float* bias, flo
 size_t attention_f32_scratch_bytes(int B, int H, int Nq, int Nk, int dh);
 int attention_f32(const float* q, int ldq, long long qbs, const float* k, const float* v, int ldkv, long long kvbs,
                   float* out, int ldo, long long obs, int B, int H, int Nq, int Nk, int dh, float scale, Arena& scratch,
-                  cudaStream_t st);
+                  cudaStream_t st, const AttnDrop* drop = nullptr);
 
 inline void params_init(Params& p) {
   memset(&p, 0, sizeof(p));

@@ -793,7 +793,7 @@ int project_vt(const Planes& ctx, int B, int Nk, int K, const Planes& Wv, int in
 
 int attention_planes(const Planes& Q, int q_batched, const Planes& K, const Planes& Vt, int B, int H, int Nq, int Nk,
                      int dh, float scale, float* rowmax, float* rowsum, const Planes& P, const Planes& O,
-                     cudaStream_t st) {
+                     cudaStream_t st, const AttnDrop* drop) {
   if (dh != 64) {
     set_error("attention_planes: dim_head must be 64 (got %d)", dh);
     return VXB_E_UNSUPPORTED_SHAPE;
@@ -833,6 +833,7 @@ int attention_planes(const Planes& Q, int q_batched, const Planes& K, const Plan
     f.alpha = scale * 1.4426950408889634f;
     f.rowmax = rowmax;
     f.out_hi = O.hi; f.out_lo = O.lo; f.ldo = O.ld;
+    if (drop && drop->thresh) { f.drop_thresh = drop->thresh; f.drop_inv_keep = drop->inv_keep; f.drop_seed = drop->seed; f.drop_ld = drop->ld; }
     CUtensorMap maps[6];
     VXB_TRY(make_map(&maps[0], Q.hi, q.rows, q.cols, Q.ld, 128));
     VXB_TRY(make_map(&maps[1], Q.lo, q.rows, q.cols, Q.ld, 128));
@@ -852,6 +853,10 @@ int attention_planes(const Planes& Q, int q_batched, const Planes& K, const Plan
     flash_attn_kernel<<<std::min(f.items, sms), FA_THREADS, FA_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], f);
     VXB_LAUNCH_CHECK();
     return VXB_OK;
+  }
+  if (drop && drop->thresh) {
+    set_error("attention_planes: dropout needs the fused attention kernel (VXB_ATTN=gemm selects the three-GEMM form)");
+    return VXB_E_UNSUPPORTED_SHAPE;
   }
   // (2) P = 2^(s - max) as planes, row sums
   Params p2 = p;
@@ -927,7 +932,7 @@ size_t attention_f32_scratch_bytes(int B, int H, int Nq, int Nk, int dh) {
 }
 int attention_f32(const float* q, int ldq, long long qbs, const float* k, const float* v, int ldkv, long long kvbs,
                   float* out, int ldo, long long obs, int B, int H, int Nq, int Nk, int dh, float scale, Arena& scratch,
-                  cudaStream_t st) {
+                  cudaStream_t st, const AttnDrop* drop) {
   AttnScratch s;
   carve_attn(scratch, B, H, Nq, Nk, dh, s);
   if (!scratch.ok) {
@@ -941,7 +946,7 @@ int attention_f32(const float* q, int ldq, long long qbs, const float* k, const 
   VXB_CUDA(cudaMemsetAsync(s.vt.lo, 0, plane_elems((long long)B * inner, s.vt.ld) * 2, st));
   split_gather_kernel<<<148 * 4, 256, 0, st>>>(v, ldkv, kvbs, B, Nk, inner, s.vt.hi, s.vt.lo, s.vt.ld, 1);
   VXB_LAUNCH_CHECK();
-  VXB_TRY(attention_planes(s.q, 1, s.k, s.vt, B, H, Nq, Nk, dh, scale, s.rmax, s.rsum, s.p, s.o, st));
+  VXB_TRY(attention_planes(s.q, 1, s.k, s.vt, B, H, Nq, Nk, dh, scale, s.rmax, s.rsum, s.p, s.o, st, drop));
   merge_planes_kernel<<<148 * 4, 256, 0, st>>>(s.o.hi, s.o.lo, s.o.ld, B, Nq, inner, out, ldo, obs);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
