@@ -97,7 +97,13 @@ typedef struct vxb_qnet_desc {
   int32_t no_language;      /* 1: language tokens zeroed (perceiver_lang_io.py:376-378) */
   float   act_slope;        /* 0.02 for 'lrelu', 0 for 'relu' */
   int32_t math_mode;        /* VXB_MATH_* */
+  int32_t final_input;      /* input of the final 3x3x3 convolution (perceiver_lang_io.py:456-462): VXB_FINAL_CAT = cat[d0, u0]
+                             * (128 channels, the default), VXB_FINAL_U0 = u0 only (no_skip_connection), VXB_FINAL_D0 = d0 only
+                             * (no_perceiver); the two ablations are inference-only and run the split-16x3 convolution */
 } vxb_qnet_desc;
+#define VXB_FINAL_CAT 0
+#define VXB_FINAL_U0  1
+#define VXB_FINAL_D0  2
 
 #define VXB_MATH_FP32_SIMT 0  /* fp32 FFMA everywhere (reference arithmetic, slow path for parity) */
 #define VXB_MATH_BF16X3    1  /* tcgen05 split-16-bit (hi*hi + hi*lo + lo*hi; fp16 planes), fp32 accumulate in TMEM */

@@ -130,7 +130,12 @@ def qnet_forward(sd, cfg, ins, proprio, lang_token_embs):
     seq_shape = x.shape
     x = x.reshape(b, -1, x.shape[-1])                                           # :412
     l = F.linear(lang_token_embs, sd['lang_preprocess.weight'], sd['lang_preprocess.bias'])  # :417
-    seq = torch.cat((l, x), dim=1) + sd['pos_encoding']                         # :418,422
+    if sd['pos_encoding'].dim() == 5:
+        # pos_encoding_with_lang=False (:392-393): the encoding [1,S,S,S,C] goes on the voxel tokens only, the language tokens
+        # stay a bag of words (the configuration of the PerAct paper, see the note at :395-406)
+        seq = torch.cat((l, x + sd['pos_encoding'].reshape(1, -1, x.shape[-1])), dim=1)
+    else:
+        seq = torch.cat((l, x), dim=1) + sd['pos_encoding']                     # :418,422
     lat = sd['latents'].unsqueeze(0).expand(b, -1, -1)                          # :425
     for _ in range(cfg.get('iterations', 1)):
         ctx = _layernorm(seq, sd, 'cross_attend_blocks.0.norm_context')
@@ -155,7 +160,12 @@ def qnet_forward(sd, cfg, ins, proprio, lang_token_embs):
         u0 = conv3d_block(u0, sd['up0.conv_up.2.conv3d.weight'], sd['up0.conv_up.2.conv3d.bias'], 1, act)
     else:
         u0 = conv3d_block(u0, sd['up0.conv_up.1.conv3d.weight'], sd['up0.conv_up.1.conv3d.bias'], 1, act)
-    u = conv3d_block(torch.cat([d0, u0], dim=1), sd['final.conv3d.weight'], sd['final.conv3d.bias'], 1, act)  # :462
+    if cfg.get('no_skip_connection', False):
+        u = conv3d_block(u0, sd['final.conv3d.weight'], sd['final.conv3d.bias'], 1, act)                      # :457
+    elif cfg.get('no_perceiver', False):
+        u = conv3d_block(d0, sd['final.conv3d.weight'], sd['final.conv3d.bias'], 1, act)                      # :459
+    else:
+        u = conv3d_block(torch.cat([d0, u0], dim=1), sd['final.conv3d.weight'], sd['final.conv3d.bias'], 1, act)  # :462
     trans = conv3d_block(u, sd['trans_decoder.conv3d.weight'], sd['trans_decoder.conv3d.bias'], 1, None)     # :465
     feats.extend([spatial_softmax3d(u), u.amax(dim=(2, 3, 4))])                          # :470
     flat = torch.cat(feats, dim=1)

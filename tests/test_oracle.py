@@ -136,6 +136,52 @@ def test_weight_tied_encoder_matches_the_reference_class_and_the_oracle():
 
 
 @needs_ref
+def test_pos_encoding_without_language_matches_the_reference_class():
+    """pos_encoding_with_lang=False (perceiver_lang_io.py:192-194, 392-393): parameter shape [1,S,S,S,C] as in the reference,
+    oracle forward == reference forward."""
+    _, RefEnc = refimport.load()
+    from voxactb_b200 import PerceiverVoxelLangEncoder
+    c = make_golden.QNET_CASES['qnet_v20']
+    kw = dict(make_golden.encoder_kwargs(c), pos_encoding_with_lang=False)
+    ref, ours = RefEnc(**kw).eval(), PerceiverVoxelLangEncoder(**kw).eval()
+    assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    sd = synth.random_state_dict(ref, 93)
+    ref.load_state_dict(sd, strict=False)
+    obs = synth.make_observation(c['seed'], c['B'], c['cameras'], c['H'], c['W'], low_dim=c['low_dim'])
+    coords, feats = synth.flatten_cameras(obs)
+    grid = torch.from_numpy(voxel_oracle.voxelize(coords.numpy(), feats.numpy(), obs['bounds'].numpy(), c['V'])).permute(0, 4, 1, 2, 3)
+    with torch.no_grad():
+        want = ref(grid, obs['proprio'], obs['lang_goal_emb'], obs['lang_token_embs'], None, obs['bounds'], None)
+        have = qnet_oracle.qnet_forward(dict(ref.state_dict()), util.oracle_cfg(c), grid, obs['proprio'], obs['lang_token_embs'])
+    for w, k in zip(want[:3], ('trans', 'rot_grip', 'collision')):
+        assert util.rel_err(have[k], w) < 2e-5, k
+
+
+@needs_ref
+@pytest.mark.parametrize('flag', ['no_skip_connection', 'no_perceiver'])
+def test_final_conv_ablations_match_the_reference_class(flag):
+    """no_skip_connection / no_perceiver (perceiver_lang_io.py:296-306, 456-462): final convolution over 64 channels (u0 or d0
+    alone); same parameter shapes as the reference, oracle forward == reference forward."""
+    _, RefEnc = refimport.load()
+    from voxactb_b200 import PerceiverVoxelLangEncoder
+    c = dict(make_golden.QNET_CASES['qnet_v20'], **{flag: True})
+    kw = dict(make_golden.encoder_kwargs(c), **{flag: True})
+    ref, ours = RefEnc(**kw).eval(), PerceiverVoxelLangEncoder(**kw).eval()
+    assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    assert tuple(ours.state_dict()['final.conv3d.weight'].shape) == (64, 64, 3, 3, 3)
+    sd = synth.random_state_dict(ref, 95)
+    ref.load_state_dict(sd, strict=False)
+    obs = synth.make_observation(c['seed'], c['B'], c['cameras'], c['H'], c['W'], low_dim=c['low_dim'])
+    coords, feats = synth.flatten_cameras(obs)
+    grid = torch.from_numpy(voxel_oracle.voxelize(coords.numpy(), feats.numpy(), obs['bounds'].numpy(), c['V'])).permute(0, 4, 1, 2, 3)
+    with torch.no_grad():
+        want = ref(grid, obs['proprio'], obs['lang_goal_emb'], obs['lang_token_embs'], None, obs['bounds'], None)
+        have = qnet_oracle.qnet_forward(dict(ref.state_dict()), util.oracle_cfg(c), grid, obs['proprio'], obs['lang_token_embs'])
+    for w, k in zip(want[:3], ('trans', 'rot_grip', 'collision')):
+        assert util.rel_err(have[k], w) < 2e-5, k
+
+
+@needs_ref
 def test_voxel_oracle_vs_live_reference():
     RefVG, _ = refimport.load()
     for seed, V, crop in ((5, 16, False), (6, 24, True)):

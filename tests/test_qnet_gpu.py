@@ -220,6 +220,39 @@ def test_f16_fp8_mode_tracks_the_scale_of_its_operands(cuda_lib, rgb_scale, weig
         assert util.rel_err(a, b) < 3.0 * util.rel_err(b3, b) + 2e-4
 
 
+@pytest.mark.parametrize('flag', ['no_skip_connection', 'no_perceiver'])
+def test_final_conv_ablations_match_oracle(cuda_lib, flag):
+    """no_skip_connection: u = final(u0); no_perceiver: u = final(d0) (perceiver_lang_io.py:456-460), every math mode."""
+    from voxactb_b200 import PerceiverVoxelLangEncoder
+    c = dict(make_golden.QNET_CASES['qnet_v20'], **{flag: True})
+    enc = PerceiverVoxelLangEncoder(**dict(make_golden.encoder_kwargs(c), **{flag: True})).eval()
+    enc.load_state_dict(synth.random_state_dict(enc, 96), strict=False)
+    sd = {k: v.clone() for k, v in enc.state_dict().items()}
+    obs = synth.make_observation(c['seed'], c['B'], c['cameras'], c['H'], c['W'], low_dim=c['low_dim'])
+    for mode in MODES:
+        _, (trans, rot_grip, coll, _) = run_qfunction(c, obs, enc, mode)
+        ref = qnet_oracle.qfunction_forward(sd, util.oracle_cfg(c), voxel_oracle.voxelize, obs['rgb'], obs['pcd'], obs['proprio'],
+                                            obs['lang_token_embs'], obs['bounds'], c['V'])
+        for ours, key in ((trans, 'trans'), (rot_grip, 'rot_grip'), (coll, 'collision')):
+            assert util.rel_err(ours, ref[key]) < util.Q_REL_TOL, (key, mode)
+
+
+def test_pos_encoding_without_language_matches_oracle(cuda_lib):
+    """pos_encoding_with_lang=False: the [1,S,S,S,C] encoding reaches the kernel as a [77 + T, C] table with zero language rows."""
+    from voxactb_b200 import PerceiverVoxelLangEncoder
+    c = make_golden.QNET_CASES['qnet_v20']
+    enc = PerceiverVoxelLangEncoder(**dict(make_golden.encoder_kwargs(c), pos_encoding_with_lang=False)).eval()
+    enc.load_state_dict(synth.random_state_dict(enc, 94), strict=False)
+    sd = {k: v.clone() for k, v in enc.state_dict().items()}
+    obs = synth.make_observation(c['seed'], c['B'], c['cameras'], c['H'], c['W'], low_dim=c['low_dim'])
+    for mode in MODES:
+        _, (trans, rot_grip, coll, _) = run_qfunction(c, obs, enc, mode)
+        ref = qnet_oracle.qfunction_forward(sd, util.oracle_cfg(c), voxel_oracle.voxelize, obs['rgb'], obs['pcd'], obs['proprio'],
+                                            obs['lang_token_embs'], obs['bounds'], c['V'])
+        for ours, key in ((trans, 'trans'), (rot_grip, 'rot_grip'), (coll, 'collision')):
+            assert util.rel_err(ours, ref[key]) < util.Q_REL_TOL, (key, mode)
+
+
 def test_weight_tied_layers_match_oracle(cuda_lib):
     """weight_tie_layers=True: all latent layers share layer 0's parameters (the C ABI simply receives the same pointers)."""
     from voxactb_b200 import PerceiverVoxelLangEncoder

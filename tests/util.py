@@ -40,7 +40,8 @@ def checksum(t):
 def oracle_cfg(c):
     return dict(voxel_patch_size=c['k'], voxel_patch_stride=c['s'], depth=c['depth'], iterations=1,
                 cross_heads=1, latent_heads=8, activation='lrelu', num_collision_classes=2,
-                arm_pred_loss=c['arm'], no_language=False)
+                arm_pred_loss=c['arm'], no_language=False, no_skip_connection=c.get('no_skip_connection', False),
+                no_perceiver=c.get('no_perceiver', False))
 
 
 def make_case(c):

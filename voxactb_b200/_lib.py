@@ -27,7 +27,8 @@ class QnetDesc(ctypes.Structure):
         'low_dim_size', 'two_robots', 'lang_seq_len', 'lang_emb_dim', 'num_latents', 'latent_dim',
         'depth', 'iterations', 'cross_heads', 'cross_dim_head', 'latent_heads', 'latent_dim_head',
         'final_dim', 'num_rotation_classes', 'num_grip_classes', 'num_collision_classes',
-        'arm_pred_loss', 'no_language')] + [('act_slope', ctypes.c_float), ('math_mode', ctypes.c_int32)]
+        'arm_pred_loss', 'no_language')] + [('act_slope', ctypes.c_float), ('math_mode', ctypes.c_int32),
+                                                 ('final_input', ctypes.c_int32)]
 
 
 class TrainOpts(ctypes.Structure):

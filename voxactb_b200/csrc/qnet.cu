@@ -21,6 +21,7 @@ void set_error(const char* fmt, ...) {
 struct Dims {
   int V, k, s, S, T, nl, n, im, C, L, D, depth, low, R, G, Cc, flat, fin;
   int ch, cdh, lh, ldh;
+  int fsrc, fcin;          // final convolution input (VXB_FINAL_*) and its channel count (128 or 64)
   size_t V3;
 };
 
@@ -64,6 +65,12 @@ static int make_dims(const vxb_qnet_desc* d, Dims& m) {
     set_error("qnet: unsupported latent/head dimensions");
     return VXB_E_UNSUPPORTED_SHAPE;
   }
+  m.fsrc = d->final_input;
+  if (m.fsrc != VXB_FINAL_CAT && m.fsrc != VXB_FINAL_U0 && m.fsrc != VXB_FINAL_D0) {
+    set_error("qnet: unknown final_input %d", m.fsrc);
+    return VXB_E_BADARG;
+  }
+  m.fcin = m.fsrc == VXB_FINAL_CAT ? 2 * m.im : m.im;
   if (d->two_robots && d->arm_pred_loss) {
     set_error("qnet: the 2-robot encoder has no arm-prediction head");
     return VXB_E_UNSUPPORTED_SHAPE;
@@ -117,10 +124,10 @@ static void carve_prepared(const Dims& m, Arena& a, Prepared& p, const void* con
   p.patch_wt = a.get<float>((size_t)64 * k3 * 64);
   p.up0_wt = a.get<float>((size_t)64 * k3 * m.C);
   p.up1_fold = a.get<float>((size_t)m.s * m.s * m.s * 64 * 27 * 64);
-  p.final_wt = a.get<float>((size_t)64 * 27 * 128);
+  p.final_wt = a.get<float>((size_t)64 * 27 * m.fcin);
   p.trans_wt = a.get<float>((size_t)27 * 64);
   p.trans_wt2 = a.get<float>((size_t)27 * 64);
-  p.final_wc = a.get<__nv_bfloat16>(umma::conv3_weight_elems(128));
+  p.final_wc = a.get<__nv_bfloat16>(umma::conv3_weight_elems(m.fcin));
   p.patch_wc = a.get<__nv_bfloat16>(umma::patchify_weight_elems(m.k));
   p.final_w16 = a.get<__nv_bfloat16>(umma::conv3_f8c_w16_elems(128));
   p.final_wmax = a.get<unsigned int>(2);
@@ -163,7 +170,7 @@ static void weight_specs(const Dims& m, const void* const* params, const Prepare
   const long long k3 = (long long)m.k * m.k * m.k, cq = m.ch * m.cdh, lq = m.lh * m.ldh;
   v.push_back({p.up0_wt, 64, k3 * m.C});
   v.push_back({p.up1_fold, (long long)m.s * m.s * m.s * 64, 27 * 64});
-  v.push_back({p.final_wt, 64, 27 * 128});
+  v.push_back({p.final_wt, 64, 27ll * m.fcin});
   v.push_back({p.q_cross, m.L, cq});
   v.push_back({P(VXB_P_LANG_W), m.C, 512});
   v.push_back({P(VXB_P_CROSS_Q_W), cq, m.D});
@@ -636,17 +643,17 @@ extern "C" int vxb_qnet_prepare(const vxb_qnet_desc* d, const void* const* param
   const int k3 = m.k * m.k * m.k;
   VXB_TRY(conv_weight_prepare(P(VXB_P_PATCH_W), p.patch_wt, 64, 64, k3, st));
   VXB_TRY(conv_weight_prepare(P(VXB_P_UP0_W), p.up0_wt, 64, m.C, k3, st));
-  VXB_TRY(conv_weight_prepare(P(VXB_P_FINAL_W), p.final_wt, 64, 128, 27, st));
+  VXB_TRY(conv_weight_prepare(P(VXB_P_FINAL_W), p.final_wt, 64, m.fcin, 27, st));
   VXB_TRY(conv_weight_prepare(P(VXB_P_TRANS_W), p.trans_wt, 1, 64, 27, st));
   if (d->two_robots) VXB_TRY(conv_weight_prepare(P(VXB_P_TRANS2_W), p.trans_wt2, 1, 64, 27, st));
-  VXB_TRY(umma::conv3_prepare_weights(p.final_wt, 128, p.final_wc, st));
+  VXB_TRY(umma::conv3_prepare_weights(p.final_wt, m.fcin, p.final_wc, st));
   VXB_TRY(umma::patchify_prepare_weights(p.patch_wt, m.k, p.patch_wc, st));
   {
     const size_t total = (size_t)m.s * m.s * m.s * 64 * 27 * 64;
     fold_upconv_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(P(VXB_P_UP1_W), p.up1_fold, 64, 64, m.k, m.s);
     VXB_LAUNCH_CHECK();
   }
-  VXB_TRY(umma::conv3_f8c_prepare(p.final_wt, 128, 64, p.final_w16, p.final_wmax, st));
+  if (m.fsrc == VXB_FINAL_CAT) VXB_TRY(umma::conv3_f8c_prepare(p.final_wt, 128, 64, p.final_w16, p.final_wmax, st));
   VXB_TRY(umma::conv3_f8c_fold_abs(p.up1_fold, (long long)m.s * m.s * m.s * 64, 64, p.up1_abs, st));
   VXB_TRY(umma::upconv_f8c_prepare(p.up1_fold, (long long)m.s * m.s * m.s * 64, 27 * 64, umma::Planes{p.up1_f8[0], p.up1_f8[1], 27 * 64},
                                    p.up1_beta, reinterpret_cast<unsigned int*>(p.up1_beta + 2), st));
@@ -699,8 +706,8 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
                              float* rot_grip, float* collision, float* rot_grip2, float* collision2, float* arm_out,
                              cudaStream_t st) {
   // VXB_MATH_F16F8C = VXB_MATH_BF16X3 everywhere except the final 3x3x3 convolution (conv_f8c.cuh)
-  const bool f8c = d->math_mode == VXB_MATH_F16F8C;
-  const int mm = f8c ? VXB_MATH_BF16X3 : d->math_mode;
+  const bool f8c = d->math_mode == VXB_MATH_F16F8C && m.fsrc == VXB_FINAL_CAT;   // the ablated final convs run split-16x3
+  const int mm = d->math_mode == VXB_MATH_F16F8C ? VXB_MATH_BF16X3 : d->math_mode;
   Ctx cx(mm, st, mm == VXB_MATH_BF16X3 ? w.scratch : nullptr, w.scratch_bytes);
   cx.wp = pw.planes;
   auto P = [&](int slot) { return (const float*)params[slot]; };
@@ -886,14 +893,22 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
       VXB_TRY(umma::conv3_f8c_planes(d0c, &u0p, 64, 64, pw.final_w16, w.final_w8, w.f8s, P(VXB_P_FINAL_B), slope, nullptr, B, m.V,
                                      st, &tail));
     } else {
-      VXB_TRY(umma::conv3_planes(d0p, &u0p, 64, 64, pw.final_wc, P(VXB_P_FINAL_B), slope, nullptr, B, m.V, st, &tail));
+      if (m.fsrc == VXB_FINAL_CAT)
+        VXB_TRY(umma::conv3_planes(d0p, &u0p, 64, 64, pw.final_wc, P(VXB_P_FINAL_B), slope, nullptr, B, m.V, st, &tail));
+      else      // ablations (perceiver_lang_io.py:456-460): u = final(u0) (no_skip_connection) or final(d0) (no_perceiver)
+        VXB_TRY(umma::conv3_planes(m.fsrc == VXB_FINAL_U0 ? u0p : d0p, nullptr, 64, 0, pw.final_wc, P(VXB_P_FINAL_B), slope, nullptr, B,
+                                   m.V, st, &tail));
     }
     STAGE_MARK();  // 9: trans decoder gather + ss_final merge (their first halves ran in the conv epilogue)
     VXB_TRY(umma::conv3_tail_finish(tail, B, m.V, st));
     STAGE_MARK();  // 10: heads
   } else {
-    VXB_TRY(conv3d(w.d0, w.u0, 64, 64, pw.final_wt, P(VXB_P_FINAL_B), w.u, B, m.V, m.V, 64, 3, 1, slope, mm, st,
-                   cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.final_wt)));
+    if (m.fsrc == VXB_FINAL_CAT)
+      VXB_TRY(conv3d(w.d0, w.u0, 64, 64, pw.final_wt, P(VXB_P_FINAL_B), w.u, B, m.V, m.V, 64, 3, 1, slope, mm, st,
+                     cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.final_wt)));
+    else
+      VXB_TRY(conv3d(m.fsrc == VXB_FINAL_U0 ? w.u0 : w.d0, nullptr, 64, 0, pw.final_wt, P(VXB_P_FINAL_B), w.u, B, m.V, m.V, 64, 3, 1,
+                     slope, mm, st, cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.final_wt)));
     STAGE_MARK();  // 9: trans decoder
     // (12) trans decoder: conv3 64 -> 1, no activation                            :465
     COUNT_LAUNCH();

@@ -159,6 +159,10 @@ static int train_supported(const vxb_qnet_desc* d, const Dims& m) {
     set_error("qnet training: the 2-robot encoder is inference-only in this library");
     return VXB_E_UNSUPPORTED_SHAPE;
   }
+  if (d->final_input != VXB_FINAL_CAT) {
+    set_error("qnet training: the no_skip_connection / no_perceiver ablations are inference-only in this library");
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
   if (d->iterations != 1) {
     set_error("qnet training: iterations must be 1 (what launch_utils.create_agent builds)");
     return VXB_E_UNSUPPORTED_SHAPE;

@@ -182,10 +182,6 @@ class PerceiverVoxelLangEncoder(nn.Module):
         unsupported = []
         if lang_fusion_type != 'seq':
             unsupported.append("lang_fusion_type=%r" % lang_fusion_type)
-        if not pos_encoding_with_lang:
-            unsupported.append('pos_encoding_with_lang=False')
-        if no_skip_connection or no_perceiver:
-            unsupported.append('no_skip_connection/no_perceiver ablations')
         if activation not in ('lrelu', 'relu'):
             unsupported.append('activation=%r' % activation)
         if num_rotation_classes <= 0:
@@ -207,7 +203,11 @@ class PerceiverVoxelLangEncoder(nn.Module):
         k, D, L = voxel_patch_size, latent_dim, num_latents
         act = activation
         reg = lambda name, t: _register(self, name, t)
-        reg('pos_encoding', torch.randn(1, 77 + spatial ** 3, C))
+        if pos_encoding_with_lang:
+            reg('pos_encoding', torch.randn(1, 77 + spatial ** 3, C))                       # reference :196-198
+        else:
+            # reference :192-194: the encoding covers the voxel tokens only (added before the language tokens are prepended)
+            reg('pos_encoding', torch.randn(1, spatial, spatial, spatial, C))
         reg('input_preprocess.conv3d.weight', _init_weight((im_channels, self.init_dim, 1, 1, 1), self.init_dim, im_channels, act))
         reg('input_preprocess.conv3d.bias', torch.zeros(im_channels))
         reg('patchify.conv3d.weight', _init_weight((im_channels, im_channels, k, k, k), im_channels * k ** 3, im_channels * k ** 3, act))
@@ -261,7 +261,9 @@ class PerceiverVoxelLangEncoder(nn.Module):
         reg('up0.conv_up.2.conv3d.bias', torch.zeros(final_dim))
         for ax, t in zip('xyz', _spatial_positions(spatial)):
             _register(self, 'ss1.pos_%s' % ax, t, buffer=True)
-        reg('final.conv3d.weight', _init_weight((im_channels, im_channels * 2, 3, 3, 3), im_channels * 2 * 27, im_channels * 27, act))
+        # reference :296-306: the skip-less / perceiver-less ablations feed the final convolution 64 channels instead of 128
+        fin_in = im_channels if (no_skip_connection or no_perceiver) else im_channels * 2
+        reg('final.conv3d.weight', _init_weight((im_channels, fin_in, 3, 3, 3), fin_in * 27, im_channels * 27, act))
         reg('final.conv3d.bias', torch.zeros(im_channels))
         reg('trans_decoder.conv3d.weight', _init_weight((1, final_dim, 3, 3, 3), final_dim * 27, 27, None))
         reg('trans_decoder.conv3d.bias', torch.zeros(1))
@@ -296,6 +298,8 @@ class PerceiverVoxelLangEncoder(nn.Module):
         # runtime state (never pickled / deep-copied with live CUDA handles: rebuilt lazily)
         self._prepared = None
         self._prepared_key = None
+        self._pos_table = None
+        self._pos_table_key = None
         self._workspace = None
         self._train_ws = None
         self._train_gen = 0
@@ -361,6 +365,7 @@ class PerceiverVoxelLangEncoder(nn.Module):
         d.no_language = int(bool(self.no_language))
         d.act_slope = LRELU_SLOPE if self.activation == 'lrelu' else 0.0
         d.math_mode = int(self.math_mode)
+        d.final_input = 1 if self.no_skip_connection else (2 if self.no_perceiver else 0)      # VXB_FINAL_* (reference :456-462)
         return d
 
     def _param_table(self):
@@ -378,6 +383,14 @@ class PerceiverVoxelLangEncoder(nn.Module):
                 arr[i] = None
                 continue
             t = _lib.f32(p.detach())
+            if i < len(names) and names[i] == 'pos_encoding' and not self.pos_encoding_with_lang:
+                # the library adds one [77 + T, C] table to the whole sequence: zeros for the language rows.  Cached on the
+                # module (a captured CUDA graph keeps reading this buffer) and rebuilt when the parameter changes.
+                key = (t.data_ptr(), p._version, t.device)
+                if getattr(self, '_pos_table_key', None) != key:
+                    self._pos_table = torch.cat([t.new_zeros(77, t.shape[-1]), t.reshape(-1, t.shape[-1])], 0).contiguous()
+                    self._pos_table_key = key
+                t = self._pos_table
             keep.append(t)
             arr[i] = t.data_ptr()
         return arr, keep, slots
@@ -421,6 +434,11 @@ class PerceiverVoxelLangEncoder(nn.Module):
             # training step (row a18): one autograd node around vxb_qnet_forward_train_f32 / vxb_qnet_backward_f32
             if self.TWO_ROBOTS:
                 raise NotImplementedError('the 2-robot encoder is inference-only in voxactb_b200 (training: single-arm encoders)')
+            if self.no_skip_connection or self.no_perceiver:
+                raise NotImplementedError('the no_skip_connection / no_perceiver ablations are inference-only in voxactb_b200')
+            if not self.pos_encoding_with_lang:
+                raise NotImplementedError('pos_encoding_with_lang=False is inference-only in voxactb_b200 (the backward writes the '
+                                          'gradient of a [77 + T, C] table)')
             if self.weight_tie_layers and self.depth > 1:
                 raise NotImplementedError('weight_tie_layers=True is inference-only in voxactb_b200 (the backward writes one '
                                           'gradient buffer per layer slot; tied layers would need their sum)')
