@@ -8,3 +8,5 @@ timeout 900 python bench.py > gpurun_out/bench_r02_final.json 2> gpurun_out/benc
 import json
 d=json.loads(open('gpurun_out/bench_r02_final.json').read().strip().splitlines()[-1])
 print(d['value'], d['ms_per_step'], {k:v for k,v in d['e2e'].items() if k!='mode'}); print(d['roofline']['frac'], d['roofline']['whole_forward_frac'], d['roofline']['voxelize']); print(d['clocks']); print(d.get('gpu_torch_comparator')); print(d.get('cpu_baseline'))"
+# voxelizer: timing by occupancy and ncu --set full of both kernels on the same binary
+bash tools/gpu_job_vox.sh

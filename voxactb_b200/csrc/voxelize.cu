@@ -8,29 +8,26 @@
 //      reference's exact fp32 operation order (sub, div, floor; no FMA contraction, no
 //      reciprocal), drops points that fall in the cropped border, and accumulates
 //      [count, xyz, features] into a per-sample open-addressing hash table that stays L2-resident
-//      (2N slots x 36 B = 4.5 MB/sample at N=65536) -- so the dense (V+2)^3 x 7 accumulation buffer
+//      (2N slots x 32 B = 4 MB/sample at N=65536; one 32-byte sector per entry, key included) -- so the dense (V+2)^3 x 7 accumulation buffer
 //      of the reference (2 x 29.7 MB zero-fill + read-back per sample) never exists.  A point costs one
-//      atomicCAS (slot claim) and two 128-bit vector reductions (red.global.add.v4.f32).  Points of one
+//      atomicCAS (slot claim) and three vector / scalar reductions on the same sector (red.global.add.v4 / .v2 / .f32).  Points of one
 //      warp that hit the same voxel are first combined with match_any + shuffles, which bounds the
 //      contention of degenerate clouds (every point in one voxel); on the surface-heavy 4-camera input of
 //      SURVEY.md section 8d neither that nor a shared-memory per-block bin removes traffic: 64 122 in-grid
 //      points of a sample fall into 48 017 voxels, and the duplicates come from DIFFERENT cameras --
 //      32-point groups hold 64 083 distinct (group, voxel) pairs, 1024-point blocks 62 885 (-2 %).
 //   2. fill: one pass writes the dense [B,V,V,V,7+F] output, a warp per (x, y) row with 128-bit stores; the
-//      94+ % empty voxels depend only on their position (index-grid channels from a per-block table of i / V,
-//      zeros elsewhere) and are told apart by an occupancy bitmap (1 bit/voxel) without touching the hash
-//      table (the first version staged 32 voxels per warp through shared memory with three fp32 divisions
-//      and two integer divisions per voxel: 290 instructions per 32 voxels, issue-bound at 48 % of the HBM peak).
+//      94+ % empty voxels depend only on their position (a template row per block, two channels patched in
+//      registers) and are told apart by an occupancy bitmap (1 bit/voxel) without touching the hash table;
+//      the look-ups of the occupied voxels are in flight while the warp streams the row's background out
+//      (history: round 1 staged 32 voxels per warp through shared memory with three fp32 and two integer
+//      divisions per voxel, 290 instructions per 32 voxels, issue-bound at 48 % of the HBM peak; the second
+//      version built whole rows in per-warp buffers and was latency-bound at 40 warps / SM).
 #include "common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace vxb {
-
-struct VoxEntry {  // 32 bytes for F<=3; generic F uses stride_f floats
-  int key;         // flat cropped voxel id + 1, 0 = empty
-  float cnt;
-  float sum[6];
-};
 
 __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
   x ^= x >> 16;
@@ -77,16 +74,34 @@ struct DepthSrc {
   int cams, H, W;
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
-template <int F> struct VoxTab { static constexpr int EF = (1 + 3 + F + 3) / 4 * 4; };   // floats per entry: count, xyz, features
+// One table entry = ONE 32-byte sector: [count, x, y, z | f0, f1, f2, key] (sums; key = flat cropped voxel id + 1 as an int,
+// 0 = empty).  Claiming, accumulating and looking an entry up all touch that one sector (the first layout kept keys and
+// values in two arrays: two sectors and two DRAM bursts per look-up).
+// The table is re-read by the fill while 580 MB of output stream through L2: its accesses carry an evict_last policy
+// (measured at B=16: 233 -> 219 us per call; a persisting-L2 window on the table was also tried and starves the stores: 420 us).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void red_add_v4_keep(float* addr, float a, float b, float c, float d, uint64_t pol) {
+  asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 ld_keep(const float4* addr, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(addr), "l"(pol));
+  return v;
+}
+constexpr int VOX_EF = 8, VOX_KEY = 7;
 
 template <int F, bool DEPTH>
 __global__ void __launch_bounds__(256)
 vox_scatter_kernel(const float* __restrict__ coords, const float* __restrict__ feats,
                    const float* __restrict__ bounds, int Bb, int N, int V,
-                   int* __restrict__ tkeys, float* __restrict__ tvals, int slots,
+                   float* __restrict__ table, int slots,
                    uint32_t* __restrict__ bitmap, int bitmap_words,
                    int32_t* __restrict__ out_idx, const DepthSrc ds) {
   const int b = blockIdx.y;
@@ -155,17 +170,19 @@ vox_scatter_kernel(const float* __restrict__ coords, const float* __restrict__ f
   }
   if (key == 0 || lane != leader) return;
 
-  constexpr int EF = VoxTab<F>::EF;
-  int* keys = tkeys + (size_t)b * slots;
+  float* tab = table + (size_t)b * slots * VOX_EF;
   uint32_t h = hash_u32((uint32_t)key) & (uint32_t)(slots - 1);
   while (true) {
-    int prev = atomicCAS(keys + h, 0, key);
+    int prev = atomicCAS(reinterpret_cast<int*>(tab + (size_t)h * VOX_EF) + VOX_KEY, 0, key);
     if (prev == 0 || prev == key) break;
     h = (h + 1) & (uint32_t)(slots - 1);
   }
-  float* e = tvals + ((size_t)b * slots + h) * EF;
-  red_add_v4(e, cnt, val[0], val[1], val[2]);
-  if constexpr (F == 3) red_add_v4(e + 4, val[3], val[4], val[5], 0.f);
+  float* e = tab + (size_t)h * VOX_EF;
+  red_add_v4_keep(e, cnt, val[0], val[1], val[2], l2_policy_evict_last());
+  if constexpr (F == 3) {
+    red_add_v2(e + 4, val[3], val[4]);
+    atomicAdd(e + 6, val[5]);
+  }
   static_assert(F == 0 || F == 3, "feature sizes compiled: 0 and 3");
   const int vid = key - 1;
   atomicOr(bitmap + (size_t)b * bitmap_words + (vid >> 5), 1u << (vid & 31));
@@ -181,46 +198,80 @@ __device__ __forceinline__ unsigned int fdiv_u32(unsigned int n, const FastDiv& 
 // bitmap (1 bit per voxel, L1-resident per row) tells them apart without touching the table; a lane whose float4 overlaps an
 // occupied voxel looks its entry up (mean = sum / clamp(count, 1), voxel_grid.py:119; occupancy 1, :192).
 template <int F>
-__device__ __forceinline__ void vox_lookup(const int* __restrict__ keys, const float* __restrict__ vals, int slots, int key, float (&m)[3 + F]) {
-  constexpr int EF = VoxTab<F>::EF;
-  uint32_t h = hash_u32((uint32_t)key) & (uint32_t)(slots - 1);
-#pragma unroll 1
-  for (int probe = 0; probe < slots; ++probe) {
-    const int kk = keys[h];
-    if (kk == key) break;
-    if (kk == 0) return;   // cannot happen for a set bit
-    h = (h + 1) & (uint32_t)(slots - 1);
-  }
-  const float4* e = reinterpret_cast<const float4*>(vals + (size_t)h * EF);
-  const float4 a = e[0];
+__device__ __forceinline__ void vox_entry_mean(const float4& a, const float4& c, float (&m)[3 + F]) {
   m[0] = a.y; m[1] = a.z; m[2] = a.w;
-  if constexpr (F == 3) {
-    const float4 c = e[1];
-    m[3] = c.x; m[4] = c.y; m[5] = c.z;
-  }
+  if constexpr (F == 3) { m[3] = c.x; m[4] = c.y; m[5] = c.z; }
   if (a.x > 1.f) {          // three of four occupied voxels of the 4-camera input hold ONE point: mean == sum, no division
 #pragma unroll
     for (int j = 0; j < 3 + F; ++j) m[j] = __fdiv_rn(m[j], a.x);
   }
 }
 template <int F>
-__global__ void __launch_bounds__(256)
-vox_fill_rows_kernel(const int* __restrict__ tkeys, const float* __restrict__ tvals, int slots,
+__device__ __forceinline__ void vox_lookup(const float* __restrict__ tab, int slots, int key, float (&m)[3 + F]) {
+  uint32_t h = hash_u32((uint32_t)key) & (uint32_t)(slots - 1);
+#pragma unroll 1
+  for (int probe = 0; probe < slots; ++probe) {
+    const float4* e = reinterpret_cast<const float4*>(tab + (size_t)h * VOX_EF);
+    const float4 c = e[1];
+    const int kk = __float_as_int(c.w);
+    if (kk == key) {
+      vox_entry_mean<F>(e[0], c, m);
+      return;
+    }
+    if (kk == 0) return;   // cannot happen for a set bit
+    h = (h + 1) & (uint32_t)(slots - 1);
+  }
+}
+// Fill, second design: NO per-warp row buffer.  The 94+ % background of a row differs from every other row only in two
+// channels (x / V and y / V), so the block keeps ONE template row in shared memory (z / V and zeros) plus a byte per float4
+// saying which of its elements are the x / y channels; a warp streams its row out as template + two register patches.  The
+// look-ups of the row's occupied voxels (compacted from the occupancy bitmap, ~5 of 100) are issued BEFORE the background stores
+// -- first-probe key and both value vectors speculatively, a mismatch falls back to the probing loop -- so the two dependent L2
+// round trips of a look-up hide behind the warp's own stores instead of serialising with them; the occupied voxels are then
+// overwritten in place (same warp, after __syncwarp: the sectors are still in L2 and merge there).  The first design built
+// every row in a 4 KB per-warp buffer: ~13 k cycles of dependent steps per row at 40 warps / SM made the fill latency-bound
+// (189 us at B=16, profiles/ncu_r02_voxelize_after_summary.json); without the buffer a block needs 8 KB and the SM holds 64 warps.
+template <int F>
+__global__ void __launch_bounds__(256, 6)       // 40 registers, 48 warps / SM (64 warps at 32 registers and 40 at 48 measured the same)
+vox_fill_rows_kernel(const float* __restrict__ table, int slots,
                      const uint32_t* __restrict__ bitmap, int bitmap_words, int V, float* __restrict__ out) {
   constexpr int CH = 7 + F;
   extern __shared__ __align__(16) float vf_smem[];
-  const int lut_floats = (V + 3) & ~3, row_floats = V * CH;      // row_floats % 4 == 0 (checked by the launcher)
-  float* lut = vf_smem;
+  const int lut_floats = (V + 3) & ~3, row_floats = V * CH, row_f4 = row_floats / 4;   // row_floats % 4 == 0 (launcher)
+  float* lut = vf_smem;                                            // i / V
+  float* tmpl = lut + lut_floats;                                  // one background row with x = y = 0
+  int* lists = reinterpret_cast<int*>(tmpl + row_floats);          // 8 x V: occupied voxels of each warp's row
+  uint8_t* sel = reinterpret_cast<uint8_t*>(lists + 8 * V);        // per float4: (element of the x channel + 1) | (y ... + 1) << 4
   for (int i = threadIdx.x; i < V; i += blockDim.x) lut[i] = __fdiv_rn((float)i, (float)V);
+  __syncthreads();
+  for (int p = threadIdx.x; p < row_floats; p += blockDim.x) {
+    const int iz = p / CH, ch = p - iz * CH;
+    tmpl[p] = ch == 5 + F ? lut[iz] : 0.f;
+  }
+  // PAIR (F = 3): the x and y channels are floats 10 iz + 6, 7 -- an aligned pair that lands in .xy or .zw of one float4
+  constexpr bool PAIR = CH % 4 == 2 && (3 + F) % 2 == 0;
+  for (int q = threadIdx.x; q < row_f4; q += blockDim.x) {
+    int s = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ch = (4 * q + j) % CH;
+      if constexpr (PAIR) {
+        if (ch == 3 + F) s = j == 0 ? 1 : 2;
+      } else {
+        if (ch == 3 + F) s |= j + 1;
+        if (ch == 4 + F) s |= (j + 1) << 4;
+      }
+    }
+    sel[q] = (uint8_t)s;
+  }
   __syncthreads();
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* rowbuf = vf_smem + lut_floats + warp * (row_floats + lut_floats);
-  int* list = reinterpret_cast<int*>(rowbuf + row_floats);         // occupied voxels of the row (<= V entries)
-  const int rows = V * V, row_f4 = row_floats / 4;
-  const int* keys = tkeys + (size_t)b * slots;
-  const float* vals = tvals + (size_t)b * slots * VoxTab<F>::EF;
+  int* list = lists + warp * V;
+  const int rows = V * V;
+  const float* tab = table + (size_t)b * slots * VOX_EF;
   const uint32_t* bm = bitmap + (size_t)b * bitmap_words;
+  const float4* tmpl4 = reinterpret_cast<const float4*>(tmpl);
   int row = blockIdx.x * 8 + warp;
   // occupancy words of a row: bits [v0, v0 + V) of the bitmap, <= 32 words (launcher: V <= 960), one per lane
   auto load_bits = [&](int r) -> uint32_t {
@@ -229,41 +280,32 @@ vox_fill_rows_kernel(const int* __restrict__ tkeys, const float* __restrict__ tv
     return lane < nw ? bm[w0 + lane] : 0u;
   };
   uint32_t wnext = load_bits(row);
-  for (; row < rows; row += gridDim.x * 8) {
+  const int step = gridDim.x * 8, step_x = step / V, step_y = step - step_x * V;
+  int ix = row / V, iy = row - ix * V;                             // advanced with the row: no division per row
+  for (; row < rows; row += step) {
     uint32_t wbits = wnext;
-    wnext = load_bits(row + gridDim.x * 8);                        // the next row's words are in flight while this row is built
-    const int ix = row / V, iy = row - ix * V;
+    wnext = load_bits(row + gridDim.x * 8);                        // the next row's words are in flight while this row leaves
     const float fx = lut[ix], fy = lut[iy];
+    ix += step_x; iy += step_y;
+    if (iy >= V) { iy -= V; ++ix; }
     const int v0 = row * V, w0 = v0 >> 5, nw = ((v0 + V - 1) >> 5) - w0 + 1;
     if (lane == 0) wbits &= ~0u << (v0 & 31);
     const int endbit = (v0 + V) - ((w0 + nw - 1) << 5);            // valid bits of the last word: 1..32
     if (lane == nw - 1 && endbit < 32) wbits &= (1u << endbit) - 1u;
-    const int cnt = __popc(wbits);
-    int pre = cnt;
+    int total = 0;
+    // first look-up round, issued ahead of the stores
+    int iz0 = -1;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), c0 = a0;
+    if (__any_sync(0xffffffffu, wbits != 0u)) {
+      const int cnt = __popc(wbits);
+      int pre = cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, pre, o);
-      if ((int)lane >= o) pre += t;
-    }
-    const int total = __shfl_sync(0xffffffffu, pre, 31);
-    pre -= cnt;
-    // background: the position-only values of every voxel of the row
-    for (int iz = lane; iz < V; iz += 32) {
-      float* r = rowbuf + iz * CH;
-      float v[CH];
-#pragma unroll
-      for (int j = 0; j < 3 + F; ++j) v[j] = 0.f;
-      v[3 + F] = fx; v[4 + F] = fy; v[5 + F] = lut[iz]; v[CH - 1] = 0.f;
-      if constexpr (CH % 2 == 0) {
-#pragma unroll
-        for (int j = 0; j < CH; j += 2) *reinterpret_cast<float2*>(r + j) = make_float2(v[j], v[j + 1]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) r[j] = v[j];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, pre, o);
+        if ((int)lane >= o) pre += t;
       }
-    }
-    if (total) {                                                   // warp-uniform
-      // occupied voxels of the row, compacted: ONE look-up round per 32 of them (a row of the 4-camera input holds ~5)
+      total = __shfl_sync(0xffffffffu, pre, 31);
+      pre -= cnt;
       uint32_t w = wbits;
       int pos = pre;
       while (w) {
@@ -272,24 +314,61 @@ vox_fill_rows_kernel(const int* __restrict__ tkeys, const float* __restrict__ tv
         list[pos++] = ((w0 + lane) << 5) + bpos - v0;
       }
       __syncwarp();
-      for (int t = lane; t < total; t += 32) {
-        const int iz = list[t];
-        float m[3 + F];
-#pragma unroll
-        for (int j = 0; j < 3 + F; ++j) m[j] = 0.f;
-        vox_lookup<F>(keys, vals, slots, v0 + iz + 1, m);
-        float* r = rowbuf + iz * CH;
-#pragma unroll
-        for (int j = 0; j < 3 + F; ++j) r[j] = m[j];
-        r[CH - 1] = 1.f;
+      if (lane < total) {
+        iz0 = list[lane];
+        const uint32_t h0 = hash_u32((uint32_t)(v0 + iz0 + 1)) & (uint32_t)(slots - 1);
+        const float4* e = reinterpret_cast<const float4*>(tab + (size_t)h0 * VOX_EF);
+        const uint64_t keep = l2_policy_evict_last();
+        a0 = ld_keep(e, keep);
+        c0 = ld_keep(e + 1, keep);
       }
     }
-    __syncwarp();
-    // the row leaves with 128-bit stores
-    float4* o = reinterpret_cast<float4*>(out + ((size_t)b * rows + row) * row_floats);
-    const float4* src = reinterpret_cast<const float4*>(rowbuf);
-    for (int q = lane; q < row_f4; q += 32) __stcs(o + q, src[q]);   // streaming stores: the 580 MB of output must not evict the table from L2
-    __syncwarp();
+    // background: template + this row's x / V and y / V, 128-bit streaming stores (the 580 MB of output must not evict the
+    // table from L2)
+    float* orow = out + ((size_t)b * rows + row) * row_floats;
+    float4* o4 = reinterpret_cast<float4*>(orow);
+    for (int q = lane; q < row_f4; q += 32) {
+      float4 v = tmpl4[q];
+      const int s = sel[q];
+      if constexpr (PAIR) {
+        if (s == 1) { v.x = fx; v.y = fy; }
+        if (s == 2) { v.z = fx; v.w = fy; }
+      } else {
+        const int jx = s & 15, jy = s >> 4;
+        if (jx == 1) v.x = fx; else if (jx == 2) v.y = fx; else if (jx == 3) v.z = fx; else if (jx == 4) v.w = fx;
+        if (jy == 1) v.x = fy; else if (jy == 2) v.y = fy; else if (jy == 3) v.z = fy; else if (jy == 4) v.w = fy;
+      }
+      __stcs(o4 + q, v);
+    }
+    if (total) {                                                   // warp-uniform
+      __syncwarp();                                                // orders the background stores before the overwrites below
+      for (int t = lane; t < total; t += 32) {
+        int iz;
+        float m[3 + F];
+        if (t == lane && __float_as_int(c0.w) == v0 + iz0 + 1) {   // first round, first probe hit (the common case)
+          iz = iz0;
+          vox_entry_mean<F>(a0, c0, m);
+        } else {
+          iz = list[t];
+#pragma unroll
+          for (int j = 0; j < 3 + F; ++j) m[j] = 0.f;
+          vox_lookup<F>(tab, slots, v0 + iz + 1, m);
+        }
+        float v[CH];
+#pragma unroll
+        for (int j = 0; j < 3 + F; ++j) v[j] = m[j];
+        v[3 + F] = fx; v[4 + F] = fy; v[5 + F] = lut[iz]; v[CH - 1] = 1.f;
+        float* r = orow + iz * CH;
+        if constexpr (CH % 2 == 0) {
+#pragma unroll
+          for (int j = 0; j < CH; j += 2) __stcs(reinterpret_cast<float2*>(r + j), make_float2(v[j], v[j + 1]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) __stcs(r + j, v[j]);
+        }
+      }
+      __syncwarp();                                                // the list is rebuilt by the next row
+    }
   }
 }
 
@@ -311,20 +390,20 @@ vox_background_scalar_kernel(float* __restrict__ out, int V, unsigned int V3) {
 // One thread per table slot: mean = sum / clamp(count, 1) (voxel_grid.py:119), occupancy = 1 (voxel_grid.py:192)
 template <int F>
 __global__ void __launch_bounds__(256)
-vox_occupied_kernel(const int* __restrict__ tkeys, const float* __restrict__ tvals, int slots, int V3, float* __restrict__ out) {
-  constexpr int CH = 7 + F, EF = VoxTab<F>::EF;
+vox_occupied_kernel(const float* __restrict__ table, int slots, int V3, float* __restrict__ out) {
+  constexpr int CH = 7 + F;
   const int b = blockIdx.y;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= slots) return;
-  const int key = tkeys[(size_t)b * slots + s];
+  const float4* e = reinterpret_cast<const float4*>(table + ((size_t)b * slots + s) * VOX_EF);
+  const float4 c = e[1];
+  const int key = __float_as_int(c.w);
   if (key == 0) return;
-  const float4* e = reinterpret_cast<const float4*>(tvals + ((size_t)b * slots + s) * EF);
   const float4 a = e[0];
   const float cnt = fmaxf(a.x, 1.f);
   float* o = out + ((size_t)b * V3 + (key - 1)) * CH;
   o[0] = __fdiv_rn(a.y, cnt); o[1] = __fdiv_rn(a.z, cnt); o[2] = __fdiv_rn(a.w, cnt);
   if constexpr (F == 3) {
-    const float4 c = e[1];
     o[3] = __fdiv_rn(c.x, cnt); o[4] = __fdiv_rn(c.y, cnt); o[5] = __fdiv_rn(c.z, cnt);
   }
   o[CH - 1] = 1.f;
@@ -335,7 +414,6 @@ static int table_slots(int N) {
   while (s < 2 * N) s <<= 1;
   return s;
 }
-static int entry_floats_for(int F) { return (1 + 3 + F + 3) / 4 * 4; }
 
 }  // namespace vxb
 
@@ -346,8 +424,7 @@ static size_t vox_bitmap_words(int V) { return align_up(((size_t)V * V * V + 31)
 extern "C" size_t vxb_voxelize_workspace_bytes(int B, int N, int V, int F) {
   if (B <= 0 || N <= 0 || V <= 0 || F < 0) return 0;
   const size_t slots = (size_t)table_slots(N);
-  return align_up((size_t)B * slots * sizeof(int), 256) + align_up((size_t)B * slots * entry_floats_for(F) * sizeof(float), 256) +
-         align_up((size_t)B * vox_bitmap_words(V) * 4, 256);
+  return align_up((size_t)B * slots * VOX_EF * sizeof(float), 256) + align_up((size_t)B * vox_bitmap_words(V) * 4, 256);
 }
 
 extern "C" int vxb_voxelize_launches(void) { return 2; }
@@ -358,34 +435,40 @@ static int voxelize_impl(const float* coords, const float* feats, const float* b
                          cudaStream_t st, const DepthSrc& ds) {
   constexpr int CH = 7 + F;
   const int slots = table_slots(N);
-  const size_t key_bytes = align_up((size_t)B * slots * sizeof(int), 256);
-  const size_t val_bytes = align_up((size_t)B * slots * entry_floats_for(F) * sizeof(float), 256);
+  const size_t tab_bytes = align_up((size_t)B * slots * VOX_EF * sizeof(float), 256);
   const int words = (int)vox_bitmap_words(V);
-  int* tkeys = (int*)ws;
-  float* tvals = (float*)((char*)ws + key_bytes);
-  uint32_t* bitmap = (uint32_t*)((char*)ws + key_bytes + val_bytes);
-  VXB_CUDA(cudaMemsetAsync(ws, 0, key_bytes + val_bytes + (size_t)B * words * 4, st));
+  float* table = (float*)ws;
+  uint32_t* bitmap = (uint32_t*)((char*)ws + tab_bytes);
+  VXB_CUDA(cudaMemsetAsync(ws, 0, tab_bytes + (size_t)B * words * 4, st));
   dim3 g1(cdiv(N, 256), B);
-  vox_scatter_kernel<F, DEPTH><<<g1, 256, 0, st>>>(coords, feats, bounds, Bb, N, V, tkeys, tvals, slots, bitmap, words, out_idx, ds);
+  vox_scatter_kernel<F, DEPTH><<<g1, 256, 0, st>>>(coords, feats, bounds, Bb, N, V, table, slots, bitmap, words, out_idx, ds);
   VXB_LAUNCH_CHECK();
   const long long V3 = (long long)V * V * V;
-  const size_t fill_smem = ((size_t)((V + 3) & ~3) * 9 + 8 * (size_t)V * CH) * sizeof(float);
+  // i / V table + template row + 8 occupied-voxel lists + one selector byte per float4 of the row
+  const size_t fill_smem = align_up(((size_t)((V + 3) & ~3) + (size_t)V * CH + 8 * (size_t)V) * sizeof(float) + (size_t)V * CH / 4, 16);
   if ((V * CH) % 4 == 0 && (((uintptr_t)out) & 15) == 0 && fill_smem <= 200 * 1024 && V <= 960) {
+    auto kern = vox_fill_rows_kernel<F>;
     static size_t attr = 0;
     if (fill_smem > 48 * 1024 && fill_smem > attr) {
-      VXB_CUDA(cudaFuncSetAttribute(vox_fill_rows_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      VXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr = 200 * 1024;
     }
     // persistent blocks (B rows of them), 8 voxel rows per block and iteration
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(fill_smem, 1)));
+    static int per_sm = 0;
+    static size_t per_sm_smem = (size_t)-1;
+    if (per_sm_smem != fill_smem) {
+      VXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, fill_smem));
+      per_sm = std::max(1, per_sm);
+      per_sm_smem = fill_smem;
+    }
     const int bx = (int)std::max<long long>(1, std::min<long long>(cdiv((long long)V * V, 8), cdiv(148 * per_sm, B)));
-    vox_fill_rows_kernel<F><<<dim3(bx, B), 256, fill_smem, st>>>(tkeys, tvals, slots, bitmap, words, V, out);
+    kern<<<dim3(bx, B), 256, fill_smem, st>>>(table, slots, bitmap, words, V, out);
     VXB_LAUNCH_CHECK();
   } else {
     // generic geometry: position pattern, then one thread per table slot patches the occupied voxels
     vox_background_scalar_kernel<CH><<<dim3((int)std::min<long long>(cdiv(V3, 256), 148 * 8), B), 256, 0, st>>>(out, V, (unsigned int)V3);
     VXB_LAUNCH_CHECK();
-    vox_occupied_kernel<F><<<dim3(cdiv(slots, 256), B), 256, 0, st>>>(tkeys, tvals, slots, (int)V3, out);
+    vox_occupied_kernel<F><<<dim3(cdiv(slots, 256), B), 256, 0, st>>>(table, slots, (int)V3, out);
     VXB_LAUNCH_CHECK();
   }
   return VXB_OK;
