@@ -76,7 +76,7 @@ inline int upconv3d_folded(const float* low, const float* wfold, const float* bi
                            int B, int S, int Ci, int Co, int s, float act_slope, int math_mode,
                            cudaStream_t st, Arena* scratch = nullptr, const umma::Planes* Wpre = nullptr,
                            const umma::Planes* out_planes = nullptr, const float* f8a = nullptr,
-                           const umma::F8cGemm* f8g = nullptr) {
+                           const umma::F8cGemm* f8g = nullptr, const umma::UpconvSparsity* sp = nullptr) {
   if (math_mode == VXB_MATH_BF16X3 && scratch && Ci % 64 == 0 && Co == 64) {
     Arena local(scratch->base, scratch->cap);
     umma::Planes wp;
@@ -93,7 +93,7 @@ inline int upconv3d_folded(const float* low, const float* wfold, const float* bi
       }
       VXB_TRY(umma::split_rows(wfold, Kt, Nt, (int)Kt, wp, st));
     }
-    return umma::upconv_f32(low, wp, bias, out, B, S, Ci, Co, s, act_slope, local, st, out_planes, f8a, f8g);
+    return umma::upconv_f32(low, wp, bias, out, B, S, Ci, Co, s, act_slope, local, st, out_planes, f8a, f8g, sp);
   }
   GemmParams p;
   gemm_params_init(p);

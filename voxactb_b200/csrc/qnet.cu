@@ -98,6 +98,11 @@ struct Prepared {
   float* up1_abs;           // [s^3 * 64][64]
   __nv_bfloat16* up1_f8[2]; // folded up-conv weights as the f8c operand of the GEMM engine (upconv_f8c_prepare)
   float* up1_beta;          // [1] their e4m3 scale
+  // block sparsity of the folded up-conv weights (umma::upconv_kmask_build): non-zero taps per phase, the phase order of the
+  // f8c planes, K-block masks per N tile for the natural order (3-term planes) and for the f8c order
+  uint32_t* up1_nz;         // [s^3]
+  uint8_t* up1_perm;        // [s^3]
+  uint32_t* up1_kmask[2];   // [64] each: natural, permuted
   float* q_cross;    // [L][ch*cdh]  = to_q(LN(latents)), batch independent
   float* lat_norm;   // [L][D] scratch for the above
   float* ff_perm_w;  // [8D][D] scratch: FF net.0 weight with the GEGLU [a | gate] 32-row interleave (split into planes)
@@ -110,6 +115,11 @@ struct Prepared {
   struct LayerF8 { umma::Planes q, kv, ff0; float* sc; };
   std::vector<LayerF8> lf8;
 };
+// the sparsity tables hold one byte per phase and one mask per 256-column tile
+static bool up_sparse(const Dims& m) {
+  const int P = m.s * m.s * m.s;
+  return P <= 255 && (P * 64 + umma::UPCONV_NT - 1) / umma::UPCONV_NT <= umma::UPCONV_MAX_TILES;
+}
 struct WeightSpec { const float* w; long long rows, cols; };
 static void add_planes(Arena& a, Prepared& p, const float* w, long long rows, long long cols) {
   umma::Planes pl;
@@ -134,6 +144,9 @@ static void carve_prepared(const Dims& m, Arena& a, Prepared& p, const void* con
   p.up1_abs = a.get<float>((size_t)m.s * m.s * m.s * 64 * 64);
   for (int i = 0; i < 2; ++i) p.up1_f8[i] = a.get<__nv_bfloat16>((size_t)m.s * m.s * m.s * 64 * 27 * 64);
   p.up1_beta = a.get<float>(4);
+  p.up1_nz = a.get<uint32_t>(256);
+  p.up1_perm = a.get<uint8_t>(256);
+  for (int i = 0; i < 2; ++i) p.up1_kmask[i] = a.get<uint32_t>(umma::UPCONV_MAX_TILES);
   p.q_cross = a.get<float>((size_t)m.L * m.ch * m.cdh);
   p.lat_norm = a.get<float>((size_t)m.L * m.D);
   p.ff_perm_w = a.get<float>((size_t)8 * m.D * m.D);
@@ -655,8 +668,9 @@ extern "C" int vxb_qnet_prepare(const vxb_qnet_desc* d, const void* const* param
   }
   if (m.fsrc == VXB_FINAL_CAT) VXB_TRY(umma::conv3_f8c_prepare(p.final_wt, 128, 64, p.final_w16, p.final_wmax, st));
   VXB_TRY(umma::conv3_f8c_fold_abs(p.up1_fold, (long long)m.s * m.s * m.s * 64, 64, p.up1_abs, st));
+  if (up_sparse(m)) VXB_TRY(umma::upconv_kmask_build(p.up1_fold, m.s, p.up1_nz, p.up1_perm, p.up1_kmask[0], p.up1_kmask[1], st));
   VXB_TRY(umma::upconv_f8c_prepare(p.up1_fold, (long long)m.s * m.s * m.s * 64, 27 * 64, umma::Planes{p.up1_f8[0], p.up1_f8[1], 27 * 64},
-                                   p.up1_beta, reinterpret_cast<unsigned int*>(p.up1_beta + 2), st));
+                                   p.up1_beta, reinterpret_cast<unsigned int*>(p.up1_beta + 2), st, up_sparse(m) ? p.up1_perm : nullptr));
   // q of the encoder cross-attention depends only on parameters: to_q(LN(latents))
   VXB_TRY(layernorm(P(VXB_P_LATENTS), P(VXB_P_CROSS_NORM_W), P(VXB_P_CROSS_NORM_B), p.lat_norm, m.L, m.D, st));
   VXB_TRY(linear(p.lat_norm, m.D, P(VXB_P_CROSS_Q_W), m.D, nullptr, nullptr, 1, 0, p.q_cross,
@@ -864,9 +878,12 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
     }
     const umma::Planes up8{pw.up1_f8[0], pw.up1_f8[1], 27 * 64};
     const umma::F8cGemm f8g{w.f8s + 8, w.f8s + 9};
+    // all-zero (phase, tap) blocks of the folded weights are skipped; the f8c planes are stored in the phase order that
+    // lets an N tile skip the most
+    const umma::UpconvSparsity sp{pw.up1_kmask[f8c ? 1 : 0], f8c ? pw.up1_perm : nullptr};
     VXB_TRY(upconv3d_folded(w.low, pw.up1_fold, P(VXB_P_UP1_B), w.u0, B, m.S, 64, 64, m.s, slope, mm, st,
                             cx.scratch.base ? &cx.scratch : nullptr, f8c ? &up8 : cx.find(pw.up1_fold), fused_planes ? &u0p : nullptr,
-                            f8c ? w.f8s + 1 : nullptr, f8c ? &f8g : nullptr));
+                            f8c ? w.f8s + 1 : nullptr, f8c ? &f8g : nullptr, up_sparse(m) ? &sp : nullptr));
   }
   STAGE_MARK();  // 8: final conv
   // (11) final: conv3 on cat[d0, u0] (128 -> 64)                               :462

@@ -321,8 +321,10 @@ static int qnet_forward_train_impl(const vxb_qnet_desc* d, const Dims& m, const 
   // (8) up0: conv k (C -> 64) at S^3, folded upsample-conv                                          :454
   VXB_TRY(conv3d(w.dec, nullptr, m.C, 0, pw.up0_wt, P(VXB_P_UP0_B), w.low, B, m.S, m.S, 64, m.k, 1, slope, mm, st,
                  cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.up0_wt)));
+  const umma::UpconvSparsity up_sp{pw.up1_kmask[0], nullptr};       // natural phase order: the 3-term planes of up1_fold
   VXB_TRY(upconv3d_folded(w.low, pw.up1_fold, P(VXB_P_UP1_B), w.u0, B, m.S, 64, 64, m.s, slope, mm, st,
-                          cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.up1_fold), nullptr));
+                          cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.up1_fold), nullptr, nullptr, nullptr,
+                          up_sparse(m) ? &up_sp : nullptr));
   // (9) final conv on cat[d0, u0]                                                                   :462
   if (mm == VXB_MATH_BF16X3 && cx.scratch.base) {
     // input-stationary tcgen05 convolution (conv_umma.cuh) with the fp32 store epilogue: the GEMM-engine form re-fetches its

@@ -218,7 +218,7 @@ struct SmemLayout {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /* alignment slack */;   // dynamic part
 };
 
-enum { EPIK_GENERIC = 0, EPIK_PLAIN = 1, EPIK_ROWMAX = 2, EPIK_EXP = 3, EPIK_GEGLU = 4 };
+enum { EPIK_GENERIC = 0, EPIK_PLAIN = 1, EPIK_ROWMAX = 2, EPIK_EXP = 3, EPIK_GEGLU = 4, EPIK_PHASE = 5 };
 
 template <int NT, int STAGES, int EPI>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
@@ -276,9 +276,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
         int n0 = nt * NT + zb * p.w_row_zb + zh * p.w_row_zh;
         int tap_col = 0, tap_rot = 0;
         if (p.tap_m) { m0 -= mt * BM; tap_col = p.tap_acol[mt]; n0 += p.tap_wrow[mt]; tap_rot = p.tap_rot[mt]; }
+        const uint32_t km = p.kmask ? __ldg(p.kmask + nt) : 0xffffffffu;
         for (int kb0 = 0; kb0 < pl.num_kb; ++kb0) {
           int kb = kb0 + tap_rot;
           if (kb >= pl.num_kb) kb -= pl.num_kb;
+          if (p.kmask && !((km >> kb) & 1u)) continue;             // all-zero weight block of this N tile
           int a_row = 0, a_col = kb * BK, a_src = 0;
           if (pl.taps) {
             const int tap = kb / pl.cpb, cb = kb - tap * pl.cpb;
@@ -338,7 +340,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_u + (uint32_t)(acc * NT);
+        uint32_t km = 0xffffffffu;
+        int last_kb = num_kb - 1;
+        if (p.kmask) {
+          km = __ldg(p.kmask + (tile % (p.m_tiles * p.n_tiles)) % p.n_tiles);
+          last_kb = 31 - __clz((int)km);
+        }
+        uint32_t started = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
+          if (p.kmask && !((km >> kb) & 1u)) continue;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
@@ -349,7 +359,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
           if (leader) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              tc_mma_bf16_lo(d_tmem, a_hi + 2 * k, b_hi + 2 * k, kDescHi, idesc, (kb | k) != 0);
+              tc_mma_bf16_lo(d_tmem, a_hi + 2 * k, b_hi + 2 * k, kDescHi, idesc, (started | k) != 0);
               if (three) {
                 tc_mma_bf16_lo(d_tmem, a_hi + 2 * k, b_lo + 2 * k, kDescHi, idesc, 1);
                 tc_mma_bf16_lo(d_tmem, a_lo + 2 * k, b_hi + 2 * k, kDescHi, idesc, 1);
@@ -357,8 +367,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
               if (f8c) tc_mma_f8_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc8, 1);
             }
             tc_commit(&empty_bar[stage]);             // smem slot reusable once these MMAs retire
-            if (kb == num_kb - 1) tc_commit(&acc_full[acc]);   // accumulator complete -> epilogue
+            if (kb == last_kb) tc_commit(&acc_full[acc]);   // accumulator complete -> epilogue
           }
+          started = 1;
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -373,6 +384,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
     // EPI selects a compile-time specialisation (the generic body costs ~60 instructions per element):
     //   EPIK_PLAIN   ROWS_PLAIN store (bias / LeakyReLU / residual / row scale; fp32 and/or plane outputs)
     //   EPIK_ROWMAX  attention pass 1, EPIK_EXP attention pass 2, EPIK_GENERIC convolution row modes + V^T planes
+    //   EPIK_PHASE   ROWS_PHASE store of the folded up-convolution (bias / LeakyReLU; fp32 rows or hi + lo / c8 planes of the
+    //                fine grid).  With the generic body this GEMM was epilogue-bound: 28 us per 128 x 256 tile on four warps
+    //                against 18 us of MMAs, so skipping a third of the K blocks (Params::kmask) changed nothing.
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const Epilogue& e = p.ep;
     const int ew = warp - 2;                        // epilogue warp index
@@ -412,9 +426,93 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
             }
           }
         }
+        // PHASE: fine-grid row of phase 0 of each of this lane's eight column-domain rows (-1 = halo row, not stored)
+        [[maybe_unused]] long long base_r[8];
+        if constexpr (EPI == EPIK_PHASE) {
+          const int Vp = e.Vp, V = Vp - 2 * e.pad, vp3 = Vp * Vp * Vp, s = e.phase_s, oV = e.out_Vp;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = mw + i * 4 + tr;
+            const int mabs = r + zb * p.a_row_zb + p.a_row_off;   // flat row of the padded coarse grid (all batches)
+            const int qb = mabs / vp3, rr = mabs - qb * vp3;
+            const int qd = rr / (Vp * Vp) - e.pad, qh = (rr / Vp) % Vp - e.pad, qw = rr % Vp - e.pad;
+            const bool ok = r < e.M && qd >= 0 && qd < V && qh >= 0 && qh < V && qw >= 0 && qw < V;
+            base_r[i] = ok ? (((long long)qb * oV + qd * s + e.out_pad) * oV + qh * s + e.out_pad) * oV + qw * s + e.out_pad : -1;
+          }
+        }
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
-        if constexpr (EPI == EPIK_GEGLU) {
+        if constexpr (EPI == EPIK_PHASE) {
+          const int s = e.phase_s, oV = e.out_Vp;
+          float* const o32 = e.out_f32 ? e.out_f32 + zb * p.c_zb + zh * p.c_zh : nullptr;
+          __nv_bfloat16* const ohi = e.out_hi ? e.out_hi + zb * p.p_zb + zh * p.p_zh : nullptr;
+          __nv_bfloat16* const olo = e.out_lo ? e.out_lo + zb * p.p_zb + zh * p.p_zh : nullptr;
+          const float fa = e.f8a ? __ldg(e.f8a) : 0.f;
+#pragma unroll 1
+          for (int c0 = half * 32; c0 < NT; c0 += 64) {
+            const int n = n0 + c0;
+            if (n >= e.N) break;                       // warp-uniform (N is a multiple of 64: chunks are whole)
+            uint32_t v[32];
+            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + c0), v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(stage + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) =
+                  make_float4(__uint_as_float(v[j]) * alpha_f, __uint_as_float(v[j + 1]) * alpha_f,
+                              __uint_as_float(v[j + 2]) * alpha_f, __uint_as_float(v[j + 3]) * alpha_f);
+            __syncwarp();
+            // 64-column block = one polyphase: fine voxel = s * q + r in the (padded) fine grid
+            const int ph = e.phase_perm ? (int)__ldg(e.phase_perm + (n >> 6)) : (n >> 6);
+            const int rd = ph / (s * s), rh = (ph / s) % s, rw = ph % s;
+            const long long poff = ((long long)rd * oV + rh) * oV + rw;
+            const int ncol = (n & 63) + tc;
+            float4 x4[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + tr;
+              x4[i] = *reinterpret_cast<const float4*>(stage + r * 32 + ((((lane & 7)) ^ (r & 7)) << 2));
+            }
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e.bias) bv = __ldg(reinterpret_cast<const float4*>(e.bias + ncol));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4& x = x4[i];
+              x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+              x.x = fmaxf(x.x, x.x * slope); x.y = fmaxf(x.y, x.y * slope);
+              x.z = fmaxf(x.z, x.z * slope); x.w = fmaxf(x.w, x.w * slope);
+            }
+            if (o32) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (base_r[i] >= 0) *reinterpret_cast<float4*>(o32 + (base_r[i] + poff) * e.ldc + ncol) = x4[i];
+            }
+            if (ohi) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (base_r[i] < 0) continue;
+                const float4 x = x4[i];
+                const long long orow = base_r[i] + poff;
+                const __nv_bfloat162 h01 = pl2_from_floats(x.x, x.y), h23 = pl2_from_floats(x.z, x.w);
+                const float2 f01 = pl2_to_float2(h01), f23 = pl2_to_float2(h23);
+                uint2 hv;
+                hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(ohi + orow * e.ldp + ncol) = hv;
+                if (e.f8a) {
+                  // c8 plane (conv_f8c.cuh): bytes [32 x lo8 | 32 x hi8] per 32-channel block of the 64-channel row
+                  uint8_t* rowb = reinterpret_cast<uint8_t*>(olo + orow * e.ldp) + (ncol >> 5) * 64 + (ncol & 31);
+                  *reinterpret_cast<uint32_t*>(rowb) = pl_e4m3x4(x.x - f01.x, x.y - f01.y, x.z - f23.x, x.w - f23.y, fa * 2048.f);
+                  *reinterpret_cast<uint32_t*>(rowb + 32) = pl_e4m3x4(x.x, x.y, x.z, x.w, fa);
+                } else {
+                  const __nv_bfloat162 l01 = pl2_from_floats(x.x - f01.x, x.y - f01.y);
+                  const __nv_bfloat162 l23 = pl2_from_floats(x.z - f23.x, x.w - f23.y);
+                  uint2 lv;
+                  lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                  *reinterpret_cast<uint2*>(olo + orow * e.ldp + ncol) = lv;
+                }
+              }
+            }
+            __syncwarp();
+          }
+        } else if constexpr (EPI == EPIK_GEGLU) {
           // pairs of 32-column chunks: [a | gate] of the same 32 output columns; the warps of a lane quarter alternate pairs
 #pragma unroll 1
           for (int c0 = half * 64; c0 < NT; c0 += 128) {
@@ -716,7 +814,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_consta
         int ncol0 = n;                                // column of the chunk inside the output row
         if (e.row_mode == ROWS_PHASE) {
           // 64-column block = one polyphase: fine voxel = s*q + r in the (padded) fine grid
-          const int ph = n / 64;
+          const int ph = e.phase_perm ? (int)__ldg(e.phase_perm + n / 64) : n / 64;
           const int s = e.phase_s;
           const int rd = ph / (s * s), rh = (ph / s) % s, rw = ph % s;
           const int oV = e.out_Vp;

@@ -40,6 +40,8 @@ struct Epilogue {
   int Vp, pad;
   int out_padded;             // CONV_FLAT: 1 = output rows keep the padded geometry (row = m), 0 = compact [B,V^3]
   int phase_s;                // ROWS_PHASE: column block j (64 cols) = phase p = n/64 -> fine voxel s*q + r
+  const uint8_t* phase_perm;  // optional device table: column block j holds phase phase_perm[j] (blocks sorted so that the
+                              // four phases of an N tile share their zero taps, see Params::kmask)
   int out_Vp, out_pad;        // ROWS_PHASE: geometry of the fine output grid (padded)
   const float* bias;          // [N] (ROWS_PHASE: [64], shared by all phases)
   float alpha;
@@ -83,6 +85,11 @@ struct Params {
   // plain [rows][K] layout of a 17M-column operand puts every row of a TMA box into its own 2 MB page: the weight-gradient GEMM
   // ran at 15 % tensor-pipe activity with DRAM at 14 % -- translation-bound).  Values = rows per K block of A / W.
   int kblk_a, kblk_w;
+  // kmask != null (num_kb <= 32): device array, one word per N tile; K block kb of that tile is loaded and multiplied only
+  // when bit kb is set.  The folded up-convolution's weight matrix is block-sparse (phase 0 of an axis never reads the +1
+  // neighbour, phase s-1 never the -1 one: 2197 of 3375 (phase, tap) blocks are non-zero); the masks come from the weights
+  // themselves (upconv_kmask_build), so skipping is exact.
+  const uint32_t* kmask;
   int tap_m;
   int tap_acol[27];
   int tap_wrow[27];
@@ -125,13 +132,20 @@ int conv3d_f32(const float* x0, const float* x1, int C0, int C1, const Planes& W
 size_t upconv_scratch_bytes(int B, int S, int Ci);
 // f8c form of the folded up-convolution GEMM: Wp = upconv_f8c_prepare planes, sc = device scalars {alpha of `low`, 1/(alpha beta)}
 struct F8cGemm { const float* alpha; const float* unscale; };
+// block sparsity of the folded weights (upconv_kmask_build): K-block mask per N tile and, optionally, the phase held by every
+// 64-column block (the weight planes must then be stored in that order: upconv_f8c_prepare(..., perm))
+constexpr int UPCONV_NT = 256, UPCONV_MAX_TILES = 64;
+struct UpconvSparsity { const uint32_t* kmask; const uint8_t* phase_perm; };
+int upconv_kmask_build(const float* wfold, int s, uint32_t* nz /*[s^3]*/, uint8_t* perm /*[s^3]*/, uint32_t* kmask_natural /*[64]*/,
+                       uint32_t* kmask_perm /*[64]*/, cudaStream_t st);
 int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out, int B, int S, int Ci, int Co, int s,
                float act_slope, Arena& scratch, cudaStream_t st, const Planes* out_planes = nullptr, const float* f8a = nullptr,
-               const F8cGemm* f8g = nullptr);
+               const F8cGemm* f8g = nullptr, const UpconvSparsity* sp = nullptr);
 // static operand of that GEMM: hi = fp16(2^-5 beta W), lo = per 64 columns [64 x e4m3(2^-11 beta W) | 64 x e4m3(beta W_lo)];
 // beta (largest power of two with 2^-11 beta max|W| <= 240) is left in *beta_out
+// (perm: output row block j of 64 rows is taken from source row block perm[j])
 int upconv_f8c_prepare(const float* wfold, long long rows, long long cols, Planes out, float* beta_out, unsigned int* tmp,
-                       cudaStream_t st);
+                       cudaStream_t st, const uint8_t* perm = nullptr);
 
 // ---- backward (training) contractions on the tensor cores ------------------------------------------------------------
 // Gradient tensors span many decades (softmax-over-10^6 logit gradients are ~1e-8), below the fp16 planes' range, so every

@@ -452,6 +452,10 @@ static int launch_t(const CUtensorMap* maps, const Params& p, cudaStream_t st) {
     if (e.mode == EPI_GEGLU) return launch_e<NT, STAGES, EPIK_GEGLU>(maps, p, st);
     return launch_e<NT, STAGES, EPIK_PLAIN>(maps, p, st);
   }
+  if (e.row_mode == ROWS_PHASE && e.mode == EPI_STORE && !e.residual && !e.row_div && !e.transpose_planes && e.N % 64 == 0 &&
+      (!e.bias || (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0) && (!e.out_f32 || ((e.ldc & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0)) && (!e.out_hi || (e.ldp & 3) == 0))
+    return launch_e<NT, STAGES, EPIK_PHASE>(maps, p, st);
   return launch_e<NT, STAGES, EPIK_GENERIC>(maps, p, st);
 }
 
@@ -645,13 +649,14 @@ static __global__ void f8c_beta_kernel(const unsigned int* __restrict__ wmax, fl
 // static weights [rows, cols] (cols % 64 == 0, ld = cols): hi = fp16(beta / 32 w), c8 blocks [64 x e4m3(2^-11 beta w) | 64 x e4m3(beta w_lo)]
 static __global__ void __launch_bounds__(256)
 split_rows_f8c_kernel(const float* __restrict__ x, long long rows, long long cols, __nv_bfloat16* __restrict__ hi,
-                      uint8_t* __restrict__ c8, const float* __restrict__ beta) {
+                      uint8_t* __restrict__ c8, const float* __restrict__ beta, const uint8_t* __restrict__ perm) {
   const long long cg = cols / 4, total = rows * cg;
   const float fb = __ldg(beta);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cg;
     const int g = (int)(i % cg);
-    const float4 a = *reinterpret_cast<const float4*>(x + r * cols + g * 4);
+    const long long rs = perm ? (long long)perm[r >> 6] * 64 + (r & 63) : r;      // output row block j <- source row block perm[j]
+    const float4 a = *reinterpret_cast<const float4*>(x + rs * cols + g * 4);
     const __nv_bfloat162 u01 = pl2_from_floats(a.x, a.y), u23 = pl2_from_floats(a.z, a.w);
     const float2 f01 = pl2_to_float2(u01), f23 = pl2_to_float2(u23);
     const float s16 = fb * (1.f / F8C_P16);
@@ -666,13 +671,75 @@ split_rows_f8c_kernel(const float* __restrict__ x, long long rows, long long col
 }
 int absmax_cols(const float* x, long long rows, int C, unsigned int* out, cudaStream_t st);
 int upconv_f8c_prepare(const float* wfold, long long rows, long long cols, Planes out, float* beta_out, unsigned int* tmp,
-                       cudaStream_t st) {
+                       cudaStream_t st, const uint8_t* perm) {
+  if (perm && rows % 64) { set_error("upconv_f8c_prepare: a row-block permutation needs rows %% 64 == 0"); return VXB_E_BADARG; }
   if (cols % 64 || out.ld != cols) { set_error("upconv_f8c_prepare: cols must be a multiple of 64 with ld == cols"); return VXB_E_BADARG; }
   VXB_CUDA(cudaMemsetAsync(tmp, 0, sizeof(unsigned int), st));
   VXB_TRY(absmax_cols(wfold, rows * cols, 1, tmp, st));
   f8c_beta_kernel<<<1, 1, 0, st>>>(tmp, beta_out);
   VXB_LAUNCH_CHECK();
-  split_rows_f8c_kernel<<<148 * 8, 256, 0, st>>>(wfold, rows, cols, out.hi, reinterpret_cast<uint8_t*>(out.lo), beta_out);
+  split_rows_f8c_kernel<<<148 * 8, 256, 0, st>>>(wfold, rows, cols, out.hi, reinterpret_cast<uint8_t*>(out.lo), beta_out, perm);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// ---- block sparsity of the folded up-convolution weights [P * 64][27 * 64] (P = s^3 phases): which (phase, tap) blocks hold a
+// non-zero value (nz[phase], bit = tap), an order of the phases in which the phases of one N tile share their zero taps
+// (greedy: seed = the remaining phase with the most taps, then the phases that grow the tile's union least), and the K-block
+// mask of every N tile in that order (Params::kmask).  All on the device: nothing here depends on host-side knowledge of the
+// up-sampling stencil, the masks are read off the weights.
+static __global__ void __launch_bounds__(256)
+upconv_block_nz_kernel(const float* __restrict__ wfold, uint32_t* __restrict__ nz) {
+  const int nb = blockIdx.x, ph = blockIdx.y;
+  const float* base = wfold + ((size_t)ph * 64) * (27 * 64) + (size_t)nb * 64;
+  int any = 0;
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) any |= base[(size_t)(i >> 6) * (27 * 64) + (i & 63)] != 0.f;
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0 && any) atomicOr(nz + ph, 1u << nb);
+}
+static __global__ void upconv_phase_order_kernel(const uint32_t* __restrict__ nz, int P, int per_tile, uint8_t* __restrict__ perm) {
+  __shared__ uint8_t used[256];
+  if (threadIdx.x) return;
+  for (int i = 0; i < P; ++i) used[i] = 0;
+  int n = 0;
+  while (n < P) {
+    int seed = -1, best = -1;
+    for (int q = 0; q < P; ++q)
+      if (!used[q] && __popc(nz[q]) > best) { best = __popc(nz[q]); seed = q; }
+    used[seed] = 1; perm[n++] = (uint8_t)seed;
+    uint32_t m = nz[seed];
+    for (int k = 1; k < per_tile && n < P; ++k) {
+      int c = -1, grow = 1 << 30, own = -1;
+      for (int q = 0; q < P; ++q) {
+        if (used[q]) continue;
+        const int g = __popc(m | nz[q]), o = __popc(nz[q]);
+        if (g < grow || (g == grow && o > own)) { grow = g; own = o; c = q; }
+      }
+      used[c] = 1; perm[n++] = (uint8_t)c;
+      m |= nz[c];
+    }
+  }
+}
+static __global__ void upconv_tile_mask_kernel(const uint32_t* __restrict__ nz, const uint8_t* __restrict__ perm, int P, int per_tile,
+                                               int n_tiles, uint32_t* __restrict__ kmask) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  uint32_t m = 0;
+  for (int j = t * per_tile; j < min(P, (t + 1) * per_tile); ++j) m |= nz[perm ? perm[j] : j];
+  kmask[t] = m ? m : 1u;            // a tile never skips everything: its accumulator must be written
+}
+int upconv_kmask_build(const float* wfold, int s, uint32_t* nz, uint8_t* perm, uint32_t* kmask_natural, uint32_t* kmask_perm,
+                       cudaStream_t st) {
+  const int P = s * s * s, per_tile = UPCONV_NT / 64, n_tiles = cdiv(P * 64, UPCONV_NT);
+  if (P > 255 || n_tiles > UPCONV_MAX_TILES) { set_error("upconv_kmask_build: s=%d not supported", s); return VXB_E_UNSUPPORTED_SHAPE; }
+  VXB_CUDA(cudaMemsetAsync(nz, 0, (size_t)P * sizeof(uint32_t), st));
+  upconv_block_nz_kernel<<<dim3(27, P), 256, 0, st>>>(wfold, nz);
+  VXB_LAUNCH_CHECK();
+  upconv_phase_order_kernel<<<1, 32, 0, st>>>(nz, P, per_tile, perm);
+  VXB_LAUNCH_CHECK();
+  upconv_tile_mask_kernel<<<1, 256, 0, st>>>(nz, nullptr, P, per_tile, n_tiles, kmask_natural);
+  VXB_LAUNCH_CHECK();
+  upconv_tile_mask_kernel<<<1, 256, 0, st>>>(nz, perm, P, per_tile, n_tiles, kmask_perm);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }
@@ -681,7 +748,7 @@ int upconv_f8c_prepare(const float* wfold, long long rows, long long cols, Plane
 // replicate-padded fine grid [B,(S*s+2)^3,64] (interior written here, halo by halo_fill); Wp planes of [s^3*64][27*Ci]
 int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out, int B, int S, int Ci, int Co, int s,
                float act_slope, Arena& scratch, cudaStream_t st, const Planes* out_planes, const float* f8a,
-               const F8cGemm* f8g) {
+               const F8cGemm* f8g, const UpconvSparsity* sp) {
   if (Ci % 64 || Co != 64) {
     set_error("umma upconv: needs Ci %% 64 == 0 and Co == 64");
     return VXB_E_UNSUPPORTED_SHAPE;
@@ -699,7 +766,8 @@ int upconv_f32(const float* low, const Planes& Wp, const float* bias, float* out
   params_init(p);
   if (f8g) { p.terms = 2; p.ep.alpha_dev = f8g->unscale; }
   const int N = s * s * s * 64;
-  const int nt = 256;
+  const int nt = UPCONV_NT;
+  if (sp && sp->kmask && Ci == 64) { p.kmask = sp->kmask; p.ep.phase_perm = sp->phase_perm; }   // 27 K blocks = 27 taps
   // one batch entry per sample, restricted to the rows between the first and the last interior voxel (the two
   // all-halo z planes of the padded low-resolution grid are skipped)
   const long long sp3 = Sp * Sp * Sp;
