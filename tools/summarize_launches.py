@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel summary of an `ncu --metrics gpu__time_duration.sum --csv` launch list (profiles/launches_*.csv):
-launch count, total time and share of the LAST complete forward in the file (from its input_preprocess launch on).
+launch count, total time and share of the LAST complete forward in the file (between its input_preprocess launch and
+the next one; the capture's launch limit usually cuts the final forward short).
 
     python tools/summarize_launches.py profiles/launches_r01_final.csv
 
@@ -17,7 +18,15 @@ def main(path):
     ki, vi = h.index('Kernel Name'), h.index('Metric Value')
     seq = [(r[ki], float(r[vi].replace(',', ''))) for r in rows[1:]]
     starts = [i for i, (n, _) in enumerate(seq) if 'input_preprocess' in n]
-    seq = seq[starts[-1]:] if starts else seq
+    if len(starts) >= 2:
+        a, b = starts[-2], starts[-1]
+        # the forward ends where the next voxelizer call begins; its own voxelizer launches sit right before its start
+        nxt = [i for i in range(a, b) if 'vox_scatter' in seq[i][0]]
+        body = seq[a:(nxt[0] if nxt else b)]
+        head = [x for x in seq[max(0, a - 4):a] if 'vox_' in x[0]][-2:]
+        seq = head + body
+    elif starts:
+        seq = seq[starts[-1]:]
     agg = collections.OrderedDict()
     for n, v in seq:
         k = n.split('(')[0][:64]
