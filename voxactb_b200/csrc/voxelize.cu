@@ -97,18 +97,18 @@ __device__ __forceinline__ float4 ld_keep(const float4* addr, uint64_t pol) {
 }
 constexpr int VOX_EF = 8, VOX_KEY = 7;
 
-// One block of 256 points of sample b.  BITMAP: also mark the voxel in the occupancy bitmap (read by vox_fill_rows_kernel; the
-// table-scan patch of the fused path does not need it, which saves one atomic per voxel group).
-template <int F, bool DEPTH, bool BITMAP>
-__device__ __forceinline__ void vox_scatter_block(const float* __restrict__ coords, const float* __restrict__ feats,
+template <int F, bool DEPTH>
+__global__ void __launch_bounds__(256)
+vox_scatter_kernel(const float* __restrict__ coords, const float* __restrict__ feats,
                    const float* __restrict__ bounds, int Bb, int N, int V,
                    float* __restrict__ table, int slots,
                    uint32_t* __restrict__ bitmap, int bitmap_words,
-                   int32_t* __restrict__ out_idx, const DepthSrc& ds, const int b, const int chunk) {
+                   int32_t* __restrict__ out_idx, const DepthSrc ds) {
+  const int b = blockIdx.y;
   __shared__ AxisMap maps[3];
   if (threadIdx.x == 0) make_axis_maps(bounds + (Bb == 1 ? 0 : b) * 6, V, maps);
   __syncthreads();
-  const int n = chunk * blockDim.x + threadIdx.x;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = n < N;
   float val[3 + F];
   int key = 0;
@@ -184,21 +184,8 @@ __device__ __forceinline__ void vox_scatter_block(const float* __restrict__ coor
     atomicAdd(e + 6, val[5]);
   }
   static_assert(F == 0 || F == 3, "feature sizes compiled: 0 and 3");
-  if constexpr (BITMAP) {
-    const int vid = key - 1;
-    atomicOr(bitmap + (size_t)b * bitmap_words + (vid >> 5), 1u << (vid & 31));
-  }
-}
-
-template <int F, bool DEPTH>
-__global__ void __launch_bounds__(256)
-vox_scatter_kernel(const float* __restrict__ coords, const float* __restrict__ feats,
-                   const float* __restrict__ bounds, int Bb, int N, int V,
-                   float* __restrict__ table, int slots,
-                   uint32_t* __restrict__ bitmap, int bitmap_words,
-                   int32_t* __restrict__ out_idx, const DepthSrc ds) {
-  vox_scatter_block<F, DEPTH, true>(coords, feats, bounds, Bb, N, V, table, slots, bitmap, bitmap_words, out_idx, ds,
-                                    (int)blockIdx.y, (int)blockIdx.x);
+  const int vid = key - 1;
+  atomicOr(bitmap + (size_t)b * bitmap_words + (vid >> 5), 1u << (vid & 31));
 }
 
 // exact n / d for n < 2^32 with one 64-bit high multiply: m = ceil(2^64 / d)
@@ -385,113 +372,6 @@ vox_fill_rows_kernel(const float* __restrict__ table, int slots,
   }
 }
 
-// Fourth design (shipped): the scatter and the background stores use disjoint resources -- L2 atomic throughput (DRAM at 19 %)
-// against the DRAM write stream (no table access at all) -- so ONE launch runs both: the first `fill_blocks` blocks are
-// persistent background writers (template row + x / V, y / V register patches, exactly the v3 background, every row of every
-// sample, no bitmap, no look-ups), the blocks after them are the 256-point scatter blocks, which flow through the SM slots the
-// writers leave free.  The occupied voxels (6 %) are written afterwards by vox_patch_kernel, one thread per table slot: a
-// sequential scan of the table instead of ~1.5 M random 64-byte look-ups inside the store stream (what bounded v3's fill:
-// 116 us of pure stores, 160 us with the look-ups), and no occupancy bitmap (one atomic less per voxel group in the scatter).
-template <int F, bool DEPTH>
-__global__ void __launch_bounds__(256, 6)
-vox_scatter_fill_kernel(const float* __restrict__ coords, const float* __restrict__ feats, const float* __restrict__ bounds,
-                        int Bb, int B, int N, int V, float* __restrict__ table, int slots, int32_t* __restrict__ out_idx,
-                        const DepthSrc ds, int fill_blocks, int chunks, float* __restrict__ out) {
-  if ((int)blockIdx.x >= fill_blocks) {
-    const int s = (int)blockIdx.x - fill_blocks;
-    const int b = s / chunks;
-    vox_scatter_block<F, DEPTH, false>(coords, feats, bounds, Bb, N, V, table, slots, nullptr, 0, out_idx, ds, b, s - b * chunks);
-    return;
-  }
-  constexpr int CH = 7 + F;
-  extern __shared__ __align__(16) float vf_smem[];
-  const int lut_floats = (V + 3) & ~3, row_floats = V * CH, row_f4 = row_floats / 4;   // row_floats % 4 == 0 (launcher)
-  float* lut = vf_smem;                                            // i / V
-  float* tmpl = lut + lut_floats;                                  // one background row with x = y = 0
-  uint8_t* sel = reinterpret_cast<uint8_t*>(tmpl + row_floats);    // per float4: which elements are the x / y channels
-  for (int i = threadIdx.x; i < V; i += blockDim.x) lut[i] = __fdiv_rn((float)i, (float)V);
-  __syncthreads();
-  for (int p = threadIdx.x; p < row_floats; p += blockDim.x) {
-    const int iz = p / CH, ch = p - iz * CH;
-    tmpl[p] = ch == 5 + F ? lut[iz] : 0.f;
-  }
-  constexpr bool PAIR = CH % 4 == 2 && (3 + F) % 2 == 0;
-  for (int q = threadIdx.x; q < row_f4; q += blockDim.x) {
-    int s = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int ch = (4 * q + j) % CH;
-      if constexpr (PAIR) {
-        if (ch == 3 + F) s = j == 0 ? 1 : 2;
-      } else {
-        if (ch == 3 + F) s |= j + 1;
-        if (ch == 4 + F) s |= (j + 1) << 4;
-      }
-    }
-    sel[q] = (uint8_t)s;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float4* tmpl4 = reinterpret_cast<const float4*>(tmpl);
-  const int rows = V * V;
-  const long long rows_total = (long long)B * rows, step = (long long)fill_blocks * 8;
-  for (long long r = (long long)blockIdx.x * 8 + warp; r < rows_total; r += step) {
-    const int row = (int)(r % rows);
-    const int ix = row / V, iy = row - ix * V;
-    const float fx = lut[ix], fy = lut[iy];
-    float4* o4 = reinterpret_cast<float4*>(out + (size_t)r * row_floats);
-    for (int q = lane; q < row_f4; q += 32) {
-      float4 v = tmpl4[q];
-      const int s = sel[q];
-      if constexpr (PAIR) {
-        if (s == 1) { v.x = fx; v.y = fy; }
-        if (s == 2) { v.z = fx; v.w = fy; }
-      } else {
-        const int jx = s & 15, jy = s >> 4;
-        if (jx == 1) v.x = fx; else if (jx == 2) v.y = fx; else if (jx == 3) v.z = fx; else if (jx == 4) v.w = fx;
-        if (jy == 1) v.x = fy; else if (jy == 2) v.y = fy; else if (jy == 3) v.z = fy; else if (jy == 4) v.w = fy;
-      }
-      __stcs(o4 + q, v);
-    }
-  }
-}
-
-// Occupied voxels of the fused path, one thread per table slot: mean = sum / clamp(count, 1) (voxel_grid.py:119), position
-// channels index / V (:197), occupancy 1 (:192) -- the whole (7+F)-float record, over the background the launch before wrote.
-template <int F>
-__global__ void __launch_bounds__(256)
-vox_patch_kernel(const float* __restrict__ table, int slots, int V, float* __restrict__ out) {
-  constexpr int CH = 7 + F;
-  const int b = blockIdx.y;
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= slots) return;
-  const float4* e = reinterpret_cast<const float4*>(table + ((size_t)b * slots + s) * VOX_EF);
-  const float4 c = __ldcs(e + 1);
-  const int key = __float_as_int(c.w);
-  if (key == 0) return;
-  const float4 a = __ldcs(e);
-  float v[CH];
-  {
-    float m[3 + F];
-    vox_entry_mean<F>(a, c, m);
-#pragma unroll
-    for (int j = 0; j < 3 + F; ++j) v[j] = m[j];
-  }
-  const int vid = key - 1;
-  const int t = vid / V, iz = vid - t * V, ix = t / V, iy = t - ix * V;
-  const float fv = (float)V;
-  v[3 + F] = __fdiv_rn((float)ix, fv); v[4 + F] = __fdiv_rn((float)iy, fv); v[5 + F] = __fdiv_rn((float)iz, fv);
-  v[CH - 1] = 1.f;
-  float* r = out + ((size_t)b * V * V * V + vid) * CH;
-  if constexpr (CH % 2 == 0) {
-#pragma unroll
-    for (int j = 0; j < CH; j += 2) *reinterpret_cast<float2*>(r + j) = make_float2(v[j], v[j + 1]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < CH; ++j) r[j] = v[j];
-  }
-}
-
 // generic geometry (V * (7+F) not a multiple of 4): scalar position pattern + per-slot patch
 template <int CH>
 __global__ void __launch_bounds__(256)
@@ -559,33 +439,11 @@ static int voxelize_impl(const float* coords, const float* feats, const float* b
   const int words = (int)vox_bitmap_words(V);
   float* table = (float*)ws;
   uint32_t* bitmap = (uint32_t*)((char*)ws + tab_bytes);
-  const long long V3 = (long long)V * V * V;
-  // VXB_VOX_PATH=v3 keeps the previous two-kernel design (scatter, then a fill with look-ups) for A/B measurements;
-  // VXB_VOX_FILL_PER_SM = persistent background blocks per SM in the fused launch (of 6 resident; default 4)
-  static const int vox_path = [] { const char* e = getenv("VXB_VOX_PATH"); return (e && e[0] == 'v' && e[1] == '3') ? 3 : 4; }();
-  static const int fill_per_sm = [] { const char* e = getenv("VXB_VOX_FILL_PER_SM"); const int v = e ? atoi(e) : 4; return std::min(6, std::max(1, v)); }();
-  const long long chunks = cdiv(N, 256);
-  if (vox_path == 4 && (V * CH) % 4 == 0 && (((uintptr_t)out) & 15) == 0 && V <= 960 && chunks * B < (1ll << 30)) {
-    VXB_CUDA(cudaMemsetAsync(ws, 0, tab_bytes, st));
-    const size_t smem = align_up(((size_t)((V + 3) & ~3) + (size_t)V * CH) * sizeof(float) + (size_t)V * CH / 4, 16);
-    auto kern = vox_scatter_fill_kernel<F, DEPTH>;
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-      VXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      attr = 64 * 1024;
-    }
-    const int fill_blocks = (int)std::max<long long>(1, std::min<long long>(cdiv((long long)B * V * V, 8), 148ll * fill_per_sm));
-    kern<<<(unsigned)(fill_blocks + chunks * B), 256, smem, st>>>(coords, feats, bounds, Bb, B, N, V, table, slots, out_idx, ds,
-                                                                 fill_blocks, (int)chunks, out);
-    VXB_LAUNCH_CHECK();
-    vox_patch_kernel<F><<<dim3(cdiv(slots, 256), B), 256, 0, st>>>(table, slots, V, out);
-    VXB_LAUNCH_CHECK();
-    return VXB_OK;
-  }
   VXB_CUDA(cudaMemsetAsync(ws, 0, tab_bytes + (size_t)B * words * 4, st));
   dim3 g1(cdiv(N, 256), B);
   vox_scatter_kernel<F, DEPTH><<<g1, 256, 0, st>>>(coords, feats, bounds, Bb, N, V, table, slots, bitmap, words, out_idx, ds);
   VXB_LAUNCH_CHECK();
+  const long long V3 = (long long)V * V * V;
   // i / V table + template row + 8 occupied-voxel lists + one selector byte per float4 of the row
   const size_t fill_smem = align_up(((size_t)((V + 3) & ~3) + (size_t)V * CH + 8 * (size_t)V) * sizeof(float) + (size_t)V * CH / 4, 16);
   if ((V * CH) % 4 == 0 && (((uintptr_t)out) & 15) == 0 && fill_smem <= 200 * 1024 && V <= 960) {
