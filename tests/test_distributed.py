@@ -40,7 +40,7 @@ def _worker(rank, world, port, n, out_dir):
 
 
 def _grad_worker(rank, world, port, out_dir):
-    """DDP-equivalent gradient averaging of the training step (voxactb_b200.train.allreduce_gradients; the reference
+    """DDP-equivalent gradient averaging of the training step (voxactb_b200.train.GradientReducer, the flat-arena reducer of PerActTrainer.update; the reference
     wraps the Q-network in DDP over gloo, agent:50-54): several buckets, ragged sizes, a parameter without a gradient."""
     from voxactb_b200 import train
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -53,7 +53,9 @@ def _grad_worker(rank, world, port, out_dir):
         base = [torch.randn(*s, generator=g) for s in shapes]
         for p, b in zip(params, base):
             p.grad = b * (rank + 1)                           # rank-dependent gradient; the last parameter has none
-        train.allreduce_gradients(params, bucket_bytes=128)   # tiny buckets: exercise the flush logic
+        red = train.GradientReducer(params, bucket_bytes=128)   # tiny buckets: several slices of the flat arena, ragged tail
+        red.allreduce()
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(params[:-1], red.views))   # grads now live in the arena
         mean_factor = sum(r + 1 for r in range(world)) / world
         for p, b in zip(params, base):
             assert torch.allclose(p.grad, b * mean_factor, rtol=1e-6, atol=1e-6)

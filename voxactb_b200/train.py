@@ -137,33 +137,6 @@ class Adam(_FusedOptimizer):
         return loss
 
 
-def allreduce_gradients(params, bucket_bytes=25 << 20):
-    """DDP-equivalent gradient averaging (reference agent:50-54 wraps the Q-network in DDP over gloo): bucketed
-    all-reduce (sum) of the gradients over the default process group -- NCCL over NVLink on GPUs -- then / world."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return
-    world = dist.get_world_size()
-    grads = [p.grad for p in params if p.grad is not None]
-    bucket, size = [], 0
-    def flush():
-        if not bucket:
-            return
-        flat = torch.cat([g.reshape(-1) for g in bucket])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat.div_(world)
-        o = 0
-        for g in bucket:
-            g.copy_(flat[o:o + g.numel()].view_as(g))
-            o += g.numel()
-    for g in grads:
-        bucket.append(g)
-        size += g.numel() * g.element_size()
-        if size >= bucket_bytes:
-            flush()
-            bucket, size = [], 0
-    flush()
-
-
 class PerActTrainer:
     """Host-side mirror of the training half of QAttentionPerActBCAgent (reference qattention_peract_bc_agent.py:418-641)
     for one QFunction: ``update`` = forward (training mode) -> the four (five with the arm head) cross-entropy losses on
