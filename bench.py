@@ -46,7 +46,7 @@ def parse():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--batch', type=int, default=16, help='samples per GPU')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--math', default=os.environ.get('VXB_MATH', 'auto'), choices=['auto', 'fp32', 'bf16x3', 'f16f8c'])
+    ap.add_argument('--math', default=os.environ.get('VXB_MATH', 'auto'), choices=['auto', 'fp32', 'f16x3', 'bf16x3', 'f16f8c'])
     ap.add_argument('--workload', default='single', choices=['single', 'dual', 'crop', 'train'],
                     help='single = BASELINE config 2 geometry at --batch (headline); dual = config 3 (acting + stabilizing '
                          'encoders, low_dim 7 + arm head, on the same observations; value counts agent-passes); '
@@ -257,7 +257,7 @@ def run_ours(args):
             os.close(saved)
     L = _lib.lib()
     _lib.check(L.vxb_check_device(), 'vxb_check_device')
-    math_mode = {'fp32': _lib.MATH_FP32_SIMT, 'bf16x3': _lib.MATH_BF16X3, 'f16f8c': _lib.MATH_F16F8C,
+    math_mode = {'fp32': _lib.MATH_FP32_SIMT, 'f16x3': _lib.MATH_F16X3, 'bf16x3': _lib.MATH_F16X3, 'f16f8c': _lib.MATH_F16F8C,
                  'auto': PerceiverVoxelLangEncoder.math_mode}[args.math]
     B, V = args.batch, 100
     torch.manual_seed(1234 + rank)
@@ -417,11 +417,11 @@ def run_ours(args):
     padded = (102 / 100) ** 2 * 1.02            # rows the kernel multiplies / useful rows (replicate halo of the flat plane tiles)
     whole_tf = FLOPS_PER_PASS * B * passes_per_sample / (per_step * 1e-3) / 1e12
     dtype = {_lib.MATH_FP32_SIMT: 'f32',
-             _lib.MATH_BF16X3: 'f16x3 (split-fp16 hi/lo planes, 3 tcgen05 kind::f16 MMAs per product, fp32 accumulate in TMEM)',
+             _lib.MATH_F16X3: 'f16x3 (split-fp16 hi/lo planes, 3 tcgen05 kind::f16 MMAs per product, fp32 accumulate in TMEM)',
              _lib.MATH_F16F8C: 'f16x3 (split-fp16 hi/lo planes, fp32 accumulate in TMEM); final conv + folded up-conv: fp16 hi*hi '
                                '+ one kind::f8f6f4 E4M3 MMA carrying both 2^-11 correction terms'}[math_mode]
     kernel = {_lib.MATH_FP32_SIMT: 'final conv 3x3x3, 128->64 @100^3 (fp32 FFMA implicit GEMM)',
-              _lib.MATH_BF16X3: 'conv3_umma_kernel: final conv 3x3x3, 128->64 @100^3 (input-stationary tcgen05, split-fp16 x3)',
+              _lib.MATH_F16X3: 'conv3_umma_kernel: final conv 3x3x3, 128->64 @100^3 (input-stationary tcgen05, split-fp16 x3)',
               _lib.MATH_F16F8C: 'conv3_f8c_kernel: final conv 3x3x3, 128->64 @100^3 (input-stationary tcgen05, fp16 + E4M3-corrected, '
                                 'dz taps merged into N=192 MMAs)'}[math_mode]
     line = {
@@ -430,7 +430,7 @@ def run_ours(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': dtype,
         'data': 'synthetic',
         'config': {'workload': workload, 'global_batch': world * B, 'parallelism': 'batch-sharded x%d, no collective' % world,
-                   'math_mode': {_lib.MATH_FP32_SIMT: 'fp32_simt', _lib.MATH_BF16X3: 'split16x3_tcgen05',
+                   'math_mode': {_lib.MATH_FP32_SIMT: 'fp32_simt', _lib.MATH_F16X3: 'split16x3_tcgen05',
                                  _lib.MATH_F16F8C: 'split16x3_tcgen05 + f16_fp8c convs'}[math_mode],
                    'parity_gate': 'max|a-b| / max|b| per output tensor < 1e-3 vs the reference goldens (tests/util.py rel_err); '
                                   'voxel indices and arg-max actions bit-exact',
@@ -547,7 +547,7 @@ def run_train(args):
             os.close(saved)
     L = _lib.lib()
     _lib.check(L.vxb_check_device(), 'vxb_check_device')
-    math_mode = {'fp32': _lib.MATH_FP32_SIMT, 'bf16x3': _lib.MATH_BF16X3, 'f16f8c': _lib.MATH_F16F8C,
+    math_mode = {'fp32': _lib.MATH_FP32_SIMT, 'f16x3': _lib.MATH_F16X3, 'bf16x3': _lib.MATH_F16X3, 'f16f8c': _lib.MATH_F16F8C,
                  'auto': PerceiverVoxelLangEncoder.math_mode}[args.math]
     B, V = args.batch, 100
     torch.manual_seed(4321)                                # identical initial weights on every rank (DDP broadcast equivalent)

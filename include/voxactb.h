@@ -106,10 +106,11 @@ typedef struct vxb_qnet_desc {
 #define VXB_FINAL_D0  2
 
 #define VXB_MATH_FP32_SIMT 0  /* fp32 FFMA everywhere (reference arithmetic, slow path for parity) */
-#define VXB_MATH_BF16X3    1  /* tcgen05 split-16-bit (hi*hi + hi*lo + lo*hi; fp16 planes), fp32 accumulate in TMEM */
-#define VXB_MATH_F16F8C    2  /* as VXB_MATH_BF16X3, but the 3x3x3 final convolution forms x.w as fp16 hi*hi plus ONE E4M3 MMA that
+#define VXB_MATH_F16X3     1  /* tcgen05 split-16-bit (hi*hi + hi*lo + lo*hi; fp16 planes), fp32 accumulate in TMEM */
+#define VXB_MATH_BF16X3    VXB_MATH_F16X3  /* round-1 name (the planes were bf16 then); kept for source compatibility */
+#define VXB_MATH_F16F8C    2  /* as VXB_MATH_F16X3, but the 3x3x3 final convolution forms x.w as fp16 hi*hi plus ONE E4M3 MMA that
                                * carries both 2^-11 correction terms (conv_f8c.cuh): 2 MMA units per product instead of 3, same
-                               * accuracy class (the corrections only need ~4 bits).  Training entries treat it as VXB_MATH_BF16X3. */
+                               * accuracy class (the corrections only need ~4 bits).  Training entries treat it as VXB_MATH_F16X3. */
 
 /* Parameter slots: device pointers to contiguous fp32 tensors with the reference's shapes
  * (perceiver_lang_io.py:137-334; state-dict names in the comments). */
@@ -257,7 +258,7 @@ int vxb_se3_perturb_f32(const float* pcd, const float* xform, float* out, int B,
 
 /* ------------------------------------------------------------------ building blocks (exported for the per-op parity tests) */
 /* number of tcgen05 (split 16-bit x3) GEMM kernels launched so far by this process: lets tests prove that
- * VXB_MATH_BF16X3 really ran on the tensor cores and did not fall back to the FFMA path */
+ * VXB_MATH_F16X3 really ran on the tensor cores and did not fall back to the FFMA path */
 long long vxb_umma_launch_count(void);
 
 /* C[M,N] = act(alpha * A[M,K] * W[N,K]^T + bias[N]) (+ residual[(m % res_rows),N]); row-major fp32.

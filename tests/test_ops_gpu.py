@@ -11,8 +11,8 @@ from voxactb_b200 import _lib
 
 pytestmark = pytest.mark.gpu
 
-MODES = [_lib.MATH_FP32_SIMT, _lib.MATH_BF16X3]
-TOL = {_lib.MATH_FP32_SIMT: 2e-5, _lib.MATH_BF16X3: 1e-4}
+MODES = [_lib.MATH_FP32_SIMT, _lib.MATH_F16X3]
+TOL = {_lib.MATH_FP32_SIMT: 2e-5, _lib.MATH_F16X3: 1e-4}
 
 
 def ws(nbytes):
@@ -29,7 +29,7 @@ class tensor_core_check:
         self.before = self.lib.vxb_umma_launch_count()
 
     def __exit__(self, *exc):
-        if exc[0] is None and self.mode == _lib.MATH_BF16X3 and self.expect:
+        if exc[0] is None and self.mode == _lib.MATH_F16X3 and self.expect:
             assert self.lib.vxb_umma_launch_count() > self.before, 'BF16X3 mode did not use tcgen05'
 
 

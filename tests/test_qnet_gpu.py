@@ -12,7 +12,7 @@ import make_golden
 
 pytestmark = pytest.mark.gpu
 
-MODES = [_lib.MATH_FP32_SIMT, _lib.MATH_BF16X3, _lib.MATH_F16F8C]
+MODES = [_lib.MATH_FP32_SIMT, _lib.MATH_F16X3, _lib.MATH_F16F8C]
 
 
 def run_qfunction(c, obs, enc, mode):
@@ -189,7 +189,7 @@ def test_full_size_tensor_core_path_matches_fp32_path(cuda_lib):
     obs, enc, sd = util.make_case(c)
     _, (t0, r0, c0, g0) = run_qfunction(c, obs, enc, _lib.MATH_FP32_SIMT)
     t0, r0, c0, g0 = t0.clone(), r0.clone(), c0.clone(), g0.clone()
-    _, (t1, r1, c1, g1) = run_qfunction(c, obs, enc, _lib.MATH_BF16X3)
+    _, (t1, r1, c1, g1) = run_qfunction(c, obs, enc, _lib.MATH_F16X3)
     assert torch.equal(g0[:, 6:], g1[:, 6:])                 # index-grid + occupancy channels bit-exact
     assert torch.allclose(g0[:, :6], g1[:, :6], rtol=2e-6, atol=2e-6)   # means: atomic fp32 sums, order differs
     assert util.rel_err(t1, t0) < 5e-4 and util.rel_err(r1, r0) < util.Q_REL_TOL and util.rel_err(c1, c0) < util.Q_REL_TOL
@@ -210,7 +210,7 @@ def test_f16_fp8_mode_tracks_the_scale_of_its_operands(cuda_lib, rgb_scale, weig
                 p.mul_(weight_scale)
     _, (t0, r0, c0, _) = run_qfunction(c, obs, enc, _lib.MATH_FP32_SIMT)
     t0, r0, c0 = t0.clone(), r0.clone(), c0.clone()
-    _, (t1, r1, c1, _) = run_qfunction(c, obs, enc, _lib.MATH_BF16X3)
+    _, (t1, r1, c1, _) = run_qfunction(c, obs, enc, _lib.MATH_F16X3)
     t1, r1, c1 = t1.clone(), r1.clone(), c1.clone()
     _, (t2, r2, c2, _) = run_qfunction(c, obs, enc, _lib.MATH_F16F8C)
     assert torch.isfinite(t2).all() and torch.isfinite(r2).all()

@@ -6,7 +6,7 @@ Public surface mirrors the reference's classes for this path:
   QFunction                      (reference peract/agents/peract_bc/qattention_peract_bc_agent.py:31-135)
 All arithmetic runs in libvoxactb.so (hand-written CUDA behind the C ABI of include/voxactb.h).
 """
-from ._lib import MATH_BF16X3, MATH_F16F8C, MATH_FP32_SIMT, LIB_PATH, lib  # noqa: F401
+from ._lib import MATH_F16X3, MATH_F16F8C, MATH_FP32_SIMT, LIB_PATH, lib  # noqa: F401
 from .perceiver_lang_io import PerceiverVoxelLangEncoder, PerceiverVoxelLang2RobotsEncoder  # noqa: F401
 from .qfunction import QFunction, QFunction2Robots  # noqa: F401
 from .voxel_grid import VoxelGrid  # noqa: F401

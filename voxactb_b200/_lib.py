@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libvoxactb.so')
 
 MATH_FP32_SIMT = 0
-MATH_BF16X3 = 1
+MATH_F16X3 = 1
+MATH_BF16X3 = MATH_F16X3   # round-1 name
 MATH_F16F8C = 2
 
 c_int, c_float, c_size_t, c_void_p, c_ll = (ctypes.c_int, ctypes.c_float, ctypes.c_size_t,

@@ -268,7 +268,7 @@ extern "C" int vxb_conv3d_f32(const float* x, const float* w, const float* bias,
   if (Co == 1 && Ci == 64 && k == 3 && s == 1 && act_slope < 0.f)   // trans_decoder shape: streaming stencil
     return trans_stencil_run<64>(x, (const float*)ws, bias, y, B, Di, st);
   Arena scratch((char*)ws + conv_w_bytes(Ci, Co, k), ws_bytes - conv_w_bytes(Ci, Co, k));
-  if (math_mode == VXB_MATH_BF16X3 && s > 1 && Co == 64 && Ci == 64 && bias) {
+  if (math_mode == VXB_MATH_F16X3 && s > 1 && Co == 64 && Ci == 64 && bias) {
     // strided (patchify) convolution: gather-loader tcgen05 kernel (patchify_umma.cuh)
     __nv_bfloat16* wc = scratch.get<__nv_bfloat16>(umma::patchify_weight_elems(k));
     if (!scratch.ok) {
@@ -283,7 +283,7 @@ extern "C" int vxb_conv3d_f32(const float* x, const float* w, const float* bias,
     VXB_CHECK_ARG(k == 3 && s == 1 && Co == 64 && Ci == 64 && bias, "conv3d: VXB_MATH_F16F8C needs k=3, s=1, Ci=Co=64 and a bias");
     return umma::conv3_f8c_f32(x, (const float*)ws, bias, act_slope, y, B, Di, scratch, st);
   }
-  if (math_mode == VXB_MATH_BF16X3 && k == 3 && s == 1 && Co == 64 && Ci == 64 && bias) {
+  if (math_mode == VXB_MATH_F16X3 && k == 3 && s == 1 && Co == 64 && Ci == 64 && bias) {
     // input-stationary tcgen05 convolution (conv_umma.cuh): padded hi/lo planes + re-laid weights
     __nv_bfloat16* wc = scratch.get<__nv_bfloat16>(umma::conv3_weight_elems(Ci));
     umma::Planes xp;
@@ -347,7 +347,7 @@ extern "C" int vxb_attention_f32(const float* q, int ldq, long long q_batch_stri
     set_error("attention: workspace too small");
     return VXB_E_WORKSPACE_TOO_SMALL;
   }
-  if (math_mode == VXB_MATH_BF16X3 && dh == 64) {
+  if (math_mode == VXB_MATH_F16X3 && dh == 64) {
     Arena scratch(ws, ws_bytes);
     return umma::attention_f32(q, ldq, q_batch_stride, k, v, ldkv, kv_batch_stride, out, ldo, o_batch_stride, B, H,
                                Nq, Nk, dh, scale, scratch, (cudaStream_t)stream);

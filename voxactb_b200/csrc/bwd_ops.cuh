@@ -14,13 +14,13 @@
 namespace vxb {
 namespace bwd {
 
-// Arithmetic of the backward contractions for the current vxb_qnet_backward_f32 call: VXB_MATH_BF16X3 routes the large
+// Arithmetic of the backward contractions for the current vxb_qnet_backward_f32 call: VXB_MATH_F16X3 routes the large
 // GEMMs / convolution dgrads to the tcgen05 split-fp16 engine (operands scaled per tensor, umma::gemm_any_f32), anything
 // small -- and everything in VXB_MATH_FP32_SIMT -- runs as fp32 FFMA.
 struct TensorCtx { int mm; void* scratch; size_t scratch_bytes; };
 static thread_local TensorCtx g_tc = {VXB_MATH_FP32_SIMT, nullptr, 0};
 inline bool use_tensor(int M, int N, int K) {
-  return g_tc.mm == VXB_MATH_BF16X3 && g_tc.scratch && M >= 128 && N >= 32 && K >= 64;
+  return g_tc.mm == VXB_MATH_F16X3 && g_tc.scratch && M >= 128 && N >= 32 && K >= 64;
 }
 // returns VXB_OK when the tensor path ran, 1 when the caller should run the FFMA path, < 0 on error
 inline int try_tensor_gemm(const float* A, long long lda, bool at, const float* W, long long ldw, bool wt, float* C, int ldc,
@@ -502,7 +502,7 @@ inline int conv_dgrad_padded(const float* gz, int Co, const float* wd, int Ci, f
 inline int conv_dgrad_fold(const float* gz, int Cz, const float* wd, int Cx, float* gxp, int B, int V, int k, const FoldDst* dst,
                            bool accumulate, cudaStream_t st) {
   const int pad = k / 2, Pn = V + 2 * pad;
-  if (g_tc.mm == VXB_MATH_BF16X3 && g_tc.scratch && Cz % 64 == 0 && Cx % 64 == 0) {
+  if (g_tc.mm == VXB_MATH_F16X3 && g_tc.scratch && Cz % 64 == 0 && Cx % 64 == 0) {
     Arena local(g_tc.scratch, g_tc.scratch_bytes);
     float* scale = local.get<float>(64);
     const int rc = umma::conv_dgrad_f32(gz, Cz, wd, Cx, gxp, B, V, k, scale, local, st);

@@ -12,7 +12,7 @@ inline int linear(const float* A, int lda, const float* W, int ldw, const float*
                   const float* residual, int res_rows, int ldr, float* C, int ldc, int M, int N,
                   int K, float alpha, float act_slope, int math_mode, cudaStream_t st,
                   Arena* scratch = nullptr, const umma::Planes* Wpre = nullptr) {
-  if (math_mode == VXB_MATH_BF16X3 && scratch && M >= 128 && N >= 32 && K >= 32) {
+  if (math_mode == VXB_MATH_F16X3 && scratch && M >= 128 && N >= 32 && K >= 32) {
     Arena local(scratch->base, scratch->cap);   // every op bumps from the start of the scratch arena
     return umma::linear_f32(A, lda, W, ldw, Wpre, bias, residual, res_rows, ldr, C, ldc, M, N, K, alpha,
                             act_slope, local, st);
@@ -35,7 +35,7 @@ inline int conv3d(const float* src0, const float* src1, int C0, int C1, const fl
                   const float* bias, float* out, int B, int Di, int Do, int Co, int k, int stride,
                   float act_slope, int math_mode, cudaStream_t st, Arena* scratch = nullptr,
                   const umma::Planes* Wpre = nullptr) {
-  if (math_mode == VXB_MATH_BF16X3 && scratch && stride == 1 && Di == Do && C0 % 64 == 0 && C1 % 64 == 0 &&
+  if (math_mode == VXB_MATH_F16X3 && scratch && stride == 1 && Di == Do && C0 % 64 == 0 && C1 % 64 == 0 &&
       Co == 64) {
     Arena local(scratch->base, scratch->cap);
     umma::Planes wp;
@@ -77,7 +77,7 @@ inline int upconv3d_folded(const float* low, const float* wfold, const float* bi
                            cudaStream_t st, Arena* scratch = nullptr, const umma::Planes* Wpre = nullptr,
                            const umma::Planes* out_planes = nullptr, const float* f8a = nullptr,
                            const umma::F8cGemm* f8g = nullptr, const umma::UpconvSparsity* sp = nullptr) {
-  if (math_mode == VXB_MATH_BF16X3 && scratch && Ci % 64 == 0 && Co == 64) {
+  if (math_mode == VXB_MATH_F16X3 && scratch && Ci % 64 == 0 && Co == 64) {
     Arena local(scratch->base, scratch->cap);
     umma::Planes wp;
     const long long Kt = 27ll * Ci, Nt = (long long)s * s * s * Co;

@@ -75,7 +75,7 @@ static int make_dims(const vxb_qnet_desc* d, Dims& m) {
     set_error("qnet: the 2-robot encoder has no arm-prediction head");
     return VXB_E_UNSUPPORTED_SHAPE;
   }
-  if (d->math_mode != VXB_MATH_FP32_SIMT && d->math_mode != VXB_MATH_BF16X3 && d->math_mode != VXB_MATH_F16F8C) {
+  if (d->math_mode != VXB_MATH_FP32_SIMT && d->math_mode != VXB_MATH_F16X3 && d->math_mode != VXB_MATH_F16F8C) {
     set_error("qnet: unknown math_mode %d", d->math_mode);
     return VXB_E_BADARG;
   }
@@ -719,10 +719,10 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
                              const float* proprio2, const float* lang_tokens, int B, float* q_trans, float* q_trans2,
                              float* rot_grip, float* collision, float* rot_grip2, float* collision2, float* arm_out,
                              cudaStream_t st) {
-  // VXB_MATH_F16F8C = VXB_MATH_BF16X3 everywhere except the final 3x3x3 convolution (conv_f8c.cuh)
+  // VXB_MATH_F16F8C = VXB_MATH_F16X3 everywhere except the final 3x3x3 convolution (conv_f8c.cuh)
   const bool f8c = d->math_mode == VXB_MATH_F16F8C && m.fsrc == VXB_FINAL_CAT;   // the ablated final convs run split-16x3
-  const int mm = d->math_mode == VXB_MATH_F16F8C ? VXB_MATH_BF16X3 : d->math_mode;
-  Ctx cx(mm, st, mm == VXB_MATH_BF16X3 ? w.scratch : nullptr, w.scratch_bytes);
+  const int mm = d->math_mode == VXB_MATH_F16F8C ? VXB_MATH_F16X3 : d->math_mode;
+  Ctx cx(mm, st, mm == VXB_MATH_F16X3 ? w.scratch : nullptr, w.scratch_bytes);
   cx.wp = pw.planes;
   auto P = [&](int slot) { return (const float*)params[slot]; };
   auto PL = [&](int layer, int slot) {
@@ -734,7 +734,7 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   STAGE_MARK();  // 0: input_preprocess
   // (1) d0 = act(conv1x1(grid)), fused with (2) feats[0:256] = [ss0(d0), maxpool(d0)]   perceiver_lang_io.py:357-360
   g_launches += 2;
-  const bool fused_planes = mm == VXB_MATH_BF16X3;   // producers write the final conv's operand planes directly
+  const bool fused_planes = mm == VXB_MATH_F16X3;   // producers write the final conv's operand planes directly
   if (f8c) {
     // e4m3 scale of d0 from a bound of |d0|: per-channel maxima of the voxel grid x |weights| of the 1x1 convolution
     g_launches += 2;
@@ -753,7 +753,7 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   STAGE_MARK();  // 2: patchify
   // (3) patchify conv k, stride s, replicate pad                   :363
   COUNT_LAUNCH();
-  if (mm == VXB_MATH_BF16X3) {
+  if (mm == VXB_MATH_F16X3) {
     const umma::Planes d0p{w.d0p[0], w.d0p[1], 64};
     VXB_TRY(umma::patchify_f32(nullptr, pw.patch_wc, P(VXB_P_PATCH_B), slope, w.patch, B, m.V, m.k, m.s, st, &d0p));
   } else {
@@ -787,7 +787,7 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
 
   STAGE_MARK();  // 4: transformer (cross + latent self-attention + FF)
   // (5) latents: x = repeat(latents) is never materialised; the first residual reads latents[m % L]   :425
-  const bool planes_path = mm == VXB_MATH_BF16X3 && m.cdh == 64 && m.ldh == 64 && m.C % 8 == 0 && m.D % 32 == 0;
+  const bool planes_path = mm == VXB_MATH_F16X3 && m.cdh == 64 && m.ldh == 64 && m.C % 8 == 0 && m.D % 32 == 0;
   if (planes_path) {
     // fp16 + E4M3 for the LayerNorm-fed transformer GEMMs is built but OFF by default: measured -0.53 ms of 9.7 (B=16), but the
     // rotation / collision heads move from 1.5e-4 .. 4.7e-4 to 2.2e-4 .. 9.6e-4 of the reference goldens (tools/report_errors.py,
@@ -889,7 +889,7 @@ static int qnet_forward_impl(const vxb_qnet_desc* d, const Dims& m, const void* 
   // (11) final: conv3 on cat[d0, u0] (128 -> 64)                               :462
   COUNT_LAUNCH();
   const int off = 256 + 4 * m.C;
-  if (mm == VXB_MATH_BF16X3) {
+  if (mm == VXB_MATH_F16X3) {
     // input-stationary tcgen05 convolution on the padded hi/lo planes of d0 and u0 (no concat, no re-fetch per tap)
     // with the tail fused into its epilogue: the 27 trans_decoder tap products and the ss_final / max-pool partials
     // are formed from the accumulator rows, u itself is never written (steps 12 and 13 below)     :462-470
@@ -1041,10 +1041,10 @@ extern "C" int vxb_profile_read(double* ms) {
 }
 
 // ---- training step: forward that keeps the activations + backward
-// the training step has no f16 + fp8 convolution: VXB_MATH_F16F8C trains as VXB_MATH_BF16X3
+// the training step has no f16 + fp8 convolution: VXB_MATH_F16F8C trains as VXB_MATH_F16X3
 static vxb_qnet_desc train_desc(const vxb_qnet_desc* d) {
   vxb_qnet_desc t = *d;
-  if (t.math_mode == VXB_MATH_F16F8C) t.math_mode = VXB_MATH_BF16X3;
+  if (t.math_mode == VXB_MATH_F16F8C) t.math_mode = VXB_MATH_F16X3;
   return t;
 }
 static int train_setup(const vxb_qnet_desc* d, const vxb_train_opts* o, Dims& m, TrainDropout& drop) {

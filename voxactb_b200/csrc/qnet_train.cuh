@@ -229,7 +229,7 @@ static int qnet_forward_train_impl(const vxb_qnet_desc* d, const Dims& m, const 
                                    TrainBufs& t, const float* grid, const float* proprio, const float* lang_tokens, int B,
                                    float* q_trans, float* rot_grip, float* collision, float* arm_out,
                                    const TrainDropout& drop, cudaStream_t st) {
-  Ctx cx(d->math_mode, st, d->math_mode == VXB_MATH_BF16X3 ? w.scratch : nullptr, w.scratch_bytes);
+  Ctx cx(d->math_mode, st, d->math_mode == VXB_MATH_F16X3 ? w.scratch : nullptr, w.scratch_bytes);
   cx.wp = pw.planes;
   auto P = [&](int slot) { return (const float*)params[slot]; };
   auto PL = [&](int layer, int slot) {
@@ -261,7 +261,7 @@ static int qnet_forward_train_impl(const vxb_qnet_desc* d, const Dims& m, const 
                                                   m.T, m.C, 64);
   VXB_LAUNCH_CHECK();
   Arena tc_arena(t.tc_scratch, t.tc_scratch_bytes);
-  Arena* tcp = (mm == VXB_MATH_BF16X3 && t.tc_scratch) ? &tc_arena : nullptr;      // tensor-core attention forward
+  Arena* tcp = (mm == VXB_MATH_F16X3 && t.tc_scratch) ? &tc_arena : nullptr;      // tensor-core attention forward
   // (4) encoder cross attention block                                                              :431-432
   {
     BlockSaved& s = t.blk[0];
@@ -326,7 +326,7 @@ static int qnet_forward_train_impl(const vxb_qnet_desc* d, const Dims& m, const 
                           cx.scratch.base ? &cx.scratch : nullptr, cx.find(pw.up1_fold), nullptr, nullptr, nullptr,
                           up_sparse(m) ? &up_sp : nullptr));
   // (9) final conv on cat[d0, u0]                                                                   :462
-  if (mm == VXB_MATH_BF16X3 && cx.scratch.base) {
+  if (mm == VXB_MATH_F16X3 && cx.scratch.base) {
     // input-stationary tcgen05 convolution (conv_umma.cuh) with the fp32 store epilogue: the GEMM-engine form re-fetches its
     // operand tile per tap from L2 (23.7 ms at B=16 against 18 ms)
     Arena local(cx.scratch.base, cx.scratch.cap);
@@ -419,7 +419,7 @@ static int qnet_backward_impl(const vxb_qnet_desc* d, const Dims& m, const void*
     if (dbg && dbg[i]) VXB_CUDA(cudaMemcpyAsync(dbg[i], src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return VXB_OK;
   };
-  bwd::g_tc = bwd::TensorCtx{d->math_mode, d->math_mode == VXB_MATH_BF16X3 ? (void*)t.tc_scratch : nullptr, t.tc_scratch_bytes};
+  bwd::g_tc = bwd::TensorCtx{d->math_mode, d->math_mode == VXB_MATH_F16X3 ? (void*)t.tc_scratch : nullptr, t.tc_scratch_bytes};
   const float slope = d->act_slope;
   const int cq = m.ch * m.cdh, lq = m.lh * m.ldh;
   const long long rowsL = (long long)B * m.L;
@@ -473,7 +473,7 @@ static int qnet_backward_impl(const vxb_qnet_desc* d, const Dims& m, const void*
   if (G.at(VXB_P_FINAL_B)) VXB_TRY(bwd::colsum(t.g_u, 64, (long long)B * m.V3, 64, G.at(VXB_P_FINAL_B), false, st));
   if (G.at(VXB_P_FINAL_W)) {
     int rc = 1;
-    if (bwd::g_tc.mm == VXB_MATH_BF16X3 && bwd::g_tc.scratch) {
+    if (bwd::g_tc.mm == VXB_MATH_F16X3 && bwd::g_tc.scratch) {
       Arena local(bwd::g_tc.scratch, bwd::g_tc.scratch_bytes);
       rc = umma::conv3_wgrad_f32(w.d0, w.u0, t.g_u, t.dwt, B, m.V, local, st);
       if (rc == VXB_E_WORKSPACE_TOO_SMALL) rc = 1;

@@ -1,6 +1,6 @@
 // fp32 FFMA tiled GEMM / implicit-GEMM convolution (math_mode VXB_MATH_FP32_SIMT).
 // This is the exact-arithmetic path used for parity and for the small shapes; the big
-// contractions run on tcgen05 (umma_gemm.cuh) when math_mode == VXB_MATH_BF16X3.
+// contractions run on tcgen05 (umma_gemm.cuh) when math_mode == VXB_MATH_F16X3.
 #pragma once
 #include "common.cuh"
 

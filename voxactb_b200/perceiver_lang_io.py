@@ -137,7 +137,7 @@ class PerceiverVoxelLangEncoder(nn.Module):
 
     # arithmetic of the dense contractions: tcgen05 split-16-bit products with fp32-class accuracy.
     # MATH_F16F8C (default): three fp16 MMAs per product in the transformer, fp16 hi*hi + one E4M3 correction MMA in the two
-    # large convolutions; MATH_BF16X3: three fp16 MMAs everywhere; MATH_FP32_SIMT: fp32 FFMA everywhere (slow reference mode)
+    # large convolutions; MATH_F16X3: three fp16 MMAs everywhere; MATH_FP32_SIMT: fp32 FFMA everywhere (slow reference mode)
     math_mode = _lib.MATH_F16F8C
     TWO_ROBOTS = False     # PerceiverVoxelLang2RobotsEncoder: two proprio streams (C = 3 * im_channels), two head sets
 
