@@ -284,9 +284,157 @@ softmax_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ gA, int
 
 struct AttnDropout { float p; unsigned long long seed; };
 
+// Register-resident forms of the two row kernels above (a row of ld <= 1024 * NV floats lives in NV float4 per thread: one
+// read and one write per element instead of three / two passes over global memory with scalar accesses):
+//   softmax_rows_reg_kernel: P = softmax(x) in place and, with `dropped`, A = dropout(P) in the same pass (was a separate
+//   pass over [B*H*Nq, Nk] with a 64-bit modulo per element: 10.5 ms of a training step at B=16);
+//   softmax_bwd_rows_reg_kernel: gS = P * (gP - sum(gP * P)) * scale in place of gA, gP = gA * mask / keep.
+__device__ __forceinline__ float block_reduce_256(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();                                  // `red` may still be read from the previous reduction
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+  return r;
+}
+template <int NV>
+static __global__ void __launch_bounds__(256)
+softmax_rows_reg_kernel(float* __restrict__ x, float* __restrict__ dropped, int n, int ld, unsigned long long seed,
+                        unsigned int thresh, float inv_keep) {
+  const size_t row = blockIdx.x;
+  float4* xr = reinterpret_cast<float4*>(x + row * ld);
+  const int nv = ld >> 2;
+  __shared__ float red[8];
+  float4 v[NV];
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int q = threadIdx.x + k * 256;
+    v[k] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (q < nv) {
+      v[k] = xr[q];
+      const int c = q * 4;
+      if (c + 3 >= n) {                             // pad columns [n, ld) do not take part (exp -> 0)
+        if (c >= n) v[k].x = -INFINITY;
+        if (c + 1 >= n) v[k].y = -INFINITY;
+        if (c + 2 >= n) v[k].z = -INFINITY;
+        v[k].w = -INFINITY;
+      }
+      m = fmaxf(m, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
+    }
+  }
+  m = block_reduce_256(m, red, true);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    v[k].x = expf(v[k].x - m); v[k].y = expf(v[k].y - m); v[k].z = expf(v[k].z - m); v[k].w = expf(v[k].w - m);
+    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  }
+  s = block_reduce_256(s, red, false);
+  const float inv = 1.f / s;
+  float4* dr = dropped ? reinterpret_cast<float4*>(dropped + row * ld) : nullptr;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int q = threadIdx.x + k * 256;
+    if (q < nv) {
+      float4 p = make_float4(v[k].x * inv, v[k].y * inv, v[k].z * inv, v[k].w * inv);
+      xr[q] = p;
+      if (dr) {
+        const unsigned long long i0 = (unsigned long long)row * ld + (unsigned long long)(q * 4);
+        p.x = dropout_keep(seed, i0, thresh) ? p.x * inv_keep : 0.f;
+        p.y = dropout_keep(seed, i0 + 1, thresh) ? p.y * inv_keep : 0.f;
+        p.z = dropout_keep(seed, i0 + 2, thresh) ? p.z * inv_keep : 0.f;
+        p.w = dropout_keep(seed, i0 + 3, thresh) ? p.w * inv_keep : 0.f;
+        dr[q] = p;
+      }
+    }
+  }
+}
+template <int NV>
+static __global__ void __launch_bounds__(256)
+softmax_bwd_rows_reg_kernel(const float* __restrict__ P, float* __restrict__ gA, int n, int ld, float scale,
+                            unsigned long long seed, unsigned int thresh, float inv_keep) {
+  const size_t row = blockIdx.x;
+  const float4* pr = reinterpret_cast<const float4*>(P + row * ld);
+  float4* gr = reinterpret_cast<float4*>(gA + row * ld);
+  const int nv = ld >> 2;
+  __shared__ float red[8];
+  float4 p[NV], g[NV];
+  float d = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int q = threadIdx.x + k * 256;
+    p[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    g[k] = p[k];
+    if (q < nv) {
+      p[k] = pr[q];                                 // pad columns of P are zero (softmax_rows_*): they add nothing
+      g[k] = gr[q];
+      if (thresh) {
+        const unsigned long long i0 = (unsigned long long)row * ld + (unsigned long long)(q * 4);
+        g[k].x = dropout_keep(seed, i0, thresh) ? g[k].x * inv_keep : 0.f;
+        g[k].y = dropout_keep(seed, i0 + 1, thresh) ? g[k].y * inv_keep : 0.f;
+        g[k].z = dropout_keep(seed, i0 + 2, thresh) ? g[k].z * inv_keep : 0.f;
+        g[k].w = dropout_keep(seed, i0 + 3, thresh) ? g[k].w * inv_keep : 0.f;
+      }
+      const int c = q * 4;
+      if (c + 3 >= n) {                             // gA's pad columns hold whatever the GEMM left there
+        if (c >= n) g[k].x = 0.f;
+        if (c + 1 >= n) g[k].y = 0.f;
+        if (c + 2 >= n) g[k].z = 0.f;
+        g[k].w = 0.f;
+      }
+      d += (g[k].x * p[k].x + g[k].y * p[k].y) + (g[k].z * p[k].z + g[k].w * p[k].w);
+    }
+  }
+  d = block_reduce_256(d, red, false);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int q = threadIdx.x + k * 256;
+    if (q < nv)
+      gr[q] = make_float4(p[k].x * (g[k].x - d) * scale, p[k].y * (g[k].y - d) * scale, p[k].z * (g[k].z - d) * scale,
+                          p[k].w * (g[k].w - d) * scale);
+  }
+}
+
 // forward with materialised probabilities (dispatch.cuh attention_materialized) + train-mode dropout on them
 inline int dropout_rows(const float* P, float* out, long long rows, int n, int ld, const AttnDropout& dr, cudaStream_t st) {
   dropout_rows_kernel<<<148 * 16, 256, 0, st>>>(P, out, rows, n, ld, dr.seed, dropout_threshold(dr.p), 1.f / (1.f - dr.p));
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
+// P = softmax(P) in place (+ A = dropout(P) when dr.p > 0); rows of n valid columns, leading dimension ld (multiple of 4)
+inline int softmax_rows_dropout(float* P, float* A, long long rows, int n, int ld, const AttnDropout& dr, cudaStream_t st) {
+  const bool drop = dr.p > 0.f;
+  const unsigned int th = drop ? dropout_threshold(dr.p) : 0u;
+  const float ik = drop ? 1.f / (1.f - dr.p) : 1.f;
+  const int nv = ld / 4;
+  const bool vec = ld % 4 == 0 && (((uintptr_t)P | (uintptr_t)A) & 15) == 0;
+  if (vec && nv <= 256 * 2) softmax_rows_reg_kernel<2><<<(unsigned)rows, 256, 0, st>>>(P, drop ? A : nullptr, n, ld, dr.seed, th, ik);
+  else if (vec && nv <= 256 * 4) softmax_rows_reg_kernel<4><<<(unsigned)rows, 256, 0, st>>>(P, drop ? A : nullptr, n, ld, dr.seed, th, ik);
+  else if (vec && nv <= 256 * 8) softmax_rows_reg_kernel<8><<<(unsigned)rows, 256, 0, st>>>(P, drop ? A : nullptr, n, ld, dr.seed, th, ik);
+  else {
+    softmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(P, n, ld);
+    VXB_LAUNCH_CHECK();
+    if (drop) return dropout_rows(P, A, rows, n, ld, dr, st);
+  }
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+inline int softmax_bwd_rows(const float* P, float* gA, long long rows, int n, int ld, float scale, const AttnDropout& dr,
+                            cudaStream_t st) {
+  const bool drop = dr.p > 0.f;
+  const unsigned int th = drop ? dropout_threshold(dr.p) : 0u;
+  const float ik = drop ? 1.f / (1.f - dr.p) : 1.f;
+  const int nv = ld / 4;
+  const bool vec = ld % 4 == 0 && (((uintptr_t)P | (uintptr_t)gA) & 15) == 0;
+  if (vec && nv <= 256 * 2) softmax_bwd_rows_reg_kernel<2><<<(unsigned)rows, 256, 0, st>>>(P, gA, n, ld, scale, dr.seed, th, ik);
+  else if (vec && nv <= 256 * 4) softmax_bwd_rows_reg_kernel<4><<<(unsigned)rows, 256, 0, st>>>(P, gA, n, ld, scale, dr.seed, th, ik);
+  else if (vec && nv <= 256 * 8) softmax_bwd_rows_reg_kernel<8><<<(unsigned)rows, 256, 0, st>>>(P, gA, n, ld, scale, dr.seed, th, ik);
+  else softmax_bwd_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(P, gA, n, ld, scale, dr.seed, th, ik);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }
@@ -310,8 +458,8 @@ inline int attention_bwd(const float* q, int ldq, long long qbs, const float* k,
   p.C = bufP; p.ldc = Nkp; p.c_stride_zb = szb; p.c_stride_zh = szh;
   p.Hz = H; p.alpha = scale;
   VXB_TRY((launch_simt_gemm<A_PLAIN, B_NT, O_PLAIN>(p, B * H, st)));
-  softmax_rows_kernel<<<(unsigned)((size_t)B * H * Nq), 256, 0, st>>>(bufP, Nk, Nkp);
-  VXB_LAUNCH_CHECK();
+  const bool drop = dr.p > 0.f;
+  VXB_TRY(softmax_rows_dropout(bufP, bufA, (long long)B * H * Nq, Nk, Nkp, dr, st));   // also bufA = dropout(P)
   // (2) gA = go v^T
   gemm_params_init(p);
   p.M = Nq; p.N = Nk; p.K = dh;
@@ -321,12 +469,7 @@ inline int attention_bwd(const float* q, int ldq, long long qbs, const float* k,
   p.Hz = H;
   VXB_TRY((launch_simt_gemm<A_PLAIN, B_NT, O_PLAIN>(p, B * H, st)));
   // (3) gv = A^T go, A = dropout(P)
-  const float* A = bufP;
-  const bool drop = dr.p > 0.f;
-  if (drop) {
-    VXB_TRY(dropout_rows(bufP, bufA, (long long)B * H * Nq, Nk, Nkp, dr, st));
-    A = bufA;
-  }
+  const float* A = drop ? bufA : bufP;
   gemm_params_init(p);
   p.M = Nk; p.N = dh; p.K = Nq;
   p.A = A; p.lda = Nkp; p.a_stride_zb = szb; p.a_stride_zh = szh;
@@ -335,10 +478,7 @@ inline int attention_bwd(const float* q, int ldq, long long qbs, const float* k,
   p.Hz = H;
   VXB_TRY((launch_simt_gemm<A_TRANS, B_NN, O_PLAIN>(p, B * H, st)));
   // (4) gS in place of gA
-  softmax_bwd_rows_kernel<<<(unsigned)((size_t)B * H * Nq), 256, 0, st>>>(bufP, bufG, Nk, Nkp, scale, dr.seed,
-                                                                         drop ? dropout_threshold(dr.p) : 0u,
-                                                                         drop ? 1.f / (1.f - dr.p) : 1.f);
-  VXB_LAUNCH_CHECK();
+  VXB_TRY(softmax_bwd_rows(bufP, bufG, (long long)B * H * Nq, Nk, Nkp, scale, dr, st));
   // (5) gq = gS k
   gemm_params_init(p);
   p.M = Nq; p.N = dh; p.K = Nk;
@@ -370,8 +510,38 @@ channel_argmax_kernel(const float* __restrict__ x, const float* __restrict__ mx,
     if (x[i] == mx[(size_t)b * mx_stride + c]) atomicMin(idx + b * C + c, (int)pos);
   }
 }
+// the same for C / 4 a divisor of 256 (every shipped call: C = 64): grid (chunks, B), a thread keeps its 4 channels for the
+// whole walk, 128-bit loads, no division (the generic kernel pays two 64-bit divisions per element: 2.7 ms per 4 GB tensor)
+static __global__ void __launch_bounds__(256)
+channel_argmax_vec_kernel(const float* __restrict__ x, const float* __restrict__ mx, int mx_stride, long long P, int C,
+                          int* __restrict__ idx) {
+  const int G = C >> 2, b = blockIdx.y;
+  const int cg = threadIdx.x % G;
+  const float4 m = *reinterpret_cast<const float4*>(mx + (size_t)b * mx_stride + cg * 4);
+  const float4* xb = reinterpret_cast<const float4*>(x + (size_t)b * P * C);
+  const int ppb = 256 / G;                                       // positions per block and iteration
+  int best[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+  for (long long pos = (long long)blockIdx.x * ppb + threadIdx.x / G; pos < P; pos += (long long)gridDim.x * ppb) {
+    const float4 v = xb[pos * G + cg];
+    if (v.x == m.x) best[0] = min(best[0], (int)pos);
+    if (v.y == m.y) best[1] = min(best[1], (int)pos);
+    if (v.z == m.z) best[2] = min(best[2], (int)pos);
+    if (v.w == m.w) best[3] = min(best[3], (int)pos);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (best[j] != 0x7fffffff) atomicMin(idx + b * C + cg * 4 + j, best[j]);
+}
 inline int channel_argmax(const float* x, const float* mx, int mx_stride, int B, long long P, int C, int* idx, cudaStream_t st) {
   VXB_CUDA(cudaMemsetAsync(idx, 0x7f, (size_t)B * C * sizeof(int), st));
+  if (C % 4 == 0 && 256 % (C / 4) == 0 && mx_stride % 4 == 0 && P < (1ll << 31) &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(mx)) & 15) == 0) {
+    const int ppb = 256 / (C / 4);
+    const int bx = (int)std::max<long long>(1, std::min<long long>((P + ppb - 1) / ppb, (148 * 16 + B - 1) / B));
+    channel_argmax_vec_kernel<<<dim3(bx, B), 256, 0, st>>>(x, mx, mx_stride, P, C, idx);
+    VXB_LAUNCH_CHECK();
+    return VXB_OK;
+  }
   channel_argmax_kernel<<<148 * 16, 256, 0, st>>>(x, mx, mx_stride, B, P, C, idx);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
@@ -710,13 +880,14 @@ static __global__ void fold_upconv_weights_bwd_kernel(const float* __restrict__ 
 //   G[v][t] = sum_{o : clamp(o + t - 1) == v} g[o];   gu[v][c] (+)= sum_t w[t][c] G[v][t];   dw[t][c] += u[v][c] G[v][t]
 // 16 threads per voxel (4 channels each); dw accumulated per block in shared memory, then atomically (dw zeroed by caller).
 template <int C>
-static __global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(128, 3)       // <= 168 registers (27 x 4 weight-gradient accumulators per thread): 12 warps / SM
 trans_bwd_kernel(const float* __restrict__ g, const float* __restrict__ u, const float* __restrict__ wt /*[27][C]*/,
                  float* __restrict__ gu, int accumulate, float* __restrict__ dwt /*[27][C]*/, int B, int V) {
   constexpr int G4 = C / 4;
   static_assert(G4 == 16, "one half-warp per voxel");
   __shared__ float sdw[27 * C];
-  for (int i = threadIdx.x; i < 27 * C; i += 256) sdw[i] = 0.f;
+  __shared__ __align__(16) float swt[27 * C];     // the stencil weights: 27 LDS.128 per voxel instead of 27 L1 requests
+  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) { sdw[i] = 0.f; swt[i] = wt[i]; }
   __syncthreads();
   const long long total = (long long)B * V * V * V * G4;
   float acc[27][4];
@@ -729,19 +900,24 @@ trans_bwd_kernel(const float* __restrict__ g, const float* __restrict__ u, const
   for (long long i0 = wbase; i0 < total; i0 += (long long)gridDim.x * blockDim.x) {
     const long long i = i0 + (threadIdx.x & 31);
     const bool valid = i < total;
-    long long r = (valid ? i : 0) / G4;
-    const long long vox = r;
-    const int x = (int)(r % V); r /= V;
-    const int y = (int)(r % V); r /= V;
-    const int z = (int)(r % V);
-    const int b = (int)(r / V);
+    const long long vox = (valid ? i : 0) / G4;
+    unsigned int r = (unsigned int)vox;            // B * V^3 < 2^32 (launcher): 32-bit index arithmetic
+    const int x = (int)(r % (unsigned int)V); r /= (unsigned int)V;
+    const int y = (int)(r % (unsigned int)V); r /= (unsigned int)V;
+    const int z = (int)(r % (unsigned int)V);
+    const int b = (int)(r / (unsigned int)V);
     const float* gb = g + (size_t)b * V * V * V;
+    // interior voxels (94 % at V = 100) have exactly one source per tap: o = v - t + 1
+    const bool interior = x >= 1 && x <= V - 2 && y >= 1 && y <= V - 2 && z >= 1 && z <= V - 2;
     // the 27 gathered sums G[t] of this voxel: lane hl forms taps hl and hl + 16, the half-warp shares them by shuffle
     float gpart[2] = {0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int t = hl + 16 * k;
-      if (t < 27 && valid) {
+      if (t < 27 && valid && interior) {
+        const int dz = t / 9, dy = (t / 3) % 3, dx = t % 3;
+        gpart[k] = __ldg(gb + ((size_t)(z - dz + 1) * V + (y - dy + 1)) * V + (x - dx + 1));
+      } else if (t < 27 && valid) {
         const int dz = t / 9, dy = (t / 3) % 3, dx = t % 3;
         int zs[2], ys[2], xs[2], nz = 0, ny = 0, nx = 0;
         { const int a = z - dz + 1; if (a >= 0 && a < V) zs[nz++] = a; if (z == 0 && dz == 0) zs[nz++] = 0; if (z == V - 1 && dz == 2) zs[nz++] = V - 1; }
@@ -760,7 +936,7 @@ trans_bwd_kernel(const float* __restrict__ g, const float* __restrict__ u, const
 #pragma unroll
     for (int t = 0; t < 27; ++t) {
       const float G = __shfl_sync(0xffffffffu, gpart[t >> 4], t & 15, 16);
-      const float4 wv = *reinterpret_cast<const float4*>(wt + t * C + c);
+      const float4 wv = *reinterpret_cast<const float4*>(swt + t * C + c);
       o.x = fmaf(wv.x, G, o.x); o.y = fmaf(wv.y, G, o.y); o.z = fmaf(wv.z, G, o.z); o.w = fmaf(wv.w, G, o.w);
       acc[t][0] = fmaf(uv.x, G, acc[t][0]); acc[t][1] = fmaf(uv.y, G, acc[t][1]);
       acc[t][2] = fmaf(uv.z, G, acc[t][2]); acc[t][3] = fmaf(uv.w, G, acc[t][3]);
@@ -776,7 +952,7 @@ trans_bwd_kernel(const float* __restrict__ g, const float* __restrict__ u, const
 #pragma unroll
     for (int j = 0; j < 4; ++j) atomicAdd(&sdw[t * C + c + j], acc[t][j]);
   __syncthreads();
-  for (int i = threadIdx.x; i < 27 * C; i += 256) atomicAdd(dwt + i, sdw[i]);
+  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) atomicAdd(dwt + i, sdw[i]);
 }
 
 // replicate-padded 3x3x3 im2col of a channels-last grid: out[(b, q)][(nb, c)] = x[b, clamp(q + nb - 1), c]

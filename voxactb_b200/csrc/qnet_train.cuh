@@ -459,7 +459,11 @@ static int qnet_backward_impl(const vxb_qnet_desc* d, const Dims& m, const void*
   VXB_TRY(bwd::ss_bwd(w.u, t.statsF, w.feats + off, m.flat, t.g_feats + off, m.flat, t.g_feats + off + 192, m.flat, t.argF, t.g_u,
                       false, B, m.V, m.V, m.V, 64, st));
   VXB_CUDA(cudaMemsetAsync(t.dwt, 0, (size_t)27 * 64 * sizeof(float), st));
-  bwd::trans_bwd_kernel<64><<<148 * 4, 256, 0, st>>>(g_trans, w.u, pw.trans_wt, t.g_u, 1, t.dwt, B, m.V);
+  if ((long long)B * m.V3 >= (1ll << 32)) {
+    set_error("qnet_backward: B * V^3 = %lld voxels exceed the 32-bit voxel index of the trans_decoder adjoint", (long long)B * m.V3);
+    return VXB_E_UNSUPPORTED_SHAPE;
+  }
+  bwd::trans_bwd_kernel<64><<<148 * 3, 128, 0, st>>>(g_trans, w.u, pw.trans_wt, t.g_u, 1, t.dwt, B, m.V);
   VXB_LAUNCH_CHECK();
   if (G.at(VXB_P_TRANS_W)) {
     bwd::wgrad_to_torch_kernel<<<8, 256, 0, st>>>(t.dwt, G.at(VXB_P_TRANS_W), 1, 64, 27);

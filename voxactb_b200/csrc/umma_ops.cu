@@ -1023,12 +1023,33 @@ int attention_f32(const float* q, int ldq, long long qbs, const float* k, const 
 
 // ------------------------------------------------------------------------------------------ backward contractions
 // max |x| of a strided matrix -> power-of-two scale that puts it near 2^12 (fp16 planes: max 65504, normals from 6e-5)
+// (contiguous and 16-byte aligned: 128-bit loads, no index arithmetic; strided views: a warp per row -- the first version
+// paid a 64-bit division and modulo per element, 18 ms of a training step over 82 launches)
 static __global__ void __launch_bounds__(256)
 amax_kernel(const float* __restrict__ x, long long ld, long long rows, int cols, unsigned int* __restrict__ out) {
-  const long long total = rows * cols;
   float m = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(x[(i / cols) * ld + (i % cols)]));
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+  if (ld == cols && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const long long total = rows * cols, n4 = total >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    long long i = tid;
+    for (; i + nthr < n4; i += 2 * nthr) {          // two independent loads in flight
+      const float4 a = x4[i], b = x4[i + nthr];
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+    }
+    for (; i < n4; i += nthr) {
+      const float4 a = x4[i];
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+    }
+    for (long long j = (n4 << 2) + tid; j < total; j += nthr) m = fmaxf(m, fabsf(x[j]));
+  } else {
+    const int lane = threadIdx.x & 31;
+    for (long long r = tid >> 5; r < rows; r += nthr >> 5) {
+      const float* xr = x + r * ld;
+      for (int c = lane; c < cols; c += 32) m = fmaxf(m, fabsf(xr[c]));
+    }
+  }
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));     // non-negative floats order like their bit patterns
 }
@@ -1073,26 +1094,32 @@ split_rows_scaled_kernel(const float* __restrict__ x, long long ldx, long long r
     *reinterpret_cast<uint4*>(lo + r * ldp + c) = l;
   }
 }
-// fp32 x stored [R, Cc] (ldx) * scale -> TRANSPOSED planes [Cc, ldp] (ldp >= R); 32 x 32 tiles through shared memory
+// fp32 x stored [R, Cc] (ldx) * scale -> TRANSPOSED planes [Cc, ldp] (ldp >= R, ldp % 8 == 0); 64 x 64 tiles through shared
+// memory: 256-byte row reads, and a thread packs 8 consecutive output columns into one 128-bit store per plane (the first
+// version moved 32 x 32 tiles with 2-byte stores: 11.5 ms of a training step over 114 launches)
 static __global__ void __launch_bounds__(256)
 split_transpose_scaled_kernel(const float* __restrict__ x, long long ldx, int R, int Cc, const float* __restrict__ scale,
                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldp) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][65];
   const float sc = *scale;
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int j = ty; j < 32; j += 8) {
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  for (int j = ty; j < 64; j += 4) {
     const int r = r0 + j, c = c0 + tx;
     tile[j][tx] = (r < R && c < Cc) ? x[(long long)r * ldx + c] * sc : 0.f;
   }
   __syncthreads();
-  for (int j = ty; j < 32; j += 8) {
-    const int c = c0 + j, r = r0 + tx;              // output row c, column r
+  for (int id = threadIdx.x; id < 64 * 8; id += 256) {
+    const int g = id & 7, j = id >> 3;
+    const int c = c0 + j, r = r0 + g * 8;           // output row c, columns r .. r + 7
     if (c < Cc && r < ldp) {
-      const float f = r < R ? tile[tx][j] : 0.f;
-      const __nv_bfloat16 h = pl_from_float(f);
-      hi[(long long)c * ldp + r] = h;
-      lo[(long long)c * ldp + r] = pl_from_float(f - pl_to_float(h));
+      float f[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) f[t] = (r + t < R) ? tile[g * 8 + t][j] : 0.f;
+      uint4 h, l;
+      split8(f, h, l);
+      *reinterpret_cast<uint4*>(hi + (long long)c * ldp + r) = h;
+      *reinterpret_cast<uint4*>(lo + (long long)c * ldp + r) = l;
     }
   }
 }
@@ -1142,7 +1169,7 @@ int gemm_any_f32(const float* A, long long lda, bool a_trans, const float* W, lo
       split_rows_scaled_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(X, ldx, rows, K, scale, P.hi,
                                                                                                         P.lo, P.ld);
     } else {
-      split_transpose_scaled_kernel<<<dim3(cdiv(rows, 32), cdiv(P.ld, 32)), 256, 0, st>>>(X, ldx, K, rows, scale, P.hi, P.lo, P.ld);
+      split_transpose_scaled_kernel<<<dim3(cdiv(rows, 64), cdiv(P.ld, 64)), 256, 0, st>>>(X, ldx, K, rows, scale, P.hi, P.lo, P.ld);
     }
     VXB_LAUNCH_CHECK();
     return VXB_OK;
@@ -1201,15 +1228,18 @@ pad_transpose_split_kernel(const float* __restrict__ x, int B, int V, int Vx, in
     tile[j][c] = s >= 0 ? x[s * 64 + c] * sc : 0.f;
   }
   __syncthreads();
-  // K-blocked output [K / 64][ctot channels][64]: this block of 64 K positions, channels choff .. choff + 63
-  const int rr = threadIdx.x & 63;
-  for (int ch = rl; ch < 64; ch += 4) {
-    const long long r = r0 + rr;
-    const float f = r < rows ? tile[rr][ch] : 0.f;
-    const __nv_bfloat16 h = pl_from_float(f);
-    const long long o = ((long long)blockIdx.x * ctot + choff + ch) * 64 + rr;
-    hi[o] = h;
-    lo[o] = pl_from_float(f - pl_to_float(h));
+  // K-blocked output [K / 64][ctot channels][64]: this block of 64 K positions, channels choff .. choff + 63; a thread packs
+  // 8 consecutive K positions of one channel into one 128-bit store per plane (the first version stored element by element)
+  for (int id = threadIdx.x; id < 64 * 8; id += 256) {
+    const int g = id & 7, ch = id >> 3;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (r0 + g * 8 + j < rows) ? tile[g * 8 + j][ch] : 0.f;
+    uint4 h, l;
+    split8(f, h, l);
+    const long long o = ((long long)blockIdx.x * ctot + choff + ch) * 64 + g * 8;
+    *reinterpret_cast<uint4*>(hi + o) = h;
+    *reinterpret_cast<uint4*>(lo + o) = l;
   }
 }
 // dwt[(tap, ci)][co] = inv * sum_split partial[tap][split][ci][co]
