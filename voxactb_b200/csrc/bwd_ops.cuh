@@ -450,7 +450,17 @@ inline int attention_bwd(const float* q, int ldq, long long qbs, const float* k,
   const int Nkp = (Nk + 3) / 4 * 4;
   const long long szb = (long long)H * Nq * Nkp, szh = (long long)Nq * Nkp;
   GemmParams p;
+  // the two K = dh products (P logits, gA) on the tensor cores when the step runs in VXB_MATH_F16X3; 1 = run the FFMA form
+  auto scores_tc = [&](const float* a, int lda, long long abs_, const float* w, float* out, float alpha, bool dyn) -> int {
+    if (g_tc.mm != VXB_MATH_F16X3 || !g_tc.scratch) return 1;
+    Arena local(g_tc.scratch, g_tc.scratch_bytes);
+    const int rc = umma::attn_scores_f32(a, lda, abs_, w, ldkv, kvbs, out, Nkp, B, H, Nq, Nk, dh, alpha, dyn, local, st);
+    return (rc == VXB_E_WORKSPACE_TOO_SMALL || rc == VXB_E_UNSUPPORTED_SHAPE) ? 1 : rc;
+  };
   // (1) P = softmax(scale q k^T)
+  int rc = scores_tc(q, ldq, qbs, k, bufP, scale, false);
+  if (rc < 0) return rc;
+  if (rc == 1) {
   gemm_params_init(p);
   p.M = Nq; p.N = Nk; p.K = dh;
   p.A = q; p.lda = ldq; p.a_stride_zb = qbs; p.a_stride_zh = dh;
@@ -458,9 +468,13 @@ inline int attention_bwd(const float* q, int ldq, long long qbs, const float* k,
   p.C = bufP; p.ldc = Nkp; p.c_stride_zb = szb; p.c_stride_zh = szh;
   p.Hz = H; p.alpha = scale;
   VXB_TRY((launch_simt_gemm<A_PLAIN, B_NT, O_PLAIN>(p, B * H, st)));
+  }
   const bool drop = dr.p > 0.f;
   VXB_TRY(softmax_rows_dropout(bufP, bufA, (long long)B * H * Nq, Nk, Nkp, dr, st));   // also bufA = dropout(P)
   // (2) gA = go v^T
+  rc = scores_tc(go, ldo, obs, v, bufG, 1.f, true);
+  if (rc < 0) return rc;
+  if (rc == 1) {
   gemm_params_init(p);
   p.M = Nq; p.N = Nk; p.K = dh;
   p.A = go; p.lda = ldo; p.a_stride_zb = obs; p.a_stride_zh = dh;
@@ -468,6 +482,7 @@ inline int attention_bwd(const float* q, int ldq, long long qbs, const float* k,
   p.C = bufG; p.ldc = Nkp; p.c_stride_zb = szb; p.c_stride_zh = szh;
   p.Hz = H;
   VXB_TRY((launch_simt_gemm<A_PLAIN, B_NT, O_PLAIN>(p, B * H, st)));
+  }
   // (3) gv = A^T go, A = dropout(P)
   const float* A = drop ? bufA : bufP;
   gemm_params_init(p);

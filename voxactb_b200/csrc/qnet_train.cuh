@@ -65,6 +65,10 @@ static size_t train_tc_scratch_bytes(const Dims& m, int B) {
   sb = std::max(sb, umma::attention_f32_scratch_bytes(B, m.lh, m.L, m.L, m.ldh));
   sb = std::max(sb, umma::attention_f32_scratch_bytes(B, m.ch, m.L, m.n, m.cdh));
   sb = std::max(sb, umma::attention_f32_scratch_bytes(B, m.ch, m.T, m.L, m.cdh));
+  // backward: operand planes of the two K = dim_head products of every attention (P logits, gA)
+  sb = std::max(sb, umma::attn_scores_scratch_bytes(B, m.lh, m.L, m.L, m.ldh));
+  sb = std::max(sb, umma::attn_scores_scratch_bytes(B, m.ch, m.L, m.n, m.cdh));
+  sb = std::max(sb, umma::attn_scores_scratch_bytes(B, m.ch, m.T, m.L, m.cdh));
   return sb + 8192;
 }
 

@@ -157,6 +157,11 @@ int upconv_f8c_prepare(const float* wfold, long long rows, long long cols, Plane
 int gemm_any_f32(const float* A, long long lda, bool a_trans, const float* W, long long ldw, bool w_trans, float* C, int ldc,
                  int M, int N, int K, bool accumulate, Arena& scratch, cudaStream_t st, bool w_dynamic_scale = false);
 size_t gemm_any_scratch_bytes(int M, int N, int K, bool accumulate);
+// Batched K = dim_head products of the attention backward: out[b, h] = alpha * A_bh W_bh^T (fp32 [B, H, Nq, ldc]); A scaled
+// per tensor when a_dynamic (a gradient).  VXB_E_UNSUPPORTED_SHAPE / VXB_E_WORKSPACE_TOO_SMALL: the caller runs its FFMA form.
+size_t attn_scores_scratch_bytes(int B, int H, int Nq, int Nk, int dh);
+int attn_scores_f32(const float* A, int lda, long long abs_, const float* W, int ldw, long long wbs, float* out, long long ldc,
+                    int B, int H, int Nq, int Nk, int dh, float alpha, bool a_dynamic, Arena& scratch, cudaStream_t st);
 // Weight gradient of the 3x3x3 convolution on cat[x0, x1] (64 channels each, fp32 compact [B, V^3, 64]) given the
 // pre-activation gradient gz [B, V^3, 64]:  dwt[(tap, ci)][co] = sum_rows xpad[row + shift(tap)][ci] gz[row][co]
 // (tap-major, the layout bwd::wgrad_to_torch_kernel converts).  Runs as 27 split-K GEMMs on channel-major (transposed)
