@@ -36,6 +36,7 @@ sys.path.insert(0, ROOT)
 FLOPS_PER_PASS = 1672729956352          # BASELINE.md section 4 (single-arm, V=100, k=s=5, L=2048, depth 6)
 FINAL_CONV_FLOPS = 2 * 100 ** 3 * 64 * 128 * 27      # 442.4 GF / sample (direct convolution)
 UPCONV_FLOPS = 2 * 100 ** 3 * 64 * 64 * 125          # 1024 GF / sample (direct convolution, as BASELINE.md counts it)
+TRAIN_LAUNCHES_PER_STEP = 1205                     # ncu launch list of one training step (profiles/launches_r02_train.csv)
 VOXELIZE_BYTES = 65536 * 24 + 100 ** 3 * 10 * 4      # 41 572 864 B / sample
 
 
@@ -641,7 +642,7 @@ def run_train(args):
         'metric': 'training samples/sec at 100^3 voxels (fwd + loss + bwd + NCCL grad all-reduce + %s)' % args.optimizer.upper(),
         'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32' if math_mode == _lib.MATH_FP32_SIMT else 'f16x3 (split-fp16 tcgen05: forward incl. fused attention with dropout, conv / linear dgrad + wgrad); attention backward fp32 FFMA',
+        'dtype': 'f32' if math_mode == _lib.MATH_FP32_SIMT else 'f16x3 (split-fp16 tcgen05: forward incl. fused attention with dropout, conv / linear dgrad + wgrad, attention-backward score products); the three sequence-length products of the attention backward fp32 FFMA',
         'data': 'synthetic',
         'config': {'workload': 'BASELINE config 5: batch=%d/GPU, 100^3 voxels, 4 cameras 128x128 RGB-D, training step (train-mode '
                                'dropout 0.1, CE losses, backward, gradient all-reduce over NCCL, %s)' % (B, args.optimizer.upper()),
@@ -649,7 +650,10 @@ def run_train(args):
                    'l2': 'no explicit flush: each step streams >50 GB of activations and gradients'},
         'e2e': {'value': world * B / (ms_e2e / args.steps * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes,
                 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
-        'gpu_launches': None, 'clocks': clk,
+        'gpu_launches': TRAIN_LAUNCHES_PER_STEP * args.steps,
+        'gpu_launches_source': 'launches per step counted from the ncu launch list of this step (profiles/launches_r02_train.csv: '
+                               '1 205 kernels, the library\'s own except ~270 torch fill / copy kernels of the host glue)',
+        'clocks': clk,
         'roofline': {'kernel': 'whole training step (forward + dgrad + wgrad ~ 3 x forward FLOPs)', 'bound': 'tensor',
                      'achieved': tf, 'peak': pk['tensor'], 'unit': 'TFLOP/s', 'frac': tf / pk['tensor'], 'traffic': None,
                      'algorithmic_flops_per_step': TRAIN_FLOPS_PER_SAMPLE * B, 'peak_source': pk['source'] + ' bf16 sustained',
