@@ -1124,18 +1124,33 @@ split_transpose_scaled_kernel(const float* __restrict__ x, long long ldx, int R,
   }
 }
 // C[m, n] = (accumulate ? C : 0) + tmp[m, n] / (sa * sw)   (tmp == C allowed when not accumulating)
+// (nsplit > 1: tmp holds split-K partials [nsplit][M][ldt], summed here)
 static __global__ void __launch_bounds__(256)
 unscale_kernel(float* __restrict__ C, int ldc, const float* __restrict__ tmp, int ldt, long long M, int N,
-               const float* __restrict__ sa, const float* __restrict__ sw, int accumulate) {
+               const float* __restrict__ sa, const float* __restrict__ sw, int accumulate, int nsplit, long long split_stride) {
   const float inv = 1.f / (*sa * *sw);
   const long long total = M * N;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long m = i / N;
     const int n = (int)(i % N);
-    const float v = tmp[m * ldt + n] * inv;
+    float acc = tmp[m * ldt + n];
+    for (int sp = 1; sp < nsplit; ++sp) acc += tmp[sp * split_stride + m * ldt + n];
+    const float v = acc * inv;
     float* d = C + m * ldc + n;
     *d = accumulate ? *d + v : v;
   }
+}
+// Split-K for the weight-gradient shapes (M x N = a weight matrix, K = every token of the batch): dW of a 512 x 512 projection
+// is 8 tiles of 128 x 256 over K = 32 768 -- one wave on 8 of 148 SMs, ~1 ms whatever the matrix; with the K range cut into
+// `splits` batch entries (the engine's per-batch K offsets) the launch fills the chip and the partials are summed by unscale_kernel
+static int pick_gemm_ksplits(int M, int N, int nt, int K) {
+  const long long tiles = (long long)cdiv(M, BM) * cdiv(N, nt);
+  const int nkb = cdiv(K, BK);
+  if (tiles * 2 > 148 || nkb < 32) return 1;
+  const long long s = std::min<long long>(std::min<long long>(148 / tiles, nkb / 8), 32);
+  if (s <= 1) return 1;
+  const int kc = cdiv(nkb, (int)s);
+  return cdiv(nkb, kc);
 }
 
 size_t gemm_any_scratch_bytes(int M, int N, int K, bool accumulate) {
@@ -1144,6 +1159,8 @@ size_t gemm_any_scratch_bytes(int M, int N, int K, bool accumulate) {
   alloc_planes(a, N, pad8(K));
   a.get<float>(64);
   if (accumulate) a.get<float>((size_t)M * N);
+  const int ns = pick_gemm_ksplits(M, N, pick_ntile(N), K);
+  if (ns > 1) a.get<float>((size_t)ns * M * N);
   return a.off;
 }
 
@@ -1208,6 +1225,12 @@ int gemm_any_f32(const float* A, long long lda, bool a_trans, const float* W, lo
   float* sc = scratch.get<float>(64);           // [0] sa, [1] sw, [2..3] amax temporaries
   float* tmp = accumulate ? scratch.get<float>((size_t)M * N) : C;
   if (!scratch.ok) return VXB_E_WORKSPACE_TOO_SMALL;
+  int nsplit = pick_gemm_ksplits(M, N, pick_ntile(N), K);
+  float* part = nullptr;
+  if (nsplit > 1) {
+    if (scratch.off + align_up((size_t)nsplit * M * N * sizeof(float), 256) <= scratch.cap) part = scratch.get<float>((size_t)nsplit * M * N);
+    else nsplit = 1;                                // short scratch: one K range, as before
+  }
   auto split_op = [&](const float* X, long long ldx, bool trans, int rows /*M or N*/, Planes P, float* scale, unsigned int* amax,
                       bool dynamic) -> int {
     // stored extent: [rows, K] (plain) or [K, rows] (transposed)
@@ -1236,11 +1259,23 @@ int gemm_any_f32(const float* A, long long lda, bool a_trans, const float* W, lo
   p.plan.num_kb = cdiv(K, BK);
   p.ep.M = M; p.ep.N = N; p.ep.row_mode = ROWS_PLAIN;
   p.ep.out_f32 = tmp; p.ep.ldc = accumulate ? N : ldc;
+  if (nsplit > 1) {
+    const int kc = cdiv(p.plan.num_kb, nsplit);     // K blocks per split; the last split's excess columns read as zero (TMA)
+    p.plan.num_kb = kc;
+    p.batches = nsplit; p.Hz = nsplit;
+    p.a_col_zh = kc * BK; p.w_col_zh = kc * BK;
+    p.ep.out_f32 = part; p.ep.ldc = N;
+    p.c_zh = (long long)M * N;
+  }
   Operand a{Ap, M, K}, w{Wp, N, K};
   VXB_TRY(gemm(a, nullptr, w, nt, p, st));
   const long long total = (long long)M * N;
+  if (nsplit > 1)
+    unscale_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(C, ldc, part, N, M, N, sc, sc + 1,
+                                                                                           accumulate ? 1 : 0, nsplit, (long long)M * N);
+  else
   unscale_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(C, ldc, tmp, accumulate ? N : ldc, M, N, sc,
-                                                                                         sc + 1, accumulate ? 1 : 0);
+                                                                                         sc + 1, accumulate ? 1 : 0, 1, 0);
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }
