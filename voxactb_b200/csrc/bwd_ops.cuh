@@ -63,11 +63,93 @@ inline int pick_ksplit(int M, int N, int K) {
   want = std::min<long long>(want, K / 1024);
   return (int)std::max<long long>(1, want);
 }
+// C[m][n] (+)= sum_k At[k][m] W[k][n] for M = 64 and N <= NX <= 16 over a very tall K: the weight gradient of the 1 x 1
+// input_preprocess convolution (64 x 10 over B V^3 = 16 M voxels).  A 128 x 64 GEMM tile computes 12 x more products than the
+// 64 x 10 result needs (6 ms as a split-K FFMA GEMM); here a warp streams rows (256-byte gradient row: two channels per lane,
+// the N inputs broadcast), 2 NX accumulators per lane, one shared-memory + one global atomic reduction per block: HBM-bound.
+template <int NX>
+static __global__ void __launch_bounds__(256)
+wgrad_tall64_kernel(const float* __restrict__ At, int lda, const float* __restrict__ W, int ldw, int n_valid, long long K,
+                    float* __restrict__ C, int ldc, const float* __restrict__ y, float slope, float* __restrict__ db) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc0[NX], acc1[NX], b0 = 0.f, b1 = 0.f;
+#pragma unroll
+  for (int n = 0; n < NX; ++n) acc0[n] = acc1[n] = 0.f;
+  // optional fused LeakyReLU adjoint: the gradient row is taken through y > 0 ? g : slope * g on the way in (y = the layer's
+  // output, same [K, lda] layout), so the in-place lrelu pass and the bias column sum over the 4 GB tensor are not needed
+  auto grow = [&](long long k) -> float2 {
+    float2 g = *reinterpret_cast<const float2*>(At + k * lda + lane * 2);
+    if (y) {
+      const float2 yv = *reinterpret_cast<const float2*>(y + k * lda + lane * 2);
+      g.x = yv.x > 0.f ? g.x : g.x * slope;
+      g.y = yv.y > 0.f ? g.y : g.y * slope;
+    }
+    return g;
+  };
+  const long long nw = (long long)gridDim.x * 8;
+  long long k = (long long)blockIdx.x * 8 + warp;
+  for (; k + nw < K; k += 2 * nw) {                 // two rows in flight
+    const float2 ga = grow(k), gb = grow(k + nw);
+    const float* xa = W + k * ldw;
+    const float* xb = W + (k + nw) * ldw;
+    b0 += ga.x + gb.x; b1 += ga.y + gb.y;
+#pragma unroll
+    for (int n = 0; n < NX; ++n) {
+      const float va = n < n_valid ? __ldg(xa + n) : 0.f, vb = n < n_valid ? __ldg(xb + n) : 0.f;
+      acc0[n] = fmaf(ga.x, va, acc0[n]); acc1[n] = fmaf(ga.y, va, acc1[n]);
+      acc0[n] = fmaf(gb.x, vb, acc0[n]); acc1[n] = fmaf(gb.y, vb, acc1[n]);
+    }
+  }
+  for (; k < K; k += nw) {
+    const float2 ga = grow(k);
+    const float* xa = W + k * ldw;
+    b0 += ga.x; b1 += ga.y;
+#pragma unroll
+    for (int n = 0; n < NX; ++n) {
+      const float va = n < n_valid ? __ldg(xa + n) : 0.f;
+      acc0[n] = fmaf(ga.x, va, acc0[n]); acc1[n] = fmaf(ga.y, va, acc1[n]);
+    }
+  }
+  __shared__ float red[64 * NX + 64];
+  for (int i = threadIdx.x; i < 64 * NX + 64; i += 256) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int n = 0; n < NX; ++n) {
+    atomicAdd(&red[(lane * 2) * NX + n], acc0[n]);
+    atomicAdd(&red[(lane * 2 + 1) * NX + n], acc1[n]);
+  }
+  atomicAdd(&red[64 * NX + lane * 2], b0);
+  atomicAdd(&red[64 * NX + lane * 2 + 1], b1);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * NX; i += 256) {
+    const int m = i / NX, n = i - m * NX;
+    if (n < n_valid) atomicAdd(C + (size_t)m * ldc + n, red[i]);
+  }
+  if (db && threadIdx.x < 64) atomicAdd(db + threadIdx.x, red[64 * NX + threadIdx.x]);
+}
+inline bool wgrad_tall64_ok(const float* At, int lda, int M, int N, int K) {
+  return M == 64 && N >= 1 && N <= 16 && K >= 8192 && (lda & 1) == 0 && (reinterpret_cast<uintptr_t>(At) & 7) == 0;
+}
+// y / slope: optional fused LeakyReLU adjoint of the gradient rows (y == nullptr: At is used as it is); db: optional bias gradient
+inline int wgrad_tall64(const float* At, int lda, const float* W, int ldw, float* C, int ldc, int N, long long K, bool accumulate,
+                        cudaStream_t st, const float* y = nullptr, float slope = 1.f, float* db = nullptr) {
+  if (!accumulate) VXB_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), 64, st));
+  if (db) VXB_CUDA(cudaMemsetAsync(db, 0, 64 * sizeof(float), st));
+  const int grid = 148 * 8;
+  if (N <= 4) wgrad_tall64_kernel<4><<<grid, 256, 0, st>>>(At, lda, W, ldw, N, K, C, ldc, y, slope, db);
+  else if (N <= 8) wgrad_tall64_kernel<8><<<grid, 256, 0, st>>>(At, lda, W, ldw, N, K, C, ldc, y, slope, db);
+  else if (N <= 12) wgrad_tall64_kernel<12><<<grid, 256, 0, st>>>(At, lda, W, ldw, N, K, C, ldc, y, slope, db);
+  else wgrad_tall64_kernel<16><<<grid, 256, 0, st>>>(At, lda, W, ldw, N, K, C, ldc, y, slope, db);
+  VXB_LAUNCH_CHECK();
+  return VXB_OK;
+}
+
 // C[M,N] (+)= At[K,M]^T W[K,N]          (wgrad of a linear: dW = dY^T X); C contiguous (ldc == N) when split-K is used
 inline int gemm_tn(const float* At, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
                    bool accumulate, cudaStream_t st) {
   const int rc = try_tensor_gemm(At, lda, true, W, ldw, true, C, ldc, M, N, K, accumulate, st);
   if (rc <= 0) return rc;
+  if (wgrad_tall64_ok(At, lda, M, N, K)) return wgrad_tall64(At, lda, W, ldw, C, ldc, N, K, accumulate, st);
   GemmParams p;
   gemm_params_init(p);
   p.M = M; p.N = N; p.K = K;

@@ -388,6 +388,10 @@ struct Grads {
 // y = act(x W^T + b): given gy (overwritten by the pre-activation gradient), returns dW, db and optionally gx (=|+=)
 static int linear_bwd(float* gy, const float* y_or_null, float slope, const float* x, int ldx, const float* W, int ldw,
                       float* dW, float* db, float* gx, int ldgx, bool gx_accumulate, long long M, int N, int K, cudaStream_t st) {
+  // last layer of the chain (no input gradient wanted), 64 outputs, a handful of inputs, millions of rows -- input_preprocess:
+  // one streaming kernel forms dW and db with the LeakyReLU adjoint applied on the way in (gy is left untouched)
+  if (dW && !gx && M < (1ll << 31) && bwd::wgrad_tall64_ok(gy, N, N, K, (int)M) && (!y_or_null || (reinterpret_cast<uintptr_t>(y_or_null) & 7) == 0))
+    return bwd::wgrad_tall64(gy, N, x, ldx, dW, K, K, M, false, st, (y_or_null && slope >= 0.f) ? y_or_null : nullptr, slope, db);
   if (y_or_null) VXB_TRY(bwd::lrelu_bwd(gy, y_or_null, M * N, slope, st));
   if (dW) VXB_TRY(bwd::gemm_tn(gy, N, x, ldx, dW, K, N, K, (int)M, false, st));
   if (db) VXB_TRY(bwd::colsum(gy, N, M, N, db, false, st));
