@@ -1165,6 +1165,7 @@ size_t gemm_any_scratch_bytes(int M, int N, int K, bool accumulate) {
 }
 
 static __global__ void set_one_kernel(float* p) { *p = 1.f; }
+static __global__ void inv_prod_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out) { *out = 1.f / (*a * *b); }
 
 // ---- the two K = dim_head contractions of the attention backward (bwd_ops.cuh attention_bwd): for every (batch, head)
 //   out[b, h] (fp32 [Nq, ldc]) = alpha * A[b, :, h dh : (h+1) dh] W[b, :, h dh : (h+1) dh]^T
@@ -1267,15 +1268,21 @@ int gemm_any_f32(const float* A, long long lda, bool a_trans, const float* W, lo
     p.ep.out_f32 = part; p.ep.ldc = N;
     p.c_zh = (long long)M * N;
   }
+  else {
+    // one K range: the epilogue un-scales by the device scalar 1 / (sa sw) and, when accumulating, adds C in place (each
+    // element is read and written by the same thread) -- no separate pass over the output
+    inv_prod_kernel<<<1, 1, 0, st>>>(sc, sc + 1, sc + 4);
+    p.ep.alpha_dev = sc + 4;
+    p.ep.out_f32 = C; p.ep.ldc = ldc;
+    if (accumulate) { p.ep.residual = C; p.ep.res_rows = M; p.ep.ldr = ldc; }
+  }
   Operand a{Ap, M, K}, w{Wp, N, K};
   VXB_TRY(gemm(a, nullptr, w, nt, p, st));
-  const long long total = (long long)M * N;
-  if (nsplit > 1)
+  if (nsplit > 1) {
+    const long long total = (long long)M * N;
     unscale_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(C, ldc, part, N, M, N, sc, sc + 1,
                                                                                            accumulate ? 1 : 0, nsplit, (long long)M * N);
-  else
-  unscale_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(C, ldc, tmp, accumulate ? N : ldc, M, N, sc,
-                                                                                         sc + 1, accumulate ? 1 : 0, 1, 0);
+  }
   VXB_LAUNCH_CHECK();
   return VXB_OK;
 }
@@ -1325,6 +1332,52 @@ pad_transpose_split_kernel(const float* __restrict__ x, int B, int V, int Vx, in
     uint4 h, l;
     split8(f, h, l);
     const long long o = ((long long)blockIdx.x * ctot + choff + ch) * 64 + g * 8;
+    *reinterpret_cast<uint4*>(hi + o) = h;
+    *reinterpret_cast<uint4*>(lo + o) = l;
+  }
+}
+// The three x-shifted copies of the zero-padded gradient (dxs = -1, 0, +1 into channel blocks 0, 64, 128 of a 192-channel
+// K-blocked plane pair) from ONE read of gz: copy dxs at flat row r is the base copy at row r - dxs (rows that would cross an
+// x-row boundary land on halo columns of the base copy, which are zero), so a block loads rows r0 - 1 .. r0 + 64 once and
+// writes three 64-row slices (three launches of pad_transpose_split_kernel read the 4 GB gradient three times).
+static __global__ void __launch_bounds__(256)
+pad_transpose_split3_kernel(const float* __restrict__ x, int B, int V, int Vx, const float* __restrict__ scale,
+                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ctot, long long rows) {
+  __shared__ float tile[66][65];
+  __shared__ long long src[66];
+  const float sc = *scale;
+  const int Vp = V + 2;
+  const long long r0 = (long long)blockIdx.x * 64;
+  if (threadIdx.x < 66) {
+    const long long r = r0 - 1 + threadIdx.x;
+    long long s = -1;
+    if (r >= 0 && r < rows) {
+      long long v = r;
+      const int pw = (int)(v % Vx); v /= Vx;
+      const int ph = (int)(v % Vp); v /= Vp;
+      const int pd = (int)(v % Vp);
+      const int b = (int)(v / Vp);
+      if (pd >= 1 && pd <= V && ph >= 1 && ph <= V && pw >= 1 && pw <= V && b < B)
+        s = (((long long)b * V + (pd - 1)) * V + (ph - 1)) * V + (pw - 1);
+    }
+    src[threadIdx.x] = s;
+  }
+  __syncthreads();
+  const int c = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  for (int j = rl; j < 66; j += 4) {
+    const long long s = src[j];
+    tile[j][c] = s >= 0 ? x[s * 64 + c] * sc : 0.f;
+  }
+  __syncthreads();
+  for (int id = threadIdx.x; id < 3 * 64 * 8; id += 256) {
+    const int copy = id >> 9, rem = id & 511;       // copy i holds dxs = i - 1: out[rr] = base[rr - dxs] = tile[rr + 2 - i]
+    const int g = rem & 7, ch = rem >> 3;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (r0 + g * 8 + j < rows) ? tile[g * 8 + j + 2 - copy][ch] : 0.f;
+    uint4 h, l;
+    split8(f, h, l);
+    const long long o = ((long long)blockIdx.x * ctot + copy * 64 + ch) * 64 + g * 8;
     *reinterpret_cast<uint4*>(hi + o) = h;
     *reinterpret_cast<uint4*>(lo + o) = l;
   }
@@ -1389,8 +1442,7 @@ int conv3_wgrad_f32(const float* x0, const float* x1, const float* gz, float* dw
   pad_transpose_split_kernel<<<tb, 256, 0, st>>>(x0, B, V, (int)Vx, 0, 1, sc, xt.hi, xt.lo, 128, 0, rows);
   pad_transpose_split_kernel<<<tb, 256, 0, st>>>(x1, B, V, (int)Vx, 0, 1, sc, xt.hi, xt.lo, 128, 64, rows);
   // sum_r X[r + S + dx] G[r] = sum_r' X[r' + S] G[r' - dx]: the copy for tap dx holds the gradient moved by +dx
-  for (int i = 0; i < 3; ++i)
-    pad_transpose_split_kernel<<<tb, 256, 0, st>>>(gz, B, V, (int)Vx, i - 1, 0, sc + 1, gall.hi, gall.lo, 192, i * 64, rows);
+  pad_transpose_split3_kernel<<<tb, 256, 0, st>>>(gz, B, V, (int)Vx, sc + 1, gall.hi, gall.lo, 192, rows);
   VXB_LAUNCH_CHECK();
   const long long Kc = (rows + kWgradSplits - 1) / kWgradSplits;
   const long long Kcb = (Kc + BK - 1) / BK * BK;
